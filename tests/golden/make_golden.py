@@ -1,0 +1,195 @@
+#!/usr/bin/env python
+"""Generate the golden vectors that pin oracle/ (and, through it, the CUDA path) to the live reference.
+
+Runs ONLY in the build container: it imports the reference scripts by path from /root/reference
+(never copied) and writes small JSON / npz fixtures next to this file.
+
+    PYTHONHASHSEED=0 python tests/golden/make_golden.py [case ...]
+
+Outputs
+  core_<case>.json     per-window records of NN_degenerate.get_primers (row, sidecar digests, the
+                       primers handed to mis_primer_check in call order) + region start/stop
+  msa_<case>.npz       the input alignment as 4-bit base sets + ids (inputs must travel to the GPU box)
+  kat.json             known-answer vectors of the scalar formulas (Tm, dH/dS, dG, Loss, get_Y, ...)
+  dimer_*.json / cover_*.json   finDimer_V4 / get_Maxprimerset_V1.3 outputs on committed primer sets
+"""
+from __future__ import annotations
+
+import hashlib
+import importlib.util
+import json
+import os
+import sys
+import tempfile
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+REF = "/root/reference"
+
+warnings.filterwarnings("ignore")
+from multiprime_b200 import synth  # noqa: E402
+
+CHARS = synth.CODE_CHARS
+CHAR2CODE = {c: i for i, c in enumerate(CHARS)}
+
+
+def load_ref(name, fname):
+    spec = importlib.util.spec_from_file_location(name, os.path.join(REF, "scripts", fname))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def digest(obj) -> str:
+    """order-insensitive over dict keys (the reference's key order depends on PYTHONHASHSEED), order
+    preserving inside the id lists"""
+    return hashlib.sha256(json.dumps(obj, sort_keys=True).encode()).hexdigest()[:16]
+
+
+CASES = {
+    # name: (input, kwargs for NN_degenerate, window positions)
+    "c2_k18": ("test_data/1000_fasta.msa",
+               dict(primer_length=18, coverage=0.8, number_of_dege_bases=6, score_of_dege_bases=64,
+                    raw_entropy_threshold=3.6, product_len=100, position="1,2,-1", variation=2, distance=4,
+                    GC="0.2,0.7"),
+               list(range(45, 85)) + list(range(300, 320)) + list(range(740, 757))),
+    "c2_k22": ("test_data/1000_fasta.msa",
+               dict(primer_length=22, coverage=0.8, number_of_dege_bases=6, score_of_dege_bases=64,
+                    raw_entropy_threshold=3.6, product_len=100, position="1,2,-1", variation=2, distance=4,
+                    GC="0.2,0.7"),
+               list(range(45, 65)) + list(range(500, 510))),
+    "c3_tmsa": ("test_data/results/Clusters_msa/Cluster_0_20727.tmsa",
+                dict(primer_length=18, coverage=0.7, number_of_dege_bases=4, score_of_dege_bases=10,
+                     raw_entropy_threshold=3.6, product_len=150, position="2,3,-1", variation=1, distance=4,
+                     GC="0.2,0.7"),
+                list(range(29, 60)) + list(range(590, 610)) + list(range(1480, 1500))),
+    "c1_testfa": ("test_data/test.fa",
+                  dict(primer_length=18, coverage=0.8, number_of_dege_bases=4, score_of_dege_bases=4,
+                       raw_entropy_threshold=3.6, product_len=100, position="1,2,-1", variation=1, distance=4,
+                       GC="0.2,0.7"),
+                  list(range(0, 30)) + list(range(7290, 7310)) + list(range(8100, 8112))),
+    "synth300": ("@synth:300:240:7",
+                 dict(primer_length=18, coverage=0.8, number_of_dege_bases=8, score_of_dege_bases=256,
+                      raw_entropy_threshold=3.6, product_len=100, position="1,2,-1", variation=3, distance=4,
+                      GC="0.2,0.7"),
+                 None),
+    "synth_iupac": ("@synth:200:200:11:0.004:0.003",
+                    dict(primer_length=20, coverage=0.8, number_of_dege_bases=6, score_of_dege_bases=64,
+                         raw_entropy_threshold=3.6, product_len=100, position="1,-1", variation=2, distance=4,
+                         GC="0.2,0.7"),
+                    None),
+}
+
+
+def materialise(inp: str, tmp: str) -> str:
+    if not inp.startswith("@synth:"):
+        return os.path.join(REF, inp)
+    f = inp.split(":")[1:]
+    n, L, seed = int(f[0]), int(f[1]), int(f[2])
+    kw = {}
+    if len(f) > 3:
+        kw = dict(gap_rate=float(f[3]), iupac_rate=float(f[4]))
+    codes = synth.synth_codes(n, L, seed=seed, **kw)
+    path = os.path.join(tmp, "synth_%d_%d_%d.fa" % (n, L, seed))
+    synth.write_fasta(path, codes)
+    return path
+
+
+def run_case(core, name):
+    inp, kw, positions = CASES[name]
+    with tempfile.TemporaryDirectory() as tmp:
+        path = materialise(inp, tmp)
+        app = core.NN_degenerate(seq_file=path, nproc=1, outfile=os.path.join(tmp, "x.out"), **kw)
+        ids = list(app.seq_dict.keys())
+        seqs = list(app.seq_dict.values())
+        start, stop = int(app.start_position), int(app.stop_position)
+        if positions is None:
+            positions = list(range(start, stop - kw["primer_length"]))
+        trace = []
+        orig = app.mis_primer_check
+
+        def wrapped(all_primers, primer, cover, ngsi):
+            trace.append(primer)
+            return orig(all_primers, primer, cover, ngsi)
+
+        app.mis_primer_check = wrapped
+        records = []
+        for p in positions:
+            trace.clear()
+            app.get_primers(app.seq_dict, p)
+            r = app.resQ.get()
+            if r is None:
+                records.append({"pos": p, "row": None, "trace": list(trace)})
+                continue
+            row = [r[0][0]] + list(r[0][1])
+            row = [x.item() if hasattr(x, "item") else x for x in row]
+            records.append({"pos": p, "row": row, "trace": list(trace),
+                            "f_non": digest(r[1][1][0]), "r_non": digest(r[1][1][1]),
+                            "gap_ids": digest(dict(r[2][1])),
+                            "n_f_non": len(r[1][1][0]), "n_r_non": len(r[1][1][1])})
+        L = max(len(s) for s in seqs)
+        codes = np.zeros((len(seqs), L), dtype=np.uint8)
+        lens = np.array([len(s) for s in seqs], dtype=np.int32)
+        for i, s in enumerate(seqs):
+            codes[i, :len(s)] = [CHAR2CODE[c] for c in s]
+        packed = (codes[:, 0::2] | (np.pad(codes, ((0, 0), (0, L % 2)))[:, 1::2] << 4)).astype(np.uint8)
+        if not inp.startswith("@synth:"):
+            np.savez_compressed(os.path.join(HERE, "msa_%s.npz" % name), packed=packed, n_col=L, lens=lens,
+                                ids=np.array(ids))
+        with open(os.path.join(HERE, "core_%s.json" % name), "w") as fh:
+            json.dump({"input": inp, "params": kw, "start": start, "stop": stop, "n_seq": len(seqs),
+                       "records": records}, fh, indent=0)
+        acc = sum(1 for r in records if r["row"] is not None)
+        print(name, "windows", len(records), "accepted", acc, "region", start, stop)
+
+
+def make_kat(core):
+    kat = {"tm": {}, "dh_ds": {}, "dg": {}, "loss": [], "get_y": {}, "deg": {}, "filters": {}}
+    seqs = ["ATGAAGACCATCATTGCC", "GGTACGGCCTCAGACATC", "ACGTACGTACGTACGT", "A" * 18, "GC" * 9, "TTTAAACAGCCTGTGGGT",
+            "GCGCGCGC", "ACGTTGCA", "TTTTTTTTTTTTTTTTTTTTTT", "CAGTCAGTCAGTCAGTCAGT", "AATTAATT"]
+    for s in seqs:
+        kat["tm"][s] = core.Calc_Tm_v2(s)
+        kat["dh_ds"][s] = list(core.Calc_deltaH_deltaS(s))
+    app = core.NN_degenerate.__new__(core.NN_degenerate)
+    app.distance = 4
+    app.GC = ["0.2", "0.7"]
+    for s in ["GCAACTGTTACC", "GCATC", "GGGTA", "ACGTTA", "ACGCGT", "T" * 14, "GCRYC", "ACGTWSTA", "GGCC", "ACGT",
+              "CCGGYTA"]:
+        kat["dg"][s] = app.deltaG(s)
+    for a in [(12, 6, 0, 0), (5, 3, 0, 0), (5, 2, 0, 3), (18, 9, 0, 0), (5, 0, 0, 13), (7, 4, 0, 1), (9, 9, 0, 2)]:
+        kat["loss"].append([list(a), core.Penalty_points(*a)])
+    for coord, k in [("1,2,-1", 18), ("2,3,-1", 18), ("1,-1", 20), ("-2,4", 22)]:
+        app.position, app.primer_length = coord, k
+        f, r = app.get_Y()
+        kat["get_y"]["%s|%d" % (coord, k)] = [sorted(f), sorted(r)]
+    for s in ["GGTAYGGYYTCAGRCATC", "ACGTNNAC", "HBVDACGT", "AAAA"]:
+        kat["deg"][s] = [core.score_trans(s), core.dege_number(s)]
+    primers = ["TTTMAAMCAGCCTGTGGG", "ACYCACCCAMAGGGCCCA", "ATGAAGACYRTCATTGCY", "DATGGAWAAGCTTRCCGA",
+               "ACACACACGGTTGGCCAA", "GGGGATCGATCGATTAGC", "ACGTTTTTCCCCCAAACGT", "CAGCAGCAGTTGACCATG",
+               "GCGGCCGCTTTTGCGGCCGC", "AARYTTRCYGACCTCWAY", "ATATATATGCGTACGTAC", "ACTGACCCGGGTCAGTTT"]
+    for p in primers:
+        kat["filters"][p] = {"info": app.primer_pre_filter(p), "self_dimer": bool(app.dimer_check(p)),
+                             "hairpin": bool(app.hairpin_check(p)), "repeat": bool(app.di_nucleotide(p)),
+                             "gc": app.GC_fraction(p)}
+    with open(os.path.join(HERE, "kat.json"), "w") as fh:
+        json.dump(kat, fh, indent=1)
+    print("kat written")
+
+
+def main():
+    assert os.environ.get("PYTHONHASHSEED") == "0", "run with PYTHONHASHSEED=0"
+    core = load_ref("mpcore", "multiPrime-core_V20.py")
+    which = sys.argv[1:] or (["kat"] + list(CASES))
+    for name in which:
+        if name == "kat":
+            make_kat(core)
+        elif name in CASES:
+            run_case(core, name)
+
+
+if __name__ == "__main__":
+    main()
