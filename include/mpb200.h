@@ -1,0 +1,145 @@
+/*
+ * mpb200.h — C ABI of libmpb200.so, the B200 (sm_100a) implementation of multiPrime's degenerate-primer
+ * candidate scan.  Loaded from Python with ctypes (multiprime_b200/_lib.py); no torch / C++ types cross
+ * this boundary: plain pointers, sizes and opaque handles only.
+ *
+ * The reference (joybio/multiPrime) has no in-process API — its boundary is "python scripts/<tool>.py
+ * <flags>" (multiPrime.py:202-206 etc.).  Each entry point below therefore names the reference FUNCTION it
+ * replaces (core = scripts/multiPrime-core_V20.py); multiprime_b200/core.py re-assembles them behind the
+ * reference's CLI.  INTEGRATION.md shows the ctypes binding a maintainer would add to the reference.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative MPB_E* code on failure; mpb_last_error() gives the
+ *     message of the last failure on the calling thread.  CUDA errors are mapped, never abort().
+ *   - "hd" pointers may be HOST or DEVICE addresses (detected with cudaPointerGetAttributes); host buffers
+ *     are staged through the context's stream.  Output buffers are caller-owned.
+ *   - all work is enqueued on the context's stream (mpb_ctx_set_stream; default: the legacy stream); calls
+ *     that fill HOST outputs synchronise that stream before returning, calls that fill DEVICE outputs do not.
+ *   - alignment cells are 4-bit base sets: A=1, C=2, G=4, T=8, IUPAC code = OR of its bases, gap = 0
+ *     (core:441-455 parse_seq maps every other character, N included, to '-').
+ *   - primer length k: 3 <= k <= 27 (haplotype keys are 64-bit; see DESIGN.md "keys").
+ */
+#ifndef MPB200_H
+#define MPB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPB_ABI_VERSION 1
+#define MPB_MAX_K 27
+#define MPB_MAX_EXPANSIONS 65536 /* expansions of one k-mer window of one sequence */
+
+#define MPB_OK 0
+#define MPB_EINVAL (-1)    /* bad argument */
+#define MPB_ECUDA (-2)     /* CUDA runtime error (message has the cudaError string) */
+#define MPB_ENOMEM (-3)    /* device allocation failed */
+#define MPB_EOVERFLOW (-4) /* haplotype table full: retry mpb_hist_build with a larger log2_cap */
+#define MPB_EEXPAND (-5)   /* a window holds more than MPB_MAX_EXPANSIONS expansions / a row has < k bases */
+
+typedef struct mpb_ctx mpb_ctx;   /* one CUDA device + stream */
+typedef struct mpb_msa mpb_msa;   /* an alignment resident in HBM as base bit-planes */
+typedef struct mpb_hist mpb_hist; /* per-window haplotype tables of one window batch */
+
+int mpb_abi_version(void);
+const char* mpb_last_error(void);
+int mpb_device_count(void);
+
+int mpb_ctx_create(int device, mpb_ctx** out);
+void mpb_ctx_destroy(mpb_ctx* ctx);
+int mpb_ctx_set_stream(mpb_ctx* ctx, void* cuda_stream);
+int mpb_ctx_sync(mpb_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py's "gpu_launches") */
+int64_t mpb_ctx_launches(mpb_ctx* ctx);
+
+/* ---- alignment ---------------------------------------------------------------------------------------
+ * core:441-455 parse_seq keeps the alignment as {id: string}; here it lives in HBM as four bit-planes
+ * (A,C,G,T) per 32-column word, sequence index fastest: planes[col_word][plane][seq].
+ * packed4_hd: n_seq rows of row_bytes bytes, two cells per byte, low nibble = even column.
+ * lens (host, may be NULL = all n_col): row lengths of a ragged (unaligned) input such as test_data/test.fa.
+ */
+int mpb_msa_upload(mpb_ctx* ctx, const uint8_t* packed4_hd, int64_t n_seq, int64_t n_col, int64_t row_bytes,
+                   const int32_t* lens, mpb_msa** out);
+void mpb_msa_free(mpb_msa* msa);
+int64_t mpb_msa_nseq(const mpb_msa* msa);
+
+/* core:617-627 seq_attribute, per-sequence part: number of leading gap cells and length after stripping
+ * trailing gaps.  The two quantiles (core:629-633) are taken by the host. */
+int mpb_seq_attr(mpb_msa* msa, int32_t* lead_gaps_hd, int32_t* rstrip_len_hd);
+
+/* ---- window haplotype tables: core:651-711 (sequence loop of get_primers) ---------------------------------
+ * For every window start win_pos[i] (host array) extract each sequence's k-mer with the reference's
+ * terminal-gap patching, expand IUPAC cells, and count haplotypes into an open-addressing table per window
+ * (cover / gap_sequence dictionaries of the reference).  log2_cap = 0 picks 2^ceil(log2(2*n_seq+64)).
+ */
+int mpb_hist_build(mpb_msa* msa, int k, int v, const int32_t* win_pos, int32_t nw, int log2_cap, mpb_hist** out);
+void mpb_hist_free(mpb_hist* h);
+
+/* Insert foreign (key, count, first) triples into the tables (multi-GPU merge of per-rank tables).
+ * win_off (host, nw+1) delimits the triples of each window inside the hd arrays. */
+int mpb_hist_merge(mpb_hist* h, const int64_t* win_off, const uint64_t* keys_hd, const uint32_t* cnt_hd,
+                   const uint64_t* first_hd);
+
+/* Per-window summary (all outputs hd, any may be NULL):
+ *   gap_n[nw]        sequences with more than v gaps (gap_sequence_number, core:689-691)
+ *   ent[nw*4]        sum(c), sum(c*log2 c) over cover haplotypes; the same two sums over gap k-mers
+ *                    (ingredients of core:602-614 entropy; the host rounds / re-derives exactly)
+ *   nuniq[nw*3]      distinct cover haplotypes, distinct gap k-mers, distinct gap-free cover haplotypes
+ *   mm_key/mm_cnt/mm_first[nw]  most frequent gap-free haplotype, first seen wins ties (core:595-600)
+ *   n_iupac_gap[nw]  gap rows holding IUPAC cells (not in the table; listed by mpb_hist_exceptions)
+ */
+int mpb_hist_stats(mpb_hist* h, int64_t* gap_n, double* ent, int64_t* nuniq, uint64_t* mm_key, int64_t* mm_cnt,
+                   uint64_t* mm_first, int64_t* n_iupac_gap);
+
+/* core:541-554 state_matrix and core:556-577 trans_matrix for the windows with sel[i] != 0 (host array):
+ *   freq[nw*4*k]       freq[w][b][col]  expansion rows with base b (A,C,G,T) at column col
+ *   nn[nw*(k-1)*16]    nn[w][col][x*4+y] expansion rows with x at col and y at col+1
+ */
+int mpb_hist_tensors(mpb_hist* h, const uint8_t* sel, int64_t* freq_hd, int64_t* nn_hd);
+
+/* All entries of window w, unordered: keys (see DESIGN.md for the encoding), counts, first-seen order
+ * (seq_index << 16 | expansion_index).  *n_out receives the number of entries (<= max_n). */
+int mpb_hist_dump(mpb_hist* h, int32_t w, int64_t max_n, uint64_t* keys_hd, uint32_t* cnt_hd, uint64_t* first_hd,
+                  int64_t* n_out);
+
+/* Number of DISTINCT gap-free haplotypes of window q_win[i] (index into the batch) that are expansions of the
+ * degenerate pattern q_allow[i*4 + b] (bit col set = base b allowed at col).  Used for nonsense_primer_number
+ * (core:846). */
+int mpb_hist_match(mpb_hist* h, const int32_t* q_win, const uint32_t* q_allow, int32_t nq, int64_t* distinct_hd);
+
+/* (window index, sequence index) pairs of gap rows that hold IUPAC cells, at most max_n pairs */
+int mpb_hist_exceptions(mpb_hist* h, int64_t max_n, int32_t* win_idx, int32_t* seq_idx, int64_t* n_out);
+
+/* ---- the candidate scan: core:1103-1130 mis_primer_check + core:229-233 Y_distance ---------------------------
+ * One evaluation = one candidate primer against one sequence's (patched, expanded) k-mer of the candidate's
+ * window.  cand_pos[nc] window start columns (ascending), cand_allow[nc*4] allowed-base bit masks.
+ * fmask / rmask: bit i set = a mismatch at primer position i disqualifies F / R coverage (core:1091-1101).
+ *   counts[nc*3]   expansion rows with 0 mismatches | 1..v mismatches and none at an F-strict position |
+ *                  the same for R      (perfect coverage, F_mis_cover, R_mis_cover of the reference)
+ *   bits_slot[nc]  (host, may be NULL) >= 0: also write per-sequence bit vectors for this candidate into
+ *                  bits[slot*3*words .. ): F non-cover, R non-cover, gap row; words = ceil(n_seq/32)
+ */
+int mpb_scan(mpb_msa* msa, int k, int v, uint32_t fmask, uint32_t rmask, const int32_t* cand_pos_hd,
+             const uint32_t* cand_allow_hd, int64_t nc, int64_t* counts_hd, const int32_t* bits_slot,
+             uint32_t* bits_hd);
+
+/* Per (window, sequence) haplotype key, for the JSON side files (core:1172-1176): the table key of the
+ * sequence's k-mer, MPB_KEY_IUPAC for rows whose window holds IUPAC cells. out[nw*n_seq]. */
+#define MPB_KEY_IUPAC 0xFFFFFFFFFFFFFFFEull
+#define MPB_KEY_EMPTY 0xFFFFFFFFFFFFFFFFull
+#define MPB_KEY_BASE5 (1ull << 54) /* keys >= this are base-5 numbers of k-mers that hold gaps */
+int mpb_seqkeys(mpb_msa* msa, int k, const int32_t* win_pos, int32_t nw, uint64_t* out_hd);
+
+/* ---- nearest-neighbour Tm: core:249-261 Calc_deltaH_deltaS + core:328-335 ---------------------------------
+ * seqs2bit[n*k] bases 0..3 (A,C,G,T).  consts = {R*ln(C/4e9), R*ln(C/1e9), salt correction} evaluated by the
+ * host with the reference's expressions; tm_out[n] unrounded fp64 (the host applies Python round()).
+ */
+int mpb_tm(mpb_ctx* ctx, const uint8_t* seqs2bit_hd, int k, int64_t n, const double* consts3, double* tm_hd,
+           double* dh_hd, double* ds_hd);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPB200_H */

@@ -1,0 +1,255 @@
+"""ctypes binding of libmpb200.so (include/mpb200.h).  No CPU fallback: every compute call needs a B200."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libmpb200.so")
+
+MAX_K = 27
+KEY_EMPTY = 0xFFFFFFFFFFFFFFFF
+KEY_IUPAC = 0xFFFFFFFFFFFFFFFE
+KEY_BASE5 = 1 << 54
+
+_lib = None
+
+# name -> (restype, argtypes); mirrors include/mpb200.h one to one
+_P = C.c_void_p
+SIGNATURES = {
+    "mpb_abi_version": (C.c_int, []),
+    "mpb_last_error": (C.c_char_p, []),
+    "mpb_device_count": (C.c_int, []),
+    "mpb_ctx_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
+    "mpb_ctx_destroy": (None, [_P]),
+    "mpb_ctx_set_stream": (C.c_int, [_P, _P]),
+    "mpb_ctx_sync": (C.c_int, [_P]),
+    "mpb_ctx_launches": (C.c_int64, [_P]),
+    "mpb_msa_upload": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, _P, C.POINTER(_P)]),
+    "mpb_msa_free": (None, [_P]),
+    "mpb_msa_nseq": (C.c_int64, [_P]),
+    "mpb_seq_attr": (C.c_int, [_P, _P, _P]),
+    "mpb_hist_build": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int32, C.c_int, C.POINTER(_P)]),
+    "mpb_hist_free": (None, [_P]),
+    "mpb_hist_merge": (C.c_int, [_P, _P, _P, _P, _P]),
+    "mpb_hist_stats": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
+    "mpb_hist_tensors": (C.c_int, [_P, _P, _P, _P]),
+    "mpb_hist_dump": (C.c_int, [_P, C.c_int32, C.c_int64, _P, _P, _P, C.POINTER(C.c_int64)]),
+    "mpb_hist_match": (C.c_int, [_P, _P, _P, C.c_int32, _P]),
+    "mpb_hist_exceptions": (C.c_int, [_P, C.c_int64, _P, _P, C.POINTER(C.c_int64)]),
+    "mpb_scan": (C.c_int, [_P, C.c_int, C.c_int, C.c_uint32, C.c_uint32, _P, _P, C.c_int64, _P, _P, _P]),
+    "mpb_seqkeys": (C.c_int, [_P, C.c_int, _P, C.c_int32, _P]),
+    "mpb_tm": (C.c_int, [_P, _P, C.c_int, C.c_int64, _P, _P, _P, _P]),
+}
+
+
+class MpbError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__("libmpb200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+def load():
+    """dlopen libmpb200.so (building it is build.py's job; a missing library is an error, not a fallback)"""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("libmpb200.so is missing: run `python -m multiprime_b200.build` (needs nvcc)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.mpb_abi_version() != 1:
+        raise ImportError("libmpb200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(rc: int):
+    if rc != 0:
+        raise MpbError(rc, load().mpb_last_error().decode())
+
+
+def ptr(x):
+    """numpy array / torch tensor / int / None -> void*"""
+    if x is None:
+        return None
+    if isinstance(x, np.ndarray):
+        assert x.flags["C_CONTIGUOUS"]
+        return x.ctypes.data_as(C.c_void_p)
+    if hasattr(x, "data_ptr"):
+        return C.c_void_p(x.data_ptr())
+    return C.c_void_p(int(x))
+
+
+class Context:
+    """one CUDA device + stream"""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        lib = load()
+        h = C.c_void_p()
+        check(lib.mpb_ctx_create(device, C.byref(h)))
+        self.h = h
+        self.device = device
+        if stream is not None:
+            self.set_stream(stream)
+
+    def set_stream(self, stream: int):
+        check(load().mpb_ctx_set_stream(self.h, C.c_void_p(stream)))
+
+    def sync(self):
+        check(load().mpb_ctx_sync(self.h))
+
+    @property
+    def launches(self) -> int:
+        return load().mpb_ctx_launches(self.h)
+
+    def close(self):
+        if self.h:
+            load().mpb_ctx_destroy(self.h)
+            self.h = None
+
+    # -- Tm -------------------------------------------------------------------------------------------
+    def tm(self, seqs2bit: np.ndarray, consts3, want_hs: bool = False):
+        n, k = seqs2bit.shape
+        seqs2bit = np.ascontiguousarray(seqs2bit, dtype=np.uint8)
+        cst = np.asarray(consts3, dtype=np.float64)
+        tm = np.empty(n, np.float64)
+        dh = np.empty(n, np.float64) if want_hs else None
+        ds = np.empty(n, np.float64) if want_hs else None
+        check(load().mpb_tm(self.h, ptr(seqs2bit), k, n, ptr(cst), ptr(tm), ptr(dh), ptr(ds)))
+        return (tm, dh, ds) if want_hs else tm
+
+
+class Msa:
+    """an alignment resident in HBM (bit-planes)"""
+
+    def __init__(self, ctx: Context, packed4, n_seq: int, n_col: int, row_bytes: int | None = None, lens=None):
+        self.ctx = ctx
+        self.n_seq, self.n_col = int(n_seq), int(n_col)
+        row_bytes = row_bytes if row_bytes is not None else (n_col + 1) // 2
+        if lens is not None:
+            lens = np.ascontiguousarray(lens, dtype=np.int32)
+        h = C.c_void_p()
+        check(load().mpb_msa_upload(ctx.h, ptr(packed4), n_seq, n_col, row_bytes, ptr(lens), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if self.h:
+            load().mpb_msa_free(self.h)
+            self.h = None
+
+    def seq_attr(self):
+        lead = np.empty(self.n_seq, np.int32)
+        rstrip = np.empty(self.n_seq, np.int32)
+        check(load().mpb_seq_attr(self.h, ptr(lead), ptr(rstrip)))
+        return lead, rstrip
+
+    def hist(self, k: int, v: int, win_pos, log2_cap: int = 0) -> "Hist":
+        return Hist(self, k, v, win_pos, log2_cap)
+
+    def scan(self, k: int, v: int, fmask: int, rmask: int, cand_pos, cand_allow, bits_slot=None, counts_out=None,
+             bits_out=None):
+        """returns (counts[nc,3] int64, bits[nslots,3,words] uint32 or None)"""
+        cand_pos = np.ascontiguousarray(cand_pos, dtype=np.int32)
+        cand_allow = np.ascontiguousarray(cand_allow, dtype=np.uint32).reshape(-1, 4)
+        nc = len(cand_pos)
+        counts = counts_out if counts_out is not None else np.zeros((nc, 3), np.int64)
+        bits = bits_out
+        if bits_slot is not None:
+            bits_slot = np.ascontiguousarray(bits_slot, dtype=np.int32)
+            nslots = int(bits_slot.max()) + 1 if nc else 0
+            words = (self.n_seq + 31) // 32
+            if bits is None:
+                bits = np.zeros((max(nslots, 0), 3, words), np.uint32)
+        if nc:
+            check(load().mpb_scan(self.h, k, v, fmask, rmask, ptr(cand_pos), ptr(cand_allow), nc, ptr(counts),
+                                  ptr(bits_slot), ptr(bits)))
+        return counts, bits
+
+    def seqkeys(self, k: int, win_pos) -> np.ndarray:
+        win_pos = np.ascontiguousarray(win_pos, dtype=np.int32)
+        out = np.empty((len(win_pos), self.n_seq), np.uint64)
+        check(load().mpb_seqkeys(self.h, k, ptr(win_pos), len(win_pos), ptr(out)))
+        return out
+
+
+class Hist:
+    """per-window haplotype tables of one window batch"""
+
+    def __init__(self, msa: Msa, k: int, v: int, win_pos, log2_cap: int = 0):
+        self.msa = msa
+        self.k, self.v = k, v
+        self.win_pos = np.ascontiguousarray(win_pos, dtype=np.int32)
+        self.nw = len(self.win_pos)
+        self.h = None
+        cap = log2_cap
+        while True:
+            h = C.c_void_p()
+            rc = load().mpb_hist_build(msa.h, k, v, ptr(self.win_pos), self.nw, cap, C.byref(h))
+            if rc == -4:  # MPB_EOVERFLOW: IUPAC expansions outgrew the table, double it
+                if cap == 0:
+                    cap = max(6, int(np.ceil(np.log2(2 * msa.n_seq + 64))))
+                cap += 1
+                continue
+            check(rc)
+            self.h = h
+            break
+
+    def close(self):
+        if self.h:
+            load().mpb_hist_free(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def stats(self):
+        nw = self.nw
+        out = dict(gap_n=np.empty(nw, np.int64), ent=np.empty((nw, 4), np.float64), nuniq=np.empty((nw, 3), np.int64),
+                   mm_key=np.empty(nw, np.uint64), mm_cnt=np.empty(nw, np.int64), mm_first=np.empty(nw, np.uint64),
+                   n_iupac_gap=np.empty(nw, np.int64))
+        check(load().mpb_hist_stats(self.h, ptr(out["gap_n"]), ptr(out["ent"]), ptr(out["nuniq"]), ptr(out["mm_key"]),
+                                    ptr(out["mm_cnt"]), ptr(out["mm_first"]), ptr(out["n_iupac_gap"])))
+        return out
+
+    def tensors(self, sel):
+        sel = np.ascontiguousarray(sel, dtype=np.uint8)
+        freq = np.empty((self.nw, 4, self.k), np.int64)
+        nn = np.empty((self.nw, self.k - 1, 4, 4), np.int64)
+        check(load().mpb_hist_tensors(self.h, ptr(sel), ptr(freq), ptr(nn)))
+        return freq, nn
+
+    def dump(self, w: int, max_n: int):
+        keys = np.empty(max_n, np.uint64)
+        cnt = np.empty(max_n, np.uint32)
+        first = np.empty(max_n, np.uint64)
+        n = C.c_int64()
+        check(load().mpb_hist_dump(self.h, w, max_n, ptr(keys), ptr(cnt), ptr(first), C.byref(n)))
+        n = min(n.value, max_n)
+        order = np.argsort(first[:n], kind="stable")
+        return keys[:n][order], cnt[:n][order], first[:n][order]
+
+    def match(self, q_win, q_allow):
+        q_win = np.ascontiguousarray(q_win, dtype=np.int32)
+        q_allow = np.ascontiguousarray(q_allow, dtype=np.uint32).reshape(-1, 4)
+        out = np.zeros(len(q_win), np.int64)
+        if len(q_win):
+            check(load().mpb_hist_match(self.h, ptr(q_win), ptr(q_allow), len(q_win), ptr(out)))
+        return out
+
+    def exceptions(self):
+        n = C.c_int64()
+        check(load().mpb_hist_exceptions(self.h, 0, None, None, C.byref(n)))
+        w = np.empty(n.value, np.int32)
+        s = np.empty(n.value, np.int32)
+        if n.value:
+            check(load().mpb_hist_exceptions(self.h, n.value, ptr(w), ptr(s), C.byref(n)))
+        return w, s

@@ -1,0 +1,770 @@
+"""Host side of the degenerate-primer candidate scan: a drop-in for scripts/multiPrime-core.py (V20).
+
+`NN_degenerate` keeps the reference's constructor arguments, `run()` and output files (core:343-365,
+1133-1180).  All per-sequence work — window extraction with gap patching, haplotype counting, base / dinucleotide
+tensors, the mismatch scan, Tm — runs in libmpb200.so on a B200; this module holds the per-window control logic
+(gates, seeds, the NN-array refinement walk, filters, writers), which only ever touches O(k) numbers per window.
+
+There is no CPU fallback: constructing NN_degenerate without a CUDA device raises.
+"""
+from __future__ import annotations
+
+import json
+import math
+import sys
+import time
+from fractions import Fraction
+from statistics import mean
+
+import numpy as np
+
+from . import _lib
+from .iupac import (BASES, CODE_CHARS, CHAR_CODE, FOLD, allow_masks, comp_set, degeneracy, expand_keys, expand_strings,
+                    n_degenerate, primer_string, rc_sets, sets_of)
+
+TSV_HEADER = ["Position", "Entropy of cover (bit)", "Entropy of total (bit)", "Optimal_primer",
+              "primer_degenerate_number", "nonsense_primer_number", "Optimal_coverage", "Mis-F-coverage",
+              "Mis-R-coverage", "Tm", "Information"]
+
+
+# ----------------------------------------------------------------------------------------------------------
+# input
+# ----------------------------------------------------------------------------------------------------------
+def _byte_table() -> bytes:
+    t = bytearray(256)
+    for ch, code in CHAR_CODE.items():
+        if ch in "ACGTRYMKSWHBVD":              # core:453: everything else (N included) becomes a gap
+            t[ord(ch)] = code
+            t[ord(ch.lower())] = code
+    return bytes(t)
+
+
+_BYTE_TABLE = _byte_table()
+
+
+def parse_msa(path: str):
+    """core:441-455 parse_seq -> (ids, codes uint8 [n_seq, n_col] of 4-bit base sets, lens int32)"""
+    order: dict[str, list] = {}
+    cur = None
+    with open(path, "rb") as fh:
+        for line in fh:
+            if line.startswith(b"#"):
+                continue
+            if line.startswith(b">"):
+                cur = line.decode().strip().split(" ")[0]
+            else:
+                order.setdefault(cur, []).append(line.strip().translate(_BYTE_TABLE))
+    ids = list(order.keys())
+    rows = [b"".join(parts) for parts in order.values()]
+    lens = np.array([len(r) for r in rows], dtype=np.int32)
+    n_col = int(lens.max()) if len(rows) else 0
+    if len(rows) and (lens == n_col).all():
+        codes = np.frombuffer(b"".join(rows), dtype=np.uint8).reshape(len(rows), n_col)
+    else:
+        codes = np.zeros((len(rows), n_col), dtype=np.uint8)
+        for i, r in enumerate(rows):
+            codes[i, :len(r)] = np.frombuffer(r, dtype=np.uint8)
+    return ids, codes, lens
+
+
+def pack4(codes: np.ndarray) -> np.ndarray:
+    """two cells per byte, low nibble = even column"""
+    n, L = codes.shape
+    if L % 2:
+        codes = np.concatenate([codes, np.zeros((n, 1), np.uint8)], axis=1)
+    return (codes[:, 0::2] | (codes[:, 1::2] << 4)).astype(np.uint8)
+
+
+def strict_masks(coordinate: str, k: int):
+    """core:1091-1101 get_Y as bit masks over 0-based primer positions (indices >= k never match anything)"""
+    f = r = 0
+    for tok in coordinate.split(","):
+        y = int(tok.strip())
+        fi, ri = (y, k - y) if y > 0 else (k + y + 1, -y + 1)
+        if 0 <= fi < k:
+            f |= 1 << fi
+        if 0 <= ri < k:
+            r |= 1 << ri
+    return f, r
+
+
+# ----------------------------------------------------------------------------------------------------------
+# scalar pieces evaluated per window on the host
+# ----------------------------------------------------------------------------------------------------------
+def _tm_consts():
+    """the sequence-independent terms of core:293-335, spelled as the reference spells them"""
+    primer_concentration, Mo, Di, dNTP = 100, 50, 1.5, 0.25
+    free_divalent = (Di - dNTP) / 1000.0
+    a = 3.92 * pow(10, -5) * (0.843 - (0.352 * math.sqrt(Mo / 1000.0) * math.log(Mo / 1000.0, math.e)))
+    b = - 9.11 * pow(10, -6)
+    correction = a + (b * math.log(free_divalent, math.e))          # core:323 (the rest of Eq 16 is dead code)
+    c4 = 1.9872 * math.log(primer_concentration / (4 * pow(10, 9)), math.e)
+    c1 = 1.9872 * math.log(primer_concentration / (1 * pow(10, 9)), math.e)
+    return c4, c1, correction
+
+
+TM_CONSTS = _tm_consts()
+
+
+def viterbi_seed(freq, nn, k: int):
+    """core:579-593: max-sum path over freq[b][t] + nn[t-1][prev][cur]; first maximum wins"""
+    score = [int(freq[b][0]) for b in range(4)]
+    back = []
+    for t in range(1, k):
+        layer = nn[t - 1]
+        new, bp = [], []
+        for cur in range(4):
+            best, arg = None, 0
+            for prev in range(4):
+                val = score[prev] + layer[prev * 4 + cur]
+                if best is None or val > best:
+                    best, arg = val, prev
+            new.append(best + int(freq[cur][t]))
+            bp.append(arg)
+        score = new
+        back.append(bp)
+    cur = 0
+    for b in range(1, 4):
+        if score[b] > score[cur]:
+            cur = b
+    path = [cur]
+    for bp in reversed(back):
+        cur = bp[cur]
+        path.append(cur)
+    return path[::-1]
+
+
+def _order_desc(vals):
+    """np.argsort(vals)[::-1] for a stable ascending sort (reference numpy 1.21 on 4 elements)"""
+    return sorted(range(4), key=vals.__getitem__)[::-1]
+
+
+def _npos(vals):
+    return sum(1 for x in vals if x > 0)
+
+
+def refine_options(sets, seed, nn_cov, nn):
+    """core:922-1080: for every junction tied at the minimum NN coverage, the refinement the reference would try.
+    Yields (pos, base, new_layers, new_cov) or None (junction cannot be refined) per tied junction."""
+    k = len(sets)
+    last = k - 2
+    lowest = min(nn_cov)
+    out = []
+    for j in range(k - 1):
+        if nn_cov[j] != lowest:
+            continue
+        row, col = seed[j], seed[j + 1]
+        L = nn[j]
+
+        def middle(jj):
+            nrow, ncol = seed[jj + 1], seed[jj + 2]
+            L0, L1 = nn[jj], nn[jj + 1]
+            m = [min(L0[row * 4 + x], L1[x * 4 + ncol]) for x in range(4)]
+            if _npos(m) <= 1:
+                return None
+            idx = next(i for i in _order_desc(m) if i != col)
+            n0, n1 = list(L0), list(L1)
+            for x in range(4):
+                n0[x * 4 + col] += L0[x * 4 + idx]
+                n0[x * 4 + idx] = 0
+            for y in range(4):
+                n1[nrow * 4 + y] += L1[idx * 4 + y]
+                n1[idx * 4 + y] = 0
+            cov = list(nn_cov)
+            cov[jj] = n0[row * 4 + col]
+            cov[jj + 1] = n1[nrow * 4 + ncol]
+            return (jj + 1, idx, {jj: n0, jj + 1: n1}, cov)
+
+        if j == 0:
+            column0 = [L[x * 4 + col] for x in range(4)]
+            if _npos(column0) > 1:
+                idx = next(i for i in _order_desc(column0) if i != row)
+                n0 = list(L)
+                for y in range(4):
+                    n0[row * 4 + y] += L[idx * 4 + y]
+                    n0[idx * 4 + y] = 0
+                cov = list(nn_cov)
+                cov[0] = n0[row * 4 + col]
+                out.append((0, idx, {0: n0}, cov))
+            elif _npos(L[row * 4:row * 4 + 4]) > 1:
+                out.append(middle(0))
+            else:
+                out.append(None)
+        elif j == last:
+            rowvals = L[row * 4:row * 4 + 4]
+            if _npos(rowvals) > 1:
+                idx = next(i for i in _order_desc(rowvals) if i != col)
+                n0 = list(L)
+                for x in range(4):
+                    n0[x * 4 + col] += L[x * 4 + idx]
+                    n0[x * 4 + idx] = 0
+                cov = list(nn_cov)
+                cov[j] = n0[row * 4 + col]
+                out.append((j + 1, idx, {j: n0}, cov))
+            else:
+                out.append(None)
+        else:
+            out.append(middle(j))
+    return out
+
+
+# ---- filters (core:387-416, 507-521) on base-set lists, no expansion ------------------------------------
+def _repeat_patterns():
+    pats = set()
+    for i in range(4):
+        pats.add((i,) * 4)
+        for j in range(4):
+            if i != j:
+                pats.add((i, j) * 4)
+            for kk in range(4):
+                if i != j and j != kk:
+                    pats.add((i, j, kk) * 3)
+    return sorted(pats)
+
+
+_REPEATS = _repeat_patterns()
+
+
+def gc_content(sets) -> float:
+    """core:401-407: mean over expansions of round(gc/len, 3), rounded to 2 — via the GC-count distribution"""
+    k = len(sets)
+    dist = [1]                                    # dist[g] = number of expansions of the prefix with g G/C
+    for s in sets:
+        n_gc = ((s >> 1) & 1) + ((s >> 2) & 1)
+        n_at = (s & 1) + ((s >> 3) & 1)
+        new = [0] * (len(dist) + 1)
+        for g, m in enumerate(dist):
+            new[g] += m * n_at
+            new[g + 1] += m * n_gc
+        dist = new
+    total = sum(dist)
+    acc = Fraction(0)
+    for g, m in enumerate(dist):
+        if m:
+            acc += m * Fraction(round(g / k, 3))  # statistics.mean: exact rational mean of the floats
+    return round(float(acc / total), 2)
+
+
+def has_repeat(sets) -> bool:
+    """core:410-416: some expansion contains XXXX, (XY)x4 or (XYZ)x3"""
+    k = len(sets)
+    allow = allow_masks(sets)
+    for pat in _REPEATS:
+        n = len(pat)
+        if n > k:
+            continue
+        hit = (1 << (k - n + 1)) - 1
+        for t, b in enumerate(pat):
+            hit &= allow[b] >> t
+            if not hit:
+                break
+        if hit:
+            return True
+    return False
+
+
+def has_hairpin(sets, distance: int) -> bool:
+    """core:387-398: a 5-mer whose reverse complement can occur at least `distance` bases downstream"""
+    k = len(sets)
+    n = 0
+    while n <= k - 5 - 5 - distance:
+        target = rc_sets(sets[n:n + 5])
+        tail0 = n + 5 + distance
+        for o in range(tail0, k - 5 + 1):
+            if all(target[t] & sets[o + t] for t in range(5)):
+                return True
+        n += 1
+    return False
+
+
+def information(sets, gc_lo: float, gc_hi: float, distance: int):
+    """core:507-521 primer_pre_filter"""
+    notes = []
+    gc = gc_content(sets)
+    if not gc_lo <= gc <= gc_hi:
+        notes.append("GC_out_of_range (" + str(gc) + ")")
+    if has_repeat(sets):
+        notes.append("di_nucleotide")
+    if has_hairpin(sets, distance):
+        notes.append("hairpin")
+    return gc if not notes else "|".join(notes)
+
+
+class _Track:
+    """one run of core:860-920 coverage_stast (NM or MM seed) advanced in lock step with the scan"""
+    __slots__ = ("seed", "sets", "nn", "nn_cov", "init", "fm", "rm", "state", "opts", "trace", "seed_cover")
+
+    def __init__(self, seed, nn):
+        self.seed = seed
+        self.sets = [1 << b for b in seed]
+        self.nn = nn                                  # list of k-1 flat 4x4 lists; layers are copied on write
+        self.nn_cov = [nn[j][seed[j] * 4 + seed[j + 1]] for j in range(len(seed) - 1)]
+        self.init = 0
+        self.seed_cover = 0                           # cover[seed] (core:787/800/809/835)
+        self.fm = self.rm = 0
+        self.state = "seed"                           # seed -> refine* -> done
+        self.opts = None
+        self.trace = []
+
+
+class NN_degenerate(object):
+    """Drop-in for the reference class of the same name (core:342-365); same keyword arguments.
+
+    Extra keyword arguments (not in the reference): device, windows_per_batch, sidecars."""
+
+    def __init__(self, seq_file, primer_length=18, coverage=0.8, number_of_dege_bases=18, score_of_dege_bases=1000,
+                 product_len=250, position="2,-1", variation=2, raw_entropy_threshold=3.6, distance=4, GC="0.4,0.6",
+                 nproc=10, outfile="", device=0, windows_per_batch=0, sidecars=True, alignment=None, stream=None,
+                 _backend=None):
+        self.primer_length = primer_length
+        self.coverage = coverage
+        self.number_of_dege_bases = number_of_dege_bases
+        self.score_of_dege_bases = score_of_dege_bases
+        self.product = product_len
+        self.position = position
+        self.variation = variation
+        self.distance = distance
+        self.GC = GC.split(",")
+        self.nproc = nproc                      # accepted and ignored, as in the reference (core:1143)
+        self.raw_entropy_threshold = raw_entropy_threshold
+        self.outfile = outfile
+        self.sidecars = sidecars
+        self.windows_per_batch = windows_per_batch
+        if not 3 <= primer_length <= _lib.MAX_K:
+            raise ValueError("primer length must be within 3..%d" % _lib.MAX_K)
+        self.fmask, self.rmask = strict_masks(position, primer_length)
+        if alignment is not None:
+            self.ids, codes, lens = alignment
+        else:
+            self.ids, codes, lens = parse_msa(seq_file)
+        self.total_sequence_number = len(self.ids)
+        self.n_col = codes.shape[1]
+        self.codes = codes                      # host copy: only read for the rare IUPAC-in-gap-row side-file entries
+        self.lens = lens
+        backend = _backend or _lib                # tests inject tests/fake_device.py to exercise the host logic
+        self.ctx = backend.Context(device, stream)
+        self.msa = backend.Msa(self.ctx, pack4(codes), len(self.ids), self.n_col,
+                            lens=None if (lens == self.n_col).all() else lens)
+        self.position_list = self.seq_attribute()
+        self.start_position, self.stop_position, self.length = self.position_list
+        self.entropy_threshold = self.entropy_threshold_adjust(self.length)
+        self.stats = {"windows": 0, "accepted": 0, "scan_calls": 0, "evals": 0, "candidates": 0}
+
+    # -- core:617-649 -------------------------------------------------------------------------------------
+    def seq_attribute(self):
+        lead, rstrip = self.msa.seq_attr()
+        start = int(np.quantile(lead.reshape(1, -1), self.coverage, method="higher"))
+        stop = int(np.quantile(rstrip.reshape(1, -1), self.coverage, method="lower"))
+        if stop - start < int(self.product):
+            print("Error: max length of PCR product is shorter than the default min Product length with {} "
+                  "coverage! Non candidate primers !!!".format(self.coverage))
+            sys.exit(1)
+        return [start, stop, stop - start]
+
+    def entropy_threshold_adjust(self, length):
+        if length < 5000:
+            return self.raw_entropy_threshold
+        if length < 10000:
+            return self.raw_entropy_threshold * 0.95
+        return self.raw_entropy_threshold * 0.9
+
+    # -- entropy (core:602-614) ----------------------------------------------------------------------------
+    def _entropy_exact(self, hist, wi, pos, n_unique):
+        """the reference's left-to-right float sums, over the table dumped in first-seen order"""
+        k, v = self.primer_length, self.variation
+        keys, cnt, first = hist.dump(wi, int(n_unique) + 8)
+        cover, gaps = [], []                     # (first, count)
+        for key, c, f in zip(keys.tolist(), cnt.tolist(), first.tolist()):
+            if key >= _lib.KEY_BASE5 and _count_gap_digits(key - _lib.KEY_BASE5, k) > v:
+                gaps.append((f, c))
+            else:
+                cover.append((f, c))
+        # gap rows that hold IUPAC cells are not in the table: group them by their raw k-mer
+        exc_w, exc_s = self._exceptions(hist)
+        raw = {}
+        for s in exc_s[exc_w == wi].tolist():
+            w = self._window_cells(s, pos)
+            raw.setdefault(w, [s << 16, 0])[1] += 1
+        gaps.extend((f, c) for f, c in raw.values())
+        gaps.sort()
+        gap_n = sum(c for _, c in gaps)
+        cover_number = self.total_sequence_number - gap_n
+        tot = cover_number + gap_n
+        c_bit = 0
+        t_bit = 0
+        for _, c in cover:
+            c_bit += (c / cover_number) * math.log((c / cover_number), 2)
+            t_bit += (c / tot) * math.log((c / tot), 2)
+        for _, c in gaps:
+            t_bit += (c / tot) * math.log((c / tot), 2)
+        return round(-c_bit, 2), round(-t_bit, 2)
+
+    def _exceptions(self, hist):
+        if getattr(hist, "_exc", None) is None:
+            hist._exc = hist.exceptions()
+        return hist._exc
+
+    def _window_cells(self, s: int, p: int) -> bytes:
+        """core:666-687 for one (sequence, window) on the host copy; only used for IUPAC-holding gap rows"""
+        k = self.primer_length
+        row = self.codes[s, :self.lens[s]].tobytes()
+        gap = b"\x00"
+        w = row[p:p + k]
+        if w != gap * k:
+            if w.startswith(gap):
+                body = w.lstrip(gap)
+                g = len(w) - len(body)
+                left = row[0:p].replace(gap, b"")
+                if len(left) >= g:
+                    w = left[len(left) - g:] + body
+            if w.endswith(gap):
+                body = w.rstrip(gap)
+                g = len(w) - len(body)
+                right = row[p + k:].replace(gap, b"")
+                if len(right) >= g:
+                    w = body + right[0:g]
+        if len(w) < k:
+            g = k - len(w)
+            left = row[0:p].replace(gap, b"")
+            if len(left) >= g:
+                w = left[len(left) - g:] + w
+        return w
+
+    # -- the window pipeline --------------------------------------------------------------------------------
+    def design(self, positions):
+        """Run the per-window algorithm (core:651-858) for the given window start columns.
+        Returns a list of records {row, non_cov, gap_ids, trace} (rejected windows are absent)."""
+        positions = [int(p) for p in positions]
+        if not positions:
+            return []
+        per_batch = self.windows_per_batch or _default_batch(self.total_sequence_number)
+        out = []
+        for b0 in range(0, len(positions), per_batch):
+            out.extend(self._design_batch(positions[b0:b0 + per_batch]))
+        return out
+
+    def _design_batch(self, positions):
+        k, v, N = self.primer_length, self.variation, self.total_sequence_number
+        self.stats["windows"] += len(positions)
+        with self.msa.hist(k, v, positions) as hist:
+            st = hist.stats()
+            accepted = {}
+            sel = np.zeros(len(positions), np.uint8)
+            for wi, pos in enumerate(positions):
+                gap_n = int(st["gap_n"][wi])
+                if round(gap_n / N, 2) >= (1 - self.coverage):          # core:713
+                    continue
+                n_cover_u, n_gap_u, n_gapfree = (int(x) for x in st["nuniq"][wi])
+                if n_cover_u < 1:                                        # core:716
+                    continue
+                ent = self._entropy(hist, st, wi, pos, gap_n, n_cover_u + n_gap_u)
+                if ent is None:
+                    continue
+                accepted[wi] = {"pos": pos, "c_bit": ent[0], "t_bit": ent[1], "cover_number": N - gap_n,
+                                "has_mm": n_gapfree > 0}
+                sel[wi] = 1
+            if not accepted:
+                return []
+            freq, nn = hist.tensors(sel)
+            tracks = {}
+            for wi in list(accepted):
+                f = freq[wi]
+                if (f.sum(axis=1) == 0).any() or (f.sum(axis=0) == 0).any():   # core:736-740
+                    del accepted[wi]
+                    continue
+                layers = [row.reshape(16).tolist() for row in nn[wi]]
+                nm = viterbi_seed(f.tolist(), layers, k)
+                info = accepted[wi]
+                if info["has_mm"]:
+                    mm = _key_bases(int(st["mm_key"][wi]), k)
+                    info["seeds"] = [nm] if nm == mm else [nm, mm]
+                else:
+                    info["seeds"] = [nm]
+                tracks[wi] = [_Track(seed, layers) for seed in info["seeds"]]
+            self._run_tracks(positions, accepted, tracks)
+            return self._finish(hist, positions, accepted, tracks)
+
+    def _entropy(self, hist, st, wi, pos, gap_n, n_unique):
+        """(cBit, tBit) rounded as the reference rounds them, or None when tBit exceeds the threshold"""
+        N = self.total_sequence_number
+        s0c, s1c, s0g, s1g = (float(x) for x in st["ent"][wi])
+        cover_number = N - gap_n
+        exact = st["n_iupac_gap"][wi] > 0
+        if not exact:
+            tot = float(N)
+            c_raw = -(s1c - s0c * math.log2(cover_number)) / cover_number
+            t_raw = -((s1c - s0c * math.log2(tot)) + (s1g - s0g * math.log2(tot))) / tot
+            # device sums use another summation order than the reference; fall back to the exact replay whenever
+            # that could change a rounded digit or the gate
+            # (an exact zero prints as "-0.0" in the reference: round(-0.0, 2); leave that to the replay too)
+            if _near_half(c_raw) or _near_half(t_raw) or abs(t_raw - self.entropy_threshold) < 1e-6 \
+                    or abs(c_raw) < 1e-9 or abs(t_raw) < 1e-9:
+                exact = True
+            elif t_raw > self.entropy_threshold + 0.006:
+                return None
+        if exact:
+            c_bit, t_bit = self._entropy_exact(hist, wi, pos, n_unique)
+        else:
+            c_bit, t_bit = round(c_raw, 2), round(t_raw, 2)
+        if t_bit > self.entropy_threshold:                                # core:723
+            return None
+        return c_bit, t_bit
+
+    # -- refinement walk in lock step with the scan (core:860-1089) ------------------------------------------
+    def _run_tracks(self, positions, accepted, tracks):
+        k, v = self.primer_length, self.variation
+        d_max, n_max = self.score_of_dege_bases, self.number_of_dege_bases
+        live = [(wi, t) for wi in accepted for t in tracks[wi]]
+        while live:
+            cand_pos, cand_allow, owners = [], [], []
+            for wi, t in live:
+                pos = accepted[wi]["pos"]
+                if t.state == "seed":
+                    cand_pos.append(pos)
+                    cand_allow.append(allow_masks(t.sets))
+                    owners.append((t, "seed", None))
+                else:
+                    t.opts = refine_options(t.sets, t.seed, t.nn_cov, t.nn)
+                    for oi, opt in enumerate(t.opts):
+                        if opt is None:
+                            continue
+                        p, b = opt[0], opt[1]
+                        trial = list(t.sets)
+                        trial[p] = 1 << b
+                        cand_pos.append(pos)
+                        cand_allow.append(allow_masks(trial))
+                        owners.append((t, "trial", oi))
+                        new = list(t.sets)
+                        assert not new[p] & (1 << b), "refinement would re-add a base (reference raises KeyError)"
+                        new[p] |= 1 << b
+                        cand_pos.append(pos)
+                        cand_allow.append(allow_masks(new))
+                        owners.append((t, "new", oi))
+            order = np.argsort(np.asarray(cand_pos, dtype=np.int64), kind="stable")
+            counts, _ = self.msa.scan(k, v, self.fmask, self.rmask, np.asarray(cand_pos, np.int32)[order],
+                                      np.asarray(cand_allow, np.uint32)[order])
+            self.stats["scan_calls"] += 1
+            self.stats["candidates"] += len(cand_pos)
+            inv = np.empty(len(order), np.int64)
+            inv[order] = np.arange(len(order))
+            got = {}
+            for ci, (t, kind, oi) in enumerate(owners):
+                got.setdefault(id(t), {})[(kind, oi)] = counts[inv[ci]]
+            nxt = []
+            for wi, t in live:
+                total = accepted[wi]["cover_number"]
+                res = got.get(id(t), {})
+                if t.state == "seed":
+                    c = res[("seed", None)]
+                    t.init, t.fm, t.rm = int(c[0]), int(c[1]), int(c[2])
+                    t.seed_cover = t.init
+                    t.trace.append(primer_string(t.sets))
+                    t.state = "refine"
+                    if t.init + t.fm < total or t.init + t.rm < total:
+                        nxt.append((wi, t))
+                    else:
+                        t.state = "done"
+                    continue
+                best, best_gain = 0, None
+                for oi, opt in enumerate(t.opts):
+                    gain = t.init + (int(res[("trial", oi)][0]) if opt is not None else 0)
+                    if best_gain is None or gain > best_gain:
+                        best, best_gain = oi, gain
+                opt = t.opts[best]
+                if opt is None:
+                    cov_new = list(t.nn_cov)
+                    c = None
+                else:
+                    p, b, layers, cov_new = opt
+                    t.sets[p] |= 1 << b
+                    t.nn = list(t.nn)
+                    for j, layer in layers.items():
+                        t.nn[j] = layer
+                    c = res[("new", best)]
+                t.init = best_gain
+                if c is not None:
+                    t.fm, t.rm = int(c[1]), int(c[2])
+                # else: primer unchanged, the reference's second mis_primer_check returns the same counts
+                t.trace.append(primer_string(t.sets))
+                deg, ndeg = degeneracy(t.sets), n_degenerate(t.sets)
+                if max(t.fm, t.rm) == total:
+                    t.state = "done"
+                elif cov_new == t.nn_cov:
+                    t.state = "done"
+                elif 2 * deg > d_max or 3 * deg / 2 > d_max or ndeg == n_max:
+                    t.state = "done"
+                else:
+                    t.nn_cov = cov_new
+                    if t.init + t.fm < total or t.init + t.rm < total:
+                        nxt.append((wi, t))
+                    else:
+                        t.state = "done"
+            live = nxt
+
+    # -- rows, filters, side files ----------------------------------------------------------------------------
+    def _finish(self, hist, positions, accepted, tracks):
+        k, v, N = self.primer_length, self.variation, self.total_sequence_number
+        gc_lo, gc_hi = float(self.GC[0]), float(self.GC[1])
+        chosen = {}
+        for wi, info in accepted.items():
+            ts = tracks[wi]
+            if len(ts) == 1:
+                t = ts[0]
+            else:   # core:816: NM only when strictly better
+                nm, mm = ts
+                t = nm if (nm.init + nm.fm + nm.init + nm.rm) > (mm.init + mm.fm + mm.init + mm.rm) else mm
+            chosen[wi] = t
+            self.stats["evals"] += sum(len(x.trace) for x in ts) * N
+        wis = sorted(chosen)
+        # final pass of the scan: perfect coverage of the chosen primer (+ per-sequence non-cover bits)
+        allow = np.asarray([allow_masks(chosen[wi].sets) for wi in wis], np.uint32)
+        pos = np.asarray([accepted[wi]["pos"] for wi in wis], np.int32)
+        slots = np.arange(len(wis), dtype=np.int32) if self.sidecars else None
+        counts, bits = self.msa.scan(k, v, self.fmask, self.rmask, pos, allow, bits_slot=slots)
+        self.stats["scan_calls"] += 1
+        distinct = hist.match(np.asarray(wis, np.int32), allow)
+        # Tm of every expansion of every chosen primer in one launch
+        exp_bases, spans = [], []
+        for wi in wis:
+            e = expand_keys(chosen[wi].sets)
+            spans.append((len(exp_bases), len(e)))
+            exp_bases.extend(e)
+        tm_raw = self.ctx.tm(np.asarray(exp_bases, np.uint8).reshape(-1, k), TM_CONSTS)
+        seqkeys = self.msa.seqkeys(k, pos) if self.sidecars else None
+        out = []
+        for n, wi in enumerate(wis):
+            t, info = chosen[wi], accepted[wi]
+            sets = t.sets
+            primer = primer_string(sets)
+            deg = degeneracy(sets)
+            # core:846: expansions that are not keys of `cover`; the defaultdict look-ups of the seeds (core:787-835)
+            # added their strings as keys, observed or not
+            nonsense = deg - int(distinct[n])
+            for tr in tracks[wi]:
+                seed_sets = [1 << b for b in tr.seed]
+                if tr.seed_cover == 0 and all(a & b for a, b in zip(sets, seed_sets)):
+                    nonsense -= 1
+            a, cnt = spans[n]
+            tms = [round(float(x), 2) for x in tm_raw[a:a + cnt]]
+            tm_avg = round(mean(tms), 2)
+            perfect = int(counts[n][0])
+            info_col = information(sets, gc_lo, gc_hi, self.distance)
+            if self_dimer(sets):
+                continue                                                  # core:749-751
+            row = [info["pos"], info["c_bit"], info["t_bit"], primer, n_degenerate(sets), nonsense, perfect,
+                   t.init + t.fm, t.init + t.rm, tm_avg, info_col]
+            rec = {"row": row, "trace": [p for tr in tracks[wi] for p in tr.trace]}
+            if self.sidecars:
+                rec["non_cov"], rec["gap_ids"] = self._sidecars(hist, wi, info["pos"], sets, bits[n], seqkeys[n])
+            out.append(rec)
+        self.stats["accepted"] += len(out)
+        return out
+
+    def _sidecars(self, hist, wi, pos, sets, bits, keys):
+        """core:1116-1125 / 696-698: {haplotype: [ids]} of the sequences the final primer does not cover (F, R) and
+        of the gap rows, rebuilt from the scan's per-sequence bits and the per-sequence table keys"""
+        k, v = self.primer_length, self.variation
+        N = self.total_sequence_number
+        ids = self.ids
+        unpack = lambda words: np.unpackbits(words.view(np.uint8), bitorder="little")[:N].astype(bool)
+        non_f, non_r, gap = unpack(bits[0]), unpack(bits[1]), unpack(bits[2])
+        iupac = keys == np.uint64(_lib.KEY_IUPAC)
+        groups = ({}, {}, {})                      # F non-cover, R non-cover, gap rows: haplotype -> [sequence index]
+        for flag, dct in zip((non_f, non_r, gap), groups):
+            by_key = {}
+            for s in np.nonzero(flag & ~iupac)[0].tolist():       # plain rows: one haplotype per sequence
+                by_key.setdefault(int(keys[s]), []).append(s)
+            for key, ss in by_key.items():
+                dct[_key_string(key, k)] = ss
+        # rows whose window holds IUPAC cells: every expansion is its own haplotype (rare; replayed on the host copy)
+        for s in np.nonzero(iupac)[0].tolist():
+            wsets = list(self._window_cells(s, pos))
+            is_gap = sum(1 for c in wsets if c == 0) > v
+            for hap in expand_strings(wsets):
+                if is_gap:
+                    groups[2].setdefault(hap, []).append(s)
+                    continue
+                m = 0
+                for i, ch in enumerate(hap):
+                    if ch == "-" or not (sets[i] >> BASES.index(ch)) & 1:
+                        m |= 1 << i
+                if not m:
+                    continue
+                far = bin(m).count("1") > v
+                if far or m & self.fmask:
+                    groups[0].setdefault(hap, []).append(s)
+                if far or m & self.rmask:
+                    groups[1].setdefault(hap, []).append(s)
+        f_dict, r_dict, g_dict = ({hap: [ids[s] for s in sorted(ss)] for hap, ss in dct.items()} for dct in groups)
+        return [f_dict, r_dict], g_dict
+
+    # -- core:1133-1180 -------------------------------------------------------------------------------------
+    def run(self):
+        k = self.primer_length
+        recs = self.design(range(self.start_position, self.stop_position - k))
+        recs.sort(key=lambda r: r["row"][0])
+        with open(self.outfile, "w") as fo:
+            fo.write("\t".join(TSV_HEADER) + "\n")
+            for r in recs:
+                fo.write("\t".join(map(str, r["row"])) + "\n")
+        non_cov = {r["row"][0]: r["non_cov"] for r in recs} if self.sidecars else {}
+        gap_ids = {r["row"][0]: r["gap_ids"] for r in recs} if self.sidecars else {}
+        with open(self.outfile + ".non_coverage_seq_id_json", "w") as fj:
+            json.dump(non_cov, fj, indent=4)
+        with open(self.outfile + ".gap_seq_id_json", "w") as fg:
+            json.dump(gap_ids, fg, indent=4)
+        return recs
+
+    def close(self):
+        self.msa.close()
+        self.ctx.close()
+
+
+# ----------------------------------------------------------------------------------------------------------
+def _default_batch(n_seq: int) -> int:
+    # table bytes per window = 20 * 2^ceil(log2(2n+64)); keep a batch under ~8 GB
+    cap = 1 << max(6, int(math.ceil(math.log2(2 * n_seq + 64))))
+    return max(1, min(4096, int(8e9 // (20 * cap))))
+
+
+def _near_half(x: float) -> bool:
+    """x*100 within 1e-6 of a rounding boundary"""
+    y = x * 100.0
+    return abs((y - math.floor(y)) - 0.5) < 1e-6
+
+
+def _count_gap_digits(x: int, k: int) -> int:
+    n = 0
+    for _ in range(k):
+        n += (x % 5) == 4
+        x //= 5
+    return n
+
+
+def _key_bases(key: int, k: int):
+    """gap-free table key -> base indices"""
+    mask = (1 << k) - 1
+    b0, b1 = key & mask, (key >> k) & mask
+    return [((b0 >> i) & 1) | (((b1 >> i) & 1) << 1) for i in range(k)]
+
+
+def _key_string(key: int, k: int) -> str:
+    if key < _lib.KEY_BASE5:
+        return "".join(BASES[b] for b in _key_bases(key, k))
+    x = key - _lib.KEY_BASE5
+    out = []
+    for _ in range(k):
+        out.append("ACGT-"[x % 5])
+        x //= 5
+    return "".join(out)
+
+
+def self_dimer(sets) -> bool:
+    """core:487-503 dimer_check, by enumeration (replaced by the dimer kernel for degenerate-heavy inputs)"""
+    from .dimer import self_dimer as impl
+    return impl(sets)
+
+
+def main(argv=None):
+    from .cli_core import main as cli_main
+    return cli_main(argv)

@@ -1,0 +1,1086 @@
+// mpb200.cu — libmpb200.so: kernels + C ABI (include/mpb200.h) of the B200 degenerate-primer candidate scan.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC (see build.py)
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "mpb200.h"
+#include "mpb_device.cuh"
+
+// ------------------------------------------------------------------------------------------------------
+// host-side plumbing
+// ------------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return fail(e__ == cudaErrorMemoryAllocation ? MPB_ENOMEM : MPB_ECUDA, "%s:%d %s: %s", \
+                        __FILE__, __LINE__, #call, cudaGetErrorString(e__));                       \
+    } while (0)
+
+struct mpb_ctx {
+    int device;
+    cudaStream_t stream;
+    int64_t launches;
+    int sm_count;
+};
+
+struct mpb_msa {
+    mpb_ctx* ctx;
+    int64_t n_seq, nsp, n_col;
+    int ncw;            // column words incl. the trailing zero word
+    uint32_t* planes;   // [ncw][4][nsp]
+    int32_t* lens;      // [nsp]
+    int* err;           // device error flags
+};
+
+struct mpb_hist {
+    mpb_msa* msa;
+    int k, v, nw, log2cap;
+    uint64_t* keys;   // [nw][cap]
+    uint32_t* cnt;    // [nw][cap]
+    uint64_t* first;  // [nw][cap]
+    int32_t* win_pos; // device copy
+    unsigned long long* gap_n;        // [nw]
+    unsigned long long* iupac_gap_n;  // [nw]
+    int32_t* exc;                     // [2*exc_max]
+    unsigned long long* exc_n;
+    int64_t exc_max;
+};
+
+static bool is_device_ptr(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+// input that may live on host or device: dev() is a device pointer valid on the ctx stream
+struct InBuf {
+    mpb_ctx* ctx;
+    void* tmp = nullptr;
+    const void* d = nullptr;
+    int rc = 0;
+    InBuf(mpb_ctx* c, const void* hd, size_t bytes) : ctx(c) {
+        if (!hd || bytes == 0) return;
+        if (is_device_ptr(hd)) {
+            d = hd;
+            return;
+        }
+        cudaError_t e = cudaMallocAsync(&tmp, bytes, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(tmp, hd, bytes, cudaMemcpyHostToDevice, ctx->stream);
+        if (e != cudaSuccess) rc = fail(MPB_ECUDA, "staging input: %s", cudaGetErrorString(e));
+        d = tmp;
+    }
+    ~InBuf() {
+        if (tmp) cudaFreeAsync(tmp, ctx->stream);
+    }
+    template <class T>
+    const T* dev() const {
+        return (const T*)d;
+    }
+};
+
+// output that may live on host or device; finish() copies back (async) — caller syncs when any output is host
+struct OutBuf {
+    mpb_ctx* ctx;
+    void* tmp = nullptr;
+    void* d = nullptr;
+    void* host = nullptr;
+    size_t bytes;
+    int rc = 0;
+    OutBuf(mpb_ctx* c, void* hd, size_t nbytes) : ctx(c), bytes(nbytes) {
+        if (!hd || nbytes == 0) return;
+        if (is_device_ptr(hd)) {
+            d = hd;
+            return;
+        }
+        host = hd;
+        cudaError_t e = cudaMallocAsync(&tmp, nbytes, ctx->stream);
+        if (e != cudaSuccess) rc = fail(MPB_ENOMEM, "staging output: %s", cudaGetErrorString(e));
+        d = tmp;
+    }
+    ~OutBuf() {
+        if (tmp) cudaFreeAsync(tmp, ctx->stream);
+    }
+    template <class T>
+    T* dev() const {
+        return (T*)d;
+    }
+    bool is_host() const { return host != nullptr; }
+    cudaError_t finish() {
+        if (host) return cudaMemcpyAsync(host, tmp, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+        return cudaSuccess;
+    }
+};
+
+static int check_flags(mpb_ctx* ctx, int* dflags) {
+    int f = 0;
+    CK(cudaMemcpyAsync(&f, dflags, sizeof f, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (f) {
+        int zero = 0;
+        cudaMemcpyAsync(dflags, &zero, sizeof zero, cudaMemcpyHostToDevice, ctx->stream);
+    }
+    if (f & MPB_ERR_TABLE_FULL) return fail(MPB_EOVERFLOW, "haplotype table full: rebuild with a larger log2_cap");
+    if (f & MPB_ERR_EXPAND)
+        return fail(MPB_EEXPAND, "a window of one sequence expands to more than %u haplotypes", MPB_MAX_EXP);
+    if (f & MPB_ERR_SHORT_ROW) return fail(MPB_EEXPAND, "a sequence holds fewer than k bases");
+    return 0;
+}
+
+extern "C" int mpb_abi_version(void) { return MPB_ABI_VERSION; }
+extern "C" const char* mpb_last_error(void) { return g_err.c_str(); }
+extern "C" int mpb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+extern "C" int mpb_ctx_create(int device, mpb_ctx** out) {
+    if (!out) return fail(MPB_EINVAL, "out is NULL");
+    int n = mpb_device_count();
+    if (n == 0) return fail(MPB_ECUDA, "no CUDA device: libmpb200 has no CPU fallback");
+    if (device < 0 || device >= n) return fail(MPB_EINVAL, "device %d out of range (0..%d)", device, n - 1);
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(MPB_ECUDA, "device %d is sm_%d%d; libmpb200 is built for sm_100a only", device,
+                                     prop.major, prop.minor);
+    cudaMemPool_t pool;
+    CK(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t thr = UINT64_MAX;
+    CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    mpb_ctx* c = new mpb_ctx;
+    c->device = device;
+    c->stream = 0;
+    c->launches = 0;
+    c->sm_count = prop.multiProcessorCount;
+    *out = c;
+    return 0;
+}
+extern "C" void mpb_ctx_destroy(mpb_ctx* ctx) { delete ctx; }
+extern "C" int mpb_ctx_set_stream(mpb_ctx* ctx, void* s) {
+    if (!ctx) return fail(MPB_EINVAL, "ctx is NULL");
+    ctx->stream = (cudaStream_t)s;
+    return 0;
+}
+extern "C" int mpb_ctx_sync(mpb_ctx* ctx) {
+    if (!ctx) return fail(MPB_EINVAL, "ctx is NULL");
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+extern "C" int64_t mpb_ctx_launches(mpb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+#define LAUNCH(ctx, kern, grid, block, smem, ...)                   \
+    do {                                                            \
+        kern<<<grid, block, smem, (ctx)->stream>>>(__VA_ARGS__);    \
+        (ctx)->launches++;                                          \
+        CK(cudaGetLastError());                                     \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------------
+// alignment upload: nibble rows -> bit-planes
+// ------------------------------------------------------------------------------------------------------
+// thread = (sequence, column word); sequence fastest so the plane stores coalesce
+__global__ void k_pack_planes(const uint8_t* __restrict__ packed, int64_t n_seq, int64_t nsp, int64_t row_bytes,
+                              int n_col, const int32_t* __restrict__ lens, int ncw, uint32_t* __restrict__ planes) {
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int cw = blockIdx.y;
+    if (s >= nsp) return;
+    uint32_t a = 0, c = 0, g = 0, t = 0;
+    if (s < n_seq && cw < ncw - 1) {
+        int len = lens[s];
+        const uint8_t* row = packed + s * row_bytes;
+        int col0 = cw * 32;
+        for (int i = 0; i < 32; i += 2) {
+            int col = col0 + i;
+            if (col >= len) break;
+            uint32_t b = row[col >> 1];
+            uint32_t x = b & 15u;
+            uint32_t y = (col + 1 < len) ? (b >> 4) : 0u;
+            a |= ((x & 1u) << i) | ((y & 1u) << (i + 1));
+            c |= (((x >> 1) & 1u) << i) | (((y >> 1) & 1u) << (i + 1));
+            g |= (((x >> 2) & 1u) << i) | (((y >> 2) & 1u) << (i + 1));
+            t |= (((x >> 3) & 1u) << i) | (((y >> 3) & 1u) << (i + 1));
+        }
+    }
+    uint32_t* w = planes + ((int64_t)cw * 4) * nsp + s;
+    w[0] = a;
+    w[nsp] = c;
+    w[2 * nsp] = g;
+    w[3 * nsp] = t;
+}
+
+extern "C" int mpb_msa_upload(mpb_ctx* ctx, const uint8_t* packed4, int64_t n_seq, int64_t n_col, int64_t row_bytes,
+                              const int32_t* lens, mpb_msa** out) {
+    if (!ctx || !packed4 || !out) return fail(MPB_EINVAL, "NULL argument");
+    if (n_seq < 1 || n_col < 1 || row_bytes < (n_col + 1) / 2)
+        return fail(MPB_EINVAL, "bad shape n_seq=%lld n_col=%lld row_bytes=%lld", (long long)n_seq, (long long)n_col,
+                    (long long)row_bytes);
+    if (n_seq >= (1ll << 31)) return fail(MPB_EINVAL, "n_seq must be < 2^31");
+    CK(cudaSetDevice(ctx->device));
+    mpb_msa* m = new mpb_msa;
+    m->ctx = ctx;
+    m->n_seq = n_seq;
+    m->nsp = (n_seq + 127) / 128 * 128;
+    m->n_col = n_col;
+    m->ncw = (int)((n_col + 31) / 32) + 1;
+    m->planes = nullptr;
+    m->lens = nullptr;
+    m->err = nullptr;
+    size_t pbytes = (size_t)m->ncw * 4 * m->nsp * sizeof(uint32_t);
+    cudaError_t e = cudaMalloc(&m->planes, pbytes);
+    if (e == cudaSuccess) e = cudaMalloc(&m->lens, m->nsp * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&m->err, sizeof(int));
+    if (e != cudaSuccess) {
+        mpb_msa_free(m);
+        return fail(MPB_ENOMEM, "alignment planes (%zu bytes): %s", pbytes, cudaGetErrorString(e));
+    }
+    CK(cudaMemsetAsync(m->err, 0, sizeof(int), ctx->stream));
+    std::vector<int32_t> hl(m->nsp, 0);
+    for (int64_t i = 0; i < n_seq; ++i) {
+        int32_t l = lens ? lens[i] : (int32_t)n_col;
+        if (l < 0 || l > n_col) {
+            mpb_msa_free(m);
+            return fail(MPB_EINVAL, "lens[%lld]=%d outside 0..n_col", (long long)i, l);
+        }
+        hl[i] = l;
+    }
+    CK(cudaMemcpyAsync(m->lens, hl.data(), m->nsp * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    {
+        InBuf in(ctx, packed4, (size_t)n_seq * row_bytes);
+        if (in.rc) {
+            mpb_msa_free(m);
+            return in.rc;
+        }
+        dim3 grid((unsigned)((m->nsp + 255) / 256), (unsigned)m->ncw);
+        LAUNCH(ctx, k_pack_planes, grid, 256, 0, in.dev<uint8_t>(), n_seq, m->nsp, row_bytes, (int)n_col, m->lens,
+               m->ncw, m->planes);
+        CK(cudaStreamSynchronize(ctx->stream));  // hl / staging lifetime
+    }
+    *out = m;
+    return 0;
+}
+
+extern "C" void mpb_msa_free(mpb_msa* m) {
+    if (!m) return;
+    cudaFree(m->planes);
+    cudaFree(m->lens);
+    cudaFree(m->err);
+    delete m;
+}
+extern "C" int64_t mpb_msa_nseq(const mpb_msa* m) { return m ? m->n_seq : 0; }
+
+// core:625-627: leading gap count and length without trailing gaps, per sequence
+__global__ void k_seq_attr(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq, const int32_t* __restrict__ lens,
+                           int ncw, int32_t* __restrict__ lead, int32_t* __restrict__ rstrip) {
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_seq) return;
+    int len = lens[s];
+    int first = -1, last = -1;
+    for (int cw = 0; cw < ncw - 1; ++cw) {
+        const uint32_t* w = pl + ((int64_t)cw * 4) * nsp + s;
+        uint32_t any = w[0] | w[nsp] | w[2 * nsp] | w[3 * nsp];
+        if (any) {
+            if (first < 0) first = cw * 32 + __ffs(any) - 1;
+            last = cw * 32 + 31 - __clz(any);
+        }
+    }
+    lead[s] = first < 0 ? len : first;
+    rstrip[s] = last + 1;
+}
+
+extern "C" int mpb_seq_attr(mpb_msa* m, int32_t* lead_hd, int32_t* rstrip_hd) {
+    if (!m || !lead_hd || !rstrip_hd) return fail(MPB_EINVAL, "NULL argument");
+    mpb_ctx* ctx = m->ctx;
+    CK(cudaSetDevice(ctx->device));
+    OutBuf lead(ctx, lead_hd, m->n_seq * sizeof(int32_t)), rs(ctx, rstrip_hd, m->n_seq * sizeof(int32_t));
+    if (lead.rc || rs.rc) return lead.rc ? lead.rc : rs.rc;
+    LAUNCH(ctx, k_seq_attr, (unsigned)((m->n_seq + 255) / 256), 256, 0, m->planes, m->nsp, m->n_seq, m->lens, m->ncw,
+           lead.dev<int32_t>(), rs.dev<int32_t>());
+    CK(lead.finish());
+    CK(rs.finish());
+    if (lead.is_host() || rs.is_host()) CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// window haplotype tables
+// ------------------------------------------------------------------------------------------------------
+#define HIST_THREADS 256
+
+// thread = sequence; blockIdx.y strides over the windows of the batch
+__global__ void __launch_bounds__(HIST_THREADS)
+k_hist(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq, const int32_t* __restrict__ lens, int k, int v,
+       const int32_t* __restrict__ win_pos, int nw, uint64_t* __restrict__ keys, uint32_t* __restrict__ cnt,
+       uint64_t* __restrict__ first, int log2cap, unsigned long long* __restrict__ gap_n,
+       unsigned long long* __restrict__ iupac_gap_n, int32_t* __restrict__ exc, unsigned long long* __restrict__ exc_n,
+       long long exc_max, int* __restrict__ err) {
+    const int64_t s = (int64_t)blockIdx.x * HIST_THREADS + threadIdx.x;
+    const bool valid = s < n_seq;
+    const int lane = threadIdx.x & 31;
+    const uint32_t kmask = (k == 32) ? 0xFFFFFFFFu : ((1u << k) - 1u);
+    const int len = valid ? lens[s] : 0;
+    const uint64_t cap = 1ull << log2cap;
+    for (int wi = blockIdx.y; wi < nw; wi += gridDim.y) {
+        const int p = win_pos[wi];
+        Win w;
+        w.a = w.c = w.g = w.t = w.multi = 0;
+        w.gapv = kmask;
+        bool ok = true;
+        if (valid) ok = mpb_load_window(pl, nsp, s, len, p, k, kmask, w);
+        if (!ok) atomicOr(err, MPB_ERR_SHORT_ROW);
+        const int ngap = __popc(w.gapv);
+        const bool isgap = valid && ngap > v;
+        const bool cover = valid && !isgap;
+        const unsigned gb = __ballot_sync(0xffffffffu, isgap);
+        if (lane == 0 && gb) atomicAdd(&gap_n[wi], (unsigned long long)__popc(gb));
+        uint64_t* K = keys + (uint64_t)wi * cap;
+        uint32_t* C = cnt + (uint64_t)wi * cap;
+        uint64_t* F = first + (uint64_t)wi * cap;
+        const bool simple = cover && w.multi == 0;
+        const unsigned smask = __ballot_sync(0xffffffffu, simple);
+        if (simple) {
+            const uint64_t key = mpb_key(w.c, w.g, w.t, w.gapv, k);
+            const unsigned peers = __match_any_sync(smask, key);
+            if (lane == __ffs(peers) - 1)  // lowest lane = lowest sequence index = first seen
+                mpb_table_add(K, C, F, log2cap, key, (uint32_t)__popc(peers), (uint64_t)s << 16, err);
+        } else if (cover) {
+            const uint32_t total = mpb_expansions(w);
+            if (total > MPB_MAX_EXP) {
+                atomicOr(err, MPB_ERR_EXPAND);
+            } else {
+                for (uint32_t e = 0; e < total; ++e) {
+                    uint32_t a, c, g, t;
+                    mpb_expand(w, e, a, c, g, t);
+                    mpb_table_add(K, C, F, log2cap, mpb_key(c, g, t, w.gapv, k), 1u, ((uint64_t)s << 16) | e, err);
+                }
+            }
+        } else if (isgap) {
+            if (w.multi == 0) {
+                mpb_table_add(K, C, F, log2cap, mpb_key(w.c, w.g, w.t, w.gapv, k), 1u, (uint64_t)s << 16, err);
+            } else {
+                atomicAdd(&iupac_gap_n[wi], 1ull);
+                unsigned long long slot = atomicAdd(exc_n, 1ull);
+                if ((long long)slot < exc_max) {
+                    exc[2 * slot] = wi;
+                    exc[2 * slot + 1] = (int32_t)s;
+                }
+            }
+        }
+    }
+}
+
+extern "C" int mpb_hist_build(mpb_msa* m, int k, int v, const int32_t* win_pos, int32_t nw, int log2_cap,
+                              mpb_hist** out) {
+    if (!m || !win_pos || !out) return fail(MPB_EINVAL, "NULL argument");
+    if (k < 3 || k > MPB_MAX_K) return fail(MPB_EINVAL, "primer length %d outside 3..%d", k, MPB_MAX_K);
+    if (v < 0 || nw < 1) return fail(MPB_EINVAL, "bad v=%d or nw=%d", v, nw);
+    for (int i = 0; i < nw; ++i)
+        if (win_pos[i] < 0 || win_pos[i] >= m->n_col)
+            return fail(MPB_EINVAL, "win_pos[%d]=%d outside the alignment", i, win_pos[i]);
+    mpb_ctx* ctx = m->ctx;
+    CK(cudaSetDevice(ctx->device));
+    if (log2_cap <= 0) {
+        log2_cap = 6;
+        while ((1ll << log2_cap) < 2 * m->n_seq + 64) ++log2_cap;
+    }
+    if (log2_cap > 31) return fail(MPB_EINVAL, "log2_cap %d too large", log2_cap);
+    mpb_hist* h = new mpb_hist;
+    memset(h, 0, sizeof *h);
+    h->msa = m;
+    h->k = k;
+    h->v = v;
+    h->nw = nw;
+    h->log2cap = log2_cap;
+    h->exc_max = 1 << 20;
+    const uint64_t slots = (uint64_t)nw << log2_cap;
+    cudaError_t e = cudaMallocAsync(&h->keys, slots * 8, ctx->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&h->cnt, slots * 4, ctx->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&h->first, slots * 8, ctx->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&h->win_pos, (size_t)nw * 4, ctx->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&h->gap_n, (size_t)nw * 8, ctx->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&h->iupac_gap_n, (size_t)nw * 8, ctx->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&h->exc, (size_t)h->exc_max * 8, ctx->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&h->exc_n, 8, ctx->stream);
+    if (e != cudaSuccess) {
+        mpb_hist_free(h);
+        return fail(MPB_ENOMEM, "haplotype tables (%d windows x 2^%d slots): %s", nw, log2_cap, cudaGetErrorString(e));
+    }
+    CK(cudaMemsetAsync(h->keys, 0xFF, slots * 8, ctx->stream));
+    CK(cudaMemsetAsync(h->cnt, 0, slots * 4, ctx->stream));
+    CK(cudaMemsetAsync(h->first, 0xFF, slots * 8, ctx->stream));
+    CK(cudaMemsetAsync(h->gap_n, 0, (size_t)nw * 8, ctx->stream));
+    CK(cudaMemsetAsync(h->iupac_gap_n, 0, (size_t)nw * 8, ctx->stream));
+    CK(cudaMemsetAsync(h->exc_n, 0, 8, ctx->stream));
+    CK(cudaMemcpyAsync(h->win_pos, win_pos, (size_t)nw * 4, cudaMemcpyHostToDevice, ctx->stream));
+    const unsigned gx = (unsigned)((m->n_seq + HIST_THREADS - 1) / HIST_THREADS);
+    unsigned gy = (unsigned)nw;
+    const unsigned want = (unsigned)ctx->sm_count * 8;
+    if (gx >= want) gy = 1;
+    else if (gy > (want + gx - 1) / gx) gy = (want + gx - 1) / gx;
+    LAUNCH(ctx, k_hist, dim3(gx, gy), HIST_THREADS, 0, m->planes, m->nsp, m->n_seq, m->lens, k, v, h->win_pos, nw,
+           h->keys, h->cnt, h->first, log2_cap, h->gap_n, h->iupac_gap_n, h->exc, h->exc_n, (long long)h->exc_max,
+           m->err);
+    int rc = check_flags(ctx, m->err);  // also makes the host win_pos copy safe to release
+    if (rc) {
+        mpb_hist_free(h);
+        return rc;
+    }
+    *out = h;
+    return 0;
+}
+
+extern "C" void mpb_hist_free(mpb_hist* h) {
+    if (!h) return;
+    cudaStream_t st = h->msa->ctx->stream;
+    if (h->keys) cudaFreeAsync(h->keys, st);
+    if (h->cnt) cudaFreeAsync(h->cnt, st);
+    if (h->first) cudaFreeAsync(h->first, st);
+    if (h->win_pos) cudaFreeAsync(h->win_pos, st);
+    if (h->gap_n) cudaFreeAsync(h->gap_n, st);
+    if (h->iupac_gap_n) cudaFreeAsync(h->iupac_gap_n, st);
+    if (h->exc) cudaFreeAsync(h->exc, st);
+    if (h->exc_n) cudaFreeAsync(h->exc_n, st);
+    delete h;
+}
+
+__global__ void k_hist_merge(const long long* __restrict__ win_off, int nw, const uint64_t* __restrict__ in_keys,
+                             const uint32_t* __restrict__ in_cnt, const uint64_t* __restrict__ in_first,
+                             uint64_t* __restrict__ keys, uint32_t* __restrict__ cnt, uint64_t* __restrict__ first,
+                             int log2cap, int* __restrict__ err) {
+    const long long total = win_off[nw];
+    const uint64_t cap = 1ull << log2cap;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int lo = 0, hi = nw;  // largest w with win_off[w] <= i
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (win_off[mid] <= i) lo = mid;
+            else hi = mid;
+        }
+        mpb_table_add(keys + (uint64_t)lo * cap, cnt + (uint64_t)lo * cap, first + (uint64_t)lo * cap, log2cap,
+                      in_keys[i], in_cnt[i], in_first[i], err);
+    }
+}
+
+extern "C" int mpb_hist_merge(mpb_hist* h, const int64_t* win_off, const uint64_t* keys_hd, const uint32_t* cnt_hd,
+                              const uint64_t* first_hd) {
+    if (!h || !win_off || !keys_hd || !cnt_hd || !first_hd) return fail(MPB_EINVAL, "NULL argument");
+    mpb_ctx* ctx = h->msa->ctx;
+    CK(cudaSetDevice(ctx->device));
+    const int64_t total = win_off[h->nw];
+    if (total <= 0) return 0;
+    InBuf off(ctx, win_off, (size_t)(h->nw + 1) * 8), ik(ctx, keys_hd, total * 8), ic(ctx, cnt_hd, total * 4),
+        ifr(ctx, first_hd, total * 8);
+    if (off.rc || ik.rc || ic.rc || ifr.rc) return MPB_ECUDA;
+    unsigned grid = (unsigned)((total + 255) / 256);
+    if (grid > (unsigned)ctx->sm_count * 16) grid = ctx->sm_count * 16;
+    LAUNCH(ctx, k_hist_merge, grid, 256, 0, off.dev<long long>(), h->nw, ik.dev<uint64_t>(), ic.dev<uint32_t>(),
+           ifr.dev<uint64_t>(), h->keys, h->cnt, h->first, h->log2cap, h->msa->err);
+    return check_flags(ctx, h->msa->err);
+}
+
+// one block per window: entropy ingredients, distinct counts, most frequent gap-free haplotype
+#define STATS_THREADS 256
+struct Best {
+    unsigned long long cnt, first, key;
+};
+__device__ __forceinline__ bool better(const Best& x, const Best& y) {  // x beats y
+    return x.cnt > y.cnt || (x.cnt == y.cnt && x.first < y.first);
+}
+
+__global__ void __launch_bounds__(STATS_THREADS)
+k_hist_stats(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ cnt, const uint64_t* __restrict__ first,
+             int log2cap, int k, int v, double* __restrict__ ent, long long* __restrict__ nuniq,
+             unsigned long long* __restrict__ mm_key, long long* __restrict__ mm_cnt,
+             unsigned long long* __restrict__ mm_first) {
+    const int wi = blockIdx.x;
+    const uint64_t cap = 1ull << log2cap;
+    const uint64_t* K = keys + (uint64_t)wi * cap;
+    const uint32_t* C = cnt + (uint64_t)wi * cap;
+    const uint64_t* F = first + (uint64_t)wi * cap;
+    double s0c = 0, s1c = 0, s0g = 0, s1g = 0;
+    long long nc = 0, ng = 0, ngf = 0;
+    Best best = {0ull, ~0ull, MPB_KEY_EMPTY_D};
+    for (uint64_t i = threadIdx.x; i < cap; i += STATS_THREADS) {
+        const uint64_t key = K[i];
+        if (key == MPB_KEY_EMPTY_D) continue;
+        const double c = (double)C[i];
+        bool is_cover = true;
+        if (key >= MPB_KEY_BASE5_D) {
+            uint64_t x = key - MPB_KEY_BASE5_D;
+            int gaps = 0;
+            for (int j = 0; j < k; ++j) {
+                gaps += (x % 5ull) == 4ull;
+                x /= 5ull;
+            }
+            is_cover = gaps <= v;
+        } else {
+            ++ngf;
+            Best b = {(unsigned long long)C[i], F[i], key};
+            if (better(b, best)) best = b;
+        }
+        if (is_cover) {
+            s0c += c;
+            s1c += c * log2(c);
+            ++nc;
+        } else {
+            s0g += c;
+            s1g += c * log2(c);
+            ++ng;
+        }
+    }
+    __shared__ double sd[4][STATS_THREADS / 32];
+    __shared__ long long sl[3][STATS_THREADS / 32];
+    __shared__ Best sb[STATS_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int o = 16; o > 0; o >>= 1) {
+        s0c += __shfl_xor_sync(0xffffffffu, s0c, o);
+        s1c += __shfl_xor_sync(0xffffffffu, s1c, o);
+        s0g += __shfl_xor_sync(0xffffffffu, s0g, o);
+        s1g += __shfl_xor_sync(0xffffffffu, s1g, o);
+        nc += __shfl_xor_sync(0xffffffffu, nc, o);
+        ng += __shfl_xor_sync(0xffffffffu, ng, o);
+        ngf += __shfl_xor_sync(0xffffffffu, ngf, o);
+        Best ob;
+        ob.cnt = __shfl_xor_sync(0xffffffffu, best.cnt, o);
+        ob.first = __shfl_xor_sync(0xffffffffu, best.first, o);
+        ob.key = __shfl_xor_sync(0xffffffffu, best.key, o);
+        if (better(ob, best)) best = ob;
+    }
+    if (lane == 0) {
+        sd[0][warp] = s0c;
+        sd[1][warp] = s1c;
+        sd[2][warp] = s0g;
+        sd[3][warp] = s1g;
+        sl[0][warp] = nc;
+        sl[1][warp] = ng;
+        sl[2][warp] = ngf;
+        sb[warp] = best;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < STATS_THREADS / 32; ++w) {
+            sd[0][0] += sd[0][w];
+            sd[1][0] += sd[1][w];
+            sd[2][0] += sd[2][w];
+            sd[3][0] += sd[3][w];
+            sl[0][0] += sl[0][w];
+            sl[1][0] += sl[1][w];
+            sl[2][0] += sl[2][w];
+            if (better(sb[w], sb[0])) sb[0] = sb[w];
+        }
+        if (ent) {
+            ent[wi * 4 + 0] = sd[0][0];
+            ent[wi * 4 + 1] = sd[1][0];
+            ent[wi * 4 + 2] = sd[2][0];
+            ent[wi * 4 + 3] = sd[3][0];
+        }
+        if (nuniq) {
+            nuniq[wi * 3 + 0] = sl[0][0];
+            nuniq[wi * 3 + 1] = sl[1][0];
+            nuniq[wi * 3 + 2] = sl[2][0];
+        }
+        if (mm_key) mm_key[wi] = sb[0].key;
+        if (mm_cnt) mm_cnt[wi] = (long long)sb[0].cnt;
+        if (mm_first) mm_first[wi] = sb[0].first;
+    }
+}
+
+extern "C" int mpb_hist_stats(mpb_hist* h, int64_t* gap_n, double* ent, int64_t* nuniq, uint64_t* mm_key,
+                              int64_t* mm_cnt, uint64_t* mm_first, int64_t* n_iupac_gap) {
+    if (!h) return fail(MPB_EINVAL, "NULL argument");
+    mpb_ctx* ctx = h->msa->ctx;
+    CK(cudaSetDevice(ctx->device));
+    const size_t nw = h->nw;
+    OutBuf o_ent(ctx, ent, nw * 4 * 8), o_nu(ctx, nuniq, nw * 3 * 8), o_mk(ctx, mm_key, nw * 8), o_mc(ctx, mm_cnt, nw * 8),
+        o_mf(ctx, mm_first, nw * 8);
+    if (o_ent.rc || o_nu.rc || o_mk.rc || o_mc.rc || o_mf.rc) return MPB_ENOMEM;
+    LAUNCH(ctx, k_hist_stats, (unsigned)nw, STATS_THREADS, 0, h->keys, h->cnt, h->first, h->log2cap, h->k, h->v,
+           o_ent.dev<double>(), o_nu.dev<long long>(), o_mk.dev<unsigned long long>(), o_mc.dev<long long>(),
+           o_mf.dev<unsigned long long>());
+    CK(o_ent.finish());
+    CK(o_nu.finish());
+    CK(o_mk.finish());
+    CK(o_mc.finish());
+    CK(o_mf.finish());
+    bool sync = o_ent.is_host() || o_nu.is_host() || o_mk.is_host() || o_mc.is_host() || o_mf.is_host();
+    if (gap_n) {
+        const bool dev = is_device_ptr(gap_n);
+        CK(cudaMemcpyAsync(gap_n, h->gap_n, nw * 8, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
+        sync = sync || !dev;
+    }
+    if (n_iupac_gap) {
+        const bool dev = is_device_ptr(n_iupac_gap);
+        CK(cudaMemcpyAsync(n_iupac_gap, h->iupac_gap_n, nw * 8, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                           ctx->stream));
+        sync = sync || !dev;
+    }
+    if (sync) CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// one block per selected window: base counts per column and dinucleotide counts per junction, weighted by the
+// haplotype counts (core:541-577 restated over the table instead of over a pandas frame of expansion rows)
+#define TENS_THREADS 256
+__global__ void __launch_bounds__(TENS_THREADS)
+k_hist_tensors(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ cnt, int log2cap, int k, int v,
+               const int32_t* __restrict__ sel_idx, long long* __restrict__ freq, long long* __restrict__ nn) {
+    __shared__ unsigned long long s_freq[4 * MPB_MAX_K];
+    __shared__ unsigned long long s_nn[(MPB_MAX_K - 1) * 16];
+    const int wi = sel_idx[blockIdx.x];
+    const uint64_t cap = 1ull << log2cap;
+    const uint64_t* K = keys + (uint64_t)wi * cap;
+    const uint32_t* C = cnt + (uint64_t)wi * cap;
+    const uint32_t kmask = (1u << k) - 1u;
+    for (int i = threadIdx.x; i < 4 * k; i += TENS_THREADS) s_freq[i] = 0;
+    for (int i = threadIdx.x; i < (k - 1) * 16; i += TENS_THREADS) s_nn[i] = 0;
+    __syncthreads();
+    for (uint64_t i = threadIdx.x; i < cap; i += TENS_THREADS) {
+        const uint64_t key = K[i];
+        if (key == MPB_KEY_EMPTY_D) continue;
+        uint32_t a, c, g, t, gapv;
+        mpb_key_planes(key, k, kmask, a, c, g, t, gapv);
+        if (__popc(gapv) > v) continue;  // gap k-mer, not a cover haplotype
+        const unsigned long long n = C[i];
+        int prev = -1;
+        for (int j = 0; j < k; ++j) {
+            int d = ((gapv >> j) & 1u) ? -1 : (int)(((c >> j) & 1u) + 2u * ((g >> j) & 1u) + 3u * ((t >> j) & 1u));
+            if (d >= 0) atomicAdd(&s_freq[d * k + j], n);
+            if (j > 0 && d >= 0 && prev >= 0) atomicAdd(&s_nn[(j - 1) * 16 + prev * 4 + d], n);
+            prev = d;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 4 * k; i += TENS_THREADS) freq[(long long)wi * 4 * k + i] = (long long)s_freq[i];
+    for (int i = threadIdx.x; i < (k - 1) * 16; i += TENS_THREADS)
+        nn[(long long)wi * (k - 1) * 16 + i] = (long long)s_nn[i];
+}
+
+extern "C" int mpb_hist_tensors(mpb_hist* h, const uint8_t* sel, int64_t* freq_hd, int64_t* nn_hd) {
+    if (!h || !sel || !freq_hd || !nn_hd) return fail(MPB_EINVAL, "NULL argument");
+    mpb_ctx* ctx = h->msa->ctx;
+    CK(cudaSetDevice(ctx->device));
+    std::vector<int32_t> idx;
+    for (int i = 0; i < h->nw; ++i)
+        if (sel[i]) idx.push_back(i);
+    const size_t fb = (size_t)h->nw * 4 * h->k * 8, nb = (size_t)h->nw * (h->k - 1) * 16 * 8;
+    OutBuf of(ctx, freq_hd, fb), on(ctx, nn_hd, nb);
+    if (of.rc || on.rc) return MPB_ENOMEM;
+    CK(cudaMemsetAsync(of.d, 0, fb, ctx->stream));
+    CK(cudaMemsetAsync(on.d, 0, nb, ctx->stream));
+    if (!idx.empty()) {
+        InBuf si(ctx, idx.data(), idx.size() * 4);
+        if (si.rc) return si.rc;
+        LAUNCH(ctx, k_hist_tensors, (unsigned)idx.size(), TENS_THREADS, 0, h->keys, h->cnt, h->log2cap, h->k, h->v,
+               si.dev<int32_t>(), of.dev<long long>(), on.dev<long long>());
+        CK(of.finish());
+        CK(on.finish());
+        CK(cudaStreamSynchronize(ctx->stream));  // idx lifetime
+        return 0;
+    }
+    CK(of.finish());
+    CK(on.finish());
+    if (of.is_host() || on.is_host()) CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+__global__ void k_hist_dump(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ cnt,
+                            const uint64_t* __restrict__ first, int log2cap, int wi, long long max_n,
+                            uint64_t* __restrict__ ok, uint32_t* __restrict__ oc, uint64_t* __restrict__ of,
+                            unsigned long long* __restrict__ n_out) {
+    const uint64_t cap = 1ull << log2cap;
+    const uint64_t* K = keys + (uint64_t)wi * cap;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t key = K[i];
+        if (key == MPB_KEY_EMPTY_D) continue;
+        unsigned long long slot = atomicAdd(n_out, 1ull);
+        if ((long long)slot < max_n) {
+            ok[slot] = key;
+            oc[slot] = cnt[(uint64_t)wi * cap + i];
+            of[slot] = first[(uint64_t)wi * cap + i];
+        }
+    }
+}
+
+extern "C" int mpb_hist_dump(mpb_hist* h, int32_t w, int64_t max_n, uint64_t* keys_hd, uint32_t* cnt_hd,
+                             uint64_t* first_hd, int64_t* n_out) {
+    if (!h || !keys_hd || !cnt_hd || !first_hd || !n_out) return fail(MPB_EINVAL, "NULL argument");
+    if (w < 0 || w >= h->nw || max_n < 0) return fail(MPB_EINVAL, "window %d outside the batch", w);
+    mpb_ctx* ctx = h->msa->ctx;
+    CK(cudaSetDevice(ctx->device));
+    OutBuf ok(ctx, keys_hd, max_n * 8), oc(ctx, cnt_hd, max_n * 4), of(ctx, first_hd, max_n * 8);
+    if (ok.rc || oc.rc || of.rc) return MPB_ENOMEM;
+    unsigned long long* dn;
+    CK(cudaMallocAsync(&dn, 8, ctx->stream));
+    CK(cudaMemsetAsync(dn, 0, 8, ctx->stream));
+    const uint64_t cap = 1ull << h->log2cap;
+    unsigned grid = (unsigned)((cap + 255) / 256);
+    if (grid > (unsigned)ctx->sm_count * 8) grid = ctx->sm_count * 8;
+    LAUNCH(ctx, k_hist_dump, grid, 256, 0, h->keys, h->cnt, h->first, h->log2cap, (int)w, (long long)max_n,
+           ok.dev<uint64_t>(), oc.dev<uint32_t>(), of.dev<uint64_t>(), dn);
+    unsigned long long n = 0;
+    CK(cudaMemcpyAsync(&n, dn, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ok.finish());
+    CK(oc.finish());
+    CK(of.finish());
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaFreeAsync(dn, ctx->stream));
+    *n_out = (int64_t)n;
+    return 0;
+}
+
+// one block per query: distinct gap-free table entries matched exactly by a degenerate pattern
+__global__ void __launch_bounds__(256)
+k_hist_match(const uint64_t* __restrict__ keys, int log2cap, int k, const int32_t* __restrict__ q_win,
+             const uint32_t* __restrict__ q_allow, long long* __restrict__ out) {
+    const int q = blockIdx.x;
+    const uint64_t cap = 1ull << log2cap;
+    const uint64_t* K = keys + (uint64_t)q_win[q] * cap;
+    const uint32_t kmask = (1u << k) - 1u;
+    const uint32_t na = ~q_allow[q * 4 + 0] & kmask, ncm = ~q_allow[q * 4 + 1] & kmask, ngm = ~q_allow[q * 4 + 2] & kmask,
+                   nt = ~q_allow[q * 4 + 3] & kmask;
+    unsigned n = 0;
+    for (uint64_t i = threadIdx.x; i < cap; i += 256) {
+        const uint64_t key = K[i];
+        if (key >= MPB_KEY_BASE5_D) continue;  // empty, or a k-mer with gaps (never an expansion of a primer)
+        uint32_t a, c, g, t, gapv;
+        mpb_key_planes(key, k, kmask, a, c, g, t, gapv);
+        n += ((a & na) | (c & ncm) | (g & ngm) | (t & nt)) == 0u;
+    }
+    __shared__ unsigned sn[8];
+    n = __reduce_add_sync(0xffffffffu, n);
+    if ((threadIdx.x & 31) == 0) sn[threadIdx.x >> 5] = n;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned tot = 0;
+        for (int w = 0; w < 8; ++w) tot += sn[w];
+        out[q] = tot;
+    }
+}
+
+extern "C" int mpb_hist_match(mpb_hist* h, const int32_t* q_win, const uint32_t* q_allow, int32_t nq,
+                              int64_t* distinct_hd) {
+    if (!h || !q_win || !q_allow || !distinct_hd) return fail(MPB_EINVAL, "NULL argument");
+    if (nq < 1) return 0;
+    if (!is_device_ptr(q_win))
+        for (int i = 0; i < nq; ++i)
+            if (q_win[i] < 0 || q_win[i] >= h->nw) return fail(MPB_EINVAL, "q_win[%d]=%d outside the batch", i, q_win[i]);
+    mpb_ctx* ctx = h->msa->ctx;
+    CK(cudaSetDevice(ctx->device));
+    InBuf qw(ctx, q_win, (size_t)nq * 4), qa(ctx, q_allow, (size_t)nq * 16);
+    OutBuf o(ctx, distinct_hd, (size_t)nq * 8);
+    if (qw.rc || qa.rc || o.rc) return MPB_ECUDA;
+    LAUNCH(ctx, k_hist_match, (unsigned)nq, 256, 0, h->keys, h->log2cap, h->k, qw.dev<int32_t>(), qa.dev<uint32_t>(),
+           o.dev<long long>());
+    CK(o.finish());
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int mpb_hist_exceptions(mpb_hist* h, int64_t max_n, int32_t* win_idx, int32_t* seq_idx, int64_t* n_out) {
+    if (!h || !n_out) return fail(MPB_EINVAL, "NULL argument");
+    mpb_ctx* ctx = h->msa->ctx;
+    CK(cudaSetDevice(ctx->device));
+    unsigned long long n = 0;
+    CK(cudaMemcpyAsync(&n, h->exc_n, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if ((int64_t)n > h->exc_max) return fail(MPB_EOVERFLOW, "more than %lld IUPAC gap rows in one batch", (long long)h->exc_max);
+    *n_out = (int64_t)n;
+    int64_t take = (int64_t)n < max_n ? (int64_t)n : max_n;
+    if (take > 0 && win_idx && seq_idx) {
+        std::vector<int32_t> tmp(2 * take);
+        CK(cudaMemcpyAsync(tmp.data(), h->exc, take * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (int64_t i = 0; i < take; ++i) {
+            win_idx[i] = tmp[2 * i];
+            seq_idx[i] = tmp[2 * i + 1];
+        }
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// the candidate scan (mis_primer_check, core:1103-1130)
+// ------------------------------------------------------------------------------------------------------
+#define SCAN_THREADS 256
+#define SCAN_GROUP 128  // candidates per blockIdx.y
+
+// thread = sequence (blockIdx.x tiles the sequences), blockIdx.y = group of SCAN_GROUP candidates sorted by
+// window, so consecutive candidates mostly reuse the window already held in registers.
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_scan(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq, const int32_t* __restrict__ lens, int k, int v,
+       uint32_t fmask, uint32_t rmask, const int32_t* __restrict__ cand_pos, const uint32_t* __restrict__ cand_allow,
+       long long nc, unsigned long long* __restrict__ counts, const int32_t* __restrict__ bits_slot,
+       uint32_t* __restrict__ bits, long long words, int* __restrict__ err) {
+    __shared__ uint32_t s_nmask[SCAN_GROUP][4];
+    __shared__ int32_t s_pos[SCAN_GROUP];
+    __shared__ int32_t s_slot[SCAN_GROUP];
+    __shared__ unsigned int s_cnt[SCAN_GROUP][3];
+    const long long c0 = (long long)blockIdx.y * SCAN_GROUP;
+    const int ng = (int)((nc - c0) < SCAN_GROUP ? (nc - c0) : SCAN_GROUP);
+    const uint32_t kmask = (1u << k) - 1u;
+    for (int i = threadIdx.x; i < ng; i += SCAN_THREADS) {
+        s_pos[i] = cand_pos[c0 + i];
+        s_slot[i] = bits_slot ? bits_slot[c0 + i] : -1;
+        for (int b = 0; b < 4; ++b) s_nmask[i][b] = ~cand_allow[(c0 + i) * 4 + b] & kmask;
+        s_cnt[i][0] = s_cnt[i][1] = s_cnt[i][2] = 0;
+    }
+    __syncthreads();
+    const int64_t s = (int64_t)blockIdx.x * SCAN_THREADS + threadIdx.x;
+    const bool valid = s < n_seq;
+    const int lane = threadIdx.x & 31;
+    const int len = valid ? lens[s] : 0;
+    int cur_pos = -1;
+    Win w;
+    w.a = w.c = w.g = w.t = w.multi = 0;
+    w.gapv = kmask;
+    bool cover = false, isgap = false;
+    uint32_t nexp = 1;
+    for (int ci = 0; ci < ng; ++ci) {
+        const int p = s_pos[ci];
+        if (p != cur_pos) {  // uniform across the block
+            cur_pos = p;
+            if (valid) {
+                if (!mpb_load_window(pl, nsp, s, len, p, k, kmask, w)) atomicOr(err, MPB_ERR_SHORT_ROW);
+                isgap = __popc(w.gapv) > v;
+                cover = !isgap;
+                nexp = 1;
+                if (cover && w.multi) {
+                    nexp = mpb_expansions(w);
+                    if (nexp > MPB_MAX_EXP) {
+                        atomicOr(err, MPB_ERR_EXPAND);
+                        nexp = 1;
+                    }
+                }
+            }
+        }
+        const uint32_t nA = s_nmask[ci][0], nC = s_nmask[ci][1], nG = s_nmask[ci][2], nT = s_nmask[ci][3];
+        unsigned n0 = 0, nf = 0, nr = 0;
+        bool non_f = false, non_r = false;
+        if (cover) {
+            if (w.multi == 0) {
+                const uint32_t mis = w.gapv | (w.a & nA) | (w.c & nC) | (w.g & nG) | (w.t & nT);
+                const bool within = __popc(mis) <= v;
+                const bool z = mis == 0u;
+                const bool okf = within && (mis & fmask) == 0u;
+                const bool okr = within && (mis & rmask) == 0u;
+                n0 = z;
+                nf = okf && !z;
+                nr = okr && !z;
+                non_f = !okf;
+                non_r = !okr;
+            } else {
+                for (uint32_t e = 0; e < nexp; ++e) {
+                    uint32_t a, c, g, t;
+                    mpb_expand(w, e, a, c, g, t);
+                    const uint32_t mis = w.gapv | (a & nA) | (c & nC) | (g & nG) | (t & nT);
+                    const bool within = __popc(mis) <= v;
+                    const bool z = mis == 0u;
+                    const bool okf = within && (mis & fmask) == 0u;
+                    const bool okr = within && (mis & rmask) == 0u;
+                    n0 += z;
+                    nf += okf && !z;
+                    nr += okr && !z;
+                    non_f = non_f || !okf;
+                    non_r = non_r || !okr;
+                }
+            }
+        }
+        n0 = __reduce_add_sync(0xffffffffu, n0);
+        nf = __reduce_add_sync(0xffffffffu, nf);
+        nr = __reduce_add_sync(0xffffffffu, nr);
+        if (lane == 0) {
+            if (n0) atomicAdd(&s_cnt[ci][0], n0);
+            if (nf) atomicAdd(&s_cnt[ci][1], nf);
+            if (nr) atomicAdd(&s_cnt[ci][2], nr);
+        }
+        const int slot = s_slot[ci];
+        if (slot >= 0) {  // uniform
+            const unsigned bf = __ballot_sync(0xffffffffu, non_f);
+            const unsigned br = __ballot_sync(0xffffffffu, non_r);
+            const unsigned bg = __ballot_sync(0xffffffffu, valid && isgap);
+            const long long word = (long long)blockIdx.x * (SCAN_THREADS / 32) + (threadIdx.x >> 5);
+            if (lane == 0 && word < words) {
+                uint32_t* o = bits + (long long)slot * 3 * words;
+                o[word] = bf;
+                o[words + word] = br;
+                o[2 * words + word] = bg;
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < ng * 3; i += SCAN_THREADS) {
+        unsigned int x = s_cnt[i / 3][i % 3];
+        if (x) atomicAdd(&counts[(c0 + i / 3) * 3 + i % 3], (unsigned long long)x);
+    }
+}
+
+extern "C" int mpb_scan(mpb_msa* m, int k, int v, uint32_t fmask, uint32_t rmask, const int32_t* cand_pos_hd,
+                        const uint32_t* cand_allow_hd, int64_t nc, int64_t* counts_hd, const int32_t* bits_slot,
+                        uint32_t* bits_hd) {
+    if (!m || !cand_pos_hd || !cand_allow_hd || !counts_hd) return fail(MPB_EINVAL, "NULL argument");
+    if (k < 3 || k > MPB_MAX_K) return fail(MPB_EINVAL, "primer length %d outside 3..%d", k, MPB_MAX_K);
+    if (nc < 1) return 0;
+    if (bits_slot && !bits_hd) return fail(MPB_EINVAL, "bits_slot without bits");
+    mpb_ctx* ctx = m->ctx;
+    CK(cudaSetDevice(ctx->device));
+    const long long words = (m->n_seq + 31) / 32;
+    int nslots = 0;
+    if (bits_slot)
+        for (int64_t i = 0; i < nc; ++i)
+            if (bits_slot[i] >= nslots) nslots = bits_slot[i] + 1;
+    if (!is_device_ptr(cand_pos_hd))
+        for (int64_t i = 0; i < nc; ++i)
+            if (cand_pos_hd[i] < 0 || cand_pos_hd[i] >= m->n_col)
+                return fail(MPB_EINVAL, "cand_pos[%lld]=%d outside the alignment", (long long)i, cand_pos_hd[i]);
+    InBuf cp(ctx, cand_pos_hd, (size_t)nc * 4), ca(ctx, cand_allow_hd, (size_t)nc * 16), bs(ctx, bits_slot, (size_t)nc * 4);
+    OutBuf oc(ctx, counts_hd, (size_t)nc * 3 * 8), ob(ctx, bits_hd, (size_t)nslots * 3 * words * 4);
+    if (cp.rc || ca.rc || bs.rc || oc.rc || ob.rc) return MPB_ECUDA;
+    CK(cudaMemsetAsync(oc.d, 0, (size_t)nc * 3 * 8, ctx->stream));
+    dim3 grid((unsigned)((m->n_seq + SCAN_THREADS - 1) / SCAN_THREADS), (unsigned)((nc + SCAN_GROUP - 1) / SCAN_GROUP));
+    LAUNCH(ctx, k_scan, grid, SCAN_THREADS, 0, m->planes, m->nsp, m->n_seq, m->lens, k, v, fmask, rmask,
+           cp.dev<int32_t>(), ca.dev<uint32_t>(), (long long)nc, oc.dev<unsigned long long>(),
+           bits_slot ? bs.dev<int32_t>() : nullptr, ob.dev<uint32_t>(), words, m->err);
+    CK(oc.finish());
+    CK(ob.finish());
+    if (oc.is_host() || ob.is_host() || cp.tmp || ca.tmp || bs.tmp) return check_flags(ctx, m->err);
+    return 0;
+}
+
+// per (window, sequence) table key, for the JSON side files
+__global__ void k_seqkeys(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq, const int32_t* __restrict__ lens,
+                          int k, const int32_t* __restrict__ win_pos, int nw, uint64_t* __restrict__ out) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_seq) return;
+    const uint32_t kmask = (1u << k) - 1u;
+    const int len = lens[s];
+    for (int wi = blockIdx.y; wi < nw; wi += gridDim.y) {
+        Win w;
+        mpb_load_window(pl, nsp, s, len, win_pos[wi], k, kmask, w);
+        out[(int64_t)wi * n_seq + s] = w.multi ? MPB_KEY_IUPAC_D : mpb_key(w.c, w.g, w.t, w.gapv, k);
+    }
+}
+
+extern "C" int mpb_seqkeys(mpb_msa* m, int k, const int32_t* win_pos, int32_t nw, uint64_t* out_hd) {
+    if (!m || !win_pos || !out_hd) return fail(MPB_EINVAL, "NULL argument");
+    if (k < 3 || k > MPB_MAX_K || nw < 1) return fail(MPB_EINVAL, "bad k=%d or nw=%d", k, nw);
+    mpb_ctx* ctx = m->ctx;
+    CK(cudaSetDevice(ctx->device));
+    InBuf wp(ctx, win_pos, (size_t)nw * 4);
+    OutBuf o(ctx, out_hd, (size_t)nw * m->n_seq * 8);
+    if (wp.rc || o.rc) return MPB_ECUDA;
+    unsigned gx = (unsigned)((m->n_seq + 255) / 256), gy = (unsigned)nw;
+    if (gy > 1024) gy = 1024;
+    LAUNCH(ctx, k_seqkeys, dim3(gx, gy), 256, 0, m->planes, m->nsp, m->n_seq, m->lens, k, wp.dev<int32_t>(), nw,
+           o.dev<uint64_t>());
+    CK(o.finish());
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// nearest-neighbour Tm (core:249-261, 328-335).  The 4x4 dH / dS tables and the initiation terms are staged
+// into shared memory with one TMA bulk copy (cp.async.bulk) per CTA, completion on an mbarrier.
+// ------------------------------------------------------------------------------------------------------
+// [0..15] dH[next][cur], [16..31] dS[next][cur], [32..35] dH init (A,C,G,T), [36..39] dS init
+__device__ __align__(16) double g_nn_tables[40] = {
+    -7.9, -8.5, -8.2, -7.2, -8.4, -8.0, -9.8, -8.2, -7.8, -10.6, -8.0, -8.5, -7.2, -7.8, -8.4, -7.9,
+    -22.2, -22.7, -22.2, -21.3, -22.4, -19.9, -24.4, -22.2, -21.0, -27.2, -19.9, -22.7, -20.4, -21.0, -22.4, -22.2,
+    2.3, 0.1, 0.1, 2.3, 4.1, -2.8, -2.8, 4.1};
+
+__global__ void __launch_bounds__(128)
+k_tm(const uint8_t* __restrict__ seqs, int k, long long n, double c_nonsym, double c_sym, double corr,
+     double* __restrict__ tm, double* __restrict__ dh_out, double* __restrict__ ds_out) {
+    __shared__ __align__(16) double tab[40];
+    __shared__ __align__(8) unsigned long long bar;
+    const unsigned bar_addr = (unsigned)__cvta_generic_to_shared(&bar);
+    const unsigned tab_addr = (unsigned)__cvta_generic_to_shared(tab);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_addr));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(320u) : "memory");
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(tab_addr),
+            "l"(g_nn_tables), "r"(320u), "r"(bar_addr)
+            : "memory");
+    }
+    {
+        unsigned done = 0;
+        while (!done) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done)
+                : "r"(bar_addr), "r"(0u)
+                : "memory");
+        }
+    }
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t* q = seqs + i * k;
+    // left-to-right sums starting from 0, exactly the reference's operation order; no FMA contraction
+    double dh = 0.0, ds = 0.0;
+    for (int j = 0; j + 1 < k; ++j) {
+        const int nx = q[j + 1], cu = q[j];
+        dh = __dadd_rn(dh, tab[nx * 4 + cu]);
+        ds = __dadd_rn(ds, tab[16 + nx * 4 + cu]);
+    }
+    dh = __dadd_rn(dh, __dadd_rn(tab[32 + q[0]], tab[32 + q[k - 1]]));
+    ds = __dadd_rn(ds, __dadd_rn(tab[36 + q[0]], tab[36 + q[k - 1]]));
+    bool sym = (k % 2) == 0;
+    for (int j = 0; sym && j < k / 2; ++j) sym = (q[j] + q[k / 2 + j]) == 3;  // first half == complement(second half)
+    if (sym) ds = __dadd_rn(ds, -1.4);
+    dh = __dmul_rn(dh, 1000.0);
+    const double denom = __dadd_rn(ds, sym ? c_sym : c_nonsym);
+    const double t = __dadd_rn(__ddiv_rn(1.0, __dadd_rn(__ddiv_rn(1.0, __ddiv_rn(dh, denom)), corr)), -273.15);
+    tm[i] = t;
+    if (dh_out) dh_out[i] = dh;
+    if (ds_out) ds_out[i] = ds;
+}
+
+extern "C" int mpb_tm(mpb_ctx* ctx, const uint8_t* seqs_hd, int k, int64_t n, const double* consts3, double* tm_hd,
+                      double* dh_hd, double* ds_hd) {
+    if (!ctx || !seqs_hd || !consts3 || !tm_hd) return fail(MPB_EINVAL, "NULL argument");
+    if (k < 2 || n < 0) return fail(MPB_EINVAL, "bad k=%d n=%lld", k, (long long)n);
+    if (n == 0) return 0;
+    CK(cudaSetDevice(ctx->device));
+    InBuf in(ctx, seqs_hd, (size_t)n * k);
+    OutBuf ot(ctx, tm_hd, n * 8), oh(ctx, dh_hd, n * 8), os(ctx, ds_hd, n * 8);
+    if (in.rc || ot.rc || oh.rc || os.rc) return MPB_ECUDA;
+    LAUNCH(ctx, k_tm, (unsigned)((n + 127) / 128), 128, 0, in.dev<uint8_t>(), k, (long long)n, consts3[0], consts3[1],
+           consts3[2], ot.dev<double>(), oh.dev<double>(), os.dev<double>());
+    CK(ot.finish());
+    CK(oh.finish());
+    CK(os.finish());
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}

@@ -1,0 +1,247 @@
+"""A pure-Python stand-in for multiprime_b200._lib (Context / Msa / Hist), built on oracle primitives.
+
+TEST INFRASTRUCTURE ONLY: it lets the CPU test-suite drive the host logic of multiprime_b200.core (gates, seeds,
+refinement walk, filters, writers) without a GPU, and documents the contract of every libmpb200 entry point
+(key encoding, count semantics).  The GPU tests run the same cases against the real library.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from multiprime_b200.iupac import BASES, CODE_CHARS
+from oracle import mp_oracle as o
+
+KEY_EMPTY = 0xFFFFFFFFFFFFFFFF
+KEY_IUPAC = 0xFFFFFFFFFFFFFFFE
+KEY_BASE5 = 1 << 54
+MAX_K = 27
+
+
+def hap_key(hap: str) -> int:
+    """table key of a plain haplotype string (ACGT-)"""
+    k = len(hap)
+    if "-" not in hap:
+        b0 = b1 = 0
+        for i, ch in enumerate(hap):
+            b = BASES.index(ch)
+            b0 |= (b & 1) << i
+            b1 |= (b >> 1) << i
+        return b0 | (b1 << k)
+    return KEY_BASE5 + sum("ACGT-".index(ch) * 5 ** i for i, ch in enumerate(hap))
+
+
+class Context:
+    def __init__(self, device=0, stream=None):
+        self.launches = 0
+
+    def tm(self, seqs2bit, consts3, want_hs=False):
+        tm, dh, ds = [], [], []
+        for row in np.asarray(seqs2bit):
+            s = "".join(BASES[b] for b in row)
+            tm.append(o.tm_unrounded(s))
+            h, e = o.delta_h_s(s)
+            dh.append(h)
+            ds.append(e)
+        if want_hs:
+            return np.array(tm), np.array(dh), np.array(ds)
+        return np.array(tm)
+
+    def sync(self):
+        pass
+
+    def close(self):
+        pass
+
+
+class Msa:
+    def __init__(self, ctx, packed4, n_seq, n_col, row_bytes=None, lens=None):
+        self.ctx = ctx
+        self.n_seq, self.n_col = n_seq, n_col
+        codes = np.empty((n_seq, packed4.shape[1] * 2), np.uint8)
+        codes[:, 0::2] = packed4 & 15
+        codes[:, 1::2] = packed4 >> 4
+        lens = np.full(n_seq, n_col) if lens is None else lens
+        self.rows = ["".join(CODE_CHARS[c] for c in codes[i, :lens[i]]) for i in range(n_seq)]
+
+    def close(self):
+        pass
+
+    def seq_attr(self):
+        lead = np.array([len(s) - len(s.lstrip("-")) for s in self.rows], np.int32)
+        rstrip = np.array([len(s.rstrip("-")) for s in self.rows], np.int32)
+        return lead, rstrip
+
+    def hist(self, k, v, win_pos, log2_cap=0):
+        return Hist(self, k, v, win_pos)
+
+    def scan(self, k, v, fmask, rmask, cand_pos, cand_allow, bits_slot=None, counts_out=None, bits_out=None):
+        cand_allow = np.asarray(cand_allow).reshape(-1, 4)
+        nc = len(cand_pos)
+        counts = np.zeros((nc, 3), np.int64)
+        words = (self.n_seq + 31) // 32
+        bits = None
+        if bits_slot is not None:
+            bits = np.zeros((int(max(bits_slot)) + 1 if nc else 0, 3, words), np.uint32)
+        cache = {}
+        for ci in range(nc):
+            p = int(cand_pos[ci])
+            if p not in cache:
+                cache[p] = [o.window_kmer(s, p, k) for s in self.rows]
+            allow = [int(x) for x in cand_allow[ci]]
+            for si, w in enumerate(cache[p]):
+                assert len(w) == k
+                isgap = w.count("-") > v
+                non_f = non_r = False
+                if not isgap:
+                    for hap in o.expand(w):
+                        m = 0
+                        for i, ch in enumerate(hap):
+                            if ch == "-" or not (allow[BASES.index(ch)] >> i) & 1:
+                                m |= 1 << i
+                        within = bin(m).count("1") <= v
+                        okf = within and not (m & fmask)
+                        okr = within and not (m & rmask)
+                        counts[ci, 0] += m == 0
+                        counts[ci, 1] += okf and m != 0
+                        counts[ci, 2] += okr and m != 0
+                        non_f |= not okf
+                        non_r |= not okr
+                if bits is not None and bits_slot[ci] >= 0:
+                    sl = bits_slot[ci]
+                    for j, flag in enumerate((non_f, non_r, isgap)):
+                        if flag:
+                            bits[sl, j, si >> 5] |= np.uint32(1 << (si & 31))
+        return counts, bits
+
+    def seqkeys(self, k, win_pos):
+        out = np.empty((len(win_pos), self.n_seq), np.uint64)
+        for wi, p in enumerate(win_pos):
+            for si, s in enumerate(self.rows):
+                w = o.window_kmer(s, int(p), k)
+                out[wi, si] = KEY_IUPAC if any(ch not in "ACGT-" for ch in w) else hap_key(w)
+        return out
+
+
+class Hist:
+    def __init__(self, msa, k, v, win_pos):
+        self.msa, self.k, self.v = msa, k, v
+        self.win_pos = [int(p) for p in win_pos]
+        self.nw = len(self.win_pos)
+        self.tables = []      # per window: {key: [count, first]}
+        self.gap_n = []
+        self.exc = []
+        self.n_iupac_gap = []
+        for wi, p in enumerate(self.win_pos):
+            tab, gaps, nig = {}, 0, 0
+            for si, s in enumerate(msa.rows):
+                w = o.window_kmer(s, p, k)
+                assert len(w) == k
+                iupac = any(ch not in "ACGT-" for ch in w)
+                if w.count("-") > v:
+                    gaps += 1
+                    if iupac:
+                        nig += 1
+                        self.exc.append((wi, si))
+                    else:
+                        e = tab.setdefault(hap_key(w), [0, si << 16])
+                        e[0] += 1
+                else:
+                    for ei, hap in enumerate(o.expand(w)):
+                        e = tab.setdefault(hap_key(hap), [0, (si << 16) | ei])
+                        e[0] += 1
+            self.tables.append(tab)
+            self.gap_n.append(gaps)
+            self.n_iupac_gap.append(nig)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        pass
+
+    def close(self):
+        pass
+
+    def _is_cover(self, key):
+        if key < KEY_BASE5:
+            return True
+        x, g = key - KEY_BASE5, 0
+        for _ in range(self.k):
+            g += x % 5 == 4
+            x //= 5
+        return g <= self.v
+
+    def stats(self):
+        nw = self.nw
+        out = dict(gap_n=np.array(self.gap_n, np.int64), ent=np.zeros((nw, 4)), nuniq=np.zeros((nw, 3), np.int64),
+                   mm_key=np.full(nw, KEY_EMPTY, np.uint64), mm_cnt=np.zeros(nw, np.int64),
+                   mm_first=np.full(nw, KEY_EMPTY, np.uint64), n_iupac_gap=np.array(self.n_iupac_gap, np.int64))
+        for wi, tab in enumerate(self.tables):
+            best = None
+            for key, (c, f) in tab.items():
+                if self._is_cover(key):
+                    out["ent"][wi, 0] += c
+                    out["ent"][wi, 1] += c * np.log2(c)
+                    out["nuniq"][wi, 0] += 1
+                else:
+                    out["ent"][wi, 2] += c
+                    out["ent"][wi, 3] += c * np.log2(c)
+                    out["nuniq"][wi, 1] += 1
+                if key < KEY_BASE5:
+                    out["nuniq"][wi, 2] += 1
+                    if best is None or c > best[0] or (c == best[0] and f < best[1]):
+                        best = (c, f, key)
+            if best:
+                out["mm_cnt"][wi], out["mm_first"][wi], out["mm_key"][wi] = best
+        return out
+
+    def tensors(self, sel):
+        k = self.k
+        freq = np.zeros((self.nw, 4, k), np.int64)
+        nn = np.zeros((self.nw, k - 1, 4, 4), np.int64)
+        for wi, tab in enumerate(self.tables):
+            if not sel[wi]:
+                continue
+            for key, (c, _) in tab.items():
+                if not self._is_cover(key):
+                    continue
+                hap = key_string(key, k)
+                for i, ch in enumerate(hap):
+                    if ch != "-":
+                        freq[wi, BASES.index(ch), i] += c
+                        if i and hap[i - 1] != "-":
+                            nn[wi, i - 1, BASES.index(hap[i - 1]), BASES.index(ch)] += c
+        return freq, nn
+
+    def dump(self, w, max_n):
+        items = sorted(self.tables[w].items(), key=lambda kv: kv[1][1])
+        return (np.array([k for k, _ in items], np.uint64), np.array([v[0] for _, v in items], np.uint32),
+                np.array([v[1] for _, v in items], np.uint64))
+
+    def match(self, q_win, q_allow):
+        q_allow = np.asarray(q_allow).reshape(-1, 4)
+        out = np.zeros(len(q_win), np.int64)
+        for qi, wi in enumerate(q_win):
+            allow = [int(x) for x in q_allow[qi]]
+            for key in self.tables[int(wi)]:
+                if key < KEY_BASE5:
+                    hap = key_string(key, self.k)
+                    out[qi] += all((allow[BASES.index(ch)] >> i) & 1 for i, ch in enumerate(hap))
+        return out
+
+    def exceptions(self):
+        return (np.array([w for w, _ in self.exc], np.int32), np.array([s for _, s in self.exc], np.int32))
+
+
+def key_string(key: int, k: int) -> str:
+    key = int(key)
+    if key < KEY_BASE5:
+        mask = (1 << k) - 1
+        b0, b1 = key & mask, (key >> k) & mask
+        return "".join(BASES[((b0 >> i) & 1) | (((b1 >> i) & 1) << 1)] for i in range(k))
+    x = key - KEY_BASE5
+    out = []
+    for _ in range(k):
+        out.append("ACGT-"[x % 5])
+        x //= 5
+    return "".join(out)
