@@ -54,6 +54,13 @@ int mpb_ctx_sync(mpb_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py's "gpu_launches") */
 int64_t mpb_ctx_launches(mpb_ctx* ctx);
 
+/* Profiling: when enabled every kernel launch is bracketed by CUDA events on the context's stream.
+ * mpb_ctx_profile_read sums duration (ms), launch count and algorithmic work units (candidate x sequence
+ * evaluations for "k_scan", extracted k-mers for "k_hist") of the launches of one kernel since the last clear;
+ * kernel == NULL clears the records. */
+int mpb_ctx_profile(mpb_ctx* ctx, int enable);
+int mpb_ctx_profile_read(mpb_ctx* ctx, const char* kernel, double* ms, int64_t* launches, double* units);
+
 /* ---- alignment ---------------------------------------------------------------------------------------
  * core:441-455 parse_seq keeps the alignment as {id: string}; here it lives in HBM as four bit-planes
  * (A,C,G,T) per 32-column word, sequence index fastest: planes[col_word][plane][seq].

@@ -27,6 +27,9 @@ SIGNATURES = {
     "mpb_ctx_set_stream": (C.c_int, [_P, _P]),
     "mpb_ctx_sync": (C.c_int, [_P]),
     "mpb_ctx_launches": (C.c_int64, [_P]),
+    "mpb_ctx_profile": (C.c_int, [_P, C.c_int]),
+    "mpb_ctx_profile_read": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int64),
+                                        C.POINTER(C.c_double)]),
     "mpb_msa_upload": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, _P, C.POINTER(_P)]),
     "mpb_msa_free": (None, [_P]),
     "mpb_msa_nseq": (C.c_int64, [_P]),
@@ -107,6 +110,16 @@ class Context:
     @property
     def launches(self) -> int:
         return load().mpb_ctx_launches(self.h)
+
+    def profile(self, enable: bool = True):
+        check(load().mpb_ctx_profile(self.h, int(enable)))
+
+    def profile_read(self, kernel: str | None):
+        """(total ms, launches, work units) of one kernel's event-timed launches; None clears the records"""
+        ms, n, u = C.c_double(), C.c_int64(), C.c_double()
+        check(load().mpb_ctx_profile_read(self.h, kernel.encode() if kernel else None, C.byref(ms), C.byref(n),
+                                          C.byref(u)))
+        return ms.value, n.value, u.value
 
     def close(self):
         if self.h:

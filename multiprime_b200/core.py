@@ -314,8 +314,8 @@ class NN_degenerate(object):
 
     def __init__(self, seq_file, primer_length=18, coverage=0.8, number_of_dege_bases=18, score_of_dege_bases=1000,
                  product_len=250, position="2,-1", variation=2, raw_entropy_threshold=3.6, distance=4, GC="0.4,0.6",
-                 nproc=10, outfile="", device=0, windows_per_batch=0, sidecars=True, alignment=None, stream=None,
-                 _backend=None):
+                 nproc=10, outfile="", device=0, windows_per_batch=0, sidecars=True, alignment=None, packed=None,
+                 stream=None, _backend=None):
         self.primer_length = primer_length
         self.coverage = coverage
         self.number_of_dege_bases = number_of_dege_bases
@@ -333,18 +333,21 @@ class NN_degenerate(object):
         if not 3 <= primer_length <= _lib.MAX_K:
             raise ValueError("primer length must be within 3..%d" % _lib.MAX_K)
         self.fmask, self.rmask = strict_masks(position, primer_length)
-        if alignment is not None:
-            self.ids, codes, lens = alignment
+        if packed is not None:                   # (ids, nibble-packed rows, n_col, lens): already in upload format
+            self.ids, packed4, self.n_col, lens = packed
+            self._codes = None
         else:
-            self.ids, codes, lens = parse_msa(seq_file)
+            self.ids, codes, lens = alignment if alignment is not None else parse_msa(seq_file)
+            self.n_col = codes.shape[1]
+            self._codes = codes
+            packed4 = pack4(codes)
+        self._packed4 = packed4                 # host copy: only read for the rare IUPAC-in-gap-row side-file entries
         self.total_sequence_number = len(self.ids)
-        self.n_col = codes.shape[1]
-        self.codes = codes                      # host copy: only read for the rare IUPAC-in-gap-row side-file entries
-        self.lens = lens
+        self.lens = lens if lens is not None else np.full(len(self.ids), self.n_col, np.int32)
         backend = _backend or _lib                # tests inject tests/fake_device.py to exercise the host logic
         self.ctx = backend.Context(device, stream)
-        self.msa = backend.Msa(self.ctx, pack4(codes), len(self.ids), self.n_col,
-                            lens=None if (lens == self.n_col).all() else lens)
+        self.msa = backend.Msa(self.ctx, packed4, len(self.ids), self.n_col,
+                               lens=None if (self.lens == self.n_col).all() else self.lens)
         self.position_list = self.seq_attribute()
         self.start_position, self.stop_position, self.length = self.position_list
         self.entropy_threshold = self.entropy_threshold_adjust(self.length)
@@ -369,34 +372,46 @@ class NN_degenerate(object):
         return self.raw_entropy_threshold * 0.9
 
     # -- entropy (core:602-614) ----------------------------------------------------------------------------
-    def _entropy_exact(self, hist, wi, pos, n_unique):
-        """the reference's left-to-right float sums, over the table dumped in first-seen order"""
-        k, v = self.primer_length, self.variation
-        keys, cnt, first = hist.dump(wi, int(n_unique) + 8)
-        cover, gaps = [], []                     # (first, count)
-        for key, c, f in zip(keys.tolist(), cnt.tolist(), first.tolist()):
-            if key >= _lib.KEY_BASE5 and _count_gap_digits(key - _lib.KEY_BASE5, k) > v:
-                gaps.append((f, c))
-            else:
-                cover.append((f, c))
-        # gap rows that hold IUPAC cells are not in the table: group them by their raw k-mer
+    def _iupac_gap_groups(self, hist, wi, pos):
+        """gap rows that hold IUPAC cells are not in the device table (their raw k-mer needs 4 bits per cell):
+        group the few of them by raw k-mer here -> [(first order, count)]"""
         exc_w, exc_s = self._exceptions(hist)
         raw = {}
         for s in exc_s[exc_w == wi].tolist():
-            w = self._window_cells(s, pos)
-            raw.setdefault(w, [s << 16, 0])[1] += 1
-        gaps.extend((f, c) for f, c in raw.values())
+            raw.setdefault(self._window_cells(s, pos), [s << 16, 0])[1] += 1
+        return [(f, c) for f, c in raw.values()]
+
+    def _entropy_exact(self, hist, wi, pos, n_unique):
+        """the reference's left-to-right float sums (core:602-614), over the table dumped in first-seen order"""
+        k, v = self.primer_length, self.variation
+        keys, cnt, first = hist.dump(wi, int(n_unique) + 8)
+        is_gap = np.zeros(len(keys), bool)
+        b5 = keys >= np.uint64(_lib.KEY_BASE5)
+        if b5.any():
+            x = (keys[b5] - np.uint64(_lib.KEY_BASE5)).astype(np.uint64)
+            g = np.zeros(len(x), np.int64)
+            for _ in range(k):
+                g += (x % np.uint64(5)) == np.uint64(4)
+                x //= np.uint64(5)
+            is_gap[b5] = g > v
+        cover = cnt[~is_gap].tolist()                                   # dump() is sorted by first-seen order
+        gaps = list(zip(first[is_gap].tolist(), cnt[is_gap].tolist())) + self._iupac_gap_groups(hist, wi, pos)
         gaps.sort()
         gap_n = sum(c for _, c in gaps)
         cover_number = self.total_sequence_number - gap_n
         tot = cover_number + gap_n
+        term_c, term_t = {}, {}
+        for c in set(cover):
+            term_c[c] = (c / cover_number) * math.log((c / cover_number), 2)
+        for c in set(cover) | {c for _, c in gaps}:
+            term_t[c] = (c / tot) * math.log((c / tot), 2)
         c_bit = 0
         t_bit = 0
-        for _, c in cover:
-            c_bit += (c / cover_number) * math.log((c / cover_number), 2)
-            t_bit += (c / tot) * math.log((c / tot), 2)
+        for c in cover:                  # plain left-to-right adds (the builtin sum() is compensated since 3.12)
+            c_bit += term_c[c]
+            t_bit += term_t[c]
         for _, c in gaps:
-            t_bit += (c / tot) * math.log((c / tot), 2)
+            t_bit += term_t[c]
         return round(-c_bit, 2), round(-t_bit, 2)
 
     def _exceptions(self, hist):
@@ -407,7 +422,14 @@ class NN_degenerate(object):
     def _window_cells(self, s: int, p: int) -> bytes:
         """core:666-687 for one (sequence, window) on the host copy; only used for IUPAC-holding gap rows"""
         k = self.primer_length
-        row = self.codes[s, :self.lens[s]].tobytes()
+        if self._codes is not None:
+            row = self._codes[s, :self.lens[s]].tobytes()
+        else:
+            pk = self._packed4[s]
+            cells = np.empty(pk.shape[0] * 2, np.uint8)
+            cells[0::2] = pk & 15
+            cells[1::2] = pk >> 4
+            row = cells[:self.lens[s]].tobytes()
         gap = b"\x00"
         w = row[p:p + k]
         if w != gap * k:
@@ -489,7 +511,11 @@ class NN_degenerate(object):
         N = self.total_sequence_number
         s0c, s1c, s0g, s1g = (float(x) for x in st["ent"][wi])
         cover_number = N - gap_n
-        exact = st["n_iupac_gap"][wi] > 0
+        exact = False
+        if st["n_iupac_gap"][wi] > 0:
+            for _, c in self._iupac_gap_groups(hist, wi, pos):
+                s0g += c
+                s1g += c * math.log2(c)
         if not exact:
             tot = float(N)
             c_raw = -(s1c - s0c * math.log2(cover_number)) / cover_number

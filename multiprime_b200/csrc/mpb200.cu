@@ -35,11 +35,19 @@ static int fail(int code, const char* fmt, ...) {
                         __FILE__, __LINE__, #call, cudaGetErrorString(e__));                       \
     } while (0)
 
+struct ProfRec {
+    const char* name;
+    cudaEvent_t e0, e1;
+    double units;  // algorithmic work units of this launch (kernel specific; evals for k_scan)
+};
 struct mpb_ctx {
     int device;
     cudaStream_t stream;
     int64_t launches;
     int sm_count;
+    bool profile;
+    std::vector<ProfRec> recs;
+    double pending_units;
 };
 
 struct mpb_msa {
@@ -179,6 +187,8 @@ extern "C" int mpb_ctx_create(int device, mpb_ctx** out) {
     c->stream = 0;
     c->launches = 0;
     c->sm_count = prop.multiProcessorCount;
+    c->profile = false;
+    c->pending_units = 0;
     *out = c;
     return 0;
 }
@@ -195,12 +205,59 @@ extern "C" int mpb_ctx_sync(mpb_ctx* ctx) {
 }
 extern "C" int64_t mpb_ctx_launches(mpb_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
-#define LAUNCH(ctx, kern, grid, block, smem, ...)                   \
-    do {                                                            \
-        kern<<<grid, block, smem, (ctx)->stream>>>(__VA_ARGS__);    \
-        (ctx)->launches++;                                          \
-        CK(cudaGetLastError());                                     \
+// every kernel goes through LAUNCH: counted, and (when profiling is on) bracketed by CUDA events on the stream
+#define LAUNCH(ctx, kern, grid, block, smem, ...)                                 \
+    do {                                                                          \
+        ProfRec pr__ = {#kern, nullptr, nullptr, (ctx)->pending_units};           \
+        if ((ctx)->profile) {                                                     \
+            CK(cudaEventCreate(&pr__.e0));                                        \
+            CK(cudaEventCreate(&pr__.e1));                                        \
+            CK(cudaEventRecord(pr__.e0, (ctx)->stream));                          \
+        }                                                                         \
+        kern<<<grid, block, smem, (ctx)->stream>>>(__VA_ARGS__);                  \
+        (ctx)->launches++;                                                        \
+        CK(cudaGetLastError());                                                   \
+        if ((ctx)->profile) {                                                     \
+            CK(cudaEventRecord(pr__.e1, (ctx)->stream));                          \
+            (ctx)->recs.push_back(pr__);                                          \
+        }                                                                         \
+        (ctx)->pending_units = 0;                                                 \
     } while (0)
+
+extern "C" int mpb_ctx_profile(mpb_ctx* ctx, int enable) {
+    if (!ctx) return fail(MPB_EINVAL, "ctx is NULL");
+    ctx->profile = enable != 0;
+    return 0;
+}
+
+// Sum the event-timed durations of all launches of `kernel` recorded since the last read; clears them when
+// kernel is NULL.  ms / launches / units may be NULL.
+extern "C" int mpb_ctx_profile_read(mpb_ctx* ctx, const char* kernel, double* ms, int64_t* launches, double* units) {
+    if (!ctx) return fail(MPB_EINVAL, "ctx is NULL");
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (!kernel) {
+        for (auto& r : ctx->recs) {
+            cudaEventDestroy(r.e0);
+            cudaEventDestroy(r.e1);
+        }
+        ctx->recs.clear();
+        return 0;
+    }
+    double t = 0, u = 0;
+    int64_t n = 0;
+    for (auto& r : ctx->recs)
+        if (strncmp(r.name, kernel, strlen(kernel)) == 0 && (r.name[strlen(kernel)] == 0 || r.name[strlen(kernel)] == '<')) {
+            float f = 0;
+            CK(cudaEventElapsedTime(&f, r.e0, r.e1));
+            t += f;
+            u += r.units;
+            ++n;
+        }
+    if (ms) *ms = t;
+    if (launches) *launches = n;
+    if (units) *units = u;
+    return 0;
+}
 
 // ------------------------------------------------------------------------------------------------------
 // alignment upload: nibble rows -> bit-planes
@@ -443,6 +500,7 @@ extern "C" int mpb_hist_build(mpb_msa* m, int k, int v, const int32_t* win_pos, 
     const unsigned want = (unsigned)ctx->sm_count * 8;
     if (gx >= want) gy = 1;
     else if (gy > (want + gx - 1) / gx) gy = (want + gx - 1) / gx;
+    ctx->pending_units = (double)nw * (double)m->n_seq;  // (window, sequence) k-mers extracted
     LAUNCH(ctx, k_hist, dim3(gx, gy), HIST_THREADS, 0, m->planes, m->nsp, m->n_seq, m->lens, k, v, h->win_pos, nw,
            h->keys, h->cnt, h->first, log2_cap, h->gap_n, h->iupac_gap_n, h->exc, h->exc_n, (long long)h->exc_max,
            m->err);
@@ -828,116 +886,140 @@ extern "C" int mpb_hist_exceptions(mpb_hist* h, int64_t max_n, int32_t* win_idx,
 // the candidate scan (mis_primer_check, core:1103-1130)
 // ------------------------------------------------------------------------------------------------------
 #define SCAN_THREADS 256
-#define SCAN_GROUP 128  // candidates per blockIdx.y
+#define SCAN_CHUNK 8       // candidates of one window evaluated together against a window held in registers
+#define SCAN_MAX_CPB 128   // chunks per block (shared-memory counters: 128*8*3*4 = 12 KB)
 
-// thread = sequence (blockIdx.x tiles the sequences), blockIdx.y = group of SCAN_GROUP candidates sorted by
-// window, so consecutive candidates mostly reuse the window already held in registers.
+// one candidate against one one-hot k-mer: mismatch vector, then the three classes of core:1114-1127
+#define SCAN_EVAL(A_, C_, G_, T_, ci)                                                             \
+    {                                                                                             \
+        const uint32_t mis = w.gapv | ((A_) & nA[ci]) | ((C_) & nC[ci]) | ((G_) & nG[ci]) | ((T_) & nT[ci]); \
+        const bool within = __popc(mis) <= v;                                                     \
+        const bool z = mis == 0u;                                                                 \
+        const bool okf = within && (mis & fmask) == 0u;                                           \
+        const bool okr = within && (mis & rmask) == 0u;                                           \
+        acc0[ci] += z;                                                                            \
+        accf[ci] += okf && !z;                                                                    \
+        accr[ci] += okr && !z;                                                                    \
+        if (BITS) {                                                                               \
+            nonf |= (!okf) << ci;                                                                 \
+            nonr |= (!okr) << ci;                                                                 \
+        }                                                                                         \
+    }
+
+// Block (x, y): sequences [x*T*256, (x+1)*T*256) against the chunks [y*cpb, (y+1)*cpb).  A chunk = up to
+// SCAN_CHUNK candidates of ONE window: their masks sit in registers while the block walks its T sequence tiles,
+// each thread keeping per-candidate counters in registers; one warp reduction per chunk, block-private counters in
+// shared memory, one coalesced store of the block's partial counts at the end (no global atomics).
+template <bool BITS>
 __global__ void __launch_bounds__(SCAN_THREADS)
 k_scan(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq, const int32_t* __restrict__ lens, int k, int v,
-       uint32_t fmask, uint32_t rmask, const int32_t* __restrict__ cand_pos, const uint32_t* __restrict__ cand_allow,
-       long long nc, unsigned long long* __restrict__ counts, const int32_t* __restrict__ bits_slot,
-       uint32_t* __restrict__ bits, long long words, int* __restrict__ err) {
-    __shared__ uint32_t s_nmask[SCAN_GROUP][4];
-    __shared__ int32_t s_pos[SCAN_GROUP];
-    __shared__ int32_t s_slot[SCAN_GROUP];
-    __shared__ unsigned int s_cnt[SCAN_GROUP][3];
-    const long long c0 = (long long)blockIdx.y * SCAN_GROUP;
-    const int ng = (int)((nc - c0) < SCAN_GROUP ? (nc - c0) : SCAN_GROUP);
-    const uint32_t kmask = (1u << k) - 1u;
-    for (int i = threadIdx.x; i < ng; i += SCAN_THREADS) {
-        s_pos[i] = cand_pos[c0 + i];
-        s_slot[i] = bits_slot ? bits_slot[c0 + i] : -1;
-        for (int b = 0; b < 4; ++b) s_nmask[i][b] = ~cand_allow[(c0 + i) * 4 + b] & kmask;
-        s_cnt[i][0] = s_cnt[i][1] = s_cnt[i][2] = 0;
-    }
+       uint32_t fmask, uint32_t rmask, const int4* __restrict__ chunks, int n_chunks, int cpb, int tiles_per_block,
+       const uint32_t* __restrict__ cand_allow, uint32_t* __restrict__ partial, long long nc,
+       const int32_t* __restrict__ bits_slot, uint32_t* __restrict__ bits, long long words, int* __restrict__ err) {
+    __shared__ unsigned int s_cnt[SCAN_MAX_CPB * SCAN_CHUNK * 3];
+    const int ch0 = blockIdx.y * cpb;
+    const int ch1 = min(n_chunks, ch0 + cpb);
+    for (int i = threadIdx.x; i < (ch1 - ch0) * SCAN_CHUNK * 3; i += SCAN_THREADS) s_cnt[i] = 0;
     __syncthreads();
-    const int64_t s = (int64_t)blockIdx.x * SCAN_THREADS + threadIdx.x;
-    const bool valid = s < n_seq;
+    const uint32_t kmask = (1u << k) - 1u;
     const int lane = threadIdx.x & 31;
-    const int len = valid ? lens[s] : 0;
-    int cur_pos = -1;
-    Win w;
-    w.a = w.c = w.g = w.t = w.multi = 0;
-    w.gapv = kmask;
-    bool cover = false, isgap = false;
-    uint32_t nexp = 1;
-    for (int ci = 0; ci < ng; ++ci) {
-        const int p = s_pos[ci];
-        if (p != cur_pos) {  // uniform across the block
-            cur_pos = p;
+    const long long tile0 = (long long)blockIdx.x * tiles_per_block;
+    for (int ch = ch0; ch < ch1; ++ch) {
+        const int4 cd = chunks[ch];  // first candidate, count, window column
+        const int first = cd.x, cnt = cd.y, p = cd.z;
+        uint32_t nA[SCAN_CHUNK], nC[SCAN_CHUNK], nG[SCAN_CHUNK], nT[SCAN_CHUNK];
+        unsigned acc0[SCAN_CHUNK], accf[SCAN_CHUNK], accr[SCAN_CHUNK];
+#pragma unroll
+        for (int ci = 0; ci < SCAN_CHUNK; ++ci) {
+            const bool on = ci < cnt;
+            const uint4 al = on ? __ldg((const uint4*)(cand_allow) + first + ci) : make_uint4(0, 0, 0, 0);
+            nA[ci] = ~al.x & kmask;
+            nC[ci] = ~al.y & kmask;
+            nG[ci] = ~al.z & kmask;
+            nT[ci] = ~al.w & kmask;
+            acc0[ci] = accf[ci] = accr[ci] = 0;
+        }
+        for (int t = 0; t < tiles_per_block; ++t) {
+            const long long tile = tile0 + t;
+            const int64_t s = tile * SCAN_THREADS + threadIdx.x;
+            if (tile * SCAN_THREADS >= n_seq) break;  // uniform
+            const bool valid = s < n_seq;
+            Win w;
+            w.a = w.c = w.g = w.t = w.multi = 0;
+            w.gapv = kmask;
+            bool isgap = false;
+            unsigned nonf = 0, nonr = 0;
             if (valid) {
-                if (!mpb_load_window(pl, nsp, s, len, p, k, kmask, w)) atomicOr(err, MPB_ERR_SHORT_ROW);
+                if (!mpb_load_window(pl, nsp, s, lens[s], p, k, kmask, w)) atomicOr(err, MPB_ERR_SHORT_ROW);
                 isgap = __popc(w.gapv) > v;
-                cover = !isgap;
-                nexp = 1;
-                if (cover && w.multi) {
-                    nexp = mpb_expansions(w);
-                    if (nexp > MPB_MAX_EXP) {
-                        atomicOr(err, MPB_ERR_EXPAND);
-                        nexp = 1;
+                if (!isgap) {
+                    if (w.multi == 0) {
+#pragma unroll
+                        for (int ci = 0; ci < SCAN_CHUNK; ++ci)
+                            if (ci < cnt) SCAN_EVAL(w.a, w.c, w.g, w.t, ci)
+                    } else {
+                        const uint32_t nexp = mpb_expansions(w);
+                        if (nexp > MPB_MAX_EXP) {
+                            atomicOr(err, MPB_ERR_EXPAND);
+                        } else {
+                            for (uint32_t e = 0; e < nexp; ++e) {
+                                uint32_t a, c, g, tt;
+                                mpb_expand(w, e, a, c, g, tt);
+#pragma unroll
+                                for (int ci = 0; ci < SCAN_CHUNK; ++ci)
+                                    if (ci < cnt) SCAN_EVAL(a, c, g, tt, ci)
+                            }
+                        }
+                    }
+                }
+            }
+            if (BITS) {
+                const long long word = tile * (SCAN_THREADS / 32) + (threadIdx.x >> 5);
+                const unsigned bg = __ballot_sync(0xffffffffu, isgap);
+                for (int ci = 0; ci < cnt; ++ci) {
+                    const int slot = bits_slot[first + ci];
+                    if (slot < 0) continue;  // uniform
+                    const unsigned bf = __ballot_sync(0xffffffffu, (nonf >> ci) & 1u);
+                    const unsigned br = __ballot_sync(0xffffffffu, (nonr >> ci) & 1u);
+                    if (lane == 0 && word < words) {
+                        uint32_t* o = bits + (long long)slot * 3 * words;
+                        o[word] = bf;
+                        o[words + word] = br;
+                        o[2 * words + word] = bg;
                     }
                 }
             }
         }
-        const uint32_t nA = s_nmask[ci][0], nC = s_nmask[ci][1], nG = s_nmask[ci][2], nT = s_nmask[ci][3];
-        unsigned n0 = 0, nf = 0, nr = 0;
-        bool non_f = false, non_r = false;
-        if (cover) {
-            if (w.multi == 0) {
-                const uint32_t mis = w.gapv | (w.a & nA) | (w.c & nC) | (w.g & nG) | (w.t & nT);
-                const bool within = __popc(mis) <= v;
-                const bool z = mis == 0u;
-                const bool okf = within && (mis & fmask) == 0u;
-                const bool okr = within && (mis & rmask) == 0u;
-                n0 = z;
-                nf = okf && !z;
-                nr = okr && !z;
-                non_f = !okf;
-                non_r = !okr;
-            } else {
-                for (uint32_t e = 0; e < nexp; ++e) {
-                    uint32_t a, c, g, t;
-                    mpb_expand(w, e, a, c, g, t);
-                    const uint32_t mis = w.gapv | (a & nA) | (c & nC) | (g & nG) | (t & nT);
-                    const bool within = __popc(mis) <= v;
-                    const bool z = mis == 0u;
-                    const bool okf = within && (mis & fmask) == 0u;
-                    const bool okr = within && (mis & rmask) == 0u;
-                    n0 += z;
-                    nf += okf && !z;
-                    nr += okr && !z;
-                    non_f = non_f || !okf;
-                    non_r = non_r || !okr;
+#pragma unroll
+        for (int ci = 0; ci < SCAN_CHUNK; ++ci) {
+            if (ci < cnt) {
+                const unsigned r0 = __reduce_add_sync(0xffffffffu, acc0[ci]);
+                const unsigned rf = __reduce_add_sync(0xffffffffu, accf[ci]);
+                const unsigned rr = __reduce_add_sync(0xffffffffu, accr[ci]);
+                if (lane < 3) {
+                    const unsigned val = lane == 0 ? r0 : (lane == 1 ? rf : rr);
+                    if (val) atomicAdd(&s_cnt[((ch - ch0) * SCAN_CHUNK + ci) * 3 + lane], val);
                 }
-            }
-        }
-        n0 = __reduce_add_sync(0xffffffffu, n0);
-        nf = __reduce_add_sync(0xffffffffu, nf);
-        nr = __reduce_add_sync(0xffffffffu, nr);
-        if (lane == 0) {
-            if (n0) atomicAdd(&s_cnt[ci][0], n0);
-            if (nf) atomicAdd(&s_cnt[ci][1], nf);
-            if (nr) atomicAdd(&s_cnt[ci][2], nr);
-        }
-        const int slot = s_slot[ci];
-        if (slot >= 0) {  // uniform
-            const unsigned bf = __ballot_sync(0xffffffffu, non_f);
-            const unsigned br = __ballot_sync(0xffffffffu, non_r);
-            const unsigned bg = __ballot_sync(0xffffffffu, valid && isgap);
-            const long long word = (long long)blockIdx.x * (SCAN_THREADS / 32) + (threadIdx.x >> 5);
-            if (lane == 0 && word < words) {
-                uint32_t* o = bits + (long long)slot * 3 * words;
-                o[word] = bf;
-                o[words + word] = br;
-                o[2 * words + word] = bg;
             }
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < ng * 3; i += SCAN_THREADS) {
-        unsigned int x = s_cnt[i / 3][i % 3];
-        if (x) atomicAdd(&counts[(c0 + i / 3) * 3 + i % 3], (unsigned long long)x);
+    // partial[x][candidate][3]
+    uint32_t* out = partial + (long long)blockIdx.x * nc * 3;
+    for (int ch = ch0; ch < ch1; ++ch) {
+        const int4 cd = chunks[ch];
+        for (int i = threadIdx.x; i < cd.y * 3; i += SCAN_THREADS)
+            out[(long long)cd.x * 3 + i] = s_cnt[(ch - ch0) * SCAN_CHUNK * 3 + i];
     }
+}
+
+__global__ void k_scan_reduce(const uint32_t* __restrict__ partial, int gx, long long n3,
+                              unsigned long long* __restrict__ counts) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n3) return;
+    unsigned long long acc = 0;
+    for (int x = 0; x < gx; ++x) acc += partial[(long long)x * n3 + i];
+    counts[i] = acc;
 }
 
 extern "C" int mpb_scan(mpb_msa* m, int k, int v, uint32_t fmask, uint32_t rmask, const int32_t* cand_pos_hd,
@@ -946,30 +1028,67 @@ extern "C" int mpb_scan(mpb_msa* m, int k, int v, uint32_t fmask, uint32_t rmask
     if (!m || !cand_pos_hd || !cand_allow_hd || !counts_hd) return fail(MPB_EINVAL, "NULL argument");
     if (k < 3 || k > MPB_MAX_K) return fail(MPB_EINVAL, "primer length %d outside 3..%d", k, MPB_MAX_K);
     if (nc < 1) return 0;
+    if (nc >= (1ll << 31) / 4) return fail(MPB_EINVAL, "too many candidates in one call");
     if (bits_slot && !bits_hd) return fail(MPB_EINVAL, "bits_slot without bits");
     mpb_ctx* ctx = m->ctx;
     CK(cudaSetDevice(ctx->device));
     const long long words = (m->n_seq + 31) / 32;
+    // candidate windows are needed on the host to cut the chunks
+    std::vector<int32_t> pos_copy;
+    const int32_t* pos = cand_pos_hd;
+    if (is_device_ptr(cand_pos_hd)) {
+        pos_copy.resize(nc);
+        CK(cudaMemcpyAsync(pos_copy.data(), cand_pos_hd, nc * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        pos = pos_copy.data();
+    }
+    std::vector<int4> chunks;
+    for (int64_t i = 0; i < nc;) {
+        if (pos[i] < 0 || pos[i] >= m->n_col)
+            return fail(MPB_EINVAL, "cand_pos[%lld]=%d outside the alignment", (long long)i, pos[i]);
+        int64_t j = i + 1;
+        while (j < nc && j - i < SCAN_CHUNK && pos[j] == pos[i]) ++j;
+        chunks.push_back(make_int4((int)i, (int)(j - i), pos[i], 0));
+        i = j;
+    }
     int nslots = 0;
     if (bits_slot)
         for (int64_t i = 0; i < nc; ++i)
             if (bits_slot[i] >= nslots) nslots = bits_slot[i] + 1;
-    if (!is_device_ptr(cand_pos_hd))
-        for (int64_t i = 0; i < nc; ++i)
-            if (cand_pos_hd[i] < 0 || cand_pos_hd[i] >= m->n_col)
-                return fail(MPB_EINVAL, "cand_pos[%lld]=%d outside the alignment", (long long)i, cand_pos_hd[i]);
-    InBuf cp(ctx, cand_pos_hd, (size_t)nc * 4), ca(ctx, cand_allow_hd, (size_t)nc * 16), bs(ctx, bits_slot, (size_t)nc * 4);
+    const int n_chunks = (int)chunks.size();
+    const long long n_tiles = (m->n_seq + SCAN_THREADS - 1) / SCAN_THREADS;
+    const long long target = (long long)ctx->sm_count * 8;  // blocks in flight we want at least
+    int tpb = (int)(n_tiles * n_chunks / (target * 16));     // tiles per block: long walks amortise the reductions
+    if (tpb < 1) tpb = 1;
+    if (tpb > 16) tpb = 16;
+    const int gx = (int)((n_tiles + tpb - 1) / tpb);
+    int cpb = (int)(((long long)n_chunks * gx + target - 1) / target);
+    if (cpb < 1) cpb = 1;
+    if (cpb > SCAN_MAX_CPB) cpb = SCAN_MAX_CPB;
+    const int gy = (n_chunks + cpb - 1) / cpb;
+    InBuf ca(ctx, cand_allow_hd, (size_t)nc * 16), bs(ctx, bits_slot, (size_t)nc * 4),
+        chk(ctx, chunks.data(), chunks.size() * sizeof(int4));
     OutBuf oc(ctx, counts_hd, (size_t)nc * 3 * 8), ob(ctx, bits_hd, (size_t)nslots * 3 * words * 4);
-    if (cp.rc || ca.rc || bs.rc || oc.rc || ob.rc) return MPB_ECUDA;
-    CK(cudaMemsetAsync(oc.d, 0, (size_t)nc * 3 * 8, ctx->stream));
-    dim3 grid((unsigned)((m->n_seq + SCAN_THREADS - 1) / SCAN_THREADS), (unsigned)((nc + SCAN_GROUP - 1) / SCAN_GROUP));
-    LAUNCH(ctx, k_scan, grid, SCAN_THREADS, 0, m->planes, m->nsp, m->n_seq, m->lens, k, v, fmask, rmask,
-           cp.dev<int32_t>(), ca.dev<uint32_t>(), (long long)nc, oc.dev<unsigned long long>(),
-           bits_slot ? bs.dev<int32_t>() : nullptr, ob.dev<uint32_t>(), words, m->err);
+    if (ca.rc || bs.rc || chk.rc || oc.rc || ob.rc) return MPB_ECUDA;
+    uint32_t* partial = nullptr;
+    CK(cudaMallocAsync(&partial, (size_t)gx * nc * 3 * 4, ctx->stream));
+    dim3 grid((unsigned)gx, (unsigned)gy);
+    ctx->pending_units = (double)nc * (double)m->n_seq;  // candidate x sequence evaluations of this launch
+    if (bits_slot) {
+        LAUNCH(ctx, k_scan<true>, grid, SCAN_THREADS, 0, m->planes, m->nsp, m->n_seq, m->lens, k, v, fmask, rmask,
+               chk.dev<int4>(), n_chunks, cpb, tpb, ca.dev<uint32_t>(), partial, (long long)nc, bs.dev<int32_t>(),
+               ob.dev<uint32_t>(), words, m->err);
+    } else {
+        LAUNCH(ctx, k_scan<false>, grid, SCAN_THREADS, 0, m->planes, m->nsp, m->n_seq, m->lens, k, v, fmask, rmask,
+               chk.dev<int4>(), n_chunks, cpb, tpb, ca.dev<uint32_t>(), partial, (long long)nc, (const int32_t*)nullptr,
+               (uint32_t*)nullptr, words, m->err);
+    }
+    LAUNCH(ctx, k_scan_reduce, (unsigned)((nc * 3 + 255) / 256), 256, 0, partial, gx, (long long)nc * 3,
+           oc.dev<unsigned long long>());
+    CK(cudaFreeAsync(partial, ctx->stream));
     CK(oc.finish());
     CK(ob.finish());
-    if (oc.is_host() || ob.is_host() || cp.tmp || ca.tmp || bs.tmp) return check_flags(ctx, m->err);
-    return 0;
+    return check_flags(ctx, m->err);  // also keeps the host chunk list alive until the kernels are done
 }
 
 // per (window, sequence) table key, for the JSON side files
