@@ -146,6 +146,26 @@ int mpb_seqkeys(mpb_msa* msa, int k, const int32_t* win_pos, int32_t nw, uint64_
 int mpb_tm(mpb_ctx* ctx, const uint8_t* seqs2bit_hd, int k, int64_t n, const double* consts3, double* tm_hd,
            double* dh_hd, double* ds_hd);
 
+/* ---- primer-dimer predicates: core:457-503 dimer_check, finDimer_V4.py:191-224 ---------------------------------
+ * sets[n*32] 4-bit base sets of n primers (one byte per position, row stride 32), lens[n] (host arrays).
+ * Ends = suffixes of length min(max_end, len) .. min_end, longest first, each expanded in product order
+ * (core:457-464 current_end after the stable length sort of core:489).
+ * loss_table[33*33*33] (host): loss_table[(len*33+gc)*33+d2] != 0 when the reference's Loss test passes for an end of
+ * that length / GC count at distance d2 (the host evaluates core:192-193 itself, so >= vs > and the threshold are its
+ * business).  dg_consts[24] (host): stacking terms of core:466-485, see mpb_dimer.cu.  init_both = 0 selects the
+ * get_multiPrime.py:400-416 variant of dG (initiation term of the first base only).
+ */
+typedef struct mpb_dimer mpb_dimer;
+int mpb_dimer_prepare(mpb_ctx* ctx, const uint8_t* sets, const int32_t* lens, int32_t n, int min_end, int max_end,
+                      int init_both, const uint8_t* loss_table, const double* dg_consts, mpb_dimer** out);
+void mpb_dimer_free(mpb_dimer* d);
+/* expansion / end offsets per primer (host arrays of n+1) */
+int mpb_dimer_counts(mpb_dimer* d, int64_t* off_p, int64_t* off_e);
+/* For each pair (pi[q], pj[q]) (host arrays): first_hit[q] = e_index * n_expansions(pj) + p_index of the first
+ * (end of pi, expansion of pj) in reference order that forms a dimer, or -1; hit_d2[q] its distance 2. */
+int mpb_dimer_pairs(mpb_dimer* d, const int32_t* pi, const int32_t* pj, int64_t n_pairs, int64_t* first_hit,
+                    int32_t* hit_d2);
+
 #ifdef __cplusplus
 }
 #endif

@@ -45,6 +45,10 @@ SIGNATURES = {
     "mpb_scan": (C.c_int, [_P, C.c_int, C.c_int, C.c_uint32, C.c_uint32, _P, _P, C.c_int64, _P, _P, _P]),
     "mpb_seqkeys": (C.c_int, [_P, C.c_int, _P, C.c_int32, _P]),
     "mpb_tm": (C.c_int, [_P, _P, C.c_int, C.c_int64, _P, _P, _P, _P]),
+    "mpb_dimer_prepare": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int, C.c_int, C.c_int, _P, _P, C.POINTER(_P)]),
+    "mpb_dimer_free": (None, [_P]),
+    "mpb_dimer_counts": (C.c_int, [_P, _P, _P]),
+    "mpb_dimer_pairs": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P]),
 }
 
 
@@ -266,3 +270,43 @@ class Hist:
         if n.value:
             check(load().mpb_hist_exceptions(self.h, n.value, ptr(w), ptr(s), C.byref(n)))
         return w, s
+
+
+class Dimer:
+    """expansions + 3' end tables of a primer list on the device; pair queries (include/mpb200.h mpb_dimer_*)"""
+
+    def __init__(self, ctx: Context, sets_list, min_end: int, max_end: int, init_both: bool, loss_table: np.ndarray,
+                 dg_consts):
+        n = len(sets_list)
+        sets = np.zeros((n, 32), np.uint8)
+        lens = np.zeros(n, np.int32)
+        for i, s in enumerate(sets_list):
+            sets[i, :len(s)] = s
+            lens[i] = len(s)
+        self.n = n
+        self.lens = lens
+        cst = np.ascontiguousarray(dg_consts, dtype=np.float64)
+        tab = np.ascontiguousarray(loss_table, dtype=np.uint8)
+        assert tab.shape == (33, 33, 33) and cst.shape == (24,)
+        h = C.c_void_p()
+        check(load().mpb_dimer_prepare(ctx.h, ptr(sets), ptr(lens), n, min_end, max_end, int(init_both), ptr(tab),
+                                       ptr(cst), C.byref(h)))
+        self.h = h
+        self.off_p = np.zeros(n + 1, np.int64)
+        self.off_e = np.zeros(n + 1, np.int64)
+        check(load().mpb_dimer_counts(self.h, ptr(self.off_p), ptr(self.off_e)))
+
+    def pairs(self, pi, pj):
+        """first hit per pair: (order index or -1, d2)"""
+        pi = np.ascontiguousarray(pi, dtype=np.int32)
+        pj = np.ascontiguousarray(pj, dtype=np.int32)
+        hit = np.full(len(pi), -1, np.int64)
+        d2 = np.full(len(pi), -1, np.int32)
+        if len(pi):
+            check(load().mpb_dimer_pairs(self.h, ptr(pi), ptr(pj), len(pi), ptr(hit), ptr(d2)))
+        return hit, d2
+
+    def close(self):
+        if self.h:
+            load().mpb_dimer_free(self.h)
+            self.h = None

@@ -657,6 +657,7 @@ class NN_degenerate(object):
             exp_bases.extend(e)
         tm_raw = self.ctx.tm(np.asarray(exp_bases, np.uint8).reshape(-1, k), TM_CONSTS)
         seqkeys = self.msa.seqkeys(k, pos) if self.sidecars else None
+        dimer = self._self_dimer([chosen[wi].sets for wi in wis])        # core:487-503 for all windows at once
         out = []
         for n, wi in enumerate(wis):
             t, info = chosen[wi], accepted[wi]
@@ -675,7 +676,7 @@ class NN_degenerate(object):
             tm_avg = round(mean(tms), 2)
             perfect = int(counts[n][0])
             info_col = information(sets, gc_lo, gc_hi, self.distance)
-            if self_dimer(sets):
+            if dimer[n]:
                 continue                                                  # core:749-751
             row = [info["pos"], info["c_bit"], info["t_bit"], primer, n_degenerate(sets), nonsense, perfect,
                    t.init + t.fm, t.init + t.rm, tm_avg, info_col]
@@ -723,6 +724,12 @@ class NN_degenerate(object):
                     groups[1].setdefault(hap, []).append(s)
         f_dict, r_dict, g_dict = ({hap: [ids[s] for s in sorted(ss)] for hap, ss in dct.items()} for dct in groups)
         return [f_dict, r_dict], g_dict
+
+    def _self_dimer(self, sets_list):
+        if hasattr(self.ctx, "h"):
+            from .dimer import dimer_flags
+            return dimer_flags(self.ctx, sets_list)
+        return self.ctx.dimer_flags(sets_list)       # injected test backend
 
     # -- core:1133-1180 -------------------------------------------------------------------------------------
     def run(self):
@@ -783,12 +790,6 @@ def _key_string(key: int, k: int) -> str:
         out.append("ACGT-"[x % 5])
         x //= 5
     return "".join(out)
-
-
-def self_dimer(sets) -> bool:
-    """core:487-503 dimer_check, by enumeration (replaced by the dimer kernel for degenerate-heavy inputs)"""
-    from .dimer import self_dimer as impl
-    return impl(sets)
 
 
 def main(argv=None):

@@ -10,14 +10,15 @@
 #include <vector>
 
 #include "mpb200.h"
+#include "mpb_host.h"
 #include "mpb_device.cuh"
 
 // ------------------------------------------------------------------------------------------------------
-// host-side plumbing
+// host-side plumbing (shared pieces live in mpb_host.h)
 // ------------------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
 
-static int fail(int code, const char* fmt, ...) {
+int mpb_fail(int code, const char* fmt, ...) {
     char buf[512];
     va_list ap;
     va_start(ap, fmt);
@@ -26,29 +27,9 @@ static int fail(int code, const char* fmt, ...) {
     g_err = buf;
     return code;
 }
-
-#define CK(call)                                                                                   \
-    do {                                                                                           \
-        cudaError_t e__ = (call);                                                                  \
-        if (e__ != cudaSuccess)                                                                    \
-            return fail(e__ == cudaErrorMemoryAllocation ? MPB_ENOMEM : MPB_ECUDA, "%s:%d %s: %s", \
-                        __FILE__, __LINE__, #call, cudaGetErrorString(e__));                       \
-    } while (0)
-
-struct ProfRec {
-    const char* name;
-    cudaEvent_t e0, e1;
-    double units;  // algorithmic work units of this launch (kernel specific; evals for k_scan)
-};
-struct mpb_ctx {
-    int device;
-    cudaStream_t stream;
-    int64_t launches;
-    int sm_count;
-    bool profile;
-    std::vector<ProfRec> recs;
-    double pending_units;
-};
+#define fail mpb_fail
+#define CK MPB_CK
+#define LAUNCH MPB_LAUNCH
 
 struct mpb_msa {
     mpb_ctx* ctx;
@@ -204,25 +185,6 @@ extern "C" int mpb_ctx_sync(mpb_ctx* ctx) {
     return 0;
 }
 extern "C" int64_t mpb_ctx_launches(mpb_ctx* ctx) { return ctx ? ctx->launches : 0; }
-
-// every kernel goes through LAUNCH: counted, and (when profiling is on) bracketed by CUDA events on the stream
-#define LAUNCH(ctx, kern, grid, block, smem, ...)                                 \
-    do {                                                                          \
-        ProfRec pr__ = {#kern, nullptr, nullptr, (ctx)->pending_units};           \
-        if ((ctx)->profile) {                                                     \
-            CK(cudaEventCreate(&pr__.e0));                                        \
-            CK(cudaEventCreate(&pr__.e1));                                        \
-            CK(cudaEventRecord(pr__.e0, (ctx)->stream));                          \
-        }                                                                         \
-        kern<<<grid, block, smem, (ctx)->stream>>>(__VA_ARGS__);                  \
-        (ctx)->launches++;                                                        \
-        CK(cudaGetLastError());                                                   \
-        if ((ctx)->profile) {                                                     \
-            CK(cudaEventRecord(pr__.e1, (ctx)->stream));                          \
-            (ctx)->recs.push_back(pr__);                                          \
-        }                                                                         \
-        (ctx)->pending_units = 0;                                                 \
-    } while (0)
 
 extern "C" int mpb_ctx_profile(mpb_ctx* ctx, int enable) {
     if (!ctx) return fail(MPB_EINVAL, "ctx is NULL");

@@ -159,6 +159,75 @@ __device__ __noinline__ bool mpb_window_slow(const uint32_t* __restrict__ pl, in
     return ok;
 }
 
+// Terminal-gap patching of core:671-682 for a window that lies inside the row (p + k <= len), on bit-planes:
+// the leading gap run (g cells) is replaced by the last g bases left of the window, the trailing run by the first
+// g bases right of it — each only when the row holds that many bases there.  The flanks are found with clz / ffs
+// on the "any base" word of each column word instead of walking cell by cell.
+__device__ __forceinline__ void mpb_patch_edges(const uint32_t* __restrict__ pl, int64_t nsp, int64_t s, int len,
+                                                int p, int k, uint32_t kmask, Win& w) {
+    uint32_t gapv = ~(w.a | w.c | w.g | w.t) & kmask;
+    if (gapv & 1u) {  // leading run
+        const int g = __ffs(~gapv) - 1;  // < k because gapv != kmask
+        uint32_t pa = 0, pc = 0, pg = 0, pt = 0;
+        int got = 0;
+        int j = (p - 1) >> 5;
+        uint32_t below = (p & 31) ? ((1u << (p & 31)) - 1u) : 0xFFFFFFFFu;  // columns < p inside word j
+        for (; j >= 0 && got < g; --j) {
+            const uint32_t* q = pl + ((int64_t)j * 4) * nsp + s;
+            const uint32_t wa = q[0], wc = q[nsp], wg = q[2 * nsp], wt = q[3 * nsp];
+            uint32_t any = (wa | wc | wg | wt) & below;
+            below = 0xFFFFFFFFu;
+            while (any && got < g) {
+                const int b = 31 - __clz(any);
+                any &= ~(1u << b);
+                const int dst = g - 1 - got;  // nearest base goes right before the body
+                pa |= ((wa >> b) & 1u) << dst;
+                pc |= ((wc >> b) & 1u) << dst;
+                pg |= ((wg >> b) & 1u) << dst;
+                pt |= ((wt >> b) & 1u) << dst;
+                ++got;
+            }
+        }
+        if (p > 0 && got == g) {
+            w.a |= pa;
+            w.c |= pc;
+            w.g |= pg;
+            w.t |= pt;
+            gapv = ~(w.a | w.c | w.g | w.t) & kmask;
+        }
+    }
+    if ((gapv >> (k - 1)) & 1u) {  // trailing run (of the possibly updated window)
+        const int g = __clz(~(gapv << (32 - k)));  // run of ones ending at bit k-1
+        uint32_t pa = 0, pc = 0, pg = 0, pt = 0;
+        int got = 0;
+        const int c0 = p + k;
+        const int jlast = (len - 1) >> 5;
+        uint32_t above = ~((c0 & 31) ? ((1u << (c0 & 31)) - 1u) : 0u);  // columns >= c0 inside the first word
+        for (int j = c0 >> 5; j <= jlast && got < g && c0 < len; ++j) {
+            const uint32_t* q = pl + ((int64_t)j * 4) * nsp + s;
+            const uint32_t wa = q[0], wc = q[nsp], wg = q[2 * nsp], wt = q[3 * nsp];
+            uint32_t any = (wa | wc | wg | wt) & above;  // cells >= len are stored as zero
+            above = 0xFFFFFFFFu;
+            while (any && got < g) {
+                const int b = __ffs(any) - 1;
+                any &= any - 1;
+                const int dst = k - g + got;
+                pa |= ((wa >> b) & 1u) << dst;
+                pc |= ((wc >> b) & 1u) << dst;
+                pg |= ((wg >> b) & 1u) << dst;
+                pt |= ((wt >> b) & 1u) << dst;
+                ++got;
+            }
+        }
+        if (got == g) {
+            w.a |= pa;
+            w.c |= pc;
+            w.g |= pg;
+            w.t |= pt;
+        }
+    }
+}
+
 // Load the window starting at column p of sequence s.  Fast path: a funnel shift per plane.
 __device__ __forceinline__ bool mpb_load_window(const uint32_t* __restrict__ pl, int64_t nsp, int64_t s, int len,
                                                 int p, int k, uint32_t kmask, Win& w) {
@@ -171,9 +240,16 @@ __device__ __forceinline__ bool mpb_load_window(const uint32_t* __restrict__ pl,
     w.t = __funnelshift_r(w0[3 * nsp], w1[3 * nsp], sh) & kmask;
     uint32_t gapv = ~(w.a | w.c | w.g | w.t) & kmask;
     bool ok = true;
-    const bool edge = (gapv & 1u) | ((gapv >> (k - 1)) & 1u);
-    if ((p + k > len) || (edge && gapv != kmask)) {
-        ok = mpb_window_slow(pl, nsp, s, len, p, k, w);
+    if (p + k > len) {  // ragged row shorter than the window end: the generic cell-by-cell restatement
+        Win t;
+        ok = mpb_window_slow(pl, nsp, s, len, p, k, t);
+        w.a = t.a;
+        w.c = t.c;
+        w.g = t.g;
+        w.t = t.t;
+        gapv = ~(w.a | w.c | w.g | w.t) & kmask;
+    } else if (((gapv & 1u) | ((gapv >> (k - 1)) & 1u)) && gapv != kmask) {
+        mpb_patch_edges(pl, nsp, s, len, p, k, kmask, w);
         gapv = ~(w.a | w.c | w.g | w.t) & kmask;
     }
     w.gapv = gapv;

@@ -1,0 +1,311 @@
+// mpb_dimer.cu — primer-dimer predicates on the GPU (core:457-503 dimer_check, finDimer_V4.py:191-224,
+// get_Maxprimerset_V1.3.py:193-215, get_multiPrime.py:419-437).
+//
+// The reference enumerates, for a primer pair (i, j): every 3' end e of i (suffix lengths high to low, each suffix
+// expanded in product order) x every expansion p of j, takes the LEFTMOST occurrence idx of RC(e) in p and tests
+//     Loss(len, GC(e), 0, d2 = len(p) - len(e) - idx) >= threshold   or   (dG(e) < -5 and d2 == 0).
+// Here both primers' expansions are materialised once (2-bit packed), the Loss comparison is a host-built truth
+// table [len][GC][d2] (so it is decided by the reference's own float expression), dG(e) is summed in the reference's
+// operation order without FMA, and each (e, p) pair is one thread-iteration.  The first hit in reference order is
+// the minimum of e_index * n_p + p_index.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <vector>
+
+#include "mpb200.h"
+#include "mpb_host.h"
+
+#define DIMER_MAXLEN 32
+
+struct mpb_dimer {
+    mpb_ctx* ctx;
+    int n;
+    uint8_t* sets;       // [n][32] 4-bit sets
+    int32_t* lens;       // [n]
+    int64_t* off_p;      // [n+1] expansion offsets
+    int64_t* off_e;      // [n+1] end offsets
+    uint64_t* exp;       // packed expansions
+    uint64_t* end_rc;    // packed reverse complement of each end
+    uint32_t* end_info;  // len | gc << 8 | dgflag << 16
+    uint8_t* table;      // [33][33][33] loss >= threshold
+    std::vector<int64_t> h_off_p, h_off_e;
+};
+
+__constant__ uint8_t d_fold[16] = {1, 1, 1, 2, 1, 2, 2, 3, 1, 2, 2, 3, 2, 3, 3, 4};
+#define O2(a, b) ((a) | ((b) << 2))
+#define O3(a, b, c) ((a) | ((b) << 2) | ((c) << 4))
+#define O4(a, b, c, d) ((a) | ((b) << 2) | ((c) << 4) | ((d) << 6))
+// expansion order of each base set (core:105-107), see mpb_device.cuh
+__constant__ uint8_t d_order[16] = {0, 0, 1, O2(0, 1), 2, O2(0, 2), O2(2, 1), O3(2, 0, 1), 3, O2(0, 3), O2(1, 3),
+                                    O3(0, 3, 1), O2(2, 3), O3(2, 0, 3), O3(2, 3, 1), O4(0, 3, 2, 1)};
+
+// e-th expansion (product order, leftmost position slowest) of sets[a..b) -> bases packed 2 bits each, position a at
+// bits 0..1
+__device__ __forceinline__ uint64_t expand_packed(const uint8_t* sets, int a, int b, uint64_t e) {
+    uint64_t out = 0;
+    for (int i = b - 1; i >= a; --i) {
+        const int code = sets[i];
+        const unsigned n = d_fold[code];
+        const unsigned d = (unsigned)(e % n);
+        e /= n;
+        const uint64_t base = (d_order[code] >> (2 * d)) & 3u;
+        out |= base << (2 * (i - a));
+    }
+    return out;
+}
+
+__device__ __forceinline__ int find_owner(const int64_t* off, int n, int64_t idx) {
+    int lo = 0, hi = n;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (off[mid] <= idx) lo = mid;
+        else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void k_dimer_expand(const uint8_t* __restrict__ sets, const int32_t* __restrict__ lens,
+                               const int64_t* __restrict__ off_p, int n, uint64_t* __restrict__ exp) {
+    const int64_t total = off_p[n];
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int i = find_owner(off_p, n, idx);
+        exp[idx] = expand_packed(sets + (int64_t)i * DIMER_MAXLEN, 0, lens[i], (uint64_t)(idx - off_p[i]));
+    }
+}
+
+// dg consts: [0..15] stack[next][cur] = freedom*hbonds+penalty, [16..19] init (A,C,G,T), [20] terminal TA, [21] per-base
+// salt term, [22] symmetry, [23] threshold: dG(e) < -5 (after round(.,2))  <=>  g <= consts[23]
+__global__ void k_dimer_ends(const uint8_t* __restrict__ sets, const int32_t* __restrict__ lens,
+                             const int64_t* __restrict__ off_e, int n, int min_end, int max_end, int init_both,
+                             const double* __restrict__ cst, uint64_t* __restrict__ end_rc,
+                             uint32_t* __restrict__ end_info) {
+    const int64_t total = off_e[n];
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int i = find_owner(off_e, n, idx);
+        const uint8_t* S = sets + (int64_t)i * DIMER_MAXLEN;
+        const int k = lens[i];
+        int64_t r = idx - off_e[i];
+        // suffix lengths from high to low: min(max_end, k) .. min_end
+        int L = max_end < k ? max_end : k;
+        for (; L >= min_end; --L) {
+            int64_t cnt = 1;
+            for (int q = k - L; q < k; ++q) cnt *= d_fold[S[q]];
+            if (r < cnt) break;
+            r -= cnt;
+        }
+        const uint64_t e = expand_packed(S, k - L, k, (uint64_t)r);  // position j of the end at bits 2j
+        // reverse complement: rc[t] = 3 - e[L-1-t]
+        uint64_t rc = 0;
+        int gc = 0;
+        for (int t = 0; t < L; ++t) {
+            const uint64_t b = (e >> (2 * (L - 1 - t))) & 3u;
+            rc |= (3u - b) << (2 * t);
+            gc += (b == 1) | (b == 2);
+        }
+        // dG of the plain end (core:466-485 with a single expansion), reference operation order, no FMA
+        double g = 0.0;
+        for (int q = 0; q + 1 < L; ++q) {
+            const int cur = (int)((e >> (2 * q)) & 3u), nxt = (int)((e >> (2 * (q + 1))) & 3u);
+            g = __dadd_rn(g, cst[nxt * 4 + cur]);
+        }
+        const int b0 = (int)(e & 3u), bl = (int)((e >> (2 * (L - 1))) & 3u);
+        double t = init_both ? __dadd_rn(cst[16 + b0], cst[16 + bl]) : cst[16 + b0];
+        const bool ta = L >= 2 && ((e >> (2 * (L - 2))) & 3u) == 3u && bl == 0;  // end[-2:] == "TA"
+        if (ta) t = __dadd_rn(t, cst[20]);
+        g = __dadd_rn(g, t);
+        g = __dsub_rn(g, __dmul_rn(cst[21], (double)L));
+        bool sym = (L % 2) == 0;
+        for (int q = 0; sym && q < L / 2; ++q) sym = (((e >> (2 * q)) & 3u) + ((e >> (2 * (L / 2 + q))) & 3u)) == 3u;
+        if (sym) g = __dadd_rn(g, cst[22]);
+        const uint32_t flag = g <= cst[23] ? 1u : 0u;
+        end_rc[idx] = rc;
+        end_info[idx] = (uint32_t)L | ((uint32_t)gc << 8) | (flag << 16);
+    }
+}
+
+// leftmost occurrence of the L-base pattern rc inside the kj-base string p (both 2-bit packed), or -1
+__device__ __forceinline__ int find_leftmost(uint64_t p, int kj, uint64_t rc, int L) {
+    const uint64_t mask = L >= 32 ? ~0ull : ((1ull << (2 * L)) - 1ull);
+    for (int o = 0; o + L <= kj; ++o)
+        if (((p >> (2 * o)) & mask) == rc) return o;
+    return -1;
+}
+
+// block per pair: first hit (in reference order) among ends(i) x expansions(j)
+#define PAIR_THREADS 128
+__global__ void __launch_bounds__(PAIR_THREADS)
+k_dimer_pairs(const int32_t* __restrict__ pi, const int32_t* __restrict__ pj, const int32_t* __restrict__ lens,
+              const int64_t* __restrict__ off_p, const int64_t* __restrict__ off_e, const uint64_t* __restrict__ exp,
+              const uint64_t* __restrict__ end_rc, const uint32_t* __restrict__ end_info,
+              const uint8_t* __restrict__ table, long long* __restrict__ first_hit, int32_t* __restrict__ hit_d2) {
+    __shared__ unsigned long long best;
+    __shared__ int best_d2;
+    const int q = blockIdx.x;
+    const int i = pi[q], j = pj[q];
+    const int64_t ne = off_e[i + 1] - off_e[i], np = off_p[j + 1] - off_p[j];
+    const int kj = lens[j];
+    const unsigned long long total = (unsigned long long)ne * (unsigned long long)np;
+    if (threadIdx.x == 0) {
+        best = ~0ull;
+        best_d2 = -1;
+    }
+    __syncthreads();
+    for (unsigned long long base = 0; base < total; base += PAIR_THREADS) {
+        const unsigned long long idx = base + threadIdx.x;
+        if (idx < total) {
+            const int64_t e = (int64_t)(idx / (unsigned long long)np), p = (int64_t)(idx % (unsigned long long)np);
+            const uint32_t info = end_info[off_e[i] + e];
+            const int L = info & 255, gc = (info >> 8) & 255;
+            const int o = find_leftmost(exp[off_p[j] + p], kj, end_rc[off_e[i] + e], L);
+            if (o >= 0) {
+                const int d2 = kj - L - o;
+                if (table[(L * 33 + gc) * 33 + d2] || (d2 == 0 && (info >> 16))) {
+                    const unsigned long long old = atomicMin(&best, idx);
+                    (void)old;
+                }
+            }
+        }
+        __syncthreads();
+        if (best != ~0ull) break;  // later chunks only hold larger order indices
+        __syncthreads();
+    }
+    __syncthreads();
+    if (best != ~0ull) {
+        const unsigned long long idx = best;
+        if ((idx % PAIR_THREADS) == threadIdx.x) {
+            const int64_t e = (int64_t)(idx / (unsigned long long)np), p = (int64_t)(idx % (unsigned long long)np);
+            const int L = end_info[off_e[i] + e] & 255;
+            best_d2 = kj - L - find_leftmost(exp[off_p[j] + p], kj, end_rc[off_e[i] + e], L);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        first_hit[q] = best == ~0ull ? -1ll : (long long)best;
+        if (hit_d2) hit_d2[q] = best_d2;
+    }
+}
+
+extern "C" int mpb_dimer_prepare(mpb_ctx* ctx, const uint8_t* sets, const int32_t* lens, int32_t n, int min_end,
+                                 int max_end, int init_both, const uint8_t* loss_table, const double* dg_consts,
+                                 mpb_dimer** out) {
+    if (!ctx || !sets || !lens || !loss_table || !dg_consts || !out) return mpb_fail(MPB_EINVAL, "NULL argument");
+    if (n < 1 || min_end < 1 || max_end < min_end || max_end > DIMER_MAXLEN)
+        return mpb_fail(MPB_EINVAL, "bad n=%d or end range %d..%d", n, min_end, max_end);
+    MPB_CK(cudaSetDevice(mpb_ctx_device(ctx)));
+    cudaStream_t st = mpb_ctx_stream(ctx);
+    mpb_dimer* d = new mpb_dimer;
+    d->ctx = ctx;
+    d->n = n;
+    d->sets = nullptr;
+    d->h_off_p.assign(n + 1, 0);
+    d->h_off_e.assign(n + 1, 0);
+    static const int fold[16] = {1, 1, 1, 2, 1, 2, 2, 3, 1, 2, 2, 3, 2, 3, 3, 4};
+    for (int i = 0; i < n; ++i) {
+        const int k = lens[i];
+        if (k < min_end || k > DIMER_MAXLEN) {
+            delete d;
+            return mpb_fail(MPB_EINVAL, "primer %d has length %d (supported: %d..%d)", i, k, min_end, DIMER_MAXLEN);
+        }
+        int64_t deg = 1, ends = 0, suf = 1;
+        for (int q = k - 1; q >= 0; --q) {
+            const int f = fold[sets[(int64_t)i * DIMER_MAXLEN + q] & 15];
+            if (f == 0 || sets[(int64_t)i * DIMER_MAXLEN + q] == 0) {
+                delete d;
+                return mpb_fail(MPB_EINVAL, "primer %d holds a gap / empty set", i);
+            }
+            deg *= f;
+            suf *= f;
+            const int L = k - q;
+            if (L >= min_end && L <= max_end) ends += suf;
+            if (deg > (1ll << 40)) break;
+        }
+        if (deg > (1ll << 24)) {
+            delete d;
+            return mpb_fail(MPB_EINVAL, "primer %d expands to more than 2^24 sequences", i);
+        }
+        d->h_off_p[i + 1] = d->h_off_p[i] + deg;
+        d->h_off_e[i + 1] = d->h_off_e[i] + ends;
+    }
+    const int64_t tp = d->h_off_p[n], te = d->h_off_e[n];
+    double* cst = nullptr;
+    cudaError_t e = cudaMalloc(&d->sets, (size_t)n * DIMER_MAXLEN);
+    if (e == cudaSuccess) e = cudaMalloc(&d->lens, (size_t)n * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&d->off_p, (size_t)(n + 1) * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&d->off_e, (size_t)(n + 1) * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&d->exp, (size_t)tp * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&d->end_rc, (size_t)(te ? te : 1) * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&d->end_info, (size_t)(te ? te : 1) * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&d->table, 33 * 33 * 33);
+    if (e == cudaSuccess) e = cudaMalloc(&cst, 24 * 8);
+    if (e != cudaSuccess) return mpb_fail(MPB_ENOMEM, "dimer tables: %s", cudaGetErrorString(e));
+    MPB_CK(cudaMemcpyAsync(d->sets, sets, (size_t)n * DIMER_MAXLEN, cudaMemcpyHostToDevice, st));
+    MPB_CK(cudaMemcpyAsync(d->lens, lens, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    MPB_CK(cudaMemcpyAsync(d->off_p, d->h_off_p.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
+    MPB_CK(cudaMemcpyAsync(d->off_e, d->h_off_e.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
+    MPB_CK(cudaMemcpyAsync(d->table, loss_table, 33 * 33 * 33, cudaMemcpyHostToDevice, st));
+    MPB_CK(cudaMemcpyAsync(cst, dg_consts, 24 * 8, cudaMemcpyHostToDevice, st));
+    const int sm = mpb_ctx_sms(ctx);
+    unsigned g1 = (unsigned)((tp + 255) / 256), g2 = (unsigned)((te + 255) / 256);
+    if (g1 > (unsigned)sm * 32) g1 = sm * 32;
+    if (g2 > (unsigned)sm * 32) g2 = sm * 32;
+    MPB_LAUNCH(ctx, k_dimer_expand, g1, 256, 0, d->sets, d->lens, d->off_p, n, d->exp);
+    if (te > 0)
+        MPB_LAUNCH(ctx, k_dimer_ends, g2, 256, 0, d->sets, d->lens, d->off_e, n, min_end, max_end, init_both, cst,
+                   d->end_rc, d->end_info);
+    MPB_CK(cudaStreamSynchronize(st));
+    cudaFree(cst);
+    *out = d;
+    return 0;
+}
+
+extern "C" void mpb_dimer_free(mpb_dimer* d) {
+    if (!d) return;
+    cudaFree(d->sets);
+    cudaFree(d->lens);
+    cudaFree(d->off_p);
+    cudaFree(d->off_e);
+    cudaFree(d->exp);
+    cudaFree(d->end_rc);
+    cudaFree(d->end_info);
+    cudaFree(d->table);
+    delete d;
+}
+
+extern "C" int mpb_dimer_counts(mpb_dimer* d, int64_t* off_p, int64_t* off_e) {
+    if (!d) return mpb_fail(MPB_EINVAL, "NULL argument");
+    if (off_p) memcpy(off_p, d->h_off_p.data(), (size_t)(d->n + 1) * 8);
+    if (off_e) memcpy(off_e, d->h_off_e.data(), (size_t)(d->n + 1) * 8);
+    return 0;
+}
+
+extern "C" int mpb_dimer_pairs(mpb_dimer* d, const int32_t* pi, const int32_t* pj, int64_t n_pairs,
+                               int64_t* first_hit, int32_t* hit_d2) {
+    if (!d || !pi || !pj || !first_hit) return mpb_fail(MPB_EINVAL, "NULL argument");
+    if (n_pairs < 1) return 0;
+    for (int64_t q = 0; q < n_pairs; ++q)
+        if (pi[q] < 0 || pi[q] >= d->n || pj[q] < 0 || pj[q] >= d->n)
+            return mpb_fail(MPB_EINVAL, "pair %lld outside the primer table", (long long)q);
+    mpb_ctx* ctx = d->ctx;
+    MPB_CK(cudaSetDevice(mpb_ctx_device(ctx)));
+    cudaStream_t st = mpb_ctx_stream(ctx);
+    int32_t *dpi, *dpj, *dd2;
+    long long* dfh;
+    MPB_CK(cudaMallocAsync(&dpi, n_pairs * 4, st));
+    MPB_CK(cudaMallocAsync(&dpj, n_pairs * 4, st));
+    MPB_CK(cudaMallocAsync(&dd2, n_pairs * 4, st));
+    MPB_CK(cudaMallocAsync(&dfh, n_pairs * 8, st));
+    MPB_CK(cudaMemcpyAsync(dpi, pi, n_pairs * 4, cudaMemcpyHostToDevice, st));
+    MPB_CK(cudaMemcpyAsync(dpj, pj, n_pairs * 4, cudaMemcpyHostToDevice, st));
+    MPB_LAUNCH(ctx, k_dimer_pairs, (unsigned)n_pairs, PAIR_THREADS, 0, dpi, dpj, d->lens, d->off_p, d->off_e, d->exp,
+               d->end_rc, d->end_info, d->table, dfh, dd2);
+    MPB_CK(cudaMemcpyAsync(first_hit, dfh, n_pairs * 8, cudaMemcpyDeviceToHost, st));
+    if (hit_d2) MPB_CK(cudaMemcpyAsync(hit_d2, dd2, n_pairs * 4, cudaMemcpyDeviceToHost, st));
+    MPB_CK(cudaStreamSynchronize(st));
+    cudaFreeAsync(dpi, st);
+    cudaFreeAsync(dpj, st);
+    cudaFreeAsync(dd2, st);
+    cudaFreeAsync(dfh, st);
+    return 0;
+}

@@ -46,6 +46,9 @@ class Context:
             return np.array(tm), np.array(dh), np.array(ds)
         return np.array(tm)
 
+    def dimer_flags(self, sets_list):
+        return np.array([o.self_dimer("".join(CODE_CHARS[c] for c in s)) for s in sets_list], bool)
+
     def sync(self):
         pass
 

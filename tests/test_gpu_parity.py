@@ -33,3 +33,28 @@ def test_tm_kernel_bit_exact():
             assert tm[i] == o.tm_unrounded(s), (s, tm[i], o.tm_unrounded(s))
             assert (dh[i], ds[i]) == o.delta_h_s(s)
     ctx.close()
+
+
+def test_self_dimer_engine_vs_oracle():
+    """core:487-503 on random degenerate primers (up to 192 expansions): device flags == oracle"""
+    import json
+    import os
+    import random
+    from multiprime_b200 import _lib, dimer
+    from multiprime_b200.iupac import sets_of
+    from oracle import mp_oracle as o
+    from tests.helpers import GOLDEN
+    random.seed(11)
+    kat = json.load(open(os.path.join(GOLDEN, "kat.json")))["filters"]
+    primers = list(kat)
+    codes = "ACGTRYMKSWHBVDN"
+    while len(primers) < 260:
+        k = random.choice([16, 18, 20, 22, 25])
+        p = "".join(random.choice("ACGT" * 7 + codes) for _ in range(k))
+        if o.degeneracy(p) <= 192:
+            primers.append(p)
+    ctx = _lib.Context(0)
+    flags = dimer.dimer_flags(ctx, [sets_of(p) for p in primers])
+    for p, f in zip(primers, flags):
+        assert bool(f) == o.self_dimer(p), p
+    ctx.close()
