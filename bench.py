@@ -174,9 +174,14 @@ def run_b200(args):
     ids = synth.seq_ids(n_seq, rank * n_seq)
     stream = torch.cuda.current_stream().cuda_stream
 
+    comm = None
+    if world > 1:
+        from multiprime_b200.comm import TorchComm
+        comm = TorchComm(torch.device("cuda", local))
+
     def make_app():
         return core.NN_degenerate(seq_file=None, outfile="", packed=(ids, packed_pinned, n_col, None), device=local,
-                                  sidecars=False, stream=stream, **PARAMS)
+                                  sidecars=False, stream=stream, comm=comm, row0=rank * n_seq, **PARAMS)
 
     def barrier():
         if world > 1:
@@ -232,10 +237,7 @@ def run_b200(args):
             results["scan_calls"] = app.stats["scan_calls"] / args.steps
             results["candidates"] = app.stats["candidates"] / args.steps
             app.ctx.profile(False)
-    ev = torch.tensor([results["evals_per_step"]], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ev, op=dist.ReduceOp.SUM)
-    evals_all = float(ev.item())
+    evals_all = float(results["evals_per_step"])      # already global: calls x (sequences of ALL shards)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -253,6 +255,7 @@ def run_b200(args):
         "config": {"workload": "synthetic MSA %dx%d per GPU (multiprime_b200/synth.py seed 20240923), k=%d, -n %d -d %d "
                                "-v %d, %d windows, %d rows out" % (n_seq, n_col, K, DNUM, DEG, VAR, len(positions),
                                                                   results["value"]["rows"]),
+                   "parallelism": "sequence shards x%d, all-reduce of coverage counts per scan round" % world,
                    "l2": "inputs (%.0f MB of bit-planes + GB-sized haplotype tables) exceed the 126 MB L2" %
                          (n_seq * n_col / 2 / 1e6),
                    "evals_per_step": evals_all, "scan_launches_per_step": results["scan_calls"],

@@ -72,6 +72,9 @@ int mpb_msa_upload(mpb_ctx* ctx, const uint8_t* packed4_hd, int64_t n_seq, int64
 void mpb_msa_free(mpb_msa* msa);
 int64_t mpb_msa_nseq(const mpb_msa* msa);
 
+/* Sequence-sharded runs: global index of this shard's first sequence (enters the first-seen order of the tables). */
+int mpb_msa_set_row0(mpb_msa* msa, int64_t row0);
+
 /* core:617-627 seq_attribute, per-sequence part: number of leading gap cells and length after stripping
  * trailing gaps.  The two quantiles (core:629-633) are taken by the host. */
 int mpb_seq_attr(mpb_msa* msa, int32_t* lead_gaps_hd, int32_t* rstrip_len_hd);
@@ -83,6 +86,11 @@ int mpb_seq_attr(mpb_msa* msa, int32_t* lead_gaps_hd, int32_t* rstrip_len_hd);
  */
 int mpb_hist_build(mpb_msa* msa, int k, int v, const int32_t* win_pos, int32_t nw, int log2_cap, mpb_hist** out);
 void mpb_hist_free(mpb_hist* h);
+
+/* Copy all entries of the windows with sel[i] != 0 (host array) into compact arrays: window i's entries land in
+ * [win_off[i], win_off[i+1]) (host array of nw+1, sized by the caller from mpb_hist_stats' nuniq; unordered). */
+int mpb_hist_export(mpb_hist* h, const uint8_t* sel, const int64_t* win_off, uint64_t* keys_hd, uint32_t* cnt_hd,
+                    uint64_t* first_hd);
 
 /* Insert foreign (key, count, first) triples into the tables (multi-GPU merge of per-rank tables).
  * win_off (host, nw+1) delimits the triples of each window inside the hd arrays. */

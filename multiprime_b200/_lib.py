@@ -33,6 +33,8 @@ SIGNATURES = {
     "mpb_msa_upload": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, _P, C.POINTER(_P)]),
     "mpb_msa_free": (None, [_P]),
     "mpb_msa_nseq": (C.c_int64, [_P]),
+    "mpb_msa_set_row0": (C.c_int, [_P, C.c_int64]),
+    "mpb_hist_export": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "mpb_seq_attr": (C.c_int, [_P, _P, _P]),
     "mpb_hist_build": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int32, C.c_int, C.POINTER(_P)]),
     "mpb_hist_free": (None, [_P]),
@@ -160,6 +162,9 @@ class Msa:
             load().mpb_msa_free(self.h)
             self.h = None
 
+    def set_row0(self, row0: int):
+        check(load().mpb_msa_set_row0(self.h, row0))
+
     def seq_attr(self):
         lead = np.empty(self.n_seq, np.int32)
         rstrip = np.empty(self.n_seq, np.int32)
@@ -253,6 +258,26 @@ class Hist:
         n = min(n.value, max_n)
         order = np.argsort(first[:n], kind="stable")
         return keys[:n][order], cnt[:n][order], first[:n][order]
+
+    def export(self, sel, counts):
+        """entries of the selected windows; counts[w] = entries of window w -> (win_off, keys, cnt, first)"""
+        sel = np.ascontiguousarray(sel, dtype=np.uint8)
+        off = np.zeros(self.nw + 1, np.int64)
+        off[1:] = np.cumsum(np.where(sel != 0, counts, 0))
+        total = int(off[-1])
+        keys = np.empty(total, np.uint64)
+        cnt = np.empty(total, np.uint32)
+        first = np.empty(total, np.uint64)
+        if total:
+            check(load().mpb_hist_export(self.h, ptr(sel), ptr(off), ptr(keys), ptr(cnt), ptr(first)))
+        return off, keys, cnt, first
+
+    def merge(self, win_off, keys, cnt, first):
+        win_off = np.ascontiguousarray(win_off, dtype=np.int64)
+        if win_off[-1] > 0:
+            check(load().mpb_hist_merge(self.h, ptr(win_off), ptr(np.ascontiguousarray(keys, dtype=np.uint64)),
+                                        ptr(np.ascontiguousarray(cnt, dtype=np.uint32)),
+                                        ptr(np.ascontiguousarray(first, dtype=np.uint64))))
 
     def match(self, q_win, q_allow):
         q_win = np.ascontiguousarray(q_win, dtype=np.int32)

@@ -1,0 +1,73 @@
+"""Sequence-shard communicator: one process per GPU, torch.distributed (NCCL over NVLink on the GPU box, gloo in the
+CPU tests).  All collectives of the hot path are here: an integer all-reduce of coverage counts per scan round, an
+all-reduce of gap counts / entropy bounds and an all-gather of compact haplotype entries per window batch."""
+from __future__ import annotations
+
+import numpy as np
+
+
+class NoComm:
+    world = 1
+    rank = 0
+
+    def allreduce_sum(self, arr):
+        return arr
+
+    def allgather_concat(self, arr):
+        return arr, np.array([len(arr)], np.int64)
+
+    def allgather_object(self, obj):
+        return [obj]
+
+    def barrier(self):
+        pass
+
+
+class TorchComm:
+    def __init__(self, device=None, group=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.group = torch, dist, group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" \
+                else torch.device("cpu")
+        self.device = device
+
+    def _to(self, arr):
+        t = self.torch.from_numpy(np.ascontiguousarray(arr))
+        return t.to(self.device) if self.device.type != "cpu" else t.clone()
+
+    def allreduce_sum(self, arr):
+        """element-wise sum over ranks of an int64 / float64 array"""
+        arr = np.asarray(arr)
+        kind = np.float64 if arr.dtype.kind == "f" else np.int64
+        t = self._to(arr.astype(kind))
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+        return t.cpu().numpy().astype(arr.dtype).reshape(arr.shape)
+
+    def allgather_concat(self, arr):
+        """concatenation over ranks of 1-d arrays of different lengths -> (all, lengths per rank)"""
+        arr = np.ascontiguousarray(arr)
+        n = self.torch.tensor([arr.shape[0]], dtype=self.torch.int64, device=self.device)
+        sizes = [self.torch.zeros_like(n) for _ in range(self.world)]
+        self.dist.all_gather(sizes, n, group=self.group)
+        sizes = np.array([int(x.item()) for x in sizes], np.int64)
+        m = int(sizes.max())
+        view = arr.view(np.uint8).reshape(arr.shape[0], -1) if arr.shape[0] else np.zeros((0, arr.dtype.itemsize), np.uint8)
+        pad = np.zeros((m, arr.dtype.itemsize), np.uint8)
+        pad[:arr.shape[0]] = view
+        t = self._to(pad)
+        outs = [self.torch.zeros_like(t) for _ in range(self.world)]
+        self.dist.all_gather(outs, t, group=self.group)
+        parts = [o.cpu().numpy()[:sizes[r]].reshape(-1).view(arr.dtype) for r, o in enumerate(outs)]
+        return np.concatenate(parts) if parts else arr, sizes
+
+    def allgather_object(self, obj):
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj, group=self.group)
+        return out
+
+    def barrier(self):
+        self.dist.barrier(group=self.group)

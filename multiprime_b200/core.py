@@ -19,6 +19,7 @@ from statistics import mean
 import numpy as np
 
 from . import _lib
+from .comm import NoComm
 from .iupac import (BASES, CODE_CHARS, CHAR_CODE, FOLD, allow_masks, comp_set, degeneracy, expand_keys, expand_strings,
                     n_degenerate, primer_string, rc_sets, sets_of)
 
@@ -315,7 +316,7 @@ class NN_degenerate(object):
     def __init__(self, seq_file, primer_length=18, coverage=0.8, number_of_dege_bases=18, score_of_dege_bases=1000,
                  product_len=250, position="2,-1", variation=2, raw_entropy_threshold=3.6, distance=4, GC="0.4,0.6",
                  nproc=10, outfile="", device=0, windows_per_batch=0, sidecars=True, alignment=None, packed=None,
-                 stream=None, _backend=None):
+                 stream=None, comm=None, row0=0, _backend=None):
         self.primer_length = primer_length
         self.coverage = coverage
         self.number_of_dege_bases = number_of_dege_bases
@@ -342,12 +343,17 @@ class NN_degenerate(object):
             self._codes = codes
             packed4 = pack4(codes)
         self._packed4 = packed4                 # host copy: only read for the rare IUPAC-in-gap-row side-file entries
-        self.total_sequence_number = len(self.ids)
+        self.comm = comm or NoComm()            # sequence shards: this process holds rows [row0, row0 + n_local)
+        self.row0 = row0
+        self.n_local = len(self.ids)
+        self.total_sequence_number = int(self.comm.allreduce_sum(np.array([self.n_local], np.int64))[0])
         self.lens = lens if lens is not None else np.full(len(self.ids), self.n_col, np.int32)
         backend = _backend or _lib                # tests inject tests/fake_device.py to exercise the host logic
         self.ctx = backend.Context(device, stream)
         self.msa = backend.Msa(self.ctx, packed4, len(self.ids), self.n_col,
                                lens=None if (self.lens == self.n_col).all() else self.lens)
+        if row0:
+            self.msa.set_row0(row0)
         self.position_list = self.seq_attribute()
         self.start_position, self.stop_position, self.length = self.position_list
         self.entropy_threshold = self.entropy_threshold_adjust(self.length)
@@ -356,6 +362,9 @@ class NN_degenerate(object):
     # -- core:617-649 -------------------------------------------------------------------------------------
     def seq_attribute(self):
         lead, rstrip = self.msa.seq_attr()
+        if self.comm.world > 1:                 # the quantiles are over all sequences
+            lead, _ = self.comm.allgather_concat(lead)
+            rstrip, _ = self.comm.allgather_concat(rstrip)
         start = int(np.quantile(lead.reshape(1, -1), self.coverage, method="higher"))
         stop = int(np.quantile(rstrip.reshape(1, -1), self.coverage, method="lower"))
         if stop - start < int(self.product):
@@ -375,11 +384,21 @@ class NN_degenerate(object):
     def _iupac_gap_groups(self, hist, wi, pos):
         """gap rows that hold IUPAC cells are not in the device table (their raw k-mer needs 4 bits per cell):
         group the few of them by raw k-mer here -> [(first order, count)]"""
-        exc_w, exc_s = self._exceptions(hist)
-        raw = {}
-        for s in exc_s[exc_w == wi].tolist():
-            raw.setdefault(self._window_cells(s, pos), [s << 16, 0])[1] += 1
-        return [(f, c) for f, c in raw.values()]
+        cache = getattr(hist, "_iupac_groups", None)
+        if cache is None:
+            exc_w, exc_s = self._exceptions(hist)
+            local = {}
+            for w, s in zip(exc_w.tolist(), exc_s.tolist()):
+                g = local.setdefault((w, self._window_cells(s, hist.win_pos[w])), [(self.row0 + s) << 16, 0])
+                g[1] += 1
+            cache = {}
+            for part in self.comm.allgather_object(local):          # shards in rank order = sequence order
+                for key, (f, c) in part.items():
+                    g = cache.setdefault(key, [f, 0])
+                    g[0] = min(g[0], f)
+                    g[1] += c
+            hist._iupac_groups = cache
+        return [(f, c) for (w, _), (f, c) in cache.items() if w == wi]
 
     def _entropy_exact(self, hist, wi, pos, n_unique):
         """the reference's left-to-right float sums (core:602-614), over the table dumped in first-seen order"""
@@ -459,7 +478,7 @@ class NN_degenerate(object):
         positions = [int(p) for p in positions]
         if not positions:
             return []
-        per_batch = self.windows_per_batch or _default_batch(self.total_sequence_number)
+        per_batch = self.windows_per_batch or _default_batch(self.n_local)
         out = []
         for b0 in range(0, len(positions), per_batch):
             out.extend(self._design_batch(positions[b0:b0 + per_batch]))
@@ -470,11 +489,15 @@ class NN_degenerate(object):
         self.stats["windows"] += len(positions)
         with self.msa.hist(k, v, positions) as hist:
             st = hist.stats()
+            if self.comm.world > 1:
+                st = self._merge_shards(hist, st)
             accepted = {}
             sel = np.zeros(len(positions), np.uint8)
             for wi, pos in enumerate(positions):
                 gap_n = int(st["gap_n"][wi])
                 if round(gap_n / N, 2) >= (1 - self.coverage):          # core:713
+                    continue
+                if not st.get("merged", ALL_MERGED)[wi]:                 # entropy bound of the shards already above the gate
                     continue
                 n_cover_u, n_gap_u, n_gapfree = (int(x) for x in st["nuniq"][wi])
                 if n_cover_u < 1:                                        # core:716
@@ -505,6 +528,39 @@ class NN_degenerate(object):
                 tracks[wi] = [_Track(seed, layers) for seed in info["seeds"]]
             self._run_tracks(positions, accepted, tracks)
             return self._finish(hist, positions, accepted, tracks)
+
+    def _merge_shards(self, hist, st):
+        """Sequence-sharded run: make the tables of every window that can still pass the gates GLOBAL on every rank.
+        Windows whose entropy is certainly above the threshold are left alone: entropy is concave, so the total-entropy
+        of the pooled sequences is at least the size-weighted mean of the shards' own total-entropies."""
+        comm, N, n_loc = self.comm, self.total_sequence_number, self.n_local
+        gap_n = comm.allreduce_sum(st["gap_n"])
+        iupac_gap = comm.allreduce_sum(st["n_iupac_gap"])
+        ent = st["ent"]
+        s0 = ent[:, 0] + ent[:, 2]
+        s1 = ent[:, 1] + ent[:, 3]
+        bound = comm.allreduce_sum(-(s1 - s0 * math.log2(n_loc))) / N          # <= true tBit
+        gap_fail = np.array([round(int(g) / N, 2) >= (1 - self.coverage) for g in gap_n])
+        merged = (~gap_fail) & (bound <= self.entropy_threshold + 0.006)
+        counts = st["nuniq"][:, 0] + st["nuniq"][:, 1]
+        off, keys, cnt, first = hist.export(merged.astype(np.uint8), counts)
+        sizes_all, _ = comm.allgather_concat(np.diff(off))                     # world x nw entry counts
+        sizes_all = sizes_all.reshape(comm.world, hist.nw)
+        keys_all, lens_k = comm.allgather_concat(keys)
+        cnt_all, _ = comm.allgather_concat(cnt)
+        first_all, _ = comm.allgather_concat(first)
+        starts = np.concatenate([[0], np.cumsum(lens_k)])
+        for r in range(comm.world):
+            if r == comm.rank:
+                continue
+            off_r = np.concatenate([[0], np.cumsum(sizes_all[r])]).astype(np.int64)
+            a, b = int(starts[r]), int(starts[r + 1])
+            hist.merge(off_r, keys_all[a:b], cnt_all[a:b], first_all[a:b])
+        st2 = hist.stats()                                                     # global for the merged windows
+        st2["gap_n"] = gap_n
+        st2["n_iupac_gap"] = iupac_gap
+        st2["merged"] = merged
+        return st2
 
     def _entropy(self, hist, st, wi, pos, gap_n, n_unique):
         """(cBit, tBit) rounded as the reference rounds them, or None when tBit exceeds the threshold"""
@@ -569,6 +625,7 @@ class NN_degenerate(object):
             order = np.argsort(np.asarray(cand_pos, dtype=np.int64), kind="stable")
             counts, _ = self.msa.scan(k, v, self.fmask, self.rmask, np.asarray(cand_pos, np.int32)[order],
                                       np.asarray(cand_allow, np.uint32)[order])
+            counts = self.comm.allreduce_sum(counts)        # the one collective of a scan round
             self.stats["scan_calls"] += 1
             self.stats["candidates"] += len(cand_pos)
             inv = np.empty(len(order), np.int64)
@@ -647,6 +704,7 @@ class NN_degenerate(object):
         pos = np.asarray([accepted[wi]["pos"] for wi in wis], np.int32)
         slots = np.arange(len(wis), dtype=np.int32) if self.sidecars else None
         counts, bits = self.msa.scan(k, v, self.fmask, self.rmask, pos, allow, bits_slot=slots)
+        counts = self.comm.allreduce_sum(counts)
         self.stats["scan_calls"] += 1
         distinct = hist.match(np.asarray(wis, np.int32), allow)
         # Tm of every expansion of every chosen primer in one launch
@@ -691,7 +749,7 @@ class NN_degenerate(object):
         """core:1116-1125 / 696-698: {haplotype: [ids]} of the sequences the final primer does not cover (F, R) and
         of the gap rows, rebuilt from the scan's per-sequence bits and the per-sequence table keys"""
         k, v = self.primer_length, self.variation
-        N = self.total_sequence_number
+        N = self.n_local
         ids = self.ids
         unpack = lambda words: np.unpackbits(words.view(np.uint8), bitorder="little")[:N].astype(bool)
         non_f, non_r, gap = unpack(bits[0]), unpack(bits[1]), unpack(bits[2])
@@ -736,12 +794,17 @@ class NN_degenerate(object):
         k = self.primer_length
         recs = self.design(range(self.start_position, self.stop_position - k))
         recs.sort(key=lambda r: r["row"][0])
-        with open(self.outfile, "w") as fo:
-            fo.write("\t".join(TSV_HEADER) + "\n")
-            for r in recs:
-                fo.write("\t".join(map(str, r["row"])) + "\n")
+        if self.comm.rank == 0:
+            with open(self.outfile, "w") as fo:
+                fo.write("\t".join(TSV_HEADER) + "\n")
+                for r in recs:
+                    fo.write("\t".join(map(str, r["row"])) + "\n")
         non_cov = {r["row"][0]: r["non_cov"] for r in recs} if self.sidecars else {}
         gap_ids = {r["row"][0]: r["gap_ids"] for r in recs} if self.sidecars else {}
+        if self.comm.world > 1:                 # shards hold disjoint id lists: concatenate them in rank order
+            non_cov, gap_ids = _merge_sidecars(self.comm.allgather_object((non_cov, gap_ids)))
+            if self.comm.rank != 0:
+                return recs
         with open(self.outfile + ".non_coverage_seq_id_json", "w") as fj:
             json.dump(non_cov, fj, indent=4)
         with open(self.outfile + ".gap_seq_id_json", "w") as fg:
@@ -754,6 +817,29 @@ class NN_degenerate(object):
 
 
 # ----------------------------------------------------------------------------------------------------------
+def _merge_sidecars(parts):
+    non_cov, gap_ids = {}, {}
+    for nc, gi in parts:
+        for pos, (f, r) in nc.items():
+            tgt = non_cov.setdefault(pos, [{}, {}])
+            for src, dst in ((f, tgt[0]), (r, tgt[1])):
+                for hap, ids in src.items():
+                    dst.setdefault(hap, []).extend(ids)
+        for pos, d in gi.items():
+            tgt = gap_ids.setdefault(pos, {})
+            for hap, ids in d.items():
+                tgt.setdefault(hap, []).extend(ids)
+    return non_cov, gap_ids
+
+
+class _AllMerged:
+    def __getitem__(self, i):
+        return True
+
+
+ALL_MERGED = _AllMerged()
+
+
 def _default_batch(n_seq: int) -> int:
     # table bytes per window = 20 * 2^ceil(log2(2n+64)); keep a batch under ~8 GB
     cap = 1 << max(6, int(math.ceil(math.log2(2 * n_seq + 64))))

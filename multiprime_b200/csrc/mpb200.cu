@@ -38,6 +38,7 @@ struct mpb_msa {
     uint32_t* planes;   // [ncw][4][nsp]
     int32_t* lens;      // [nsp]
     int* err;           // device error flags
+    int64_t row0;       // global index of local sequence 0 (sequence-sharded runs)
 };
 
 struct mpb_hist {
@@ -271,6 +272,7 @@ extern "C" int mpb_msa_upload(mpb_ctx* ctx, const uint8_t* packed4, int64_t n_se
     m->planes = nullptr;
     m->lens = nullptr;
     m->err = nullptr;
+    m->row0 = 0;
     size_t pbytes = (size_t)m->ncw * 4 * m->nsp * sizeof(uint32_t);
     cudaError_t e = cudaMalloc(&m->planes, pbytes);
     if (e == cudaSuccess) e = cudaMalloc(&m->lens, m->nsp * sizeof(int32_t));
@@ -313,6 +315,11 @@ extern "C" void mpb_msa_free(mpb_msa* m) {
     delete m;
 }
 extern "C" int64_t mpb_msa_nseq(const mpb_msa* m) { return m ? m->n_seq : 0; }
+extern "C" int mpb_msa_set_row0(mpb_msa* m, int64_t row0) {
+    if (!m || row0 < 0 || row0 + m->n_seq >= (1ll << 47)) return fail(MPB_EINVAL, "bad row0");
+    m->row0 = row0;
+    return 0;
+}
 
 // core:625-627: leading gap count and length without trailing gaps, per sequence
 __global__ void k_seq_attr(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq, const int32_t* __restrict__ lens,
@@ -358,8 +365,9 @@ k_hist(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq, const int32_
        const int32_t* __restrict__ win_pos, int nw, uint64_t* __restrict__ keys, uint32_t* __restrict__ cnt,
        uint64_t* __restrict__ first, int log2cap, unsigned long long* __restrict__ gap_n,
        unsigned long long* __restrict__ iupac_gap_n, int32_t* __restrict__ exc, unsigned long long* __restrict__ exc_n,
-       long long exc_max, int* __restrict__ err) {
+       long long exc_max, long long row0, int* __restrict__ err) {
     const int64_t s = (int64_t)blockIdx.x * HIST_THREADS + threadIdx.x;
+    const uint64_t gs = (uint64_t)(row0 + s);  // global sequence index: first-seen order across shards
     const bool valid = s < n_seq;
     const int lane = threadIdx.x & 31;
     const uint32_t kmask = (k == 32) ? 0xFFFFFFFFu : ((1u << k) - 1u);
@@ -387,7 +395,7 @@ k_hist(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq, const int32_
             const uint64_t key = mpb_key(w.c, w.g, w.t, w.gapv, k);
             const unsigned peers = __match_any_sync(smask, key);
             if (lane == __ffs(peers) - 1)  // lowest lane = lowest sequence index = first seen
-                mpb_table_add(K, C, F, log2cap, key, (uint32_t)__popc(peers), (uint64_t)s << 16, err);
+                mpb_table_add(K, C, F, log2cap, key, (uint32_t)__popc(peers), gs << 16, err);
         } else if (cover) {
             const uint32_t total = mpb_expansions(w);
             if (total > MPB_MAX_EXP) {
@@ -396,12 +404,12 @@ k_hist(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq, const int32_
                 for (uint32_t e = 0; e < total; ++e) {
                     uint32_t a, c, g, t;
                     mpb_expand(w, e, a, c, g, t);
-                    mpb_table_add(K, C, F, log2cap, mpb_key(c, g, t, w.gapv, k), 1u, ((uint64_t)s << 16) | e, err);
+                    mpb_table_add(K, C, F, log2cap, mpb_key(c, g, t, w.gapv, k), 1u, (gs << 16) | e, err);
                 }
             }
         } else if (isgap) {
             if (w.multi == 0) {
-                mpb_table_add(K, C, F, log2cap, mpb_key(w.c, w.g, w.t, w.gapv, k), 1u, (uint64_t)s << 16, err);
+                mpb_table_add(K, C, F, log2cap, mpb_key(w.c, w.g, w.t, w.gapv, k), 1u, gs << 16, err);
             } else {
                 atomicAdd(&iupac_gap_n[wi], 1ull);
                 unsigned long long slot = atomicAdd(exc_n, 1ull);
@@ -465,7 +473,7 @@ extern "C" int mpb_hist_build(mpb_msa* m, int k, int v, const int32_t* win_pos, 
     ctx->pending_units = (double)nw * (double)m->n_seq;  // (window, sequence) k-mers extracted
     LAUNCH(ctx, k_hist, dim3(gx, gy), HIST_THREADS, 0, m->planes, m->nsp, m->n_seq, m->lens, k, v, h->win_pos, nw,
            h->keys, h->cnt, h->first, log2_cap, h->gap_n, h->iupac_gap_n, h->exc, h->exc_n, (long long)h->exc_max,
-           m->err);
+           (long long)m->row0, m->err);
     int rc = check_flags(ctx, m->err);  // also makes the host win_pos copy safe to release
     if (rc) {
         mpb_hist_free(h);
@@ -487,6 +495,58 @@ extern "C" void mpb_hist_free(mpb_hist* h) {
     if (h->exc) cudaFreeAsync(h->exc, st);
     if (h->exc_n) cudaFreeAsync(h->exc_n, st);
     delete h;
+}
+
+// copy the entries of the selected windows into one compact array; cursor[w] starts at win_off[w]
+__global__ void k_hist_export(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ cnt,
+                              const uint64_t* __restrict__ first, int log2cap, const int32_t* __restrict__ sel_idx,
+                              unsigned long long* __restrict__ cursor, const long long* __restrict__ win_end,
+                              uint64_t* __restrict__ ok, uint32_t* __restrict__ oc, uint64_t* __restrict__ of) {
+    const int wi = sel_idx[blockIdx.y];
+    const uint64_t cap = 1ull << log2cap;
+    const uint64_t* K = keys + (uint64_t)wi * cap;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t key = K[i];
+        if (key == MPB_KEY_EMPTY_D) continue;
+        const unsigned long long slot = atomicAdd(&cursor[wi], 1ull);
+        if ((long long)slot < win_end[wi]) {
+            ok[slot] = key;
+            oc[slot] = cnt[(uint64_t)wi * cap + i];
+            of[slot] = first[(uint64_t)wi * cap + i];
+        }
+    }
+}
+
+extern "C" int mpb_hist_export(mpb_hist* h, const uint8_t* sel, const int64_t* win_off, uint64_t* keys_hd,
+                               uint32_t* cnt_hd, uint64_t* first_hd) {
+    if (!h || !sel || !win_off || !keys_hd || !cnt_hd || !first_hd) return fail(MPB_EINVAL, "NULL argument");
+    mpb_ctx* ctx = h->msa->ctx;
+    CK(cudaSetDevice(ctx->device));
+    std::vector<int32_t> idx;
+    std::vector<unsigned long long> cur(h->nw, 0);
+    std::vector<long long> end(h->nw, 0);
+    for (int i = 0; i < h->nw; ++i) {
+        cur[i] = (unsigned long long)win_off[i];
+        end[i] = win_off[i + 1];
+        if (sel[i]) idx.push_back(i);
+        else if (win_off[i + 1] != win_off[i]) return fail(MPB_EINVAL, "win_off reserves room for unselected window %d", i);
+    }
+    const int64_t total = win_off[h->nw];
+    if (idx.empty() || total <= 0) return 0;
+    InBuf si(ctx, idx.data(), idx.size() * 4), dc(ctx, cur.data(), cur.size() * 8), de(ctx, end.data(), end.size() * 8);
+    OutBuf ok(ctx, keys_hd, total * 8), oc(ctx, cnt_hd, total * 4), of(ctx, first_hd, total * 8);
+    if (si.rc || dc.rc || de.rc || ok.rc || oc.rc || of.rc) return MPB_ECUDA;
+    const uint64_t cap = 1ull << h->log2cap;
+    unsigned gx = (unsigned)((cap + 255) / 256);
+    if (gx > 64) gx = 64;
+    LAUNCH(ctx, k_hist_export, dim3(gx, (unsigned)idx.size()), 256, 0, h->keys, h->cnt, h->first, h->log2cap,
+           si.dev<int32_t>(), (unsigned long long*)dc.d, de.dev<long long>(), ok.dev<uint64_t>(), oc.dev<uint32_t>(),
+           of.dev<uint64_t>());
+    CK(ok.finish());
+    CK(oc.finish());
+    CK(of.finish());
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
 }
 
 __global__ void k_hist_merge(const long long* __restrict__ win_off, int nw, const uint64_t* __restrict__ in_keys,

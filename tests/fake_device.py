@@ -65,9 +65,13 @@ class Msa:
         codes[:, 1::2] = packed4 >> 4
         lens = np.full(n_seq, n_col) if lens is None else lens
         self.rows = ["".join(CODE_CHARS[c] for c in codes[i, :lens[i]]) for i in range(n_seq)]
+        self.row0 = 0
 
     def close(self):
         pass
+
+    def set_row0(self, row0):
+        self.row0 = row0
 
     def seq_attr(self):
         lead = np.array([len(s) - len(s.lstrip("-")) for s in self.rows], np.int32)
@@ -146,11 +150,11 @@ class Hist:
                         nig += 1
                         self.exc.append((wi, si))
                     else:
-                        e = tab.setdefault(hap_key(w), [0, si << 16])
+                        e = tab.setdefault(hap_key(w), [0, (msa.row0 + si) << 16])
                         e[0] += 1
                 else:
                     for ei, hap in enumerate(o.expand(w)):
-                        e = tab.setdefault(hap_key(hap), [0, (si << 16) | ei])
+                        e = tab.setdefault(hap_key(hap), [0, ((msa.row0 + si) << 16) | ei])
                         e[0] += 1
             self.tables.append(tab)
             self.gap_n.append(gaps)
@@ -220,6 +224,26 @@ class Hist:
         items = sorted(self.tables[w].items(), key=lambda kv: kv[1][1])
         return (np.array([k for k, _ in items], np.uint64), np.array([v[0] for _, v in items], np.uint32),
                 np.array([v[1] for _, v in items], np.uint64))
+
+    def export(self, sel, counts):
+        off = np.zeros(self.nw + 1, np.int64)
+        keys, cnt, first = [], [], []
+        for wi, tab in enumerate(self.tables):
+            if sel[wi]:
+                assert len(tab) == counts[wi]
+                for key, (c, f) in tab.items():
+                    keys.append(key)
+                    cnt.append(c)
+                    first.append(f)
+            off[wi + 1] = len(keys)
+        return off, np.array(keys, np.uint64), np.array(cnt, np.uint32), np.array(first, np.uint64)
+
+    def merge(self, win_off, keys, cnt, first):
+        for wi in range(self.nw):
+            for i in range(int(win_off[wi]), int(win_off[wi + 1])):
+                e = self.tables[wi].setdefault(int(keys[i]), [0, int(first[i])])
+                e[0] += int(cnt[i])
+                e[1] = min(e[1], int(first[i]))
 
     def match(self, q_win, q_allow):
         q_allow = np.asarray(q_allow).reshape(-1, 4)
