@@ -174,6 +174,12 @@ int mpb_dimer_counts(mpb_dimer* d, int64_t* off_p, int64_t* off_e);
 int mpb_dimer_pairs(mpb_dimer* d, const int32_t* pi, const int32_t* pj, int64_t n_pairs, int64_t* first_hit,
                     int32_t* hit_d2);
 
+/* All pairs (i, j >= i) with i in [row0, row1): finDimer_V4.py:191-224.  Host output arrays of capacity max_hits
+ * receive the pairs that form a dimer (sorted by i, j), the first-hit order index and its distance 2; *n_tested the
+ * pairs that survived the 5-mer prefilter.  Needs min_end == 5 at mpb_dimer_prepare. */
+int mpb_dimer_grid(mpb_dimer* d, int32_t row0, int32_t row1, int64_t max_hits, int32_t* hit_i, int32_t* hit_j,
+                   int64_t* hit_order, int32_t* hit_d2, int64_t* n_hits, int64_t* n_tested);
+
 #ifdef __cplusplus
 }
 #endif

@@ -51,6 +51,8 @@ SIGNATURES = {
     "mpb_dimer_free": (None, [_P]),
     "mpb_dimer_counts": (C.c_int, [_P, _P, _P]),
     "mpb_dimer_pairs": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P]),
+    "mpb_dimer_grid": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int64, _P, _P, _P, _P, C.POINTER(C.c_int64),
+                                  C.POINTER(C.c_int64)]),
 }
 
 
@@ -330,6 +332,18 @@ class Dimer:
         if len(pi):
             check(load().mpb_dimer_pairs(self.h, ptr(pi), ptr(pj), len(pi), ptr(hit), ptr(d2)))
         return hit, d2
+
+    def grid(self, row0: int, row1: int, max_hits: int = 1 << 22):
+        """dimer pairs (i in [row0,row1), j >= i) -> (i, j, order index, d2, pairs tested after the prefilter)"""
+        hi = np.empty(max_hits, np.int32)
+        hj = np.empty(max_hits, np.int32)
+        ho = np.empty(max_hits, np.int64)
+        hd = np.empty(max_hits, np.int32)
+        n, nt = C.c_int64(), C.c_int64()
+        check(load().mpb_dimer_grid(self.h, row0, row1, max_hits, ptr(hi), ptr(hj), ptr(ho), ptr(hd), C.byref(n),
+                                    C.byref(nt)))
+        n = n.value
+        return hi[:n], hj[:n], ho[:n], hd[:n], nt.value
 
     def close(self):
         if self.h:

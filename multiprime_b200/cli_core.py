@@ -1,0 +1,60 @@
+"""Command line of the drop-in multiPrime-core.py: the reference's flags and defaults (core:60-102), its output files
+and its closing `INFO ... Total times` line."""
+from __future__ import annotations
+
+import argparse
+import time
+
+
+def parseArg(argv=None):
+    parser = argparse.ArgumentParser(description="For degenerate primer design")
+    parser.add_argument("-i", "--input", type=str, required=True,
+                        help="Input file: multi-alignment output (muscle or others).", metavar="<file>")
+    parser.add_argument("-l", "--plen", type=int, default=18, help="Length of primer. Default: 18.", metavar="<int>")
+    parser.add_argument("-n", "--dnum", type=int, default=4, help="Max number of degenerate. Default: 4.",
+                        metavar="<int>")
+    parser.add_argument("-d", "--degeneracy", type=int, default=10, help="Max degeneracy of primer. Default: 10.",
+                        metavar="<int>")
+    parser.add_argument("-v", "--variation", type=int, default=1, help="Max mismatch number of primer. Default: 1",
+                        metavar="<int>")
+    parser.add_argument("-e", "--entropy", type=float, default=3.6,
+                        help="Entropy threshold of a primer-length window; windows above it are skipped. Default: 3.6.",
+                        metavar="<float>")
+    parser.add_argument("-g", "--gc", type=str, default="0.2,0.7",
+                        help="Filter primers by GC content. Default [0.2,0.7].", metavar="<str>")
+    parser.add_argument("-s", "--size", type=int, default=100,
+                        help="Filter primers by mini PRODUCT size. Default 100.", metavar="<int>")
+    parser.add_argument("-f", "--fraction", type=float, default=0.8,
+                        help="Filter primers by match fraction. Default: 0.8.", metavar="<float>")
+    parser.add_argument("-c", "--coordinate", type=str, default="1,2,-1",
+                        help="Primer positions where a mismatch disqualifies coverage-with-error "
+                             "(>0: from the 5' end, <0: from the 3' end). Default: 1,2,-1.", metavar="<str>")
+    parser.add_argument("-p", "--proc", type=int, default=20,
+                        help="Number of process to launch (accepted for compatibility; the scan runs on the GPU). "
+                             "Default: 20.", metavar="<int>")
+    parser.add_argument("-a", "--away", type=int, default=4,
+                        help="Filter hairpin structure: minimal distance between the paired bases. Default: 4.",
+                        metavar="<int>")
+    parser.add_argument("-o", "--out", type=str, required=True, help="output file", metavar="<file>")
+    parser.add_argument("--device", type=int, default=0, help=argparse.SUPPRESS)
+    return parser.parse_args(argv)
+
+
+def main(argv=None):
+    e1 = time.time()
+    args = parseArg(argv)
+    from .core import NN_degenerate
+    app = NN_degenerate(seq_file=args.input, primer_length=args.plen, coverage=args.fraction,
+                        number_of_dege_bases=args.dnum, score_of_dege_bases=args.degeneracy,
+                        raw_entropy_threshold=args.entropy, product_len=args.size, position=args.coordinate,
+                        variation=args.variation, distance=args.away, GC=args.gc, nproc=args.proc, outfile=args.out,
+                        device=args.device)
+    app.run()
+    app.close()
+    e2 = time.time()
+    print("INFO {} Total times: {}".format(time.strftime("%Y-%m-%d %H:%M:%S", time.localtime(time.time())),
+                                           round(float(e2 - e1), 2)))
+
+
+if __name__ == "__main__":
+    main()

@@ -239,11 +239,11 @@ def gc_content(sets) -> float:
             new[g + 1] += m * n_gc
         dist = new
     total = sum(dist)
-    acc = Fraction(0)
+    acc = 0
     for g, m in enumerate(dist):
         if m:
-            acc += m * Fraction(round(g / k, 3))  # statistics.mean: exact rational mean of the floats
-    return round(float(acc / total), 2)
+            acc += m * int(round(g / k, 3) * 1152921504606846976.0)   # exact: round(g/k, 3) is 0 or >= 2^-8
+    return round(acc / (total << 60), 2)                               # statistics.mean: exact rational mean
 
 
 def has_repeat(sets) -> bool:
@@ -293,11 +293,12 @@ def information(sets, gc_lo: float, gc_hi: float, distance: int):
 
 class _Track:
     """one run of core:860-920 coverage_stast (NM or MM seed) advanced in lock step with the scan"""
-    __slots__ = ("seed", "sets", "nn", "nn_cov", "init", "fm", "rm", "state", "opts", "trace", "seed_cover")
+    __slots__ = ("seed", "sets", "nn", "nn_cov", "init", "fm", "rm", "state", "opts", "trace", "seed_cover", "allow")
 
     def __init__(self, seed, nn):
         self.seed = seed
         self.sets = [1 << b for b in seed]
+        self.allow = allow_masks(self.sets)           # kept in step with `sets`
         self.nn = nn                                  # list of k-1 flat 4x4 lists; layers are copied on write
         self.nn_cov = [nn[j][seed[j] * 4 + seed[j + 1]] for j in range(len(seed) - 1)]
         self.init = 0
@@ -397,8 +398,11 @@ class NN_degenerate(object):
                     g = cache.setdefault(key, [f, 0])
                     g[0] = min(g[0], f)
                     g[1] += c
-            hist._iupac_groups = cache
-        return [(f, c) for (w, _), (f, c) in cache.items() if w == wi]
+            by_win = {}
+            for (w, _), (f, c) in cache.items():
+                by_win.setdefault(w, []).append((f, c))
+            cache = hist._iupac_groups = by_win
+        return cache.get(wi, [])
 
     def _entropy_exact(self, hist, wi, pos, n_unique):
         """the reference's left-to-right float sums (core:602-614), over the table dumped in first-seen order"""
@@ -603,36 +607,36 @@ class NN_degenerate(object):
                 pos = accepted[wi]["pos"]
                 if t.state == "seed":
                     cand_pos.append(pos)
-                    cand_allow.append(allow_masks(t.sets))
+                    cand_allow.extend(t.allow)
                     owners.append((t, "seed", None))
                 else:
                     t.opts = refine_options(t.sets, t.seed, t.nn_cov, t.nn)
+                    al = t.allow
                     for oi, opt in enumerate(t.opts):
                         if opt is None:
                             continue
                         p, b = opt[0], opt[1]
-                        trial = list(t.sets)
-                        trial[p] = 1 << b
-                        cand_pos.append(pos)
-                        cand_allow.append(allow_masks(trial))
+                        bit = 1 << p
+                        assert not t.sets[p] & (1 << b), "refinement would re-add a base (reference raises KeyError)"
+                        cand_pos.append(pos)                      # primer with position p := base b alone
+                        cand_allow.extend((al[x] | bit) if x == b else (al[x] & ~bit) for x in range(4))
                         owners.append((t, "trial", oi))
-                        new = list(t.sets)
-                        assert not new[p] & (1 << b), "refinement would re-add a base (reference raises KeyError)"
-                        new[p] |= 1 << b
-                        cand_pos.append(pos)
-                        cand_allow.append(allow_masks(new))
+                        cand_pos.append(pos)                      # primer with base b added at position p
+                        cand_allow.extend((al[x] | bit) if x == b else al[x] for x in range(4))
                         owners.append((t, "new", oi))
-            order = np.argsort(np.asarray(cand_pos, dtype=np.int64), kind="stable")
-            counts, _ = self.msa.scan(k, v, self.fmask, self.rmask, np.asarray(cand_pos, np.int32)[order],
-                                      np.asarray(cand_allow, np.uint32)[order])
+            pos_arr = np.array(cand_pos, dtype=np.int32)
+            order = np.argsort(pos_arr, kind="stable")
+            counts, _ = self.msa.scan(k, v, self.fmask, self.rmask, pos_arr[order],
+                                      np.array(cand_allow, dtype=np.uint32).reshape(-1, 4)[order])
             counts = self.comm.allreduce_sum(counts)        # the one collective of a scan round
             self.stats["scan_calls"] += 1
             self.stats["candidates"] += len(cand_pos)
             inv = np.empty(len(order), np.int64)
             inv[order] = np.arange(len(order))
             got = {}
+            counts_l = counts[inv].tolist()
             for ci, (t, kind, oi) in enumerate(owners):
-                got.setdefault(id(t), {})[(kind, oi)] = counts[inv[ci]]
+                got.setdefault(id(t), {})[(kind, oi)] = counts_l[ci]
             nxt = []
             for wi, t in live:
                 total = accepted[wi]["cover_number"]
@@ -660,6 +664,7 @@ class NN_degenerate(object):
                 else:
                     p, b, layers, cov_new = opt
                     t.sets[p] |= 1 << b
+                    t.allow[b] |= 1 << p
                     t.nn = list(t.nn)
                     for j, layer in layers.items():
                         t.nn[j] = layer
@@ -731,7 +736,7 @@ class NN_degenerate(object):
                     nonsense -= 1
             a, cnt = spans[n]
             tms = [round(float(x), 2) for x in tm_raw[a:a + cnt]]
-            tm_avg = round(mean(tms), 2)
+            tm_avg = round(exact_mean(tms), 2)
             perfect = int(counts[n][0])
             info_col = information(sets, gc_lo, gc_hi, self.distance)
             if dimer[n]:
@@ -840,10 +845,21 @@ class _AllMerged:
 ALL_MERGED = _AllMerged()
 
 
+def exact_mean(vals) -> float:
+    """statistics.mean of floats (exact rational mean, correctly rounded once) without Fractions: every value is
+    scaled by 2^60 exactly (holds for 2^-8 <= |x| < 2^11, i.e. any Tm / GC fraction; else fall back)"""
+    if all((x == 0.0) or (0.00390625 <= abs(x) < 2048.0) for x in vals):
+        total = 0
+        for x in vals:
+            total += int(x * 1152921504606846976.0)
+        return total / (len(vals) << 60)
+    return mean(vals)
+
+
 def _default_batch(n_seq: int) -> int:
-    # table bytes per window = 20 * 2^ceil(log2(2n+64)); keep a batch under ~8 GB
+    # table bytes per window = 20 * 2^ceil(log2(2n+64)); keep a batch under ~48 GB of the 180 GB HBM
     cap = 1 << max(6, int(math.ceil(math.log2(2 * n_seq + 64))))
-    return max(1, min(4096, int(8e9 // (20 * cap))))
+    return max(1, min(4096, int(48e9 // (20 * cap))))
 
 
 def _near_half(x: float) -> bool:

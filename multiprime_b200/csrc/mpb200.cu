@@ -584,21 +584,28 @@ extern "C" int mpb_hist_merge(mpb_hist* h, const int64_t* win_off, const uint64_
     return check_flags(ctx, h->msa->err);
 }
 
-// one block per window: entropy ingredients, distinct counts, most frequent gap-free haplotype
+// entropy ingredients, distinct counts and the most frequent gap-free haplotype of every window.  SB blocks share a
+// window; each writes one partial record, the final (deterministic, fixed-order) combination happens in
+// mpb_hist_stats on the host over nw x SB records.
 #define STATS_THREADS 256
+#define STATS_MAX_SB 64
 struct Best {
     unsigned long long cnt, first, key;
 };
-__device__ __forceinline__ bool better(const Best& x, const Best& y) {  // x beats y
+__device__ __host__ __forceinline__ bool better(const Best& x, const Best& y) {  // x beats y
     return x.cnt > y.cnt || (x.cnt == y.cnt && x.first < y.first);
 }
+struct StatsPart {
+    double s0c, s1c, s0g, s1g;
+    long long nc, ng, ngf;
+    Best best;
+};
 
 __global__ void __launch_bounds__(STATS_THREADS)
 k_hist_stats(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ cnt, const uint64_t* __restrict__ first,
-             int log2cap, int k, int v, double* __restrict__ ent, long long* __restrict__ nuniq,
-             unsigned long long* __restrict__ mm_key, long long* __restrict__ mm_cnt,
-             unsigned long long* __restrict__ mm_first) {
-    const int wi = blockIdx.x;
+             int log2cap, int k, int v, StatsPart* __restrict__ part) {
+    const int wi = blockIdx.y;
+    const int sb = gridDim.x;
     const uint64_t cap = 1ull << log2cap;
     const uint64_t* K = keys + (uint64_t)wi * cap;
     const uint32_t* C = cnt + (uint64_t)wi * cap;
@@ -606,7 +613,7 @@ k_hist_stats(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ cnt
     double s0c = 0, s1c = 0, s0g = 0, s1g = 0;
     long long nc = 0, ng = 0, ngf = 0;
     Best best = {0ull, ~0ull, MPB_KEY_EMPTY_D};
-    for (uint64_t i = threadIdx.x; i < cap; i += STATS_THREADS) {
+    for (uint64_t i = (uint64_t)blockIdx.x * STATS_THREADS + threadIdx.x; i < cap; i += (uint64_t)sb * STATS_THREADS) {
         const uint64_t key = K[i];
         if (key == MPB_KEY_EMPTY_D) continue;
         const double c = (double)C[i];
@@ -636,7 +643,7 @@ k_hist_stats(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ cnt
     }
     __shared__ double sd[4][STATS_THREADS / 32];
     __shared__ long long sl[3][STATS_THREADS / 32];
-    __shared__ Best sb[STATS_THREADS / 32];
+    __shared__ Best sbest[STATS_THREADS / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int o = 16; o > 0; o >>= 1) {
         s0c += __shfl_xor_sync(0xffffffffu, s0c, o);
@@ -660,35 +667,30 @@ k_hist_stats(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ cnt
         sl[0][warp] = nc;
         sl[1][warp] = ng;
         sl[2][warp] = ngf;
-        sb[warp] = best;
+        sbest[warp] = best;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
+        StatsPart r = {sd[0][0], sd[1][0], sd[2][0], sd[3][0], sl[0][0], sl[1][0], sl[2][0], sbest[0]};
         for (int w = 1; w < STATS_THREADS / 32; ++w) {
-            sd[0][0] += sd[0][w];
-            sd[1][0] += sd[1][w];
-            sd[2][0] += sd[2][w];
-            sd[3][0] += sd[3][w];
-            sl[0][0] += sl[0][w];
-            sl[1][0] += sl[1][w];
-            sl[2][0] += sl[2][w];
-            if (better(sb[w], sb[0])) sb[0] = sb[w];
+            r.s0c += sd[0][w];
+            r.s1c += sd[1][w];
+            r.s0g += sd[2][w];
+            r.s1g += sd[3][w];
+            r.nc += sl[0][w];
+            r.ng += sl[1][w];
+            r.ngf += sl[2][w];
+            if (better(sbest[w], r.best)) r.best = sbest[w];
         }
-        if (ent) {
-            ent[wi * 4 + 0] = sd[0][0];
-            ent[wi * 4 + 1] = sd[1][0];
-            ent[wi * 4 + 2] = sd[2][0];
-            ent[wi * 4 + 3] = sd[3][0];
-        }
-        if (nuniq) {
-            nuniq[wi * 3 + 0] = sl[0][0];
-            nuniq[wi * 3 + 1] = sl[1][0];
-            nuniq[wi * 3 + 2] = sl[2][0];
-        }
-        if (mm_key) mm_key[wi] = sb[0].key;
-        if (mm_cnt) mm_cnt[wi] = (long long)sb[0].cnt;
-        if (mm_first) mm_first[wi] = sb[0].first;
+        part[(long long)wi * sb + blockIdx.x] = r;
     }
+}
+
+static int blocks_per_window(mpb_ctx* ctx, int log2cap, int nw) {
+    long long sb = (1ll << log2cap) / (STATS_THREADS * 32);
+    if (sb < 1) sb = 1;
+    if (sb > STATS_MAX_SB) sb = STATS_MAX_SB;
+    return (int)sb;
 }
 
 extern "C" int mpb_hist_stats(mpb_hist* h, int64_t* gap_n, double* ent, int64_t* nuniq, uint64_t* mm_key,
@@ -697,42 +699,77 @@ extern "C" int mpb_hist_stats(mpb_hist* h, int64_t* gap_n, double* ent, int64_t*
     mpb_ctx* ctx = h->msa->ctx;
     CK(cudaSetDevice(ctx->device));
     const size_t nw = h->nw;
-    OutBuf o_ent(ctx, ent, nw * 4 * 8), o_nu(ctx, nuniq, nw * 3 * 8), o_mk(ctx, mm_key, nw * 8), o_mc(ctx, mm_cnt, nw * 8),
-        o_mf(ctx, mm_first, nw * 8);
-    if (o_ent.rc || o_nu.rc || o_mk.rc || o_mc.rc || o_mf.rc) return MPB_ENOMEM;
-    LAUNCH(ctx, k_hist_stats, (unsigned)nw, STATS_THREADS, 0, h->keys, h->cnt, h->first, h->log2cap, h->k, h->v,
-           o_ent.dev<double>(), o_nu.dev<long long>(), o_mk.dev<unsigned long long>(), o_mc.dev<long long>(),
-           o_mf.dev<unsigned long long>());
-    CK(o_ent.finish());
-    CK(o_nu.finish());
-    CK(o_mk.finish());
-    CK(o_mc.finish());
-    CK(o_mf.finish());
-    bool sync = o_ent.is_host() || o_nu.is_host() || o_mk.is_host() || o_mc.is_host() || o_mf.is_host();
-    if (gap_n) {
-        const bool dev = is_device_ptr(gap_n);
-        CK(cudaMemcpyAsync(gap_n, h->gap_n, nw * 8, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
-        sync = sync || !dev;
+    const int sb = blocks_per_window(ctx, h->log2cap, h->nw);
+    StatsPart* dpart = nullptr;
+    CK(cudaMallocAsync(&dpart, nw * sb * sizeof(StatsPart), ctx->stream));
+    LAUNCH(ctx, k_hist_stats, dim3((unsigned)sb, (unsigned)nw), STATS_THREADS, 0, h->keys, h->cnt, h->first, h->log2cap,
+           h->k, h->v, dpart);
+    std::vector<StatsPart> part(nw * sb);
+    CK(cudaMemcpyAsync(part.data(), dpart, nw * sb * sizeof(StatsPart), cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<long long> hg(nw), hi(nw);
+    CK(cudaMemcpyAsync(hg.data(), h->gap_n, nw * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(hi.data(), h->iupac_gap_n, nw * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaFreeAsync(dpart, ctx->stream));
+    std::vector<double> h_ent(nw * 4);
+    std::vector<long long> h_nu(nw * 3), h_mc(nw);
+    std::vector<unsigned long long> h_mk(nw), h_mf(nw);
+    for (size_t w = 0; w < nw; ++w) {
+        StatsPart r = part[w * sb];
+        for (int b = 1; b < sb; ++b) {
+            const StatsPart& q = part[w * sb + b];
+            r.s0c += q.s0c;
+            r.s1c += q.s1c;
+            r.s0g += q.s0g;
+            r.s1g += q.s1g;
+            r.nc += q.nc;
+            r.ng += q.ng;
+            r.ngf += q.ngf;
+            if (better(q.best, r.best)) r.best = q.best;
+        }
+        h_ent[w * 4 + 0] = r.s0c;
+        h_ent[w * 4 + 1] = r.s1c;
+        h_ent[w * 4 + 2] = r.s0g;
+        h_ent[w * 4 + 3] = r.s1g;
+        h_nu[w * 3 + 0] = r.nc;
+        h_nu[w * 3 + 1] = r.ng;
+        h_nu[w * 3 + 2] = r.ngf;
+        h_mk[w] = r.best.key;
+        h_mc[w] = (long long)r.best.cnt;
+        h_mf[w] = r.best.first;
     }
-    if (n_iupac_gap) {
-        const bool dev = is_device_ptr(n_iupac_gap);
-        CK(cudaMemcpyAsync(n_iupac_gap, h->iupac_gap_n, nw * 8, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
-                           ctx->stream));
-        sync = sync || !dev;
+    struct Out {
+        void* dst;
+        const void* src;
+        size_t bytes;
+    } outs[] = {{gap_n, hg.data(), nw * 8},      {ent, h_ent.data(), nw * 32},  {nuniq, h_nu.data(), nw * 24},
+                {mm_key, h_mk.data(), nw * 8},   {mm_cnt, h_mc.data(), nw * 8}, {mm_first, h_mf.data(), nw * 8},
+                {n_iupac_gap, hi.data(), nw * 8}};
+    bool any_dev = false;
+    for (auto& o : outs) {
+        if (!o.dst) continue;
+        if (is_device_ptr(o.dst)) {
+            CK(cudaMemcpyAsync(o.dst, o.src, o.bytes, cudaMemcpyHostToDevice, ctx->stream));
+            any_dev = true;
+        } else {
+            memcpy(o.dst, o.src, o.bytes);
+        }
     }
-    if (sync) CK(cudaStreamSynchronize(ctx->stream));
+    if (any_dev) CK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 
-// one block per selected window: base counts per column and dinucleotide counts per junction, weighted by the
-// haplotype counts (core:541-577 restated over the table instead of over a pandas frame of expansion rows)
+// base counts per column and dinucleotide counts per junction of the selected windows, weighted by the haplotype
+// counts (core:541-577 restated over the table instead of over a pandas frame of expansion rows).  SB blocks per
+// window, shared-memory accumulation, one integer atomicAdd per counter per block.
 #define TENS_THREADS 256
 __global__ void __launch_bounds__(TENS_THREADS)
 k_hist_tensors(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ cnt, int log2cap, int k, int v,
-               const int32_t* __restrict__ sel_idx, long long* __restrict__ freq, long long* __restrict__ nn) {
+               const int32_t* __restrict__ sel_idx, unsigned long long* __restrict__ freq,
+               unsigned long long* __restrict__ nn) {
     __shared__ unsigned long long s_freq[4 * MPB_MAX_K];
     __shared__ unsigned long long s_nn[(MPB_MAX_K - 1) * 16];
-    const int wi = sel_idx[blockIdx.x];
+    const int wi = sel_idx[blockIdx.y];
     const uint64_t cap = 1ull << log2cap;
     const uint64_t* K = keys + (uint64_t)wi * cap;
     const uint32_t* C = cnt + (uint64_t)wi * cap;
@@ -740,7 +777,7 @@ k_hist_tensors(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ c
     for (int i = threadIdx.x; i < 4 * k; i += TENS_THREADS) s_freq[i] = 0;
     for (int i = threadIdx.x; i < (k - 1) * 16; i += TENS_THREADS) s_nn[i] = 0;
     __syncthreads();
-    for (uint64_t i = threadIdx.x; i < cap; i += TENS_THREADS) {
+    for (uint64_t i = (uint64_t)blockIdx.x * TENS_THREADS + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * TENS_THREADS) {
         const uint64_t key = K[i];
         if (key == MPB_KEY_EMPTY_D) continue;
         uint32_t a, c, g, t, gapv;
@@ -756,9 +793,10 @@ k_hist_tensors(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ c
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 4 * k; i += TENS_THREADS) freq[(long long)wi * 4 * k + i] = (long long)s_freq[i];
+    for (int i = threadIdx.x; i < 4 * k; i += TENS_THREADS)
+        if (s_freq[i]) atomicAdd(&freq[(long long)wi * 4 * k + i], s_freq[i]);
     for (int i = threadIdx.x; i < (k - 1) * 16; i += TENS_THREADS)
-        nn[(long long)wi * (k - 1) * 16 + i] = (long long)s_nn[i];
+        if (s_nn[i]) atomicAdd(&nn[(long long)wi * (k - 1) * 16 + i], s_nn[i]);
 }
 
 extern "C" int mpb_hist_tensors(mpb_hist* h, const uint8_t* sel, int64_t* freq_hd, int64_t* nn_hd) {
@@ -776,8 +814,9 @@ extern "C" int mpb_hist_tensors(mpb_hist* h, const uint8_t* sel, int64_t* freq_h
     if (!idx.empty()) {
         InBuf si(ctx, idx.data(), idx.size() * 4);
         if (si.rc) return si.rc;
-        LAUNCH(ctx, k_hist_tensors, (unsigned)idx.size(), TENS_THREADS, 0, h->keys, h->cnt, h->log2cap, h->k, h->v,
-               si.dev<int32_t>(), of.dev<long long>(), on.dev<long long>());
+        const int sb = blocks_per_window(ctx, h->log2cap, (int)idx.size());
+        LAUNCH(ctx, k_hist_tensors, dim3((unsigned)sb, (unsigned)idx.size()), TENS_THREADS, 0, h->keys, h->cnt,
+               h->log2cap, h->k, h->v, si.dev<int32_t>(), of.dev<unsigned long long>(), on.dev<unsigned long long>());
         CK(of.finish());
         CK(on.finish());
         CK(cudaStreamSynchronize(ctx->stream));  // idx lifetime
@@ -834,33 +873,26 @@ extern "C" int mpb_hist_dump(mpb_hist* h, int32_t w, int64_t max_n, uint64_t* ke
     return 0;
 }
 
-// one block per query: distinct gap-free table entries matched exactly by a degenerate pattern
+// distinct gap-free table entries matched exactly by a degenerate pattern; SB blocks per query
 __global__ void __launch_bounds__(256)
 k_hist_match(const uint64_t* __restrict__ keys, int log2cap, int k, const int32_t* __restrict__ q_win,
-             const uint32_t* __restrict__ q_allow, long long* __restrict__ out) {
-    const int q = blockIdx.x;
+             const uint32_t* __restrict__ q_allow, unsigned long long* __restrict__ out) {
+    const int q = blockIdx.y;
     const uint64_t cap = 1ull << log2cap;
     const uint64_t* K = keys + (uint64_t)q_win[q] * cap;
     const uint32_t kmask = (1u << k) - 1u;
     const uint32_t na = ~q_allow[q * 4 + 0] & kmask, ncm = ~q_allow[q * 4 + 1] & kmask, ngm = ~q_allow[q * 4 + 2] & kmask,
                    nt = ~q_allow[q * 4 + 3] & kmask;
     unsigned n = 0;
-    for (uint64_t i = threadIdx.x; i < cap; i += 256) {
+    for (uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * 256) {
         const uint64_t key = K[i];
         if (key >= MPB_KEY_BASE5_D) continue;  // empty, or a k-mer with gaps (never an expansion of a primer)
         uint32_t a, c, g, t, gapv;
         mpb_key_planes(key, k, kmask, a, c, g, t, gapv);
         n += ((a & na) | (c & ncm) | (g & ngm) | (t & nt)) == 0u;
     }
-    __shared__ unsigned sn[8];
     n = __reduce_add_sync(0xffffffffu, n);
-    if ((threadIdx.x & 31) == 0) sn[threadIdx.x >> 5] = n;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned tot = 0;
-        for (int w = 0; w < 8; ++w) tot += sn[w];
-        out[q] = tot;
-    }
+    if ((threadIdx.x & 31) == 0 && n) atomicAdd(&out[q], (unsigned long long)n);
 }
 
 extern "C" int mpb_hist_match(mpb_hist* h, const int32_t* q_win, const uint32_t* q_allow, int32_t nq,
@@ -875,8 +907,10 @@ extern "C" int mpb_hist_match(mpb_hist* h, const int32_t* q_win, const uint32_t*
     InBuf qw(ctx, q_win, (size_t)nq * 4), qa(ctx, q_allow, (size_t)nq * 16);
     OutBuf o(ctx, distinct_hd, (size_t)nq * 8);
     if (qw.rc || qa.rc || o.rc) return MPB_ECUDA;
-    LAUNCH(ctx, k_hist_match, (unsigned)nq, 256, 0, h->keys, h->log2cap, h->k, qw.dev<int32_t>(), qa.dev<uint32_t>(),
-           o.dev<long long>());
+    CK(cudaMemsetAsync(o.d, 0, (size_t)nq * 8, ctx->stream));
+    const int sb = blocks_per_window(ctx, h->log2cap, nq);
+    LAUNCH(ctx, k_hist_match, dim3((unsigned)sb, (unsigned)nq), 256, 0, h->keys, h->log2cap, h->k, qw.dev<int32_t>(),
+           qa.dev<uint32_t>(), o.dev<unsigned long long>());
     CK(o.finish());
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;
@@ -908,7 +942,7 @@ extern "C" int mpb_hist_exceptions(mpb_hist* h, int64_t max_n, int32_t* win_idx,
 // the candidate scan (mis_primer_check, core:1103-1130)
 // ------------------------------------------------------------------------------------------------------
 #define SCAN_THREADS 256
-#define SCAN_CHUNK 8       // candidates of one window evaluated together against a window held in registers
+#define SCAN_CHUNK 4       // candidates of one window evaluated together against a window held in registers
 #define SCAN_MAX_CPB 128   // chunks per block (shared-memory counters: 128*8*3*4 = 12 KB)
 
 // one candidate against one one-hot k-mer: mismatch vector, then the three classes of core:1114-1127
@@ -933,7 +967,7 @@ extern "C" int mpb_hist_exceptions(mpb_hist* h, int64_t max_n, int32_t* win_idx,
 // each thread keeping per-candidate counters in registers; one warp reduction per chunk, block-private counters in
 // shared memory, one coalesced store of the block's partial counts at the end (no global atomics).
 template <bool BITS>
-__global__ void __launch_bounds__(SCAN_THREADS)
+__global__ void __launch_bounds__(SCAN_THREADS, 4)
 k_scan(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq, const int32_t* __restrict__ lens, int k, int v,
        uint32_t fmask, uint32_t rmask, const int4* __restrict__ chunks, int n_chunks, int cpb, int tiles_per_block,
        const uint32_t* __restrict__ cand_allow, uint32_t* __restrict__ partial, long long nc,

@@ -12,6 +12,7 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "mpb200.h"
@@ -30,6 +31,8 @@ struct mpb_dimer {
     uint64_t* end_rc;    // packed reverse complement of each end
     uint32_t* end_info;  // len | gc << 8 | dgflag << 16
     uint8_t* table;      // [33][33][33] loss >= threshold
+    uint32_t* pent;      // [n][32] 5-mer sets (built on the first grid call)
+    int min_end;
     std::vector<int64_t> h_off_p, h_off_e;
 };
 
@@ -199,6 +202,8 @@ extern "C" int mpb_dimer_prepare(mpb_ctx* ctx, const uint8_t* sets, const int32_
     d->ctx = ctx;
     d->n = n;
     d->sets = nullptr;
+    d->pent = nullptr;
+    d->min_end = min_end;
     d->h_off_p.assign(n + 1, 0);
     d->h_off_e.assign(n + 1, 0);
     static const int fold[16] = {1, 1, 1, 2, 1, 2, 2, 3, 1, 2, 2, 3, 2, 3, 3, 4};
@@ -270,6 +275,7 @@ extern "C" void mpb_dimer_free(mpb_dimer* d) {
     cudaFree(d->end_rc);
     cudaFree(d->end_info);
     cudaFree(d->table);
+    cudaFree(d->pent);
     delete d;
 }
 
@@ -308,4 +314,128 @@ extern "C" int mpb_dimer_pairs(mpb_dimer* d, const int32_t* pi, const int32_t* p
     cudaFreeAsync(dd2, st);
     cudaFreeAsync(dfh, st);
     return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// all-pairs grid (finDimer_V4.py:191-224: every primer i against every primer j >= i)
+// ------------------------------------------------------------------------------------------------------
+// A pair can only form a dimer if the reverse complement of some expansion of i's LAST 5 bases occurs in some
+// expansion of j (every longer 3' end ends with those 5 bases, so its reverse complement starts with theirs).
+// pent[j]   : 1024-bit set of the 5-mers that occur in any expansion of primer j (position-wise compatible)
+// tail5[i]  : up to TAIL_MAX packed reverse complements of the expansions of i's last min_end bases
+#define TAIL_MAX 16
+
+__global__ void k_dimer_pent(const uint8_t* __restrict__ sets, const int32_t* __restrict__ lens, int n, int m,
+                             uint32_t* __restrict__ pent /* [n][32] when m == 5 */) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const uint8_t* S = sets + (int64_t)j * DIMER_MAXLEN;
+    const int k = lens[j];
+    uint32_t* out = pent + (int64_t)j * 32;
+    for (int w = 0; w < 32; ++w) out[w] = 0;
+    for (int o = 0; o + m <= k; ++o) {
+        // enumerate the expansions of S[o..o+m)
+        int total = 1;
+        for (int q = 0; q < m; ++q) total *= d_fold[S[o + q]];
+        for (int e = 0; e < total; ++e) {
+            const uint32_t code = (uint32_t)expand_packed(S, o, o + m, (uint64_t)e);
+            out[code >> 5] |= 1u << (code & 31);
+        }
+    }
+}
+
+// thread = (i, j) pair with j >= i; survivors are appended to a queue
+__global__ void k_dimer_prefilter(const int64_t* __restrict__ off_e, const uint64_t* __restrict__ end_rc,
+                                  const uint32_t* __restrict__ end_info, const uint32_t* __restrict__ pent, int n,
+                                  int row0, int row1, int min_end, int2* __restrict__ queue,
+                                  unsigned long long* __restrict__ qn, long long qcap) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = row0 + blockIdx.y;
+    if (i >= row1 || j < i || j >= n) return;
+    // the ends of i are stored longest first; the shortest length (min_end) block is last
+    const uint32_t* P = pent + j * 32;
+    const uint32_t mask = (1u << (2 * min_end)) - 1u;
+    bool hit = false;
+    for (int64_t e = off_e[i + 1] - 1; e >= off_e[i]; --e) {
+        if ((int)(end_info[e] & 255) != min_end) break;
+        const uint32_t code = (uint32_t)end_rc[e] & mask;
+        if ((P[code >> 5] >> (code & 31)) & 1u) {
+            hit = true;
+            break;
+        }
+    }
+    if (hit) {
+        const unsigned long long slot = atomicAdd(qn, 1ull);
+        if ((long long)slot < qcap) queue[slot] = make_int2(i, (int)j);
+    }
+}
+
+// Rows [row0, row1) of the upper-triangular pair grid.  Outputs (host arrays of capacity max_hits): the pairs that
+// form a dimer with their first-hit order index and distance 2; *n_hits their number; *n_tested the pairs that
+// survived the 5-mer prefilter.  Returns MPB_EOVERFLOW when max_hits / the internal queue is too small (call again
+// with fewer rows).
+extern "C" int mpb_dimer_grid(mpb_dimer* d, int32_t row0, int32_t row1, int64_t max_hits, int32_t* hit_i,
+                              int32_t* hit_j, int64_t* hit_order, int32_t* hit_d2, int64_t* n_hits,
+                              int64_t* n_tested) {
+    if (!d || !hit_i || !hit_j || !hit_order || !hit_d2 || !n_hits) return mpb_fail(MPB_EINVAL, "NULL argument");
+    if (row0 < 0 || row1 > d->n || row0 >= row1) return mpb_fail(MPB_EINVAL, "bad row range");
+    mpb_ctx* ctx = d->ctx;
+    MPB_CK(cudaSetDevice(mpb_ctx_device(ctx)));
+    cudaStream_t st = mpb_ctx_stream(ctx);
+    if (d->min_end != 5) return mpb_fail(MPB_EINVAL, "the pair grid needs min_end == 5");
+    if (!d->pent) {
+        MPB_CK(cudaMalloc(&d->pent, (size_t)d->n * 32 * 4));
+        MPB_LAUNCH(ctx, k_dimer_pent, (unsigned)((d->n + 127) / 128), 128, 0, d->sets, d->lens, d->n, 5, d->pent);
+    }
+    const long long qcap = 1ll << 26;
+    int2* queue;
+    unsigned long long* qn;
+    MPB_CK(cudaMallocAsync(&queue, qcap * sizeof(int2), st));
+    MPB_CK(cudaMallocAsync(&qn, 8, st));
+    MPB_CK(cudaMemsetAsync(qn, 0, 8, st));
+    dim3 grid((unsigned)((d->n + 255) / 256), (unsigned)(row1 - row0));
+    MPB_LAUNCH(ctx, k_dimer_prefilter, grid, 256, 0, d->off_e, d->end_rc, d->end_info, d->pent, d->n, row0, row1, 5,
+               queue, qn, qcap);
+    unsigned long long nq = 0;
+    MPB_CK(cudaMemcpyAsync(&nq, qn, 8, cudaMemcpyDeviceToHost, st));
+    MPB_CK(cudaStreamSynchronize(st));
+    if ((long long)nq > qcap) {
+        cudaFreeAsync(queue, st);
+        cudaFreeAsync(qn, st);
+        return mpb_fail(MPB_EOVERFLOW, "dimer grid: %llu candidate pairs in one band, use fewer rows", nq);
+    }
+    if (n_tested) *n_tested = (int64_t)nq;
+    *n_hits = 0;
+    int rc = 0;
+    if (nq > 0) {
+        std::vector<int2> hq(nq);
+        MPB_CK(cudaMemcpyAsync(hq.data(), queue, nq * sizeof(int2), cudaMemcpyDeviceToHost, st));
+        MPB_CK(cudaStreamSynchronize(st));
+        std::sort(hq.begin(), hq.end(), [](const int2& a, const int2& b) { return a.x < b.x || (a.x == b.x && a.y < b.y); });
+        std::vector<int32_t> pi(nq), pj(nq), d2(nq);
+        std::vector<int64_t> fh(nq);
+        for (size_t q = 0; q < nq; ++q) {
+            pi[q] = hq[q].x;
+            pj[q] = hq[q].y;
+        }
+        rc = mpb_dimer_pairs(d, pi.data(), pj.data(), (int64_t)nq, fh.data(), d2.data());
+        if (rc == 0) {
+            int64_t nh = 0;
+            for (size_t q = 0; q < nq; ++q) {
+                if (fh[q] < 0) continue;
+                if (nh < max_hits) {
+                    hit_i[nh] = pi[q];
+                    hit_j[nh] = pj[q];
+                    hit_order[nh] = fh[q];
+                    hit_d2[nh] = d2[q];
+                }
+                ++nh;
+            }
+            *n_hits = nh;
+            if (nh > max_hits) rc = mpb_fail(MPB_EOVERFLOW, "dimer grid: %lld hits exceed max_hits", (long long)nh);
+        }
+    }
+    cudaFreeAsync(queue, st);
+    cudaFreeAsync(qn, st);
+    return rc;
 }

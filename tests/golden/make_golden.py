@@ -180,6 +180,71 @@ def make_kat(core):
     print("kat written")
 
 
+def make_dimer():
+    """finDimer_V4 (Dimer.dimer_check called per position; V4 == V5 as sets) on primers harvested from the core cases"""
+    fd = load_ref("findimer", "finDimer_V4.py")
+    primers = []
+    for name in CASES:
+        path = os.path.join(HERE, "core_%s.json" % name)
+        if os.path.exists(path):
+            for rec in json.load(open(path))["records"]:
+                if rec["row"]:
+                    primers.append(rec["row"][3])
+    core = load_ref("mpcore2", "multiPrime-core_V20.py")
+    seen, keep = set(), []
+    for p in primers:
+        if p not in seen and core.score_trans(p) <= 16:
+            seen.add(p)
+            keep.append(p)
+    keep = keep[:110]
+    keep += ["ACGTACGTACGTACGTAC", "GGGGCCCCGGGGCCCCAT", "ATATATATGCGCGCGCAT", keep[3]]     # palindromes + a duplicate
+    import random
+    rnd = random.Random(4)
+    comp = str.maketrans("ACGTRYMKSWHBVD", "TGCAYRKMSWDVBH")
+    for t in range(40):                       # partners built to pair with the 3' end of an existing primer
+        src = keep[rnd.randrange(100)]
+        L = rnd.randrange(5, 13)
+        tail = rnd.randrange(0, 4)
+        rc = src[-L:].translate(comp)[::-1]
+        body = "".join(rnd.choice("ACGT") for _ in range(20 - L - tail))
+        keep.append(body + rc + "".join(rnd.choice("ACGT") for _ in range(tail)))
+    with tempfile.TemporaryDirectory() as tmp:
+        fa = os.path.join(tmp, "p.fa")
+        with open(fa, "w") as fh:
+            for i, p in enumerate(keep):
+                fh.write(">P%03d\n%s\n" % (i, p))
+        app = fd.Dimer(primer_file=fa, outfile=os.path.join(tmp, "o.txt"), threshold=3.96, nproc=1)
+        rows = []
+        for pos in range(len(app.primers_list)):
+            app.dimer_check(pos)
+            while True:
+                r = app.resQ.get()
+                if r is None:
+                    break
+                rows.append(list(r))
+    with open(os.path.join(HERE, "dimer_findimer.json"), "w") as fh:
+        json.dump({"primers": keep, "threshold": 3.96, "rows": rows}, fh, indent=0)
+    print("finDimer rows", len(rows), "primers", len(keep))
+
+
+def make_cli():
+    """the reference CLI end to end on a small synthetic alignment: TSV text + the two JSON side files"""
+    import subprocess
+    codes = synth.synth_codes(60, 140, seed=3, gap_rate=0.004, iupac_rate=0.002)
+    with tempfile.TemporaryDirectory() as tmp:
+        fa = os.path.join(tmp, "in.fa")
+        synth.write_fasta(fa, codes)
+        out = os.path.join(tmp, "ref.out")
+        subprocess.run([sys.executable, os.path.join(REF, "scripts", "multiPrime-core.py"), "-i", fa, "-o", out,
+                        "-l", "18", "-n", "6", "-d", "64", "-v", "2", "-p", "1"], check=True, capture_output=True)
+        blob = {"args": ["-l", "18", "-n", "6", "-d", "64", "-v", "2", "-p", "1"], "synth": [60, 140, 3, 0.004, 0.002],
+                "tsv": open(out).read(), "non_cov": json.load(open(out + ".non_coverage_seq_id_json")),
+                "gap": json.load(open(out + ".gap_seq_id_json"))}
+    with open(os.path.join(HERE, "cli_core.json"), "w") as fh:
+        json.dump(blob, fh)
+    print("cli rows", blob["tsv"].count("\n") - 1)
+
+
 def main():
     assert os.environ.get("PYTHONHASHSEED") == "0", "run with PYTHONHASHSEED=0"
     core = load_ref("mpcore", "multiPrime-core_V20.py")
@@ -187,6 +252,10 @@ def main():
     for name in which:
         if name == "kat":
             make_kat(core)
+        elif name == "dimer":
+            make_dimer()
+        elif name == "cli":
+            make_cli()
         elif name in CASES:
             run_case(core, name)
 

@@ -58,3 +58,46 @@ def test_self_dimer_engine_vs_oracle():
     for p, f in zip(primers, flags):
         assert bool(f) == o.self_dimer(p), p
     ctx.close()
+
+
+def test_findimer_golden(tmp_path):
+    """finDimer: rows of the reference (finDimer_V4 == V5 as sets) on 154 primers, incl. duplicates and degenerate ones"""
+    import json
+    import os
+    from multiprime_b200 import findimer
+    from tests.helpers import GOLDEN
+    g = json.load(open(os.path.join(GOLDEN, "dimer_findimer.json")))
+    fa = tmp_path / "p.fa"
+    fa.write_text("".join(">P%03d\n%s\n" % (i, p) for i, p in enumerate(g["primers"])))
+    out = tmp_path / "o.txt"
+    app = findimer.Dimer(primer_file=str(fa), outfile=str(out), threshold=g["threshold"], nproc=1)
+    rows = app.run()
+    assert [list(r) for r in rows] == g["rows"]                 # V5 order: (i, j) ascending
+    text = out.read_text().splitlines()
+    assert text[0].split("\t") == findimer.HEADERS
+    assert [ln.split("\t") for ln in text[1:]] == [[str(x) for x in r] for r in g["rows"]]
+    assert (tmp_path / "o.txt.dimer_num").read_text().startswith("SeqName\tPrimer_ID\tDimer-primer_ID\tRowSum\n")
+
+
+def test_core_cli_bytes(tmp_path):
+    """the drop-in CLI against the reference CLI's own output files on the same FASTA: TSV byte-identical,
+    JSON side files equal as dictionaries (the reference's key order depends on PYTHONHASHSEED)"""
+    import json
+    import os
+    import subprocess
+    import sys
+    from multiprime_b200 import synth
+    from tests.helpers import GOLDEN
+    g = json.load(open(os.path.join(GOLDEN, "cli_core.json")))
+    n, L, seed, gr, ir = g["synth"]
+    fa = tmp_path / "in.fa"
+    synth.write_fasta(str(fa), synth.synth_codes(n, L, seed=seed, gap_rate=gr, iupac_rate=ir))
+    out = tmp_path / "mine.out"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "scripts", "multiPrime-core.py"), "-i", str(fa), "-o",
+                          str(out)] + g["args"], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    assert res.stdout.strip().startswith("INFO ") and "Total times:" in res.stdout
+    assert out.read_text() == g["tsv"]
+    assert json.load(open(str(out) + ".non_coverage_seq_id_json")) == g["non_cov"]
+    assert json.load(open(str(out) + ".gap_seq_id_json")) == g["gap"]
