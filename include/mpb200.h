@@ -156,7 +156,8 @@ int mpb_tm(mpb_ctx* ctx, const uint8_t* seqs2bit_hd, int k, int64_t n, const dou
 
 /* ---- primer-dimer predicates: core:457-503 dimer_check, finDimer_V4.py:191-224 ---------------------------------
  * sets[n*32] 4-bit base sets of n primers (one byte per position, row stride 32), lens[n] (host arrays).
- * Ends = suffixes of length min(max_end, len) .. min_end, longest first, each expanded in product order
+ * Ends = suffixes of length min(max_end, len) .. min_end (max_end <= 0: len + max_end .. min_end, the
+ * get_Maxprimerset_V1.3.py:149-154 variant), longest first, each expanded in product order
  * (core:457-464 current_end after the stable length sort of core:489).
  * loss_table[33*33*33] (host): loss_table[(len*33+gc)*33+d2] != 0 when the reference's Loss test passes for an end of
  * that length / GC count at distance d2 (the host evaluates core:192-193 itself, so >= vs > and the threshold are its

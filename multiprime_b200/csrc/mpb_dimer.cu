@@ -90,8 +90,8 @@ __global__ void k_dimer_ends(const uint8_t* __restrict__ sets, const int32_t* __
         const uint8_t* S = sets + (int64_t)i * DIMER_MAXLEN;
         const int k = lens[i];
         int64_t r = idx - off_e[i];
-        // suffix lengths from high to low: min(max_end, k) .. min_end
-        int L = max_end < k ? max_end : k;
+        // suffix lengths from high to low: min(max_end, k) .. min_end   (max_end <= 0 means k + max_end)
+        int L = max_end > 0 ? (max_end < k ? max_end : k) : k + max_end;
         for (; L >= min_end; --L) {
             int64_t cnt = 1;
             for (int q = k - L; q < k; ++q) cnt *= d_fold[S[q]];
@@ -194,7 +194,7 @@ extern "C" int mpb_dimer_prepare(mpb_ctx* ctx, const uint8_t* sets, const int32_
                                  int max_end, int init_both, const uint8_t* loss_table, const double* dg_consts,
                                  mpb_dimer** out) {
     if (!ctx || !sets || !lens || !loss_table || !dg_consts || !out) return mpb_fail(MPB_EINVAL, "NULL argument");
-    if (n < 1 || min_end < 1 || max_end < min_end || max_end > DIMER_MAXLEN)
+    if (n < 1 || min_end < 1 || (max_end > 0 && max_end < min_end) || max_end > DIMER_MAXLEN)
         return mpb_fail(MPB_EINVAL, "bad n=%d or end range %d..%d", n, min_end, max_end);
     MPB_CK(cudaSetDevice(mpb_ctx_device(ctx)));
     cudaStream_t st = mpb_ctx_stream(ctx);
@@ -223,7 +223,8 @@ extern "C" int mpb_dimer_prepare(mpb_ctx* ctx, const uint8_t* sets, const int32_
             deg *= f;
             suf *= f;
             const int L = k - q;
-            if (L >= min_end && L <= max_end) ends += suf;
+            const int lmax = max_end > 0 ? max_end : k + max_end;
+            if (L >= min_end && L <= lmax) ends += suf;
             if (deg > (1ll << 40)) break;
         }
         if (deg > (1ll << 24)) {

@@ -227,6 +227,48 @@ def make_dimer():
     print("finDimer rows", len(rows), "primers", len(keep))
 
 
+def make_cover():
+    """get_Maxprimerset_V1.3 (the script the pipeline calls) on clusters drawn from the finDimer primer pool"""
+    import random
+    import subprocess
+    pool = json.load(open(os.path.join(HERE, "dimer_findimer.json")))["primers"]
+    rnd = random.Random(9)
+    lines = ["/data/empty_cluster.candidate.primers.txt"]
+    for c in range(40):
+        fields = ["/data/Cluster_%d.candidate.primers.txt" % c]
+        for _ in range(rnd.randrange(1, 7)):
+            f, r = rnd.choice(pool), rnd.choice(pool)
+            start = rnd.randrange(0, 900)
+            ln = rnd.randrange(150, 900)
+            fields += [f, r, "%d:%.2f:%.3f" % (ln, rnd.uniform(48, 56), rnd.uniform(0.7, 1.0)), str(rnd.randrange(200, 500)),
+                       "%d:%d" % (start, start + ln)]
+        lines.append("\t".join(fields) + "\t")
+    easy = []
+    for c in range(14):
+        fields = ["/data/Easy_%d.candidate.primers.txt" % c]
+        for _ in range(rnd.randrange(5, 11)):
+            f, r = rnd.choice(pool), rnd.choice(pool)
+            fields += [f, r, "300:50.00:0.900", "400", "10:310"]
+        easy.append("\t".join(fields) + "\t")
+    blob = {"input": lines, "input_easy": easy}
+    for mode in ("T", "F", "F_easy"):
+        with tempfile.TemporaryDirectory() as tmp:
+            inp = os.path.join(tmp, "candidate_primers_sets.txt")
+            open(inp, "w").write("\n".join(easy if mode == "F_easy" else lines) + "\n")
+            out = os.path.join(tmp, "final_maxprimers_set.xls")
+            res = subprocess.run([sys.executable, os.path.join(REF, "scripts", "get_Maxprimerset_V1.3.py"), "-i", inp,
+                                  "-o", out, "-s", "5", "-m", mode[0]], capture_output=True, text=True)
+            blob[mode] = {"rc": res.returncode, "stdout": res.stdout,
+                          "out": open(out).read() if os.path.exists(out) else None,
+                          "sort": open(os.path.join(tmp, "sort.candidate_primers_sets.txt")).read()}
+            nxt = os.path.join(tmp, "final_maxprimers_set.next.xls")
+            blob[mode]["next"] = open(nxt).read() if os.path.exists(nxt) else None
+            print("cover mode", mode, "rc", res.returncode, "rows", (blob[mode]["out"] or "").count("\n") - 1,
+                  res.stderr[-300:])
+    with open(os.path.join(HERE, "cover_maxprimerset.json"), "w") as fh:
+        json.dump(blob, fh)
+
+
 def make_cli():
     """the reference CLI end to end on a small synthetic alignment: TSV text + the two JSON side files"""
     import subprocess
@@ -256,6 +298,8 @@ def main():
             make_dimer()
         elif name == "cli":
             make_cli()
+        elif name == "cover":
+            make_cover()
         elif name in CASES:
             run_case(core, name)
 

@@ -101,3 +101,32 @@ def test_core_cli_bytes(tmp_path):
     assert out.read_text() == g["tsv"]
     assert json.load(open(str(out) + ".non_coverage_seq_id_json")) == g["non_cov"]
     assert json.load(open(str(out) + ".gap_seq_id_json")) == g["gap"]
+
+
+@pytest.mark.parametrize("mode", ["T", "F", "F_easy"])
+def test_maxprimerset_golden(tmp_path, mode):
+    """get_Maxprimerset drop-in against get_Maxprimerset_V1.3.py: output, .next.xls and sort.* byte-identical, same
+    exit code (maximum mode without a solution exits 1 with the reference's message)"""
+    import json
+    import os
+    import subprocess
+    import sys
+    from tests.helpers import GOLDEN
+    g = json.load(open(os.path.join(GOLDEN, "cover_maxprimerset.json")))
+    lines = g["input_easy"] if mode == "F_easy" else g["input"]
+    inp = tmp_path / "candidate_primers_sets.txt"
+    inp.write_text("\n".join(lines) + "\n")
+    out = tmp_path / "final_maxprimers_set.xls"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "scripts", "get_Maxprimerset.py"), "-i", str(inp), "-o",
+                          str(out), "-s", "5", "-m", mode[0]], capture_output=True, text=True)
+    want = g[mode]
+    assert res.returncode == want["rc"], res.stderr[-2000:]
+    assert (tmp_path / "sort.candidate_primers_sets.txt").read_text() == want["sort"]
+    if want["out"] is not None:
+        assert out.read_text() == want["out"]
+    if want["next"] is not None:
+        assert (tmp_path / "final_maxprimers_set.next.xls").read_text() == want["next"]
+    ref_msgs = [ln for ln in want["stdout"].splitlines() if not ln.startswith("INFO")]
+    got_msgs = [ln for ln in res.stdout.splitlines() if not ln.startswith("INFO")]
+    assert got_msgs == ref_msgs
