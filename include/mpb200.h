@@ -154,6 +154,34 @@ int mpb_seqkeys(mpb_msa* msa, int k, const int32_t* win_pos, int32_t nw, uint64_
 int mpb_tm(mpb_ctx* ctx, const uint8_t* seqs2bit_hd, int k, int64_t n, const double* consts3, double* tm_hd,
            double* dh_hd, double* ds_hd);
 
+/* ---- per-window control logic in native host code ----------------------------------------------------------------
+ * mpb_walk: seeds (core:579-600: Viterbi over freq / nn; most frequent haplotype = mm_key, MPB_KEY_EMPTY when the window
+ * has no gap-free haplotype) and the NN-array refinement walk (core:860-1089) of all n_win windows in lock step: every
+ * round collects the candidates of all live tracks and calls `scan` once (mpb_scan semantics, candidates sorted by
+ * window; the callback adds the count all-reduce in sequence-sharded runs).  No device code, no CUDA calls.
+ *   out_sets[n_win*32]       final primer (4-bit sets) of the chosen track
+ *   out_counts[n_win*4]      optimal_coverage_init, F_mis_cover_cover, R_mis_cover_cover (core:917-918 before the
+ *                            sum), chosen track (0 = first / NM, 1 = MM)
+ *   out_seeds[n_win*2*32]    seed bases (0..3) of the tracks; out_seed_cover[n_win*2] cover[seed] (-1: no such track)
+ *   out_ntracks[n_win]       1 or 2
+ *   trace_sets[trace_cap*32], trace_off[n_win+1]   every primer handed to mis_primer_check, in call order
+ *   stats[3]                 scan rounds, candidates scanned, trace length
+ */
+typedef int (*mpb_scan_cb)(void* user, const int32_t* cand_pos, const uint32_t* cand_allow, int64_t nc,
+                           int64_t* counts /* nc*3 */);
+int mpb_walk(int k, int v, int dnum, int degeneracy, uint32_t fmask, uint32_t rmask, int32_t n_win,
+             const int32_t* win_pos, const int64_t* cover_number, const int64_t* freq, const int64_t* nn,
+             const uint64_t* mm_key, mpb_scan_cb scan, void* user, uint8_t* out_sets, int64_t* out_counts,
+             uint8_t* out_seeds, int64_t* out_seed_cover, int32_t* out_ntracks, int64_t trace_cap, uint8_t* trace_sets,
+             int64_t* trace_off, int64_t* stats);
+
+/* Tm (mean over expansions of the rounded per-expansion Tm, core:849-852; k_tm on the device), GC content and the
+ * di-nucleotide / hairpin filters (core:387-416, 507-521) of n primers sets[n*32] of length k (host arrays).
+ * flags: 1 GC outside [gc_lo, gc_hi], 2 di-nucleotide repeat, 4 hairpin, 64 / 128: the Tm / GC mean sits on a
+ * rounding tie that double arithmetic cannot decide — the caller replays that value exactly. */
+int mpb_primer_props(mpb_ctx* ctx, const uint8_t* sets, int k, int32_t n, double gc_lo, double gc_hi, int distance,
+                     const double* tm_consts3, double* tm_avg, double* gc, int32_t* flags, int32_t* deg, int32_t* ndeg);
+
 /* ---- primer-dimer predicates: core:457-503 dimer_check, finDimer_V4.py:191-224 ---------------------------------
  * sets[n*32] 4-bit base sets of n primers (one byte per position, row stride 32), lens[n] (host arrays).
  * Ends = suffixes of length min(max_end, len) .. min_end (max_end <= 0: len + max_end .. min_end, the

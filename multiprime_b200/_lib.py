@@ -47,6 +47,10 @@ SIGNATURES = {
     "mpb_scan": (C.c_int, [_P, C.c_int, C.c_int, C.c_uint32, C.c_uint32, _P, _P, C.c_int64, _P, _P, _P]),
     "mpb_seqkeys": (C.c_int, [_P, C.c_int, _P, C.c_int32, _P]),
     "mpb_tm": (C.c_int, [_P, _P, C.c_int, C.c_int64, _P, _P, _P, _P]),
+    "mpb_walk": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_int32, _P, _P, _P, _P, _P, _P,
+                           _P, _P, _P, _P, _P, _P, C.c_int64, _P, _P, _P]),
+    "mpb_primer_props": (C.c_int, [_P, _P, C.c_int, C.c_int32, C.c_double, C.c_double, C.c_int, _P, _P, _P, _P, _P,
+                                   _P]),
     "mpb_dimer_prepare": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int, C.c_int, C.c_int, _P, _P, C.POINTER(_P)]),
     "mpb_dimer_free": (None, [_P]),
     "mpb_dimer_counts": (C.c_int, [_P, _P, _P]),
@@ -54,6 +58,10 @@ SIGNATURES = {
     "mpb_dimer_grid": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int64, _P, _P, _P, _P, C.POINTER(C.c_int64),
                                   C.POINTER(C.c_int64)]),
 }
+
+
+SCAN_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_uint32), C.c_int64,
+                      C.POINTER(C.c_int64))
 
 
 class MpbError(RuntimeError):
@@ -97,6 +105,53 @@ def ptr(x):
     return C.c_void_p(int(x))
 
 
+def walk(k, v, dnum, degeneracy, fmask, rmask, win_pos, cover_number, freq, nn, mm_key, scan_fn):
+    """mpb_walk: refinement walk of a window batch; scan_fn(cand_pos int32[nc], cand_allow uint32[nc,4]) -> int64[nc,3].
+    Pure host code (usable without a GPU when scan_fn is a stand-in)."""
+    n = len(win_pos)
+    win_pos = np.ascontiguousarray(win_pos, dtype=np.int32)
+    cover_number = np.ascontiguousarray(cover_number, dtype=np.int64)
+    freq = np.ascontiguousarray(freq, dtype=np.int64)
+    nn = np.ascontiguousarray(nn, dtype=np.int64)
+    mm_key = np.ascontiguousarray(mm_key, dtype=np.uint64)
+    err = []
+
+    def cb(_user, p_pos, p_allow, nc, p_counts):
+        try:
+            pos = np.ctypeslib.as_array(p_pos, shape=(nc,))
+            allow = np.ctypeslib.as_array(p_allow, shape=(nc, 4))
+            out = np.ctypeslib.as_array(p_counts, shape=(nc, 3))
+            out[:] = scan_fn(pos, allow)
+            return 0
+        except Exception as exc:           # surfaced after mpb_walk returns
+            err.append(exc)
+            return -2
+
+    out_sets = np.zeros((n, 32), np.uint8)
+    out_counts = np.zeros((n, 4), np.int64)
+    out_seeds = np.zeros((n, 2, 32), np.uint8)
+    out_seed_cover = np.zeros((n, 2), np.int64)
+    out_nt = np.zeros(n, np.int32)
+    cap = max(64, n * 48)
+    stats = np.zeros(3, np.int64)
+    cfn = SCAN_CB(cb)
+    while True:
+        trace = np.zeros((cap, 32), np.uint8)
+        off = np.zeros(n + 1, np.int64)
+        rc = load().mpb_walk(k, v, dnum, degeneracy, fmask, rmask, n, ptr(win_pos), ptr(cover_number), ptr(freq), ptr(nn),
+                             ptr(mm_key), C.cast(cfn, C.c_void_p), None, ptr(out_sets), ptr(out_counts), ptr(out_seeds),
+                             ptr(out_seed_cover), ptr(out_nt), cap, ptr(trace), ptr(off), ptr(stats))
+        if err:
+            raise err[0]
+        if rc == -4 and stats[2] > cap:      # trace buffer too small: the walk is deterministic, run it again
+            cap = int(stats[2]) + 16
+            continue
+        check(rc)
+        break
+    return dict(sets=out_sets, counts=out_counts, seeds=out_seeds, seed_cover=out_seed_cover, ntracks=out_nt,
+                trace=trace, trace_off=off, stats=stats)
+
+
 class Context:
     """one CUDA device + stream"""
 
@@ -128,6 +183,21 @@ class Context:
         check(load().mpb_ctx_profile_read(self.h, kernel.encode() if kernel else None, C.byref(ms), C.byref(n),
                                           C.byref(u)))
         return ms.value, n.value, u.value
+
+    def primer_props(self, sets: np.ndarray, k: int, gc_lo: float, gc_hi: float, distance: int, consts3):
+        """mpb_primer_props -> (tm_avg, gc, flags, deg, ndeg)"""
+        sets = np.ascontiguousarray(sets, dtype=np.uint8)
+        n = len(sets)
+        cst = np.asarray(consts3, dtype=np.float64)
+        tm = np.zeros(n, np.float64)
+        gc = np.zeros(n, np.float64)
+        flags = np.zeros(n, np.int32)
+        deg = np.zeros(n, np.int32)
+        ndeg = np.zeros(n, np.int32)
+        if n:
+            check(load().mpb_primer_props(self.h, ptr(sets), k, n, gc_lo, gc_hi, distance, ptr(cst), ptr(tm), ptr(gc),
+                                          ptr(flags), ptr(deg), ptr(ndeg)))
+        return tm, gc, flags, deg, ndeg
 
     def close(self):
         if self.h:

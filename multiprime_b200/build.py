@@ -10,7 +10,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libmpb200.so")
-SOURCES = ["mpb200.cu", "mpb_dimer.cu"]
+SOURCES = ["mpb200.cu", "mpb_dimer.cu", "mpb_walk.cu"]
 HEADERS = [os.path.join(CSRC, "mpb_device.cuh"), os.path.join(CSRC, "mpb_host.h"), os.path.join(ROOT, "include", "mpb200.h")]
 
 

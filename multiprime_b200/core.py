@@ -107,108 +107,6 @@ def _tm_consts():
 TM_CONSTS = _tm_consts()
 
 
-def viterbi_seed(freq, nn, k: int):
-    """core:579-593: max-sum path over freq[b][t] + nn[t-1][prev][cur]; first maximum wins"""
-    score = [int(freq[b][0]) for b in range(4)]
-    back = []
-    for t in range(1, k):
-        layer = nn[t - 1]
-        new, bp = [], []
-        for cur in range(4):
-            best, arg = None, 0
-            for prev in range(4):
-                val = score[prev] + layer[prev * 4 + cur]
-                if best is None or val > best:
-                    best, arg = val, prev
-            new.append(best + int(freq[cur][t]))
-            bp.append(arg)
-        score = new
-        back.append(bp)
-    cur = 0
-    for b in range(1, 4):
-        if score[b] > score[cur]:
-            cur = b
-    path = [cur]
-    for bp in reversed(back):
-        cur = bp[cur]
-        path.append(cur)
-    return path[::-1]
-
-
-def _order_desc(vals):
-    """np.argsort(vals)[::-1] for a stable ascending sort (reference numpy 1.21 on 4 elements)"""
-    return sorted(range(4), key=vals.__getitem__)[::-1]
-
-
-def _npos(vals):
-    return sum(1 for x in vals if x > 0)
-
-
-def refine_options(sets, seed, nn_cov, nn):
-    """core:922-1080: for every junction tied at the minimum NN coverage, the refinement the reference would try.
-    Yields (pos, base, new_layers, new_cov) or None (junction cannot be refined) per tied junction."""
-    k = len(sets)
-    last = k - 2
-    lowest = min(nn_cov)
-    out = []
-    for j in range(k - 1):
-        if nn_cov[j] != lowest:
-            continue
-        row, col = seed[j], seed[j + 1]
-        L = nn[j]
-
-        def middle(jj):
-            nrow, ncol = seed[jj + 1], seed[jj + 2]
-            L0, L1 = nn[jj], nn[jj + 1]
-            m = [min(L0[row * 4 + x], L1[x * 4 + ncol]) for x in range(4)]
-            if _npos(m) <= 1:
-                return None
-            idx = next(i for i in _order_desc(m) if i != col)
-            n0, n1 = list(L0), list(L1)
-            for x in range(4):
-                n0[x * 4 + col] += L0[x * 4 + idx]
-                n0[x * 4 + idx] = 0
-            for y in range(4):
-                n1[nrow * 4 + y] += L1[idx * 4 + y]
-                n1[idx * 4 + y] = 0
-            cov = list(nn_cov)
-            cov[jj] = n0[row * 4 + col]
-            cov[jj + 1] = n1[nrow * 4 + ncol]
-            return (jj + 1, idx, {jj: n0, jj + 1: n1}, cov)
-
-        if j == 0:
-            column0 = [L[x * 4 + col] for x in range(4)]
-            if _npos(column0) > 1:
-                idx = next(i for i in _order_desc(column0) if i != row)
-                n0 = list(L)
-                for y in range(4):
-                    n0[row * 4 + y] += L[idx * 4 + y]
-                    n0[idx * 4 + y] = 0
-                cov = list(nn_cov)
-                cov[0] = n0[row * 4 + col]
-                out.append((0, idx, {0: n0}, cov))
-            elif _npos(L[row * 4:row * 4 + 4]) > 1:
-                out.append(middle(0))
-            else:
-                out.append(None)
-        elif j == last:
-            rowvals = L[row * 4:row * 4 + 4]
-            if _npos(rowvals) > 1:
-                idx = next(i for i in _order_desc(rowvals) if i != col)
-                n0 = list(L)
-                for x in range(4):
-                    n0[x * 4 + col] += L[x * 4 + idx]
-                    n0[x * 4 + idx] = 0
-                cov = list(nn_cov)
-                cov[j] = n0[row * 4 + col]
-                out.append((j + 1, idx, {j: n0}, cov))
-            else:
-                out.append(None)
-        else:
-            out.append(middle(j))
-    return out
-
-
 # ---- filters (core:387-416, 507-521) on base-set lists, no expansion ------------------------------------
 def _repeat_patterns():
     pats = set()
@@ -289,24 +187,6 @@ def information(sets, gc_lo: float, gc_hi: float, distance: int):
     if has_hairpin(sets, distance):
         notes.append("hairpin")
     return gc if not notes else "|".join(notes)
-
-
-class _Track:
-    """one run of core:860-920 coverage_stast (NM or MM seed) advanced in lock step with the scan"""
-    __slots__ = ("seed", "sets", "nn", "nn_cov", "init", "fm", "rm", "state", "opts", "trace", "seed_cover", "allow")
-
-    def __init__(self, seed, nn):
-        self.seed = seed
-        self.sets = [1 << b for b in seed]
-        self.allow = allow_masks(self.sets)           # kept in step with `sets`
-        self.nn = nn                                  # list of k-1 flat 4x4 lists; layers are copied on write
-        self.nn_cov = [nn[j][seed[j] * 4 + seed[j + 1]] for j in range(len(seed) - 1)]
-        self.init = 0
-        self.seed_cover = 0                           # cover[seed] (core:787/800/809/835)
-        self.fm = self.rm = 0
-        self.state = "seed"                           # seed -> refine* -> done
-        self.opts = None
-        self.trace = []
 
 
 class NN_degenerate(object):
@@ -495,43 +375,46 @@ class NN_degenerate(object):
             st = hist.stats()
             if self.comm.world > 1:
                 st = self._merge_shards(hist, st)
-            accepted = {}
+            gap_n = st["gap_n"]
+            # core:713 `round(gap_n / N, 2) >= 1 - coverage`: exact for all but ratios on a rounding tie
+            ratio = gap_n / N
+            gap_fail = np.round(ratio, 2) >= (1 - self.coverage)
+            for wi in np.nonzero(np.abs((ratio * 100) % 1 - 0.5) < 1e-6)[0]:
+                gap_fail[wi] = round(int(gap_n[wi]) / N, 2) >= (1 - self.coverage)
+            alive = ~gap_fail & (st["nuniq"][:, 0] >= 1)                      # core:716
+            if "merged" in st:
+                alive &= st["merged"]              # shard entropy bound already above the gate
+            accepted = []                          # (batch index, position, cBit, tBit, cover_number, has gap-free)
             sel = np.zeros(len(positions), np.uint8)
-            for wi, pos in enumerate(positions):
-                gap_n = int(st["gap_n"][wi])
-                if round(gap_n / N, 2) >= (1 - self.coverage):          # core:713
-                    continue
-                if not st.get("merged", ALL_MERGED)[wi]:                 # entropy bound of the shards already above the gate
-                    continue
-                n_cover_u, n_gap_u, n_gapfree = (int(x) for x in st["nuniq"][wi])
-                if n_cover_u < 1:                                        # core:716
-                    continue
-                ent = self._entropy(hist, st, wi, pos, gap_n, n_cover_u + n_gap_u)
-                if ent is None:
-                    continue
-                accepted[wi] = {"pos": pos, "c_bit": ent[0], "t_bit": ent[1], "cover_number": N - gap_n,
-                                "has_mm": n_gapfree > 0}
-                sel[wi] = 1
+            for wi in np.nonzero(alive)[0].tolist():
+                ent = self._entropy(hist, st, wi, positions[wi], int(gap_n[wi]), int(st["nuniq"][wi, 0] + st["nuniq"][wi, 1]))
+                if ent is not None:
+                    accepted.append((wi, positions[wi], ent[0], ent[1], N - int(gap_n[wi]), bool(st["nuniq"][wi, 2] > 0)))
+                    sel[wi] = 1
             if not accepted:
                 return []
             freq, nn = hist.tensors(sel)
-            tracks = {}
-            for wi in list(accepted):
-                f = freq[wi]
-                if (f.sum(axis=1) == 0).any() or (f.sum(axis=0) == 0).any():   # core:736-740
-                    del accepted[wi]
-                    continue
-                layers = [row.reshape(16).tolist() for row in nn[wi]]
-                nm = viterbi_seed(f.tolist(), layers, k)
-                info = accepted[wi]
-                if info["has_mm"]:
-                    mm = _key_bases(int(st["mm_key"][wi]), k)
-                    info["seeds"] = [nm] if nm == mm else [nm, mm]
-                else:
-                    info["seeds"] = [nm]
-                tracks[wi] = [_Track(seed, layers) for seed in info["seeds"]]
-            self._run_tracks(positions, accepted, tracks)
-            return self._finish(hist, positions, accepted, tracks)
+            keep = []
+            for a in accepted:                                                     # core:736-740
+                f = freq[a[0]]
+                if not ((f.sum(axis=1) == 0).any() or (f.sum(axis=0) == 0).any()):
+                    keep.append(a)
+            if not keep:
+                return []
+            wis = np.array([a[0] for a in keep], np.int64)
+            mm_key = np.where(np.array([a[5] for a in keep]), st["mm_key"][wis], np.uint64(_lib.KEY_EMPTY))
+
+            def scan_fn(pos, allow):
+                counts, _ = self.msa.scan(k, v, self.fmask, self.rmask, pos, allow)
+                self.stats["scan_calls"] += 1
+                return self.comm.allreduce_sum(counts)        # the one collective of a scan round
+
+            res = _lib.walk(k, v, self.number_of_dege_bases, self.score_of_dege_bases, self.fmask, self.rmask,
+                            np.array([a[1] for a in keep], np.int32), np.array([a[4] for a in keep], np.int64),
+                            freq[wis], nn[wis].reshape(len(keep), k - 1, 16), mm_key, scan_fn)
+            self.stats["candidates"] += int(res["stats"][1])
+            self.stats["evals"] += int(res["stats"][2]) * N
+            return self._finish(hist, keep, res)
 
     def _merge_shards(self, hist, st):
         """Sequence-sharded run: make the tables of every window that can still pass the gates GLOBAL on every rank.
@@ -597,158 +480,71 @@ class NN_degenerate(object):
         return c_bit, t_bit
 
     # -- refinement walk in lock step with the scan (core:860-1089) ------------------------------------------
-    def _run_tracks(self, positions, accepted, tracks):
-        k, v = self.primer_length, self.variation
-        d_max, n_max = self.score_of_dege_bases, self.number_of_dege_bases
-        live = [(wi, t) for wi in accepted for t in tracks[wi]]
-        while live:
-            cand_pos, cand_allow, owners = [], [], []
-            for wi, t in live:
-                pos = accepted[wi]["pos"]
-                if t.state == "seed":
-                    cand_pos.append(pos)
-                    cand_allow.extend(t.allow)
-                    owners.append((t, "seed", None))
-                else:
-                    t.opts = refine_options(t.sets, t.seed, t.nn_cov, t.nn)
-                    al = t.allow
-                    for oi, opt in enumerate(t.opts):
-                        if opt is None:
-                            continue
-                        p, b = opt[0], opt[1]
-                        bit = 1 << p
-                        assert not t.sets[p] & (1 << b), "refinement would re-add a base (reference raises KeyError)"
-                        cand_pos.append(pos)                      # primer with position p := base b alone
-                        cand_allow.extend((al[x] | bit) if x == b else (al[x] & ~bit) for x in range(4))
-                        owners.append((t, "trial", oi))
-                        cand_pos.append(pos)                      # primer with base b added at position p
-                        cand_allow.extend((al[x] | bit) if x == b else al[x] for x in range(4))
-                        owners.append((t, "new", oi))
-            pos_arr = np.array(cand_pos, dtype=np.int32)
-            order = np.argsort(pos_arr, kind="stable")
-            counts, _ = self.msa.scan(k, v, self.fmask, self.rmask, pos_arr[order],
-                                      np.array(cand_allow, dtype=np.uint32).reshape(-1, 4)[order])
-            counts = self.comm.allreduce_sum(counts)        # the one collective of a scan round
-            self.stats["scan_calls"] += 1
-            self.stats["candidates"] += len(cand_pos)
-            inv = np.empty(len(order), np.int64)
-            inv[order] = np.arange(len(order))
-            got = {}
-            counts_l = counts[inv].tolist()
-            for ci, (t, kind, oi) in enumerate(owners):
-                got.setdefault(id(t), {})[(kind, oi)] = counts_l[ci]
-            nxt = []
-            for wi, t in live:
-                total = accepted[wi]["cover_number"]
-                res = got.get(id(t), {})
-                if t.state == "seed":
-                    c = res[("seed", None)]
-                    t.init, t.fm, t.rm = int(c[0]), int(c[1]), int(c[2])
-                    t.seed_cover = t.init
-                    t.trace.append(primer_string(t.sets))
-                    t.state = "refine"
-                    if t.init + t.fm < total or t.init + t.rm < total:
-                        nxt.append((wi, t))
-                    else:
-                        t.state = "done"
-                    continue
-                best, best_gain = 0, None
-                for oi, opt in enumerate(t.opts):
-                    gain = t.init + (int(res[("trial", oi)][0]) if opt is not None else 0)
-                    if best_gain is None or gain > best_gain:
-                        best, best_gain = oi, gain
-                opt = t.opts[best]
-                if opt is None:
-                    cov_new = list(t.nn_cov)
-                    c = None
-                else:
-                    p, b, layers, cov_new = opt
-                    t.sets[p] |= 1 << b
-                    t.allow[b] |= 1 << p
-                    t.nn = list(t.nn)
-                    for j, layer in layers.items():
-                        t.nn[j] = layer
-                    c = res[("new", best)]
-                t.init = best_gain
-                if c is not None:
-                    t.fm, t.rm = int(c[1]), int(c[2])
-                # else: primer unchanged, the reference's second mis_primer_check returns the same counts
-                t.trace.append(primer_string(t.sets))
-                deg, ndeg = degeneracy(t.sets), n_degenerate(t.sets)
-                if max(t.fm, t.rm) == total:
-                    t.state = "done"
-                elif cov_new == t.nn_cov:
-                    t.state = "done"
-                elif 2 * deg > d_max or 3 * deg / 2 > d_max or ndeg == n_max:
-                    t.state = "done"
-                else:
-                    t.nn_cov = cov_new
-                    if t.init + t.fm < total or t.init + t.rm < total:
-                        nxt.append((wi, t))
-                    else:
-                        t.state = "done"
-            live = nxt
-
     # -- rows, filters, side files ----------------------------------------------------------------------------
-    def _finish(self, hist, positions, accepted, tracks):
+    def _finish(self, hist, keep, res):
+        """core:846-858 row assembly for the windows that went through the walk"""
         k, v, N = self.primer_length, self.variation, self.total_sequence_number
         gc_lo, gc_hi = float(self.GC[0]), float(self.GC[1])
-        chosen = {}
-        for wi, info in accepted.items():
-            ts = tracks[wi]
-            if len(ts) == 1:
-                t = ts[0]
-            else:   # core:816: NM only when strictly better
-                nm, mm = ts
-                t = nm if (nm.init + nm.fm + nm.init + nm.rm) > (mm.init + mm.fm + mm.init + mm.rm) else mm
-            chosen[wi] = t
-            self.stats["evals"] += sum(len(x.trace) for x in ts) * N
-        wis = sorted(chosen)
+        n = len(keep)
+        sets_arr = res["sets"]
+        sets_list = [row[:k].tolist() for row in sets_arr]
+        wis = np.array([a[0] for a in keep], np.int32)
+        pos = np.array([a[1] for a in keep], np.int32)
+        allow = np.array([allow_masks(s) for s in sets_list], np.uint32)
         # final pass of the scan: perfect coverage of the chosen primer (+ per-sequence non-cover bits)
-        allow = np.asarray([allow_masks(chosen[wi].sets) for wi in wis], np.uint32)
-        pos = np.asarray([accepted[wi]["pos"] for wi in wis], np.int32)
-        slots = np.arange(len(wis), dtype=np.int32) if self.sidecars else None
+        slots = np.arange(n, dtype=np.int32) if self.sidecars else None
         counts, bits = self.msa.scan(k, v, self.fmask, self.rmask, pos, allow, bits_slot=slots)
         counts = self.comm.allreduce_sum(counts)
         self.stats["scan_calls"] += 1
-        distinct = hist.match(np.asarray(wis, np.int32), allow)
-        # Tm of every expansion of every chosen primer in one launch
-        exp_bases, spans = [], []
-        for wi in wis:
-            e = expand_keys(chosen[wi].sets)
-            spans.append((len(exp_bases), len(e)))
-            exp_bases.extend(e)
-        tm_raw = self.ctx.tm(np.asarray(exp_bases, np.uint8).reshape(-1, k), TM_CONSTS)
+        distinct = hist.match(wis, allow)
+        tm_avg, gc, flags, deg, ndeg = self._primer_props(sets_arr, k, gc_lo, gc_hi)
         seqkeys = self.msa.seqkeys(k, pos) if self.sidecars else None
-        dimer = self._self_dimer([chosen[wi].sets for wi in wis])        # core:487-503 for all windows at once
+        dimer = self._self_dimer(sets_list)                                   # core:487-503 for all windows at once
         out = []
-        for n, wi in enumerate(wis):
-            t, info = chosen[wi], accepted[wi]
-            sets = t.sets
-            primer = primer_string(sets)
-            deg = degeneracy(sets)
+        for i in range(n):
+            wi, p, c_bit, t_bit, cover_number, _ = keep[i]
+            sets = sets_list[i]
             # core:846: expansions that are not keys of `cover`; the defaultdict look-ups of the seeds (core:787-835)
             # added their strings as keys, observed or not
-            nonsense = deg - int(distinct[n])
-            for tr in tracks[wi]:
-                seed_sets = [1 << b for b in tr.seed]
-                if tr.seed_cover == 0 and all(a & b for a, b in zip(sets, seed_sets)):
+            nonsense = int(deg[i]) - int(distinct[i])
+            for ti in range(int(res["ntracks"][i])):
+                if res["seed_cover"][i, ti] == 0 and all((sets[j] >> int(res["seeds"][i, ti, j])) & 1 for j in range(k)):
                     nonsense -= 1
-            a, cnt = spans[n]
-            tms = [round(float(x), 2) for x in tm_raw[a:a + cnt]]
-            tm_avg = round(exact_mean(tms), 2)
-            perfect = int(counts[n][0])
-            info_col = information(sets, gc_lo, gc_hi, self.distance)
-            if dimer[n]:
+            if dimer[i]:
                 continue                                                  # core:749-751
-            row = [info["pos"], info["c_bit"], info["t_bit"], primer, n_degenerate(sets), nonsense, perfect,
-                   t.init + t.fm, t.init + t.rm, tm_avg, info_col]
-            rec = {"row": row, "trace": [p for tr in tracks[wi] for p in tr.trace]}
+            fl = int(flags[i])
+            notes = []
+            if fl & 1:
+                notes.append("GC_out_of_range (" + str(float(gc[i])) + ")")
+            if fl & 2:
+                notes.append("di_nucleotide")
+            if fl & 4:
+                notes.append("hairpin")
+            init, fm, rm = (int(x) for x in res["counts"][i, :3])
+            row = [p, c_bit, t_bit, primer_string(sets), int(ndeg[i]), nonsense, int(counts[i][0]), init + fm,
+                   init + rm, float(tm_avg[i]), float(gc[i]) if not notes else "|".join(notes)]
+            a, b = int(res["trace_off"][i]), int(res["trace_off"][i + 1])
+            rec = {"row": row, "trace": [primer_string(t[:k].tolist()) for t in res["trace"][a:b]]}
             if self.sidecars:
-                rec["non_cov"], rec["gap_ids"] = self._sidecars(hist, wi, info["pos"], sets, bits[n], seqkeys[n])
+                rec["non_cov"], rec["gap_ids"] = self._sidecars(hist, wi, p, sets, bits[i], seqkeys[i])
             out.append(rec)
         self.stats["accepted"] += len(out)
         return out
+
+    def _primer_props(self, sets_arr, k, gc_lo, gc_hi):
+        """Tm average, GC content and filter flags of the chosen primers (core:849-852, 507-521)"""
+        if not hasattr(self.ctx, "h"):                 # injected test backend
+            return self.ctx.primer_props(sets_arr, k, gc_lo, gc_hi, self.distance, TM_CONSTS)
+        tm_avg, gc, flags, deg, ndeg = self.ctx.primer_props(sets_arr, k, gc_lo, gc_hi, self.distance, TM_CONSTS)
+        for i in np.nonzero(flags & (64 | 128))[0].tolist():      # a mean on a rounding tie: exact rational replay
+            sets = sets_arr[i, :k].tolist()
+            if flags[i] & 64:
+                raw = self.ctx.tm(np.asarray(expand_keys(sets), np.uint8).reshape(-1, k), TM_CONSTS)
+                tm_avg[i] = round(exact_mean([round(float(x), 2) for x in raw]), 2)
+            if flags[i] & 128:
+                gc[i] = gc_content(sets)
+                flags[i] = (flags[i] & ~1) | (0 if gc_lo <= gc[i] <= gc_hi else 1)
+        return tm_avg, gc, flags, deg, ndeg
 
     def _sidecars(self, hist, wi, pos, sets, bits, keys):
         """core:1116-1125 / 696-698: {haplotype: [ids]} of the sequences the final primer does not cover (F, R) and

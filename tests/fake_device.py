@@ -46,6 +46,20 @@ class Context:
             return np.array(tm), np.array(dh), np.array(ds)
         return np.array(tm)
 
+    def primer_props(self, sets_arr, k, gc_lo, gc_hi, distance, consts3):
+        from statistics import mean
+        n = len(sets_arr)
+        tm, gc = np.zeros(n), np.zeros(n)
+        flags, deg, ndeg = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.int32)
+        for i in range(n):
+            p = "".join(CODE_CHARS[c] for c in sets_arr[i, :k])
+            tm[i] = round(mean([o.tm(e) for e in o.expand(p)]), 2)
+            gc[i] = o.gc_content(p)
+            flags[i] = (0 if gc_lo <= gc[i] <= gc_hi else 1) | (2 if o.has_repeat(p) else 0) | \
+                       (4 if o.has_hairpin(p, distance) else 0)
+            deg[i], ndeg[i] = o.degeneracy(p), o.n_degenerate(p)
+        return tm, gc, flags, deg, ndeg
+
     def dimer_flags(self, sets_list):
         return np.array([o.self_dimer("".join(CODE_CHARS[c] for c in s)) for s in sets_list], bool)
 
