@@ -208,7 +208,7 @@ def run_b200(args):
             fn()
         app.ctx.profile_read(None)
         app.ctx.profile(name == "value")
-        app.stats.update(evals=0, scan_calls=0, candidates=0)
+        app.stats.update(evals=0, scan_calls=0, candidates=0, phase_ms={})
         launches0 = app.ctx.launches
         if name == "value":
             sampler.start()
@@ -236,6 +236,7 @@ def run_b200(args):
             results["evals_per_step"] = app.stats["evals"] / args.steps
             results["scan_calls"] = app.stats["scan_calls"] / args.steps
             results["candidates"] = app.stats["candidates"] / args.steps
+            results["phases"] = {k: round(v / args.steps, 2) for k, v in app.stats["phase_ms"].items()}
             app.ctx.profile(False)
     evals_all = float(results["evals_per_step"])      # already global: calls x (sequences of ALL shards)
     if rank != 0:
@@ -272,6 +273,7 @@ def run_b200(args):
                              BYTES_PER_EVAL},
         "kernels": {"k_hist_ms_per_step": results["hist"][0] / args.steps,
                     "k_scan_ms_per_step": scan_ms / args.steps},
+        "host_phases_ms_per_step": results["phases"],
     }
     if not args.no_cpu_baseline:
         evc, dtc = cpu_sample(args.cpu_sample_seqs, n_col, args.cpu_sample_windows, 1)

@@ -371,10 +371,21 @@ class NN_degenerate(object):
     def _design_batch(self, positions):
         k, v, N = self.primer_length, self.variation, self.total_sequence_number
         self.stats["windows"] += len(positions)
+        ph = self.stats.setdefault("phase_ms", {})
+        tick = [time.perf_counter()]
+
+        def lap(name):
+            now = time.perf_counter()
+            ph[name] = ph.get(name, 0.0) + 1000 * (now - tick[0])
+            tick[0] = now
+
         with self.msa.hist(k, v, positions) as hist:
+            lap("hist_build")
             st = hist.stats()
+            lap("hist_stats")
             if self.comm.world > 1:
                 st = self._merge_shards(hist, st)
+                lap("merge_shards")
             gap_n = st["gap_n"]
             # core:713 `round(gap_n / N, 2) >= 1 - coverage`: exact for all but ratios on a rounding tie
             ratio = gap_n / N
@@ -391,9 +402,11 @@ class NN_degenerate(object):
                 if ent is not None:
                     accepted.append((wi, positions[wi], ent[0], ent[1], N - int(gap_n[wi]), bool(st["nuniq"][wi, 2] > 0)))
                     sel[wi] = 1
+            lap("gates")
             if not accepted:
                 return []
             freq, nn = hist.tensors(sel)
+            lap("tensors")
             keep = []
             for a in accepted:                                                     # core:736-740
                 f = freq[a[0]]
@@ -412,9 +425,13 @@ class NN_degenerate(object):
             res = _lib.walk(k, v, self.number_of_dege_bases, self.score_of_dege_bases, self.fmask, self.rmask,
                             np.array([a[1] for a in keep], np.int32), np.array([a[4] for a in keep], np.int64),
                             freq[wis], nn[wis].reshape(len(keep), k - 1, 16), mm_key, scan_fn)
+            lap("walk")
             self.stats["candidates"] += int(res["stats"][1])
             self.stats["evals"] += int(res["stats"][2]) * N
-            return self._finish(hist, keep, res)
+            out = self._finish(hist, keep, res)
+            lap("finish")
+        lap("free")
+        return out
 
     def _merge_shards(self, hist, st):
         """Sequence-sharded run: make the tables of every window that can still pass the gates GLOBAL on every rank.

@@ -274,9 +274,9 @@ extern "C" int mpb_msa_upload(mpb_ctx* ctx, const uint8_t* packed4, int64_t n_se
     m->err = nullptr;
     m->row0 = 0;
     size_t pbytes = (size_t)m->ncw * 4 * m->nsp * sizeof(uint32_t);
-    cudaError_t e = cudaMalloc(&m->planes, pbytes);
-    if (e == cudaSuccess) e = cudaMalloc(&m->lens, m->nsp * sizeof(int32_t));
-    if (e == cudaSuccess) e = cudaMalloc(&m->err, sizeof(int));
+    cudaError_t e = cudaMallocAsync(&m->planes, pbytes, ctx->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&m->lens, m->nsp * sizeof(int32_t), ctx->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&m->err, sizeof(int), ctx->stream);
     if (e != cudaSuccess) {
         mpb_msa_free(m);
         return fail(MPB_ENOMEM, "alignment planes (%zu bytes): %s", pbytes, cudaGetErrorString(e));
@@ -309,9 +309,9 @@ extern "C" int mpb_msa_upload(mpb_ctx* ctx, const uint8_t* packed4, int64_t n_se
 
 extern "C" void mpb_msa_free(mpb_msa* m) {
     if (!m) return;
-    cudaFree(m->planes);
-    cudaFree(m->lens);
-    cudaFree(m->err);
+    if (m->planes) cudaFreeAsync(m->planes, m->ctx->stream);
+    if (m->lens) cudaFreeAsync(m->lens, m->ctx->stream);
+    if (m->err) cudaFreeAsync(m->err, m->ctx->stream);
     delete m;
 }
 extern "C" int64_t mpb_msa_nseq(const mpb_msa* m) { return m ? m->n_seq : 0; }
@@ -359,66 +359,122 @@ extern "C" int mpb_seq_attr(mpb_msa* m, int32_t* lead_hd, int32_t* rstrip_hd) {
 // ------------------------------------------------------------------------------------------------------
 #define HIST_THREADS 256
 
-// thread = sequence; blockIdx.y strides over the windows of the batch
+// Block-private staging table: the haplotypes of HIST_TILES x 256 sequences of one window are first counted in
+// shared memory (a hot haplotype then costs ONE global atomic per block instead of one per warp: same-address L2
+// atomics were the bound of the first version), then flushed to the window's global table.
+#define HIST_TILES 4
+#define HIST_SLOTS 512  // power of two
+#define HIST_PROBES 8
+
+__device__ __forceinline__ void hist_stage(unsigned long long* s_key, unsigned int* s_cnt, unsigned long long* s_first,
+                                           uint64_t* K, uint32_t* C, uint64_t* F, int log2cap, uint64_t key,
+                                           uint32_t add, uint64_t ord, int* err) {
+    uint32_t h = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 55) & (HIST_SLOTS - 1);
+    for (int probe = 0; probe < HIST_PROBES; ++probe) {
+        unsigned long long cur = s_key[h];
+        if (cur == MPB_KEY_EMPTY_D) {
+            cur = atomicCAS(&s_key[h], (unsigned long long)MPB_KEY_EMPTY_D, (unsigned long long)key);
+            if (cur == MPB_KEY_EMPTY_D) cur = key;
+        }
+        if (cur == key) {
+            atomicAdd(&s_cnt[h], add);
+            atomicMin(&s_first[h], (unsigned long long)ord);
+            return;
+        }
+        h = (h + 1) & (HIST_SLOTS - 1);
+    }
+    mpb_table_add(K, C, F, log2cap, key, add, ord, err);  // staging table crowded (variable window): go global
+}
+
+// block (x, y): sequence tiles [x*HIST_TILES, (x+1)*HIST_TILES) ; blockIdx.y strides over the windows of the batch
 __global__ void __launch_bounds__(HIST_THREADS)
 k_hist(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq, const int32_t* __restrict__ lens, int k, int v,
        const int32_t* __restrict__ win_pos, int nw, uint64_t* __restrict__ keys, uint32_t* __restrict__ cnt,
        uint64_t* __restrict__ first, int log2cap, unsigned long long* __restrict__ gap_n,
        unsigned long long* __restrict__ iupac_gap_n, int32_t* __restrict__ exc, unsigned long long* __restrict__ exc_n,
        long long exc_max, long long row0, int* __restrict__ err) {
-    const int64_t s = (int64_t)blockIdx.x * HIST_THREADS + threadIdx.x;
-    const uint64_t gs = (uint64_t)(row0 + s);  // global sequence index: first-seen order across shards
-    const bool valid = s < n_seq;
+    __shared__ unsigned long long s_key[HIST_SLOTS];
+    __shared__ unsigned long long s_first[HIST_SLOTS];
+    __shared__ unsigned int s_cnt[HIST_SLOTS];
+    __shared__ unsigned int s_gap;
     const int lane = threadIdx.x & 31;
-    const uint32_t kmask = (k == 32) ? 0xFFFFFFFFu : ((1u << k) - 1u);
-    const int len = valid ? lens[s] : 0;
+    const uint32_t kmask = (1u << k) - 1u;
     const uint64_t cap = 1ull << log2cap;
+    for (int i = threadIdx.x; i < HIST_SLOTS; i += HIST_THREADS) {
+        s_key[i] = MPB_KEY_EMPTY_D;
+        s_first[i] = ~0ull;
+        s_cnt[i] = 0;
+    }
+    if (threadIdx.x == 0) s_gap = 0;
+    __syncthreads();
     for (int wi = blockIdx.y; wi < nw; wi += gridDim.y) {
         const int p = win_pos[wi];
-        Win w;
-        w.a = w.c = w.g = w.t = w.multi = 0;
-        w.gapv = kmask;
-        bool ok = true;
-        if (valid) ok = mpb_load_window(pl, nsp, s, len, p, k, kmask, w);
-        if (!ok) atomicOr(err, MPB_ERR_SHORT_ROW);
-        const int ngap = __popc(w.gapv);
-        const bool isgap = valid && ngap > v;
-        const bool cover = valid && !isgap;
-        const unsigned gb = __ballot_sync(0xffffffffu, isgap);
-        if (lane == 0 && gb) atomicAdd(&gap_n[wi], (unsigned long long)__popc(gb));
         uint64_t* K = keys + (uint64_t)wi * cap;
         uint32_t* C = cnt + (uint64_t)wi * cap;
         uint64_t* F = first + (uint64_t)wi * cap;
-        const bool simple = cover && w.multi == 0;
-        const unsigned smask = __ballot_sync(0xffffffffu, simple);
-        if (simple) {
-            const uint64_t key = mpb_key(w.c, w.g, w.t, w.gapv, k);
-            const unsigned peers = __match_any_sync(smask, key);
-            if (lane == __ffs(peers) - 1)  // lowest lane = lowest sequence index = first seen
-                mpb_table_add(K, C, F, log2cap, key, (uint32_t)__popc(peers), gs << 16, err);
-        } else if (cover) {
-            const uint32_t total = mpb_expansions(w);
-            if (total > MPB_MAX_EXP) {
-                atomicOr(err, MPB_ERR_EXPAND);
-            } else {
-                for (uint32_t e = 0; e < total; ++e) {
-                    uint32_t a, c, g, t;
-                    mpb_expand(w, e, a, c, g, t);
-                    mpb_table_add(K, C, F, log2cap, mpb_key(c, g, t, w.gapv, k), 1u, (gs << 16) | e, err);
+        for (int t = 0; t < HIST_TILES; ++t) {
+            const int64_t tile = (int64_t)blockIdx.x * HIST_TILES + t;
+            if (tile * HIST_THREADS >= n_seq) break;  // uniform
+            const int64_t s = tile * HIST_THREADS + threadIdx.x;
+            const uint64_t gs = (uint64_t)(row0 + s);  // global sequence index: first-seen order across shards
+            const bool valid = s < n_seq;
+            Win w;
+            w.a = w.c = w.g = w.t = w.multi = 0;
+            w.gapv = kmask;
+            if (valid && !mpb_load_window(pl, nsp, s, lens[s], p, k, kmask, w)) atomicOr(err, MPB_ERR_SHORT_ROW);
+            const int ngap = __popc(w.gapv);
+            const bool isgap = valid && ngap > v;
+            const bool cover = valid && !isgap;
+            const unsigned gb = __ballot_sync(0xffffffffu, isgap);
+            if (lane == 0 && gb) atomicAdd(&s_gap, (unsigned)__popc(gb));
+            const bool simple = cover && w.multi == 0;
+            const unsigned smask = __ballot_sync(0xffffffffu, simple);
+            if (simple) {
+                const uint64_t key = mpb_key(w.c, w.g, w.t, w.gapv, k);
+                const unsigned peers = __match_any_sync(smask, key);
+                if (lane == __ffs(peers) - 1)  // lowest lane = lowest sequence index = first seen
+                    hist_stage(s_key, s_cnt, s_first, K, C, F, log2cap, key, (uint32_t)__popc(peers), gs << 16, err);
+            } else if (cover) {
+                const uint32_t total = mpb_expansions(w);
+                if (total > MPB_MAX_EXP) {
+                    atomicOr(err, MPB_ERR_EXPAND);
+                } else {
+                    for (uint32_t e = 0; e < total; ++e) {
+                        uint32_t a, c, g, tt;
+                        mpb_expand(w, e, a, c, g, tt);
+                        hist_stage(s_key, s_cnt, s_first, K, C, F, log2cap, mpb_key(c, g, tt, w.gapv, k), 1u,
+                                   (gs << 16) | e, err);
+                    }
                 }
-            }
-        } else if (isgap) {
-            if (w.multi == 0) {
-                mpb_table_add(K, C, F, log2cap, mpb_key(w.c, w.g, w.t, w.gapv, k), 1u, gs << 16, err);
-            } else {
-                atomicAdd(&iupac_gap_n[wi], 1ull);
-                unsigned long long slot = atomicAdd(exc_n, 1ull);
-                if ((long long)slot < exc_max) {
-                    exc[2 * slot] = wi;
-                    exc[2 * slot + 1] = (int32_t)s;
+            } else if (isgap) {
+                if (w.multi == 0) {
+                    hist_stage(s_key, s_cnt, s_first, K, C, F, log2cap, mpb_key(w.c, w.g, w.t, w.gapv, k), 1u, gs << 16,
+                               err);
+                } else {
+                    atomicAdd(&iupac_gap_n[wi], 1ull);
+                    unsigned long long slot = atomicAdd(exc_n, 1ull);
+                    if ((long long)slot < exc_max) {
+                        exc[2 * slot] = wi;
+                        exc[2 * slot + 1] = (int32_t)s;
+                    }
                 }
             }
         }
+        __syncthreads();
+        for (int i = threadIdx.x; i < HIST_SLOTS; i += HIST_THREADS) {  // flush + clear the staging table
+            const unsigned long long key = s_key[i];
+            if (key != MPB_KEY_EMPTY_D) {
+                mpb_table_add(K, C, F, log2cap, key, s_cnt[i], s_first[i], err);
+                s_key[i] = MPB_KEY_EMPTY_D;
+                s_first[i] = ~0ull;
+                s_cnt[i] = 0;
+            }
+        }
+        if (threadIdx.x == 0 && s_gap) {
+            atomicAdd(&gap_n[wi], (unsigned long long)s_gap);
+            s_gap = 0;
+        }
+        __syncthreads();
     }
 }
 
@@ -465,7 +521,7 @@ extern "C" int mpb_hist_build(mpb_msa* m, int k, int v, const int32_t* win_pos, 
     CK(cudaMemsetAsync(h->iupac_gap_n, 0, (size_t)nw * 8, ctx->stream));
     CK(cudaMemsetAsync(h->exc_n, 0, 8, ctx->stream));
     CK(cudaMemcpyAsync(h->win_pos, win_pos, (size_t)nw * 4, cudaMemcpyHostToDevice, ctx->stream));
-    const unsigned gx = (unsigned)((m->n_seq + HIST_THREADS - 1) / HIST_THREADS);
+    const unsigned gx = (unsigned)((m->n_seq + (long long)HIST_THREADS * HIST_TILES - 1) / ((long long)HIST_THREADS * HIST_TILES));
     unsigned gy = (unsigned)nw;
     const unsigned want = (unsigned)ctx->sm_count * 8;
     if (gx >= want) gy = 1;
@@ -962,10 +1018,120 @@ extern "C" int mpb_hist_exceptions(mpb_hist* h, int64_t max_n, int32_t* win_idx,
         }                                                                                         \
     }
 
+// One chunk (CNT candidates of one window, masks in registers) against the block's sequence tiles.
+template <bool BITS, int CNT>
+__device__ __forceinline__ void scan_chunk(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq,
+                                           const int32_t* __restrict__ lens, int k, int v, uint32_t kmask,
+                                           uint32_t fmask, uint32_t rmask, int first, int p, long long tile0,
+                                           int tiles_per_block, const uint32_t* __restrict__ cand_allow,
+                                           unsigned int* __restrict__ s_out, const int32_t* __restrict__ bits_slot,
+                                           uint32_t* __restrict__ bits, long long words, int* __restrict__ err) {
+    uint32_t nA[CNT], nC[CNT], nG[CNT], nT[CNT];
+    unsigned acc0[CNT], accf[CNT], accr[CNT];
+#pragma unroll
+    for (int ci = 0; ci < CNT; ++ci) {
+        const uint4 al = __ldg((const uint4*)(cand_allow) + first + ci);
+        nA[ci] = ~al.x & kmask;
+        nC[ci] = ~al.y & kmask;
+        nG[ci] = ~al.z & kmask;
+        nT[ci] = ~al.w & kmask;
+        acc0[ci] = accf[ci] = accr[ci] = 0;
+    }
+    const int lane = threadIdx.x & 31;
+    // the two column words of this window: uniform for the whole block
+    const uint32_t* __restrict__ wbase = pl + ((int64_t)(p >> 5) * 4) * nsp;
+    const int sh = p & 31;
+    const bool inside_all = true;
+    (void)inside_all;
+    for (int t = 0; t < tiles_per_block; ++t) {
+        const long long tile = tile0 + t;
+        if (tile * SCAN_THREADS >= n_seq) break;  // uniform
+        const int64_t s = tile * SCAN_THREADS + threadIdx.x;
+        const bool valid = s < n_seq;
+        Win w;
+        w.a = w.c = w.g = w.t = w.multi = 0;
+        w.gapv = kmask;
+        bool isgap = false;
+        unsigned nonf = 0, nonr = 0;
+        if (valid) {
+            const uint32_t* q = wbase + s;
+            const uint32_t a0 = q[0], c0 = q[nsp], g0 = q[2 * nsp], t0 = q[3 * nsp];
+            const uint32_t a1 = q[4 * nsp], c1 = q[5 * nsp], g1 = q[6 * nsp], t1 = q[7 * nsp];
+            w.a = __funnelshift_r(a0, a1, sh) & kmask;
+            w.c = __funnelshift_r(c0, c1, sh) & kmask;
+            w.g = __funnelshift_r(g0, g1, sh) & kmask;
+            w.t = __funnelshift_r(t0, t1, sh) & kmask;
+            uint32_t gapv = ~(w.a | w.c | w.g | w.t) & kmask;
+            const int len = lens[s];
+            if (p + k > len) {  // ragged row
+                Win tmp;
+                if (!mpb_window_slow(pl, nsp, s, len, p, k, tmp)) atomicOr(err, MPB_ERR_SHORT_ROW);
+                w.a = tmp.a;
+                w.c = tmp.c;
+                w.g = tmp.g;
+                w.t = tmp.t;
+                gapv = ~(w.a | w.c | w.g | w.t) & kmask;
+            } else if (((gapv & 1u) | ((gapv >> (k - 1)) & 1u)) && gapv != kmask) {
+                mpb_patch_edges(pl, nsp, s, len, p, k, kmask, w);
+                gapv = ~(w.a | w.c | w.g | w.t) & kmask;
+            }
+            w.gapv = gapv;
+            w.multi = mpb_multi(w.a, w.c, w.g, w.t);
+            isgap = __popc(gapv) > v;
+            if (!isgap) {
+                if (w.multi == 0) {
+#pragma unroll
+                    for (int ci = 0; ci < CNT; ++ci) SCAN_EVAL(w.a, w.c, w.g, w.t, ci)
+                } else {
+                    const uint32_t nexp = mpb_expansions(w);
+                    if (nexp > MPB_MAX_EXP) {
+                        atomicOr(err, MPB_ERR_EXPAND);
+                    } else {
+                        for (uint32_t e = 0; e < nexp; ++e) {
+                            uint32_t a, c, g, tt;
+                            mpb_expand(w, e, a, c, g, tt);
+#pragma unroll
+                            for (int ci = 0; ci < CNT; ++ci) SCAN_EVAL(a, c, g, tt, ci)
+                        }
+                    }
+                }
+            }
+        }
+        if (BITS) {
+            const long long word = tile * (SCAN_THREADS / 32) + (threadIdx.x >> 5);
+            const unsigned bg = __ballot_sync(0xffffffffu, isgap);
+#pragma unroll
+            for (int ci = 0; ci < CNT; ++ci) {
+                const int slot = bits_slot[first + ci];
+                if (slot < 0) continue;  // uniform
+                const unsigned bf = __ballot_sync(0xffffffffu, (nonf >> ci) & 1u);
+                const unsigned br = __ballot_sync(0xffffffffu, (nonr >> ci) & 1u);
+                if (lane == 0 && word < words) {
+                    uint32_t* o = bits + (long long)slot * 3 * words;
+                    o[word] = bf;
+                    o[words + word] = br;
+                    o[2 * words + word] = bg;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int ci = 0; ci < CNT; ++ci) {
+        const unsigned r0 = __reduce_add_sync(0xffffffffu, acc0[ci]);
+        const unsigned rf = __reduce_add_sync(0xffffffffu, accf[ci]);
+        const unsigned rr = __reduce_add_sync(0xffffffffu, accr[ci]);
+        if (lane < 3) {
+            const unsigned val = lane == 0 ? r0 : (lane == 1 ? rf : rr);
+            if (val) atomicAdd(&s_out[ci * 3 + lane], val);
+        }
+    }
+}
+
 // Block (x, y): sequences [x*T*256, (x+1)*T*256) against the chunks [y*cpb, (y+1)*cpb).  A chunk = up to
-// SCAN_CHUNK candidates of ONE window: their masks sit in registers while the block walks its T sequence tiles,
-// each thread keeping per-candidate counters in registers; one warp reduction per chunk, block-private counters in
-// shared memory, one coalesced store of the block's partial counts at the end (no global atomics).
+// SCAN_CHUNK candidates of ONE window: their masks sit in registers while the block walks its T sequence tiles
+// (T small enough that the tiles' words stay in L1 for the next chunk of the same column word), each thread keeping
+// per-candidate counters in registers; one warp reduction per chunk, block-private counters in shared memory, one
+// coalesced store of the block's partial counts at the end (no global atomics).
 template <bool BITS>
 __global__ void __launch_bounds__(SCAN_THREADS, 4)
 k_scan(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq, const int32_t* __restrict__ lens, int k, int v,
@@ -978,85 +1144,27 @@ k_scan(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq, const int32_
     for (int i = threadIdx.x; i < (ch1 - ch0) * SCAN_CHUNK * 3; i += SCAN_THREADS) s_cnt[i] = 0;
     __syncthreads();
     const uint32_t kmask = (1u << k) - 1u;
-    const int lane = threadIdx.x & 31;
     const long long tile0 = (long long)blockIdx.x * tiles_per_block;
     for (int ch = ch0; ch < ch1; ++ch) {
         const int4 cd = chunks[ch];  // first candidate, count, window column
-        const int first = cd.x, cnt = cd.y, p = cd.z;
-        uint32_t nA[SCAN_CHUNK], nC[SCAN_CHUNK], nG[SCAN_CHUNK], nT[SCAN_CHUNK];
-        unsigned acc0[SCAN_CHUNK], accf[SCAN_CHUNK], accr[SCAN_CHUNK];
-#pragma unroll
-        for (int ci = 0; ci < SCAN_CHUNK; ++ci) {
-            const bool on = ci < cnt;
-            const uint4 al = on ? __ldg((const uint4*)(cand_allow) + first + ci) : make_uint4(0, 0, 0, 0);
-            nA[ci] = ~al.x & kmask;
-            nC[ci] = ~al.y & kmask;
-            nG[ci] = ~al.z & kmask;
-            nT[ci] = ~al.w & kmask;
-            acc0[ci] = accf[ci] = accr[ci] = 0;
-        }
-        for (int t = 0; t < tiles_per_block; ++t) {
-            const long long tile = tile0 + t;
-            const int64_t s = tile * SCAN_THREADS + threadIdx.x;
-            if (tile * SCAN_THREADS >= n_seq) break;  // uniform
-            const bool valid = s < n_seq;
-            Win w;
-            w.a = w.c = w.g = w.t = w.multi = 0;
-            w.gapv = kmask;
-            bool isgap = false;
-            unsigned nonf = 0, nonr = 0;
-            if (valid) {
-                if (!mpb_load_window(pl, nsp, s, lens[s], p, k, kmask, w)) atomicOr(err, MPB_ERR_SHORT_ROW);
-                isgap = __popc(w.gapv) > v;
-                if (!isgap) {
-                    if (w.multi == 0) {
-#pragma unroll
-                        for (int ci = 0; ci < SCAN_CHUNK; ++ci)
-                            if (ci < cnt) SCAN_EVAL(w.a, w.c, w.g, w.t, ci)
-                    } else {
-                        const uint32_t nexp = mpb_expansions(w);
-                        if (nexp > MPB_MAX_EXP) {
-                            atomicOr(err, MPB_ERR_EXPAND);
-                        } else {
-                            for (uint32_t e = 0; e < nexp; ++e) {
-                                uint32_t a, c, g, tt;
-                                mpb_expand(w, e, a, c, g, tt);
-#pragma unroll
-                                for (int ci = 0; ci < SCAN_CHUNK; ++ci)
-                                    if (ci < cnt) SCAN_EVAL(a, c, g, tt, ci)
-                            }
-                        }
-                    }
-                }
-            }
-            if (BITS) {
-                const long long word = tile * (SCAN_THREADS / 32) + (threadIdx.x >> 5);
-                const unsigned bg = __ballot_sync(0xffffffffu, isgap);
-                for (int ci = 0; ci < cnt; ++ci) {
-                    const int slot = bits_slot[first + ci];
-                    if (slot < 0) continue;  // uniform
-                    const unsigned bf = __ballot_sync(0xffffffffu, (nonf >> ci) & 1u);
-                    const unsigned br = __ballot_sync(0xffffffffu, (nonr >> ci) & 1u);
-                    if (lane == 0 && word < words) {
-                        uint32_t* o = bits + (long long)slot * 3 * words;
-                        o[word] = bf;
-                        o[words + word] = br;
-                        o[2 * words + word] = bg;
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int ci = 0; ci < SCAN_CHUNK; ++ci) {
-            if (ci < cnt) {
-                const unsigned r0 = __reduce_add_sync(0xffffffffu, acc0[ci]);
-                const unsigned rf = __reduce_add_sync(0xffffffffu, accf[ci]);
-                const unsigned rr = __reduce_add_sync(0xffffffffu, accr[ci]);
-                if (lane < 3) {
-                    const unsigned val = lane == 0 ? r0 : (lane == 1 ? rf : rr);
-                    if (val) atomicAdd(&s_cnt[((ch - ch0) * SCAN_CHUNK + ci) * 3 + lane], val);
-                }
-            }
+        unsigned int* so = &s_cnt[(ch - ch0) * SCAN_CHUNK * 3];
+        switch (cd.y) {
+            case 1:
+                scan_chunk<BITS, 1>(pl, nsp, n_seq, lens, k, v, kmask, fmask, rmask, cd.x, cd.z, tile0, tiles_per_block,
+                                    cand_allow, so, bits_slot, bits, words, err);
+                break;
+            case 2:
+                scan_chunk<BITS, 2>(pl, nsp, n_seq, lens, k, v, kmask, fmask, rmask, cd.x, cd.z, tile0, tiles_per_block,
+                                    cand_allow, so, bits_slot, bits, words, err);
+                break;
+            case 3:
+                scan_chunk<BITS, 3>(pl, nsp, n_seq, lens, k, v, kmask, fmask, rmask, cd.x, cd.z, tile0, tiles_per_block,
+                                    cand_allow, so, bits_slot, bits, words, err);
+                break;
+            default:
+                scan_chunk<BITS, 4>(pl, nsp, n_seq, lens, k, v, kmask, fmask, rmask, cd.x, cd.z, tile0, tiles_per_block,
+                                    cand_allow, so, bits_slot, bits, words, err);
+                break;
         }
     }
     __syncthreads();
@@ -1116,7 +1224,7 @@ extern "C" int mpb_scan(mpb_msa* m, int k, int v, uint32_t fmask, uint32_t rmask
     const long long target = (long long)ctx->sm_count * 8;  // blocks in flight we want at least
     int tpb = (int)(n_tiles * n_chunks / (target * 16));     // tiles per block: long walks amortise the reductions
     if (tpb < 1) tpb = 1;
-    if (tpb > 16) tpb = 16;
+    if (tpb > 4) tpb = 4;  // 4 CTAs/SM x 4 tiles x 8 KB of window words stay L1-resident across chunks
     const int gx = (int)((n_tiles + tpb - 1) / tpb);
     int cpb = (int)(((long long)n_chunks * gx + target - 1) / target);
     if (cpb < 1) cpb = 1;

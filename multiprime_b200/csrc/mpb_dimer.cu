@@ -202,6 +202,11 @@ extern "C" int mpb_dimer_prepare(mpb_ctx* ctx, const uint8_t* sets, const int32_
     d->ctx = ctx;
     d->n = n;
     d->sets = nullptr;
+    d->lens = nullptr;
+    d->off_p = d->off_e = nullptr;
+    d->exp = d->end_rc = nullptr;
+    d->end_info = nullptr;
+    d->table = nullptr;
     d->pent = nullptr;
     d->min_end = min_end;
     d->h_off_p.assign(n + 1, 0);
@@ -236,15 +241,15 @@ extern "C" int mpb_dimer_prepare(mpb_ctx* ctx, const uint8_t* sets, const int32_
     }
     const int64_t tp = d->h_off_p[n], te = d->h_off_e[n];
     double* cst = nullptr;
-    cudaError_t e = cudaMalloc(&d->sets, (size_t)n * DIMER_MAXLEN);
-    if (e == cudaSuccess) e = cudaMalloc(&d->lens, (size_t)n * 4);
-    if (e == cudaSuccess) e = cudaMalloc(&d->off_p, (size_t)(n + 1) * 8);
-    if (e == cudaSuccess) e = cudaMalloc(&d->off_e, (size_t)(n + 1) * 8);
-    if (e == cudaSuccess) e = cudaMalloc(&d->exp, (size_t)tp * 8);
-    if (e == cudaSuccess) e = cudaMalloc(&d->end_rc, (size_t)(te ? te : 1) * 8);
-    if (e == cudaSuccess) e = cudaMalloc(&d->end_info, (size_t)(te ? te : 1) * 4);
-    if (e == cudaSuccess) e = cudaMalloc(&d->table, 33 * 33 * 33);
-    if (e == cudaSuccess) e = cudaMalloc(&cst, 24 * 8);
+    cudaError_t e = cudaMallocAsync(&d->sets, (size_t)n * DIMER_MAXLEN, st);
+    if (e == cudaSuccess) e = cudaMallocAsync(&d->lens, (size_t)n * 4, st);
+    if (e == cudaSuccess) e = cudaMallocAsync(&d->off_p, (size_t)(n + 1) * 8, st);
+    if (e == cudaSuccess) e = cudaMallocAsync(&d->off_e, (size_t)(n + 1) * 8, st);
+    if (e == cudaSuccess) e = cudaMallocAsync(&d->exp, (size_t)tp * 8, st);
+    if (e == cudaSuccess) e = cudaMallocAsync(&d->end_rc, (size_t)(te ? te : 1) * 8, st);
+    if (e == cudaSuccess) e = cudaMallocAsync(&d->end_info, (size_t)(te ? te : 1) * 4, st);
+    if (e == cudaSuccess) e = cudaMallocAsync(&d->table, 33 * 33 * 33, st);
+    if (e == cudaSuccess) e = cudaMallocAsync(&cst, 24 * 8, st);
     if (e != cudaSuccess) return mpb_fail(MPB_ENOMEM, "dimer tables: %s", cudaGetErrorString(e));
     MPB_CK(cudaMemcpyAsync(d->sets, sets, (size_t)n * DIMER_MAXLEN, cudaMemcpyHostToDevice, st));
     MPB_CK(cudaMemcpyAsync(d->lens, lens, (size_t)n * 4, cudaMemcpyHostToDevice, st));
@@ -261,22 +266,17 @@ extern "C" int mpb_dimer_prepare(mpb_ctx* ctx, const uint8_t* sets, const int32_
         MPB_LAUNCH(ctx, k_dimer_ends, g2, 256, 0, d->sets, d->lens, d->off_e, n, min_end, max_end, init_both, cst,
                    d->end_rc, d->end_info);
     MPB_CK(cudaStreamSynchronize(st));
-    cudaFree(cst);
+    cudaFreeAsync(cst, st);
     *out = d;
     return 0;
 }
 
 extern "C" void mpb_dimer_free(mpb_dimer* d) {
     if (!d) return;
-    cudaFree(d->sets);
-    cudaFree(d->lens);
-    cudaFree(d->off_p);
-    cudaFree(d->off_e);
-    cudaFree(d->exp);
-    cudaFree(d->end_rc);
-    cudaFree(d->end_info);
-    cudaFree(d->table);
-    cudaFree(d->pent);
+    cudaStream_t st = mpb_ctx_stream(d->ctx);
+    void* bufs[] = {d->sets, d->lens, d->off_p, d->off_e, d->exp, d->end_rc, d->end_info, d->table, d->pent};
+    for (void* b : bufs)
+        if (b) cudaFreeAsync(b, st);
     delete d;
 }
 
@@ -385,7 +385,7 @@ extern "C" int mpb_dimer_grid(mpb_dimer* d, int32_t row0, int32_t row1, int64_t 
     cudaStream_t st = mpb_ctx_stream(ctx);
     if (d->min_end != 5) return mpb_fail(MPB_EINVAL, "the pair grid needs min_end == 5");
     if (!d->pent) {
-        MPB_CK(cudaMalloc(&d->pent, (size_t)d->n * 32 * 4));
+        MPB_CK(cudaMallocAsync(&d->pent, (size_t)d->n * 32 * 4, st));
         MPB_LAUNCH(ctx, k_dimer_pent, (unsigned)((d->n + 127) / 128), 128, 0, d->sets, d->lens, d->n, 5, d->pent);
     }
     const long long qcap = 1ll << 26;
