@@ -182,6 +182,12 @@ int mpb_walk(int k, int v, int dnum, int degeneracy, uint32_t fmask, uint32_t rm
 int mpb_primer_props(mpb_ctx* ctx, const uint8_t* sets, int k, int32_t n, double gc_lo, double gc_hi, int distance,
                      const double* tm_consts3, double* tm_avg, double* gc, int32_t* flags, int32_t* deg, int32_t* ndeg);
 
+/* ---- pair coverage: get_multiPrime.py:560-569 ---------------------------------------------------------------------
+ * uf / ur [n_rows*words]: per-candidate bit vectors of the sequences the forward / reverse use of that candidate leaves
+ * uncovered (gap rows included), in mpb_scan's bit layout.  uncovered[q] = popcount(uf[pf[q]] | ur[pr[q]]). */
+int mpb_pair_cover(mpb_ctx* ctx, const uint32_t* uf_hd, const uint32_t* ur_hd, int32_t n_rows, int32_t words,
+                   const int32_t* pf_hd, const int32_t* pr_hd, int64_t n_pairs, int32_t* uncovered_hd);
+
 /* ---- primer-dimer predicates: core:457-503 dimer_check, finDimer_V4.py:191-224 ---------------------------------
  * sets[n*32] 4-bit base sets of n primers (one byte per position, row stride 32), lens[n] (host arrays).
  * Ends = suffixes of length min(max_end, len) .. min_end (max_end <= 0: len + max_end .. min_end, the

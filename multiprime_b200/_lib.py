@@ -51,6 +51,7 @@ SIGNATURES = {
                            _P, _P, _P, _P, _P, _P, C.c_int64, _P, _P, _P]),
     "mpb_primer_props": (C.c_int, [_P, _P, C.c_int, C.c_int32, C.c_double, C.c_double, C.c_int, _P, _P, _P, _P, _P,
                                    _P]),
+    "mpb_pair_cover": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P, _P, C.c_int64, _P]),
     "mpb_dimer_prepare": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int, C.c_int, C.c_int, _P, _P, C.POINTER(_P)]),
     "mpb_dimer_free": (None, [_P]),
     "mpb_dimer_counts": (C.c_int, [_P, _P, _P]),
@@ -198,6 +199,18 @@ class Context:
             check(load().mpb_primer_props(self.h, ptr(sets), k, n, gc_lo, gc_hi, distance, ptr(cst), ptr(tm), ptr(gc),
                                           ptr(flags), ptr(deg), ptr(ndeg)))
         return tm, gc, flags, deg, ndeg
+
+    def pair_cover(self, uf: np.ndarray, ur: np.ndarray, pf, pr) -> np.ndarray:
+        """popcount(uf[pf] | ur[pr]) per pair (get_multiPrime.py:560-569 on bit vectors)"""
+        uf = np.ascontiguousarray(uf, dtype=np.uint32)
+        ur = np.ascontiguousarray(ur, dtype=np.uint32)
+        pf = np.ascontiguousarray(pf, dtype=np.int32)
+        pr = np.ascontiguousarray(pr, dtype=np.int32)
+        out = np.zeros(len(pf), np.int32)
+        if len(pf):
+            check(load().mpb_pair_cover(self.h, ptr(uf), ptr(ur), uf.shape[0], uf.shape[1], ptr(pf), ptr(pr), len(pf),
+                                        ptr(out)))
+        return out
 
     def close(self):
         if self.h:

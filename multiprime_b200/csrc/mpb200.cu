@@ -1367,3 +1367,37 @@ extern "C" int mpb_tm(mpb_ctx* ctx, const uint8_t* seqs_hd, int k, int64_t n, co
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------------------
+// pair coverage (get_multiPrime.py:560-569): the sequences NOT covered by a primer pair are the union of the forward
+// primer's and the reverse primer's uncovered sets; with per-sequence bit vectors that is popcount(F | R).
+// ------------------------------------------------------------------------------------------------------
+__global__ void k_pair_cover(const uint32_t* __restrict__ uf, const uint32_t* __restrict__ ur,
+                             const int32_t* __restrict__ pf, const int32_t* __restrict__ pr, long long n_pairs,
+                             int words, int32_t* __restrict__ out) {
+    const long long q = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // warp per pair
+    const int lane = threadIdx.x & 31;
+    if (q >= n_pairs) return;
+    const uint32_t* a = uf + (long long)pf[q] * words;
+    const uint32_t* b = ur + (long long)pr[q] * words;
+    int n = 0;
+    for (int w = lane; w < words; w += 32) n += __popc(a[w] | b[w]);
+    n = __reduce_add_sync(0xffffffffu, n);
+    if (lane == 0) out[q] = n;
+}
+
+extern "C" int mpb_pair_cover(mpb_ctx* ctx, const uint32_t* uf_hd, const uint32_t* ur_hd, int32_t n_rows, int32_t words,
+                              const int32_t* pf_hd, const int32_t* pr_hd, int64_t n_pairs, int32_t* uncovered_hd) {
+    if (!ctx || !uf_hd || !ur_hd || !pf_hd || !pr_hd || !uncovered_hd) return fail(MPB_EINVAL, "NULL argument");
+    if (n_pairs < 1) return 0;
+    CK(cudaSetDevice(ctx->device));
+    InBuf uf(ctx, uf_hd, (size_t)n_rows * words * 4), ur(ctx, ur_hd, (size_t)n_rows * words * 4),
+        pf(ctx, pf_hd, (size_t)n_pairs * 4), pr(ctx, pr_hd, (size_t)n_pairs * 4);
+    OutBuf o(ctx, uncovered_hd, (size_t)n_pairs * 4);
+    if (uf.rc || ur.rc || pf.rc || pr.rc || o.rc) return MPB_ECUDA;
+    LAUNCH(ctx, k_pair_cover, (unsigned)((n_pairs * 32 + 255) / 256), 256, 0, uf.dev<uint32_t>(), ur.dev<uint32_t>(),
+           pf.dev<int32_t>(), pr.dev<int32_t>(), (long long)n_pairs, (int)words, o.dev<int32_t>());
+    CK(o.finish());
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}

@@ -269,6 +269,35 @@ def make_cover():
         json.dump(blob, fh)
 
 
+def make_pairs():
+    """get_multiPrime.py (V8) on the reference core's own output for a 80 x 420 synthetic alignment"""
+    import subprocess
+    n, L, seed, gr, ir = 80, 420, 17, 0.003, 0.001
+    blob = {"synth": [n, L, seed, gr, ir]}
+    with tempfile.TemporaryDirectory() as tmp:
+        fa = os.path.join(tmp, "in.fa")
+        synth.write_fasta(fa, synth.synth_codes(n, L, seed=seed, gap_rate=gr, iupac_rate=ir))
+        core_out = os.path.join(tmp, "c.out")
+        subprocess.run([sys.executable, os.path.join(REF, "scripts", "multiPrime-core.py"), "-i", fa, "-o", core_out,
+                        "-l", "18", "-n", "4", "-d", "10", "-v", "1", "-p", "1"], check=True, capture_output=True)
+        blob["core_tsv"] = open(core_out).read()
+        blob["core_non_cov"] = json.load(open(core_out + ".non_coverage_seq_id_json"))
+        blob["core_gap"] = json.load(open(core_out + ".gap_seq_id_json"))
+        for tag, extra in (("a", ["-s", "100,300", "-f", "0.3", "-t", "6", "-e", "2"]),
+                           ("b", ["-s", "150,260", "-f", "0.97", "-t", "3", "-a", ","])):
+            out = os.path.join(tmp, "Cluster_%s.candidate.primers.txt" % tag)
+            res = subprocess.run([sys.executable, os.path.join(REF, "scripts", "get_multiPrime.py"), "-i", core_out, "-r", fa,
+                                  "-o", out] + extra, capture_output=True, text=True)
+            stem = out.strip(".txt")
+            blob[tag] = {"args": extra, "rc": res.returncode, "stdout": res.stdout.replace(tmp, "<TMP>"),
+                         "txt": open(out).read().replace(tmp, "<TMP>"),
+                         "xls": open(stem + ".xls").read() if os.path.exists(stem + ".xls") else None,
+                         "fa": open(stem + ".fa").read() if os.path.exists(stem + ".fa") else None}
+            print("pairs", tag, "rc", res.returncode, "rows", (blob[tag]["xls"] or "").count("\n") - 1, res.stderr[-200:])
+    with open(os.path.join(HERE, "pairs_get_multiprime.json"), "w") as fh:
+        json.dump(blob, fh)
+
+
 def make_cli():
     """the reference CLI end to end on a small synthetic alignment: TSV text + the two JSON side files"""
     import subprocess
@@ -300,6 +329,8 @@ def main():
             make_cli()
         elif name == "cover":
             make_cover()
+        elif name == "pairs":
+            make_pairs()
         elif name in CASES:
             run_case(core, name)
 

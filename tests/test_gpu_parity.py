@@ -166,3 +166,35 @@ def test_primer_props_vs_oracle():
             assert bool(flags[i] & 2) == o.has_repeat(p), p
             assert bool(flags[i] & 4) == o.has_hairpin(p, 4), p
     ctx.close()
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_get_multiprime_golden(tmp_path, tag):
+    """get_multiPrime drop-in on the reference core's own output: the three output files byte-identical (second case
+    takes the `fewer than 10 pairs -> repeat with a looser threshold` branch), stdout lines equal"""
+    import json
+    import os
+    import subprocess
+    import sys
+    from multiprime_b200 import synth
+    from tests.helpers import GOLDEN
+    g = json.load(open(os.path.join(GOLDEN, "pairs_get_multiprime.json")))
+    n, L, seed, gr, ir = g["synth"]
+    fa = tmp_path / "in.fa"
+    synth.write_fasta(str(fa), synth.synth_codes(n, L, seed=seed, gap_rate=gr, iupac_rate=ir))
+    core_out = tmp_path / "c.out"
+    core_out.write_text(g["core_tsv"])
+    json.dump(g["core_non_cov"], open(str(core_out) + ".non_coverage_seq_id_json", "w"))
+    json.dump(g["core_gap"], open(str(core_out) + ".gap_seq_id_json", "w"))
+    out = tmp_path / ("Cluster_%s.candidate.primers.txt" % tag)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    want = g[tag]
+    res = subprocess.run([sys.executable, os.path.join(root, "scripts", "get_multiPrime.py"), "-i", str(core_out), "-r",
+                          str(fa), "-o", str(out)] + want["args"], capture_output=True, text=True)
+    assert res.returncode == want["rc"], res.stderr[-2000:]
+    stem = str(out).strip(".txt")
+    assert out.read_text().replace(str(tmp_path), "<TMP>") == want["txt"]
+    assert open(stem + ".xls").read() == want["xls"]
+    assert open(stem + ".fa").read() == want["fa"]
+    strip = lambda text: [ln for ln in text.replace(str(tmp_path), "<TMP>").splitlines() if not ln.startswith("INFO")]
+    assert strip(res.stdout) == strip(want["stdout"])
