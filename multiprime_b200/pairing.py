@@ -246,9 +246,10 @@ class Primers_filter(object):
         uncovered = self.ctx.pair_cover(uf, ur, [p[0] for p in pairs], [p[1] for p in pairs]) if pairs else []
         out = []
 
-        def one_pass(threshold):
+        def one_pass(threshold, echo):
             for s in range(n):
-                print(s)
+                if echo:                       # get_multiPrime.py:620 prints the index in the first pass only
+                    print(s)
                 for t, q in per_start[s]:
                     if q == "break":
                         print("Error! PCR product greater than max length !")
@@ -269,10 +270,10 @@ class Primers_filter(object):
                     out.append(line)
 
         coverage_threshold = 1 - self.fraction
-        one_pass(coverage_threshold)
+        one_pass(coverage_threshold, True)
         if len(out) < 10:
             coverage_threshold += 0.1
-            one_pass(coverage_threshold)
+            one_pass(coverage_threshold, False)
         ID = str(self.outfile)
         primer_ID = str(self.outfile).split("/")[-1].rstrip(".txt")
         with open(self.outfile, "w") as fo, open(self.outfile.strip(".txt") + ".xls", "w") as fo_xls, \
