@@ -223,6 +223,7 @@ class NN_degenerate(object):
             self.n_col = codes.shape[1]
             self._codes = codes
             packed4 = pack4(codes)
+        self._row_cache = {}
         self._packed4 = packed4                 # host copy: only read for the rare IUPAC-in-gap-row side-file entries
         self.comm = comm or NoComm()            # sequence shards: this process holds rows [row0, row0 + n_local)
         self.row0 = row0
@@ -325,14 +326,18 @@ class NN_degenerate(object):
     def _window_cells(self, s: int, p: int) -> bytes:
         """core:666-687 for one (sequence, window) on the host copy; only used for IUPAC-holding gap rows"""
         k = self.primer_length
-        if self._codes is not None:
-            row = self._codes[s, :self.lens[s]].tobytes()
-        else:
-            pk = self._packed4[s]
-            cells = np.empty(pk.shape[0] * 2, np.uint8)
-            cells[0::2] = pk & 15
-            cells[1::2] = pk >> 4
-            row = cells[:self.lens[s]].tobytes()
+        row = self._row_cache.get(s)
+        if row is None:
+            if self._codes is not None:
+                row = self._codes[s, :self.lens[s]].tobytes()
+            else:
+                pk = self._packed4[s]
+                cells = np.empty(pk.shape[0] * 2, np.uint8)
+                cells[0::2] = pk & 15
+                cells[1::2] = pk >> 4
+                row = cells[:self.lens[s]].tobytes()
+            if len(self._row_cache) < 200000:
+                self._row_cache[s] = row
         gap = b"\x00"
         w = row[p:p + k]
         if w != gap * k:
@@ -397,11 +402,9 @@ class NN_degenerate(object):
                 alive &= st["merged"]              # shard entropy bound already above the gate
             accepted = []                          # (batch index, position, cBit, tBit, cover_number, has gap-free)
             sel = np.zeros(len(positions), np.uint8)
-            for wi in np.nonzero(alive)[0].tolist():
-                ent = self._entropy(hist, st, wi, positions[wi], int(gap_n[wi]), int(st["nuniq"][wi, 0] + st["nuniq"][wi, 1]))
-                if ent is not None:
-                    accepted.append((wi, positions[wi], ent[0], ent[1], N - int(gap_n[wi]), bool(st["nuniq"][wi, 2] > 0)))
-                    sel[wi] = 1
+            for wi, ent in self._entropies(hist, st, positions, alive):
+                accepted.append((wi, positions[wi], ent[0], ent[1], N - int(gap_n[wi]), bool(st["nuniq"][wi, 2] > 0)))
+                sel[wi] = 1
             lap("gates")
             if not accepted:
                 return []
@@ -466,37 +469,35 @@ class NN_degenerate(object):
         st2["merged"] = merged
         return st2
 
-    def _entropy(self, hist, st, wi, pos, gap_n, n_unique):
-        """(cBit, tBit) rounded as the reference rounds them, or None when tBit exceeds the threshold"""
+    def _entropies(self, hist, st, positions, alive):
+        """(window index, (cBit, tBit)) of the windows that pass the entropy gate (core:722-726), rounded as the
+        reference rounds them.  The device sums use another summation order than the reference: whenever that could
+        change a rounded digit or the gate, the table is dumped and the reference's float sum replayed."""
         N = self.total_sequence_number
-        s0c, s1c, s0g, s1g = (float(x) for x in st["ent"][wi])
-        cover_number = N - gap_n
-        exact = False
-        if st["n_iupac_gap"][wi] > 0:
-            for _, c in self._iupac_gap_groups(hist, wi, pos):
-                s0g += c
-                s1g += c * math.log2(c)
-        if not exact:
-            tot = float(N)
-            c_raw = -(s1c - s0c * math.log2(cover_number)) / cover_number
-            t_raw = -((s1c - s0c * math.log2(tot)) + (s1g - s0g * math.log2(tot))) / tot
-            # device sums use another summation order than the reference; fall back to the exact replay whenever
-            # that could change a rounded digit or the gate
-            # (an exact zero prints as "-0.0" in the reference: round(-0.0, 2); leave that to the replay too)
-            if _near_half(c_raw) or _near_half(t_raw) or abs(t_raw - self.entropy_threshold) < 1e-6 \
-                    or abs(c_raw) < 1e-9 or abs(t_raw) < 1e-9:
-                exact = True
-            elif t_raw > self.entropy_threshold + 0.006:
-                return None
-        if exact:
-            c_bit, t_bit = self._entropy_exact(hist, wi, pos, n_unique)
-        else:
-            c_bit, t_bit = round(c_raw, 2), round(t_raw, 2)
-        if t_bit > self.entropy_threshold:                                # core:723
-            return None
-        return c_bit, t_bit
+        thr = self.entropy_threshold
+        ent = st["ent"].astype(np.float64).copy()
+        for wi in np.nonzero(alive & (st["n_iupac_gap"] > 0))[0].tolist():     # gap rows holding IUPAC cells
+            for _, c in self._iupac_gap_groups(hist, wi, positions[wi]):
+                ent[wi, 2] += c
+                ent[wi, 3] += c * math.log2(c)
+        cover_number = (N - st["gap_n"]).astype(np.float64)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            c_raw = -(ent[:, 1] - ent[:, 0] * np.log2(cover_number)) / cover_number
+            t_raw = -((ent[:, 1] - ent[:, 0] * math.log2(N)) + (ent[:, 3] - ent[:, 2] * math.log2(N))) / N
+        tie = lambda x: np.abs((x * 100.0) % 1.0 - 0.5) < 1e-6
+        exact = tie(c_raw) | tie(t_raw) | (np.abs(t_raw - thr) < 1e-6) | (np.abs(c_raw) < 1e-9) | (np.abs(t_raw) < 1e-9)
+        # (an exact zero prints as "-0.0" in the reference: round(-0.0, 2); that is left to the replay too)
+        out = []
+        for wi in np.nonzero(alive & (exact | ~(t_raw > thr + 0.006)))[0].tolist():
+            if exact[wi]:
+                c_bit, t_bit = self._entropy_exact(hist, wi, positions[wi],
+                                                   int(st["nuniq"][wi, 0] + st["nuniq"][wi, 1]))
+            else:
+                c_bit, t_bit = round(float(c_raw[wi]), 2), round(float(t_raw[wi]), 2)
+            if not t_bit > thr:                                               # core:723
+                out.append((wi, (c_bit, t_bit)))
+        return out
 
-    # -- refinement walk in lock step with the scan (core:860-1089) ------------------------------------------
     # -- rows, filters, side files ----------------------------------------------------------------------------
     def _finish(self, hist, keep, res):
         """core:846-858 row assembly for the windows that went through the walk"""

@@ -687,13 +687,14 @@ k_hist_stats(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ cnt
             Best b = {(unsigned long long)C[i], F[i], key};
             if (better(b, best)) best = b;
         }
+        const double clog = C[i] == 1u ? 0.0 : c * log2(c);  // singletons (most of a variable window) cost no log
         if (is_cover) {
             s0c += c;
-            s1c += c * log2(c);
+            s1c += clog;
             ++nc;
         } else {
             s0g += c;
-            s1g += c * log2(c);
+            s1g += clog;
             ++ng;
         }
     }
