@@ -36,6 +36,7 @@ SIGNATURES = {
     "mpb_msa_set_row0": (C.c_int, [_P, C.c_int64]),
     "mpb_hist_export": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "mpb_seq_attr": (C.c_int, [_P, _P, _P]),
+    "mpb_window_prefilter": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int32, _P, _P]),
     "mpb_hist_build": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int32, C.c_int, C.POINTER(_P)]),
     "mpb_hist_free": (None, [_P]),
     "mpb_hist_merge": (C.c_int, [_P, _P, _P, _P, _P]),
@@ -255,6 +256,14 @@ class Msa:
         rstrip = np.empty(self.n_seq, np.int32)
         check(load().mpb_seq_attr(self.h, ptr(lead), ptr(rstrip)))
         return lead, rstrip
+
+    def prefilter(self, k: int, v: int, win_pos):
+        """(s0, s1) per window: see mpb_window_prefilter"""
+        win_pos = np.ascontiguousarray(win_pos, dtype=np.int32)
+        s0 = np.zeros(len(win_pos), np.float64)
+        s1 = np.zeros(len(win_pos), np.float64)
+        check(load().mpb_window_prefilter(self.h, k, v, ptr(win_pos), len(win_pos), ptr(s0), ptr(s1)))
+        return s0, s1
 
     def hist(self, k: int, v: int, win_pos, log2_cap: int = 0) -> "Hist":
         return Hist(self, k, v, win_pos, log2_cap)

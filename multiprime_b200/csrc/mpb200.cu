@@ -478,6 +478,161 @@ k_hist(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq, const int32_
     }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// entropy prefilter: a lower bound of a window's total entropy from a coarse view of its k-mers
+// ------------------------------------------------------------------------------------------------------
+// Every item the reference counts for tBit (each expansion of a cover row, each gap row; core:602-614) is mapped to a
+// 16-bit code: the 2-bit bases of its first 8 cells (a gap cell, or the lowest base of an IUPAC cell of a gap row,
+// counts as that base).  Merging categories can only lower sum(-p log p) (f(a+b) <= f(a)+f(b) for f = -x log x), so
+// the entropy of the 65536 bins is a lower bound of tBit: windows whose bound is above the gate never need a table.
+#define PRE_BINS 65536
+__device__ __forceinline__ uint32_t pre_code(uint32_t c, uint32_t g, uint32_t t) {
+    return ((c | t) & 0xFFu) | (((g | t) & 0xFFu) << 8);
+}
+
+__device__ __forceinline__ void pre_stage(unsigned long long* s_key, unsigned int* s_cnt, unsigned int* bins,
+                                          uint32_t code, uint32_t add) {
+    uint32_t h = (code * 0x9E3779B1u) >> 23;  // 9 bits
+    for (int probe = 0; probe < HIST_PROBES; ++probe) {
+        unsigned long long cur = s_key[h];
+        if (cur == MPB_KEY_EMPTY_D) {
+            cur = atomicCAS(&s_key[h], (unsigned long long)MPB_KEY_EMPTY_D, (unsigned long long)code);
+            if (cur == MPB_KEY_EMPTY_D) cur = code;
+        }
+        if (cur == code) {
+            atomicAdd(&s_cnt[h], add);
+            return;
+        }
+        h = (h + 1) & (HIST_SLOTS - 1);
+    }
+    atomicAdd(&bins[code], add);
+}
+
+__global__ void __launch_bounds__(HIST_THREADS)
+k_prefilter(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq, const int32_t* __restrict__ lens, int k, int v,
+            const int32_t* __restrict__ win_pos, int nw, unsigned int* __restrict__ bins, int* __restrict__ err) {
+    __shared__ unsigned long long s_key[HIST_SLOTS];
+    __shared__ unsigned int s_cnt[HIST_SLOTS];
+    const uint32_t kmask = (1u << k) - 1u;
+    for (int i = threadIdx.x; i < HIST_SLOTS; i += HIST_THREADS) {
+        s_key[i] = MPB_KEY_EMPTY_D;
+        s_cnt[i] = 0;
+    }
+    __syncthreads();
+    for (int wi = blockIdx.y; wi < nw; wi += gridDim.y) {
+        const int p = win_pos[wi];
+        unsigned int* B = bins + (long long)wi * PRE_BINS;
+        for (int t = 0; t < HIST_TILES; ++t) {
+            const int64_t tile = (int64_t)blockIdx.x * HIST_TILES + t;
+            if (tile * HIST_THREADS >= n_seq) break;  // uniform
+            const int64_t s = tile * HIST_THREADS + threadIdx.x;
+            const bool valid = s < n_seq;
+            Win w;
+            w.a = w.c = w.g = w.t = w.multi = 0;
+            w.gapv = kmask;
+            if (valid && !mpb_load_window(pl, nsp, s, lens[s], p, k, kmask, w)) atomicOr(err, MPB_ERR_SHORT_ROW);
+            const bool isgap = valid && __popc(w.gapv) > v;
+            const bool simple = valid && (w.multi == 0 || isgap);
+            const unsigned smask = __ballot_sync(0xffffffffu, simple);
+            if (simple) {
+                uint32_t c = w.c, g = w.g, tt = w.t;
+                if (w.multi) {  // gap row holding IUPAC cells: lowest base of every cell
+                    const uint32_t a = w.a;
+                    c &= ~a;
+                    g &= ~(a | c);
+                    tt &= ~(a | c | g);
+                }
+                const uint32_t code = pre_code(c, g, tt);
+                const unsigned peers = __match_any_sync(smask, code);
+                if ((threadIdx.x & 31) == __ffs(peers) - 1) pre_stage(s_key, s_cnt, B, code, (uint32_t)__popc(peers));
+            } else if (valid) {
+                const uint32_t total = mpb_expansions(w);
+                if (total > MPB_MAX_EXP) {
+                    atomicOr(err, MPB_ERR_EXPAND);
+                } else {
+                    for (uint32_t e = 0; e < total; ++e) {
+                        uint32_t a, c, g, tt;
+                        mpb_expand(w, e, a, c, g, tt);
+                        pre_stage(s_key, s_cnt, B, pre_code(c, g, tt), 1u);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < HIST_SLOTS; i += HIST_THREADS) {
+            const unsigned long long key = s_key[i];
+            if (key != MPB_KEY_EMPTY_D) {
+                atomicAdd(&B[(uint32_t)key], s_cnt[i]);
+                s_key[i] = MPB_KEY_EMPTY_D;
+                s_cnt[i] = 0;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// per window: sum(c) and sum(c log2 c) over the bins
+__global__ void __launch_bounds__(256)
+k_prefilter_sums(const unsigned int* __restrict__ bins, double* __restrict__ s0, double* __restrict__ s1) {
+    const unsigned int* B = bins + (long long)blockIdx.x * PRE_BINS;
+    double a0 = 0, a1 = 0;
+    for (int i = threadIdx.x; i < PRE_BINS; i += 256) {
+        const unsigned int c = B[i];
+        if (c) {
+            a0 += (double)c;
+            if (c > 1) a1 += (double)c * log2((double)c);
+        }
+    }
+    __shared__ double sh0[8], sh1[8];
+    for (int o = 16; o > 0; o >>= 1) {
+        a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        sh0[threadIdx.x >> 5] = a0;
+        sh1[threadIdx.x >> 5] = a1;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) {
+            a0 += sh0[w];
+            a1 += sh1[w];
+        }
+        s0[blockIdx.x] = a0;
+        s1[blockIdx.x] = a1;
+    }
+}
+
+extern "C" int mpb_window_prefilter(mpb_msa* m, int k, int v, const int32_t* win_pos, int32_t nw, double* s0_hd,
+                                    double* s1_hd) {
+    if (!m || !win_pos || !s0_hd || !s1_hd) return fail(MPB_EINVAL, "NULL argument");
+    if (k < 8 || k > MPB_MAX_K || v < 0 || nw < 1) return fail(MPB_EINVAL, "prefilter needs 8 <= k <= %d", MPB_MAX_K);
+    for (int i = 0; i < nw; ++i)
+        if (win_pos[i] < 0 || win_pos[i] >= m->n_col)
+            return fail(MPB_EINVAL, "win_pos[%d]=%d outside the alignment", i, win_pos[i]);
+    mpb_ctx* ctx = m->ctx;
+    CK(cudaSetDevice(ctx->device));
+    unsigned int* bins = nullptr;
+    CK(cudaMallocAsync(&bins, (size_t)nw * PRE_BINS * 4, ctx->stream));
+    CK(cudaMemsetAsync(bins, 0, (size_t)nw * PRE_BINS * 4, ctx->stream));
+    InBuf wp(ctx, win_pos, (size_t)nw * 4);
+    OutBuf o0(ctx, s0_hd, (size_t)nw * 8), o1(ctx, s1_hd, (size_t)nw * 8);
+    if (wp.rc || o0.rc || o1.rc) return MPB_ECUDA;
+    const unsigned gx = (unsigned)((m->n_seq + (long long)HIST_THREADS * HIST_TILES - 1) / ((long long)HIST_THREADS * HIST_TILES));
+    unsigned gy = (unsigned)nw;
+    const unsigned want = (unsigned)ctx->sm_count * 8;
+    if (gx >= want) gy = 1;
+    else if (gy > (want + gx - 1) / gx) gy = (want + gx - 1) / gx;
+    ctx->pending_units = (double)nw * (double)m->n_seq;
+    LAUNCH(ctx, k_prefilter, dim3(gx, gy), HIST_THREADS, 0, m->planes, m->nsp, m->n_seq, m->lens, k, v, wp.dev<int32_t>(),
+           nw, bins, m->err);
+    LAUNCH(ctx, k_prefilter_sums, (unsigned)nw, 256, 0, bins, o0.dev<double>(), o1.dev<double>());
+    CK(o0.finish());
+    CK(o1.finish());
+    CK(cudaFreeAsync(bins, ctx->stream));
+    return check_flags(ctx, m->err);
+}
+
 extern "C" int mpb_hist_build(mpb_msa* m, int k, int v, const int32_t* win_pos, int32_t nw, int log2_cap,
                               mpb_hist** out) {
     if (!m || !win_pos || !out) return fail(MPB_EINVAL, "NULL argument");

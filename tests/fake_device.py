@@ -92,6 +92,22 @@ class Msa:
         rstrip = np.array([len(s.rstrip("-")) for s in self.rows], np.int32)
         return lead, rstrip
 
+    def prefilter(self, k, v, win_pos):
+        """coarse 16-bit view of every counted item (mpb_window_prefilter)"""
+        s0, s1 = np.zeros(len(win_pos)), np.zeros(len(win_pos))
+        low = {c: ("A" if i & 1 else "C" if i & 2 else "G" if i & 4 else "T") for i, c in enumerate(CODE_CHARS) if i}
+        low["-"] = "A"
+        for wi, p in enumerate(win_pos):
+            bins = {}
+            for s in self.rows:
+                w = o.window_kmer(s, int(p), k)
+                items = ["".join(low[ch] for ch in w)] if w.count("-") > v else [e.replace("-", "A") for e in o.expand(w)]
+                for it in items:
+                    bins[it[:8]] = bins.get(it[:8], 0) + 1
+            cs = np.array(list(bins.values()), float)
+            s0[wi], s1[wi] = cs.sum(), (cs * np.log2(cs)).sum()
+        return s0, s1
+
     def hist(self, k, v, win_pos, log2_cap=0):
         return Hist(self, k, v, win_pos)
 

@@ -198,3 +198,31 @@ def test_get_multiprime_golden(tmp_path, tag):
     assert open(stem + ".fa").read() == want["fa"]
     strip = lambda text: [ln for ln in text.replace(str(tmp_path), "<TMP>").splitlines() if not ln.startswith("INFO")]
     assert strip(res.stdout) == strip(want["stdout"])
+
+
+def test_prefilter_matches_definition():
+    """mpb_window_prefilter: item counts and sum(c log2 c) of the coarse bins equal the plain-Python definition, and
+    the bound never exceeds the reference's total entropy"""
+    from multiprime_b200 import _lib, core
+    from tests import fake_device
+    from tests.helpers import case_alignment, load_case
+    from tests.parity import alignment_arrays
+    case = load_case("synth_iupac")
+    ids, seqs = case_alignment(case, "synth_iupac")
+    _, codes, lens = alignment_arrays(ids, seqs)
+    k, v = case["params"]["primer_length"], case["params"]["variation"]
+    pos = [r["pos"] for r in case["records"]]
+    ctx = _lib.Context(0)
+    msa = _lib.Msa(ctx, core.pack4(codes), len(ids), codes.shape[1])
+    s0, s1 = msa.prefilter(k, v, pos)
+    fmsa = fake_device.Msa(None, core.pack4(codes), len(ids), codes.shape[1])
+    f0, f1 = fmsa.prefilter(k, v, pos)
+    assert (s0 == f0).all()
+    assert np.allclose(s1, f1, rtol=1e-12, atol=1e-9)
+    n = len(ids)
+    bound = (s0 * np.log2(n) - s1) / n
+    for rec, b in zip(case["records"], bound):
+        if rec["row"] is not None:
+            assert b <= rec["row"][2] + 0.006          # row[2] = Entropy of total (bit), rounded to 2 decimals
+    msa.close()
+    ctx.close()
