@@ -85,6 +85,10 @@ int mpb_seq_attr(mpb_msa* msa, int32_t* lead_gaps_hd, int32_t* rstrip_len_hd);
  * cannot raise sum(-p log p); a window whose bound exceeds the gate can be dropped without building its table. */
 int mpb_window_prefilter(mpb_msa* msa, int k, int v, const int32_t* win_pos, int32_t nw, double* s0_hd, double* s1_hd);
 
+/* The same two attributes as histograms over the values 0..n_col (hd arrays of n_col+1 int64): an order statistic
+ * needs no sort, and sequence shards add their histograms. */
+int mpb_seq_attr_hist(mpb_msa* msa, int64_t* lead_hist_hd, int64_t* rstrip_hist_hd);
+
 /* ---- window haplotype tables: core:651-711 (sequence loop of get_primers) ---------------------------------
  * For every window start win_pos[i] (host array) extract each sequence's k-mer with the reference's
  * terminal-gap patching, expand IUPAC cells, and count haplotypes into an open-addressing table per window

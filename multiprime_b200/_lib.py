@@ -36,6 +36,7 @@ SIGNATURES = {
     "mpb_msa_set_row0": (C.c_int, [_P, C.c_int64]),
     "mpb_hist_export": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "mpb_seq_attr": (C.c_int, [_P, _P, _P]),
+    "mpb_seq_attr_hist": (C.c_int, [_P, _P, _P]),
     "mpb_window_prefilter": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int32, _P, _P]),
     "mpb_hist_build": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int32, C.c_int, C.POINTER(_P)]),
     "mpb_hist_free": (None, [_P]),
@@ -264,6 +265,13 @@ class Msa:
         s1 = np.zeros(len(win_pos), np.float64)
         check(load().mpb_window_prefilter(self.h, k, v, ptr(win_pos), len(win_pos), ptr(s0), ptr(s1)))
         return s0, s1
+
+    def seq_attr_hist(self):
+        """histograms (value -> number of sequences) of the leading-gap count and of the length without trailing gaps"""
+        lead = np.zeros(self.n_col + 1, np.int64)
+        rstrip = np.zeros(self.n_col + 1, np.int64)
+        check(load().mpb_seq_attr_hist(self.h, ptr(lead), ptr(rstrip)))
+        return lead, rstrip
 
     def hist(self, k: int, v: int, win_pos, log2_cap: int = 0) -> "Hist":
         return Hist(self, k, v, win_pos, log2_cap)

@@ -214,6 +214,13 @@ class NN_degenerate(object):
         self.windows_per_batch = windows_per_batch
         if not 3 <= primer_length <= _lib.MAX_K:
             raise ValueError("primer length must be within 3..%d" % _lib.MAX_K)
+        t_init = [time.perf_counter()]
+        self.init_ms = {}
+
+        def lap(name):
+            now = time.perf_counter()
+            self.init_ms[name] = 1000 * (now - t_init[0])
+            t_init[0] = now
         self.fmask, self.rmask = strict_masks(position, primer_length)
         if packed is not None:                   # (ids, nibble-packed rows, n_col, lens): already in upload format
             self.ids, packed4, self.n_col, lens = packed
@@ -236,19 +243,24 @@ class NN_degenerate(object):
                                lens=None if (self.lens == self.n_col).all() else self.lens)
         if row0:
             self.msa.set_row0(row0)
+        lap("upload")
         self.position_list = self.seq_attribute()
+        lap("region")
         self.start_position, self.stop_position, self.length = self.position_list
         self.entropy_threshold = self.entropy_threshold_adjust(self.length)
         self.stats = {"windows": 0, "accepted": 0, "scan_calls": 0, "evals": 0, "candidates": 0}
 
     # -- core:617-649 -------------------------------------------------------------------------------------
     def seq_attribute(self):
-        lead, rstrip = self.msa.seq_attr()
-        if self.comm.world > 1:                 # the quantiles are over all sequences
-            lead, _ = self.comm.allgather_concat(lead)
-            rstrip, _ = self.comm.allgather_concat(rstrip)
-        start = int(np.quantile(lead.reshape(1, -1), self.coverage, method="higher"))
-        stop = int(np.quantile(rstrip.reshape(1, -1), self.coverage, method="lower"))
+        lead_hist, rstrip_hist = self.msa.seq_attr_hist()
+        if self.comm.world > 1:                 # the quantiles are over all sequences: shards add their histograms
+            lead_hist = self.comm.allreduce_sum(lead_hist)
+            rstrip_hist = self.comm.allreduce_sum(rstrip_hist)
+        # np.quantile(x, q, "higher" / "lower") = sorted(x)[ceil / floor((n - 1) * q)]: an order statistic, read off the
+        # cumulative histogram
+        vidx = (self.total_sequence_number - 1) * self.coverage
+        start = int(np.searchsorted(np.cumsum(lead_hist), math.ceil(vidx), side="right"))
+        stop = int(np.searchsorted(np.cumsum(rstrip_hist), math.floor(vidx), side="right"))
         if stop - start < int(self.product):
             print("Error: max length of PCR product is shorter than the default min Product length with {} "
                   "coverage! Non candidate primers !!!".format(self.coverage))

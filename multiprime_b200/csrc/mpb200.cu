@@ -255,6 +255,11 @@ __global__ void k_pack_planes(const uint8_t* __restrict__ packed, int64_t n_seq,
     w[3 * nsp] = t;
 }
 
+__global__ void k_fill_i32(int32_t* __restrict__ dst, int64_t n, int64_t n_set, int32_t value) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = i < n_set ? value : 0;
+}
+
 extern "C" int mpb_msa_upload(mpb_ctx* ctx, const uint8_t* packed4, int64_t n_seq, int64_t n_col, int64_t row_bytes,
                               const int32_t* lens, mpb_msa** out) {
     if (!ctx || !packed4 || !out) return fail(MPB_EINVAL, "NULL argument");
@@ -282,16 +287,20 @@ extern "C" int mpb_msa_upload(mpb_ctx* ctx, const uint8_t* packed4, int64_t n_se
         return fail(MPB_ENOMEM, "alignment planes (%zu bytes): %s", pbytes, cudaGetErrorString(e));
     }
     CK(cudaMemsetAsync(m->err, 0, sizeof(int), ctx->stream));
-    std::vector<int32_t> hl(m->nsp, 0);
-    for (int64_t i = 0; i < n_seq; ++i) {
-        int32_t l = lens ? lens[i] : (int32_t)n_col;
-        if (l < 0 || l > n_col) {
-            mpb_msa_free(m);
-            return fail(MPB_EINVAL, "lens[%lld]=%d outside 0..n_col", (long long)i, l);
+    std::vector<int32_t> hl;
+    if (lens) {
+        hl.assign(m->nsp, 0);
+        for (int64_t i = 0; i < n_seq; ++i) {
+            if (lens[i] < 0 || lens[i] > n_col) {
+                mpb_msa_free(m);
+                return fail(MPB_EINVAL, "lens[%lld]=%d outside 0..n_col", (long long)i, lens[i]);
+            }
+            hl[i] = lens[i];
         }
-        hl[i] = l;
+        CK(cudaMemcpyAsync(m->lens, hl.data(), m->nsp * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        LAUNCH(ctx, k_fill_i32, (unsigned)((m->nsp + 255) / 256), 256, 0, m->lens, m->nsp, n_seq, (int32_t)n_col);
     }
-    CK(cudaMemcpyAsync(m->lens, hl.data(), m->nsp * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     {
         InBuf in(ctx, packed4, (size_t)n_seq * row_bytes);
         if (in.rc) {
@@ -338,6 +347,48 @@ __global__ void k_seq_attr(const uint32_t* __restrict__ pl, int64_t nsp, int64_t
     }
     lead[s] = first < 0 ? len : first;
     rstrip[s] = last + 1;
+}
+
+// histograms of the two per-sequence attributes (values 0..n_col): the host takes the quantiles of core:629-633 from
+// the cumulative counts (an order statistic needs no sort), and sequence shards simply add their histograms
+__global__ void k_seq_attr_hist(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq,
+                                const int32_t* __restrict__ lens, int ncw, unsigned long long* __restrict__ lead_hist,
+                                unsigned long long* __restrict__ rstrip_hist) {
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_seq) return;
+    int len = lens[s];
+    int first = -1, last = -1;
+    for (int cw = 0; cw < ncw - 1; ++cw) {
+        const uint32_t* w = pl + ((int64_t)cw * 4) * nsp + s;
+        uint32_t any = w[0] | w[nsp] | w[2 * nsp] | w[3 * nsp];
+        if (any) {
+            if (first < 0) first = cw * 32 + __ffs(any) - 1;
+            last = cw * 32 + 31 - __clz(any);
+        }
+    }
+    const int lead = first < 0 ? len : first, rs = last + 1;
+    // warp-aggregate equal values before the atomics (most sequences share the value)
+    unsigned peers = __match_any_sync(__activemask(), lead);
+    if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&lead_hist[lead], (unsigned long long)__popc(peers));
+    peers = __match_any_sync(__activemask(), rs);
+    if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&rstrip_hist[rs], (unsigned long long)__popc(peers));
+}
+
+extern "C" int mpb_seq_attr_hist(mpb_msa* m, int64_t* lead_hist_hd, int64_t* rstrip_hist_hd) {
+    if (!m || !lead_hist_hd || !rstrip_hist_hd) return fail(MPB_EINVAL, "NULL argument");
+    mpb_ctx* ctx = m->ctx;
+    CK(cudaSetDevice(ctx->device));
+    const size_t bytes = (size_t)(m->n_col + 1) * 8;
+    OutBuf a(ctx, lead_hist_hd, bytes), b(ctx, rstrip_hist_hd, bytes);
+    if (a.rc || b.rc) return MPB_ENOMEM;
+    CK(cudaMemsetAsync(a.d, 0, bytes, ctx->stream));
+    CK(cudaMemsetAsync(b.d, 0, bytes, ctx->stream));
+    LAUNCH(ctx, k_seq_attr_hist, (unsigned)((m->n_seq + 255) / 256), 256, 0, m->planes, m->nsp, m->n_seq, m->lens, m->ncw,
+           a.dev<unsigned long long>(), b.dev<unsigned long long>());
+    CK(a.finish());
+    CK(b.finish());
+    if (a.is_host() || b.is_host()) CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
 }
 
 extern "C" int mpb_seq_attr(mpb_msa* m, int32_t* lead_hd, int32_t* rstrip_hd) {

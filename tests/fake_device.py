@@ -108,6 +108,11 @@ class Msa:
             s0[wi], s1[wi] = cs.sum(), (cs * np.log2(cs)).sum()
         return s0, s1
 
+    def seq_attr_hist(self):
+        lead, rstrip = self.seq_attr()
+        return (np.bincount(lead, minlength=self.n_col + 1).astype(np.int64),
+                np.bincount(rstrip, minlength=self.n_col + 1).astype(np.int64))
+
     def hist(self, k, v, win_pos, log2_cap=0):
         return Hist(self, k, v, win_pos)
 
