@@ -377,9 +377,24 @@ class Hist:
     def merge(self, win_off, keys, cnt, first):
         win_off = np.ascontiguousarray(win_off, dtype=np.int64)
         if win_off[-1] > 0:
-            check(load().mpb_hist_merge(self.h, ptr(win_off), ptr(np.ascontiguousarray(keys, dtype=np.uint64)),
-                                        ptr(np.ascontiguousarray(cnt, dtype=np.uint32)),
-                                        ptr(np.ascontiguousarray(first, dtype=np.uint64))))
+            if isinstance(keys, np.ndarray):
+                keys = np.ascontiguousarray(keys, dtype=np.uint64)
+                cnt = np.ascontiguousarray(cnt, dtype=np.uint32)
+                first = np.ascontiguousarray(first, dtype=np.uint64)
+            check(load().mpb_hist_merge(self.h, ptr(win_off), ptr(keys), ptr(cnt), ptr(first)))
+
+    def export_dev(self, sel, counts, comm):
+        """export() into device tensors allocated through the communicator -> (win_off, keys, cnt, first)"""
+        sel = np.ascontiguousarray(sel, dtype=np.uint8)
+        off = np.zeros(self.nw + 1, np.int64)
+        off[1:] = np.cumsum(np.where(sel != 0, counts, 0))
+        total = int(off[-1])
+        keys = comm.empty_dev(total, np.uint64)
+        cnt = comm.empty_dev(total, np.uint32)
+        first = comm.empty_dev(total, np.uint64)
+        if total:
+            check(load().mpb_hist_export(self.h, ptr(sel), ptr(off), ptr(keys), ptr(cnt), ptr(first)))
+        return off, keys, cnt, first
 
     def match(self, q_win, q_allow):
         q_win = np.ascontiguousarray(q_win, dtype=np.int32)

@@ -69,5 +69,26 @@ class TorchComm:
         self.dist.all_gather_object(out, obj, group=self.group)
         return out
 
+    @property
+    def on_gpu(self) -> bool:
+        return self.device.type == "cuda"
+
+    def empty_dev(self, n: int, dtype):
+        """uninitialised device tensor of a numpy dtype (haplotype entries stay on the GPU between export and merge)"""
+        tdt = {np.dtype(np.uint64): self.torch.int64, np.dtype(np.uint32): self.torch.int32,
+               np.dtype(np.int64): self.torch.int64}[np.dtype(dtype)]
+        return self.torch.empty(max(1, n), dtype=tdt, device=self.device)
+
+    def allgather_dev(self, t, n: int, max_n: int):
+        """all-gather of device tensors of different lengths (first n elements valid) -> list of per-rank tensors,
+        each padded to max_n"""
+        if t.shape[0] < max_n:
+            pad = self.torch.empty(max_n, dtype=t.dtype, device=t.device)
+            pad[:n] = t[:n]
+            t = pad
+        out = self.torch.empty(self.world * max_n, dtype=t.dtype, device=t.device)
+        self.dist.all_gather_into_tensor(out, t[:max_n].contiguous(), group=self.group)
+        return [out[r * max_n:(r + 1) * max_n] for r in range(self.world)]
+
     def barrier(self):
         self.dist.barrier(group=self.group)

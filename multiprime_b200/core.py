@@ -473,19 +473,35 @@ class NN_degenerate(object):
         gap_fail = np.array([round(int(g) / N, 2) >= (1 - self.coverage) for g in gap_n])
         merged = (~gap_fail) & (bound <= self.entropy_threshold + 0.006)
         counts = st["nuniq"][:, 0] + st["nuniq"][:, 1]
-        off, keys, cnt, first = hist.export(merged.astype(np.uint8), counts)
-        sizes_all, _ = comm.allgather_concat(np.diff(off))                     # world x nw entry counts
-        sizes_all = sizes_all.reshape(comm.world, hist.nw)
-        keys_all, lens_k = comm.allgather_concat(keys)
-        cnt_all, _ = comm.allgather_concat(cnt)
-        first_all, _ = comm.allgather_concat(first)
-        starts = np.concatenate([[0], np.cumsum(lens_k)])
-        for r in range(comm.world):
-            if r == comm.rank:
-                continue
-            off_r = np.concatenate([[0], np.cumsum(sizes_all[r])]).astype(np.int64)
-            a, b = int(starts[r]), int(starts[r + 1])
-            hist.merge(off_r, keys_all[a:b], cnt_all[a:b], first_all[a:b])
+        if getattr(comm, "on_gpu", False) and hasattr(hist, "export_dev"):
+            # entries stay in HBM: export -> NCCL all-gather -> mpb_hist_merge from device pointers
+            off, keys, cnt, first = hist.export_dev(merged.astype(np.uint8), counts, comm)
+            sizes_all, _ = comm.allgather_concat(np.diff(off))
+            sizes_all = sizes_all.reshape(comm.world, hist.nw)
+            totals = sizes_all.sum(axis=1)
+            n_mine, n_max = int(totals[comm.rank]), int(totals.max())
+            if n_max > 0:
+                gk = comm.allgather_dev(keys, n_mine, n_max)
+                gc = comm.allgather_dev(cnt, n_mine, n_max)
+                gf = comm.allgather_dev(first, n_mine, n_max)
+                for r in range(comm.world):
+                    if r != comm.rank and totals[r] > 0:
+                        off_r = np.concatenate([[0], np.cumsum(sizes_all[r])]).astype(np.int64)
+                        hist.merge(off_r, gk[r], gc[r], gf[r])
+        else:
+            off, keys, cnt, first = hist.export(merged.astype(np.uint8), counts)
+            sizes_all, _ = comm.allgather_concat(np.diff(off))                     # world x nw entry counts
+            sizes_all = sizes_all.reshape(comm.world, hist.nw)
+            keys_all, lens_k = comm.allgather_concat(keys)
+            cnt_all, _ = comm.allgather_concat(cnt)
+            first_all, _ = comm.allgather_concat(first)
+            starts = np.concatenate([[0], np.cumsum(lens_k)])
+            for r in range(comm.world):
+                if r == comm.rank:
+                    continue
+                off_r = np.concatenate([[0], np.cumsum(sizes_all[r])]).astype(np.int64)
+                a, b = int(starts[r]), int(starts[r + 1])
+                hist.merge(off_r, keys_all[a:b], cnt_all[a:b], first_all[a:b])
         st2 = hist.stats()                                                     # global for the merged windows
         st2["gap_n"] = gap_n
         st2["n_iupac_gap"] = iupac_gap

@@ -1,0 +1,81 @@
+"""GPU suite, sequence shards: two processes share cuda:0 (gloo for the collectives), each holding half of the rows of
+a golden case in the REAL library; both must produce the reference's rows.  (The NCCL path of the same code is what
+`bench.py --gpus N` runs.)"""
+import os
+import queue
+import socket
+import time
+
+import pytest
+import torch.multiprocessing as mp
+
+from tests.helpers import load_case
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, name, q):
+    import numpy as np
+    import torch.distributed as dist
+    from multiprime_b200 import core
+    from multiprime_b200.comm import TorchComm
+    from tests.helpers import case_alignment
+    from tests.parity import alignment_arrays
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    case = load_case(name)
+    ids, seqs = case_alignment(case, name)
+    n = len(ids)
+    lo, hi = rank * n // world, (rank + 1) * n // world
+    _, codes, lens = alignment_arrays(ids[lo:hi], seqs[lo:hi])
+    full_cols = max(len(s) for s in seqs)
+    if codes.shape[1] < full_cols:
+        codes = np.pad(codes, ((0, 0), (0, full_cols - codes.shape[1])))
+    app = core.NN_degenerate(seq_file=None, nproc=1, outfile="", alignment=(ids[lo:hi], codes, lens), row0=lo,
+                             comm=TorchComm(), device=0, **case["params"])
+    recs = case["records"]
+    got = {r["row"][0]: r for r in app.design([r["pos"] for r in recs])}
+    bad = []
+    for rec in recs:
+        g = got.get(rec["pos"])
+        if (g is None) != (rec["row"] is None) or (g is not None and (g["row"] != rec["row"] or g["trace"] != rec["trace"])):
+            bad.append((rec["pos"], g and g["row"], rec["row"]))
+    q.put((rank, app.start_position, app.stop_position, bad))
+    app.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name", ["synth300", "c2_k18"])
+def test_two_shards_one_gpu(name):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, name, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = []
+    t0 = time.time()
+    while len(res) < 2 and time.time() - t0 < 300:
+        try:
+            res.append(q.get(timeout=2))
+        except queue.Empty:
+            if any(p.exitcode not in (None, 0) for p in procs):
+                break
+    for p in procs:
+        p.join(10)
+        if p.is_alive():
+            p.kill()
+    assert len(res) == 2, "a rank died: exit codes %s" % [p.exitcode for p in procs]
+    case = load_case(name)
+    for rank, start, stop, bad in res:
+        assert (start, stop) == (case["start"], case["stop"])
+        assert not bad, (rank, bad[:3])
