@@ -69,6 +69,11 @@ class TorchComm:
         self.dist.all_gather_object(out, obj, group=self.group)
         return out
 
+    def allreduce_dev(self, t):
+        """in-place sum over ranks of a device tensor (NCCL), returned as a numpy array"""
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+        return t.cpu().numpy()
+
     @property
     def on_gpu(self) -> bool:
         return self.device.type == "cuda"

@@ -286,11 +286,21 @@ class NN_degenerate(object):
                 g = local.setdefault((w, self._window_cells(s, hist.win_pos[w])), [(self.row0 + s) << 16, 0])
                 g[1] += 1
             cache = {}
-            for part in self.comm.allgather_object(local):          # shards in rank order = sequence order
-                for key, (f, c) in part.items():
-                    g = cache.setdefault(key, [f, 0])
-                    g[0] = min(g[0], f)
-                    g[1] += c
+            if self.comm.world > 1:
+                # shards exchange their (window, raw k-mer, first, count) records as plain arrays
+                k = self.primer_length
+                rec = np.zeros((len(local), 4 + 32), np.int64)
+                for i, ((w, cells), (f, c)) in enumerate(local.items()):
+                    rec[i, 0], rec[i, 1], rec[i, 2] = w, f, c
+                    rec[i, 4:4 + k] = list(cells)
+                allrec, _ = self.comm.allgather_concat(rec.reshape(-1))
+                for row in allrec.reshape(-1, 36).tolist():
+                    g = cache.setdefault((row[0], bytes(row[4:4 + k])), [row[1], 0])
+                    g[0] = min(g[0], row[1])
+                    g[1] += row[2]
+            else:
+                for key, (f, c) in local.items():
+                    cache[key] = [f, c]
             by_win = {}
             for (w, _), (f, c) in cache.items():
                 by_win.setdefault(w, []).append((f, c))
@@ -443,9 +453,15 @@ class NN_degenerate(object):
             wis = np.array([a[0] for a in keep], np.int64)
             mm_key = np.where(np.array([a[5] for a in keep]), st["mm_key"][wis], np.uint64(_lib.KEY_EMPTY))
 
+            dev_reduce = getattr(self.comm, "on_gpu", False) and hasattr(self.ctx, "h")
+
             def scan_fn(pos, allow):
-                counts, _ = self.msa.scan(k, v, self.fmask, self.rmask, pos, allow)
                 self.stats["scan_calls"] += 1
+                if dev_reduce:        # counts stay in HBM: scan -> NCCL all-reduce -> one D2H
+                    t = self.comm.torch.zeros((len(pos), 3), dtype=self.comm.torch.int64, device=self.comm.device)
+                    self.msa.scan(k, v, self.fmask, self.rmask, pos, allow, counts_out=t)
+                    return self.comm.allreduce_dev(t)
+                counts, _ = self.msa.scan(k, v, self.fmask, self.rmask, pos, allow)
                 return self.comm.allreduce_sum(counts)        # the one collective of a scan round
 
             res = _lib.walk(k, v, self.number_of_dege_bases, self.score_of_dege_bases, self.fmask, self.rmask,
