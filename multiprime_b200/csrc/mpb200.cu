@@ -1225,14 +1225,23 @@ extern "C" int mpb_hist_exceptions(mpb_hist* h, int64_t max_n, int32_t* win_idx,
         }                                                                                         \
     }
 
+#define SCAN_SPECIAL_CAP 3072  // deferred (chunk, row) pairs per block
+
 // One chunk (CNT candidates of one window, masks in registers) against the block's sequence tiles.
+// Rows that need more than the funnel shift — the window starts / ends inside a gap run, holds IUPAC cells, or runs
+// past a ragged row — are "special" (about 0.5 % of the rows).  Handling them inline left most of the warp idle for
+// hundreds of instructions (profiles/README.md, stage r01-a/e), so when DEFER is set they are only recorded in a
+// block-private list and evaluated densely, one per thread, after the block has walked all its chunks.
 template <bool BITS, int CNT>
 __device__ __forceinline__ void scan_chunk(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq,
                                            const int32_t* __restrict__ lens, int k, int v, uint32_t kmask,
                                            uint32_t fmask, uint32_t rmask, int first, int p, long long tile0,
                                            int tiles_per_block, const uint32_t* __restrict__ cand_allow,
                                            unsigned int* __restrict__ s_out, const int32_t* __restrict__ bits_slot,
-                                           uint32_t* __restrict__ bits, long long words, int* __restrict__ err) {
+                                           uint32_t* __restrict__ bits, long long words, int* __restrict__ err,
+                                           int ch_local, unsigned int* __restrict__ s_special,
+                                           unsigned int* __restrict__ s_nspecial) {
+    constexpr bool DEFER = !BITS;
     uint32_t nA[CNT], nC[CNT], nG[CNT], nT[CNT];
     unsigned acc0[CNT], accf[CNT], accr[CNT];
 #pragma unroll
@@ -1248,8 +1257,6 @@ __device__ __forceinline__ void scan_chunk(const uint32_t* __restrict__ pl, int6
     // the two column words of this window: uniform for the whole block
     const uint32_t* __restrict__ wbase = pl + ((int64_t)(p >> 5) * 4) * nsp;
     const int sh = p & 31;
-    const bool inside_all = true;
-    (void)inside_all;
     for (int t = 0; t < tiles_per_block; ++t) {
         const long long tile = tile0 + t;
         if (tile * SCAN_THREADS >= n_seq) break;  // uniform
@@ -1270,20 +1277,35 @@ __device__ __forceinline__ void scan_chunk(const uint32_t* __restrict__ pl, int6
             w.t = __funnelshift_r(t0, t1, sh) & kmask;
             uint32_t gapv = ~(w.a | w.c | w.g | w.t) & kmask;
             const int len = lens[s];
-            if (p + k > len) {  // ragged row
-                Win tmp;
-                if (!mpb_window_slow(pl, nsp, s, len, p, k, tmp)) atomicOr(err, MPB_ERR_SHORT_ROW);
-                w.a = tmp.a;
-                w.c = tmp.c;
-                w.g = tmp.g;
-                w.t = tmp.t;
+            const bool ragged = p + k > len;
+            const bool edge = (((gapv & 1u) | ((gapv >> (k - 1)) & 1u)) != 0u) && gapv != kmask;
+            w.multi = mpb_multi(w.a, w.c, w.g, w.t);
+            bool special = ragged || edge || w.multi != 0u;
+            if (DEFER && special) {
+                const unsigned slot = atomicAdd(s_nspecial, 1u);
+                if (slot < SCAN_SPECIAL_CAP) {
+                    s_special[slot] = ((unsigned)ch_local << 16) | (unsigned)(t * SCAN_THREADS + threadIdx.x);
+                } else {
+                    special = true;  // list full: fall through to the inline path below
+                    atomicSub(s_nspecial, 1u);
+                }
+                if (slot < SCAN_SPECIAL_CAP) goto next_tile;
+            }
+            if (special) {
+                if (ragged) {
+                    Win tmp;
+                    if (!mpb_window_slow(pl, nsp, s, len, p, k, tmp)) atomicOr(err, MPB_ERR_SHORT_ROW);
+                    w.a = tmp.a;
+                    w.c = tmp.c;
+                    w.g = tmp.g;
+                    w.t = tmp.t;
+                } else if (edge) {
+                    mpb_patch_edges(pl, nsp, s, len, p, k, kmask, w);
+                }
                 gapv = ~(w.a | w.c | w.g | w.t) & kmask;
-            } else if (((gapv & 1u) | ((gapv >> (k - 1)) & 1u)) && gapv != kmask) {
-                mpb_patch_edges(pl, nsp, s, len, p, k, kmask, w);
-                gapv = ~(w.a | w.c | w.g | w.t) & kmask;
+                w.multi = mpb_multi(w.a, w.c, w.g, w.t);
             }
             w.gapv = gapv;
-            w.multi = mpb_multi(w.a, w.c, w.g, w.t);
             isgap = __popc(gapv) > v;
             if (!isgap) {
                 if (w.multi == 0) {
@@ -1304,6 +1326,7 @@ __device__ __forceinline__ void scan_chunk(const uint32_t* __restrict__ pl, int6
                 }
             }
         }
+    next_tile:
         if (BITS) {
             const long long word = tile * (SCAN_THREADS / 32) + (threadIdx.x >> 5);
             const unsigned bg = __ballot_sync(0xffffffffu, isgap);
@@ -1334,6 +1357,51 @@ __device__ __forceinline__ void scan_chunk(const uint32_t* __restrict__ pl, int6
     }
 }
 
+// the deferred rows of a block: one (chunk, row) pair per thread, full window logic, shared-memory counters
+__device__ __forceinline__ void scan_special(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq,
+                                             const int32_t* __restrict__ lens, int k, int v, uint32_t kmask,
+                                             uint32_t fmask, uint32_t rmask, const int4* __restrict__ chunks, int ch0,
+                                             long long tile0, const uint32_t* __restrict__ cand_allow,
+                                             unsigned int* __restrict__ s_cnt, const unsigned int* __restrict__ s_special,
+                                             unsigned int n_special, int* __restrict__ err) {
+    for (unsigned i = threadIdx.x; i < n_special; i += SCAN_THREADS) {
+        const unsigned e = s_special[i];
+        const int ch_local = (int)(e >> 16);
+        const int4 cd = chunks[ch0 + ch_local];
+        const int64_t s = tile0 * SCAN_THREADS + (e & 0xFFFFu);
+        Win w;
+        if (!mpb_load_window(pl, nsp, s, lens[s], cd.z, k, kmask, w)) atomicOr(err, MPB_ERR_SHORT_ROW);
+        if (__popc(w.gapv) > v) continue;  // gap row: no contribution
+        uint32_t nexp = 1;
+        if (w.multi) {
+            nexp = mpb_expansions(w);
+            if (nexp > MPB_MAX_EXP) {
+                atomicOr(err, MPB_ERR_EXPAND);
+                continue;
+            }
+        }
+        for (int ci = 0; ci < cd.y; ++ci) {
+            const uint4 al = __ldg((const uint4*)(cand_allow) + cd.x + ci);
+            const uint32_t nA = ~al.x & kmask, nC = ~al.y & kmask, nG = ~al.z & kmask, nT = ~al.w & kmask;
+            unsigned n0 = 0, nf = 0, nr = 0;
+            for (uint32_t x = 0; x < nexp; ++x) {
+                uint32_t a = w.a, c = w.c, g = w.g, tt = w.t;
+                if (w.multi) mpb_expand(w, x, a, c, g, tt);
+                const uint32_t mis = w.gapv | (a & nA) | (c & nC) | (g & nG) | (tt & nT);
+                const bool within = __popc(mis) <= v;
+                const bool z = mis == 0u;
+                n0 += z;
+                nf += within && (mis & fmask) == 0u && !z;
+                nr += within && (mis & rmask) == 0u && !z;
+            }
+            unsigned int* o = &s_cnt[(ch_local * SCAN_CHUNK + ci) * 3];
+            if (n0) atomicAdd(&o[0], n0);
+            if (nf) atomicAdd(&o[1], nf);
+            if (nr) atomicAdd(&o[2], nr);
+        }
+    }
+}
+
 // Block (x, y): sequences [x*T*256, (x+1)*T*256) against the chunks [y*cpb, (y+1)*cpb).  A chunk = up to
 // SCAN_CHUNK candidates of ONE window: their masks sit in registers while the block walks its T sequence tiles
 // (T small enough that the tiles' words stay in L1 for the next chunk of the same column word), each thread keeping
@@ -1346,9 +1414,12 @@ k_scan(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq, const int32_
        const uint32_t* __restrict__ cand_allow, uint32_t* __restrict__ partial, long long nc,
        const int32_t* __restrict__ bits_slot, uint32_t* __restrict__ bits, long long words, int* __restrict__ err) {
     __shared__ unsigned int s_cnt[SCAN_MAX_CPB * SCAN_CHUNK * 3];
+    __shared__ unsigned int s_special[BITS ? 1 : SCAN_SPECIAL_CAP];
+    __shared__ unsigned int s_nspecial;
     const int ch0 = blockIdx.y * cpb;
     const int ch1 = min(n_chunks, ch0 + cpb);
     for (int i = threadIdx.x; i < (ch1 - ch0) * SCAN_CHUNK * 3; i += SCAN_THREADS) s_cnt[i] = 0;
+    if (threadIdx.x == 0) s_nspecial = 0;
     __syncthreads();
     const uint32_t kmask = (1u << k) - 1u;
     const long long tile0 = (long long)blockIdx.x * tiles_per_block;
@@ -1358,23 +1429,28 @@ k_scan(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq, const int32_
         switch (cd.y) {
             case 1:
                 scan_chunk<BITS, 1>(pl, nsp, n_seq, lens, k, v, kmask, fmask, rmask, cd.x, cd.z, tile0, tiles_per_block,
-                                    cand_allow, so, bits_slot, bits, words, err);
+                                    cand_allow, so, bits_slot, bits, words, err, ch - ch0, s_special, &s_nspecial);
                 break;
             case 2:
                 scan_chunk<BITS, 2>(pl, nsp, n_seq, lens, k, v, kmask, fmask, rmask, cd.x, cd.z, tile0, tiles_per_block,
-                                    cand_allow, so, bits_slot, bits, words, err);
+                                    cand_allow, so, bits_slot, bits, words, err, ch - ch0, s_special, &s_nspecial);
                 break;
             case 3:
                 scan_chunk<BITS, 3>(pl, nsp, n_seq, lens, k, v, kmask, fmask, rmask, cd.x, cd.z, tile0, tiles_per_block,
-                                    cand_allow, so, bits_slot, bits, words, err);
+                                    cand_allow, so, bits_slot, bits, words, err, ch - ch0, s_special, &s_nspecial);
                 break;
             default:
                 scan_chunk<BITS, 4>(pl, nsp, n_seq, lens, k, v, kmask, fmask, rmask, cd.x, cd.z, tile0, tiles_per_block,
-                                    cand_allow, so, bits_slot, bits, words, err);
+                                    cand_allow, so, bits_slot, bits, words, err, ch - ch0, s_special, &s_nspecial);
                 break;
         }
     }
     __syncthreads();
+    if (!BITS) {
+        scan_special(pl, nsp, n_seq, lens, k, v, kmask, fmask, rmask, chunks, ch0, tile0, cand_allow, s_cnt, s_special,
+                     s_nspecial, err);
+        __syncthreads();
+    }
     // partial[x][candidate][3]
     uint32_t* out = partial + (long long)blockIdx.x * nc * 3;
     for (int ch = ch0; ch < ch1; ++ch) {
