@@ -35,7 +35,7 @@ struct mpb_msa {
     mpb_ctx* ctx;
     int64_t n_seq, nsp, n_col;
     int ncw;            // column words incl. the trailing zero word
-    uint32_t* planes;   // [ncw][4][nsp]
+    uint32_t* planes;   // [ncw][nsp] uint4{A,C,G,T}
     int32_t* lens;      // [nsp]
     int* err;           // device error flags
     int64_t row0;       // global index of local sequence 0 (sequence-sharded runs)
@@ -248,11 +248,7 @@ __global__ void k_pack_planes(const uint8_t* __restrict__ packed, int64_t n_seq,
             t |= (((x >> 3) & 1u) << i) | (((y >> 3) & 1u) << (i + 1));
         }
     }
-    uint32_t* w = planes + ((int64_t)cw * 4) * nsp + s;
-    w[0] = a;
-    w[nsp] = c;
-    w[2 * nsp] = g;
-    w[3 * nsp] = t;
+    reinterpret_cast<uint4*>(planes)[(int64_t)cw * nsp + s] = make_uint4(a, c, g, t);
 }
 
 __global__ void k_fill_i32(int32_t* __restrict__ dst, int64_t n, int64_t n_set, int32_t value) {
@@ -338,8 +334,8 @@ __global__ void k_seq_attr(const uint32_t* __restrict__ pl, int64_t nsp, int64_t
     int len = lens[s];
     int first = -1, last = -1;
     for (int cw = 0; cw < ncw - 1; ++cw) {
-        const uint32_t* w = pl + ((int64_t)cw * 4) * nsp + s;
-        uint32_t any = w[0] | w[nsp] | w[2 * nsp] | w[3 * nsp];
+        const uint4 w = mpb_word(pl, nsp, s, cw);
+        uint32_t any = w.x | w.y | w.z | w.w;
         if (any) {
             if (first < 0) first = cw * 32 + __ffs(any) - 1;
             last = cw * 32 + 31 - __clz(any);
@@ -359,8 +355,8 @@ __global__ void k_seq_attr_hist(const uint32_t* __restrict__ pl, int64_t nsp, in
     int len = lens[s];
     int first = -1, last = -1;
     for (int cw = 0; cw < ncw - 1; ++cw) {
-        const uint32_t* w = pl + ((int64_t)cw * 4) * nsp + s;
-        uint32_t any = w[0] | w[nsp] | w[2 * nsp] | w[3 * nsp];
+        const uint4 w = mpb_word(pl, nsp, s, cw);
+        uint32_t any = w.x | w.y | w.z | w.w;
         if (any) {
             if (first < 0) first = cw * 32 + __ffs(any) - 1;
             last = cw * 32 + 31 - __clz(any);
@@ -1213,12 +1209,11 @@ extern "C" int mpb_hist_exceptions(mpb_hist* h, int64_t max_n, int32_t* win_idx,
     {                                                                                             \
         const uint32_t mis = w.gapv | ((A_) & nA[ci]) | ((C_) & nC[ci]) | ((G_) & nG[ci]) | ((T_) & nT[ci]); \
         const bool within = __popc(mis) <= v;                                                     \
-        const bool z = mis == 0u;                                                                 \
         const bool okf = within && (mis & fmask) == 0u;                                           \
         const bool okr = within && (mis & rmask) == 0u;                                           \
-        acc0[ci] += z;                                                                            \
-        accf[ci] += okf && !z;                                                                    \
-        accr[ci] += okr && !z;                                                                    \
+        acc0[ci] += (mis == 0u);                                                                  \
+        accf[ci] += okf; /* includes the perfect matches; they are subtracted after the reduction */ \
+        accr[ci] += okr;                                                                          \
         if (BITS) {                                                                               \
             nonf |= (!okf) << ci;                                                                 \
             nonr |= (!okr) << ci;                                                                 \
@@ -1255,7 +1250,7 @@ __device__ __forceinline__ void scan_chunk(const uint32_t* __restrict__ pl, int6
     }
     const int lane = threadIdx.x & 31;
     // the two column words of this window: uniform for the whole block
-    const uint32_t* __restrict__ wbase = pl + ((int64_t)(p >> 5) * 4) * nsp;
+    const uint4* __restrict__ wbase = reinterpret_cast<const uint4*>(pl) + (int64_t)(p >> 5) * nsp;
     const int sh = p & 31;
     for (int t = 0; t < tiles_per_block; ++t) {
         const long long tile = tile0 + t;
@@ -1268,13 +1263,11 @@ __device__ __forceinline__ void scan_chunk(const uint32_t* __restrict__ pl, int6
         bool isgap = false;
         unsigned nonf = 0, nonr = 0;
         if (valid) {
-            const uint32_t* q = wbase + s;
-            const uint32_t a0 = q[0], c0 = q[nsp], g0 = q[2 * nsp], t0 = q[3 * nsp];
-            const uint32_t a1 = q[4 * nsp], c1 = q[5 * nsp], g1 = q[6 * nsp], t1 = q[7 * nsp];
-            w.a = __funnelshift_r(a0, a1, sh) & kmask;
-            w.c = __funnelshift_r(c0, c1, sh) & kmask;
-            w.g = __funnelshift_r(g0, g1, sh) & kmask;
-            w.t = __funnelshift_r(t0, t1, sh) & kmask;
+            const uint4 q0 = __ldg(wbase + s), q1 = __ldg(wbase + nsp + s);
+            w.a = __funnelshift_r(q0.x, q1.x, sh) & kmask;
+            w.c = __funnelshift_r(q0.y, q1.y, sh) & kmask;
+            w.g = __funnelshift_r(q0.z, q1.z, sh) & kmask;
+            w.t = __funnelshift_r(q0.w, q1.w, sh) & kmask;
             uint32_t gapv = ~(w.a | w.c | w.g | w.t) & kmask;
             const int len = lens[s];
             const bool ragged = p + k > len;
@@ -1348,8 +1341,8 @@ __device__ __forceinline__ void scan_chunk(const uint32_t* __restrict__ pl, int6
 #pragma unroll
     for (int ci = 0; ci < CNT; ++ci) {
         const unsigned r0 = __reduce_add_sync(0xffffffffu, acc0[ci]);
-        const unsigned rf = __reduce_add_sync(0xffffffffu, accf[ci]);
-        const unsigned rr = __reduce_add_sync(0xffffffffu, accr[ci]);
+        const unsigned rf = __reduce_add_sync(0xffffffffu, accf[ci]) - r0;   // 1..v mismatches only
+        const unsigned rr = __reduce_add_sync(0xffffffffu, accr[ci]) - r0;
         if (lane < 3) {
             const unsigned val = lane == 0 ? r0 : (lane == 1 ? rf : rr);
             if (val) atomicAdd(&s_out[ci * 3 + lane], val);

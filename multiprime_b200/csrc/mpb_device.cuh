@@ -82,12 +82,17 @@ __device__ __forceinline__ uint32_t mpb_multi(uint32_t a, uint32_t c, uint32_t g
     return (a & c) | (g & t) | ((a ^ c) & (g ^ t));
 }
 
-// planes[col_word][plane][seq]; one zero word is appended after the last column word so that word j+1 exists.
+// planes[col_word][seq] = uint4{A, C, G, T}: the four plane words of one sequence and one 32-column word sit in one
+// 16-byte vector, so a window costs two coalesced 128-bit loads; one zero word is appended after the last column word
+// so that word j+1 exists.
+__device__ __forceinline__ uint4 mpb_word(const uint32_t* __restrict__ pl, int64_t nsp, int64_t s, int cw) {
+    return __ldg(reinterpret_cast<const uint4*>(pl) + (int64_t)cw * nsp + s);
+}
+
 __device__ __forceinline__ int mpb_cell(const uint32_t* __restrict__ pl, int64_t nsp, int64_t s, int col) {
-    const uint32_t* w = pl + ((int64_t)(col >> 5) * 4) * nsp + s;
+    const uint4 w = mpb_word(pl, nsp, s, col >> 5);
     int b = col & 31;
-    return ((w[0] >> b) & 1u) | (((w[nsp] >> b) & 1u) << 1) | (((w[2 * nsp] >> b) & 1u) << 2) |
-           (((w[3 * nsp] >> b) & 1u) << 3);
+    return ((w.x >> b) & 1u) | (((w.y >> b) & 1u) << 1) | (((w.z >> b) & 1u) << 2) | (((w.w >> b) & 1u) << 3);
 }
 
 // The rare path of core:666-687: the window starts/ends inside a gap run, or runs past the end of a ragged row.
@@ -173,8 +178,8 @@ __device__ __forceinline__ void mpb_patch_edges(const uint32_t* __restrict__ pl,
         int j = (p - 1) >> 5;
         uint32_t below = (p & 31) ? ((1u << (p & 31)) - 1u) : 0xFFFFFFFFu;  // columns < p inside word j
         for (; j >= 0 && got < g; --j) {
-            const uint32_t* q = pl + ((int64_t)j * 4) * nsp + s;
-            const uint32_t wa = q[0], wc = q[nsp], wg = q[2 * nsp], wt = q[3 * nsp];
+            const uint4 q = mpb_word(pl, nsp, s, j);
+            const uint32_t wa = q.x, wc = q.y, wg = q.z, wt = q.w;
             uint32_t any = (wa | wc | wg | wt) & below;
             below = 0xFFFFFFFFu;
             while (any && got < g) {
@@ -204,8 +209,8 @@ __device__ __forceinline__ void mpb_patch_edges(const uint32_t* __restrict__ pl,
         const int jlast = (len - 1) >> 5;
         uint32_t above = ~((c0 & 31) ? ((1u << (c0 & 31)) - 1u) : 0u);  // columns >= c0 inside the first word
         for (int j = c0 >> 5; j <= jlast && got < g && c0 < len; ++j) {
-            const uint32_t* q = pl + ((int64_t)j * 4) * nsp + s;
-            const uint32_t wa = q[0], wc = q[nsp], wg = q[2 * nsp], wt = q[3 * nsp];
+            const uint4 q = mpb_word(pl, nsp, s, j);
+            const uint32_t wa = q.x, wc = q.y, wg = q.z, wt = q.w;
             uint32_t any = (wa | wc | wg | wt) & above;  // cells >= len are stored as zero
             above = 0xFFFFFFFFu;
             while (any && got < g) {
@@ -231,13 +236,13 @@ __device__ __forceinline__ void mpb_patch_edges(const uint32_t* __restrict__ pl,
 // Load the window starting at column p of sequence s.  Fast path: a funnel shift per plane.
 __device__ __forceinline__ bool mpb_load_window(const uint32_t* __restrict__ pl, int64_t nsp, int64_t s, int len,
                                                 int p, int k, uint32_t kmask, Win& w) {
-    const uint32_t* w0 = pl + ((int64_t)(p >> 5) * 4) * nsp + s;
-    const uint32_t* w1 = w0 + 4 * nsp;
+    const uint4 w0 = mpb_word(pl, nsp, s, p >> 5);
+    const uint4 w1 = mpb_word(pl, nsp, s, (p >> 5) + 1);
     const int sh = p & 31;
-    w.a = __funnelshift_r(w0[0], w1[0], sh) & kmask;
-    w.c = __funnelshift_r(w0[nsp], w1[nsp], sh) & kmask;
-    w.g = __funnelshift_r(w0[2 * nsp], w1[2 * nsp], sh) & kmask;
-    w.t = __funnelshift_r(w0[3 * nsp], w1[3 * nsp], sh) & kmask;
+    w.a = __funnelshift_r(w0.x, w1.x, sh) & kmask;
+    w.c = __funnelshift_r(w0.y, w1.y, sh) & kmask;
+    w.g = __funnelshift_r(w0.z, w1.z, sh) & kmask;
+    w.t = __funnelshift_r(w0.w, w1.w, sh) & kmask;
     uint32_t gapv = ~(w.a | w.c | w.g | w.t) & kmask;
     bool ok = true;
     if (p + k > len) {  // ragged row shorter than the window end: the generic cell-by-cell restatement
