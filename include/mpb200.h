@@ -170,8 +170,8 @@ int mpb_tm(mpb_ctx* ctx, const uint8_t* seqs2bit_hd, int k, int64_t n, const dou
  * round collects the candidates of all live tracks and calls `scan` once (mpb_scan semantics, candidates sorted by
  * window; the callback adds the count all-reduce in sequence-sharded runs).  No device code, no CUDA calls.
  *   out_sets[n_win*32]       final primer (4-bit sets) of the chosen track
- *   out_counts[n_win*4]      optimal_coverage_init, F_mis_cover_cover, R_mis_cover_cover (core:917-918 before the
- *                            sum), chosen track (0 = first / NM, 1 = MM)
+ *   out_counts[n_win*5]      optimal_coverage_init, F_mis_cover_cover, R_mis_cover_cover (core:917-918 before the
+ *                            sum), chosen track (0 = first / NM, 1 = MM), perfect_coverage of the final primer (core:853)
  *   out_seeds[n_win*2*32]    seed bases (0..3) of the tracks; out_seed_cover[n_win*2] cover[seed] (-1: no such track)
  *   out_ntracks[n_win]       1 or 2
  *   trace_sets[trace_cap*32], trace_off[n_win+1]   every primer handed to mis_primer_check, in call order

@@ -131,7 +131,7 @@ def walk(k, v, dnum, degeneracy, fmask, rmask, win_pos, cover_number, freq, nn, 
             return -2
 
     out_sets = np.zeros((n, 32), np.uint8)
-    out_counts = np.zeros((n, 4), np.int64)
+    out_counts = np.zeros((n, 5), np.int64)
     out_seeds = np.zeros((n, 2, 32), np.uint8)
     out_seed_cover = np.zeros((n, 2), np.int64)
     out_nt = np.zeros(n, np.int32)

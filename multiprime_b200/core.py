@@ -470,8 +470,9 @@ class NN_degenerate(object):
             lap("walk")
             self.stats["candidates"] += int(res["stats"][1])
             self.stats["evals"] += int(res["stats"][2]) * N
+            tick[0] = time.perf_counter()
             out = self._finish(hist, keep, res)
-            lap("finish")
+            tick[0] = time.perf_counter()
         lap("free")
         return out
 
@@ -559,20 +560,36 @@ class NN_degenerate(object):
         k, v, N = self.primer_length, self.variation, self.total_sequence_number
         gc_lo, gc_hi = float(self.GC[0]), float(self.GC[1])
         n = len(keep)
+        ph = self.stats.setdefault("phase_ms", {})
+        tick = [time.perf_counter()]
+
+        def lap(name):
+            now = time.perf_counter()
+            ph[name] = ph.get(name, 0.0) + 1000 * (now - tick[0])
+            tick[0] = now
+
         sets_arr = res["sets"]
         sets_list = [row[:k].tolist() for row in sets_arr]
         wis = np.array([a[0] for a in keep], np.int32)
         pos = np.array([a[1] for a in keep], np.int32)
         allow = np.array([allow_masks(s) for s in sets_list], np.uint32)
-        # final pass of the scan: perfect coverage of the chosen primer (+ per-sequence non-cover bits)
-        slots = np.arange(n, dtype=np.int32) if self.sidecars else None
-        counts, bits = self.msa.scan(k, v, self.fmask, self.rmask, pos, allow, bits_slot=slots)
-        counts = self.comm.allreduce_sum(counts)
-        self.stats["scan_calls"] += 1
+        # perfect coverage of the chosen primer is already known from the walk (the last candidate scanned for the
+        # track IS the final primer); a final scan pass is only needed for the per-sequence non-cover bits
+        bits = None
+        if self.sidecars:
+            _, bits = self.msa.scan(k, v, self.fmask, self.rmask, pos, allow, bits_slot=np.arange(n, dtype=np.int32))
+            self.stats["scan_calls"] += 1
+        perfect = res["counts"][:, 4]
+        lap("fin_scan")
         distinct = hist.match(wis, allow)
+        lap("fin_match")
         tm_avg, gc, flags, deg, ndeg = self._primer_props(sets_arr, k, gc_lo, gc_hi)
+        lap("fin_props")
         seqkeys = self.msa.seqkeys(k, pos) if self.sidecars else None
         dimer = self._self_dimer(sets_list)                                   # core:487-503 for all windows at once
+        lap("fin_dimer")
+        lut = np.frombuffer(CODE_CHARS.encode(), dtype=np.uint8)
+        trace_str = lut[res["trace"][:int(res["trace_off"][n]), :k]].view("S%d" % k).ravel().astype(str).tolist()
         out = []
         for i in range(n):
             wi, p, c_bit, t_bit, cover_number, _ = keep[i]
@@ -594,14 +611,15 @@ class NN_degenerate(object):
             if fl & 4:
                 notes.append("hairpin")
             init, fm, rm = (int(x) for x in res["counts"][i, :3])
-            row = [p, c_bit, t_bit, primer_string(sets), int(ndeg[i]), nonsense, int(counts[i][0]), init + fm,
+            row = [p, c_bit, t_bit, primer_string(sets), int(ndeg[i]), nonsense, int(perfect[i]), init + fm,
                    init + rm, float(tm_avg[i]), float(gc[i]) if not notes else "|".join(notes)]
             a, b = int(res["trace_off"][i]), int(res["trace_off"][i + 1])
-            rec = {"row": row, "trace": [primer_string(t[:k].tolist()) for t in res["trace"][a:b]]}
+            rec = {"row": row, "trace": trace_str[a:b]}
             if self.sidecars:
                 rec["non_cov"], rec["gap_ids"] = self._sidecars(hist, wi, p, sets, bits[i], seqkeys[i])
             out.append(rec)
         self.stats["accepted"] += len(out)
+        lap("fin_rows")
         return out
 
     def _primer_props(self, sets_arr, k, gc_lo, gc_hi):

@@ -412,6 +412,7 @@ extern "C" int mpb_seq_attr(mpb_msa* m, int32_t* lead_hd, int32_t* rstrip_hd) {
 #define HIST_TILES 4
 #define HIST_SLOTS 512  // power of two
 #define HIST_PROBES 8
+#define HIST_SPECIAL_CAP 256  // deferred rows per (block, window)
 
 __device__ __forceinline__ void hist_stage(unsigned long long* s_key, unsigned int* s_cnt, unsigned long long* s_first,
                                            uint64_t* K, uint32_t* C, uint64_t* F, int log2cap, uint64_t key,
@@ -444,6 +445,8 @@ k_hist(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq, const int32_
     __shared__ unsigned long long s_first[HIST_SLOTS];
     __shared__ unsigned int s_cnt[HIST_SLOTS];
     __shared__ unsigned int s_gap;
+    __shared__ unsigned int s_nspecial;
+    __shared__ unsigned int s_special[HIST_SPECIAL_CAP];
     const int lane = threadIdx.x & 31;
     const uint32_t kmask = (1u << k) - 1u;
     const uint64_t cap = 1ull << log2cap;
@@ -452,51 +455,94 @@ k_hist(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq, const int32_
         s_first[i] = ~0ull;
         s_cnt[i] = 0;
     }
-    if (threadIdx.x == 0) s_gap = 0;
+    if (threadIdx.x == 0) {
+        s_gap = 0;
+        s_nspecial = 0;
+    }
     __syncthreads();
     for (int wi = blockIdx.y; wi < nw; wi += gridDim.y) {
         const int p = win_pos[wi];
         uint64_t* K = keys + (uint64_t)wi * cap;
         uint32_t* C = cnt + (uint64_t)wi * cap;
         uint64_t* F = first + (uint64_t)wi * cap;
+        const uint4* __restrict__ wbase = reinterpret_cast<const uint4*>(pl) + (int64_t)(p >> 5) * nsp;
+        const int sh = p & 31;
+        // pass 1: plain rows (funnel shift only); rows needing gap patching / IUPAC expansion / ragged handling are
+        // recorded and handled densely in pass 2 (they left most of a warp idle when handled inline)
         for (int t = 0; t < HIST_TILES; ++t) {
             const int64_t tile = (int64_t)blockIdx.x * HIST_TILES + t;
             if (tile * HIST_THREADS >= n_seq) break;  // uniform
             const int64_t s = tile * HIST_THREADS + threadIdx.x;
-            const uint64_t gs = (uint64_t)(row0 + s);  // global sequence index: first-seen order across shards
             const bool valid = s < n_seq;
-            Win w;
-            w.a = w.c = w.g = w.t = w.multi = 0;
-            w.gapv = kmask;
-            if (valid && !mpb_load_window(pl, nsp, s, lens[s], p, k, kmask, w)) atomicOr(err, MPB_ERR_SHORT_ROW);
-            const int ngap = __popc(w.gapv);
-            const bool isgap = valid && ngap > v;
-            const bool cover = valid && !isgap;
-            const unsigned gb = __ballot_sync(0xffffffffu, isgap);
+            bool plain = false, isgap = false;
+            uint64_t key = 0;
+            if (valid) {
+                const uint4 q0 = __ldg(wbase + s), q1 = __ldg(wbase + nsp + s);
+                const uint32_t a = __funnelshift_r(q0.x, q1.x, sh) & kmask, c = __funnelshift_r(q0.y, q1.y, sh) & kmask,
+                               g = __funnelshift_r(q0.z, q1.z, sh) & kmask, tt = __funnelshift_r(q0.w, q1.w, sh) & kmask;
+                const uint32_t gapv = ~(a | c | g | tt) & kmask;
+                const bool special = (p + k > lens[s]) || ((((gapv & 1u) | ((gapv >> (k - 1)) & 1u)) != 0u) && gapv != kmask) ||
+                                     mpb_multi(a, c, g, tt) != 0u;
+                if (special) {
+                    const unsigned slot = atomicAdd(&s_nspecial, 1u);
+                    if (slot < HIST_SPECIAL_CAP) s_special[slot] = (unsigned)(t * HIST_THREADS + threadIdx.x);
+                } else {
+                    plain = true;
+                    isgap = __popc(gapv) > v;
+                    key = mpb_key(c, g, tt, gapv, k);
+                }
+            }
+            const unsigned gb = __ballot_sync(0xffffffffu, plain && isgap);
             if (lane == 0 && gb) atomicAdd(&s_gap, (unsigned)__popc(gb));
-            const bool simple = cover && w.multi == 0;
-            const unsigned smask = __ballot_sync(0xffffffffu, simple);
-            if (simple) {
-                const uint64_t key = mpb_key(w.c, w.g, w.t, w.gapv, k);
+            const unsigned smask = __ballot_sync(0xffffffffu, plain);
+            if (plain) {
                 const unsigned peers = __match_any_sync(smask, key);
                 if (lane == __ffs(peers) - 1)  // lowest lane = lowest sequence index = first seen
-                    hist_stage(s_key, s_cnt, s_first, K, C, F, log2cap, key, (uint32_t)__popc(peers), gs << 16, err);
-            } else if (cover) {
-                const uint32_t total = mpb_expansions(w);
-                if (total > MPB_MAX_EXP) {
-                    atomicOr(err, MPB_ERR_EXPAND);
-                } else {
-                    for (uint32_t e = 0; e < total; ++e) {
-                        uint32_t a, c, g, tt;
-                        mpb_expand(w, e, a, c, g, tt);
-                        hist_stage(s_key, s_cnt, s_first, K, C, F, log2cap, mpb_key(c, g, tt, w.gapv, k), 1u,
-                                   (gs << 16) | e, err);
-                    }
+                    hist_stage(s_key, s_cnt, s_first, K, C, F, log2cap, key, (uint32_t)__popc(peers),
+                               (uint64_t)(row0 + s) << 16, err);
+            }
+        }
+        __syncthreads();
+        // pass 2: the special rows of this window, one per thread (list overflow: every thread re-checks its rows)
+        {
+            const unsigned nsp_rows = s_nspecial;
+            const bool overflow = nsp_rows > HIST_SPECIAL_CAP;
+            const unsigned n_items = overflow ? (unsigned)(HIST_TILES * HIST_THREADS) : nsp_rows;
+            for (unsigned i = threadIdx.x; i < n_items; i += HIST_THREADS) {
+                const unsigned local = overflow ? i : s_special[i];
+                const int64_t s = (int64_t)blockIdx.x * HIST_TILES * HIST_THREADS + local;
+                if (s >= n_seq) continue;
+                const uint64_t gs = (uint64_t)(row0 + s);
+                Win w;
+                if (overflow) {  // only the rows pass 1 skipped
+                    const uint4 q0 = __ldg(wbase + s), q1 = __ldg(wbase + nsp + s);
+                    const uint32_t a = __funnelshift_r(q0.x, q1.x, sh) & kmask, c = __funnelshift_r(q0.y, q1.y, sh) & kmask,
+                                   g = __funnelshift_r(q0.z, q1.z, sh) & kmask, tt = __funnelshift_r(q0.w, q1.w, sh) & kmask;
+                    const uint32_t gapv = ~(a | c | g | tt) & kmask;
+                    const bool special = (p + k > lens[s]) ||
+                                         ((((gapv & 1u) | ((gapv >> (k - 1)) & 1u)) != 0u) && gapv != kmask) ||
+                                         mpb_multi(a, c, g, tt) != 0u;
+                    if (!special) continue;
                 }
-            } else if (isgap) {
-                if (w.multi == 0) {
-                    hist_stage(s_key, s_cnt, s_first, K, C, F, log2cap, mpb_key(w.c, w.g, w.t, w.gapv, k), 1u, gs << 16,
-                               err);
+                if (!mpb_load_window(pl, nsp, s, lens[s], p, k, kmask, w)) atomicOr(err, MPB_ERR_SHORT_ROW);
+                const bool isgap = __popc(w.gapv) > v;
+                if (isgap) atomicAdd(&s_gap, 1u);
+                if (!isgap && w.multi == 0) {
+                    hist_stage(s_key, s_cnt, s_first, K, C, F, log2cap, mpb_key(w.c, w.g, w.t, w.gapv, k), 1u, gs << 16, err);
+                } else if (!isgap) {
+                    const uint32_t total = mpb_expansions(w);
+                    if (total > MPB_MAX_EXP) {
+                        atomicOr(err, MPB_ERR_EXPAND);
+                    } else {
+                        for (uint32_t e = 0; e < total; ++e) {
+                            uint32_t a, c, g, tt;
+                            mpb_expand(w, e, a, c, g, tt);
+                            hist_stage(s_key, s_cnt, s_first, K, C, F, log2cap, mpb_key(c, g, tt, w.gapv, k), 1u,
+                                       (gs << 16) | e, err);
+                        }
+                    }
+                } else if (w.multi == 0) {
+                    hist_stage(s_key, s_cnt, s_first, K, C, F, log2cap, mpb_key(w.c, w.g, w.t, w.gapv, k), 1u, gs << 16, err);
                 } else {
                     atomicAdd(&iupac_gap_n[wi], 1ull);
                     unsigned long long slot = atomicAdd(exc_n, 1ull);
@@ -517,9 +563,10 @@ k_hist(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq, const int32_
                 s_cnt[i] = 0;
             }
         }
-        if (threadIdx.x == 0 && s_gap) {
-            atomicAdd(&gap_n[wi], (unsigned long long)s_gap);
+        if (threadIdx.x == 0) {
+            if (s_gap) atomicAdd(&gap_n[wi], (unsigned long long)s_gap);
             s_gap = 0;
+            s_nspecial = 0;
         }
         __syncthreads();
     }
@@ -555,54 +602,101 @@ __device__ __forceinline__ void pre_stage(unsigned long long* s_key, unsigned in
     atomicAdd(&bins[code], add);
 }
 
+// one item of the prefilter: a cover row expansion or a gap row, already loaded
+__device__ __forceinline__ void pre_row(const Win& w, int v, unsigned long long* s_key, unsigned int* s_cnt,
+                                        unsigned int* B, int* err) {
+    const bool isgap = __popc(w.gapv) > v;
+    if (w.multi == 0 || isgap) {
+        uint32_t c = w.c, g = w.g, tt = w.t;
+        if (w.multi) {  // gap row holding IUPAC cells: lowest base of every cell
+            const uint32_t a = w.a;
+            c &= ~a;
+            g &= ~(a | c);
+            tt &= ~(a | c | g);
+        }
+        pre_stage(s_key, s_cnt, B, pre_code(c, g, tt), 1u);
+    } else {
+        const uint32_t total = mpb_expansions(w);
+        if (total > MPB_MAX_EXP) {
+            atomicOr(err, MPB_ERR_EXPAND);
+        } else {
+            for (uint32_t e = 0; e < total; ++e) {
+                uint32_t a, c, g, tt;
+                mpb_expand(w, e, a, c, g, tt);
+                pre_stage(s_key, s_cnt, B, pre_code(c, g, tt), 1u);
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(HIST_THREADS)
 k_prefilter(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq, const int32_t* __restrict__ lens, int k, int v,
             const int32_t* __restrict__ win_pos, int nw, unsigned int* __restrict__ bins, int* __restrict__ err) {
     __shared__ unsigned long long s_key[HIST_SLOTS];
     __shared__ unsigned int s_cnt[HIST_SLOTS];
+    __shared__ unsigned int s_nspecial;
+    __shared__ unsigned int s_special[HIST_SPECIAL_CAP];
     const uint32_t kmask = (1u << k) - 1u;
     for (int i = threadIdx.x; i < HIST_SLOTS; i += HIST_THREADS) {
         s_key[i] = MPB_KEY_EMPTY_D;
         s_cnt[i] = 0;
     }
+    if (threadIdx.x == 0) s_nspecial = 0;
     __syncthreads();
     for (int wi = blockIdx.y; wi < nw; wi += gridDim.y) {
         const int p = win_pos[wi];
         unsigned int* B = bins + (long long)wi * PRE_BINS;
-        for (int t = 0; t < HIST_TILES; ++t) {
+        const uint4* __restrict__ wbase = reinterpret_cast<const uint4*>(pl) + (int64_t)(p >> 5) * nsp;
+        const int sh = p & 31;
+        for (int t = 0; t < HIST_TILES; ++t) {  // pass 1: plain rows; the others are recorded for pass 2
             const int64_t tile = (int64_t)blockIdx.x * HIST_TILES + t;
             if (tile * HIST_THREADS >= n_seq) break;  // uniform
             const int64_t s = tile * HIST_THREADS + threadIdx.x;
-            const bool valid = s < n_seq;
-            Win w;
-            w.a = w.c = w.g = w.t = w.multi = 0;
-            w.gapv = kmask;
-            if (valid && !mpb_load_window(pl, nsp, s, lens[s], p, k, kmask, w)) atomicOr(err, MPB_ERR_SHORT_ROW);
-            const bool isgap = valid && __popc(w.gapv) > v;
-            const bool simple = valid && (w.multi == 0 || isgap);
-            const unsigned smask = __ballot_sync(0xffffffffu, simple);
-            if (simple) {
-                uint32_t c = w.c, g = w.g, tt = w.t;
-                if (w.multi) {  // gap row holding IUPAC cells: lowest base of every cell
-                    const uint32_t a = w.a;
-                    c &= ~a;
-                    g &= ~(a | c);
-                    tt &= ~(a | c | g);
+            bool plain = false;
+            uint32_t code = 0;
+            if (s < n_seq) {
+                const uint4 q0 = __ldg(wbase + s), q1 = __ldg(wbase + nsp + s);
+                const uint32_t a = __funnelshift_r(q0.x, q1.x, sh) & kmask, c = __funnelshift_r(q0.y, q1.y, sh) & kmask,
+                               g = __funnelshift_r(q0.z, q1.z, sh) & kmask, tt = __funnelshift_r(q0.w, q1.w, sh) & kmask;
+                const uint32_t gapv = ~(a | c | g | tt) & kmask;
+                const bool special = (p + k > lens[s]) || ((((gapv & 1u) | ((gapv >> (k - 1)) & 1u)) != 0u) && gapv != kmask) ||
+                                     mpb_multi(a, c, g, tt) != 0u;
+                if (special) {
+                    const unsigned slot = atomicAdd(&s_nspecial, 1u);
+                    if (slot < HIST_SPECIAL_CAP) s_special[slot] = (unsigned)(t * HIST_THREADS + threadIdx.x);
+                } else {
+                    plain = true;
+                    code = pre_code(c, g, tt);
                 }
-                const uint32_t code = pre_code(c, g, tt);
+            }
+            const unsigned smask = __ballot_sync(0xffffffffu, plain);
+            if (plain) {
                 const unsigned peers = __match_any_sync(smask, code);
                 if ((threadIdx.x & 31) == __ffs(peers) - 1) pre_stage(s_key, s_cnt, B, code, (uint32_t)__popc(peers));
-            } else if (valid) {
-                const uint32_t total = mpb_expansions(w);
-                if (total > MPB_MAX_EXP) {
-                    atomicOr(err, MPB_ERR_EXPAND);
-                } else {
-                    for (uint32_t e = 0; e < total; ++e) {
-                        uint32_t a, c, g, tt;
-                        mpb_expand(w, e, a, c, g, tt);
-                        pre_stage(s_key, s_cnt, B, pre_code(c, g, tt), 1u);
-                    }
+            }
+        }
+        __syncthreads();
+        {
+            const unsigned nrec = s_nspecial;
+            const bool overflow = nrec > HIST_SPECIAL_CAP;
+            const unsigned n_items = overflow ? (unsigned)(HIST_TILES * HIST_THREADS) : nrec;
+            for (unsigned i = threadIdx.x; i < n_items; i += HIST_THREADS) {
+                const unsigned local = overflow ? i : s_special[i];
+                const int64_t s = (int64_t)blockIdx.x * HIST_TILES * HIST_THREADS + local;
+                if (s >= n_seq) continue;
+                if (overflow) {
+                    const uint4 q0 = __ldg(wbase + s), q1 = __ldg(wbase + nsp + s);
+                    const uint32_t a = __funnelshift_r(q0.x, q1.x, sh) & kmask, c = __funnelshift_r(q0.y, q1.y, sh) & kmask,
+                                   g = __funnelshift_r(q0.z, q1.z, sh) & kmask, tt = __funnelshift_r(q0.w, q1.w, sh) & kmask;
+                    const uint32_t gapv = ~(a | c | g | tt) & kmask;
+                    const bool special = (p + k > lens[s]) ||
+                                         ((((gapv & 1u) | ((gapv >> (k - 1)) & 1u)) != 0u) && gapv != kmask) ||
+                                         mpb_multi(a, c, g, tt) != 0u;
+                    if (!special) continue;
                 }
+                Win w;
+                if (!mpb_load_window(pl, nsp, s, lens[s], p, k, kmask, w)) atomicOr(err, MPB_ERR_SHORT_ROW);
+                pre_row(w, v, s_key, s_cnt, B, err);
             }
         }
         __syncthreads();
@@ -614,6 +708,7 @@ k_prefilter(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq, const i
                 s_cnt[i] = 0;
             }
         }
+        if (threadIdx.x == 0) s_nspecial = 0;
         __syncthreads();
     }
 }

@@ -42,7 +42,7 @@ struct Track {
     uint32_t allow[4];
     std::vector<std::array<int64_t, 16>> nn;
     std::vector<int64_t> nn_cov;
-    int64_t init = 0, fm = 0, rm = 0, seed_cover = 0;
+    int64_t init = 0, fm = 0, rm = 0, seed_cover = 0, perfect = 0;
     int state = 0;  // 0 seed, 1 refine, 2 done
     std::vector<Opt> opts;
     std::vector<std::array<uint8_t, 32>> trace;
@@ -318,6 +318,7 @@ extern "C" int mpb_walk(int k, int v, int dnum, int degeneracy, uint32_t fmask, 
                 t.fm = c[1];
                 t.rm = c[2];
                 t.seed_cover = t.init;
+                t.perfect = c[0];  // expansion rows matching the primer exactly (core:853 perfect_coverage)
                 push_trace(t);
                 t.state = 1;
                 if (t.init + t.fm < total || t.init + t.rm < total) next.push_back(ti);
@@ -349,6 +350,7 @@ extern "C" int mpb_walk(int k, int v, int dnum, int degeneracy, uint32_t fmask, 
                 t.allow[o.base] |= 1u << o.pos;
                 for (int l = 0; l < o.nl; ++l) memcpy(t.nn[o.lidx[l]].data(), o.layer[l], sizeof o.layer[l]);
                 cov_new = o.cov;
+                t.perfect = c[(best_ci + 1) * 3 + 0];
                 t.fm = c[(best_ci + 1) * 3 + 1];
                 t.rm = c[(best_ci + 1) * 3 + 2];
             }
@@ -382,10 +384,11 @@ extern "C" int mpb_walk(int k, int v, int dnum, int degeneracy, uint32_t fmask, 
         }
         const Track& t = tracks[pick];
         memcpy(out_sets + (int64_t)w * 32, t.sets, 32);
-        out_counts[w * 4 + 0] = t.init;
-        out_counts[w * 4 + 1] = t.fm;
-        out_counts[w * 4 + 2] = t.rm;
-        out_counts[w * 4 + 3] = pick - a;
+        out_counts[w * 5 + 0] = t.init;
+        out_counts[w * 5 + 1] = t.fm;
+        out_counts[w * 5 + 2] = t.rm;
+        out_counts[w * 5 + 3] = pick - a;
+        out_counts[w * 5 + 4] = t.perfect;
         for (int ti = 0; ti < 2; ++ti) out_seed_cover[w * 2 + ti] = ti < nt ? tracks[a + ti].seed_cover : -1;
         for (int ti = 0; ti < nt; ++ti)
             for (const auto& s : tracks[a + ti].trace) {
@@ -411,8 +414,12 @@ namespace {
 // Python round(x, 2): correctly rounded decimal -> nearest double.  Fast path when x*100 is clear of a tie.
 double round2(double x) {
     const double y = x * 100.0;
-    const double f = y - floor(y);
-    if (fabs(f - 0.5) > 1e-6 && fabs(y) < 1e13) return nearbyint(y) / 100.0;
+    if (y > -1e13 && y < 1e13) {
+        const long long fl = (long long)y - (y < (double)(long long)y ? 1 : 0);  // floor
+        const double f = y - (double)fl;
+        if (f < 0.5 - 1e-6) return (double)fl / 100.0;
+        if (f > 0.5 + 1e-6) return (double)(fl + 1) / 100.0;
+    }
     char buf[64];
     snprintf(buf, sizeof buf, "%.2f", x);  // glibc: exact, ties to even on the exact binary value
     return strtod(buf, nullptr);
