@@ -97,6 +97,10 @@ int mpb_seq_attr_hist(mpb_msa* msa, int64_t* lead_hist_hd, int64_t* rstrip_hist_
 int mpb_hist_build(mpb_msa* msa, int k, int v, const int32_t* win_pos, int32_t nw, int log2_cap, mpb_hist** out);
 void mpb_hist_free(mpb_hist* h);
 
+/* Counters kept while building (host arrays of nw, any may be NULL): gap rows, gap rows holding IUPAC cells, distinct
+ * table entries — what a sequence shard needs to size mpb_hist_export without a pass over its tables. */
+int mpb_hist_counts(mpb_hist* h, int64_t* gap_n, int64_t* n_iupac_gap, int64_t* n_entries);
+
 /* Copy all entries of the windows with sel[i] != 0 (host array) into compact arrays: window i's entries land in
  * [win_off[i], win_off[i+1]) (host array of nw+1, sized by the caller from mpb_hist_stats' nuniq; unordered). */
 int mpb_hist_export(mpb_hist* h, const uint8_t* sel, const int64_t* win_off, uint64_t* keys_hd, uint32_t* cnt_hd,

@@ -34,6 +34,7 @@ SIGNATURES = {
     "mpb_msa_free": (None, [_P]),
     "mpb_msa_nseq": (C.c_int64, [_P]),
     "mpb_msa_set_row0": (C.c_int, [_P, C.c_int64]),
+    "mpb_hist_counts": (C.c_int, [_P, _P, _P, _P]),
     "mpb_hist_export": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "mpb_seq_attr": (C.c_int, [_P, _P, _P]),
     "mpb_seq_attr_hist": (C.c_int, [_P, _P, _P]),
@@ -342,6 +343,12 @@ class Hist:
                    n_iupac_gap=np.empty(nw, np.int64))
         check(load().mpb_hist_stats(self.h, ptr(out["gap_n"]), ptr(out["ent"]), ptr(out["nuniq"]), ptr(out["mm_key"]),
                                     ptr(out["mm_cnt"]), ptr(out["mm_first"]), ptr(out["n_iupac_gap"])))
+        return out
+
+    def counts(self):
+        """(gap rows, gap rows holding IUPAC cells, distinct entries) per window, from the build counters"""
+        out = [np.zeros(self.nw, np.int64) for _ in range(3)]
+        check(load().mpb_hist_counts(self.h, ptr(out[0]), ptr(out[1]), ptr(out[2])))
         return out
 
     def tensors(self, sel):

@@ -277,34 +277,30 @@ class NN_degenerate(object):
     # -- entropy (core:602-614) ----------------------------------------------------------------------------
     def _iupac_gap_groups(self, hist, wi, pos):
         """gap rows that hold IUPAC cells are not in the device table (their raw k-mer needs 4 bits per cell):
-        group the few of them by raw k-mer here -> [(first order, count)]"""
+        group the few of them by raw k-mer here -> [(first order, count)] of window wi"""
         cache = getattr(hist, "_iupac_groups", None)
         if cache is None:
+            k = self.primer_length
             exc_w, exc_s = self._exceptions(hist)
-            local = {}
-            for w, s in zip(exc_w.tolist(), exc_s.tolist()):
-                g = local.setdefault((w, self._window_cells(s, hist.win_pos[w])), [(self.row0 + s) << 16, 0])
-                g[1] += 1
+            rec = np.zeros((len(exc_w), 3 + 32), np.int64)          # first, count, window, raw cells
+            for i, (w, s) in enumerate(zip(exc_w.tolist(), exc_s.tolist())):
+                rec[i, 0], rec[i, 1], rec[i, 2] = (self.row0 + s) << 16, 1, w
+                rec[i, 3:3 + k] = list(self._window_cells(s, hist.win_pos[w]))
+            if self.comm.world > 1:                                  # shards exchange their records as plain arrays
+                rec = self.comm.allgather_concat(rec.reshape(-1))[0].reshape(-1, 35)
             cache = {}
-            if self.comm.world > 1:
-                # shards exchange their (window, raw k-mer, first, count) records as plain arrays
-                k = self.primer_length
-                rec = np.zeros((len(local), 4 + 32), np.int64)
-                for i, ((w, cells), (f, c)) in enumerate(local.items()):
-                    rec[i, 0], rec[i, 1], rec[i, 2] = w, f, c
-                    rec[i, 4:4 + k] = list(cells)
-                allrec, _ = self.comm.allgather_concat(rec.reshape(-1))
-                for row in allrec.reshape(-1, 36).tolist():
-                    g = cache.setdefault((row[0], bytes(row[4:4 + k])), [row[1], 0])
-                    g[0] = min(g[0], row[1])
-                    g[1] += row[2]
-            else:
-                for key, (f, c) in local.items():
-                    cache[key] = [f, c]
-            by_win = {}
-            for (w, _), (f, c) in cache.items():
-                by_win.setdefault(w, []).append((f, c))
-            cache = hist._iupac_groups = by_win
+            if len(rec):
+                uniq, inv = np.unique(rec[:, 2:], axis=0, return_inverse=True)
+                inv = inv.reshape(-1)
+                first = np.full(len(uniq), np.iinfo(np.int64).max, np.int64)
+                count = np.zeros(len(uniq), np.int64)
+                np.minimum.at(first, inv, rec[:, 0])
+                np.add.at(count, inv, rec[:, 1])
+                win = uniq[:, 0]                                      # np.unique sorts rows: windows are contiguous
+                cuts = np.nonzero(np.diff(win))[0] + 1
+                for lo, hi in zip(np.concatenate([[0], cuts]), np.concatenate([cuts, [len(win)]])):
+                    cache[int(win[lo])] = list(zip(first[lo:hi].tolist(), count[lo:hi].tolist()))
+            hist._iupac_groups = cache
         return cache.get(wi, [])
 
     def _entropy_exact(self, hist, wi, pos, n_unique):
@@ -419,11 +415,12 @@ class NN_degenerate(object):
             return []
         with self.msa.hist(k, v, positions) as hist:
             lap("hist_build")
-            st = hist.stats()
-            lap("hist_stats")
             if self.comm.world > 1:
-                st = self._merge_shards(hist, st)
+                st = self._merge_shards(hist)
                 lap("merge_shards")
+            else:
+                st = hist.stats()
+                lap("hist_stats")
             gap_n = st["gap_n"]
             # core:713 `round(gap_n / N, 2) >= 1 - coverage`: exact for all but ratios on a rounding tie
             ratio = gap_n / N
@@ -476,20 +473,15 @@ class NN_degenerate(object):
         lap("free")
         return out
 
-    def _merge_shards(self, hist, st):
-        """Sequence-sharded run: make the tables of every window that can still pass the gates GLOBAL on every rank.
-        Windows whose entropy is certainly above the threshold are left alone: entropy is concave, so the total-entropy
-        of the pooled sequences is at least the size-weighted mean of the shards' own total-entropies."""
-        comm, N, n_loc = self.comm, self.total_sequence_number, self.n_local
-        gap_n = comm.allreduce_sum(st["gap_n"])
-        iupac_gap = comm.allreduce_sum(st["n_iupac_gap"])
-        ent = st["ent"]
-        s0 = ent[:, 0] + ent[:, 2]
-        s1 = ent[:, 1] + ent[:, 3]
-        bound = comm.allreduce_sum(-(s1 - s0 * math.log2(n_loc))) / N          # <= true tBit
+    def _merge_shards(self, hist):
+        """Sequence-sharded run: make the tables of every window that can still pass the gates GLOBAL on every rank
+        (the prefilter already dropped the windows whose pooled entropy bound is above the gate)."""
+        comm, N = self.comm, self.total_sequence_number
+        gap_local, iupac_local, counts = hist.counts()
+        gap_n = comm.allreduce_sum(gap_local)
+        iupac_gap = comm.allreduce_sum(iupac_local)
         gap_fail = np.array([round(int(g) / N, 2) >= (1 - self.coverage) for g in gap_n])
-        merged = (~gap_fail) & (bound <= self.entropy_threshold + 0.006)
-        counts = st["nuniq"][:, 0] + st["nuniq"][:, 1]
+        merged = ~gap_fail
         if getattr(comm, "on_gpu", False) and hasattr(hist, "export_dev"):
             # entries stay in HBM: export -> NCCL all-gather -> mpb_hist_merge from device pointers
             off, keys, cnt, first = hist.export_dev(merged.astype(np.uint8), counts, comm)

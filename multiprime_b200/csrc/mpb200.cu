@@ -50,6 +50,7 @@ struct mpb_hist {
     int32_t* win_pos; // device copy
     unsigned long long* gap_n;        // [nw]
     unsigned long long* iupac_gap_n;  // [nw]
+    unsigned long long* n_entries;    // [nw] distinct table entries inserted by k_hist
     int32_t* exc;                     // [2*exc_max]
     unsigned long long* exc_n;
     int64_t exc_max;
@@ -416,7 +417,7 @@ extern "C" int mpb_seq_attr(mpb_msa* m, int32_t* lead_hd, int32_t* rstrip_hd) {
 
 __device__ __forceinline__ void hist_stage(unsigned long long* s_key, unsigned int* s_cnt, unsigned long long* s_first,
                                            uint64_t* K, uint32_t* C, uint64_t* F, int log2cap, uint64_t key,
-                                           uint32_t add, uint64_t ord, int* err) {
+                                           uint32_t add, uint64_t ord, int* err, unsigned long long* n_new) {
     uint32_t h = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 55) & (HIST_SLOTS - 1);
     for (int probe = 0; probe < HIST_PROBES; ++probe) {
         unsigned long long cur = s_key[h];
@@ -431,7 +432,7 @@ __device__ __forceinline__ void hist_stage(unsigned long long* s_key, unsigned i
         }
         h = (h + 1) & (HIST_SLOTS - 1);
     }
-    mpb_table_add(K, C, F, log2cap, key, add, ord, err);  // staging table crowded (variable window): go global
+    mpb_table_add(K, C, F, log2cap, key, add, ord, err, n_new);  // staging table crowded (variable window): go global
 }
 
 // block (x, y): sequence tiles [x*HIST_TILES, (x+1)*HIST_TILES) ; blockIdx.y strides over the windows of the batch
@@ -440,7 +441,7 @@ k_hist(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq, const int32_
        const int32_t* __restrict__ win_pos, int nw, uint64_t* __restrict__ keys, uint32_t* __restrict__ cnt,
        uint64_t* __restrict__ first, int log2cap, unsigned long long* __restrict__ gap_n,
        unsigned long long* __restrict__ iupac_gap_n, int32_t* __restrict__ exc, unsigned long long* __restrict__ exc_n,
-       long long exc_max, long long row0, int* __restrict__ err) {
+       long long exc_max, long long row0, unsigned long long* __restrict__ n_entries, int* __restrict__ err) {
     __shared__ unsigned long long s_key[HIST_SLOTS];
     __shared__ unsigned long long s_first[HIST_SLOTS];
     __shared__ unsigned int s_cnt[HIST_SLOTS];
@@ -499,7 +500,7 @@ k_hist(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq, const int32_
                 const unsigned peers = __match_any_sync(smask, key);
                 if (lane == __ffs(peers) - 1)  // lowest lane = lowest sequence index = first seen
                     hist_stage(s_key, s_cnt, s_first, K, C, F, log2cap, key, (uint32_t)__popc(peers),
-                               (uint64_t)(row0 + s) << 16, err);
+                               (uint64_t)(row0 + s) << 16, err, &n_entries[wi]);
             }
         }
         __syncthreads();
@@ -528,7 +529,7 @@ k_hist(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq, const int32_
                 const bool isgap = __popc(w.gapv) > v;
                 if (isgap) atomicAdd(&s_gap, 1u);
                 if (!isgap && w.multi == 0) {
-                    hist_stage(s_key, s_cnt, s_first, K, C, F, log2cap, mpb_key(w.c, w.g, w.t, w.gapv, k), 1u, gs << 16, err);
+                    hist_stage(s_key, s_cnt, s_first, K, C, F, log2cap, mpb_key(w.c, w.g, w.t, w.gapv, k), 1u, gs << 16, err, &n_entries[wi]);
                 } else if (!isgap) {
                     const uint32_t total = mpb_expansions(w);
                     if (total > MPB_MAX_EXP) {
@@ -538,11 +539,11 @@ k_hist(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq, const int32_
                             uint32_t a, c, g, tt;
                             mpb_expand(w, e, a, c, g, tt);
                             hist_stage(s_key, s_cnt, s_first, K, C, F, log2cap, mpb_key(c, g, tt, w.gapv, k), 1u,
-                                       (gs << 16) | e, err);
+                                       (gs << 16) | e, err, &n_entries[wi]);
                         }
                     }
                 } else if (w.multi == 0) {
-                    hist_stage(s_key, s_cnt, s_first, K, C, F, log2cap, mpb_key(w.c, w.g, w.t, w.gapv, k), 1u, gs << 16, err);
+                    hist_stage(s_key, s_cnt, s_first, K, C, F, log2cap, mpb_key(w.c, w.g, w.t, w.gapv, k), 1u, gs << 16, err, &n_entries[wi]);
                 } else {
                     atomicAdd(&iupac_gap_n[wi], 1ull);
                     unsigned long long slot = atomicAdd(exc_n, 1ull);
@@ -557,7 +558,7 @@ k_hist(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq, const int32_
         for (int i = threadIdx.x; i < HIST_SLOTS; i += HIST_THREADS) {  // flush + clear the staging table
             const unsigned long long key = s_key[i];
             if (key != MPB_KEY_EMPTY_D) {
-                mpb_table_add(K, C, F, log2cap, key, s_cnt[i], s_first[i], err);
+                mpb_table_add(K, C, F, log2cap, key, s_cnt[i], s_first[i], err, &n_entries[wi]);
                 s_key[i] = MPB_KEY_EMPTY_D;
                 s_first[i] = ~0ull;
                 s_cnt[i] = 0;
@@ -805,6 +806,7 @@ extern "C" int mpb_hist_build(mpb_msa* m, int k, int v, const int32_t* win_pos, 
     if (e == cudaSuccess) e = cudaMallocAsync(&h->win_pos, (size_t)nw * 4, ctx->stream);
     if (e == cudaSuccess) e = cudaMallocAsync(&h->gap_n, (size_t)nw * 8, ctx->stream);
     if (e == cudaSuccess) e = cudaMallocAsync(&h->iupac_gap_n, (size_t)nw * 8, ctx->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&h->n_entries, (size_t)nw * 8, ctx->stream);
     if (e == cudaSuccess) e = cudaMallocAsync(&h->exc, (size_t)h->exc_max * 8, ctx->stream);
     if (e == cudaSuccess) e = cudaMallocAsync(&h->exc_n, 8, ctx->stream);
     if (e != cudaSuccess) {
@@ -816,6 +818,7 @@ extern "C" int mpb_hist_build(mpb_msa* m, int k, int v, const int32_t* win_pos, 
     CK(cudaMemsetAsync(h->first, 0xFF, slots * 8, ctx->stream));
     CK(cudaMemsetAsync(h->gap_n, 0, (size_t)nw * 8, ctx->stream));
     CK(cudaMemsetAsync(h->iupac_gap_n, 0, (size_t)nw * 8, ctx->stream));
+    CK(cudaMemsetAsync(h->n_entries, 0, (size_t)nw * 8, ctx->stream));
     CK(cudaMemsetAsync(h->exc_n, 0, 8, ctx->stream));
     CK(cudaMemcpyAsync(h->win_pos, win_pos, (size_t)nw * 4, cudaMemcpyHostToDevice, ctx->stream));
     const unsigned gx = (unsigned)((m->n_seq + (long long)HIST_THREADS * HIST_TILES - 1) / ((long long)HIST_THREADS * HIST_TILES));
@@ -826,13 +829,26 @@ extern "C" int mpb_hist_build(mpb_msa* m, int k, int v, const int32_t* win_pos, 
     ctx->pending_units = (double)nw * (double)m->n_seq;  // (window, sequence) k-mers extracted
     LAUNCH(ctx, k_hist, dim3(gx, gy), HIST_THREADS, 0, m->planes, m->nsp, m->n_seq, m->lens, k, v, h->win_pos, nw,
            h->keys, h->cnt, h->first, log2_cap, h->gap_n, h->iupac_gap_n, h->exc, h->exc_n, (long long)h->exc_max,
-           (long long)m->row0, m->err);
+           (long long)m->row0, h->n_entries, m->err);
     int rc = check_flags(ctx, m->err);  // also makes the host win_pos copy safe to release
     if (rc) {
         mpb_hist_free(h);
         return rc;
     }
     *out = h;
+    return 0;
+}
+
+// counters kept by k_hist (host arrays of nw, any may be NULL): gap rows, gap rows holding IUPAC cells, distinct entries
+extern "C" int mpb_hist_counts(mpb_hist* h, int64_t* gap_n, int64_t* n_iupac_gap, int64_t* n_entries) {
+    if (!h) return fail(MPB_EINVAL, "NULL argument");
+    mpb_ctx* ctx = h->msa->ctx;
+    CK(cudaSetDevice(ctx->device));
+    const size_t bytes = (size_t)h->nw * 8;
+    if (gap_n) CK(cudaMemcpyAsync(gap_n, h->gap_n, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (n_iupac_gap) CK(cudaMemcpyAsync(n_iupac_gap, h->iupac_gap_n, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (n_entries) CK(cudaMemcpyAsync(n_entries, h->n_entries, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 
@@ -845,6 +861,7 @@ extern "C" void mpb_hist_free(mpb_hist* h) {
     if (h->win_pos) cudaFreeAsync(h->win_pos, st);
     if (h->gap_n) cudaFreeAsync(h->gap_n, st);
     if (h->iupac_gap_n) cudaFreeAsync(h->iupac_gap_n, st);
+    if (h->n_entries) cudaFreeAsync(h->n_entries, st);
     if (h->exc) cudaFreeAsync(h->exc, st);
     if (h->exc_n) cudaFreeAsync(h->exc_n, st);
     delete h;

@@ -347,7 +347,7 @@ __device__ __forceinline__ uint32_t mpb_hash(uint64_t key, int log2cap) {
 // open addressing, linear probing; count += add, first = min(first, ord)
 __device__ __forceinline__ void mpb_table_add(uint64_t* __restrict__ keys, uint32_t* __restrict__ cnt,
                                               uint64_t* __restrict__ first, int log2cap, uint64_t key, uint32_t add,
-                                              uint64_t ord, int* err) {
+                                              uint64_t ord, int* err, unsigned long long* n_new = nullptr) {
     const uint32_t mask = (1u << log2cap) - 1u;
     uint32_t h = mpb_hash(key, log2cap);
     for (uint32_t probe = 0; probe <= mask; ++probe) {
@@ -355,7 +355,10 @@ __device__ __forceinline__ void mpb_table_add(uint64_t* __restrict__ keys, uint3
         if (cur == MPB_KEY_EMPTY_D) {
             cur = atomicCAS((unsigned long long*)&keys[h], (unsigned long long)MPB_KEY_EMPTY_D,
                             (unsigned long long)key);
-            if (cur == MPB_KEY_EMPTY_D) cur = key;
+            if (cur == MPB_KEY_EMPTY_D) {
+                cur = key;
+                if (n_new) atomicAdd(n_new, 1ull);  // this call claimed the slot: one more distinct entry
+            }
         }
         if (cur == key) {
             atomicAdd(&cnt[h], add);

@@ -213,6 +213,10 @@ class Hist:
             x //= 5
         return g <= self.v
 
+    def counts(self):
+        return (np.array(self.gap_n, np.int64), np.array(self.n_iupac_gap, np.int64),
+                np.array([len(t) for t in self.tables], np.int64))
+
     def stats(self):
         nw = self.nw
         out = dict(gap_n=np.array(self.gap_n, np.int64), ent=np.zeros((nw, 4)), nuniq=np.zeros((nw, 3), np.int64),
