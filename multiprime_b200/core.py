@@ -290,16 +290,26 @@ class NN_degenerate(object):
                 rec = self.comm.allgather_concat(rec.reshape(-1))[0].reshape(-1, 35)
             cache = {}
             if len(rec):
-                uniq, inv = np.unique(rec[:, 2:], axis=0, return_inverse=True)
-                inv = inv.reshape(-1)
-                first = np.full(len(uniq), np.iinfo(np.int64).max, np.int64)
-                count = np.zeros(len(uniq), np.int64)
-                np.minimum.at(first, inv, rec[:, 0])
-                np.add.at(count, inv, rec[:, 1])
-                win = uniq[:, 0]                                      # np.unique sorts rows: windows are contiguous
+                # group by (window, raw k-mer): the k 4-bit cells are folded into two integers, rows sorted, runs reduced
+                cells = rec[:, 3:]
+                lo = np.zeros(len(rec), np.int64)
+                hi = np.zeros(len(rec), np.int64)
+                for j in range(k):
+                    if j < 15:
+                        lo |= cells[:, j] << (4 * j)
+                    else:
+                        hi |= cells[:, j] << (4 * (j - 15))
+                order = np.lexsort((lo, hi, rec[:, 2]))
+                w_s, lo_s, hi_s = rec[order, 2], lo[order], hi[order]
+                new_run = np.ones(len(rec), bool)
+                new_run[1:] = (w_s[1:] != w_s[:-1]) | (lo_s[1:] != lo_s[:-1]) | (hi_s[1:] != hi_s[:-1])
+                starts = np.nonzero(new_run)[0]
+                first = np.minimum.reduceat(rec[order, 0], starts)
+                count = np.add.reduceat(rec[order, 1], starts)
+                win = w_s[starts]
                 cuts = np.nonzero(np.diff(win))[0] + 1
-                for lo, hi in zip(np.concatenate([[0], cuts]), np.concatenate([cuts, [len(win)]])):
-                    cache[int(win[lo])] = list(zip(first[lo:hi].tolist(), count[lo:hi].tolist()))
+                for a, b in zip(np.concatenate([[0], cuts]).tolist(), np.concatenate([cuts, [len(win)]]).tolist()):
+                    cache[int(win[a])] = list(zip(first[a:b].tolist(), count[a:b].tolist()))
             hist._iupac_groups = cache
         return cache.get(wi, [])
 
