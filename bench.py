@@ -83,6 +83,15 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows)}
 
 
+def scan_traffic():
+    """DRAM bytes (read + write) of one k_scan launch from the committed `ncu --set full` capture"""
+    path = os.path.join(ROOT, "profiles", "k_scan_traffic.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return json.load(fh)["traffic_bytes_per_launch"]
+    return None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -276,11 +285,14 @@ def run_b200(args):
                 "setup_ms_per_step": {kk: round(vv / args.steps, 2) for kk, vv in e2e_init.items()}},
         "gpu_launches": int(results["launches"]),
         "roofline": {"bound": "hbm", "kernel": "k_scan", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": scan_traffic(), "peak_source": peak_src,
                      "launches": scan_n, "avg_launch_ms": scan_ms / max(1, scan_n),
                      "evals_in_launches": scan_units,
-                     "note": "achieved = scanned candidate x sequence pairs x %.2f B / event-timed k_scan time" %
-                             BYTES_PER_EVAL},
+                     "note": "achieved = scanned candidate x sequence pairs x %.2f B / event-timed k_scan time; traffic = "
+                             "dram read+write bytes of one launch (ncu --set full, profiles/): far BELOW the algorithmic "
+                             "bytes because a loaded window serves all candidates of its window and neighbouring windows "
+                             "share words through L1/L2 - the kernel is bound by integer issue (ncu: 77%% issue active, "
+                             "2.7%% of peak DRAM throughput)" % BYTES_PER_EVAL},
         "kernels": {"k_hist_ms_per_step": results["hist"][0] / args.steps,
                     "k_scan_ms_per_step": scan_ms / args.steps},
         "host_phases_ms_per_step": results["phases"],
