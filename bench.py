@@ -168,20 +168,21 @@ def run_reference(args):
 
 # ----------------------------------------------------------------------------------------------------------
 def run_b200(args):
-    import torch
-    import torch.distributed as dist
     from multiprime_b200 import core, synth
 
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n_seq, n_col = args.n_seq, args.n_col
+    # synthetic input first: the generator forks worker processes, which must happen before CUDA / NCCL threads exist
     codes = synth.synth_codes_parallel(n_seq, n_col, row0=rank * n_seq, procs=max(1, (os.cpu_count() or 8) // world))
     packed = core.pack4(codes)
     del codes
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     pinned = torch.from_numpy(packed).pin_memory()
     packed_pinned = pinned.numpy()
     ids = synth.seq_ids(n_seq, rank * n_seq)

@@ -89,6 +89,7 @@ def synth_codes_parallel(n_seq: int, n_col: int = 600, seed: int = 20240923, row
     if procs <= 1 or len(jobs) <= 1:
         return synth_codes(n_seq, n_col, seed, row0, **kw)
     out = np.empty((n_seq, n_col), dtype=np.uint8)
+    # (forks: call this before CUDA / NCCL threads exist in the process, as bench.py does)
     with ProcessPoolExecutor(procs) as ex:
         futs = [(a, b, ex.submit(synth_codes, b - a, n_col, seed, a, **kw)) for a, b in jobs]
         for a, b, f in futs:

@@ -19,7 +19,7 @@ def test_scan_and_tables_are_additive_over_sequences():
     from multiprime_b200 import _lib, synth
     from multiprime_b200.iupac import allow_masks, sets_of
     n = 200_000
-    codes = synth.synth_codes_parallel(n, 600, seed=77)
+    codes = synth.synth_codes(n, 600, seed=77)
     cut = 83_111
     ctx = _lib.Context(0)
     parts = [_msa(ctx, codes[:cut]), _msa(ctx, codes[cut:]), _msa(ctx, codes)]
