@@ -13,15 +13,13 @@ import json
 import math
 import sys
 import time
-from fractions import Fraction
 from statistics import mean
 
 import numpy as np
 
 from . import _lib
 from .comm import NoComm
-from .iupac import (BASES, CODE_CHARS, CHAR_CODE, FOLD, allow_masks, comp_set, degeneracy, expand_keys, expand_strings,
-                    n_degenerate, primer_string, rc_sets, sets_of)
+from .iupac import BASES, CODE_CHARS, CHAR_CODE, allow_masks, expand_keys, expand_strings, primer_string, rc_sets
 
 TSV_HEADER = ["Position", "Entropy of cover (bit)", "Entropy of total (bit)", "Optimal_primer",
               "primer_degenerate_number", "nonsense_primer_number", "Optimal_coverage", "Mis-F-coverage",

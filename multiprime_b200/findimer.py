@@ -7,7 +7,6 @@ here with the reference's own float expressions."""
 from __future__ import annotations
 
 import argparse
-import math
 import os
 import time
 from collections import defaultdict

@@ -12,8 +12,6 @@ import re
 import sys
 import time
 
-import numpy as np
-
 from . import _lib
 from .dimer import dg_consts, loss_table
 from .iupac import sets_of

@@ -23,7 +23,7 @@ import numpy as np
 from . import _lib
 from .core import exact_mean, has_hairpin, has_repeat
 from .dimer import dg_consts, loss_table
-from .iupac import CODE_CHARS, FOLD, comp_set, sets_of
+from .iupac import FOLD, sets_of
 
 
 def parseArg(argv=None):
