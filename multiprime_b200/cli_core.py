@@ -40,20 +40,52 @@ def parseArg(argv=None):
     return parser.parse_args(argv)
 
 
+def _shard_setup(args):
+    """Launched under torchrun (RANK / WORLD_SIZE set): every rank parses the alignment, keeps a contiguous block of
+    its rows on its own GPU and joins the process group (NCCL; MPB_DIST_BACKEND=gloo for ranks that share one GPU).
+    Returns the extra keyword arguments for NN_degenerate."""
+    import os
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1:
+        return {"device": args.device}, 0
+    import torch
+    import torch.distributed as dist
+    from .comm import TorchComm
+    from .core import parse_msa
+    rank, local = int(os.environ["RANK"]), int(os.environ.get("LOCAL_RANK", "0"))
+    backend = os.environ.get("MPB_DIST_BACKEND", "nccl")
+    device = local if backend == "nccl" else args.device
+    if backend == "nccl":
+        torch.cuda.set_device(device)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", device))
+    else:
+        dist.init_process_group(backend)
+    ids, codes, lens = parse_msa(args.input)
+    n = len(ids)
+    lo, hi = rank * n // world, (rank + 1) * n // world
+    return {"device": device, "alignment": (ids[lo:hi], codes[lo:hi], lens[lo:hi]), "row0": lo,
+            "comm": TorchComm()}, rank
+
+
 def main(argv=None):
     e1 = time.time()
     args = parseArg(argv)
     from .core import NN_degenerate
+    extra, rank = _shard_setup(args)
     app = NN_degenerate(seq_file=args.input, primer_length=args.plen, coverage=args.fraction,
                         number_of_dege_bases=args.dnum, score_of_dege_bases=args.degeneracy,
                         raw_entropy_threshold=args.entropy, product_len=args.size, position=args.coordinate,
                         variation=args.variation, distance=args.away, GC=args.gc, nproc=args.proc, outfile=args.out,
-                        device=args.device)
+                        **extra)
     app.run()
     app.close()
+    if "comm" in extra:
+        import torch.distributed as dist
+        dist.destroy_process_group()
     e2 = time.time()
-    print("INFO {} Total times: {}".format(time.strftime("%Y-%m-%d %H:%M:%S", time.localtime(time.time())),
-                                           round(float(e2 - e1), 2)))
+    if rank == 0:
+        print("INFO {} Total times: {}".format(time.strftime("%Y-%m-%d %H:%M:%S", time.localtime(time.time())),
+                                               round(float(e2 - e1), 2)))
 
 
 if __name__ == "__main__":

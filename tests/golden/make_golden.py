@@ -62,6 +62,11 @@ CASES = {
                     raw_entropy_threshold=3.6, product_len=100, position="1,2,-1", variation=2, distance=4,
                     GC="0.2,0.7"),
                list(range(45, 65)) + list(range(500, 510))),
+    "c2_k20": ("test_data/1000_fasta.msa",
+               dict(primer_length=20, coverage=0.8, number_of_dege_bases=6, score_of_dege_bases=64,
+                    raw_entropy_threshold=3.6, product_len=100, position="1,2,-1", variation=2, distance=4,
+                    GC="0.2,0.7"),
+               list(range(200, 222)) + list(range(640, 650))),
     "c3_tmsa": ("test_data/results/Clusters_msa/Cluster_0_20727.tmsa",
                 dict(primer_length=18, coverage=0.7, number_of_dege_bases=4, score_of_dege_bases=10,
                      raw_entropy_threshold=3.6, product_len=150, position="2,3,-1", variation=1, distance=4,

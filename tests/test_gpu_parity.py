@@ -7,7 +7,7 @@ from tests.parity import check_case
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("name", ["synth_iupac", "synth300", "c2_k18", "c2_k22", "c3_tmsa", "c1_testfa"])
+@pytest.mark.parametrize("name", ["synth_iupac", "synth300", "c2_k18", "c2_k20", "c2_k22", "c3_tmsa", "c1_testfa"])
 def test_golden_case(name):
     stats = check_case(name)
     assert stats["scan_calls"] > 0

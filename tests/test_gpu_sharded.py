@@ -79,3 +79,27 @@ def test_two_shards_one_gpu(name):
     for rank, start, stop, bad in res:
         assert (start, stop) == (case["start"], case["stop"])
         assert not bad, (rank, bad[:3])
+
+
+def test_cli_under_torchrun(tmp_path):
+    """`torchrun ... scripts/multiPrime-core.py`: two ranks (sharing cuda:0, gloo) write the reference CLI's files"""
+    import json
+    import subprocess
+    import sys
+    from multiprime_b200 import synth
+    from tests.helpers import GOLDEN
+    g = json.load(open(os.path.join(GOLDEN, "cli_core.json")))
+    n, L, seed, gr, ir = g["synth"]
+    fa = tmp_path / "in.fa"
+    synth.write_fasta(str(fa), synth.synth_codes(n, L, seed=seed, gap_rate=gr, iupac_rate=ir))
+    out = tmp_path / "mine.out"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, MPB_DIST_BACKEND="gloo")
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
+                          os.path.join(root, "scripts", "multiPrime-core.py"), "-i", str(fa), "-o", str(out)] + g["args"],
+                         capture_output=True, text=True, env=env, timeout=600)
+    assert res.returncode == 0, res.stderr[-3000:]
+    assert out.read_text() == g["tsv"]
+    assert json.load(open(str(out) + ".non_coverage_seq_id_json")) == g["non_cov"]
+    assert json.load(open(str(out) + ".gap_seq_id_json")) == g["gap"]

@@ -8,7 +8,7 @@ import pytest
 from oracle import mp_oracle as o
 from tests.helpers import GOLDEN, case_alignment, digest, load_case, oracle_params
 
-CASES = ["synth300", "synth_iupac", "c2_k18", "c2_k22", "c3_tmsa", "c1_testfa"]
+CASES = ["synth300", "synth_iupac", "c2_k18", "c2_k20", "c2_k22", "c3_tmsa", "c1_testfa"]
 
 
 @pytest.mark.parametrize("name", CASES)
