@@ -45,6 +45,16 @@ def _worker(rank, world, port, name, limit, q):
         g = got.get(rec["pos"])
         if (g is None) != (rec["row"] is None) or (g is not None and (g["row"] != rec["row"] or g["trace"] != rec["trace"])):
             bad.append((rec["pos"], g and g["row"], rec["row"]))
+    # the JSON side files of a sharded run: shards hold disjoint id lists, merged in rank order (core.run)
+    from tests.helpers import digest
+    non_cov = {r["row"][0]: r["non_cov"] for r in got.values()}
+    gap_ids = {r["row"][0]: r["gap_ids"] for r in got.values()}
+    non_cov, gap_ids = core._merge_sidecars(app.comm.allgather_object((non_cov, gap_ids)))
+    for rec in recs:
+        if rec["row"] is not None and (digest(non_cov[rec["pos"]][0]) != rec["f_non"] or
+                                       digest(non_cov[rec["pos"]][1]) != rec["r_non"] or
+                                       digest(gap_ids[rec["pos"]]) != rec["gap_ids"]):
+            bad.append((rec["pos"], "side files"))
     q.put((rank, app.start_position, app.stop_position, bad, sum(1 for r in recs if r["row"] is not None)))
     dist.destroy_process_group()
 
