@@ -520,6 +520,9 @@ class NN_degenerate(object):
                 a, b = int(starts[r]), int(starts[r + 1])
                 hist.merge(off_r, keys_all[a:b], cnt_all[a:b], first_all[a:b])
         st2 = hist.stats()                                                     # global for the merged windows
+        # the float sums depend on each rank's slot order in the last bits: rank 0's copy is the one every rank uses, so
+        # that all ranks take the same (collective-bearing) decisions even on a rounding edge
+        st2["ent"] = comm.allreduce_sum(st2["ent"] if comm.rank == 0 else np.zeros_like(st2["ent"]))
         st2["gap_n"] = gap_n
         st2["n_iupac_gap"] = iupac_gap
         st2["merged"] = merged
