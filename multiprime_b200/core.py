@@ -411,11 +411,14 @@ class NN_degenerate(object):
             tick[0] = now
 
         # entropy prefilter: windows whose coarse-grained entropy bound is above the gate never get a table
-        s0, s1 = self.msa.prefilter(k, v, positions)
-        bound = (s0 * math.log2(self.n_local) - s1) / N         # shards: size-weighted (concavity of the entropy)
-        if self.comm.world > 1:
-            bound = self.comm.allreduce_sum(bound)
-        keep_pos = bound <= self.entropy_threshold + 0.006
+        if k >= 8:
+            s0, s1 = self.msa.prefilter(k, v, positions)
+            bound = (s0 * math.log2(self.n_local) - s1) / N     # shards: size-weighted (concavity of the entropy)
+            if self.comm.world > 1:
+                bound = self.comm.allreduce_sum(bound)
+            keep_pos = bound <= self.entropy_threshold + 0.006
+        else:                                                    # the coarse view needs 8 cells: keep every window
+            keep_pos = np.ones(len(positions), bool)
         self.stats["prefiltered"] = self.stats.get("prefiltered", 0) + int((~keep_pos).sum())
         positions = [p for p, kp in zip(positions, keep_pos.tolist()) if kp]
         lap("prefilter")
