@@ -74,14 +74,16 @@ def nth_end(sets, e_idx: int, min_end: int = 5, max_end: int = 18) -> str:
 class Dimer(object):
     """finDimer_V4.py:127-146 constructor arguments"""
 
-    def __init__(self, primer_file="", outfile="", threshold=3.96, nproc=10, device=0, ctx=None, comm=None):
+    def __init__(self, primer_file="", outfile="", threshold=3.96, nproc=10, device=0, ctx=None, comm=None,
+                 _backend=None):
         self.nproc = nproc
         self.primers_file = primer_file
         self.threshold = threshold
         self.outfile = os.path.abspath(outfile)
         self.primers = self.parse_primers()
         self.primers_list = list(self.primers.keys())
-        self.ctx = ctx or _lib.Context(device)
+        self._backend = _backend or _lib          # tests inject tests/fake_device.py
+        self.ctx = ctx or self._backend.Context(device)
         self.comm = comm
 
     def parse_primers(self):
@@ -100,7 +102,7 @@ class Dimer(object):
         """all dimer rows in (i, j) order"""
         plist = self.primers_list
         sets_list = [sets_of(p.upper()) for p in plist]
-        eng = _lib.Dimer(self.ctx, sets_list, 5, 18, True, loss_table(self.threshold), dg_consts())
+        eng = self._backend.Dimer(self.ctx, sets_list, 5, 18, True, loss_table(self.threshold), dg_consts())
         n = len(plist)
         rank, world = (self.comm.rank, self.comm.world) if self.comm else (0, 1)
         band = rows_per_band or max(1, min(n, (1 << 24) // max(1, n) * 8))

@@ -51,14 +51,14 @@ def argsParse(argv=None):
 class DimerExaminer:
     """V1.3:193-215 dimer_examination over a fixed universe of primers, held on the device"""
 
-    def __init__(self, ctx, primers):
+    def __init__(self, ctx, primers, _backend=None):
         self.index = {}
         uniq = []
         for p in primers:
             if p not in self.index:
                 self.index[p] = len(uniq)
                 uniq.append(p)
-        self.eng = _lib.Dimer(ctx, [sets_of(p) for p in uniq], 5, -1, True, loss_table(3.0), dg_consts())
+        self.eng = (_backend or _lib).Dimer(ctx, [sets_of(p) for p in uniq], 5, -1, True, loss_table(3.0), dg_consts())
         self.cache = {}
         self.queries = 0
 
@@ -160,8 +160,9 @@ def greedy_primers(primers, step, exam: DimerExaminer, output):
     return rows
 
 
-def main(argv=None):
+def main(argv=None, _backend=None):
     e1 = time.time()
+    backend = _backend or _lib
     options = argsParse(argv)
     if re.search("/", options.input):
         sort_dir = options.input.split("/")
@@ -179,8 +180,8 @@ def main(argv=None):
         while col <= len(row) - step:
             universe.extend(row[col:col + 2])
             col += step
-    ctx = _lib.Context(options.device)
-    exam = DimerExaminer(ctx, universe) if universe else None
+    ctx = backend.Context(options.device)
+    exam = DimerExaminer(ctx, universe, backend) if universe else None
     try:
         if options.method == "T":
             next_candidate = options.out.rstrip(".xls") + ".next.xls"

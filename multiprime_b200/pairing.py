@@ -100,7 +100,7 @@ class Primers_filter(object):
     """get_multiPrime.py:303-321 constructor arguments"""
 
     def __init__(self, ref_file, primer_file, adaptor, rep_seq_number=500, distance=4, outfile="", diff_Tm=5,
-                 size="300,700", position=9, GC="0.4,0.6", nproc=10, fraction=0.6, device=0):
+                 size="300,700", position=9, GC="0.4,0.6", nproc=10, fraction=0.6, device=0, _backend=None):
         self.nproc = nproc
         self.primer_file = primer_file
         self.adaptor = adaptor
@@ -115,7 +115,8 @@ class Primers_filter(object):
         self.number = self.get_number()
         self.position = position
         self.primers, self.gap_id, self.non_cover_id = self.parse_primers()
-        self.ctx = _lib.Context(device)
+        self._backend = _backend or _lib          # tests inject tests/fake_device.py
+        self.ctx = self._backend.Context(device)
         self.pre_filter_primers = self.pre_filter()
 
     def parse_primers(self):
@@ -232,7 +233,7 @@ class Primers_filter(object):
         # F-R dimer check (get_multiPrime.py:419-437) of all pairs in one batch on the GPU
         dimer = np.zeros(len(pairs), bool)
         if pairs:
-            eng = _lib.Dimer(self.ctx, fsets + rsets, 5, 18, False, loss_table(3.6, True), dg_consts())
+            eng = self._backend.Dimer(self.ctx, fsets + rsets, 5, 18, False, loss_table(3.6, True), dg_consts())
             try:
                 idx = np.arange(2 * n, dtype=np.int32)
                 self_hit = eng.pairs(idx, idx)[0] >= 0
@@ -290,12 +291,12 @@ class Primers_filter(object):
         return out
 
 
-def main(argv=None):
+def main(argv=None, _backend=None):
     e1 = time.time()
     args = parseArg(argv)
     app = Primers_filter(ref_file=args.ref, primer_file=args.input, adaptor=args.adaptor, rep_seq_number=args.maxseq,
                          distance=args.dist, outfile=args.out, size=args.size, position=args.end, fraction=args.fraction,
-                         diff_Tm=args.Tm, nproc=args.proc, device=args.device)
+                         diff_Tm=args.Tm, nproc=args.proc, device=args.device, _backend=_backend)
     app.run()
     e2 = time.time()
     print("INFO {} Total times: {}".format(time.strftime("%Y-%m-%d %H:%M:%S", time.localtime(time.time())),

@@ -60,6 +60,9 @@ class Context:
             deg[i], ndeg[i] = o.degeneracy(p), o.n_degenerate(p)
         return tm, gc, flags, deg, ndeg
 
+    def pair_cover(self, uf, ur, pf, pr):
+        return np.array([int(np.unpackbits((uf[a] | ur[b]).view(np.uint8)).sum()) for a, b in zip(pf, pr)], np.int32)
+
     def dimer_flags(self, sets_list):
         return np.array([o.self_dimer("".join(CODE_CHARS[c] for c in s)) for s in sets_list], bool)
 
@@ -311,3 +314,56 @@ def key_string(key: int, k: int) -> str:
         out.append("ACGT-"[x % 5])
         x //= 5
     return "".join(out)
+
+
+class Dimer:
+    """stand-in for _lib.Dimer: literal enumeration of (3' end, expansion) pairs in the reference's order"""
+
+    def __init__(self, ctx, sets_list, min_end, max_end, init_both, loss_table, dg_consts):
+        from oracle import dimer_oracle as dor
+        self.primers = ["".join(CODE_CHARS[c] for c in s) for s in sets_list]
+        self.n = len(self.primers)
+        self.table = loss_table
+        self.init_both = init_both
+        self._dg = dor.delta_g
+        self.ends = []
+        for p in self.primers:
+            k = len(p)
+            top = min(max_end, k) if max_end > 0 else k + max_end
+            lst = []
+            for L in range(top, min_end - 1, -1):
+                lst.extend(o.expand(p[k - L:]))
+            self.ends.append(lst)
+        self.exps = [o.expand(p) for p in self.primers]
+        self.off_p = np.concatenate([[0], np.cumsum([len(e) for e in self.exps])]).astype(np.int64)
+        self.off_e = np.concatenate([[0], np.cumsum([len(e) for e in self.ends])]).astype(np.int64)
+
+    def _first(self, i, j):
+        n_p = len(self.exps[j])
+        for ei, end in enumerate(self.ends[i]):
+            target = o.rc(end)
+            gc = end.count("G") + end.count("C")
+            for pi, p in enumerate(self.exps[j]):
+                idx = p.find(target)
+                if idx >= 0:
+                    d2 = len(p) - len(end) - idx
+                    if self.table[len(end), gc, d2] or (d2 == 0 and self._dg(end, self.init_both) < -5):
+                        return ei * n_p + pi, d2
+        return -1, -1
+
+    def pairs(self, pi, pj):
+        res = [self._first(int(a), int(b)) for a, b in zip(pi, pj)]
+        return np.array([r[0] for r in res], np.int64), np.array([r[1] for r in res], np.int32)
+
+    def grid(self, row0, row1, max_hits=1 << 22):
+        out = []
+        for i in range(row0, row1):
+            for j in range(i, self.n):
+                h, d2 = self._first(i, j)
+                if h >= 0:
+                    out.append((i, j, h, d2))
+        a = np.array(out, np.int64).reshape(-1, 4)
+        return a[:, 0].astype(np.int32), a[:, 1].astype(np.int32), a[:, 2], a[:, 3].astype(np.int32), 0
+
+    def close(self):
+        pass
