@@ -296,7 +296,7 @@ def run_b200(args):
                     "k_scan_ms_per_step": scan_ms / args.steps},
         "host_phases_ms_per_step": results["phases"],
     }
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:       # the CPU baseline is timed on rank 0 at N = 1 only
         evc, dtc = cpu_sample(args.cpu_sample_seqs, n_col, args.cpu_sample_windows, 1)
         line["cpu_baseline"] = {"value": evc / dtc, "unit": "evals/s", "cores": 1, "kind": "port",
                                 "sample": "oracle/mp_oracle.py, first %d synthetic sequences x %d windows, %.1f s" %
