@@ -196,6 +196,15 @@ int mpb_walk(int k, int v, int dnum, int degeneracy, uint32_t fmask, uint32_t rm
 int mpb_primer_props(mpb_ctx* ctx, const uint8_t* sets, int k, int32_t n, double gc_lo, double gc_hi, int distance,
                      const double* tm_consts3, double* tm_avg, double* gc, int32_t* flags, int32_t* deg, int32_t* ndeg);
 
+/* The reference's raw k-mer of (sequence, window) pairs — window cut, terminal-gap patching and the left extension of
+ * a short row, core:666-687 — read from the HOST copy of the alignment (nibble-packed rows as mpb_msa_upload takes them:
+ * cell c of a row = (row[c / 2] >> 4 * (c & 1)) & 15; lens NULL = every row n_col cells).  Pure host code, no context:
+ * used for the handful of gap rows holding IUPAC cells, which the device tables do not store (mpb_hist_exceptions).
+ * cells[n*32]: 4-bit base sets of the k-mer, zero padded; out_len[n]: its length (< k when the row cannot supply k
+ * cells). */
+int mpb_window_cells(const uint8_t* packed, int64_t row_stride, const int32_t* lens, int32_t n_col, int k, int64_t n,
+                     const int64_t* seq, const int32_t* pos, uint8_t* cells, int32_t* out_len);
+
 /* ---- pair coverage: get_multiPrime.py:560-569 ---------------------------------------------------------------------
  * uf / ur [n_rows*words]: per-candidate bit vectors of the sequences the forward / reverse use of that candidate leaves
  * uncovered (gap rows included), in mpb_scan's bit layout.  uncovered[q] = popcount(uf[pf[q]] | ur[pr[q]]). */

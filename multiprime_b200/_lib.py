@@ -54,6 +54,7 @@ SIGNATURES = {
                            _P, _P, _P, _P, _P, _P, C.c_int64, _P, _P, _P]),
     "mpb_primer_props": (C.c_int, [_P, _P, C.c_int, C.c_int32, C.c_double, C.c_double, C.c_int, _P, _P, _P, _P, _P,
                                    _P]),
+    "mpb_window_cells": (C.c_int, [_P, C.c_int64, _P, C.c_int32, C.c_int, C.c_int64, _P, _P, _P, _P]),
     "mpb_pair_cover": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P, _P, C.c_int64, _P]),
     "mpb_dimer_prepare": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int, C.c_int, C.c_int, _P, _P, C.POINTER(_P)]),
     "mpb_dimer_free": (None, [_P]),
@@ -107,6 +108,24 @@ def ptr(x):
     if hasattr(x, "data_ptr"):
         return C.c_void_p(x.data_ptr())
     return C.c_void_p(int(x))
+
+
+def window_cells(packed4: np.ndarray, lens, n_col: int, k: int, seq, pos):
+    """mpb_window_cells: raw k-mers (core:666-687) of (sequence, window) pairs from the host copy of the alignment
+    -> (cells uint8[n, 32], length int32[n]).  Pure host code."""
+    assert packed4.dtype == np.uint8 and packed4.flags.c_contiguous and packed4.ndim == 2
+    seq = np.ascontiguousarray(seq, dtype=np.int64)
+    pos = np.ascontiguousarray(pos, dtype=np.int32)
+    lens = None if lens is None else np.ascontiguousarray(lens, dtype=np.int32)
+    n = len(seq)
+    cells = np.zeros((n, 32), np.uint8)
+    out_len = np.zeros(n, np.int32)
+    if n:
+        if seq.min() < 0 or seq.max() >= packed4.shape[0]:
+            raise IndexError("sequence index outside the alignment")
+        check(load().mpb_window_cells(ptr(packed4), packed4.shape[1], ptr(lens), n_col, k, n, ptr(seq), ptr(pos),
+                                      ptr(cells), ptr(out_len)))
+    return cells, out_len
 
 
 def walk(k, v, dnum, degeneracy, fmask, rmask, win_pos, cover_number, freq, nn, mm_key, scan_fn):

@@ -281,9 +281,16 @@ class NN_degenerate(object):
             k = self.primer_length
             exc_w, exc_s = self._exceptions(hist)
             rec = np.zeros((len(exc_w), 3 + 32), np.int64)          # first, count, window, raw cells
-            for i, (w, s) in enumerate(zip(exc_w.tolist(), exc_s.tolist())):
-                rec[i, 0], rec[i, 1], rec[i, 2] = (self.row0 + s) << 16, 1, w
-                rec[i, 3:3 + k] = list(self._window_cells(s, hist.win_pos[w]))
+            if len(exc_w):
+                exc_pos = np.asarray(hist.win_pos)[exc_w]
+                cells, got = _lib.window_cells(self._packed4, self.lens, self.n_col, k, exc_s, exc_pos)
+                if (got < k).any():
+                    raise ValueError("a sequence is too short to supply a %d-mer at window %d"
+                                     % (k, int(exc_pos[np.argmax(got < k)])))
+                rec[:, 0] = (self.row0 + exc_s.astype(np.int64)) << 16
+                rec[:, 1] = 1
+                rec[:, 2] = exc_w
+                rec[:, 3:] = cells
             if self.comm.world > 1:                                  # shards exchange their records as plain arrays
                 rec = self.comm.allgather_concat(rec.reshape(-1))[0].reshape(-1, 35)
             cache = {}

@@ -484,6 +484,63 @@ bool has_hairpin(const uint8_t* sets, int k, int distance) {
 
 }  // namespace
 
+// core:666-687 on the host copy of the alignment (the device restatement is mpb_window_slow in mpb_device.cuh)
+extern "C" int mpb_window_cells(const uint8_t* packed, int64_t row_stride, const int32_t* lens, int32_t n_col, int k,
+                                int64_t n, const int64_t* seq, const int32_t* pos, uint8_t* cells, int32_t* out_len) {
+    if (!packed || !seq || !pos || !cells || !out_len) return mpb_fail(MPB_EINVAL, "NULL argument");
+    if (k < 1 || k > 32 || n < 0 || n_col < 0 || row_stride * 2 < n_col) return mpb_fail(MPB_EINVAL, "bad k, n or stride");
+    for (int64_t i = 0; i < n; ++i) {
+        const uint8_t* row = packed + seq[i] * row_stride;
+        const int len = lens ? lens[seq[i]] : n_col;
+        const int p = pos[i];
+        if (p < 0 || len < 0 || len > n_col) return mpb_fail(MPB_EINVAL, "window %lld outside the row", (long long)i);
+        auto cell = [&](int c) { return (row[c >> 1] >> (4 * (c & 1))) & 15; };
+        uint8_t w[32], buf[32];
+        int m = std::min(std::max(len - p, 0), k);  // cells the row holds inside the window
+        bool allgap = true;
+        for (int j = 0; j < m; ++j) {
+            w[j] = (uint8_t)cell(p + j);
+            allgap = allgap && w[j] == 0;
+        }
+        const int left_end = std::min(p, len);
+        auto bases_left = [&](int g) {  // the last g bases left of the window, nearest first, into buf
+            int got = 0;
+            for (int c = left_end - 1; c >= 0 && got < g; --c)
+                if (cell(c)) buf[got++] = (uint8_t)cell(c);
+            return got == g;
+        };
+        if (!(m == k && allgap)) {
+            if (m > 0 && w[0] == 0) {  // leading gap run
+                int g = 0;
+                while (g < m && w[g] == 0) ++g;
+                if (bases_left(g))
+                    for (int j = 0; j < g; ++j) w[j] = buf[g - 1 - j];
+            }
+            if (m > 0 && w[m - 1] == 0) {  // trailing gap run
+                int g = 0;
+                while (g < m && w[m - 1 - g] == 0) ++g;
+                int got = 0;
+                for (int c = p + k; c < len && got < g; ++c)
+                    if (cell(c)) buf[got++] = (uint8_t)cell(c);
+                if (got == g)
+                    for (int j = 0; j < g; ++j) w[m - g + j] = buf[j];
+            }
+        }
+        if (m < k) {  // row ends inside the window: extend to the left
+            const int g = k - m;
+            if (bases_left(g)) {
+                for (int j = m - 1; j >= 0; --j) w[j + g] = w[j];
+                for (int j = 0; j < g; ++j) w[j] = buf[g - 1 - j];
+                m = k;
+            }
+        }
+        uint8_t* o = cells + i * 32;
+        for (int j = 0; j < 32; ++j) o[j] = j < m ? w[j] : 0;
+        out_len[i] = m;
+    }
+    return 0;
+}
+
 // flags: 1 GC out of range, 2 di-nucleotide repeat, 4 hairpin, 64 Tm mean needs the exact host replay,
 // 128 GC mean needs the exact host replay (a rounding tie could not be excluded in double arithmetic)
 extern "C" int mpb_primer_props(mpb_ctx* ctx, const uint8_t* sets, int k, int32_t n, double gc_lo, double gc_hi,
