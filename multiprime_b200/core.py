@@ -585,7 +585,9 @@ class NN_degenerate(object):
         sets_list = [row[:k].tolist() for row in sets_arr]
         wis = np.array([a[0] for a in keep], np.int32)
         pos = np.array([a[1] for a in keep], np.int32)
-        allow = np.array([allow_masks(s) for s in sets_list], np.uint32)
+        place = np.uint32(1) << np.arange(k, dtype=np.uint32)            # allow_masks() of every primer at once
+        allow = np.stack([(((sets_arr[:, :k] >> b) & 1).astype(np.uint32) * place).sum(axis=1, dtype=np.uint32)
+                          for b in range(4)], axis=1)
         # perfect coverage of the chosen primer is already known from the walk (the last candidate scanned for the
         # track IS the final primer); a final scan pass is only needed for the per-sequence non-cover bits
         bits = None

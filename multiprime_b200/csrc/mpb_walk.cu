@@ -561,21 +561,35 @@ extern "C" int mpb_primer_props(mpb_ctx* ctx, const uint8_t* sets, int k, int32_
     }
     std::vector<uint8_t> seqs((size_t)off[n] * k);
     for (int i = 0; i < n; ++i) {
+        // odometer over the positions, rightmost fastest: each expansion is its predecessor with a changed suffix
         const uint8_t* S = sets + (int64_t)i * 32;
         const int64_t d = off[i + 1] - off[i];
-        for (int64_t e = 0; e < d; ++e) {
-            int64_t r = e;
-            uint8_t* q = &seqs[(size_t)(off[i] + e) * k];
+        int digit[32];
+        uint8_t* q = &seqs[(size_t)off[i] * k];
+        for (int p = 0; p < k; ++p) {
+            digit[p] = 0;
+            q[p] = (uint8_t)ORD[S[p] & 15][0];
+        }
+        for (int64_t e = 1; e < d; ++e) {
+            uint8_t* nx = q + k;
+            memcpy(nx, q, (size_t)k);
             for (int p = k - 1; p >= 0; --p) {
-                const int f = FOLD[S[p] & 15];
-                q[p] = (uint8_t)ORD[S[p] & 15][r % f];
-                r /= f;
+                const int code = S[p] & 15;
+                if (++digit[p] < FOLD[code]) {
+                    nx[p] = (uint8_t)ORD[code][digit[p]];
+                    break;
+                }
+                digit[p] = 0;
+                nx[p] = (uint8_t)ORD[code][0];
             }
+            q = nx;
         }
     }
     std::vector<double> tm(off[n]);
     int rc = mpb_tm(ctx, seqs.data(), k, off[n], tm_consts3, tm.data(), nullptr, nullptr);
     if (rc) return rc;
+    double gc_frac[33];  // round(g / k, 3) of core:405 for every possible G/C count
+    for (int g = 0; g <= k; ++g) gc_frac[g] = round3((double)g / (double)k);
     for (int i = 0; i < n; ++i) {
         const uint8_t* S = sets + (int64_t)i * 32;
         int fl = 0;
@@ -590,21 +604,17 @@ extern "C" int mpb_primer_props(mpb_ctx* ctx, const uint8_t* sets, int k, int32_
         }
         // GC: mean over expansions of round(gc/len, 3), rounded to 2 (core:401-407), via the GC-count distribution
         {
-            std::vector<long double> dist(1, 1.0L);
+            uint64_t dist[34] = {1};  // dist[g]: expansions of the prefix with g G/C bases (< 4^27: exact)
             for (int p = 0; p < k; ++p) {
                 const int s = S[p] & 15;
-                const int n_gc = ((s >> 1) & 1) + ((s >> 2) & 1), n_at = (s & 1) + ((s >> 3) & 1);
-                std::vector<long double> nw(dist.size() + 1, 0.0L);
-                for (size_t g = 0; g < dist.size(); ++g) {
-                    nw[g] += dist[g] * n_at;
-                    nw[g + 1] += dist[g] * n_gc;
-                }
-                dist.swap(nw);
+                const uint64_t n_gc = ((s >> 1) & 1) + ((s >> 2) & 1), n_at = (s & 1) + ((s >> 3) & 1);
+                for (int g = p + 1; g >= 1; --g) dist[g] = dist[g] * n_at + dist[g - 1] * n_gc;
+                dist[0] *= n_at;
             }
             long double tot = 0.0L, acc = 0.0L;
-            for (size_t g = 0; g < dist.size(); ++g) {
-                tot += dist[g];
-                if (dist[g] > 0) acc += dist[g] * (long double)round3((double)g / (double)k);
+            for (int g = 0; g <= k; ++g) {
+                tot += (long double)dist[g];
+                if (dist[g] > 0) acc += (long double)dist[g] * (long double)gc_frac[g];
             }
             const double m = (double)(acc / tot);
             if (near_tie2(m)) fl |= 128;
