@@ -80,8 +80,8 @@ int mpb_msa_set_row0(mpb_msa* msa, int64_t row0);
 int mpb_seq_attr(mpb_msa* msa, int32_t* lead_gaps_hd, int32_t* rstrip_len_hd);
 
 /* Entropy prefilter.  For every window: s0 = number of items the reference's total entropy runs over (expansions of
- * cover rows + gap rows), s1 = sum(c log2 c) over a 65536-bin coarsening of their k-mers (2-bit bases of the first 8
- * cells).  (s0 log2 N - s1) / N is a LOWER bound of "Entropy of total" (core:602-614) because merging categories
+ * cover rows + gap rows), s1 = sum(c log2 c) over a 65536-bin coarsening of their k-mers (a 16-bit hash of the 2-bit
+ * bases of all cells).  (s0 log2 N - s1) / N is a LOWER bound of "Entropy of total" (core:602-614) because merging categories
  * cannot raise sum(-p log p); a window whose bound exceeds the gate can be dropped without building its table. */
 int mpb_window_prefilter(mpb_msa* msa, int k, int v, const int32_t* win_pos, int32_t nw, double* s0_hd, double* s1_hd);
 

@@ -424,7 +424,7 @@ class NN_degenerate(object):
             if self.comm.world > 1:
                 bound = self.comm.allreduce_sum(bound)
             keep_pos = bound <= self.entropy_threshold + 0.006
-        else:                                                    # the coarse view needs 8 cells: keep every window
+        else:                                                    # very short primers: keep every window
             keep_pos = np.ones(len(positions), bool)
         self.stats["prefiltered"] = self.stats.get("prefiltered", 0) + int((~keep_pos).sum())
         positions = [p for p, kp in zip(positions, keep_pos.tolist()) if kp]

@@ -577,12 +577,16 @@ k_hist(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq, const int32_
 // entropy prefilter: a lower bound of a window's total entropy from a coarse view of its k-mers
 // ------------------------------------------------------------------------------------------------------
 // Every item the reference counts for tBit (each expansion of a cover row, each gap row; core:602-614) is mapped to a
-// 16-bit code: the 2-bit bases of its first 8 cells (a gap cell, or the lowest base of an IUPAC cell of a gap row,
-// counts as that base).  Merging categories can only lower sum(-p log p) (f(a+b) <= f(a)+f(b) for f = -x log x), so
-// the entropy of the 65536 bins is a lower bound of tBit: windows whose bound is above the gate never need a table.
+// 16-bit code: a hash of the 2-bit bases of ALL its cells (a gap cell, or the lowest base of an IUPAC cell of a gap
+// row, counts as that base).  The code is a function of the item's identity, so the bins merge categories, and merging
+// can only lower sum(-p log p) (f(a+b) <= f(a)+f(b) for f = -x log x): the entropy of the 65536 bins is a lower bound
+// of tBit, and windows whose bound is above the gate never need a table.  Hashing the whole window (instead of
+// projecting onto a few cells) keeps the bound tight for windows that are only partly variable: on the synthetic
+// workload it lets through exactly the windows the exact gate accepts.
 #define PRE_BINS 65536
 __device__ __forceinline__ uint32_t pre_code(uint32_t c, uint32_t g, uint32_t t) {
-    return ((c | t) & 0xFFu) | (((g | t) & 0xFFu) << 8);
+    const uint32_t lo = c | t, hi = g | t;  // bit j of (lo, hi) = base of cell j as 2 bits (A=00 C=01 G=10 T=11)
+    return ((lo ^ (hi << 7) ^ (hi >> 9)) * 0x9E3779B1u) >> 16;
 }
 
 __device__ __forceinline__ void pre_stage(unsigned long long* s_key, unsigned int* s_cnt, unsigned int* bins,

@@ -96,7 +96,7 @@ class Msa:
         return lead, rstrip
 
     def prefilter(self, k, v, win_pos):
-        """coarse 16-bit view of every counted item (mpb_window_prefilter)"""
+        """coarse 16-bit view (a hash of the whole item) of every counted item (mpb_window_prefilter)"""
         s0, s1 = np.zeros(len(win_pos)), np.zeros(len(win_pos))
         low = {c: ("A" if i & 1 else "C" if i & 2 else "G" if i & 4 else "T") for i, c in enumerate(CODE_CHARS) if i}
         low["-"] = "A"
@@ -106,7 +106,11 @@ class Msa:
                 w = o.window_kmer(s, int(p), k)
                 items = ["".join(low[ch] for ch in w)] if w.count("-") > v else [e.replace("-", "A") for e in o.expand(w)]
                 for it in items:
-                    bins[it[:8]] = bins.get(it[:8], 0) + 1
+                    lo = sum(1 << j for j, ch in enumerate(it) if ch in "CT")       # pre_code() of mpb200.cu
+                    hi = sum(1 << j for j, ch in enumerate(it) if ch in "GT")
+                    x = (lo ^ ((hi << 7) & 0xFFFFFFFF) ^ (hi >> 9)) & 0xFFFFFFFF
+                    code = ((x * 0x9E3779B1) & 0xFFFFFFFF) >> 16
+                    bins[code] = bins.get(code, 0) + 1
             cs = np.array(list(bins.values()), float)
             s0[wi], s1[wi] = cs.sum(), (cs * np.log2(cs)).sum()
         return s0, s1
