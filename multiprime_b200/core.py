@@ -393,6 +393,19 @@ class NN_degenerate(object):
                 w = left[len(left) - g:] + w
         return w
 
+    def _table_log2cap(self, k: int) -> int:
+        """log2 of the slots per haplotype table, 0 = the library default (two slots per sequence).
+        The windows that reach the tables passed the prefilter: the entropy of their 65536 coarse bins is at most the
+        gate, so a fraction x of items that are (nearly) alone in their bin costs x * (16 + log2(1/x)) bits and x stays
+        below thr / 16-ish (0.2 for the default 3.6 bits) — distinct haplotypes are a fifth of the sequences at most,
+        in practice far fewer.  Tables of N / 2 slots (load <= 0.4) are a quarter of the default: every table reader
+        walks a quarter of the slots.  A table that fills up anyway reports MPB_EOVERFLOW and the batch is rebuilt
+        with doubled tables (_lib.Hist)."""
+        n = self.total_sequence_number                # merged tables hold the haplotypes of all shards
+        if k < 8 or n < (1 << 17) or self.entropy_threshold > 4.0:
+            return 0
+        return max(10, int(math.ceil(math.log2(n / 2))))
+
     # -- the window pipeline --------------------------------------------------------------------------------
     def design(self, positions):
         """Run the per-window algorithm (core:651-858) for the given window start columns.
@@ -431,7 +444,7 @@ class NN_degenerate(object):
         lap("prefilter")
         if not positions:
             return []
-        with self.msa.hist(k, v, positions) as hist:
+        with self.msa.hist(k, v, positions, self._table_log2cap(k)) as hist:
             lap("hist_build")
             if self.comm.world > 1:
                 st = self._merge_shards(hist)

@@ -349,8 +349,9 @@ __device__ __forceinline__ void mpb_table_add(uint64_t* __restrict__ keys, uint3
                                               uint64_t* __restrict__ first, int log2cap, uint64_t key, uint32_t add,
                                               uint64_t ord, int* err, unsigned long long* n_new = nullptr) {
     const uint32_t mask = (1u << log2cap) - 1u;
+    const uint32_t last_probe = mask < 8191u ? mask : 8191u;  // a run this long means the table is as good as full
     uint32_t h = mpb_hash(key, log2cap);
-    for (uint32_t probe = 0; probe <= mask; ++probe) {
+    for (uint32_t probe = 0; probe <= last_probe; ++probe) {
         uint64_t cur = *((volatile uint64_t*)&keys[h]);
         if (cur == MPB_KEY_EMPTY_D) {
             cur = atomicCAS((unsigned long long*)&keys[h], (unsigned long long)MPB_KEY_EMPTY_D,
