@@ -136,9 +136,12 @@ __device__ __forceinline__ int find_leftmost(uint64_t p, int kj, uint64_t rc, in
     return -1;
 }
 
-// block per pair: first hit (in reference order) among ends(i) x expansions(j)
+// block per pair: first hit (in reference order) among ends(i) x expansions(j).  Any block size works (the order
+// index decides, not the thread): 128 threads when there are many pairs, 512 when a few pairs of highly degenerate
+// primers (the self-dimer gate of the window pipeline) would otherwise leave most of the GPU idle.
 #define PAIR_THREADS 128
-__global__ void __launch_bounds__(PAIR_THREADS)
+#define PAIR_THREADS_WIDE 512
+__global__ void __launch_bounds__(PAIR_THREADS_WIDE)
 k_dimer_pairs(const int32_t* __restrict__ pi, const int32_t* __restrict__ pj, const int32_t* __restrict__ lens,
               const int64_t* __restrict__ off_p, const int64_t* __restrict__ off_e, const uint64_t* __restrict__ exp,
               const uint64_t* __restrict__ end_rc, const uint32_t* __restrict__ end_info,
@@ -155,7 +158,7 @@ k_dimer_pairs(const int32_t* __restrict__ pi, const int32_t* __restrict__ pj, co
         best_d2 = -1;
     }
     __syncthreads();
-    for (unsigned long long base = 0; base < total; base += PAIR_THREADS) {
+    for (unsigned long long base = 0; base < total; base += blockDim.x) {
         const unsigned long long idx = base + threadIdx.x;
         if (idx < total) {
             const int64_t e = (int64_t)(idx / (unsigned long long)np), p = (int64_t)(idx % (unsigned long long)np);
@@ -177,7 +180,7 @@ k_dimer_pairs(const int32_t* __restrict__ pi, const int32_t* __restrict__ pj, co
     __syncthreads();
     if (best != ~0ull) {
         const unsigned long long idx = best;
-        if ((idx % PAIR_THREADS) == threadIdx.x) {
+        if ((idx % blockDim.x) == threadIdx.x) {
             const int64_t e = (int64_t)(idx / (unsigned long long)np), p = (int64_t)(idx % (unsigned long long)np);
             const int L = end_info[off_e[i] + e] & 255;
             best_d2 = kj - L - find_leftmost(exp[off_p[j] + p], kj, end_rc[off_e[i] + e], L);
@@ -305,7 +308,8 @@ extern "C" int mpb_dimer_pairs(mpb_dimer* d, const int32_t* pi, const int32_t* p
     MPB_CK(cudaMallocAsync(&dfh, n_pairs * 8, st));
     MPB_CK(cudaMemcpyAsync(dpi, pi, n_pairs * 4, cudaMemcpyHostToDevice, st));
     MPB_CK(cudaMemcpyAsync(dpj, pj, n_pairs * 4, cudaMemcpyHostToDevice, st));
-    MPB_LAUNCH(ctx, k_dimer_pairs, (unsigned)n_pairs, PAIR_THREADS, 0, dpi, dpj, d->lens, d->off_p, d->off_e, d->exp,
+    const int pair_threads = n_pairs < 4ll * mpb_ctx_sms(ctx) ? PAIR_THREADS_WIDE : PAIR_THREADS;
+    MPB_LAUNCH(ctx, k_dimer_pairs, (unsigned)n_pairs, pair_threads, 0, dpi, dpj, d->lens, d->off_p, d->off_e, d->exp,
                d->end_rc, d->end_info, d->table, dfh, dd2);
     MPB_CK(cudaMemcpyAsync(first_hit, dfh, n_pairs * 8, cudaMemcpyDeviceToHost, st));
     if (hit_d2) MPB_CK(cudaMemcpyAsync(hit_d2, dd2, n_pairs * 4, cudaMemcpyDeviceToHost, st));
