@@ -127,3 +127,31 @@ def test_single_sequence_alignment():
         p = r["row"][0]
         assert r["row"][3] == seq[p:p + 18] and r["row"][6] == 1 and r["row"][1] == -0.0
     app.close()
+
+
+def test_small_tables_overflow_and_are_rebuilt():
+    """a table with too few slots reports MPB_EOVERFLOW (probe runs are bounded) and _lib.Hist rebuilds the batch with
+    doubled tables until it fits: the statistics equal those of the default-sized tables"""
+    from multiprime_b200 import _lib, synth
+    codes = synth.synth_codes(3000, 200, seed=9, gap_rate=0.004, iupac_rate=0.001)
+    ctx = _lib.Context(0)
+    m = _msa(ctx, codes)
+    pos = [0, 30, 75, 120, 150]                      # conserved and variable blocks
+    with m.hist(K, V, pos) as h0:
+        want = h0.stats()
+        want_t = h0.tensors(np.ones(len(pos), np.uint8))
+    assert want["nuniq"][:, :2].sum(axis=1).max() > 256          # some window cannot fit 2^7 slots
+    with pytest.raises(_lib.MpbError) as info:                   # the C ABI itself reports the overflow ...
+        h = _lib.C.c_void_p()
+        wp = np.array(pos, np.int32)
+        _lib.check(_lib.load().mpb_hist_build(m.h, K, V, _lib.ptr(wp), len(pos), 7, _lib.C.byref(h)))
+    assert info.value.code == -4
+    with m.hist(K, V, pos, 7) as h1:                             # ... and the binding grows the tables
+        got = h1.stats()
+        got_t = h1.tensors(np.ones(len(pos), np.uint8))
+    for key in ("gap_n", "nuniq", "mm_key", "mm_cnt", "mm_first", "n_iupac_gap"):
+        assert (got[key] == want[key]).all(), key
+    assert np.allclose(got["ent"], want["ent"], rtol=1e-12, atol=1e-9)
+    assert (got_t[0] == want_t[0]).all() and (got_t[1] == want_t[1]).all()
+    m.close()
+    ctx.close()
