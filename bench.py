@@ -193,7 +193,8 @@ def run_b200(args):
 
     def make_app():
         return core.NN_degenerate(seq_file=None, outfile="", packed=(ids, packed_pinned, n_col, None), device=local,
-                                  sidecars=False, stream=stream, comm=comm, row0=rank * n_seq, **PARAMS)
+                                  sidecars=False, want_trace=False, keep_bits=True, stream=stream, comm=comm,
+                                  row0=rank * n_seq, **PARAMS)
 
     def barrier():
         if world > 1:
@@ -248,7 +249,11 @@ def run_b200(args):
         if name == "value":
             sampler.stop_flag.set()
             results["launches"] = app.ctx.launches - launches0
-            results["scan"] = app.ctx.profile_read("k_scan")
+            results["scan"] = app.ctx.profile_read("k_cscan")
+            results["kernel_ms"] = {kn: app.ctx.profile_read(kn)[0] / args.steps for kn in
+                                    ("k_prefilter", "k_prefilter_sums", "k_hist", "k_hist_summary", "k_hist_match",
+                                     "k_cscan", "k_cscan_plan", "k_cscan_special", "k_walk_advance", "k_walk_seed",
+                                     "k_tm", "k_dimer_pairs", "k_dimer_expand", "k_dimer_ends")}
             results["hist"] = app.ctx.profile_read("k_hist")
             results["evals_per_step"] = app.stats["evals"] / args.steps
             results["scan_calls"] = app.stats["scan_calls"] / args.steps
@@ -283,7 +288,7 @@ def run_b200(args):
                 "d2h_bytes_per_step": int(results["value"]["rows"] * 120), "ms_per_step": e2e_ms,
                 "setup_ms_per_step": {kk: round(vv / args.steps, 2) for kk, vv in e2e_init.items()}},
         "gpu_launches": int(results["launches"]),
-        "roofline": {"bound": "hbm", "kernel": "k_scan", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "k_cscan", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": scan_traffic(), "peak_source": peak_src,
                      "launches": scan_n, "avg_launch_ms": scan_ms / max(1, scan_n),
                      "evals_in_launches": scan_units,
@@ -293,7 +298,8 @@ def run_b200(args):
                              "share words through L1/L2 - the kernel is bound by integer issue (ncu: 77%% issue active, "
                              "2.7%% of peak DRAM throughput)" % BYTES_PER_EVAL},
         "kernels": {"k_hist_ms_per_step": results["hist"][0] / args.steps,
-                    "k_scan_ms_per_step": scan_ms / args.steps},
+                    "k_scan_ms_per_step": scan_ms / args.steps,
+                    "ms_per_step": {kk: round(vv, 3) for kk, vv in results["kernel_ms"].items()}},
         "host_phases_ms_per_step": results["phases"],
     }
     if not args.no_cpu_baseline and world == 1:       # the CPU baseline is timed on rank 0 at N = 1 only

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MPB_ABI_VERSION 1
+#define MPB_ABI_VERSION 2
 #define MPB_MAX_K 27
 #define MPB_MAX_EXPANSIONS 65536 /* expansions of one k-mer window of one sequence */
 
@@ -53,6 +53,8 @@ int mpb_ctx_set_stream(mpb_ctx* ctx, void* cuda_stream);
 int mpb_ctx_sync(mpb_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py's "gpu_launches") */
 int64_t mpb_ctx_launches(mpb_ctx* ctx);
+/* copy between host / device memory on the context's stream; returns after the copy has completed */
+int mpb_ctx_memcpy(mpb_ctx* ctx, void* dst, const void* src, int64_t bytes);
 
 /* Profiling: when enabled every kernel launch is bracketed by CUDA events on the context's stream.
  * mpb_ctx_profile_read sums duration (ms), launch count and algorithmic work units (candidate x sequence
@@ -97,6 +99,12 @@ int mpb_seq_attr_hist(mpb_msa* msa, int64_t* lead_hist_hd, int64_t* rstrip_hist_
 int mpb_hist_build(mpb_msa* msa, int k, int v, const int32_t* win_pos, int32_t nw, int log2_cap, mpb_hist** out);
 void mpb_hist_free(mpb_hist* h);
 
+/* The same tables, empty: the OWNER tables of a sequence-sharded run hold the windows one rank owns and
+ * are filled with the entries of every shard through mpb_hist_merge; gap-row counters come in through
+ * mpb_hist_add_counts (host arrays of nw, already summed over the shards). */
+int mpb_hist_create_empty(mpb_msa* msa, int k, int v, const int32_t* win_pos, int32_t nw, int log2_cap, mpb_hist** out);
+int mpb_hist_add_counts(mpb_hist* h, const int64_t* gap_n, const int64_t* n_iupac_gap);
+
 /* Counters kept while building (host arrays of nw, any may be NULL): gap rows, gap rows holding IUPAC cells, distinct
  * table entries — what a sequence shard needs to size mpb_hist_export without a pass over its tables. */
 int mpb_hist_counts(mpb_hist* h, int64_t* gap_n, int64_t* n_iupac_gap, int64_t* n_entries);
@@ -111,7 +119,17 @@ int mpb_hist_export(mpb_hist* h, const uint8_t* sel, const int64_t* win_off, uin
 int mpb_hist_merge(mpb_hist* h, const int64_t* win_off, const uint64_t* keys_hd, const uint32_t* cnt_hd,
                    const uint64_t* first_hd);
 
-/* Per-window summary (all outputs hd, any may be NULL):
+/* One pass over the occupied slots of every window: mpb_hist_stats and mpb_hist_tensors together (HOST outputs, any
+ * may be NULL; freq / nn for ALL windows of the batch).  The tensors also stay on the device for mpb_walk_dev_begin. */
+int mpb_hist_summary(mpb_hist* h, int64_t* gap_n, double* ent, int64_t* nuniq, uint64_t* mm_key, int64_t* mm_cnt,
+                     uint64_t* mm_first, int64_t* n_iupac_gap, int64_t* freq, int64_t* nn);
+
+/* The same with n_seg = m * nw segments (seg_off[n_seg + 1], host): segment s belongs to window s % nw — what an owner
+ * receives from m source ranks in one all-to-all. */
+int mpb_hist_merge_segments(mpb_hist* h, int32_t n_seg, const int64_t* seg_off, const uint64_t* keys_hd,
+                            const uint32_t* cnt_hd, const uint64_t* first_hd);
+
+/* Per-window summary (HOST outputs, any may be NULL):
  *   gap_n[nw]        sequences with more than v gaps (gap_sequence_number, core:689-691)
  *   ent[nw*4]        sum(c), sum(c*log2 c) over cover haplotypes; the same two sums over gap k-mers
  *                    (ingredients of core:602-614 entropy; the host rounds / re-derives exactly)
@@ -154,6 +172,24 @@ int mpb_scan(mpb_msa* msa, int k, int v, uint32_t fmask, uint32_t rmask, const i
              const uint32_t* cand_allow_hd, int64_t nc, int64_t* counts_hd, const int32_t* bits_slot,
              uint32_t* bits_hd);
 
+/* The same evaluation on the COLUMN view of the alignment (one thread = one candidate against 32 sequences: the
+ * mismatch word of a position is the complement of the OR of the allowed bases' column-plane words, mismatches are
+ * counted by a carry-save adder on the 32 lanes, the 3'-end rules are ORs over the strict positions).  Rows whose
+ * window is not the plain column cut (terminal-gap patching, IUPAC cells, ragged end: recorded per window by
+ * mpb_hist_build) are evaluated from their stored patched windows.  Candidates name a window of h's batch.
+ *   cands[nc]      hd; trial >= 0 also counts the perfect matches that carry base (trial >> 8) at position
+ *                  (trial & 255): the reference's coverage_renew look-up (core:954-956) folded into its parent
+ *   counts[nc*4]   hd: perfect | F_mis | R_mis | trial perfect  (mpb_scan's first three)
+ *   bits_slot / bits   as mpb_scan (bits hd, slots host)
+ * variation (h's v) must be <= 15. */
+typedef struct mpb_cand {
+    int32_t win;   /* index into the window batch of the mpb_hist */
+    int32_t trial; /* position | base << 8, or -1 */
+    uint32_t allow[4];
+} mpb_cand;
+int mpb_cscan(mpb_hist* h, uint32_t fmask, uint32_t rmask, const mpb_cand* cands_hd, int64_t nc, int64_t* counts_hd,
+              const int32_t* bits_slot, uint32_t* bits_hd);
+
 /* Per (window, sequence) haplotype key, for the JSON side files (core:1172-1176): the table key of the
  * sequence's k-mer, MPB_KEY_IUPAC for rows whose window holds IUPAC cells. out[nw*n_seq]. */
 #define MPB_KEY_IUPAC 0xFFFFFFFFFFFFFFFEull
@@ -168,11 +204,41 @@ int mpb_seqkeys(mpb_msa* msa, int k, const int32_t* win_pos, int32_t nw, uint64_
 int mpb_tm(mpb_ctx* ctx, const uint8_t* seqs2bit_hd, int k, int64_t n, const double* consts3, double* tm_hd,
            double* dh_hd, double* ds_hd);
 
-/* ---- per-window control logic in native host code ----------------------------------------------------------------
- * mpb_walk: seeds (core:579-600: Viterbi over freq / nn; most frequent haplotype = mm_key, MPB_KEY_EMPTY when the window
- * has no gap-free haplotype) and the NN-array refinement walk (core:860-1089) of all n_win windows in lock step: every
- * round collects the candidates of all live tracks and calls `scan` once (mpb_scan semantics, candidates sorted by
- * window; the callback adds the count all-reduce in sequence-sharded runs).  No device code, no CUDA calls.
+/* ---- per-window control logic: seeds core:579-600, NN-array refinement walk core:860-1089, NM-vs-MM core:816 ----------
+ * The logic lives once in csrc/mpb_walk_core.h and compiles for host and device.
+ *
+ * mpb_walk_dev_*: the product path.  Tracks (two per window: Viterbi seed and, when different, the most frequent
+ * haplotype) are resident in HBM; every round is a chain of kernels on the context's stream — advance all tracks with
+ * the previous round's counts and emit the next candidates, plan them, column scan, special rows — with NO host
+ * round trip: the host only enqueues.  In sequence-sharded runs the caller all-reduces the count vector between
+ * mpb_walk_dev_scan and the next mpb_walk_dev_advance (counts_dev is caller-visible device memory).
+ *   n_win, win_idx[n_win]      the windows that walk (indices into h's batch), host array
+ *   cover_number[n_win], mm_key[n_win]   host arrays (MPB_KEY_EMPTY: no gap-free haplotype)
+ *   freq_hd[n_win*4*k], nn_hd[n_win*(k-1)*16]  hd, or NULL = h's own summary tensors (mpb_hist_summary) at win_idx
+ * mpb_walk_dev_round = advance + scan.  Rounds after the last live track are no-ops.
+ * mpb_walk_dev_finish synchronises and returns mpb_walk's outputs. */
+typedef struct mpb_walk_dev mpb_walk_dev;
+int mpb_walk_dev_begin(mpb_hist* h, int dnum, int degeneracy, uint32_t fmask, uint32_t rmask, int32_t n_win,
+                       const int32_t* win_idx, const int64_t* cover_number, const uint64_t* mm_key, const int64_t* freq_hd,
+                       const int64_t* nn_hd, mpb_walk_dev** out);
+int mpb_walk_dev_advance(mpb_walk_dev* w);
+int mpb_walk_dev_scan(mpb_walk_dev* w);
+int mpb_walk_dev_round(mpb_walk_dev* w);
+/* device address and capacity (int64 elements) of the count vector of the current round, for the caller's all-reduce */
+int mpb_walk_dev_counts(mpb_walk_dev* w, void** counts_dev, int64_t* n_elems);
+/* number of live tracks after the last advance that has completed (-1: none yet); never blocks */
+int64_t mpb_walk_dev_live(mpb_walk_dev* w);
+int mpb_walk_dev_max_rounds(mpb_walk_dev* w);
+/* block until the live-track count after advance number `round` (0-based) is known */
+int mpb_walk_dev_wait(mpb_walk_dev* w, int round, int64_t* live);
+/* single-process driver: advance / scan until no track is live, the host at most `lag` rounds ahead of the device */
+int mpb_walk_dev_run(mpb_walk_dev* w, int lag, int64_t* rounds);
+int mpb_walk_dev_finish(mpb_walk_dev* w, uint8_t* out_sets, int64_t* out_counts, uint8_t* out_seeds, int64_t* out_seed_cover,
+                        int32_t* out_ntracks, int64_t trace_cap, uint8_t* trace_sets, int64_t* trace_off, int64_t* stats);
+void mpb_walk_dev_free(mpb_walk_dev* w);
+
+/* mpb_walk: the same walk driven from the host with the scan as a callback (no device code, no CUDA calls): the CPU
+ * tests run it against a stand-in scan.  Candidates name windows 0..n_win-1.
  *   out_sets[n_win*32]       final primer (4-bit sets) of the chosen track
  *   out_counts[n_win*5]      optimal_coverage_init, F_mis_cover_cover, R_mis_cover_cover (core:917-918 before the
  *                            sum), chosen track (0 = first / NM, 1 = MM), perfect_coverage of the final primer (core:853)
@@ -181,13 +247,11 @@ int mpb_tm(mpb_ctx* ctx, const uint8_t* seqs2bit_hd, int k, int64_t n, const dou
  *   trace_sets[trace_cap*32], trace_off[n_win+1]   every primer handed to mis_primer_check, in call order
  *   stats[3]                 scan rounds, candidates scanned, trace length
  */
-typedef int (*mpb_scan_cb)(void* user, const int32_t* cand_pos, const uint32_t* cand_allow, int64_t nc,
-                           int64_t* counts /* nc*3 */);
-int mpb_walk(int k, int v, int dnum, int degeneracy, uint32_t fmask, uint32_t rmask, int32_t n_win,
-             const int32_t* win_pos, const int64_t* cover_number, const int64_t* freq, const int64_t* nn,
-             const uint64_t* mm_key, mpb_scan_cb scan, void* user, uint8_t* out_sets, int64_t* out_counts,
-             uint8_t* out_seeds, int64_t* out_seed_cover, int32_t* out_ntracks, int64_t trace_cap, uint8_t* trace_sets,
-             int64_t* trace_off, int64_t* stats);
+typedef int (*mpb_scan_cb)(void* user, const mpb_cand* cands, int64_t nc, int64_t* counts /* nc*4 */);
+int mpb_walk(int k, int v, int dnum, int degeneracy, int32_t n_win, const int64_t* cover_number, const int64_t* freq,
+             const int64_t* nn, const uint64_t* mm_key, mpb_scan_cb scan, void* user, uint8_t* out_sets,
+             int64_t* out_counts, uint8_t* out_seeds, int64_t* out_seed_cover, int32_t* out_ntracks, int64_t trace_cap,
+             uint8_t* trace_sets, int64_t* trace_off, int64_t* stats);
 
 /* Tm (mean over expansions of the rounded per-expansion Tm, core:849-852; k_tm on the device), GC content and the
  * di-nucleotide / hairpin filters (core:387-416, 507-521) of n primers sets[n*32] of length k (host arrays).

@@ -27,6 +27,7 @@ SIGNATURES = {
     "mpb_ctx_set_stream": (C.c_int, [_P, _P]),
     "mpb_ctx_sync": (C.c_int, [_P]),
     "mpb_ctx_launches": (C.c_int64, [_P]),
+    "mpb_ctx_memcpy": (C.c_int, [_P, _P, _P, C.c_int64]),
     "mpb_ctx_profile": (C.c_int, [_P, C.c_int]),
     "mpb_ctx_profile_read": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int64),
                                         C.POINTER(C.c_double)]),
@@ -50,8 +51,25 @@ SIGNATURES = {
     "mpb_scan": (C.c_int, [_P, C.c_int, C.c_int, C.c_uint32, C.c_uint32, _P, _P, C.c_int64, _P, _P, _P]),
     "mpb_seqkeys": (C.c_int, [_P, C.c_int, _P, C.c_int32, _P]),
     "mpb_tm": (C.c_int, [_P, _P, C.c_int, C.c_int64, _P, _P, _P, _P]),
-    "mpb_walk": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_int32, _P, _P, _P, _P, _P, _P,
-                           _P, _P, _P, _P, _P, _P, C.c_int64, _P, _P, _P]),
+    "mpb_walk": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int32, _P, _P, _P, _P, _P, _P,
+                           _P, _P, _P, _P, _P, C.c_int64, _P, _P, _P]),
+    "mpb_hist_merge_segments": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P]),
+    "mpb_hist_create_empty": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int32, C.c_int, C.POINTER(_P)]),
+    "mpb_hist_add_counts": (C.c_int, [_P, _P, _P]),
+    "mpb_hist_summary": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "mpb_cscan": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P, C.c_int64, _P, _P, _P]),
+    "mpb_walk_dev_begin": (C.c_int, [_P, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_int32, _P, _P, _P, _P, _P,
+                                      C.POINTER(_P)]),
+    "mpb_walk_dev_advance": (C.c_int, [_P]),
+    "mpb_walk_dev_scan": (C.c_int, [_P]),
+    "mpb_walk_dev_round": (C.c_int, [_P]),
+    "mpb_walk_dev_counts": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int64)]),
+    "mpb_walk_dev_live": (C.c_int64, [_P]),
+    "mpb_walk_dev_max_rounds": (C.c_int, [_P]),
+    "mpb_walk_dev_wait": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int64)]),
+    "mpb_walk_dev_run": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int64)]),
+    "mpb_walk_dev_finish": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int64, _P, _P, _P]),
+    "mpb_walk_dev_free": (None, [_P]),
     "mpb_primer_props": (C.c_int, [_P, _P, C.c_int, C.c_int32, C.c_double, C.c_double, C.c_int, _P, _P, _P, _P, _P,
                                    _P]),
     "mpb_window_cells": (C.c_int, [_P, C.c_int64, _P, C.c_int32, C.c_int, C.c_int64, _P, _P, _P, _P]),
@@ -65,8 +83,8 @@ SIGNATURES = {
 }
 
 
-SCAN_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_uint32), C.c_int64,
-                      C.POINTER(C.c_int64))
+SCAN_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64))
+CAND_DTYPE = np.dtype([("win", np.int32), ("trial", np.int32), ("allow", np.uint32, (4,))])     # struct mpb_cand
 
 
 class MpbError(RuntimeError):
@@ -87,7 +105,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.mpb_abi_version() != 1:
+    if lib.mpb_abi_version() != 2:
         raise ImportError("libmpb200.so ABI version mismatch")
     _lib = lib
     return lib
@@ -128,51 +146,60 @@ def window_cells(packed4: np.ndarray, lens, n_col: int, k: int, seq, pos):
     return cells, out_len
 
 
-def walk(k, v, dnum, degeneracy, fmask, rmask, win_pos, cover_number, freq, nn, mm_key, scan_fn):
-    """mpb_walk: refinement walk of a window batch; scan_fn(cand_pos int32[nc], cand_allow uint32[nc,4]) -> int64[nc,3].
-    Pure host code (usable without a GPU when scan_fn is a stand-in)."""
-    n = len(win_pos)
-    win_pos = np.ascontiguousarray(win_pos, dtype=np.int32)
+def make_cands(win, allow, trial=None) -> np.ndarray:
+    """struct mpb_cand array from window indices, allowed-base masks [n, 4] and optional trial codes"""
+    win = np.asarray(win, dtype=np.int32)
+    c = np.zeros(len(win), CAND_DTYPE)
+    c["win"] = win
+    c["allow"] = np.asarray(allow, dtype=np.uint32).reshape(-1, 4)
+    c["trial"] = -1 if trial is None else np.asarray(trial, dtype=np.int32)
+    return c
+
+
+def _walk_outputs(n):
+    return dict(sets=np.zeros((n, 32), np.uint8), counts=np.zeros((n, 5), np.int64), seeds=np.zeros((n, 2, 32), np.uint8),
+                seed_cover=np.zeros((n, 2), np.int64), ntracks=np.zeros(n, np.int32), stats=np.zeros(3, np.int64))
+
+
+def walk(k, v, dnum, degeneracy, cover_number, freq, nn, mm_key, scan_fn, want_trace=True):
+    """mpb_walk: refinement walk of a window batch on the HOST; scan_fn(cands: CAND_DTYPE[nc]) -> int64[nc,4]
+    (perfect, F_mis, R_mis, trial perfect); candidates name windows 0..n-1.  No CUDA calls: the CPU tests drive it
+    with a stand-in scan; the GPU path is WalkDev."""
+    n = len(cover_number)
     cover_number = np.ascontiguousarray(cover_number, dtype=np.int64)
     freq = np.ascontiguousarray(freq, dtype=np.int64)
     nn = np.ascontiguousarray(nn, dtype=np.int64)
     mm_key = np.ascontiguousarray(mm_key, dtype=np.uint64)
     err = []
 
-    def cb(_user, p_pos, p_allow, nc, p_counts):
+    def cb(_user, p_cands, nc, p_counts):
         try:
-            pos = np.ctypeslib.as_array(p_pos, shape=(nc,))
-            allow = np.ctypeslib.as_array(p_allow, shape=(nc, 4))
-            out = np.ctypeslib.as_array(p_counts, shape=(nc, 3))
-            out[:] = scan_fn(pos, allow)
+            cands = np.ctypeslib.as_array(C.cast(p_cands, C.POINTER(C.c_uint8)), shape=(nc * CAND_DTYPE.itemsize,))
+            out = np.ctypeslib.as_array(p_counts, shape=(nc, 4))
+            out[:] = scan_fn(cands.view(CAND_DTYPE))
             return 0
         except Exception as exc:           # surfaced after mpb_walk returns
             err.append(exc)
             return -2
 
-    out_sets = np.zeros((n, 32), np.uint8)
-    out_counts = np.zeros((n, 5), np.int64)
-    out_seeds = np.zeros((n, 2, 32), np.uint8)
-    out_seed_cover = np.zeros((n, 2), np.int64)
-    out_nt = np.zeros(n, np.int32)
+    res = _walk_outputs(n)
     cap = max(64, n * 48)
-    stats = np.zeros(3, np.int64)
     cfn = SCAN_CB(cb)
     while True:
         trace = np.zeros((cap, 32), np.uint8)
         off = np.zeros(n + 1, np.int64)
-        rc = load().mpb_walk(k, v, dnum, degeneracy, fmask, rmask, n, ptr(win_pos), ptr(cover_number), ptr(freq), ptr(nn),
-                             ptr(mm_key), C.cast(cfn, C.c_void_p), None, ptr(out_sets), ptr(out_counts), ptr(out_seeds),
-                             ptr(out_seed_cover), ptr(out_nt), cap, ptr(trace), ptr(off), ptr(stats))
+        rc = load().mpb_walk(k, v, dnum, degeneracy, n, ptr(cover_number), ptr(freq), ptr(nn), ptr(mm_key),
+                             C.cast(cfn, C.c_void_p), None, ptr(res["sets"]), ptr(res["counts"]), ptr(res["seeds"]),
+                             ptr(res["seed_cover"]), ptr(res["ntracks"]), cap, ptr(trace), ptr(off), ptr(res["stats"]))
         if err:
             raise err[0]
-        if rc == -4 and stats[2] > cap:      # trace buffer too small: the walk is deterministic, run it again
-            cap = int(stats[2]) + 16
+        if rc == -4 and res["stats"][2] > cap:      # trace buffer too small: the walk is deterministic, run it again
+            cap = int(res["stats"][2]) + 16
             continue
         check(rc)
         break
-    return dict(sets=out_sets, counts=out_counts, seeds=out_seeds, seed_cover=out_seed_cover, ntracks=out_nt,
-                trace=trace, trace_off=off, stats=stats)
+    res.update(trace=trace, trace_off=off)
+    return res
 
 
 class Context:
@@ -293,8 +320,8 @@ class Msa:
         check(load().mpb_seq_attr_hist(self.h, ptr(lead), ptr(rstrip)))
         return lead, rstrip
 
-    def hist(self, k: int, v: int, win_pos, log2_cap: int = 0) -> "Hist":
-        return Hist(self, k, v, win_pos, log2_cap)
+    def hist(self, k: int, v: int, win_pos, log2_cap: int = 0, empty: bool = False) -> "Hist":
+        return Hist(self, k, v, win_pos, log2_cap, empty)
 
     def scan(self, k: int, v: int, fmask: int, rmask: int, cand_pos, cand_allow, bits_slot=None, counts_out=None,
              bits_out=None):
@@ -325,13 +352,19 @@ class Msa:
 class Hist:
     """per-window haplotype tables of one window batch"""
 
-    def __init__(self, msa: Msa, k: int, v: int, win_pos, log2_cap: int = 0):
+    def __init__(self, msa: Msa, k: int, v: int, win_pos, log2_cap: int = 0, empty: bool = False):
         self.msa = msa
         self.k, self.v = k, v
         self.win_pos = np.ascontiguousarray(win_pos, dtype=np.int32)
         self.nw = len(self.win_pos)
         self.h = None
         cap = log2_cap
+        if empty:                       # owner tables of a sequence-sharded run: filled through merge() only
+            h = C.c_void_p()
+            check(load().mpb_hist_create_empty(msa.h, k, v, ptr(self.win_pos), self.nw, cap, C.byref(h)))
+            self.h = h
+            self.log2_cap = cap
+            return
         while True:
             h = C.c_void_p()
             rc = load().mpb_hist_build(msa.h, k, v, ptr(self.win_pos), self.nw, cap, C.byref(h))
@@ -342,6 +375,7 @@ class Hist:
                 continue
             check(rc)
             self.h = h
+            self.log2_cap = cap
             break
 
     def close(self):
@@ -354,6 +388,61 @@ class Hist:
 
     def __exit__(self, *a):
         self.close()
+
+    def summary(self):
+        """mpb_hist_summary: stats() and tensors() of every window in one pass over the occupied slots"""
+        nw, k = self.nw, self.k
+        out = dict(gap_n=np.empty(nw, np.int64), ent=np.empty((nw, 4), np.float64), nuniq=np.empty((nw, 3), np.int64),
+                   mm_key=np.empty(nw, np.uint64), mm_cnt=np.empty(nw, np.int64), mm_first=np.empty(nw, np.uint64),
+                   n_iupac_gap=np.empty(nw, np.int64), freq=np.empty((nw, 4, k), np.int64),
+                   nn=np.empty((nw, k - 1, 4, 4), np.int64))
+        check(load().mpb_hist_summary(self.h, ptr(out["gap_n"]), ptr(out["ent"]), ptr(out["nuniq"]), ptr(out["mm_key"]),
+                                      ptr(out["mm_cnt"]), ptr(out["mm_first"]), ptr(out["n_iupac_gap"]),
+                                      ptr(out["freq"]), ptr(out["nn"])))
+        return out
+
+    def add_counts(self, gap_n, n_iupac_gap):
+        gap_n = np.ascontiguousarray(gap_n, dtype=np.int64)
+        n_iupac_gap = np.ascontiguousarray(n_iupac_gap, dtype=np.int64)
+        check(load().mpb_hist_add_counts(self.h, ptr(gap_n), ptr(n_iupac_gap)))
+
+    def cscan(self, fmask: int, rmask: int, cands: np.ndarray, bits_slot=None, counts_out=None, bits_out=None):
+        """mpb_cscan: column scan of CAND_DTYPE candidates -> (counts[nc,4] int64, bits[nslots,3,words] uint32 or None)"""
+        cands = np.ascontiguousarray(cands, dtype=CAND_DTYPE)
+        nc = len(cands)
+        counts = counts_out if counts_out is not None else np.zeros((nc, 4), np.int64)
+        bits = bits_out
+        if bits_slot is not None:
+            bits_slot = np.ascontiguousarray(bits_slot, dtype=np.int32)
+            nslots = int(bits_slot.max()) + 1 if nc else 0
+            if bits is None:
+                bits = np.zeros((max(nslots, 0), 3, (self.msa.n_seq + 31) // 32), np.uint32)
+        if nc:
+            check(load().mpb_cscan(self.h, fmask, rmask, ptr(cands), nc, ptr(counts), ptr(bits_slot), ptr(bits)))
+        return counts, bits
+
+    def walk(self, dnum, degeneracy, fmask, rmask, win_idx, cover_number, mm_key, freq=None, nn=None, comm=None,
+             want_trace=True, lag=2):
+        """the device-resident refinement walk of the windows win_idx (indices into this batch) -> walk() outputs.
+        comm (sequence shards): the count vector is all-reduced between scan and advance."""
+        with WalkDev(self, dnum, degeneracy, fmask, rmask, win_idx, cover_number, mm_key, freq, nn) as w:
+            if comm is None or comm.world == 1:
+                w.run(lag)
+            else:
+                on_gpu = getattr(comm, "on_gpu", False)
+                counts_t = w.counts_tensor(comm) if on_gpu else None
+                r = 0
+                while True:
+                    w.advance()
+                    if r >= lag and w.wait(r - lag) == 0:       # identical on every rank: same counts, same rounds
+                        break
+                    w.scan()
+                    if on_gpu:
+                        comm.allreduce_dev_inplace(counts_t)    # NCCL over NVLink, on the context's stream
+                    else:                                       # host communicator (gloo): through host memory
+                        w.set_counts(comm.allreduce_sum(w.get_counts()))
+                    r += 1
+            return w.finish(want_trace)
 
     def stats(self):
         nw = self.nw
@@ -409,6 +498,16 @@ class Hist:
                 first = np.ascontiguousarray(first, dtype=np.uint64)
             check(load().mpb_hist_merge(self.h, ptr(win_off), ptr(keys), ptr(cnt), ptr(first)))
 
+    def merge_segments(self, seg_off, keys, cnt, first):
+        """merge() for m * nw segments: segment s belongs to window s % nw (keys / cnt / first: numpy or device tensors)"""
+        seg_off = np.ascontiguousarray(seg_off, dtype=np.int64)
+        if seg_off[-1] > 0:
+            if isinstance(keys, np.ndarray):
+                keys = np.ascontiguousarray(keys, dtype=np.uint64)
+                cnt = np.ascontiguousarray(cnt, dtype=np.uint32)
+                first = np.ascontiguousarray(first, dtype=np.uint64)
+            check(load().mpb_hist_merge_segments(self.h, len(seg_off) - 1, ptr(seg_off), ptr(keys), ptr(cnt), ptr(first)))
+
     def export_dev(self, sel, counts, comm):
         """export() into device tensors allocated through the communicator -> (win_off, keys, cnt, first)"""
         sel = np.ascontiguousarray(sel, dtype=np.uint8)
@@ -438,6 +537,86 @@ class Hist:
         if n.value:
             check(load().mpb_hist_exceptions(self.h, n.value, ptr(w), ptr(s), C.byref(n)))
         return w, s
+
+
+class WalkDev:
+    """mpb_walk_dev_*: tracks resident in HBM, rounds chained on the context's stream"""
+
+    def __init__(self, hist: Hist, dnum, degeneracy, fmask, rmask, win_idx, cover_number, mm_key, freq=None, nn=None):
+        self.hist = hist
+        self.n = len(win_idx)
+        win_idx = np.ascontiguousarray(win_idx, dtype=np.int32)
+        cover_number = np.ascontiguousarray(cover_number, dtype=np.int64)
+        mm_key = np.ascontiguousarray(mm_key, dtype=np.uint64)
+        if freq is not None and isinstance(freq, np.ndarray):
+            freq = np.ascontiguousarray(freq, dtype=np.int64)
+            nn = np.ascontiguousarray(nn, dtype=np.int64)
+        h = C.c_void_p()
+        check(load().mpb_walk_dev_begin(hist.h, dnum, degeneracy, fmask, rmask, self.n, ptr(win_idx), ptr(cover_number),
+                                        ptr(mm_key), ptr(freq), ptr(nn), C.byref(h)))
+        self.h = h
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def close(self):
+        if self.h:
+            load().mpb_walk_dev_free(self.h)
+            self.h = None
+
+    def advance(self):
+        check(load().mpb_walk_dev_advance(self.h))
+
+    def scan(self):
+        check(load().mpb_walk_dev_scan(self.h))
+
+    def wait(self, rnd: int) -> int:
+        live = C.c_int64()
+        check(load().mpb_walk_dev_wait(self.h, rnd, C.byref(live)))
+        return live.value
+
+    def run(self, lag: int = 2) -> int:
+        rounds = C.c_int64()
+        check(load().mpb_walk_dev_run(self.h, lag, C.byref(rounds)))
+        return rounds.value
+
+    def counts_tensor(self, comm):
+        """the device count vector as a tensor of the communicator's framework (no copy)"""
+        p, n = C.c_void_p(), C.c_int64()
+        check(load().mpb_walk_dev_counts(self.h, C.byref(p), C.byref(n)))
+        return comm.wrap_dev(p.value, n.value)
+
+    def _counts_ptr(self):
+        p, n = C.c_void_p(), C.c_int64()
+        check(load().mpb_walk_dev_counts(self.h, C.byref(p), C.byref(n)))
+        return p, n.value
+
+    def get_counts(self) -> np.ndarray:
+        p, n = self._counts_ptr()
+        out = np.empty(n, np.int64)
+        check(load().mpb_ctx_memcpy(self.hist.msa.ctx.h, ptr(out), p, n * 8))
+        return out
+
+    def set_counts(self, arr: np.ndarray):
+        p, n = self._counts_ptr()
+        arr = np.ascontiguousarray(arr, dtype=np.int64)
+        assert len(arr) == n
+        check(load().mpb_ctx_memcpy(self.hist.msa.ctx.h, p, ptr(arr), n * 8))
+
+    def finish(self, want_trace=True):
+        n = self.n
+        res = _walk_outputs(n)
+        cap = n * 2 * 48 if want_trace else 0
+        trace = np.zeros((cap, 32), np.uint8) if want_trace else None
+        off = np.zeros(n + 1, np.int64)
+        check(load().mpb_walk_dev_finish(self.h, ptr(res["sets"]), ptr(res["counts"]), ptr(res["seeds"]),
+                                         ptr(res["seed_cover"]), ptr(res["ntracks"]), cap, ptr(trace), ptr(off),
+                                         ptr(res["stats"])))
+        res.update(trace=trace, trace_off=off)
+        return res
 
 
 class Dimer:

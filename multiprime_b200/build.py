@@ -10,8 +10,9 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libmpb200.so")
-SOURCES = ["mpb200.cu", "mpb_dimer.cu", "mpb_walk.cu"]
-HEADERS = [os.path.join(CSRC, "mpb_device.cuh"), os.path.join(CSRC, "mpb_host.h"), os.path.join(ROOT, "include", "mpb200.h")]
+SOURCES = ["mpb200.cu", "mpb_cscan.cu", "mpb_walk_dev.cu", "mpb_dimer.cu", "mpb_walk.cu"]
+HEADERS = [os.path.join(CSRC, h) for h in ("mpb_device.cuh", "mpb_host.h", "mpb_cscan.h", "mpb_walk_core.h")] + \
+    [os.path.join(ROOT, "include", "mpb200.h")]
 
 
 def nvcc_path() -> str:
@@ -33,7 +34,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
     cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-           "-Xptxas", "-v" if verbose else "-O3", "-shared", "-Xcompiler", "-fPIC", "-cudart", "static",
+           "-Xptxas", "-v" if verbose else "-O3", "-shared", "-Xcompiler", "-fPIC", "-cudart", "static", "-t", "5",
            "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:

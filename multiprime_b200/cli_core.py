@@ -62,9 +62,13 @@ def _shard_setup(args):
         dist.init_process_group(backend)
     ids, codes, lens = parse_msa(args.input)
     n = len(ids)
+    if n < world:
+        raise SystemExit("Error: %d sequences cannot be sharded over %d ranks; run a single process." % (n, world))
     lo, hi = rank * n // world, (rank + 1) * n // world
-    return {"device": device, "alignment": (ids[lo:hi], codes[lo:hi], lens[lo:hi]), "row0": lo,
-            "comm": TorchComm()}, rank
+    extra = {"device": device, "alignment": (ids[lo:hi], codes[lo:hi], lens[lo:hi]), "row0": lo, "comm": TorchComm()}
+    if backend == "nccl":            # the library's kernels and torch's collectives share one stream
+        extra["stream"] = torch.cuda.current_stream().cuda_stream
+    return extra, rank
 
 
 def main(argv=None):

@@ -19,6 +19,9 @@ class NoComm:
     def allgather_object(self, obj):
         return [obj]
 
+    def alltoall(self, arr, send_counts, recv_counts):
+        return arr
+
     def barrier(self):
         pass
 
@@ -68,6 +71,35 @@ class TorchComm:
         out = [None] * self.world
         self.dist.all_gather_object(out, obj, group=self.group)
         return out
+
+    def alltoall(self, arr, send_counts, recv_counts):
+        """variable-size all-to-all of a 1-d numpy array: send_counts[r] consecutive elements go to rank r; returns the
+        received elements in source-rank order (recv_counts[r] from rank r)"""
+        arr = np.ascontiguousarray(arr)
+        it = arr.dtype.itemsize
+        src = self._to(arr.view(np.uint8).reshape(-1))
+        out = self.torch.empty(int(np.sum(recv_counts)) * it, dtype=self.torch.uint8, device=self.device)
+        self.dist.all_to_all_single(out, src, [int(c) * it for c in recv_counts], [int(c) * it for c in send_counts],
+                                    group=self.group)
+        return out.cpu().numpy().view(arr.dtype)
+
+    def alltoall_dev(self, t, send_counts, recv_counts):
+        """the same for a device tensor (first sum(send_counts) elements valid); stays on the device (NCCL)"""
+        n_out = int(np.sum(recv_counts))
+        out = self.torch.empty(max(1, n_out), dtype=t.dtype, device=t.device)
+        self.dist.all_to_all_single(out[:n_out], t[:int(np.sum(send_counts))], [int(c) for c in recv_counts],
+                                    [int(c) for c in send_counts], group=self.group)
+        return out
+
+    def allreduce_dev_inplace(self, t):
+        """in-place sum over ranks of a device tensor (NCCL over NVLink), no host copy"""
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+
+    def wrap_dev(self, ptr: int, n: int):
+        """int64 tensor view of n elements of raw device memory (the walk's count vector), zero copy"""
+        class _Raw:
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 2}
+        return self.torch.as_tensor(_Raw(), device=self.device)
 
     def allreduce_dev(self, t):
         """in-place sum over ranks of a device tensor (NCCL), returned as a numpy array"""

@@ -195,7 +195,7 @@ class NN_degenerate(object):
     def __init__(self, seq_file, primer_length=18, coverage=0.8, number_of_dege_bases=18, score_of_dege_bases=1000,
                  product_len=250, position="2,-1", variation=2, raw_entropy_threshold=3.6, distance=4, GC="0.4,0.6",
                  nproc=10, outfile="", device=0, windows_per_batch=0, sidecars=True, alignment=None, packed=None,
-                 stream=None, comm=None, row0=0, _backend=None):
+                 stream=None, comm=None, row0=0, want_trace=True, keep_bits=False, _backend=None):
         self.primer_length = primer_length
         self.coverage = coverage
         self.number_of_dege_bases = number_of_dege_bases
@@ -209,6 +209,9 @@ class NN_degenerate(object):
         self.raw_entropy_threshold = raw_entropy_threshold
         self.outfile = outfile
         self.sidecars = sidecars
+        self.want_trace = want_trace            # record the primers handed to mis_primer_check (the tests compare them)
+        self.keep_bits = keep_bits              # keep the per-sequence F / R / gap bit vectors of every row (pairing)
+        self.bit_vectors = []
         self.windows_per_batch = windows_per_batch
         if not 3 <= primer_length <= _lib.MAX_K:
             raise ValueError("primer length must be within 3..%d" % _lib.MAX_K)
@@ -273,7 +276,7 @@ class NN_degenerate(object):
         return self.raw_entropy_threshold * 0.9
 
     # -- entropy (core:602-614) ----------------------------------------------------------------------------
-    def _iupac_gap_groups(self, hist, wi, pos):
+    def _iupac_gap_groups(self, hist, wi):
         """gap rows that hold IUPAC cells are not in the device table (their raw k-mer needs 4 bits per cell):
         group the few of them by raw k-mer here -> [(first order, count)] of window wi"""
         cache = getattr(hist, "_iupac_groups", None)
@@ -318,10 +321,12 @@ class NN_degenerate(object):
             hist._iupac_groups = cache
         return cache.get(wi, [])
 
-    def _entropy_exact(self, hist, wi, pos, n_unique):
-        """the reference's left-to-right float sums (core:602-614), over the table dumped in first-seen order"""
+    def _entropy_exact(self, table, ti, wi, n_unique, hist=None):
+        """the reference's left-to-right float sums (core:602-614), over the table dumped in first-seen order.
+        table / ti: the handle holding the complete table of the window and its index there; wi: the window's index in
+        the batch (hist: the local handle that carries the exception rows, when it is another one than `table`)."""
         k, v = self.primer_length, self.variation
-        keys, cnt, first = hist.dump(wi, int(n_unique) + 8)
+        keys, cnt, first = table.dump(ti, int(n_unique) + 8)
         is_gap = np.zeros(len(keys), bool)
         b5 = keys >= np.uint64(_lib.KEY_BASE5)
         if b5.any():
@@ -332,7 +337,7 @@ class NN_degenerate(object):
                 x //= np.uint64(5)
             is_gap[b5] = g > v
         cover = cnt[~is_gap].tolist()                                   # dump() is sorted by first-seen order
-        gaps = list(zip(first[is_gap].tolist(), cnt[is_gap].tolist())) + self._iupac_gap_groups(hist, wi, pos)
+        gaps = list(zip(first[is_gap].tolist(), cnt[is_gap].tolist())) + self._iupac_gap_groups(hist or table, wi)
         gaps.sort()
         gap_n = sum(c for _, c in gaps)
         cover_number = self.total_sequence_number - gap_n
@@ -393,15 +398,15 @@ class NN_degenerate(object):
                 w = left[len(left) - g:] + w
         return w
 
-    def _table_log2cap(self, k: int) -> int:
-        """log2 of the slots per haplotype table, 0 = the library default (two slots per sequence).
+    def _table_log2cap(self, k: int, n: int) -> int:
+        """log2 of the slots per haplotype table holding the haplotypes of n sequences, 0 = the library default (two
+        slots per sequence).
         The windows that reach the tables passed the prefilter: the entropy of their 65536 coarse bins is at most the
         gate, so a fraction x of items that are (nearly) alone in their bin costs x * (16 + log2(1/x)) bits and x stays
         below thr / 16-ish (0.2 for the default 3.6 bits) — distinct haplotypes are a fifth of the sequences at most,
-        in practice far fewer.  Tables of N / 2 slots (load <= 0.4) are a quarter of the default: every table reader
-        walks a quarter of the slots.  A table that fills up anyway reports MPB_EOVERFLOW and the batch is rebuilt
-        with doubled tables (_lib.Hist)."""
-        n = self.total_sequence_number                # merged tables hold the haplotypes of all shards
+        in practice far fewer.  Tables of N / 2 slots (load <= 0.4) are a quarter of the default.  A table that fills
+        up anyway reports MPB_EOVERFLOW and is rebuilt with doubled capacity (_lib.Hist for the local build,
+        _exchange for the owner tables of a sharded run)."""
         if k < 8 or n < (1 << 17) or self.entropy_threshold > 4.0:
             return 0
         return max(10, int(math.ceil(math.log2(n / 2))))
@@ -421,6 +426,7 @@ class NN_degenerate(object):
 
     def _design_batch(self, positions):
         k, v, N = self.primer_length, self.variation, self.total_sequence_number
+        comm = self.comm
         self.stats["windows"] += len(positions)
         ph = self.stats.setdefault("phase_ms", {})
         tick = [time.perf_counter()]
@@ -432,10 +438,13 @@ class NN_degenerate(object):
 
         # entropy prefilter: windows whose coarse-grained entropy bound is above the gate never get a table
         if k >= 8:
-            s0, s1 = self.msa.prefilter(k, v, positions)
-            bound = (s0 * math.log2(self.n_local) - s1) / N     # shards: size-weighted (concavity of the entropy)
-            if self.comm.world > 1:
-                bound = self.comm.allreduce_sum(bound)
+            if self.n_local > 0:
+                s0, s1 = self.msa.prefilter(k, v, positions)
+                bound = (s0 * math.log2(self.n_local) - s1) / N     # shards: size-weighted (concavity of the entropy)
+            else:
+                bound = np.zeros(len(positions))
+            if comm.world > 1:
+                bound = comm.allreduce_sum(bound)
             keep_pos = bound <= self.entropy_threshold + 0.006
         else:                                                    # very short primers: keep every window
             keep_pos = np.ones(len(positions), bool)
@@ -444,122 +453,165 @@ class NN_degenerate(object):
         lap("prefilter")
         if not positions:
             return []
-        with self.msa.hist(k, v, positions, self._table_log2cap(k)) as hist:
+        if comm.world > 1:
+            # sequence shards: rank r OWNS the windows with (index mod world) == r; the batch is laid out owner-major so
+            # that a shard's table entries leave in one contiguous piece per destination
+            order = sorted(range(len(positions)), key=lambda i: (i % comm.world, i))
+            positions = [positions[i] for i in order]
+            owner = np.array([i % comm.world for i in order], np.int32)
+        else:
+            owner = np.zeros(len(positions), np.int32)
+        with self.msa.hist(k, v, positions, self._table_log2cap(k, self.n_local)) as hist:
             lap("hist_build")
-            if self.comm.world > 1:
-                st = self._merge_shards(hist)
-                lap("merge_shards")
-            else:
-                st = hist.stats()
-                lap("hist_stats")
-            gap_n = st["gap_n"]
-            # core:713 `round(gap_n / N, 2) >= 1 - coverage`: exact for all but ratios on a rounding tie
-            ratio = gap_n / N
-            gap_fail = np.round(ratio, 2) >= (1 - self.coverage)
-            for wi in np.nonzero(np.abs((ratio * 100) % 1 - 0.5) < 1e-6)[0]:
-                gap_fail[wi] = round(int(gap_n[wi]) / N, 2) >= (1 - self.coverage)
-            alive = ~gap_fail & (st["nuniq"][:, 0] >= 1)                      # core:716
-            if "merged" in st:
-                alive &= st["merged"]              # shard entropy bound already above the gate
-            accepted = []                          # (batch index, position, cBit, tBit, cover_number, has gap-free)
-            sel = np.zeros(len(positions), np.uint8)
-            for wi, ent in self._entropies(hist, st, positions, alive):
-                accepted.append((wi, positions[wi], ent[0], ent[1], N - int(gap_n[wi]), bool(st["nuniq"][wi, 2] > 0)))
-                sel[wi] = 1
-            lap("gates")
-            if not accepted:
-                return []
-            freq, nn = hist.tensors(sel)
-            lap("tensors")
-            keep = []
-            for a in accepted:                                                     # core:736-740
-                f = freq[a[0]]
-                if not ((f.sum(axis=1) == 0).any() or (f.sum(axis=0) == 0).any()):
-                    keep.append(a)
-            if not keep:
-                return []
-            wis = np.array([a[0] for a in keep], np.int64)
-            mm_key = np.where(np.array([a[5] for a in keep]), st["mm_key"][wis], np.uint64(_lib.KEY_EMPTY))
-
-            dev_reduce = getattr(self.comm, "on_gpu", False) and hasattr(self.ctx, "h")
-
-            def scan_fn(pos, allow):
-                self.stats["scan_calls"] += 1
-                if dev_reduce:        # counts stay in HBM: scan -> NCCL all-reduce -> one D2H
-                    t = self.comm.torch.zeros((len(pos), 3), dtype=self.comm.torch.int64, device=self.comm.device)
-                    self.msa.scan(k, v, self.fmask, self.rmask, pos, allow, counts_out=t)
-                    return self.comm.allreduce_dev(t)
-                counts, _ = self.msa.scan(k, v, self.fmask, self.rmask, pos, allow)
-                return self.comm.allreduce_sum(counts)        # the one collective of a scan round
-
-            res = _lib.walk(k, v, self.number_of_dege_bases, self.score_of_dege_bases, self.fmask, self.rmask,
-                            np.array([a[1] for a in keep], np.int32), np.array([a[4] for a in keep], np.int64),
-                            freq[wis], nn[wis].reshape(len(keep), k - 1, 16), mm_key, scan_fn)
-            lap("walk")
-            self.stats["candidates"] += int(res["stats"][1])
-            self.stats["evals"] += int(res["stats"][2]) * N
-            tick[0] = time.perf_counter()
-            out = self._finish(hist, keep, res)
-            tick[0] = time.perf_counter()
+            own = None
+            try:
+                if comm.world > 1:
+                    st, own, mine = self._exchange(hist, positions, owner)
+                    lap("exchange")
+                else:
+                    st, mine = hist.summary(), None
+                    lap("summary")
+                out = self._gates_walk_finish(hist, own, mine, owner, st, positions, lap)
+            finally:
+                if own is not None:
+                    own.close()
         lap("free")
         return out
 
-    def _merge_shards(self, hist):
-        """Sequence-sharded run: make the tables of every window that can still pass the gates GLOBAL on every rank
-        (the prefilter already dropped the windows whose pooled entropy bound is above the gate)."""
-        comm, N = self.comm, self.total_sequence_number
-        gap_local, iupac_local, counts = hist.counts()
-        gap_n = comm.allreduce_sum(gap_local)
-        iupac_gap = comm.allreduce_sum(iupac_local)
-        gap_fail = np.array([round(int(g) / N, 2) >= (1 - self.coverage) for g in gap_n])
-        merged = ~gap_fail
-        if getattr(comm, "on_gpu", False) and hasattr(hist, "export_dev"):
-            # entries stay in HBM: export -> NCCL all-gather -> mpb_hist_merge from device pointers
-            off, keys, cnt, first = hist.export_dev(merged.astype(np.uint8), counts, comm)
-            sizes_all, _ = comm.allgather_concat(np.diff(off))
-            sizes_all = sizes_all.reshape(comm.world, hist.nw)
-            totals = sizes_all.sum(axis=1)
-            n_mine, n_max = int(totals[comm.rank]), int(totals.max())
-            if n_max > 0:
-                gk = comm.allgather_dev(keys, n_mine, n_max)
-                gc = comm.allgather_dev(cnt, n_mine, n_max)
-                gf = comm.allgather_dev(first, n_mine, n_max)
-                for r in range(comm.world):
-                    if r != comm.rank and totals[r] > 0:
-                        off_r = np.concatenate([[0], np.cumsum(sizes_all[r])]).astype(np.int64)
-                        hist.merge(off_r, gk[r], gc[r], gf[r])
-        else:
-            off, keys, cnt, first = hist.export(merged.astype(np.uint8), counts)
-            sizes_all, _ = comm.allgather_concat(np.diff(off))                     # world x nw entry counts
-            sizes_all = sizes_all.reshape(comm.world, hist.nw)
-            keys_all, lens_k = comm.allgather_concat(keys)
-            cnt_all, _ = comm.allgather_concat(cnt)
-            first_all, _ = comm.allgather_concat(first)
-            starts = np.concatenate([[0], np.cumsum(lens_k)])
-            for r in range(comm.world):
-                if r == comm.rank:
-                    continue
-                off_r = np.concatenate([[0], np.cumsum(sizes_all[r])]).astype(np.int64)
-                a, b = int(starts[r]), int(starts[r + 1])
-                hist.merge(off_r, keys_all[a:b], cnt_all[a:b], first_all[a:b])
-        st2 = hist.stats()                                                     # global for the merged windows
-        # the float sums depend on each rank's slot order in the last bits: rank 0's copy is the one every rank uses, so
-        # that all ranks take the same (collective-bearing) decisions even on a rounding edge
-        st2["ent"] = comm.allreduce_sum(st2["ent"] if comm.rank == 0 else np.zeros_like(st2["ent"]))
-        st2["gap_n"] = gap_n
-        st2["n_iupac_gap"] = iupac_gap
-        st2["merged"] = merged
-        return st2
+    def _gates_walk_finish(self, hist, own, mine, owner, st, positions, lap):
+        k, v, N = self.primer_length, self.variation, self.total_sequence_number
+        comm = self.comm
+        gap_n = st["gap_n"]
+        # core:713 `round(gap_n / N, 2) >= 1 - coverage`: exact for all but ratios on a rounding tie
+        ratio = gap_n / N
+        gap_fail = np.round(ratio, 2) >= (1 - self.coverage)
+        for wi in np.nonzero(np.abs((ratio * 100) % 1 - 0.5) < 1e-6)[0]:
+            gap_fail[wi] = round(int(gap_n[wi]) / N, 2) >= (1 - self.coverage)
+        alive = ~gap_fail & (st["nuniq"][:, 0] >= 1)                      # core:716
+        accepted = []                          # (batch index, position, cBit, tBit, cover_number, has gap-free)
+        for wi, ent in self._entropies(hist, own, mine, owner, st, positions, alive):
+            accepted.append((wi, positions[wi], ent[0], ent[1], N - int(gap_n[wi]), bool(st["nuniq"][wi, 2] > 0)))
+        lap("gates")
+        freq, nn = st["freq"], st["nn"]
+        keep = []
+        for a in accepted:                                                     # core:736-740
+            f = freq[a[0]]
+            if not ((f.sum(axis=1) == 0).any() or (f.sum(axis=0) == 0).any()):
+                keep.append(a)
+        if not keep:
+            return []
+        wis = np.array([a[0] for a in keep], np.int32)
+        mm_key = np.where(np.array([a[5] for a in keep]), st["mm_key"][wis], np.uint64(_lib.KEY_EMPTY))
+        sharded = comm.world > 1
+        res = hist.walk(self.number_of_dege_bases, self.score_of_dege_bases, self.fmask, self.rmask, wis,
+                        np.array([a[4] for a in keep], np.int64), mm_key,
+                        freq=freq[wis] if sharded else None, nn=nn[wis].reshape(len(keep), k - 1, 16) if sharded else None,
+                        comm=comm if sharded else None, want_trace=self.want_trace)
+        lap("walk")
+        self.stats["scan_calls"] += int(res["stats"][0])
+        self.stats["candidates"] += int(res["stats"][1])
+        self.stats["evals"] += int(res["stats"][2]) * N
+        return self._finish(hist, own, mine, owner, keep, res)
 
-    def _entropies(self, hist, st, positions, alive):
+    def _exchange(self, hist, positions, owner):
+        """Sequence-sharded run: every per-window quantity is a sum over sequences.  Gap counters are
+        all-reduced; the haplotype entries of every window travel to the window's OWNER (one all-to-all), which merges
+        them into its own table, takes the window statistics and tensors, and the small per-window results are
+        all-gathered: every rank ends up with the same `st` for all windows and takes identical decisions, while the
+        table work is divided by the world size."""
+        comm, N, k, v = self.comm, self.total_sequence_number, self.primer_length, self.variation
+        world, rank, nw = comm.world, comm.rank, len(positions)
+        gap_local, iupac_local, n_ent = hist.counts()
+        both = comm.allreduce_sum(np.concatenate([gap_local, iupac_local]))
+        gap_n, iupac_gap = both[:nw], both[nw:]
+        gap_fail = np.array([round(int(g) / N, 2) >= (1 - self.coverage) for g in gap_n])
+        travel = ~gap_fail
+        n_send = np.where(travel, n_ent, 0).astype(np.int64)
+        sizes_all, _ = comm.allgather_concat(n_send)                      # world x nw entry counts
+        sizes_all = sizes_all.reshape(world, nw)
+        mine = np.nonzero(owner == rank)[0]                               # my windows (ascending batch index)
+        send_counts = np.array([int(n_send[owner == r].sum()) for r in range(world)], np.int64)
+        recv_counts = sizes_all[:, mine].sum(axis=1).astype(np.int64)
+        on_gpu = getattr(comm, "on_gpu", False) and hasattr(hist, "export_dev")
+        if on_gpu:                                 # entries stay in HBM: export -> NCCL all-to-all -> merge
+            _, keys, cnt, first = hist.export_dev(travel.astype(np.uint8), n_ent, comm)
+            rk, rc, rf = (comm.alltoall_dev(t, send_counts, recv_counts) for t in (keys, cnt, first))
+        else:
+            _, keys, cnt, first = hist.export(travel.astype(np.uint8), n_ent)
+            rk, rc, rf = (comm.alltoall(a, send_counts, recv_counts) for a in (keys, cnt, first))
+        # segment offsets of the received entries: source rank major, my windows inside
+        seg = np.concatenate([[0], np.cumsum(sizes_all[:, mine].reshape(-1))]).astype(np.int64)
+        my_pos = [positions[i] for i in mine]
+        log2cap = self._table_log2cap(k, N)
+        if log2cap == 0:
+            log2cap = max(6, int(math.ceil(math.log2(2 * N + 64))))
+        own = None
+        while True:
+            failed = 0
+            if len(mine):
+                own = self.msa.hist(k, v, my_pos, log2cap, empty=True)
+                try:
+                    own.merge_segments(seg, rk, rc, rf)
+                except _lib.MpbError as exc:
+                    if exc.code != -4:
+                        raise
+                    failed = 1
+            # a full table on one rank is a collective event: everybody rebuilds with doubled owner tables
+            if int(comm.allreduce_sum(np.array([failed], np.int64))[0]) == 0:
+                break
+            if own is not None:
+                own.close()
+                own = None
+            log2cap += 1
+        if own is not None:
+            own.add_counts(gap_n[mine], iupac_gap[mine])
+            st_own = own.summary()
+        else:
+            st_own = None
+        # all-gather the per-window results (fixed-size records, windows per rank padded to the maximum)
+        per = int(np.ceil(nw / world))
+        fields = [("ent", 4, np.float64), ("nuniq", 3, np.int64), ("mm_key", 1, np.uint64), ("mm_cnt", 1, np.int64),
+                  ("mm_first", 1, np.uint64), ("freq", 4 * k, np.int64), ("nn", 16 * (k - 1), np.int64)]
+        width = sum(f[1] for f in fields)
+        rec = np.zeros((per, width), np.int64)
+        if st_own is not None:
+            c0 = 0
+            for name, w, dt in fields:
+                rec[:len(mine), c0:c0 + w] = np.ascontiguousarray(st_own[name]).reshape(len(mine), w).view(np.int64)
+                c0 += w
+        rec_all, _ = comm.allgather_concat(rec.reshape(-1))
+        rec_all = rec_all.reshape(world, per, width)
+        st = {}
+        c0 = 0
+        for name, w, dt in fields:
+            full = np.zeros((nw, w), dt)
+            for r in range(world):
+                idx = np.nonzero(owner == r)[0]
+                full[idx] = np.ascontiguousarray(rec_all[r, :len(idx), c0:c0 + w]).view(dt)
+            st[name] = full.reshape(nw) if w == 1 else full
+            c0 += w
+        st["freq"] = st["freq"].reshape(nw, 4, k)
+        st["nn"] = st["nn"].reshape(nw, k - 1, 4, 4)
+        st["gap_n"] = gap_n
+        st["n_iupac_gap"] = iupac_gap
+        # windows that failed the gap gate did not travel: their (empty) statistics must not pass a later gate
+        st["nuniq"][gap_fail] = 0
+        return st, own, mine
+
+    def _entropies(self, hist, own, mine, owner, st, positions, alive):
         """(window index, (cBit, tBit)) of the windows that pass the entropy gate (core:722-726), rounded as the
         reference rounds them.  The device sums use another summation order than the reference: whenever that could
-        change a rounded digit or the gate, the table is dumped and the reference's float sum replayed."""
+        change a rounded digit or the gate, the table is dumped and the reference's float sum replayed (by the window's
+        owner in a sharded run; the result is shared)."""
         N = self.total_sequence_number
         thr = self.entropy_threshold
+        comm = self.comm
         ent = st["ent"].astype(np.float64).copy()
-        for wi in np.nonzero(alive & (st["n_iupac_gap"] > 0))[0].tolist():     # gap rows holding IUPAC cells
-            for _, c in self._iupac_gap_groups(hist, wi, positions[wi]):
+        with_iupac = np.nonzero(alive & (st["n_iupac_gap"] > 0))[0].tolist()
+        if with_iupac or (comm.world > 1 and bool((st["n_iupac_gap"] > 0).any())):
+            self._iupac_gap_groups(hist, 0)                   # collective in a sharded run: every rank, same moment
+        for wi in with_iupac:                                  # gap rows holding IUPAC cells
+            for _, c in self._iupac_gap_groups(hist, wi):
                 ent[wi, 2] += c
                 ent[wi, 3] += c * math.log2(c)
         cover_number = (N - st["gap_n"]).astype(np.float64)
@@ -569,11 +621,24 @@ class NN_degenerate(object):
         tie = lambda x: np.abs((x * 100.0) % 1.0 - 0.5) < 1e-6
         exact = tie(c_raw) | tie(t_raw) | (np.abs(t_raw - thr) < 1e-6) | (np.abs(c_raw) < 1e-9) | (np.abs(t_raw) < 1e-9)
         # (an exact zero prints as "-0.0" in the reference: round(-0.0, 2); that is left to the replay too)
+        cand = np.nonzero(alive & (exact | ~(t_raw > thr + 0.006)))[0].tolist()
+        replay = {}
+        need = [wi for wi in cand if exact[wi]]
+        if need:
+            vals = np.zeros((len(need), 2), np.float64)
+            for j, wi in enumerate(need):
+                if comm.world == 1:
+                    vals[j] = self._entropy_exact(hist, wi, wi, int(st["nuniq"][wi, 0] + st["nuniq"][wi, 1]))
+                elif owner[wi] == comm.rank:
+                    vals[j] = self._entropy_exact(own, int(np.searchsorted(mine, wi)), wi,
+                                                  int(st["nuniq"][wi, 0] + st["nuniq"][wi, 1]), hist)
+            if comm.world > 1:          # only the owner holds the merged table; -0.0 survives as a bit pattern
+                vals = comm.allreduce_sum(vals.view(np.int64)).view(np.float64)
+            replay = {wi: (float(vals[j, 0]), float(vals[j, 1])) for j, wi in enumerate(need)}
         out = []
-        for wi in np.nonzero(alive & (exact | ~(t_raw > thr + 0.006)))[0].tolist():
+        for wi in cand:
             if exact[wi]:
-                c_bit, t_bit = self._entropy_exact(hist, wi, positions[wi],
-                                                   int(st["nuniq"][wi, 0] + st["nuniq"][wi, 1]))
+                c_bit, t_bit = replay[wi]
             else:
                 c_bit, t_bit = round(float(c_raw[wi]), 2), round(float(t_raw[wi]), 2)
             if not t_bit > thr:                                               # core:723
@@ -581,7 +646,7 @@ class NN_degenerate(object):
         return out
 
     # -- rows, filters, side files ----------------------------------------------------------------------------
-    def _finish(self, hist, keep, res):
+    def _finish(self, hist, own, mine, owner, keep, res):
         """core:846-858 row assembly for the windows that went through the walk"""
         k, v, N = self.primer_length, self.variation, self.total_sequence_number
         gc_lo, gc_hi = float(self.GC[0]), float(self.GC[1])
@@ -604,12 +669,21 @@ class NN_degenerate(object):
         # perfect coverage of the chosen primer is already known from the walk (the last candidate scanned for the
         # track IS the final primer); a final scan pass is only needed for the per-sequence non-cover bits
         bits = None
-        if self.sidecars:
-            _, bits = self.msa.scan(k, v, self.fmask, self.rmask, pos, allow, bits_slot=np.arange(n, dtype=np.int32))
+        if self.sidecars or self.keep_bits:
+            _, bits = hist.cscan(self.fmask, self.rmask, _lib.make_cands(wis, allow), bits_slot=np.arange(n, dtype=np.int32))
             self.stats["scan_calls"] += 1
+            if self.keep_bits:
+                self.bit_vectors = [(int(p), bits[i]) for i, p in enumerate(pos.tolist())]
         perfect = res["counts"][:, 4]
         lap("fin_scan")
-        distinct = hist.match(wis, allow)
+        if self.comm.world == 1:
+            distinct = hist.match(wis, allow)
+        else:                          # the merged table of a window lives on its owner
+            distinct = np.zeros(n, np.int64)
+            sel = np.nonzero(owner[wis] == self.comm.rank)[0]
+            if len(sel):
+                distinct[sel] = own.match(np.searchsorted(mine, wis[sel]).astype(np.int32), allow[sel])
+            distinct = self.comm.allreduce_sum(distinct)
         lap("fin_match")
         tm_avg, gc, flags, deg, ndeg = self._primer_props(sets_arr, k, gc_lo, gc_hi)
         lap("fin_props")
@@ -617,7 +691,9 @@ class NN_degenerate(object):
         dimer = self._self_dimer(sets_list)                                   # core:487-503 for all windows at once
         lap("fin_dimer")
         lut = np.frombuffer(CODE_CHARS.encode(), dtype=np.uint8)
-        trace_str = lut[res["trace"][:int(res["trace_off"][n]), :k]].view("S%d" % k).ravel().astype(str).tolist()
+        trace_str = None
+        if res["trace"] is not None:
+            trace_str = lut[res["trace"][:int(res["trace_off"][n]), :k]].view("S%d" % k).ravel().astype(str).tolist()
         out = []
         for i in range(n):
             wi, p, c_bit, t_bit, cover_number, _ = keep[i]
@@ -641,8 +717,10 @@ class NN_degenerate(object):
             init, fm, rm = (int(x) for x in res["counts"][i, :3])
             row = [p, c_bit, t_bit, primer_string(sets), int(ndeg[i]), nonsense, int(perfect[i]), init + fm,
                    init + rm, float(tm_avg[i]), float(gc[i]) if not notes else "|".join(notes)]
-            a, b = int(res["trace_off"][i]), int(res["trace_off"][i + 1])
-            rec = {"row": row, "trace": trace_str[a:b]}
+            rec = {"row": row}
+            if trace_str is not None:
+                a, b = int(res["trace_off"][i]), int(res["trace_off"][i + 1])
+                rec["trace"] = trace_str[a:b]
             if self.sidecars:
                 rec["non_cov"], rec["gap_ids"] = self._sidecars(hist, wi, p, sets, bits[i], seqkeys[i])
             out.append(rec)

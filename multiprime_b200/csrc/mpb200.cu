@@ -31,101 +31,7 @@ int mpb_fail(int code, const char* fmt, ...) {
 #define CK MPB_CK
 #define LAUNCH MPB_LAUNCH
 
-struct mpb_msa {
-    mpb_ctx* ctx;
-    int64_t n_seq, nsp, n_col;
-    int ncw;            // column words incl. the trailing zero word
-    uint32_t* planes;   // [ncw][nsp] uint4{A,C,G,T}
-    int32_t* lens;      // [nsp]
-    int* err;           // device error flags
-    int64_t row0;       // global index of local sequence 0 (sequence-sharded runs)
-};
-
-struct mpb_hist {
-    mpb_msa* msa;
-    int k, v, nw, log2cap;
-    uint64_t* keys;   // [nw][cap]
-    uint32_t* cnt;    // [nw][cap]
-    uint64_t* first;  // [nw][cap]
-    int32_t* win_pos; // device copy
-    unsigned long long* gap_n;        // [nw]
-    unsigned long long* iupac_gap_n;  // [nw]
-    unsigned long long* n_entries;    // [nw] distinct table entries inserted by k_hist
-    int32_t* exc;                     // [2*exc_max]
-    unsigned long long* exc_n;
-    int64_t exc_max;
-};
-
-static bool is_device_ptr(const void* p) {
-    if (!p) return false;
-    cudaPointerAttributes at;
-    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
-        cudaGetLastError();
-        return false;
-    }
-    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
-}
-
-// input that may live on host or device: dev() is a device pointer valid on the ctx stream
-struct InBuf {
-    mpb_ctx* ctx;
-    void* tmp = nullptr;
-    const void* d = nullptr;
-    int rc = 0;
-    InBuf(mpb_ctx* c, const void* hd, size_t bytes) : ctx(c) {
-        if (!hd || bytes == 0) return;
-        if (is_device_ptr(hd)) {
-            d = hd;
-            return;
-        }
-        cudaError_t e = cudaMallocAsync(&tmp, bytes, ctx->stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(tmp, hd, bytes, cudaMemcpyHostToDevice, ctx->stream);
-        if (e != cudaSuccess) rc = fail(MPB_ECUDA, "staging input: %s", cudaGetErrorString(e));
-        d = tmp;
-    }
-    ~InBuf() {
-        if (tmp) cudaFreeAsync(tmp, ctx->stream);
-    }
-    template <class T>
-    const T* dev() const {
-        return (const T*)d;
-    }
-};
-
-// output that may live on host or device; finish() copies back (async) — caller syncs when any output is host
-struct OutBuf {
-    mpb_ctx* ctx;
-    void* tmp = nullptr;
-    void* d = nullptr;
-    void* host = nullptr;
-    size_t bytes;
-    int rc = 0;
-    OutBuf(mpb_ctx* c, void* hd, size_t nbytes) : ctx(c), bytes(nbytes) {
-        if (!hd || nbytes == 0) return;
-        if (is_device_ptr(hd)) {
-            d = hd;
-            return;
-        }
-        host = hd;
-        cudaError_t e = cudaMallocAsync(&tmp, nbytes, ctx->stream);
-        if (e != cudaSuccess) rc = fail(MPB_ENOMEM, "staging output: %s", cudaGetErrorString(e));
-        d = tmp;
-    }
-    ~OutBuf() {
-        if (tmp) cudaFreeAsync(tmp, ctx->stream);
-    }
-    template <class T>
-    T* dev() const {
-        return (T*)d;
-    }
-    bool is_host() const { return host != nullptr; }
-    cudaError_t finish() {
-        if (host) return cudaMemcpyAsync(host, tmp, bytes, cudaMemcpyDeviceToHost, ctx->stream);
-        return cudaSuccess;
-    }
-};
-
-static int check_flags(mpb_ctx* ctx, int* dflags) {
+int mpb_check_flags(mpb_ctx* ctx, int* dflags) {
     int f = 0;
     CK(cudaMemcpyAsync(&f, dflags, sizeof f, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -172,10 +78,23 @@ extern "C" int mpb_ctx_create(int device, mpb_ctx** out) {
     c->sm_count = prop.multiProcessorCount;
     c->profile = false;
     c->pending_units = 0;
+    c->copy_stream = nullptr;
+    if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete c;
+        return fail(MPB_ECUDA, "copy stream");
+    }
     *out = c;
     return 0;
 }
-extern "C" void mpb_ctx_destroy(mpb_ctx* ctx) { delete ctx; }
+extern "C" void mpb_ctx_destroy(mpb_ctx* ctx) {
+    if (!ctx) return;
+    for (auto& r : ctx->recs) {
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    delete ctx;
+}
 extern "C" int mpb_ctx_set_stream(mpb_ctx* ctx, void* s) {
     if (!ctx) return fail(MPB_EINVAL, "ctx is NULL");
     ctx->stream = (cudaStream_t)s;
@@ -187,6 +106,15 @@ extern "C" int mpb_ctx_sync(mpb_ctx* ctx) {
     return 0;
 }
 extern "C" int64_t mpb_ctx_launches(mpb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// plain copy between any two of host / device memory on the context's stream, synchronised on return
+extern "C" int mpb_ctx_memcpy(mpb_ctx* ctx, void* dst, const void* src, int64_t bytes) {
+    if (!ctx || !dst || !src || bytes < 0) return fail(MPB_EINVAL, "bad argument");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDefault, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
 
 extern "C" int mpb_ctx_profile(mpb_ctx* ctx, int enable) {
     if (!ctx) return fail(MPB_EINVAL, "ctx is NULL");
@@ -205,9 +133,14 @@ extern "C" int mpb_ctx_profile_read(mpb_ctx* ctx, const char* kernel, double* ms
             cudaEventDestroy(r.e1);
         }
         ctx->recs.clear();
+        ctx->extra_units.clear();
         return 0;
     }
     double t = 0, u = 0;
+    {
+        auto it = ctx->extra_units.find(kernel);  // units counted on the device (candidates of the resident walk)
+        if (it != ctx->extra_units.end()) u += it->second;
+    }
     int64_t n = 0;
     for (auto& r : ctx->recs)
         if (strncmp(r.name, kernel, strlen(kernel)) == 0 && (r.name[strlen(kernel)] == 0 || r.name[strlen(kernel)] == '<')) {
@@ -226,36 +159,96 @@ extern "C" int mpb_ctx_profile_read(mpb_ctx* ctx, const char* kernel, double* ms
 // ------------------------------------------------------------------------------------------------------
 // alignment upload: nibble rows -> bit-planes
 // ------------------------------------------------------------------------------------------------------
-// thread = (sequence, column word); sequence fastest so the plane stores coalesce
-__global__ void k_pack_planes(const uint8_t* __restrict__ packed, int64_t n_seq, int64_t nsp, int64_t row_bytes,
-                              int n_col, const int32_t* __restrict__ lens, int ncw, uint32_t* __restrict__ planes) {
-    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int cw = blockIdx.y;
-    if (s >= nsp) return;
-    uint32_t a = 0, c = 0, g = 0, t = 0;
-    if (s < n_seq && cw < ncw - 1) {
-        int len = lens[s];
-        const uint8_t* row = packed + s * row_bytes;
-        int col0 = cw * 32;
-        for (int i = 0; i < 32; i += 2) {
-            int col = col0 + i;
-            if (col >= len) break;
-            uint32_t b = row[col >> 1];
-            uint32_t x = b & 15u;
-            uint32_t y = (col + 1 < len) ? (b >> 4) : 0u;
-            a |= ((x & 1u) << i) | ((y & 1u) << (i + 1));
-            c |= (((x >> 1) & 1u) << i) | (((y >> 1) & 1u) << (i + 1));
-            g |= (((x >> 2) & 1u) << i) | (((y >> 2) & 1u) << (i + 1));
-            t |= (((x >> 3) & 1u) << i) | (((y >> 3) & 1u) << (i + 1));
+// nibble rows -> row planes.  A block stages PACK_ROWS rows x PACK_SEG bytes (512 columns) through shared memory so
+// that the global reads are contiguous pieces of each row (the first version read 16 B at a row stride per thread);
+// thread = (row, column word), rows fastest, so the uint4 plane stores coalesce too.
+#define PACK_ROWS 64
+#define PACK_SEG 256
+__global__ void __launch_bounds__(256)
+k_pack_planes(const uint8_t* __restrict__ packed, int64_t row_first, int64_t n_rows, int64_t n_seq, int64_t nsp,
+              int64_t row_bytes, const int32_t* __restrict__ lens, int ncw, uint32_t* __restrict__ planes) {
+    __shared__ __align__(16) uint8_t tile[PACK_ROWS][PACK_SEG + 4];
+    const int64_t r0 = (int64_t)blockIdx.x * PACK_ROWS;  // relative to row_first
+    const int64_t seg0 = (int64_t)blockIdx.y * PACK_SEG;
+    for (int i = threadIdx.x; i < PACK_ROWS * PACK_SEG; i += 256) {
+        const int r = i / PACK_SEG, b = i % PACK_SEG;
+        const int64_t s = row_first + r0 + r;
+        uint8_t x = 0;
+        if (r0 + r < n_rows && s < n_seq && seg0 + b < row_bytes) x = packed[(r0 + r) * row_bytes + seg0 + b];
+        tile[r][b] = x;
+    }
+    __syncthreads();
+    const int r = threadIdx.x & (PACK_ROWS - 1);
+    const int64_t s = row_first + r0 + r;
+    if (r0 + r >= n_rows || s >= nsp) return;
+    const int len = s < n_seq ? lens[s] : 0;
+    for (int cwl = threadIdx.x / PACK_ROWS; cwl < PACK_SEG / 16; cwl += 256 / PACK_ROWS) {
+        const int cw = blockIdx.y * (PACK_SEG / 16) + cwl;
+        if (cw >= ncw) break;
+        uint32_t a = 0, c = 0, g = 0, t = 0;
+        const int col0 = cw * 32;
+        if (cw < ncw - 1) {
+            for (int i = 0; i < 32; i += 2) {
+                const int col = col0 + i;
+                if (col >= len) break;
+                const uint32_t b = tile[r][cwl * 16 + (i >> 1)];
+                const uint32_t x = b & 15u;
+                const uint32_t y = (col + 1 < len) ? (b >> 4) : 0u;
+                a |= ((x & 1u) << i) | ((y & 1u) << (i + 1));
+                c |= (((x >> 1) & 1u) << i) | (((y >> 1) & 1u) << (i + 1));
+                g |= (((x >> 2) & 1u) << i) | (((y >> 2) & 1u) << (i + 1));
+                t |= (((x >> 3) & 1u) << i) | (((y >> 3) & 1u) << (i + 1));
+            }
+        }
+        reinterpret_cast<uint4*>(planes)[(int64_t)cw * nsp + s] = make_uint4(a, c, g, t);
+    }
+}
+
+// row planes -> column view: a 32 x 32 bit transpose per (column word, 32-sequence word, base).  Block = 32 warps =
+// 32 consecutive sequence words of one column word; warp: lane = sequence, one ballot per (base, column); the 32 x 4
+// x 32 result words go through shared memory so that every column-plane row is written in 128-byte pieces.
+__global__ void __launch_bounds__(1024)
+k_build_colp(const uint32_t* __restrict__ planes, int64_t nsp, int64_t nwords, int64_t word_first, int64_t n_words_chunk,
+             uint32_t* __restrict__ colp) {
+    __shared__ uint32_t tile[32 * 4][33];
+    const int cw = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t w = word_first + (int64_t)blockIdx.x * 32 + warp;
+    const bool live = (int64_t)blockIdx.x * 32 + warp < n_words_chunk && w < nwords;
+    uint4 q = make_uint4(0, 0, 0, 0);
+    if (live) q = __ldg(reinterpret_cast<const uint4*>(planes) + (int64_t)cw * nsp + w * 32 + lane);
+#pragma unroll 4
+    for (int c = 0; c < 32; ++c) {
+        const unsigned ba = __ballot_sync(0xffffffffu, (q.x >> c) & 1u), bc = __ballot_sync(0xffffffffu, (q.y >> c) & 1u),
+                       bg = __ballot_sync(0xffffffffu, (q.z >> c) & 1u), bt = __ballot_sync(0xffffffffu, (q.w >> c) & 1u);
+        if (lane == 0) {
+            tile[c * 4 + 0][warp] = ba;
+            tile[c * 4 + 1][warp] = bc;
+            tile[c * 4 + 2][warp] = bg;
+            tile[c * 4 + 3][warp] = bt;
         }
     }
-    reinterpret_cast<uint4*>(planes)[(int64_t)cw * nsp + s] = make_uint4(a, c, g, t);
+    __syncthreads();
+    // thread (row = c*4 + b, word): 128 rows x 32 words = 4 per thread
+    for (int i = threadIdx.x; i < 128 * 32; i += 1024) {
+        const int row = i >> 5, ww = i & 31;
+        const int64_t wo = word_first + (int64_t)blockIdx.x * 32 + ww;
+        if ((int64_t)blockIdx.x * 32 + ww < n_words_chunk && wo < nwords)
+            colp[((int64_t)cw * 128 + row) * nwords + wo] = tile[row][ww];
+    }
+}
+
+__global__ void k_fill_u32(uint32_t* __restrict__ dst, int64_t n, uint32_t value) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = value;
 }
 
 __global__ void k_fill_i32(int32_t* __restrict__ dst, int64_t n, int64_t n_set, int32_t value) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = i < n_set ? value : 0;
 }
+
+#define UPLOAD_CHUNK_ROWS 65536  // multiple of 1024 (k_build_colp tiles) and of PACK_ROWS
 
 extern "C" int mpb_msa_upload(mpb_ctx* ctx, const uint8_t* packed4, int64_t n_seq, int64_t n_col, int64_t row_bytes,
                               const int32_t* lens, mpb_msa** out) {
@@ -266,22 +259,22 @@ extern "C" int mpb_msa_upload(mpb_ctx* ctx, const uint8_t* packed4, int64_t n_se
     if (n_seq >= (1ll << 31)) return fail(MPB_EINVAL, "n_seq must be < 2^31");
     CK(cudaSetDevice(ctx->device));
     mpb_msa* m = new mpb_msa;
+    memset(m, 0, sizeof *m);
     m->ctx = ctx;
     m->n_seq = n_seq;
     m->nsp = (n_seq + 127) / 128 * 128;
+    m->nwords = m->nsp / 32;
     m->n_col = n_col;
     m->ncw = (int)((n_col + 31) / 32) + 1;
-    m->planes = nullptr;
-    m->lens = nullptr;
-    m->err = nullptr;
-    m->row0 = 0;
-    size_t pbytes = (size_t)m->ncw * 4 * m->nsp * sizeof(uint32_t);
+    const size_t pbytes = (size_t)m->ncw * 4 * m->nsp * sizeof(uint32_t);
+    const size_t crows = (size_t)(m->ncw - 1) * 128 + 2;
     cudaError_t e = cudaMallocAsync(&m->planes, pbytes, ctx->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&m->colp, crows * m->nwords * 4, ctx->stream);
     if (e == cudaSuccess) e = cudaMallocAsync(&m->lens, m->nsp * sizeof(int32_t), ctx->stream);
     if (e == cudaSuccess) e = cudaMallocAsync(&m->err, sizeof(int), ctx->stream);
     if (e != cudaSuccess) {
         mpb_msa_free(m);
-        return fail(MPB_ENOMEM, "alignment planes (%zu bytes): %s", pbytes, cudaGetErrorString(e));
+        return fail(MPB_ENOMEM, "alignment planes (2 x %zu bytes): %s", pbytes, cudaGetErrorString(e));
     }
     CK(cudaMemsetAsync(m->err, 0, sizeof(int), ctx->stream));
     std::vector<int32_t> hl;
@@ -298,16 +291,62 @@ extern "C" int mpb_msa_upload(mpb_ctx* ctx, const uint8_t* packed4, int64_t n_se
     } else {
         LAUNCH(ctx, k_fill_i32, (unsigned)((m->nsp + 255) / 256), 256, 0, m->lens, m->nsp, n_seq, (int32_t)n_col);
     }
-    {
-        InBuf in(ctx, packed4, (size_t)n_seq * row_bytes);
-        if (in.rc) {
-            mpb_msa_free(m);
-            return in.rc;
+    LAUNCH(ctx, k_fill_u32, (unsigned)((m->nwords + 255) / 256), 256, 0, m->colp + (size_t)MPB_COLP_ONES(m) * m->nwords,
+           m->nwords, 0xFFFFFFFFu);
+    LAUNCH(ctx, k_fill_u32, (unsigned)((m->nwords + 255) / 256), 256, 0, m->colp + (size_t)MPB_COLP_ZEROS(m) * m->nwords,
+           m->nwords, 0u);
+    // rows travel in chunks: the H2D copy of chunk i+1 (copy stream) overlaps the plane / column-view build of chunk i
+    const bool on_dev = mpb_is_device_ptr(packed4);
+    const int64_t chunk = UPLOAD_CHUNK_ROWS;
+    uint8_t* stage[2] = {nullptr, nullptr};
+    cudaEvent_t copied[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr};
+    int rc = 0;
+    if (!on_dev) {
+        const size_t sb = (size_t)(n_seq < chunk ? n_seq : chunk) * row_bytes;
+        for (int i = 0; i < 2 && rc == 0; ++i) {
+            if (cudaMallocAsync(&stage[i], sb, ctx->stream) != cudaSuccess || cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&consumed[i], cudaEventDisableTiming) != cudaSuccess)
+                rc = fail(MPB_ENOMEM, "upload staging buffers");
         }
-        dim3 grid((unsigned)((m->nsp + 255) / 256), (unsigned)m->ncw);
-        LAUNCH(ctx, k_pack_planes, grid, 256, 0, in.dev<uint8_t>(), n_seq, m->nsp, row_bytes, (int)n_col, m->lens,
-               m->ncw, m->planes);
-        CK(cudaStreamSynchronize(ctx->stream));  // hl / staging lifetime
+        if (rc == 0 && cudaEventRecord(consumed[0], ctx->stream) != cudaSuccess) rc = fail(MPB_ECUDA, "event record");
+        if (rc == 0 && cudaEventRecord(consumed[1], ctx->stream) != cudaSuccess) rc = fail(MPB_ECUDA, "event record");
+    }
+    int slot = 0;
+    for (int64_t r0 = 0; r0 < m->nsp && rc == 0; r0 += chunk, slot ^= 1) {
+        const int64_t rows = (m->nsp - r0 < chunk) ? m->nsp - r0 : chunk;          // plane rows (incl. padding rows)
+        const int64_t src_rows = r0 >= n_seq ? 0 : ((n_seq - r0 < chunk) ? n_seq - r0 : chunk);
+        const uint8_t* src = packed4 + r0 * row_bytes;
+        if (!on_dev && src_rows > 0) {
+            cudaError_t ce = cudaStreamWaitEvent(ctx->copy_stream, consumed[slot], 0);  // staging slot free again
+            if (ce == cudaSuccess)
+                ce = cudaMemcpyAsync(stage[slot], src, (size_t)src_rows * row_bytes, cudaMemcpyHostToDevice, ctx->copy_stream);
+            if (ce == cudaSuccess) ce = cudaEventRecord(copied[slot], ctx->copy_stream);
+            if (ce == cudaSuccess) ce = cudaStreamWaitEvent(ctx->stream, copied[slot], 0);
+            if (ce != cudaSuccess) {
+                rc = fail(MPB_ECUDA, "upload chunk: %s", cudaGetErrorString(ce));
+                break;
+            }
+            src = stage[slot];
+        }
+        dim3 grid((unsigned)((rows + PACK_ROWS - 1) / PACK_ROWS), (unsigned)((m->ncw * 16 + PACK_SEG - 1) / PACK_SEG));
+        k_pack_planes<<<grid, 256, 0, ctx->stream>>>(src, r0, rows, n_seq, m->nsp, row_bytes, m->lens, m->ncw, m->planes);
+        ctx->launches++;
+        dim3 g2((unsigned)((rows / 32 + 31) / 32), (unsigned)(m->ncw - 1));
+        k_build_colp<<<g2, 1024, 0, ctx->stream>>>(m->planes, m->nsp, m->nwords, r0 / 32, rows / 32, m->colp);
+        ctx->launches++;
+        if (cudaGetLastError() != cudaSuccess) rc = fail(MPB_ECUDA, "upload kernels");
+        if (!on_dev && rc == 0 && cudaEventRecord(consumed[slot], ctx->stream) != cudaSuccess) rc = fail(MPB_ECUDA, "event record");
+    }
+    cudaError_t se = cudaStreamSynchronize(ctx->stream);  // hl / staging lifetime
+    for (int i = 0; i < 2; ++i) {
+        if (stage[i]) cudaFreeAsync(stage[i], ctx->stream);
+        if (copied[i]) cudaEventDestroy(copied[i]);
+        if (consumed[i]) cudaEventDestroy(consumed[i]);
+    }
+    if (rc == 0 && se != cudaSuccess) rc = fail(MPB_ECUDA, "upload: %s", cudaGetErrorString(se));
+    if (rc) {
+        mpb_msa_free(m);
+        return rc;
     }
     *out = m;
     return 0;
@@ -316,6 +355,7 @@ extern "C" int mpb_msa_upload(mpb_ctx* ctx, const uint8_t* packed4, int64_t n_se
 extern "C" void mpb_msa_free(mpb_msa* m) {
     if (!m) return;
     if (m->planes) cudaFreeAsync(m->planes, m->ctx->stream);
+    if (m->colp) cudaFreeAsync(m->colp, m->ctx->stream);
     if (m->lens) cudaFreeAsync(m->lens, m->ctx->stream);
     if (m->err) cudaFreeAsync(m->err, m->ctx->stream);
     delete m;
@@ -417,7 +457,8 @@ extern "C" int mpb_seq_attr(mpb_msa* m, int32_t* lead_hd, int32_t* rstrip_hd) {
 
 __device__ __forceinline__ void hist_stage(unsigned long long* s_key, unsigned int* s_cnt, unsigned long long* s_first,
                                            uint64_t* K, uint32_t* C, uint64_t* F, int log2cap, uint64_t key,
-                                           uint32_t add, uint64_t ord, int* err, unsigned long long* n_new) {
+                                           uint32_t add, uint64_t ord, int* err, unsigned long long* n_new,
+                                           uint32_t* E) {
     uint32_t h = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 55) & (HIST_SLOTS - 1);
     for (int probe = 0; probe < HIST_PROBES; ++probe) {
         unsigned long long cur = s_key[h];
@@ -432,7 +473,7 @@ __device__ __forceinline__ void hist_stage(unsigned long long* s_key, unsigned i
         }
         h = (h + 1) & (HIST_SLOTS - 1);
     }
-    mpb_table_add(K, C, F, log2cap, key, add, ord, err, n_new);  // staging table crowded (variable window): go global
+    mpb_table_add(K, C, F, log2cap, key, add, ord, err, n_new, E);  // staging table crowded (variable window): go global
 }
 
 // block (x, y): sequence tiles [x*HIST_TILES, (x+1)*HIST_TILES) ; blockIdx.y strides over the windows of the batch
@@ -441,7 +482,10 @@ k_hist(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq, const int32_
        const int32_t* __restrict__ win_pos, int nw, uint64_t* __restrict__ keys, uint32_t* __restrict__ cnt,
        uint64_t* __restrict__ first, int log2cap, unsigned long long* __restrict__ gap_n,
        unsigned long long* __restrict__ iupac_gap_n, int32_t* __restrict__ exc, unsigned long long* __restrict__ exc_n,
-       long long exc_max, long long row0, unsigned long long* __restrict__ n_entries, int* __restrict__ err) {
+       long long exc_max, long long row0, unsigned long long* __restrict__ n_entries, uint32_t* __restrict__ elist,
+       uint32_t* __restrict__ spec_bits, uint32_t* __restrict__ gap_bits, long long nwords, uint4* __restrict__ spec_win,
+       int32_t* __restrict__ spec_row, unsigned long long* __restrict__ spec_n, long long spec_cap,
+       int* __restrict__ err) {
     __shared__ unsigned long long s_key[HIST_SLOTS];
     __shared__ unsigned long long s_first[HIST_SLOTS];
     __shared__ unsigned int s_cnt[HIST_SLOTS];
@@ -466,6 +510,7 @@ k_hist(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq, const int32_
         uint64_t* K = keys + (uint64_t)wi * cap;
         uint32_t* C = cnt + (uint64_t)wi * cap;
         uint64_t* F = first + (uint64_t)wi * cap;
+        uint32_t* E = elist + (uint64_t)wi * cap;
         const uint4* __restrict__ wbase = reinterpret_cast<const uint4*>(pl) + (int64_t)(p >> 5) * nsp;
         const int sh = p & 31;
         // pass 1: plain rows (funnel shift only); rows needing gap patching / IUPAC expansion / ragged handling are
@@ -496,11 +541,18 @@ k_hist(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq, const int32_
             const unsigned gb = __ballot_sync(0xffffffffu, plain && isgap);
             if (lane == 0 && gb) atomicAdd(&s_gap, (unsigned)__popc(gb));
             const unsigned smask = __ballot_sync(0xffffffffu, plain);
+            {   // row classes of this 32-sequence word for the column scan (padding rows count as special)
+                const long long word = tile * (HIST_THREADS / 32) + (threadIdx.x >> 5);
+                if (lane == 0 && word < nwords) {
+                    spec_bits[(long long)wi * nwords + word] = ~smask;
+                    gap_bits[(long long)wi * nwords + word] = gb;
+                }
+            }
             if (plain) {
                 const unsigned peers = __match_any_sync(smask, key);
                 if (lane == __ffs(peers) - 1)  // lowest lane = lowest sequence index = first seen
                     hist_stage(s_key, s_cnt, s_first, K, C, F, log2cap, key, (uint32_t)__popc(peers),
-                               (uint64_t)(row0 + s) << 16, err, &n_entries[wi]);
+                               (uint64_t)(row0 + s) << 16, err, &n_entries[wi], E);
             }
         }
         __syncthreads();
@@ -527,9 +579,18 @@ k_hist(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq, const int32_
                 }
                 if (!mpb_load_window(pl, nsp, s, lens[s], p, k, kmask, w)) atomicOr(err, MPB_ERR_SHORT_ROW);
                 const bool isgap = __popc(w.gapv) > v;
-                if (isgap) atomicAdd(&s_gap, 1u);
+                if (isgap) {
+                    atomicAdd(&s_gap, 1u);
+                    atomicOr(&gap_bits[(long long)wi * nwords + (s >> 5)], 1u << (s & 31));
+                } else {  // the patched window itself, for the column scan's special pass
+                    const unsigned long long slot = atomicAdd(&spec_n[wi], 1ull);
+                    if ((long long)slot < spec_cap) {
+                        spec_win[(long long)wi * spec_cap + slot] = make_uint4(w.a, w.c, w.g, w.t);
+                        spec_row[(long long)wi * spec_cap + slot] = (int32_t)s;
+                    }
+                }
                 if (!isgap && w.multi == 0) {
-                    hist_stage(s_key, s_cnt, s_first, K, C, F, log2cap, mpb_key(w.c, w.g, w.t, w.gapv, k), 1u, gs << 16, err, &n_entries[wi]);
+                    hist_stage(s_key, s_cnt, s_first, K, C, F, log2cap, mpb_key(w.c, w.g, w.t, w.gapv, k), 1u, gs << 16, err, &n_entries[wi], E);
                 } else if (!isgap) {
                     const uint32_t total = mpb_expansions(w);
                     if (total > MPB_MAX_EXP) {
@@ -539,11 +600,11 @@ k_hist(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq, const int32_
                             uint32_t a, c, g, tt;
                             mpb_expand(w, e, a, c, g, tt);
                             hist_stage(s_key, s_cnt, s_first, K, C, F, log2cap, mpb_key(c, g, tt, w.gapv, k), 1u,
-                                       (gs << 16) | e, err, &n_entries[wi]);
+                                       (gs << 16) | e, err, &n_entries[wi], E);
                         }
                     }
                 } else if (w.multi == 0) {
-                    hist_stage(s_key, s_cnt, s_first, K, C, F, log2cap, mpb_key(w.c, w.g, w.t, w.gapv, k), 1u, gs << 16, err, &n_entries[wi]);
+                    hist_stage(s_key, s_cnt, s_first, K, C, F, log2cap, mpb_key(w.c, w.g, w.t, w.gapv, k), 1u, gs << 16, err, &n_entries[wi], E);
                 } else {
                     atomicAdd(&iupac_gap_n[wi], 1ull);
                     unsigned long long slot = atomicAdd(exc_n, 1ull);
@@ -558,7 +619,7 @@ k_hist(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq, const int32_
         for (int i = threadIdx.x; i < HIST_SLOTS; i += HIST_THREADS) {  // flush + clear the staging table
             const unsigned long long key = s_key[i];
             if (key != MPB_KEY_EMPTY_D) {
-                mpb_table_add(K, C, F, log2cap, key, s_cnt[i], s_first[i], err, &n_entries[wi]);
+                mpb_table_add(K, C, F, log2cap, key, s_cnt[i], s_first[i], err, &n_entries[wi], E);
                 s_key[i] = MPB_KEY_EMPTY_D;
                 s_first[i] = ~0ull;
                 s_cnt[i] = 0;
@@ -777,11 +838,48 @@ extern "C" int mpb_window_prefilter(mpb_msa* m, int k, int v, const int32_t* win
     CK(o0.finish());
     CK(o1.finish());
     CK(cudaFreeAsync(bins, ctx->stream));
-    return check_flags(ctx, m->err);
+    return mpb_check_flags(ctx, m->err);
 }
 
-extern "C" int mpb_hist_build(mpb_msa* m, int k, int v, const int32_t* win_pos, int32_t nw, int log2_cap,
-                              mpb_hist** out) {
+static int hist_alloc_spec(mpb_hist* h, int64_t spec_cap) {
+    mpb_ctx* ctx = h->msa->ctx;
+    h->spec_cap = spec_cap;
+    cudaError_t e = cudaMallocAsync(&h->spec_win, (size_t)h->nw * spec_cap * sizeof(uint4), ctx->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&h->spec_row, (size_t)h->nw * spec_cap * 4, ctx->stream);
+    if (e != cudaSuccess) return fail(MPB_ENOMEM, "special-row lists (%d windows x %lld rows): %s", h->nw, (long long)spec_cap,
+                                      cudaGetErrorString(e));
+    return 0;
+}
+
+static int hist_launch_build(mpb_hist* h) {
+    mpb_msa* m = h->msa;
+    mpb_ctx* ctx = m->ctx;
+    const int nw = h->nw;
+    const uint64_t slots = (uint64_t)nw << h->log2cap;
+    CK(cudaMemsetAsync(h->keys, 0xFF, slots * 8, ctx->stream));
+    CK(cudaMemsetAsync(h->cnt, 0, slots * 4, ctx->stream));
+    CK(cudaMemsetAsync(h->first, 0xFF, slots * 8, ctx->stream));
+    CK(cudaMemsetAsync(h->gap_n, 0, (size_t)nw * 8, ctx->stream));
+    CK(cudaMemsetAsync(h->iupac_gap_n, 0, (size_t)nw * 8, ctx->stream));
+    CK(cudaMemsetAsync(h->n_entries, 0, (size_t)nw * 8, ctx->stream));
+    CK(cudaMemsetAsync(h->spec_n, 0, (size_t)nw * 8, ctx->stream));
+    CK(cudaMemsetAsync(h->exc_n, 0, 8, ctx->stream));
+    const unsigned gx = (unsigned)((m->n_seq + (long long)HIST_THREADS * HIST_TILES - 1) / ((long long)HIST_THREADS * HIST_TILES));
+    unsigned gy = (unsigned)nw;
+    const unsigned want = (unsigned)ctx->sm_count * 8;
+    if (gx >= want) gy = 1;
+    else if (gy > (want + gx - 1) / gx) gy = (want + gx - 1) / gx;
+    ctx->pending_units = (double)nw * (double)m->n_seq;  // (window, sequence) k-mers extracted
+    LAUNCH(ctx, k_hist, dim3(gx, gy), HIST_THREADS, 0, m->planes, m->nsp, m->n_seq, m->lens, h->k, h->v, h->win_pos, nw,
+           h->keys, h->cnt, h->first, h->log2cap, h->gap_n, h->iupac_gap_n, h->exc, h->exc_n, (long long)h->exc_max,
+           (long long)m->row0, h->n_entries, h->elist, h->spec_bits, h->gap_bits, (long long)m->nwords, h->spec_win,
+           h->spec_row, h->spec_n, (long long)h->spec_cap, m->err);
+    return 0;
+}
+
+// Allocate the tables of nw windows without filling them from the alignment (owner tables of a sequence-sharded run
+// receive their entries through mpb_hist_merge only) when `fill` is 0.
+static int hist_create(mpb_msa* m, int k, int v, const int32_t* win_pos, int32_t nw, int log2_cap, int fill, mpb_hist** out) {
     if (!m || !win_pos || !out) return fail(MPB_EINVAL, "NULL argument");
     if (k < 3 || k > MPB_MAX_K) return fail(MPB_EINVAL, "primer length %d outside 3..%d", k, MPB_MAX_K);
     if (v < 0 || nw < 1) return fail(MPB_EINVAL, "bad v=%d or nw=%d", v, nw);
@@ -795,52 +893,88 @@ extern "C" int mpb_hist_build(mpb_msa* m, int k, int v, const int32_t* win_pos, 
         while ((1ll << log2_cap) < 2 * m->n_seq + 64) ++log2_cap;
     }
     if (log2_cap > 31) return fail(MPB_EINVAL, "log2_cap %d too large", log2_cap);
-    mpb_hist* h = new mpb_hist;
-    memset(h, 0, sizeof *h);
+    mpb_hist* h = new mpb_hist();
     h->msa = m;
     h->k = k;
     h->v = v;
     h->nw = nw;
     h->log2cap = log2_cap;
     h->exc_max = 1 << 20;
+    h->h_win_pos.assign(win_pos, win_pos + nw);
     const uint64_t slots = (uint64_t)nw << log2_cap;
     cudaError_t e = cudaMallocAsync(&h->keys, slots * 8, ctx->stream);
     if (e == cudaSuccess) e = cudaMallocAsync(&h->cnt, slots * 4, ctx->stream);
     if (e == cudaSuccess) e = cudaMallocAsync(&h->first, slots * 8, ctx->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&h->elist, slots * 4, ctx->stream);
     if (e == cudaSuccess) e = cudaMallocAsync(&h->win_pos, (size_t)nw * 4, ctx->stream);
     if (e == cudaSuccess) e = cudaMallocAsync(&h->gap_n, (size_t)nw * 8, ctx->stream);
     if (e == cudaSuccess) e = cudaMallocAsync(&h->iupac_gap_n, (size_t)nw * 8, ctx->stream);
     if (e == cudaSuccess) e = cudaMallocAsync(&h->n_entries, (size_t)nw * 8, ctx->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&h->spec_n, (size_t)nw * 8, ctx->stream);
     if (e == cudaSuccess) e = cudaMallocAsync(&h->exc, (size_t)h->exc_max * 8, ctx->stream);
     if (e == cudaSuccess) e = cudaMallocAsync(&h->exc_n, 8, ctx->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&h->spec_bits, (size_t)nw * m->nwords * 4, ctx->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&h->gap_bits, (size_t)nw * m->nwords * 4, ctx->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&h->freq, (size_t)nw * 4 * k * 8, ctx->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&h->nn, (size_t)nw * (k - 1) * 16 * 8, ctx->stream);
     if (e != cudaSuccess) {
         mpb_hist_free(h);
         return fail(MPB_ENOMEM, "haplotype tables (%d windows x 2^%d slots): %s", nw, log2_cap, cudaGetErrorString(e));
     }
-    CK(cudaMemsetAsync(h->keys, 0xFF, slots * 8, ctx->stream));
-    CK(cudaMemsetAsync(h->cnt, 0, slots * 4, ctx->stream));
-    CK(cudaMemsetAsync(h->first, 0xFF, slots * 8, ctx->stream));
-    CK(cudaMemsetAsync(h->gap_n, 0, (size_t)nw * 8, ctx->stream));
-    CK(cudaMemsetAsync(h->iupac_gap_n, 0, (size_t)nw * 8, ctx->stream));
-    CK(cudaMemsetAsync(h->n_entries, 0, (size_t)nw * 8, ctx->stream));
-    CK(cudaMemsetAsync(h->exc_n, 0, 8, ctx->stream));
-    CK(cudaMemcpyAsync(h->win_pos, win_pos, (size_t)nw * 4, cudaMemcpyHostToDevice, ctx->stream));
-    const unsigned gx = (unsigned)((m->n_seq + (long long)HIST_THREADS * HIST_TILES - 1) / ((long long)HIST_THREADS * HIST_TILES));
-    unsigned gy = (unsigned)nw;
-    const unsigned want = (unsigned)ctx->sm_count * 8;
-    if (gx >= want) gy = 1;
-    else if (gy > (want + gx - 1) / gx) gy = (want + gx - 1) / gx;
-    ctx->pending_units = (double)nw * (double)m->n_seq;  // (window, sequence) k-mers extracted
-    LAUNCH(ctx, k_hist, dim3(gx, gy), HIST_THREADS, 0, m->planes, m->nsp, m->n_seq, m->lens, k, v, h->win_pos, nw,
-           h->keys, h->cnt, h->first, log2_cap, h->gap_n, h->iupac_gap_n, h->exc, h->exc_n, (long long)h->exc_max,
-           (long long)m->row0, h->n_entries, m->err);
-    int rc = check_flags(ctx, m->err);  // also makes the host win_pos copy safe to release
-    if (rc) {
-        mpb_hist_free(h);
-        return rc;
+    CK(cudaMemcpyAsync(h->win_pos, h->h_win_pos.data(), (size_t)nw * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (!fill) {
+        const uint64_t sl = (uint64_t)nw << log2_cap;
+        CK(cudaMemsetAsync(h->keys, 0xFF, sl * 8, ctx->stream));
+        CK(cudaMemsetAsync(h->cnt, 0, sl * 4, ctx->stream));
+        CK(cudaMemsetAsync(h->first, 0xFF, sl * 8, ctx->stream));
+        CK(cudaMemsetAsync(h->gap_n, 0, (size_t)nw * 8, ctx->stream));
+        CK(cudaMemsetAsync(h->iupac_gap_n, 0, (size_t)nw * 8, ctx->stream));
+        CK(cudaMemsetAsync(h->n_entries, 0, (size_t)nw * 8, ctx->stream));
+        CK(cudaMemsetAsync(h->spec_n, 0, (size_t)nw * 8, ctx->stream));
+        CK(cudaMemsetAsync(h->exc_n, 0, 8, ctx->stream));
+        *out = h;
+        return 0;
+    }
+    // special-row lists: room for 1/32 of the rows per window at first; a window with more (gap-rich alignments)
+    // reports its true count and the build is repeated once with exactly the room it needs
+    int64_t cap = m->n_seq / 32;
+    if (cap < 1024) cap = m->n_seq < 1024 ? m->n_seq : 1024;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        int rc = hist_alloc_spec(h, cap);
+        if (rc == 0) rc = hist_launch_build(h);
+        if (rc == 0) rc = mpb_check_flags(ctx, m->err);
+        if (rc) {
+            mpb_hist_free(h);
+            return rc;
+        }
+        std::vector<unsigned long long> sn(nw);
+        CK(cudaMemcpyAsync(sn.data(), h->spec_n, (size_t)nw * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        unsigned long long mx = 0;
+        for (auto x : sn) mx = x > mx ? x : mx;
+        if ((int64_t)mx <= cap) break;
+        if (attempt == 1) {
+            mpb_hist_free(h);
+            return fail(MPB_EOVERFLOW, "special-row list overflow after resize");
+        }
+        cudaFreeAsync(h->spec_win, ctx->stream);
+        cudaFreeAsync(h->spec_row, ctx->stream);
+        h->spec_win = nullptr;
+        h->spec_row = nullptr;
+        cap = (int64_t)mx;
     }
     *out = h;
     return 0;
+}
+
+extern "C" int mpb_hist_build(mpb_msa* m, int k, int v, const int32_t* win_pos, int32_t nw, int log2_cap,
+                              mpb_hist** out) {
+    return hist_create(m, k, v, win_pos, nw, log2_cap, 1, out);
+}
+
+extern "C" int mpb_hist_create_empty(mpb_msa* m, int k, int v, const int32_t* win_pos, int32_t nw, int log2_cap,
+                                     mpb_hist** out) {
+    return hist_create(m, k, v, win_pos, nw, log2_cap, 0, out);
 }
 
 // counters kept by k_hist (host arrays of nw, any may be NULL): gap rows, gap rows holding IUPAC cells, distinct entries
@@ -859,35 +993,31 @@ extern "C" int mpb_hist_counts(mpb_hist* h, int64_t* gap_n, int64_t* n_iupac_gap
 extern "C" void mpb_hist_free(mpb_hist* h) {
     if (!h) return;
     cudaStream_t st = h->msa->ctx->stream;
-    if (h->keys) cudaFreeAsync(h->keys, st);
-    if (h->cnt) cudaFreeAsync(h->cnt, st);
-    if (h->first) cudaFreeAsync(h->first, st);
-    if (h->win_pos) cudaFreeAsync(h->win_pos, st);
-    if (h->gap_n) cudaFreeAsync(h->gap_n, st);
-    if (h->iupac_gap_n) cudaFreeAsync(h->iupac_gap_n, st);
-    if (h->n_entries) cudaFreeAsync(h->n_entries, st);
-    if (h->exc) cudaFreeAsync(h->exc, st);
-    if (h->exc_n) cudaFreeAsync(h->exc_n, st);
+    void* ptrs[] = {h->keys, h->cnt, h->first, h->elist, h->win_pos, h->gap_n, h->iupac_gap_n, h->n_entries, h->exc,
+                    h->exc_n, h->spec_bits, h->gap_bits, h->spec_win, h->spec_row, h->spec_n, h->freq, h->nn};
+    for (void* p : ptrs)
+        if (p) cudaFreeAsync(p, st);
     delete h;
 }
 
-// copy the entries of the selected windows into one compact array; cursor[w] starts at win_off[w]
+// copy the entries of the selected windows into one compact array: window w's entries land at win_off[w] + (their
+// position in the entry list); room for win_off[w+1] - win_off[w] of them
 __global__ void k_hist_export(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ cnt,
-                              const uint64_t* __restrict__ first, int log2cap, const int32_t* __restrict__ sel_idx,
-                              unsigned long long* __restrict__ cursor, const long long* __restrict__ win_end,
+                              const uint64_t* __restrict__ first, const uint32_t* __restrict__ elist,
+                              const unsigned long long* __restrict__ n_entries, int log2cap,
+                              const int32_t* __restrict__ sel_idx, const long long* __restrict__ win_off,
                               uint64_t* __restrict__ ok, uint32_t* __restrict__ oc, uint64_t* __restrict__ of) {
     const int wi = sel_idx[blockIdx.y];
     const uint64_t cap = 1ull << log2cap;
-    const uint64_t* K = keys + (uint64_t)wi * cap;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t key = K[i];
-        if (key == MPB_KEY_EMPTY_D) continue;
-        const unsigned long long slot = atomicAdd(&cursor[wi], 1ull);
-        if ((long long)slot < win_end[wi]) {
-            ok[slot] = key;
-            oc[slot] = cnt[(uint64_t)wi * cap + i];
-            of[slot] = first[(uint64_t)wi * cap + i];
-        }
+    const uint64_t base = (uint64_t)wi * cap;
+    long long n = (long long)n_entries[wi];
+    const long long room = win_off[wi + 1] - win_off[wi];
+    if (n > room) n = room;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const uint64_t slot = base + elist[base + i];
+        ok[win_off[wi] + i] = keys[slot];
+        oc[win_off[wi] + i] = cnt[slot];
+        of[win_off[wi] + i] = first[slot];
     }
 }
 
@@ -897,25 +1027,17 @@ extern "C" int mpb_hist_export(mpb_hist* h, const uint8_t* sel, const int64_t* w
     mpb_ctx* ctx = h->msa->ctx;
     CK(cudaSetDevice(ctx->device));
     std::vector<int32_t> idx;
-    std::vector<unsigned long long> cur(h->nw, 0);
-    std::vector<long long> end(h->nw, 0);
     for (int i = 0; i < h->nw; ++i) {
-        cur[i] = (unsigned long long)win_off[i];
-        end[i] = win_off[i + 1];
         if (sel[i]) idx.push_back(i);
         else if (win_off[i + 1] != win_off[i]) return fail(MPB_EINVAL, "win_off reserves room for unselected window %d", i);
     }
     const int64_t total = win_off[h->nw];
     if (idx.empty() || total <= 0) return 0;
-    InBuf si(ctx, idx.data(), idx.size() * 4), dc(ctx, cur.data(), cur.size() * 8), de(ctx, end.data(), end.size() * 8);
+    InBuf si(ctx, idx.data(), idx.size() * 4), wo(ctx, win_off, (size_t)(h->nw + 1) * 8);
     OutBuf ok(ctx, keys_hd, total * 8), oc(ctx, cnt_hd, total * 4), of(ctx, first_hd, total * 8);
-    if (si.rc || dc.rc || de.rc || ok.rc || oc.rc || of.rc) return MPB_ECUDA;
-    const uint64_t cap = 1ull << h->log2cap;
-    unsigned gx = (unsigned)((cap + 255) / 256);
-    if (gx > 64) gx = 64;
-    LAUNCH(ctx, k_hist_export, dim3(gx, (unsigned)idx.size()), 256, 0, h->keys, h->cnt, h->first, h->log2cap,
-           si.dev<int32_t>(), (unsigned long long*)dc.d, de.dev<long long>(), ok.dev<uint64_t>(), oc.dev<uint32_t>(),
-           of.dev<uint64_t>());
+    if (si.rc || wo.rc || ok.rc || oc.rc || of.rc) return MPB_ECUDA;
+    LAUNCH(ctx, k_hist_export, dim3(32, (unsigned)idx.size()), 256, 0, h->keys, h->cnt, h->first, h->elist, h->n_entries,
+           h->log2cap, si.dev<int32_t>(), wo.dev<long long>(), ok.dev<uint64_t>(), oc.dev<uint32_t>(), of.dev<uint64_t>());
     CK(ok.finish());
     CK(oc.finish());
     CK(of.finish());
@@ -923,46 +1045,73 @@ extern "C" int mpb_hist_export(mpb_hist* h, const uint8_t* sel, const int64_t* w
     return 0;
 }
 
-__global__ void k_hist_merge(const long long* __restrict__ win_off, int nw, const uint64_t* __restrict__ in_keys,
+// entries arrive in n_seg segments (seg_off[n_seg + 1]); segment s belongs to window s % nw (a sharded run receives
+// one run of segments per source rank)
+__global__ void k_hist_merge(const long long* __restrict__ seg_off, int n_seg, int nw, const uint64_t* __restrict__ in_keys,
                              const uint32_t* __restrict__ in_cnt, const uint64_t* __restrict__ in_first,
                              uint64_t* __restrict__ keys, uint32_t* __restrict__ cnt, uint64_t* __restrict__ first,
-                             int log2cap, int* __restrict__ err) {
-    const long long total = win_off[nw];
+                             uint32_t* __restrict__ elist, unsigned long long* __restrict__ n_entries, int log2cap,
+                             int* __restrict__ err) {
+    const long long total = seg_off[n_seg];
     const uint64_t cap = 1ull << log2cap;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        int lo = 0, hi = nw;  // largest w with win_off[w] <= i
+        int lo = 0, hi = n_seg;  // largest s with seg_off[s] <= i
         while (hi - lo > 1) {
             int mid = (lo + hi) >> 1;
-            if (win_off[mid] <= i) lo = mid;
+            if (seg_off[mid] <= i) lo = mid;
             else hi = mid;
         }
-        mpb_table_add(keys + (uint64_t)lo * cap, cnt + (uint64_t)lo * cap, first + (uint64_t)lo * cap, log2cap,
-                      in_keys[i], in_cnt[i], in_first[i], err);
+        const int w = lo % nw;
+        mpb_table_add(keys + (uint64_t)w * cap, cnt + (uint64_t)w * cap, first + (uint64_t)w * cap, log2cap, in_keys[i],
+                      in_cnt[i], in_first[i], err, &n_entries[w], elist + (uint64_t)w * cap);
     }
 }
 
-extern "C" int mpb_hist_merge(mpb_hist* h, const int64_t* win_off, const uint64_t* keys_hd, const uint32_t* cnt_hd,
-                              const uint64_t* first_hd) {
-    if (!h || !win_off || !keys_hd || !cnt_hd || !first_hd) return fail(MPB_EINVAL, "NULL argument");
+extern "C" int mpb_hist_merge_segments(mpb_hist* h, int32_t n_seg, const int64_t* seg_off, const uint64_t* keys_hd,
+                                       const uint32_t* cnt_hd, const uint64_t* first_hd) {
+    if (!h || !seg_off || !keys_hd || !cnt_hd || !first_hd) return fail(MPB_EINVAL, "NULL argument");
+    if (n_seg < 1 || n_seg % h->nw != 0) return fail(MPB_EINVAL, "n_seg must be a multiple of the window count");
     mpb_ctx* ctx = h->msa->ctx;
     CK(cudaSetDevice(ctx->device));
-    const int64_t total = win_off[h->nw];
+    const int64_t total = seg_off[n_seg];
     if (total <= 0) return 0;
-    InBuf off(ctx, win_off, (size_t)(h->nw + 1) * 8), ik(ctx, keys_hd, total * 8), ic(ctx, cnt_hd, total * 4),
+    InBuf off(ctx, seg_off, (size_t)(n_seg + 1) * 8), ik(ctx, keys_hd, total * 8), ic(ctx, cnt_hd, total * 4),
         ifr(ctx, first_hd, total * 8);
     if (off.rc || ik.rc || ic.rc || ifr.rc) return MPB_ECUDA;
     unsigned grid = (unsigned)((total + 255) / 256);
     if (grid > (unsigned)ctx->sm_count * 16) grid = ctx->sm_count * 16;
-    LAUNCH(ctx, k_hist_merge, grid, 256, 0, off.dev<long long>(), h->nw, ik.dev<uint64_t>(), ic.dev<uint32_t>(),
-           ifr.dev<uint64_t>(), h->keys, h->cnt, h->first, h->log2cap, h->msa->err);
-    return check_flags(ctx, h->msa->err);
+    LAUNCH(ctx, k_hist_merge, grid, 256, 0, off.dev<long long>(), (int)n_seg, h->nw, ik.dev<uint64_t>(), ic.dev<uint32_t>(),
+           ifr.dev<uint64_t>(), h->keys, h->cnt, h->first, h->elist, h->n_entries, h->log2cap, h->msa->err);
+    h->have_summary = false;
+    return mpb_check_flags(ctx, h->msa->err);
 }
 
-// entropy ingredients, distinct counts and the most frequent gap-free haplotype of every window.  SB blocks share a
-// window; each writes one partial record, the final (deterministic, fixed-order) combination happens in
-// mpb_hist_stats on the host over nw x SB records.
-#define STATS_THREADS 256
-#define STATS_MAX_SB 64
+extern "C" int mpb_hist_merge(mpb_hist* h, const int64_t* win_off, const uint64_t* keys_hd, const uint32_t* cnt_hd,
+                              const uint64_t* first_hd) {
+    if (!h) return fail(MPB_EINVAL, "NULL argument");
+    return mpb_hist_merge_segments(h, h->nw, win_off, keys_hd, cnt_hd, first_hd);
+}
+
+// sharded runs: add foreign gap-row counters to the owner's (they are not table entries)
+extern "C" int mpb_hist_add_counts(mpb_hist* h, const int64_t* gap_n, const int64_t* n_iupac_gap) {
+    if (!h || !gap_n || !n_iupac_gap) return fail(MPB_EINVAL, "NULL argument");
+    mpb_ctx* ctx = h->msa->ctx;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(h->gap_n, gap_n, (size_t)h->nw * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(h->iupac_gap_n, n_iupac_gap, (size_t)h->nw * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// One pass over the ENTRY LIST of every window (not over the slots): entropy ingredients, distinct counts, the most
+// frequent gap-free haplotype (core:595-600), base counts per column and dinucleotide counts per junction weighted by
+// the haplotype counts (core:541-577 restated over the table instead of over a pandas frame of expansion rows).
+// SUM_SB blocks share a window; each writes one partial record (combined in fixed order on the host) and adds its
+// integer tensors with atomics.
+// ------------------------------------------------------------------------------------------------------
+#define SUM_THREADS 256
+#define SUM_SB 8
 struct Best {
     unsigned long long cnt, first, key;
 };
@@ -975,50 +1124,58 @@ struct StatsPart {
     Best best;
 };
 
-__global__ void __launch_bounds__(STATS_THREADS)
-k_hist_stats(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ cnt, const uint64_t* __restrict__ first,
-             int log2cap, int k, int v, StatsPart* __restrict__ part) {
+__global__ void __launch_bounds__(SUM_THREADS)
+k_hist_summary(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ cnt, const uint64_t* __restrict__ first,
+               const uint32_t* __restrict__ elist, const unsigned long long* __restrict__ n_entries, int log2cap, int k,
+               int v, StatsPart* __restrict__ part, unsigned long long* __restrict__ freq,
+               unsigned long long* __restrict__ nn) {
+    __shared__ unsigned long long s_freq[4 * MPB_MAX_K];
+    __shared__ unsigned long long s_nn[(MPB_MAX_K - 1) * 16];
     const int wi = blockIdx.y;
-    const int sb = gridDim.x;
     const uint64_t cap = 1ull << log2cap;
-    const uint64_t* K = keys + (uint64_t)wi * cap;
-    const uint32_t* C = cnt + (uint64_t)wi * cap;
-    const uint64_t* F = first + (uint64_t)wi * cap;
+    const uint64_t base = (uint64_t)wi * cap;
+    const uint32_t kmask = (1u << k) - 1u;
+    const long long n = (long long)n_entries[wi];
+    for (int i = threadIdx.x; i < 4 * k; i += SUM_THREADS) s_freq[i] = 0;
+    for (int i = threadIdx.x; i < (k - 1) * 16; i += SUM_THREADS) s_nn[i] = 0;
+    __syncthreads();
     double s0c = 0, s1c = 0, s0g = 0, s1g = 0;
     long long nc = 0, ng = 0, ngf = 0;
     Best best = {0ull, ~0ull, MPB_KEY_EMPTY_D};
-    for (uint64_t i = (uint64_t)blockIdx.x * STATS_THREADS + threadIdx.x; i < cap; i += (uint64_t)sb * STATS_THREADS) {
-        const uint64_t key = K[i];
-        if (key == MPB_KEY_EMPTY_D) continue;
-        const double c = (double)C[i];
-        bool is_cover = true;
-        if (key >= MPB_KEY_BASE5_D) {
-            uint64_t x = key - MPB_KEY_BASE5_D;
-            int gaps = 0;
-            for (int j = 0; j < k; ++j) {
-                gaps += (x % 5ull) == 4ull;
-                x /= 5ull;
-            }
-            is_cover = gaps <= v;
-        } else {
+    for (long long i = (long long)blockIdx.x * SUM_THREADS + threadIdx.x; i < n; i += (long long)SUM_SB * SUM_THREADS) {
+        const uint64_t slot = base + elist[base + i];
+        const uint64_t key = keys[slot];
+        const uint32_t ci = cnt[slot];
+        const double c = (double)ci;
+        uint32_t pa, pc, pg, pt, gapv;
+        mpb_key_planes(key, k, kmask, pa, pc, pg, pt, gapv);
+        const bool is_cover = __popc(gapv) <= v;
+        if (key < MPB_KEY_BASE5_D) {
             ++ngf;
-            Best b = {(unsigned long long)C[i], F[i], key};
+            Best b = {(unsigned long long)ci, first[slot], key};
             if (better(b, best)) best = b;
         }
-        const double clog = C[i] == 1u ? 0.0 : c * log2(c);  // singletons (most of a variable window) cost no log
+        const double clog = ci == 1u ? 0.0 : c * log2(c);  // singletons (most of a variable window) cost no log
         if (is_cover) {
             s0c += c;
             s1c += clog;
             ++nc;
+            int prev = -1;
+            for (int j = 0; j < k; ++j) {
+                const int d = ((gapv >> j) & 1u) ? -1 : (int)(((pc >> j) & 1u) + 2u * ((pg >> j) & 1u) + 3u * ((pt >> j) & 1u));
+                if (d >= 0) atomicAdd(&s_freq[d * k + j], (unsigned long long)ci);
+                if (j > 0 && d >= 0 && prev >= 0) atomicAdd(&s_nn[(j - 1) * 16 + prev * 4 + d], (unsigned long long)ci);
+                prev = d;
+            }
         } else {
             s0g += c;
             s1g += clog;
             ++ng;
         }
     }
-    __shared__ double sd[4][STATS_THREADS / 32];
-    __shared__ long long sl[3][STATS_THREADS / 32];
-    __shared__ Best sbest[STATS_THREADS / 32];
+    __shared__ double sd[4][SUM_THREADS / 32];
+    __shared__ long long sl[3][SUM_THREADS / 32];
+    __shared__ Best sbest[SUM_THREADS / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int o = 16; o > 0; o >>= 1) {
         s0c += __shfl_xor_sync(0xffffffffu, s0c, o);
@@ -1047,7 +1204,7 @@ k_hist_stats(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ cnt
     __syncthreads();
     if (threadIdx.x == 0) {
         StatsPart r = {sd[0][0], sd[1][0], sd[2][0], sd[3][0], sl[0][0], sl[1][0], sl[2][0], sbest[0]};
-        for (int w = 1; w < STATS_THREADS / 32; ++w) {
+        for (int w = 1; w < SUM_THREADS / 32; ++w) {
             r.s0c += sd[0][w];
             r.s1c += sd[1][w];
             r.s0g += sd[2][w];
@@ -1057,42 +1214,43 @@ k_hist_stats(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ cnt
             r.ngf += sl[2][w];
             if (better(sbest[w], r.best)) r.best = sbest[w];
         }
-        part[(long long)wi * sb + blockIdx.x] = r;
+        part[(long long)wi * SUM_SB + blockIdx.x] = r;
     }
+    for (int i = threadIdx.x; i < 4 * k; i += SUM_THREADS)
+        if (s_freq[i]) atomicAdd(&freq[(long long)wi * 4 * k + i], s_freq[i]);
+    for (int i = threadIdx.x; i < (k - 1) * 16; i += SUM_THREADS)
+        if (s_nn[i]) atomicAdd(&nn[(long long)wi * (k - 1) * 16 + i], s_nn[i]);
 }
 
-static int blocks_per_window(mpb_ctx* ctx, int log2cap, int nw) {
-    long long sb = (1ll << log2cap) / (STATS_THREADS * 32);
-    if (sb < 1) sb = 1;
-    if (sb > STATS_MAX_SB) sb = STATS_MAX_SB;
-    return (int)sb;
-}
-
-extern "C" int mpb_hist_stats(mpb_hist* h, int64_t* gap_n, double* ent, int64_t* nuniq, uint64_t* mm_key,
-                              int64_t* mm_cnt, uint64_t* mm_first, int64_t* n_iupac_gap) {
+// all outputs host arrays (any may be NULL); freq / nn also stay on the device for the walk (mpb_walk_dev.cu)
+extern "C" int mpb_hist_summary(mpb_hist* h, int64_t* gap_n, double* ent, int64_t* nuniq, uint64_t* mm_key,
+                                int64_t* mm_cnt, uint64_t* mm_first, int64_t* n_iupac_gap, int64_t* freq, int64_t* nn) {
     if (!h) return fail(MPB_EINVAL, "NULL argument");
     mpb_ctx* ctx = h->msa->ctx;
     CK(cudaSetDevice(ctx->device));
     const size_t nw = h->nw;
-    const int sb = blocks_per_window(ctx, h->log2cap, h->nw);
+    const int k = h->k;
+    const size_t fb = nw * 4 * k * 8, nb = nw * (k - 1) * 16 * 8;
     StatsPart* dpart = nullptr;
-    CK(cudaMallocAsync(&dpart, nw * sb * sizeof(StatsPart), ctx->stream));
-    LAUNCH(ctx, k_hist_stats, dim3((unsigned)sb, (unsigned)nw), STATS_THREADS, 0, h->keys, h->cnt, h->first, h->log2cap,
-           h->k, h->v, dpart);
-    std::vector<StatsPart> part(nw * sb);
-    CK(cudaMemcpyAsync(part.data(), dpart, nw * sb * sizeof(StatsPart), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMallocAsync(&dpart, nw * SUM_SB * sizeof(StatsPart), ctx->stream));
+    CK(cudaMemsetAsync(h->freq, 0, fb, ctx->stream));
+    CK(cudaMemsetAsync(h->nn, 0, nb, ctx->stream));
+    LAUNCH(ctx, k_hist_summary, dim3(SUM_SB, (unsigned)nw), SUM_THREADS, 0, h->keys, h->cnt, h->first, h->elist,
+           h->n_entries, h->log2cap, k, h->v, dpart, h->freq, h->nn);
+    std::vector<StatsPart> part(nw * SUM_SB);
+    CK(cudaMemcpyAsync(part.data(), dpart, nw * SUM_SB * sizeof(StatsPart), cudaMemcpyDeviceToHost, ctx->stream));
     std::vector<long long> hg(nw), hi(nw);
     CK(cudaMemcpyAsync(hg.data(), h->gap_n, nw * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(hi.data(), h->iupac_gap_n, nw * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (freq) CK(cudaMemcpyAsync(freq, h->freq, fb, cudaMemcpyDeviceToHost, ctx->stream));
+    if (nn) CK(cudaMemcpyAsync(nn, h->nn, nb, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaFreeAsync(dpart, ctx->stream));
-    std::vector<double> h_ent(nw * 4);
-    std::vector<long long> h_nu(nw * 3), h_mc(nw);
-    std::vector<unsigned long long> h_mk(nw), h_mf(nw);
+    h->have_summary = true;
     for (size_t w = 0; w < nw; ++w) {
-        StatsPart r = part[w * sb];
-        for (int b = 1; b < sb; ++b) {
-            const StatsPart& q = part[w * sb + b];
+        StatsPart r = part[w * SUM_SB];
+        for (int b = 1; b < SUM_SB; ++b) {
+            const StatsPart& q = part[w * SUM_SB + b];
             r.s0c += q.s0c;
             r.s1c += q.s1c;
             r.s0g += q.s0g;
@@ -1102,122 +1260,54 @@ extern "C" int mpb_hist_stats(mpb_hist* h, int64_t* gap_n, double* ent, int64_t*
             r.ngf += q.ngf;
             if (better(q.best, r.best)) r.best = q.best;
         }
-        h_ent[w * 4 + 0] = r.s0c;
-        h_ent[w * 4 + 1] = r.s1c;
-        h_ent[w * 4 + 2] = r.s0g;
-        h_ent[w * 4 + 3] = r.s1g;
-        h_nu[w * 3 + 0] = r.nc;
-        h_nu[w * 3 + 1] = r.ng;
-        h_nu[w * 3 + 2] = r.ngf;
-        h_mk[w] = r.best.key;
-        h_mc[w] = (long long)r.best.cnt;
-        h_mf[w] = r.best.first;
-    }
-    struct Out {
-        void* dst;
-        const void* src;
-        size_t bytes;
-    } outs[] = {{gap_n, hg.data(), nw * 8},      {ent, h_ent.data(), nw * 32},  {nuniq, h_nu.data(), nw * 24},
-                {mm_key, h_mk.data(), nw * 8},   {mm_cnt, h_mc.data(), nw * 8}, {mm_first, h_mf.data(), nw * 8},
-                {n_iupac_gap, hi.data(), nw * 8}};
-    bool any_dev = false;
-    for (auto& o : outs) {
-        if (!o.dst) continue;
-        if (is_device_ptr(o.dst)) {
-            CK(cudaMemcpyAsync(o.dst, o.src, o.bytes, cudaMemcpyHostToDevice, ctx->stream));
-            any_dev = true;
-        } else {
-            memcpy(o.dst, o.src, o.bytes);
+        if (gap_n) gap_n[w] = hg[w];
+        if (n_iupac_gap) n_iupac_gap[w] = hi[w];
+        if (ent) {
+            ent[w * 4 + 0] = r.s0c;
+            ent[w * 4 + 1] = r.s1c;
+            ent[w * 4 + 2] = r.s0g;
+            ent[w * 4 + 3] = r.s1g;
         }
+        if (nuniq) {
+            nuniq[w * 3 + 0] = r.nc;
+            nuniq[w * 3 + 1] = r.ng;
+            nuniq[w * 3 + 2] = r.ngf;
+        }
+        if (mm_key) mm_key[w] = r.best.key;
+        if (mm_cnt) mm_cnt[w] = (long long)r.best.cnt;
+        if (mm_first) mm_first[w] = r.best.first;
     }
-    if (any_dev) CK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 
-// base counts per column and dinucleotide counts per junction of the selected windows, weighted by the haplotype
-// counts (core:541-577 restated over the table instead of over a pandas frame of expansion rows).  SB blocks per
-// window, shared-memory accumulation, one integer atomicAdd per counter per block.
-#define TENS_THREADS 256
-__global__ void __launch_bounds__(TENS_THREADS)
-k_hist_tensors(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ cnt, int log2cap, int k, int v,
-               const int32_t* __restrict__ sel_idx, unsigned long long* __restrict__ freq,
-               unsigned long long* __restrict__ nn) {
-    __shared__ unsigned long long s_freq[4 * MPB_MAX_K];
-    __shared__ unsigned long long s_nn[(MPB_MAX_K - 1) * 16];
-    const int wi = sel_idx[blockIdx.y];
-    const uint64_t cap = 1ull << log2cap;
-    const uint64_t* K = keys + (uint64_t)wi * cap;
-    const uint32_t* C = cnt + (uint64_t)wi * cap;
-    const uint32_t kmask = (1u << k) - 1u;
-    for (int i = threadIdx.x; i < 4 * k; i += TENS_THREADS) s_freq[i] = 0;
-    for (int i = threadIdx.x; i < (k - 1) * 16; i += TENS_THREADS) s_nn[i] = 0;
-    __syncthreads();
-    for (uint64_t i = (uint64_t)blockIdx.x * TENS_THREADS + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * TENS_THREADS) {
-        const uint64_t key = K[i];
-        if (key == MPB_KEY_EMPTY_D) continue;
-        uint32_t a, c, g, t, gapv;
-        mpb_key_planes(key, k, kmask, a, c, g, t, gapv);
-        if (__popc(gapv) > v) continue;  // gap k-mer, not a cover haplotype
-        const unsigned long long n = C[i];
-        int prev = -1;
-        for (int j = 0; j < k; ++j) {
-            int d = ((gapv >> j) & 1u) ? -1 : (int)(((c >> j) & 1u) + 2u * ((g >> j) & 1u) + 3u * ((t >> j) & 1u));
-            if (d >= 0) atomicAdd(&s_freq[d * k + j], n);
-            if (j > 0 && d >= 0 && prev >= 0) atomicAdd(&s_nn[(j - 1) * 16 + prev * 4 + d], n);
-            prev = d;
-        }
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 4 * k; i += TENS_THREADS)
-        if (s_freq[i]) atomicAdd(&freq[(long long)wi * 4 * k + i], s_freq[i]);
-    for (int i = threadIdx.x; i < (k - 1) * 16; i += TENS_THREADS)
-        if (s_nn[i]) atomicAdd(&nn[(long long)wi * (k - 1) * 16 + i], s_nn[i]);
+// the two historical views of the summary (host outputs)
+extern "C" int mpb_hist_stats(mpb_hist* h, int64_t* gap_n, double* ent, int64_t* nuniq, uint64_t* mm_key,
+                              int64_t* mm_cnt, uint64_t* mm_first, int64_t* n_iupac_gap) {
+    return mpb_hist_summary(h, gap_n, ent, nuniq, mm_key, mm_cnt, mm_first, n_iupac_gap, nullptr, nullptr);
 }
 
 extern "C" int mpb_hist_tensors(mpb_hist* h, const uint8_t* sel, int64_t* freq_hd, int64_t* nn_hd) {
     if (!h || !sel || !freq_hd || !nn_hd) return fail(MPB_EINVAL, "NULL argument");
-    mpb_ctx* ctx = h->msa->ctx;
-    CK(cudaSetDevice(ctx->device));
-    std::vector<int32_t> idx;
-    for (int i = 0; i < h->nw; ++i)
-        if (sel[i]) idx.push_back(i);
-    const size_t fb = (size_t)h->nw * 4 * h->k * 8, nb = (size_t)h->nw * (h->k - 1) * 16 * 8;
-    OutBuf of(ctx, freq_hd, fb), on(ctx, nn_hd, nb);
-    if (of.rc || on.rc) return MPB_ENOMEM;
-    CK(cudaMemsetAsync(of.d, 0, fb, ctx->stream));
-    CK(cudaMemsetAsync(on.d, 0, nb, ctx->stream));
-    if (!idx.empty()) {
-        InBuf si(ctx, idx.data(), idx.size() * 4);
-        if (si.rc) return si.rc;
-        const int sb = blocks_per_window(ctx, h->log2cap, (int)idx.size());
-        LAUNCH(ctx, k_hist_tensors, dim3((unsigned)sb, (unsigned)idx.size()), TENS_THREADS, 0, h->keys, h->cnt,
-               h->log2cap, h->k, h->v, si.dev<int32_t>(), of.dev<unsigned long long>(), on.dev<unsigned long long>());
-        CK(of.finish());
-        CK(on.finish());
-        CK(cudaStreamSynchronize(ctx->stream));  // idx lifetime
-        return 0;
-    }
-    CK(of.finish());
-    CK(on.finish());
-    if (of.is_host() || on.is_host()) CK(cudaStreamSynchronize(ctx->stream));
+    int rc = mpb_hist_summary(h, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, freq_hd, nn_hd);
+    if (rc) return rc;
+    const size_t f1 = 4 * (size_t)h->k, n1 = (size_t)(h->k - 1) * 16;
+    for (int w = 0; w < h->nw; ++w)
+        if (!sel[w]) {
+            memset(freq_hd + w * f1, 0, f1 * 8);
+            memset(nn_hd + w * n1, 0, n1 * 8);
+        }
     return 0;
 }
 
 __global__ void k_hist_dump(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ cnt,
-                            const uint64_t* __restrict__ first, int log2cap, int wi, long long max_n,
-                            uint64_t* __restrict__ ok, uint32_t* __restrict__ oc, uint64_t* __restrict__ of,
-                            unsigned long long* __restrict__ n_out) {
-    const uint64_t cap = 1ull << log2cap;
-    const uint64_t* K = keys + (uint64_t)wi * cap;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t key = K[i];
-        if (key == MPB_KEY_EMPTY_D) continue;
-        unsigned long long slot = atomicAdd(n_out, 1ull);
-        if ((long long)slot < max_n) {
-            ok[slot] = key;
-            oc[slot] = cnt[(uint64_t)wi * cap + i];
-            of[slot] = first[(uint64_t)wi * cap + i];
-        }
+                            const uint64_t* __restrict__ first, const uint32_t* __restrict__ elist, int log2cap, int wi,
+                            long long n, uint64_t* __restrict__ ok, uint32_t* __restrict__ oc, uint64_t* __restrict__ of) {
+    const uint64_t base = (uint64_t)wi << log2cap;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const uint64_t slot = base + elist[base + i];
+        ok[i] = keys[slot];
+        oc[i] = cnt[slot];
+        of[i] = first[slot];
     }
 }
 
@@ -1227,41 +1317,41 @@ extern "C" int mpb_hist_dump(mpb_hist* h, int32_t w, int64_t max_n, uint64_t* ke
     if (w < 0 || w >= h->nw || max_n < 0) return fail(MPB_EINVAL, "window %d outside the batch", w);
     mpb_ctx* ctx = h->msa->ctx;
     CK(cudaSetDevice(ctx->device));
-    OutBuf ok(ctx, keys_hd, max_n * 8), oc(ctx, cnt_hd, max_n * 4), of(ctx, first_hd, max_n * 8);
-    if (ok.rc || oc.rc || of.rc) return MPB_ENOMEM;
-    unsigned long long* dn;
-    CK(cudaMallocAsync(&dn, 8, ctx->stream));
-    CK(cudaMemsetAsync(dn, 0, 8, ctx->stream));
-    const uint64_t cap = 1ull << h->log2cap;
-    unsigned grid = (unsigned)((cap + 255) / 256);
-    if (grid > (unsigned)ctx->sm_count * 8) grid = ctx->sm_count * 8;
-    LAUNCH(ctx, k_hist_dump, grid, 256, 0, h->keys, h->cnt, h->first, h->log2cap, (int)w, (long long)max_n,
-           ok.dev<uint64_t>(), oc.dev<uint32_t>(), of.dev<uint64_t>(), dn);
     unsigned long long n = 0;
-    CK(cudaMemcpyAsync(&n, dn, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&n, h->n_entries + w, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *n_out = (int64_t)n;
+    const long long take = (long long)n < max_n ? (long long)n : max_n;
+    if (take <= 0) return 0;
+    OutBuf ok(ctx, keys_hd, take * 8), oc(ctx, cnt_hd, take * 4), of(ctx, first_hd, take * 8);
+    if (ok.rc || oc.rc || of.rc) return MPB_ENOMEM;
+    unsigned grid = (unsigned)((take + 255) / 256);
+    if (grid > (unsigned)ctx->sm_count * 8) grid = ctx->sm_count * 8;
+    LAUNCH(ctx, k_hist_dump, grid, 256, 0, h->keys, h->cnt, h->first, h->elist, h->log2cap, (int)w, take,
+           ok.dev<uint64_t>(), oc.dev<uint32_t>(), of.dev<uint64_t>());
     CK(ok.finish());
     CK(oc.finish());
     CK(of.finish());
     CK(cudaStreamSynchronize(ctx->stream));
-    CK(cudaFreeAsync(dn, ctx->stream));
-    *n_out = (int64_t)n;
     return 0;
 }
 
-// distinct gap-free table entries matched exactly by a degenerate pattern; SB blocks per query
+// distinct gap-free table entries matched exactly by a degenerate pattern; MATCH_SB blocks per query over the entry list
+#define MATCH_SB 4
 __global__ void __launch_bounds__(256)
-k_hist_match(const uint64_t* __restrict__ keys, int log2cap, int k, const int32_t* __restrict__ q_win,
+k_hist_match(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ elist,
+             const unsigned long long* __restrict__ n_entries, int log2cap, int k, const int32_t* __restrict__ q_win,
              const uint32_t* __restrict__ q_allow, unsigned long long* __restrict__ out) {
     const int q = blockIdx.y;
-    const uint64_t cap = 1ull << log2cap;
-    const uint64_t* K = keys + (uint64_t)q_win[q] * cap;
+    const uint64_t base = (uint64_t)q_win[q] << log2cap;
+    const long long n_e = (long long)n_entries[q_win[q]];
     const uint32_t kmask = (1u << k) - 1u;
     const uint32_t na = ~q_allow[q * 4 + 0] & kmask, ncm = ~q_allow[q * 4 + 1] & kmask, ngm = ~q_allow[q * 4 + 2] & kmask,
                    nt = ~q_allow[q * 4 + 3] & kmask;
     unsigned n = 0;
-    for (uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * 256) {
-        const uint64_t key = K[i];
-        if (key >= MPB_KEY_BASE5_D) continue;  // empty, or a k-mer with gaps (never an expansion of a primer)
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n_e; i += (long long)gridDim.x * 256) {
+        const uint64_t key = keys[base + elist[base + i]];
+        if (key >= MPB_KEY_BASE5_D) continue;  // a k-mer with gaps (never an expansion of a primer)
         uint32_t a, c, g, t, gapv;
         mpb_key_planes(key, k, kmask, a, c, g, t, gapv);
         n += ((a & na) | (c & ncm) | (g & ngm) | (t & nt)) == 0u;
@@ -1274,7 +1364,7 @@ extern "C" int mpb_hist_match(mpb_hist* h, const int32_t* q_win, const uint32_t*
                               int64_t* distinct_hd) {
     if (!h || !q_win || !q_allow || !distinct_hd) return fail(MPB_EINVAL, "NULL argument");
     if (nq < 1) return 0;
-    if (!is_device_ptr(q_win))
+    if (!mpb_is_device_ptr(q_win))
         for (int i = 0; i < nq; ++i)
             if (q_win[i] < 0 || q_win[i] >= h->nw) return fail(MPB_EINVAL, "q_win[%d]=%d outside the batch", i, q_win[i]);
     mpb_ctx* ctx = h->msa->ctx;
@@ -1283,9 +1373,8 @@ extern "C" int mpb_hist_match(mpb_hist* h, const int32_t* q_win, const uint32_t*
     OutBuf o(ctx, distinct_hd, (size_t)nq * 8);
     if (qw.rc || qa.rc || o.rc) return MPB_ECUDA;
     CK(cudaMemsetAsync(o.d, 0, (size_t)nq * 8, ctx->stream));
-    const int sb = blocks_per_window(ctx, h->log2cap, nq);
-    LAUNCH(ctx, k_hist_match, dim3((unsigned)sb, (unsigned)nq), 256, 0, h->keys, h->log2cap, h->k, qw.dev<int32_t>(),
-           qa.dev<uint32_t>(), o.dev<unsigned long long>());
+    LAUNCH(ctx, k_hist_match, dim3(MATCH_SB, (unsigned)nq), 256, 0, h->keys, h->elist, h->n_entries, h->log2cap, h->k,
+           qw.dev<int32_t>(), qa.dev<uint32_t>(), o.dev<unsigned long long>());
     CK(o.finish());
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;
@@ -1592,7 +1681,7 @@ extern "C" int mpb_scan(mpb_msa* m, int k, int v, uint32_t fmask, uint32_t rmask
     // candidate windows are needed on the host to cut the chunks
     std::vector<int32_t> pos_copy;
     const int32_t* pos = cand_pos_hd;
-    if (is_device_ptr(cand_pos_hd)) {
+    if (mpb_is_device_ptr(cand_pos_hd)) {
         pos_copy.resize(nc);
         CK(cudaMemcpyAsync(pos_copy.data(), cand_pos_hd, nc * 4, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
@@ -1644,7 +1733,7 @@ extern "C" int mpb_scan(mpb_msa* m, int k, int v, uint32_t fmask, uint32_t rmask
     CK(cudaFreeAsync(partial, ctx->stream));
     CK(oc.finish());
     CK(ob.finish());
-    return check_flags(ctx, m->err);  // also keeps the host chunk list alive until the kernels are done
+    return mpb_check_flags(ctx, m->err);  // also keeps the host chunk list alive until the kernels are done
 }
 
 // per (window, sequence) table key, for the JSON side files

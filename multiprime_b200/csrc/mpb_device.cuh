@@ -20,11 +20,11 @@
 // order byte: alternative j is base ((byte >> 2j) & 3), bases A,C,G,T = 0..3.  core:105-107:
 //   R(5)=A,G  Y(10)=C,T  M(3)=A,C  K(12)=G,T  S(6)=G,C  W(9)=A,T  H(11)=A,T,C  B(14)=G,T,C  V(7)=G,A,C
 //   D(13)=G,A,T  N(15)=A,T,G,C
-__constant__ uint8_t c_fold[16] = {1, 1, 1, 2, 1, 2, 2, 3, 1, 2, 2, 3, 2, 3, 3, 4};
+static __constant__ uint8_t c_fold[16] = {1, 1, 1, 2, 1, 2, 2, 3, 1, 2, 2, 3, 2, 3, 3, 4};
 #define ORD2(a, b) ((a) | ((b) << 2))
 #define ORD3(a, b, c) ((a) | ((b) << 2) | ((c) << 4))
 #define ORD4(a, b, c, d) ((a) | ((b) << 2) | ((c) << 4) | ((d) << 6))
-__constant__ uint8_t c_order[16] = {
+static __constant__ uint8_t c_order[16] = {
     0,              // 0  gap
     0,              // 1  A
     1,              // 2  C
@@ -42,7 +42,7 @@ __constant__ uint8_t c_order[16] = {
     ORD3(2, 3, 1),  // 14 B = G,T,C
     ORD4(0, 3, 2, 1)  // 15 N = A,T,G,C
 };
-__constant__ uint64_t c_pow5[28] = {1ull,
+static __constant__ uint64_t c_pow5[28] = {1ull,
                                     5ull,
                                     25ull,
                                     125ull,
@@ -97,7 +97,7 @@ __device__ __forceinline__ int mpb_cell(const uint32_t* __restrict__ pl, int64_t
 
 // The rare path of core:666-687: the window starts/ends inside a gap run, or runs past the end of a ragged row.
 // Restated on an array of k 4-bit cells; returns false when the row cannot supply k cells (unsupported input).
-__device__ __noinline__ bool mpb_window_slow(const uint32_t* __restrict__ pl, int64_t nsp, int64_t s, int len, int p,
+static __device__ __noinline__ bool mpb_window_slow(const uint32_t* __restrict__ pl, int64_t nsp, int64_t s, int len, int p,
                                             int k, Win& out) {
     uint8_t w[32];
     uint8_t buf[32];
@@ -344,10 +344,12 @@ __device__ __forceinline__ uint32_t mpb_hash(uint64_t key, int log2cap) {
     return (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> (64 - log2cap));
 }
 
-// open addressing, linear probing; count += add, first = min(first, ord)
+// open addressing, linear probing; count += add, first = min(first, ord).  The call that claims a slot appends it to
+// the window's entry list (elist, n_new): the table readers walk that list instead of all slots.
 __device__ __forceinline__ void mpb_table_add(uint64_t* __restrict__ keys, uint32_t* __restrict__ cnt,
                                               uint64_t* __restrict__ first, int log2cap, uint64_t key, uint32_t add,
-                                              uint64_t ord, int* err, unsigned long long* n_new = nullptr) {
+                                              uint64_t ord, int* err, unsigned long long* n_new,
+                                              uint32_t* __restrict__ elist) {
     const uint32_t mask = (1u << log2cap) - 1u;
     const uint32_t last_probe = mask < 8191u ? mask : 8191u;  // a run this long means the table is as good as full
     uint32_t h = mpb_hash(key, log2cap);
@@ -358,7 +360,8 @@ __device__ __forceinline__ void mpb_table_add(uint64_t* __restrict__ keys, uint3
                             (unsigned long long)key);
             if (cur == MPB_KEY_EMPTY_D) {
                 cur = key;
-                if (n_new) atomicAdd(n_new, 1ull);  // this call claimed the slot: one more distinct entry
+                const unsigned long long idx = atomicAdd(n_new, 1ull);  // this call claimed the slot
+                elist[idx] = h;
             }
         }
         if (cur == key) {

@@ -17,382 +17,82 @@
 #include "mpb200.h"
 #include "mpb_host.h"
 
-namespace {
+#include "mpb_walk_core.h"
 
-const int FOLD[16] = {0, 1, 1, 2, 1, 2, 2, 3, 1, 2, 2, 3, 2, 3, 3, 4};
-// expansion order of each base set (core:105-107): ORD[set] lists base indices A,C,G,T = 0..3
-const int8_t ORD[16][4] = {{-1, -1, -1, -1}, {0, -1, -1, -1}, {1, -1, -1, -1}, {0, 1, -1, -1},  {2, -1, -1, -1}, {0, 2, -1, -1},
-                           {2, 1, -1, -1},   {2, 0, 1, -1},   {3, -1, -1, -1}, {0, 3, -1, -1},  {1, 3, -1, -1},  {0, 3, 1, -1},
-                           {2, 3, -1, -1},   {2, 0, 3, -1},   {2, 3, 1, -1},   {0, 3, 2, 1}};
-
-struct Opt {
-    bool valid;
-    int pos, base;
-    int nl;
-    int lidx[2];
-    int64_t layer[2][16];
-    std::vector<int64_t> cov;
-};
-
-struct Track {
-    int win;  // index into the batch
-    int k;
-    uint8_t seed[32];
-    uint8_t sets[32];
-    uint32_t allow[4];
-    std::vector<std::array<int64_t, 16>> nn;
-    std::vector<int64_t> nn_cov;
-    int64_t init = 0, fm = 0, rm = 0, seed_cover = 0, perfect = 0;
-    int state = 0;  // 0 seed, 1 refine, 2 done
-    std::vector<Opt> opts;
-    std::vector<std::array<uint8_t, 32>> trace;
-    int first_cand = 0;  // index of this track's first candidate in the current round
-};
-
-int npos4(const int64_t* v) { return (v[0] > 0) + (v[1] > 0) + (v[2] > 0) + (v[3] > 0); }
-
-// np.argsort(vals)[::-1] for a stable ascending sort: descending values, ties highest index first
-void order_desc(const int64_t* v, int* out) {
-    int idx[4] = {0, 1, 2, 3};
-    std::stable_sort(idx, idx + 4, [&](int a, int b) { return v[a] < v[b]; });
-    for (int i = 0; i < 4; ++i) out[i] = idx[3 - i];
-}
-
-int first_not(const int* ord, int skip) {
-    for (int i = 0; i < 4; ++i)
-        if (ord[i] != skip) return ord[i];
-    return -1;
-}
-
-// core:579-593: max-sum path, first maximum wins
-void viterbi(const int64_t* freq /*[4][k]*/, const int64_t* nn /*[k-1][16]*/, int k, uint8_t* path) {
-    int64_t score[4];
-    std::vector<std::array<int8_t, 4>> back(k);
-    for (int b = 0; b < 4; ++b) score[b] = freq[b * k + 0];
-    for (int t = 1; t < k; ++t) {
-        int64_t nw[4];
-        for (int cur = 0; cur < 4; ++cur) {
-            int64_t best = 0;
-            int arg = -1;
-            for (int prev = 0; prev < 4; ++prev) {
-                const int64_t val = score[prev] + nn[(t - 1) * 16 + prev * 4 + cur];
-                if (arg < 0 || val > best) {
-                    best = val;
-                    arg = prev;
-                }
-            }
-            nw[cur] = best + freq[cur * k + t];
-            back[t][cur] = (int8_t)arg;
-        }
-        memcpy(score, nw, sizeof nw);
-    }
-    int cur = 0;
-    for (int b = 1; b < 4; ++b)
-        if (score[b] > score[cur]) cur = b;
-    path[k - 1] = (uint8_t)cur;
-    for (int t = k - 1; t >= 1; --t) {
-        cur = back[t][cur];
-        path[t - 1] = (uint8_t)cur;
-    }
-}
-
-// core:922-1080: the refinement the reference would try at every junction tied at the minimum NN coverage
-void refine_options(Track& t) {
-    const int k = t.k, last = k - 2;
-    t.opts.clear();
-    int64_t lowest = t.nn_cov[0];
-    for (int j = 1; j < k - 1; ++j) lowest = std::min(lowest, t.nn_cov[j]);
-    for (int j = 0; j < k - 1; ++j) {
-        if (t.nn_cov[j] != lowest) continue;
-        const int row = t.seed[j], col = t.seed[j + 1];
-        const int64_t* L = t.nn[j].data();
-        Opt o;
-        o.valid = false;
-        auto middle = [&](int jj) {
-            const int nrow = t.seed[jj + 1], ncol = t.seed[jj + 2];
-            const int64_t* L0 = t.nn[jj].data();
-            const int64_t* L1 = t.nn[jj + 1].data();
-            int64_t m[4];
-            for (int x = 0; x < 4; ++x) m[x] = std::min(L0[row * 4 + x], L1[x * 4 + ncol]);
-            if (npos4(m) <= 1) return;
-            int ord[4];
-            order_desc(m, ord);
-            const int idx = first_not(ord, col);
-            o.valid = true;
-            o.pos = jj + 1;
-            o.base = idx;
-            o.nl = 2;
-            o.lidx[0] = jj;
-            o.lidx[1] = jj + 1;
-            memcpy(o.layer[0], L0, sizeof o.layer[0]);
-            memcpy(o.layer[1], L1, sizeof o.layer[1]);
-            for (int x = 0; x < 4; ++x) {
-                o.layer[0][x * 4 + col] += L0[x * 4 + idx];
-                o.layer[0][x * 4 + idx] = 0;
-            }
-            for (int y = 0; y < 4; ++y) {
-                o.layer[1][nrow * 4 + y] += L1[idx * 4 + y];
-                o.layer[1][idx * 4 + y] = 0;
-            }
-            o.cov = t.nn_cov;
-            o.cov[jj] = o.layer[0][row * 4 + col];
-            o.cov[jj + 1] = o.layer[1][nrow * 4 + ncol];
-        };
-        if (j == 0) {
-            int64_t column0[4];
-            for (int x = 0; x < 4; ++x) column0[x] = L[x * 4 + col];
-            if (npos4(column0) > 1) {  // position 0
-                int ord[4];
-                order_desc(column0, ord);
-                const int idx = first_not(ord, row);
-                o.valid = true;
-                o.pos = 0;
-                o.base = idx;
-                o.nl = 1;
-                o.lidx[0] = 0;
-                memcpy(o.layer[0], L, sizeof o.layer[0]);
-                for (int y = 0; y < 4; ++y) {
-                    o.layer[0][row * 4 + y] += L[idx * 4 + y];
-                    o.layer[0][idx * 4 + y] = 0;
-                }
-                o.cov = t.nn_cov;
-                o.cov[0] = o.layer[0][row * 4 + col];
-            } else if (npos4(L + row * 4) > 1) {
-                middle(0);
-            }
-        } else if (j == last) {
-            if (npos4(L + row * 4) > 1) {
-                int ord[4];
-                order_desc(L + row * 4, ord);
-                const int idx = first_not(ord, col);
-                o.valid = true;
-                o.pos = j + 1;
-                o.base = idx;
-                o.nl = 1;
-                o.lidx[0] = j;
-                memcpy(o.layer[0], L, sizeof o.layer[0]);
-                for (int x = 0; x < 4; ++x) {
-                    o.layer[0][x * 4 + col] += L[x * 4 + idx];
-                    o.layer[0][x * 4 + idx] = 0;
-                }
-                o.cov = t.nn_cov;
-                o.cov[j] = o.layer[0][row * 4 + col];
-            }
-        } else {
-            middle(j);
-        }
-        t.opts.push_back(std::move(o));
-    }
-}
-
-int degeneracy_of(const uint8_t* sets, int k, int* ndeg) {
-    long long d = 1;
-    int n = 0;
-    for (int i = 0; i < k; ++i) {
-        d *= FOLD[sets[i] & 15];
-        n += FOLD[sets[i] & 15] > 1;
-        if (d > (1ll << 40)) d = 1ll << 40;
-    }
-    if (ndeg) *ndeg = n;
-    return d > 0x7fffffff ? 0x7fffffff : (int)d;
-}
-
-void push_trace(Track& t) {
-    std::array<uint8_t, 32> a{};
-    memcpy(a.data(), t.sets, 32);
-    t.trace.push_back(a);
-}
-
-}  // namespace
-
-extern "C" int mpb_walk(int k, int v, int dnum, int degeneracy, uint32_t fmask, uint32_t rmask, int32_t n_win,
-                        const int32_t* win_pos, const int64_t* cover_number, const int64_t* freq, const int64_t* nn,
-                        const uint64_t* mm_key, mpb_scan_cb scan, void* user, uint8_t* out_sets, int64_t* out_counts,
-                        uint8_t* out_seeds, int64_t* out_seed_cover, int32_t* out_ntracks, int64_t trace_cap,
-                        uint8_t* trace_sets, int64_t* trace_off, int64_t* stats) {
-    if (!win_pos || !cover_number || !freq || !nn || !mm_key || !scan || !out_sets || !out_counts || !out_seeds ||
+// Host driver of the shared walk (mpb_walk_core.h): all windows of a batch in lock step, one scan call per round.
+// The product path on the GPU is mpb_walk_dev.cu (same core, state resident in HBM); this driver serves the CPU
+// tests (scan = a stand-in) and any caller that wants to own the scan.
+extern "C" int mpb_walk(int k, int v, int dnum, int degeneracy, int32_t n_win, const int64_t* cover_number,
+                        const int64_t* freq, const int64_t* nn, const uint64_t* mm_key, mpb_scan_cb scan, void* user,
+                        uint8_t* out_sets, int64_t* out_counts, uint8_t* out_seeds, int64_t* out_seed_cover,
+                        int32_t* out_ntracks, int64_t trace_cap, uint8_t* trace_sets, int64_t* trace_off, int64_t* stats) {
+    if (!cover_number || !freq || !nn || !mm_key || !scan || !out_sets || !out_counts || !out_seeds ||
         !out_seed_cover || !out_ntracks || !trace_off)
         return mpb_fail(MPB_EINVAL, "NULL argument");
     if (k < 3 || k > MPB_MAX_K || n_win < 0) return mpb_fail(MPB_EINVAL, "bad k or n_win");
-    std::vector<Track> tracks;
-    tracks.reserve((size_t)n_win * 2);
-    std::vector<int> first_track(n_win + 1, 0);
+    (void)v;
+    std::vector<mpb_track> tracks((size_t)n_win * 2);
+    std::vector<uint8_t> trace((size_t)n_win * 2 * MPB_WALK_MAX_ROUNDS * 32, 0);
+    std::vector<int> ntr(n_win, 0);
     for (int w = 0; w < n_win; ++w) {
-        first_track[w] = (int)tracks.size();
-        uint8_t nm[32] = {0}, mm[32] = {0};
-        viterbi(freq + (int64_t)w * 4 * k, nn + (int64_t)w * (k - 1) * 16, k, nm);
-        bool has_mm = mm_key[w] != MPB_KEY_EMPTY;
-        bool same = false;
-        if (has_mm) {
-            const uint64_t key = mm_key[w];
-            const uint64_t mask = (1ull << k) - 1ull;
-            const uint64_t b0 = key & mask, b1 = (key >> k) & mask;
-            same = true;
-            for (int i = 0; i < k; ++i) {
-                mm[i] = (uint8_t)(((b0 >> i) & 1ull) | (((b1 >> i) & 1ull) << 1));
-                same = same && mm[i] == nm[i];
-            }
-        }
-        const int nt = (has_mm && !same) ? 2 : 1;
-        out_ntracks[w] = nt;
-        for (int ti = 0; ti < nt; ++ti) {
-            Track t;
-            t.win = w;
-            t.k = k;
-            memset(t.seed, 0, 32);
-            memset(t.sets, 0, 32);
-            memcpy(t.seed, ti == 0 ? nm : mm, k);
-            memset(t.allow, 0, sizeof t.allow);
-            for (int i = 0; i < k; ++i) {
-                t.sets[i] = (uint8_t)(1u << t.seed[i]);
-                t.allow[t.seed[i]] |= 1u << i;
-            }
-            t.nn.resize(k - 1);
-            t.nn_cov.resize(k - 1);
-            for (int j = 0; j < k - 1; ++j) {
-                memcpy(t.nn[j].data(), nn + ((int64_t)w * (k - 1) + j) * 16, 16 * sizeof(int64_t));
-                t.nn_cov[j] = t.nn[j][t.seed[j] * 4 + t.seed[j + 1]];
-            }
-            memcpy(out_seeds + ((int64_t)w * 2 + ti) * 32, t.seed, 32);
-            tracks.push_back(std::move(t));
-        }
+        ntr[w] = mpb_walk_seed(w, k, freq + (int64_t)w * 4 * k, nn + (int64_t)w * (k - 1) * 16, mm_key[w],
+                               &tracks[2 * w], &tracks[2 * w + 1]);
+        out_ntracks[w] = ntr[w];
+        for (int ti = 0; ti < ntr[w]; ++ti) memcpy(out_seeds + ((int64_t)w * 2 + ti) * 32, tracks[2 * w + ti].seed, 32);
     }
-    first_track[n_win] = (int)tracks.size();
-    std::vector<int> live(tracks.size());
-    for (size_t i = 0; i < tracks.size(); ++i) live[i] = (int)i;
     int64_t rounds = 0, cands_total = 0;
-    std::vector<int32_t> cpos, cpos_sorted;
-    std::vector<uint32_t> callow, callow_sorted;
-    std::vector<int64_t> counts, counts_sorted;
-    std::vector<int> order;
-    while (!live.empty()) {
-        cpos.clear();
-        callow.clear();
-        for (int ti : live) {
-            Track& t = tracks[ti];
-            t.first_cand = (int)cpos.size();
-            const int32_t pos = win_pos[t.win];
-            if (t.state == 0) {
-                cpos.push_back(pos);
-                callow.insert(callow.end(), t.allow, t.allow + 4);
-            } else {
-                refine_options(t);
-                for (const Opt& o : t.opts) {
-                    if (!o.valid) continue;
-                    if (t.sets[o.pos] & (1u << o.base))
-                        return mpb_fail(MPB_EINVAL, "refinement would re-add a base (the reference raises KeyError)");
-                    const uint32_t bit = 1u << o.pos;
-                    cpos.push_back(pos);  // primer with position pos := base alone (coverage_renew look-up)
-                    for (int x = 0; x < 4; ++x) callow.push_back(x == o.base ? (t.allow[x] | bit) : (t.allow[x] & ~bit));
-                    cpos.push_back(pos);  // primer with the base added
-                    for (int x = 0; x < 4; ++x) callow.push_back(x == o.base ? (t.allow[x] | bit) : t.allow[x]);
-                }
+    std::vector<mpb_cand> cands;
+    std::vector<int64_t> counts;
+    mpb_cand buf[MPB_MAX_K];
+    for (;;) {
+        cands.clear();
+        for (int w = 0; w < n_win; ++w)
+            for (int ti = 0; ti < ntr[w]; ++ti) {
+                mpb_track& t = tracks[2 * w + ti];
+                if (t.state == 2) continue;
+                t.first_cand = (int32_t)cands.size();
+                const int n = mpb_walk_emit(t, k, buf);
+                cands.insert(cands.end(), buf, buf + n);
+                if (t.err == 1) return mpb_fail(MPB_EINVAL, "refinement would re-add a base (the reference raises KeyError)");
             }
-        }
-        const int64_t nc = (int64_t)cpos.size();
-        order.resize(nc);
-        for (int64_t i = 0; i < nc; ++i) order[i] = (int)i;
-        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cpos[a] < cpos[b]; });
-        cpos_sorted.resize(nc);
-        callow_sorted.resize(nc * 4);
-        for (int64_t i = 0; i < nc; ++i) {
-            cpos_sorted[i] = cpos[order[i]];
-            memcpy(&callow_sorted[i * 4], &callow[(int64_t)order[i] * 4], 16);
-        }
-        counts_sorted.assign(nc * 3, 0);
+        bool any = false;
+        for (int w = 0; w < n_win && !any; ++w)
+            for (int ti = 0; ti < ntr[w]; ++ti) any = any || tracks[2 * w + ti].state != 2;
+        if (!any) break;
+        const int64_t nc = (int64_t)cands.size();
+        counts.assign((size_t)nc * 4 + 4, 0);
         if (nc > 0) {
-            const int rc = scan(user, cpos_sorted.data(), callow_sorted.data(), nc, counts_sorted.data());
+            const int rc = scan(user, cands.data(), nc, counts.data());
             if (rc) return mpb_fail(rc, "scan callback failed");
         }
-        counts.resize(nc * 3);
-        for (int64_t i = 0; i < nc; ++i) memcpy(&counts[(int64_t)order[i] * 3], &counts_sorted[i * 3], 24);
         ++rounds;
         cands_total += nc;
-        std::vector<int> next;
-        for (int ti : live) {
-            Track& t = tracks[ti];
-            const int64_t total = cover_number[t.win];
-            const int64_t* c = &counts[(int64_t)t.first_cand * 3];
-            if (t.state == 0) {
-                t.init = c[0];
-                t.fm = c[1];
-                t.rm = c[2];
-                t.seed_cover = t.init;
-                t.perfect = c[0];  // expansion rows matching the primer exactly (core:853 perfect_coverage)
-                push_trace(t);
-                t.state = 1;
-                if (t.init + t.fm < total || t.init + t.rm < total) next.push_back(ti);
-                else t.state = 2;
-                continue;
+        for (int w = 0; w < n_win; ++w)
+            for (int ti = 0; ti < ntr[w]; ++ti) {
+                mpb_track& t = tracks[2 * w + ti];
+                if (t.state == 2) continue;
+                mpb_walk_consume(t, k, &counts[(size_t)t.first_cand * 4], cover_number[w], dnum, degeneracy,
+                                 &trace[(size_t)(2 * w + ti) * MPB_WALK_MAX_ROUNDS * 32]);
+                if (t.err == 2) return mpb_fail(MPB_EOVERFLOW, "more than %d refinement rounds in one window", MPB_WALK_MAX_ROUNDS);
             }
-            int best = 0, ci = 0, best_ci = -1;
-            int64_t best_gain = 0;
-            bool have = false;
-            for (size_t oi = 0; oi < t.opts.size(); ++oi) {
-                int64_t gain = t.init;
-                int my_ci = -1;
-                if (t.opts[oi].valid) {
-                    gain += c[ci * 3 + 0];
-                    my_ci = ci;
-                    ci += 2;
-                }
-                if (!have || gain > best_gain) {
-                    have = true;
-                    best_gain = gain;
-                    best = (int)oi;
-                    best_ci = my_ci;
-                }
-            }
-            const Opt& o = t.opts[best];
-            std::vector<int64_t> cov_new = t.nn_cov;
-            if (o.valid) {
-                t.sets[o.pos] |= (uint8_t)(1u << o.base);
-                t.allow[o.base] |= 1u << o.pos;
-                for (int l = 0; l < o.nl; ++l) memcpy(t.nn[o.lidx[l]].data(), o.layer[l], sizeof o.layer[l]);
-                cov_new = o.cov;
-                t.perfect = c[(best_ci + 1) * 3 + 0];
-                t.fm = c[(best_ci + 1) * 3 + 1];
-                t.rm = c[(best_ci + 1) * 3 + 2];
-            }
-            t.init = best_gain;
-            push_trace(t);
-            int ndeg = 0;
-            const long long deg = degeneracy_of(t.sets, k, &ndeg);
-            if (std::max(t.fm, t.rm) == total) {
-                t.state = 2;
-            } else if (cov_new == t.nn_cov) {
-                t.state = 2;
-            } else if (2 * deg > degeneracy || 3.0 * deg / 2 > degeneracy || ndeg == dnum) {
-                t.state = 2;
-            } else {
-                t.nn_cov = cov_new;
-                if (t.init + t.fm < total || t.init + t.rm < total) next.push_back(ti);
-                else t.state = 2;
-            }
-        }
-        live.swap(next);
     }
-    // choose the track (core:816: NM only when strictly better), emit results and the call trace
     int64_t tr = 0;
     for (int w = 0; w < n_win; ++w) {
         trace_off[w] = tr;
-        const int a = first_track[w], nt = first_track[w + 1] - first_track[w];
-        int pick = a;
-        if (nt == 2) {
-            const Track &nmt = tracks[a], &mmt = tracks[a + 1];
-            pick = ((nmt.init + nmt.fm) + (nmt.init + nmt.rm) > (mmt.init + mmt.fm) + (mmt.init + mmt.rm)) ? a : a + 1;
-        }
-        const Track& t = tracks[pick];
+        const mpb_track* a = &tracks[2 * w];
+        const int pick = ntr[w] == 2 ? mpb_walk_pick(a[0], a[1]) : 0;
+        const mpb_track& t = a[pick];
         memcpy(out_sets + (int64_t)w * 32, t.sets, 32);
         out_counts[w * 5 + 0] = t.init;
         out_counts[w * 5 + 1] = t.fm;
         out_counts[w * 5 + 2] = t.rm;
-        out_counts[w * 5 + 3] = pick - a;
+        out_counts[w * 5 + 3] = pick;
         out_counts[w * 5 + 4] = t.perfect;
-        for (int ti = 0; ti < 2; ++ti) out_seed_cover[w * 2 + ti] = ti < nt ? tracks[a + ti].seed_cover : -1;
-        for (int ti = 0; ti < nt; ++ti)
-            for (const auto& s : tracks[a + ti].trace) {
-                if (trace_sets && tr < trace_cap) memcpy(trace_sets + tr * 32, s.data(), 32);
+        for (int ti = 0; ti < 2; ++ti) out_seed_cover[w * 2 + ti] = ti < ntr[w] ? a[ti].seed_cover : -1;
+        for (int ti = 0; ti < ntr[w]; ++ti)
+            for (int r = 0; r < a[ti].n_trace; ++r) {
+                if (trace_sets && tr < trace_cap)
+                    memcpy(trace_sets + tr * 32, &trace[((size_t)(2 * w + ti) * MPB_WALK_MAX_ROUNDS + r) * 32], 32);
                 ++tr;
             }
     }
@@ -405,6 +105,25 @@ extern "C" int mpb_walk(int k, int v, int dnum, int degeneracy, uint32_t fmask, 
     if (trace_sets && tr > trace_cap) return mpb_fail(MPB_EOVERFLOW, "trace capacity %lld < %lld", (long long)trace_cap, (long long)tr);
     return 0;
 }
+
+namespace {
+const int FOLD[16] = {0, 1, 1, 2, 1, 2, 2, 3, 1, 2, 2, 3, 2, 3, 3, 4};
+// expansion order of each base set (core:105-107): ORD[set] lists base indices A,C,G,T = 0..3
+const int8_t ORD[16][4] = {{-1, -1, -1, -1}, {0, -1, -1, -1}, {1, -1, -1, -1}, {0, 1, -1, -1},  {2, -1, -1, -1}, {0, 2, -1, -1},
+                           {2, 1, -1, -1},   {2, 0, 1, -1},   {3, -1, -1, -1}, {0, 3, -1, -1},  {1, 3, -1, -1},  {0, 3, 1, -1},
+                           {2, 3, -1, -1},   {2, 0, 3, -1},   {2, 3, 1, -1},   {0, 3, 2, 1}};
+int degeneracy_of(const uint8_t* sets, int k, int* ndeg) {
+    long long d = 1;
+    int n = 0;
+    for (int i = 0; i < k; ++i) {
+        d *= FOLD[sets[i] & 15];
+        n += FOLD[sets[i] & 15] > 1;
+        if (d > (1ll << 40)) d = 1ll << 40;
+    }
+    if (ndeg) *ndeg = n;
+    return d > 0x7fffffff ? 0x7fffffff : (int)d;
+}
+}  // namespace
 
 // ------------------------------------------------------------------------------------------------------
 // properties of finished primers

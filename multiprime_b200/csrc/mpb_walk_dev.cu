@@ -1,0 +1,328 @@
+// mpb_walk_dev.cu — the refinement walk of a window batch resident on the device.
+//
+// The reference's coverage_stast loop (core:860-920) alternates a data-dependent refinement step with a scan of every
+// sequence (mis_primer_check).  Round 1 drove it from the host: 11 dependent launch -> sync -> D2H -> Python callback
+// round trips per window batch.  Here the tracks (mpb_walk_core.h: seeds, NN arrays, counters) live in HBM and a
+// round is a chain of kernels on one stream:
+//     k_walk_advance   one thread per track: take the previous round's counts, advance (mpb_walk_consume), emit the
+//                      next candidates (mpb_walk_emit) at a slot range claimed with one atomicAdd
+//     k_cscan_plan / k_cscan / k_cscan_special    (mpb_cscan.cu) read the candidate count from device memory
+// The host only enqueues; it learns the number of live tracks from a pinned word written by an asynchronous copy and
+// stops enqueueing when it reads zero (rounds enqueued past the end are no-ops: zero candidates).
+// Sequence-sharded runs all-reduce the count vector between scan and advance (the caller does, on the same stream).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <vector>
+
+#include "mpb200.h"
+#include "mpb_host.h"
+#include "mpb_cscan.h"
+#include "mpb_walk_core.h"
+
+#define fail mpb_fail
+#define CK MPB_CK
+#define LAUNCH MPB_LAUNCH
+
+struct mpb_walk_dev {
+    mpb_hist* h;
+    int k, dnum, degeneracy, n_win, max_cands, rounds_enqueued, max_rounds;
+    uint32_t fmask, rmask;
+    mpb_track* tracks;      // [2 * n_win]
+    int32_t* ntracks;       // [n_win]
+    int64_t* cover;         // [n_win]
+    uint8_t* trace;         // [2 * n_win][MPB_WALK_MAX_ROUNDS][32]
+    mpb_cand* cands;        // [max_cands]
+    uint32_t* plans;        // [max_cands][CSCAN_PLAN_WORDS]
+    unsigned long long* counts;  // [max_cands][4]
+    int* n_cand;            // [2]: candidates of the current round, of the next one being emitted
+    int* live_dev;          // [max_rounds + 1] live tracks after each advance
+    unsigned long long* totals;  // [2] rounds with candidates, candidates scanned
+    int* live_host;         // pinned mirror of live_dev
+    int* err;               // track error flags (OR)
+};
+
+__global__ void k_walk_seed(int n_win, int k, const int32_t* __restrict__ win_idx, const unsigned long long* __restrict__ freq,
+                            const unsigned long long* __restrict__ nn, int tensors_by_hist_window,
+                            const uint64_t* __restrict__ mm_key, mpb_track* __restrict__ tracks, int32_t* __restrict__ ntracks) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_win) return;
+    const long long src = tensors_by_hist_window ? win_idx[w] : w;
+    ntracks[w] = mpb_walk_seed(win_idx[w], k, reinterpret_cast<const int64_t*>(freq) + src * 4 * k,
+                               reinterpret_cast<const int64_t*>(nn) + src * (k - 1) * 16, mm_key[w], &tracks[2 * w],
+                               &tracks[2 * w + 1]);
+    if (ntracks[w] == 1) tracks[2 * w + 1].state = 2;
+}
+
+// one thread per track slot.  n_cand[0]: candidates of the round whose counts are consumed; n_cand[1]: the round being
+// emitted (zeroed by the host-side memset before this kernel).
+__global__ void k_walk_advance(int n_win, int k, int dnum, int degeneracy, int round, mpb_track* __restrict__ tracks,
+                               const int32_t* __restrict__ ntracks, const int64_t* __restrict__ cover,
+                               const unsigned long long* __restrict__ counts, mpb_cand* __restrict__ cands,
+                               int* __restrict__ n_cand, int max_cands, uint8_t* __restrict__ trace, int* __restrict__ live,
+                               unsigned long long* __restrict__ totals, int* __restrict__ err) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    bool alive = false;
+    if (s < 2 * n_win && (s & 1) < ntracks[s >> 1]) {
+        mpb_track& t = tracks[s];
+        if (t.state != 2) {
+            if (round > 0)
+                mpb_walk_consume(t, k, reinterpret_cast<const int64_t*>(counts) + (long long)t.first_cand * 4, cover[s >> 1],
+                                 dnum, degeneracy, trace + (long long)s * MPB_WALK_MAX_ROUNDS * 32);
+            if (t.state != 2) {
+                mpb_cand buf[MPB_MAX_K];
+                const int n = mpb_walk_emit(t, k, buf);
+                const int base = atomicAdd(&n_cand[1], n);
+                if (base + n <= max_cands) {
+                    for (int i = 0; i < n; ++i) cands[base + i] = buf[i];
+                    t.first_cand = base;
+                } else {
+                    t.err |= 4;
+                    t.state = 2;
+                }
+                alive = t.state != 2;
+            }
+            if (t.err) atomicOr(err, t.err);
+        }
+    }
+    const unsigned b = __ballot_sync(0xffffffffu, alive);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(&live[round], __popc(b));
+    if (s == 0 && round > 0 && n_cand[0] > 0) {
+        atomicAdd(&totals[0], 1ull);
+        atomicAdd(&totals[1], (unsigned long long)n_cand[0]);
+    }
+}
+
+__global__ void k_walk_shift(int* __restrict__ n_cand) {
+    n_cand[0] = n_cand[1];
+    n_cand[1] = 0;
+}
+
+extern "C" int mpb_walk_dev_begin(mpb_hist* h, int dnum, int degeneracy, uint32_t fmask, uint32_t rmask, int32_t n_win,
+                                  const int32_t* win_idx, const int64_t* cover_number, const uint64_t* mm_key,
+                                  const int64_t* freq_hd, const int64_t* nn_hd, mpb_walk_dev** out) {
+    if (!h || !win_idx || !cover_number || !mm_key || !out) return fail(MPB_EINVAL, "NULL argument");
+    if (n_win < 1) return fail(MPB_EINVAL, "no windows to walk");
+    if ((freq_hd == nullptr) != (nn_hd == nullptr)) return fail(MPB_EINVAL, "freq and nn come together");
+    if (!freq_hd && !h->have_summary) return fail(MPB_EINVAL, "mpb_hist_summary has not run on this handle");
+    for (int i = 0; i < n_win; ++i)
+        if (win_idx[i] < 0 || win_idx[i] >= h->nw) return fail(MPB_EINVAL, "win_idx[%d]=%d outside the batch", i, win_idx[i]);
+    mpb_ctx* ctx = h->msa->ctx;
+    CK(cudaSetDevice(ctx->device));
+    const int k = h->k;
+    mpb_walk_dev* w = new mpb_walk_dev();
+    memset(w, 0, sizeof *w);
+    w->h = h;
+    w->k = k;
+    w->dnum = dnum;
+    w->degeneracy = degeneracy;
+    w->n_win = n_win;
+    w->fmask = fmask;
+    w->rmask = rmask;
+    w->max_cands = 2 * n_win * (k - 1);
+    w->max_rounds = MPB_WALK_MAX_ROUNDS;
+    cudaError_t e = cudaMallocAsync(&w->tracks, (size_t)2 * n_win * sizeof(mpb_track), ctx->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&w->ntracks, (size_t)n_win * 4, ctx->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&w->cover, (size_t)n_win * 8, ctx->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&w->trace, (size_t)2 * n_win * MPB_WALK_MAX_ROUNDS * 32, ctx->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&w->cands, (size_t)w->max_cands * sizeof(mpb_cand), ctx->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&w->plans, (size_t)w->max_cands * CSCAN_PLAN_WORDS * 4, ctx->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&w->counts, (size_t)w->max_cands * 4 * 8, ctx->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&w->n_cand, 8, ctx->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&w->live_dev, (size_t)(w->max_rounds + 1) * 4, ctx->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&w->totals, 16, ctx->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&w->err, 4, ctx->stream);
+    if (e == cudaSuccess) e = cudaMallocHost(&w->live_host, (size_t)(w->max_rounds + 1) * 4);
+    if (e != cudaSuccess) {
+        mpb_walk_dev_free(w);
+        return fail(MPB_ENOMEM, "walk state for %d windows: %s", n_win, cudaGetErrorString(e));
+    }
+    for (int i = 0; i <= w->max_rounds; ++i) w->live_host[i] = -1;
+    CK(cudaMemsetAsync(w->n_cand, 0, 8, ctx->stream));
+    CK(cudaMemsetAsync(w->live_dev, 0, (size_t)(w->max_rounds + 1) * 4, ctx->stream));
+    CK(cudaMemsetAsync(w->totals, 0, 16, ctx->stream));
+    CK(cudaMemsetAsync(w->err, 0, 4, ctx->stream));
+    CK(cudaMemsetAsync(w->counts, 0, (size_t)w->max_cands * 4 * 8, ctx->stream));
+    CK(cudaMemcpyAsync(w->cover, cover_number, (size_t)n_win * 8, cudaMemcpyHostToDevice, ctx->stream));
+    InBuf wi(ctx, win_idx, (size_t)n_win * 4), mk(ctx, mm_key, (size_t)n_win * 8);
+    InBuf fq(ctx, freq_hd, (size_t)n_win * 4 * k * 8), nq(ctx, nn_hd, (size_t)n_win * (k - 1) * 16 * 8);
+    if (wi.rc || mk.rc || fq.rc || nq.rc) {
+        mpb_walk_dev_free(w);
+        return MPB_ECUDA;
+    }
+    LAUNCH(ctx, k_walk_seed, (unsigned)((n_win + 63) / 64), 64, 0, n_win, k, wi.dev<int32_t>(),
+           freq_hd ? fq.dev<unsigned long long>() : h->freq, freq_hd ? nq.dev<unsigned long long>() : h->nn,
+           freq_hd ? 0 : 1, mk.dev<uint64_t>(), w->tracks, w->ntracks);
+    CK(cudaStreamSynchronize(ctx->stream));  // host staging buffers (cover, win_idx, mm_key, tensors)
+    *out = w;
+    return 0;
+}
+
+extern "C" int mpb_walk_dev_advance(mpb_walk_dev* w) {
+    if (!w) return fail(MPB_EINVAL, "NULL argument");
+    if (w->rounds_enqueued >= w->max_rounds) return fail(MPB_EOVERFLOW, "more than %d walk rounds", w->max_rounds);
+    mpb_ctx* ctx = w->h->msa->ctx;
+    CK(cudaSetDevice(ctx->device));
+    const int r = w->rounds_enqueued;
+    LAUNCH(ctx, k_walk_advance, (unsigned)((2 * w->n_win + 63) / 64), 64, 0, w->n_win, w->k, w->dnum, w->degeneracy, r,
+           w->tracks, w->ntracks, w->cover, w->counts, w->cands, w->n_cand, w->max_cands, w->trace, w->live_dev, w->totals,
+           w->err);
+    LAUNCH(ctx, k_walk_shift, 1, 1, 0, w->n_cand);
+    CK(cudaMemcpyAsync(&w->live_host[r], &w->live_dev[r], 4, cudaMemcpyDeviceToHost, ctx->stream));
+    w->rounds_enqueued = r + 1;
+    return 0;
+}
+
+extern "C" int mpb_walk_dev_scan(mpb_walk_dev* w) {
+    if (!w) return fail(MPB_EINVAL, "NULL argument");
+    mpb_ctx* ctx = w->h->msa->ctx;
+    CK(cudaSetDevice(ctx->device));
+    return mpb_cscan_launch(w->h, w->fmask, w->rmask, w->cands, w->n_cand, w->max_cands, w->plans, w->counts, 1, nullptr,
+                            nullptr);
+}
+
+extern "C" int mpb_walk_dev_round(mpb_walk_dev* w) {
+    int rc = mpb_walk_dev_advance(w);
+    if (rc) return rc;
+    return mpb_walk_dev_scan(w);
+}
+
+extern "C" int mpb_walk_dev_counts(mpb_walk_dev* w, void** counts_dev, int64_t* n_elems) {
+    if (!w || !counts_dev || !n_elems) return fail(MPB_EINVAL, "NULL argument");
+    *counts_dev = w->counts;
+    *n_elems = (int64_t)w->max_cands * 4;
+    return 0;
+}
+
+extern "C" int64_t mpb_walk_dev_live(mpb_walk_dev* w) {
+    if (!w) return -1;
+    int64_t last = -1;
+    for (int r = 0; r < w->rounds_enqueued; ++r) {
+        const int v = *((volatile int*)&w->live_host[r]);
+        if (v < 0) break;
+        last = v;
+    }
+    return last;
+}
+
+extern "C" int mpb_walk_dev_max_rounds(mpb_walk_dev* w) { return w ? w->max_rounds : 0; }
+
+// Block (spin on the pinned mirror) until the number of live tracks after advance number `round` is known.
+extern "C" int mpb_walk_dev_wait(mpb_walk_dev* w, int round, int64_t* live) {
+    if (!w || !live || round < 0 || round >= w->rounds_enqueued) return fail(MPB_EINVAL, "no such round");
+    mpb_ctx* ctx = w->h->msa->ctx;
+    volatile int* p = (volatile int*)&w->live_host[round];
+    for (unsigned spin = 0;; ++spin) {
+        const int v = *p;
+        if (v >= 0) {
+            *live = v;
+            return 0;
+        }
+        if ((spin & 0x3FFu) == 0x3FFu) {
+            const cudaError_t e = cudaStreamQuery(ctx->stream);
+            if (e == cudaSuccess) {  // stream drained: the copy has landed (or never will)
+                if (*p >= 0) continue;
+                return fail(MPB_ECUDA, "walk round %d never reported", round);
+            }
+            if (e != cudaErrorNotReady) return fail(MPB_ECUDA, "walk: %s", cudaGetErrorString(e));
+        }
+    }
+}
+
+// Single-process driver: enqueue rounds, staying at most `lag` rounds ahead of the device, until no track is live.
+extern "C" int mpb_walk_dev_run(mpb_walk_dev* w, int lag, int64_t* rounds_out) {
+    if (!w) return fail(MPB_EINVAL, "NULL argument");
+    if (lag < 0) lag = 0;
+    for (;;) {
+        int rc = mpb_walk_dev_advance(w);
+        if (rc) return rc;
+        const int r = w->rounds_enqueued - 1;
+        if (r >= lag) {
+            int64_t live = 0;
+            rc = mpb_walk_dev_wait(w, r - lag, &live);
+            if (rc) return rc;
+            if (live == 0) break;
+        }
+        rc = mpb_walk_dev_scan(w);
+        if (rc) return rc;
+    }
+    if (rounds_out) *rounds_out = w->rounds_enqueued;
+    return 0;
+}
+
+extern "C" int mpb_walk_dev_finish(mpb_walk_dev* w, uint8_t* out_sets, int64_t* out_counts, uint8_t* out_seeds,
+                                   int64_t* out_seed_cover, int32_t* out_ntracks, int64_t trace_cap, uint8_t* trace_sets,
+                                   int64_t* trace_off, int64_t* stats) {
+    if (!w || !out_sets || !out_counts || !out_seeds || !out_seed_cover || !out_ntracks || !trace_off)
+        return fail(MPB_EINVAL, "NULL argument");
+    mpb_ctx* ctx = w->h->msa->ctx;
+    CK(cudaSetDevice(ctx->device));
+    const int n_win = w->n_win;
+    std::vector<mpb_track> tracks((size_t)2 * n_win);
+    std::vector<int32_t> ntr(n_win);
+    std::vector<uint8_t> trace(trace_sets ? (size_t)2 * n_win * MPB_WALK_MAX_ROUNDS * 32 : 0);
+    unsigned long long totals[2] = {0, 0};
+    int err = 0, ncand_now[2] = {0, 0};
+    CK(cudaMemcpyAsync(tracks.data(), w->tracks, tracks.size() * sizeof(mpb_track), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ntr.data(), w->ntracks, (size_t)n_win * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (trace_sets) CK(cudaMemcpyAsync(trace.data(), w->trace, trace.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(totals, w->totals, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&err, w->err, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ncand_now, w->n_cand, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (err & 1) return fail(MPB_EINVAL, "refinement would re-add a base (the reference raises KeyError)");
+    if (err & 2) return fail(MPB_EOVERFLOW, "more than %d refinement rounds in one window", MPB_WALK_MAX_ROUNDS);
+    if (err & 4) return fail(MPB_EOVERFLOW, "candidate buffer overflow");
+    // the last scanned round's candidates are not in totals yet when live tracks remain (caller stopped early)
+    for (int s = 0; s < 2 * n_win; ++s)
+        if ((s & 1) < ntr[s >> 1] && tracks[s].state != 2) return fail(MPB_EINVAL, "walk not finished: track %d still live", s);
+    int64_t tr = 0;
+    for (int wdx = 0; wdx < n_win; ++wdx) {
+        trace_off[wdx] = tr;
+        const mpb_track* a = &tracks[2 * (size_t)wdx];
+        const int pick = ntr[wdx] == 2 ? mpb_walk_pick(a[0], a[1]) : 0;
+        const mpb_track& t = a[pick];
+        memcpy(out_sets + (int64_t)wdx * 32, t.sets, 32);
+        out_counts[wdx * 5 + 0] = t.init;
+        out_counts[wdx * 5 + 1] = t.fm;
+        out_counts[wdx * 5 + 2] = t.rm;
+        out_counts[wdx * 5 + 3] = pick;
+        out_counts[wdx * 5 + 4] = t.perfect;
+        out_ntracks[wdx] = ntr[wdx];
+        for (int ti = 0; ti < 2; ++ti) {
+            out_seed_cover[wdx * 2 + ti] = ti < ntr[wdx] ? a[ti].seed_cover : -1;
+            if (ti < ntr[wdx]) memcpy(out_seeds + ((int64_t)wdx * 2 + ti) * 32, a[ti].seed, 32);
+            else memset(out_seeds + ((int64_t)wdx * 2 + ti) * 32, 0, 32);
+        }
+        for (int ti = 0; ti < ntr[wdx]; ++ti)
+            for (int r = 0; r < a[ti].n_trace; ++r) {
+                if (trace_sets && tr < trace_cap)
+                    memcpy(trace_sets + tr * 32, &trace[((size_t)(2 * wdx + ti) * MPB_WALK_MAX_ROUNDS + r) * 32], 32);
+                ++tr;
+            }
+    }
+    trace_off[n_win] = tr;
+    if (stats) {
+        stats[0] = (int64_t)totals[0];
+        stats[1] = (int64_t)totals[1];
+        stats[2] = tr;
+    }
+    ctx->extra_units["k_cscan"] += (double)totals[1] * (double)w->h->msa->n_seq;
+    if (trace_sets && tr > trace_cap) return fail(MPB_EOVERFLOW, "trace capacity %lld < %lld", (long long)trace_cap, (long long)tr);
+    return 0;
+}
+
+extern "C" void mpb_walk_dev_free(mpb_walk_dev* w) {
+    if (!w) return;
+    cudaStream_t st = w->h->msa->ctx->stream;
+    void* ptrs[] = {w->tracks, w->ntracks, w->cover, w->trace, w->cands, w->plans, w->counts, w->n_cand, w->live_dev,
+                    w->totals, w->err};
+    for (void* p : ptrs)
+        if (p) cudaFreeAsync(p, st);
+    if (w->live_host) {
+        cudaStreamSynchronize(st);  // pending async copies into the pinned mirror
+        cudaFreeHost(w->live_host);
+    }
+    delete w;
+}

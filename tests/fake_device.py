@@ -120,8 +120,8 @@ class Msa:
         return (np.bincount(lead, minlength=self.n_col + 1).astype(np.int64),
                 np.bincount(rstrip, minlength=self.n_col + 1).astype(np.int64))
 
-    def hist(self, k, v, win_pos, log2_cap=0):
-        return Hist(self, k, v, win_pos)
+    def hist(self, k, v, win_pos, log2_cap=0, empty=False):
+        return Hist(self, k, v, win_pos, empty)
 
     def scan(self, k, v, fmask, rmask, cand_pos, cand_allow, bits_slot=None, counts_out=None, bits_out=None):
         cand_allow = np.asarray(cand_allow).reshape(-1, 4)
@@ -172,7 +172,7 @@ class Msa:
 
 
 class Hist:
-    def __init__(self, msa, k, v, win_pos):
+    def __init__(self, msa, k, v, win_pos, empty=False):
         self.msa, self.k, self.v = msa, k, v
         self.win_pos = [int(p) for p in win_pos]
         self.nw = len(self.win_pos)
@@ -180,6 +180,11 @@ class Hist:
         self.gap_n = []
         self.exc = []
         self.n_iupac_gap = []
+        if empty:             # owner tables of a sharded run: filled through merge_segments / add_counts
+            self.tables = [{} for _ in self.win_pos]
+            self.gap_n = [0] * self.nw
+            self.n_iupac_gap = [0] * self.nw
+            return
         for wi, p in enumerate(self.win_pos):
             tab, gaps, nig = {}, 0, 0
             for si, s in enumerate(msa.rows):
@@ -223,6 +228,58 @@ class Hist:
     def counts(self):
         return (np.array(self.gap_n, np.int64), np.array(self.n_iupac_gap, np.int64),
                 np.array([len(t) for t in self.tables], np.int64))
+
+    def add_counts(self, gap_n, n_iupac_gap):
+        self.gap_n = [int(x) for x in gap_n]
+        self.n_iupac_gap = [int(x) for x in n_iupac_gap]
+
+    def summary(self):
+        out = self.stats()
+        out["freq"], out["nn"] = self.tensors(np.ones(self.nw, np.uint8))
+        return out
+
+    def merge_segments(self, seg_off, keys, cnt, first):
+        for s in range(len(seg_off) - 1):
+            wi = s % self.nw
+            for i in range(int(seg_off[s]), int(seg_off[s + 1])):
+                e = self.tables[wi].setdefault(int(keys[i]), [0, int(first[i])])
+                e[0] += int(cnt[i])
+                e[1] = min(e[1], int(first[i]))
+
+    def cscan(self, fmask, rmask, cands, bits_slot=None, counts_out=None, bits_out=None):
+        """mpb_cscan: mpb_scan's three counts plus the perfect matches that carry the trial base"""
+        nc = len(cands)
+        pos = [self.win_pos[int(w)] for w in cands["win"]]
+        counts3, bits = self.msa.scan(self.k, self.v, fmask, rmask, pos, cands["allow"], bits_slot=bits_slot)
+        counts = np.zeros((nc, 4), np.int64)
+        counts[:, :3] = counts3
+        for ci in range(nc):
+            tr = int(cands["trial"][ci])
+            if tr < 0:
+                continue
+            tp, tb = tr & 255, (tr >> 8) & 3
+            allow = [int(x) & ~(1 << tp) for x in cands["allow"][ci]]
+            allow[tb] |= 1 << tp
+            c1, _ = self.msa.scan(self.k, self.v, fmask, rmask, [pos[ci]], np.array([allow], np.uint32))
+            counts[ci, 3] = c1[0, 0]
+        return counts, bits
+
+    def walk(self, dnum, degeneracy, fmask, rmask, win_idx, cover_number, mm_key, freq=None, nn=None, comm=None,
+             want_trace=True, lag=2):
+        """the host driver of the shared walk (mpb_walk) over this stand-in's scan"""
+        from multiprime_b200 import _lib
+        win_idx = np.asarray(win_idx)
+        if freq is None:
+            f_all, n_all = self.tensors(np.ones(self.nw, np.uint8))
+            freq, nn = f_all[win_idx], n_all[win_idx].reshape(len(win_idx), self.k - 1, 16)
+
+        def scan_fn(cands):
+            c = cands.copy()
+            c["win"] = win_idx[c["win"]]
+            counts, _ = self.cscan(fmask, rmask, c)
+            return comm.allreduce_sum(counts) if comm is not None else counts
+
+        return _lib.walk(self.k, self.v, dnum, degeneracy, cover_number, freq, nn, mm_key, scan_fn, want_trace)
 
     def stats(self):
         nw = self.nw

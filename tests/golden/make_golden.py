@@ -77,6 +77,20 @@ CASES = {
                        raw_entropy_threshold=3.6, product_len=100, position="1,2,-1", variation=1, distance=4,
                        GC="0.2,0.7"),
                   list(range(0, 30)) + list(range(7290, 7310)) + list(range(8100, 8112))),
+    # every window of the region: 1000_fasta.msa for k = 18..22, the whole
+    # Cluster_0_20727.tmsa, and the first 10^4 rows of the north-star synthetic alignment with the C4 flags
+    **{"c2f_k%d" % kk: ("test_data/1000_fasta.msa",
+                        dict(primer_length=kk, coverage=0.8, number_of_dege_bases=6, score_of_dege_bases=64,
+                             raw_entropy_threshold=3.6, product_len=100, position="1,2,-1", variation=2, distance=4,
+                             GC="0.2,0.7"), None) for kk in (18, 19, 20, 21, 22)},
+    "c3f_tmsa": ("test_data/results/Clusters_msa/Cluster_0_20727.tmsa",
+                 dict(primer_length=18, coverage=0.7, number_of_dege_bases=4, score_of_dege_bases=10,
+                      raw_entropy_threshold=3.6, product_len=150, position="2,3,-1", variation=1, distance=4,
+                      GC="0.2,0.7"), None),
+    "c4_10k": ("@synth:10000:600:20240923",
+               dict(primer_length=18, coverage=0.8, number_of_dege_bases=8, score_of_dege_bases=256,
+                    raw_entropy_threshold=3.6, product_len=100, position="1,2,-1", variation=3, distance=4,
+                    GC="0.2,0.7"), None),
     "synth300": ("@synth:300:240:7",
                  dict(primer_length=18, coverage=0.8, number_of_dege_bases=8, score_of_dege_bases=256,
                       raw_entropy_threshold=3.6, product_len=100, position="1,2,-1", variation=3, distance=4,
@@ -88,6 +102,10 @@ CASES = {
                          GC="0.2,0.7"),
                     None),
 }
+
+
+# full-window cases read the alignment fixture of an earlier case instead of storing a second copy
+MSA_ALIAS = {**{"c2f_k%d" % kk: "c2_k18" for kk in (18, 19, 20, 21, 22)}, "c3f_tmsa": "c3_tmsa"}
 
 
 def materialise(inp: str, tmp: str) -> str:
@@ -142,12 +160,15 @@ def run_case(core, name):
         for i, s in enumerate(seqs):
             codes[i, :len(s)] = [CHAR2CODE[c] for c in s]
         packed = (codes[:, 0::2] | (np.pad(codes, ((0, 0), (0, L % 2)))[:, 1::2] << 4)).astype(np.uint8)
-        if not inp.startswith("@synth:"):
+        alias = MSA_ALIAS.get(name)
+        if not inp.startswith("@synth:") and alias is None:
             np.savez_compressed(os.path.join(HERE, "msa_%s.npz" % name), packed=packed, n_col=L, lens=lens,
                                 ids=np.array(ids))
         with open(os.path.join(HERE, "core_%s.json" % name), "w") as fh:
-            json.dump({"input": inp, "params": kw, "start": start, "stop": stop, "n_seq": len(seqs),
-                       "records": records}, fh, indent=0)
+            blob = {"input": inp, "params": kw, "start": start, "stop": stop, "n_seq": len(seqs), "records": records}
+            if alias:
+                blob["msa"] = alias
+            json.dump(blob, fh, separators=(",", ":"))
         acc = sum(1 for r in records if r["row"] is not None)
         print(name, "windows", len(records), "accepted", acc, "region", start, stop)
 

@@ -30,7 +30,7 @@ def case_alignment(case: dict, name: str):
         kw = dict(gap_rate=float(f[3]), iupac_rate=float(f[4])) if len(f) > 3 else {}
         codes = synth.synth_codes(n, L, seed=seed, **kw)
         return synth.seq_ids(n), synth.codes_to_strings(codes)
-    z = np.load(os.path.join(GOLDEN, "msa_%s.npz" % name))
+    z = np.load(os.path.join(GOLDEN, "msa_%s.npz" % case.get("msa", name)))
     packed, L, lens = z["packed"], int(z["n_col"]), z["lens"]
     codes = np.empty((packed.shape[0], packed.shape[1] * 2), dtype=np.uint8)
     codes[:, 0::2] = packed & 15

@@ -81,6 +81,92 @@ def test_two_shards_one_gpu(name):
         assert not bad, (rank, bad[:3])
 
 
+def _shard_rows(name, rank, world, comm, **extra):
+    """design() of one shard of a golden case -> (start, stop, mismatching records)"""
+    import numpy as np
+    from multiprime_b200 import core
+    from tests.helpers import case_alignment
+    from tests.parity import alignment_arrays
+    case = load_case(name)
+    ids, seqs = case_alignment(case, name)
+    n = len(ids)
+    lo, hi = rank * n // world, (rank + 1) * n // world
+    _, codes, lens = alignment_arrays(ids[lo:hi], seqs[lo:hi])
+    full_cols = max(len(s) for s in seqs)
+    if codes.shape[1] < full_cols:
+        codes = np.pad(codes, ((0, 0), (0, full_cols - codes.shape[1])))
+    app = core.NN_degenerate(seq_file=None, nproc=1, outfile="", alignment=(ids[lo:hi], codes, lens), row0=lo,
+                             comm=comm, **extra, **case["params"])
+    recs = case["records"]
+    got = {r["row"][0]: r for r in app.design([r["pos"] for r in recs])}
+    bad = []
+    for rec in recs:
+        g = got.get(rec["pos"])
+        if (g is None) != (rec["row"] is None) or (g is not None and (g["row"] != rec["row"] or g["trace"] != rec["trace"])):
+            bad.append((rec["pos"], g and g["row"], rec["row"]))
+    res = (app.start_position, app.stop_position, bad, sum(1 for r in recs if r["row"] is not None))
+    app.close()
+    return res
+
+
+@pytest.mark.parametrize("name,world", [("synth_iupac", 2), ("c2_k18", 2), ("c3_tmsa", 3)])
+def test_device_collectives_loopback(name, world):
+    """the DEVICE branches of the sharded path on one GPU: shards on threads, collectives on device tensors
+    (export_dev -> all-to-all -> merge from device pointers; in-place all-reduce of the walk's count vector)"""
+    from tests.loopback_comm import run_shards
+    res = run_shards(world, lambda rank, comm: _shard_rows(name, rank, world, comm, device=0))
+    case = load_case(name)
+    for rank, (start, stop, bad, n_acc) in enumerate(res):
+        assert (start, stop) == (case["start"], case["stop"])
+        assert not bad, (rank, bad[:3])
+        assert n_acc > 0
+
+
+def _nccl_worker(rank, world, port, name, q):
+    import torch
+    import torch.distributed as dist
+    from multiprime_b200.comm import TorchComm
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    res = _shard_rows(name, rank, world, TorchComm(torch.device("cuda", rank)), device=rank,
+                      stream=torch.cuda.current_stream().cuda_stream)
+    q.put((rank,) + res)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name", ["synth_iupac", "c2_k18"])
+def test_two_ranks_nccl(name):
+    """the NCCL path bench.py --gpus N runs: two ranks on two GPUs, rows and traces of the golden case"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, name, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = []
+    t0 = time.time()
+    while len(res) < 2 and time.time() - t0 < 300:
+        try:
+            res.append(q.get(timeout=2))
+        except queue.Empty:
+            if any(p.exitcode not in (None, 0) for p in procs):
+                break
+    for p in procs:
+        p.join(10)
+        if p.is_alive():
+            p.kill()
+    assert len(res) == 2, "a rank died: exit codes %s" % [p.exitcode for p in procs]
+    case = load_case(name)
+    for rank, start, stop, bad, n_acc in res:
+        assert (start, stop) == (case["start"], case["stop"])
+        assert not bad, (rank, bad[:3])
+
+
 def test_cli_under_torchrun(tmp_path):
     """`torchrun ... scripts/multiPrime-core.py`: two ranks (sharing cuda:0, gloo) write the reference CLI's files"""
     import json

@@ -8,7 +8,9 @@ import pytest
 from oracle import mp_oracle as o
 from tests.helpers import GOLDEN, case_alignment, digest, load_case, oracle_params
 
-CASES = ["synth300", "synth_iupac", "c2_k18", "c2_k20", "c2_k22", "c3_tmsa", "c1_testfa"]
+CASES = ["synth300", "synth_iupac", "c2_k18", "c2_k20", "c2_k22", "c3_tmsa", "c1_testfa",
+         # every window of the region: 1000_fasta.msa k = 18..22, the whole Cluster_0_20727.tmsa, 10^4 synthetic rows
+         "c2f_k18", "c2f_k19", "c2f_k20", "c2f_k21", "c2f_k22", "c3f_tmsa", "c4_10k"]
 
 
 @pytest.mark.parametrize("name", CASES)
