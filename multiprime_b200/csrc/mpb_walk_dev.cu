@@ -4,8 +4,10 @@
 // sequence (mis_primer_check).  Round 1 drove it from the host: 11 dependent launch -> sync -> D2H -> Python callback
 // round trips per window batch.  Here the tracks (mpb_walk_core.h: seeds, NN arrays, counters) live in HBM and a
 // round is a chain of kernels on one stream:
-//     k_walk_advance   one thread per track: take the previous round's counts, advance (mpb_walk_consume), emit the
-//                      next candidates (mpb_walk_emit) at a slot range claimed with one atomicAdd
+//     k_walk_advance   one thread per track: take the previous round's counts, advance (mpb_walk_consume), stage the
+//                      next candidates (mpb_walk_emit)
+//     k_walk_compact   one block: prefix sum over the tracks -> compact candidate list in track order (deterministic:
+//                      the shards of a sequence-sharded run must agree on it element by element)
 //     k_cscan_plan / k_cscan / k_cscan_special    (mpb_cscan.cu) read the candidate count from device memory
 // The host only enqueues; it learns the number of live tracks from a pinned word written by an asynchronous copy and
 // stops enqueueing when it reads zero (rounds enqueued past the end are no-ops: zero candidates).
@@ -33,10 +35,12 @@ struct mpb_walk_dev {
     int32_t* ntracks;       // [n_win]
     int64_t* cover;         // [n_win]
     uint8_t* trace;         // [2 * n_win][MPB_WALK_MAX_ROUNDS][32]
-    mpb_cand* cands;        // [max_cands]
+    mpb_cand* cands;        // [max_cands] compact candidate list of the current round
+    mpb_cand* stage;        // [2 * n_win][k - 1] per-track staging
+    int32_t* n_emit;        // [2 * n_win]
     uint32_t* plans;        // [max_cands][CSCAN_PLAN_WORDS]
     unsigned long long* counts;  // [max_cands][4]
-    int* n_cand;            // [2]: candidates of the current round, of the next one being emitted
+    int* n_cand;            // candidates of the current round
     int* live_dev;          // [max_rounds + 1] live tracks after each advance
     unsigned long long* totals;  // [2] rounds with candidates, candidates scanned
     int* live_host;         // pinned mirror of live_dev
@@ -55,48 +59,85 @@ __global__ void k_walk_seed(int n_win, int k, const int32_t* __restrict__ win_id
     if (ntracks[w] == 1) tracks[2 * w + 1].state = 2;
 }
 
-// one thread per track slot.  n_cand[0]: candidates of the round whose counts are consumed; n_cand[1]: the round being
-// emitted (zeroed by the host-side memset before this kernel).
+// one thread per track slot: take the counts of the track's candidates of the previous round, advance, and stage the
+// next candidates in the track's own region stage[s * (k - 1) ..] (n_emit[s] of them).
 __global__ void k_walk_advance(int n_win, int k, int dnum, int degeneracy, int round, mpb_track* __restrict__ tracks,
                                const int32_t* __restrict__ ntracks, const int64_t* __restrict__ cover,
-                               const unsigned long long* __restrict__ counts, mpb_cand* __restrict__ cands,
-                               int* __restrict__ n_cand, int max_cands, uint8_t* __restrict__ trace, int* __restrict__ live,
-                               unsigned long long* __restrict__ totals, int* __restrict__ err) {
+                               const unsigned long long* __restrict__ counts, mpb_cand* __restrict__ stage,
+                               int32_t* __restrict__ n_emit, uint8_t* __restrict__ trace, int* __restrict__ err) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    bool alive = false;
-    if (s < 2 * n_win && (s & 1) < ntracks[s >> 1]) {
+    if (s >= 2 * n_win) return;
+    int n = 0;
+    if ((s & 1) < ntracks[s >> 1]) {
         mpb_track& t = tracks[s];
         if (t.state != 2) {
             if (round > 0)
                 mpb_walk_consume(t, k, reinterpret_cast<const int64_t*>(counts) + (long long)t.first_cand * 4, cover[s >> 1],
                                  dnum, degeneracy, trace + (long long)s * MPB_WALK_MAX_ROUNDS * 32);
-            if (t.state != 2) {
-                mpb_cand buf[MPB_MAX_K];
-                const int n = mpb_walk_emit(t, k, buf);
-                const int base = atomicAdd(&n_cand[1], n);
-                if (base + n <= max_cands) {
-                    for (int i = 0; i < n; ++i) cands[base + i] = buf[i];
-                    t.first_cand = base;
-                } else {
-                    t.err |= 4;
-                    t.state = 2;
-                }
-                alive = t.state != 2;
-            }
+            if (t.state != 2) n = mpb_walk_emit(t, k, stage + (long long)s * (k - 1)) | (1 << 30);  // bit 30: still live
             if (t.err) atomicOr(err, t.err);
         }
     }
-    const unsigned b = __ballot_sync(0xffffffffu, alive);
-    if ((threadIdx.x & 31) == 0 && b) atomicAdd(&live[round], __popc(b));
-    if (s == 0 && round > 0 && n_cand[0] > 0) {
-        atomicAdd(&totals[0], 1ull);
-        atomicAdd(&totals[1], (unsigned long long)n_cand[0]);
-    }
+    n_emit[s] = n;
 }
 
-__global__ void k_walk_shift(int* __restrict__ n_cand) {
-    n_cand[0] = n_cand[1];
-    n_cand[1] = 0;
+// ONE block: exclusive prefix sum of n_emit over the track slots -> every track's first candidate, candidates copied to
+// their compact positions.  The slot order is the track order, so the candidate list is identical on every rank of a
+// sequence-sharded run (the count vectors are summed element by element) and from run to run.
+#define COMPACT_THREADS 1024
+__global__ void __launch_bounds__(COMPACT_THREADS)
+k_walk_compact(int n_slots, int k, int round, mpb_track* __restrict__ tracks, const mpb_cand* __restrict__ stage,
+               const int32_t* __restrict__ n_emit, mpb_cand* __restrict__ cands, int* __restrict__ n_cand,
+               int* __restrict__ live, unsigned long long* __restrict__ totals) {
+    __shared__ int s_warp[COMPACT_THREADS / 32];
+    __shared__ int s_live[COMPACT_THREADS / 32];
+    const int per = (n_slots + COMPACT_THREADS - 1) / COMPACT_THREADS;
+    const int lo = threadIdx.x * per, hi = min(n_slots, lo + per);
+    int sum = 0, alive = 0;
+    for (int s = lo; s < hi; ++s) {
+        sum += n_emit[s] & 0xFFFF;
+        alive += n_emit[s] >> 30;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = sum;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const int alive_w = __reduce_add_sync(0xffffffffu, alive);
+    if (lane == 31) s_warp[warp] = incl;
+    if (lane == 0) s_live[warp] = alive_w;
+    __syncthreads();
+    if (warp == 0) {
+        int v = s_warp[lane];
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += u;
+        }
+        s_warp[lane] = v;  // inclusive over warps
+        int l = s_live[lane];
+        l = __reduce_add_sync(0xffffffffu, l);
+        if (lane == 0) s_live[0] = l;
+    }
+    __syncthreads();
+    int base = incl - sum + (warp > 0 ? s_warp[warp - 1] : 0);
+    for (int s = lo; s < hi; ++s) {
+        const int n = n_emit[s] & 0xFFFF;
+        if (n_emit[s] >> 30) {
+            tracks[s].first_cand = base;
+            for (int i = 0; i < n; ++i) cands[base + i] = stage[(long long)s * (k - 1) + i];
+            base += n;
+        }
+    }
+    if (threadIdx.x == 0) {
+        const int total = s_warp[COMPACT_THREADS / 32 - 1];
+        n_cand[0] = total;
+        live[round] = s_live[0];
+        if (total > 0) {
+            totals[0] += 1ull;
+            totals[1] += (unsigned long long)total;
+        }
+    }
 }
 
 extern "C" int mpb_walk_dev_begin(mpb_hist* h, int dnum, int degeneracy, uint32_t fmask, uint32_t rmask, int32_t n_win,
@@ -127,6 +168,8 @@ extern "C" int mpb_walk_dev_begin(mpb_hist* h, int dnum, int degeneracy, uint32_
     if (e == cudaSuccess) e = cudaMallocAsync(&w->cover, (size_t)n_win * 8, ctx->stream);
     if (e == cudaSuccess) e = cudaMallocAsync(&w->trace, (size_t)2 * n_win * MPB_WALK_MAX_ROUNDS * 32, ctx->stream);
     if (e == cudaSuccess) e = cudaMallocAsync(&w->cands, (size_t)w->max_cands * sizeof(mpb_cand), ctx->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&w->stage, (size_t)w->max_cands * sizeof(mpb_cand), ctx->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&w->n_emit, (size_t)2 * n_win * 4, ctx->stream);
     if (e == cudaSuccess) e = cudaMallocAsync(&w->plans, (size_t)w->max_cands * CSCAN_PLAN_WORDS * 4, ctx->stream);
     if (e == cudaSuccess) e = cudaMallocAsync(&w->counts, (size_t)w->max_cands * 4 * 8, ctx->stream);
     if (e == cudaSuccess) e = cudaMallocAsync(&w->n_cand, 8, ctx->stream);
@@ -166,9 +209,9 @@ extern "C" int mpb_walk_dev_advance(mpb_walk_dev* w) {
     CK(cudaSetDevice(ctx->device));
     const int r = w->rounds_enqueued;
     LAUNCH(ctx, k_walk_advance, (unsigned)((2 * w->n_win + 63) / 64), 64, 0, w->n_win, w->k, w->dnum, w->degeneracy, r,
-           w->tracks, w->ntracks, w->cover, w->counts, w->cands, w->n_cand, w->max_cands, w->trace, w->live_dev, w->totals,
-           w->err);
-    LAUNCH(ctx, k_walk_shift, 1, 1, 0, w->n_cand);
+           w->tracks, w->ntracks, w->cover, w->counts, w->stage, w->n_emit, w->trace, w->err);
+    LAUNCH(ctx, k_walk_compact, 1, COMPACT_THREADS, 0, 2 * w->n_win, w->k, r, w->tracks, w->stage, w->n_emit, w->cands,
+           w->n_cand, w->live_dev, w->totals);
     CK(cudaMemcpyAsync(&w->live_host[r], &w->live_dev[r], 4, cudaMemcpyDeviceToHost, ctx->stream));
     w->rounds_enqueued = r + 1;
     return 0;
@@ -263,13 +306,12 @@ extern "C" int mpb_walk_dev_finish(mpb_walk_dev* w, uint8_t* out_sets, int64_t* 
     std::vector<int32_t> ntr(n_win);
     std::vector<uint8_t> trace(trace_sets ? (size_t)2 * n_win * MPB_WALK_MAX_ROUNDS * 32 : 0);
     unsigned long long totals[2] = {0, 0};
-    int err = 0, ncand_now[2] = {0, 0};
+    int err = 0;
     CK(cudaMemcpyAsync(tracks.data(), w->tracks, tracks.size() * sizeof(mpb_track), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(ntr.data(), w->ntracks, (size_t)n_win * 4, cudaMemcpyDeviceToHost, ctx->stream));
     if (trace_sets) CK(cudaMemcpyAsync(trace.data(), w->trace, trace.size(), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(totals, w->totals, 16, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(&err, w->err, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(ncand_now, w->n_cand, 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     if (err & 1) return fail(MPB_EINVAL, "refinement would re-add a base (the reference raises KeyError)");
     if (err & 2) return fail(MPB_EOVERFLOW, "more than %d refinement rounds in one window", MPB_WALK_MAX_ROUNDS);
@@ -316,8 +358,8 @@ extern "C" int mpb_walk_dev_finish(mpb_walk_dev* w, uint8_t* out_sets, int64_t* 
 extern "C" void mpb_walk_dev_free(mpb_walk_dev* w) {
     if (!w) return;
     cudaStream_t st = w->h->msa->ctx->stream;
-    void* ptrs[] = {w->tracks, w->ntracks, w->cover, w->trace, w->cands, w->plans, w->counts, w->n_cand, w->live_dev,
-                    w->totals, w->err};
+    void* ptrs[] = {w->tracks, w->ntracks, w->cover, w->trace, w->cands, w->stage, w->n_emit, w->plans, w->counts,
+                    w->n_cand, w->live_dev, w->totals, w->err};
     for (void* p : ptrs)
         if (p) cudaFreeAsync(p, st);
     if (w->live_host) {
