@@ -53,6 +53,9 @@ int mpb_ctx_set_stream(mpb_ctx* ctx, void* cuda_stream);
 int mpb_ctx_sync(mpb_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py's "gpu_launches") */
 int64_t mpb_ctx_launches(mpb_ctx* ctx);
+/* stream-ordered device memory owned by the caller (results that stay in HBM between calls) */
+int mpb_dev_alloc(mpb_ctx* ctx, int64_t bytes, void** out);
+void mpb_dev_free(mpb_ctx* ctx, void* p);
 /* copy between host / device memory on the context's stream; returns after the copy has completed */
 int mpb_ctx_memcpy(mpb_ctx* ctx, void* dst, const void* src, int64_t bytes);
 

@@ -28,6 +28,8 @@ SIGNATURES = {
     "mpb_ctx_sync": (C.c_int, [_P]),
     "mpb_ctx_launches": (C.c_int64, [_P]),
     "mpb_ctx_memcpy": (C.c_int, [_P, _P, _P, C.c_int64]),
+    "mpb_dev_alloc": (C.c_int, [_P, C.c_int64, C.POINTER(_P)]),
+    "mpb_dev_free": (None, [_P, _P]),
     "mpb_ctx_profile": (C.c_int, [_P, C.c_int]),
     "mpb_ctx_profile_read": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int64),
                                         C.POINTER(C.c_double)]),
@@ -200,6 +202,40 @@ def walk(k, v, dnum, degeneracy, cover_number, freq, nn, mm_key, scan_fn, want_t
         break
     res.update(trace=trace, trace_off=off)
     return res
+
+
+class DevBuf:
+    """caller-owned device memory (mpb_dev_alloc): results that stay in HBM between calls"""
+
+    def __init__(self, ctx: "Context", shape, dtype):
+        self.ctx, self.shape, self.dtype = ctx, tuple(int(x) for x in shape), np.dtype(dtype)
+        self.nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        p = C.c_void_p()
+        check(load().mpb_dev_alloc(ctx.h, self.nbytes, C.byref(p)))
+        self.p = p.value
+
+    def data_ptr(self) -> int:          # ptr() takes anything with data_ptr()
+        return self.p
+
+    def at(self, index: int) -> int:
+        """device address of element [index] along the first axis"""
+        return self.p + index * (self.nbytes // max(1, self.shape[0]))
+
+    def to_host(self) -> np.ndarray:
+        out = np.empty(self.shape, self.dtype)
+        check(load().mpb_ctx_memcpy(self.ctx.h, ptr(out), C.c_void_p(self.p), self.nbytes))
+        return out
+
+    def close(self):
+        if self.p and self.ctx.h:
+            load().mpb_dev_free(self.ctx.h, C.c_void_p(self.p))
+        self.p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Context:
@@ -417,6 +453,8 @@ class Hist:
             nslots = int(bits_slot.max()) + 1 if nc else 0
             if bits is None:
                 bits = np.zeros((max(nslots, 0), 3, (self.msa.n_seq + 31) // 32), np.uint32)
+            elif bits == "device":      # stay in HBM (pair coverage reads them there)
+                bits = DevBuf(self.msa.ctx, (max(nslots, 1), 3, (self.msa.n_seq + 31) // 32), np.uint32)
         if nc:
             check(load().mpb_cscan(self.h, fmask, rmask, ptr(cands), nc, ptr(counts), ptr(bits_slot), ptr(bits)))
         return counts, bits
@@ -555,6 +593,7 @@ class WalkDev:
         check(load().mpb_walk_dev_begin(hist.h, dnum, degeneracy, fmask, rmask, self.n, ptr(win_idx), ptr(cover_number),
                                         ptr(mm_key), ptr(freq), ptr(nn), C.byref(h)))
         self.h = h
+        self._inputs = (win_idx, cover_number, mm_key, freq, nn)     # alive until the walk is done
 
     def __enter__(self):
         return self

@@ -416,6 +416,7 @@ class NN_degenerate(object):
         """Run the per-window algorithm (core:651-858) for the given window start columns.
         Returns a list of records {row, non_cov, gap_ids, trace} (rejected windows are absent)."""
         positions = [int(p) for p in positions]
+        self.bit_vectors = []
         if not positions:
             return []
         per_batch = self.windows_per_batch or _default_batch(self.n_local)
@@ -511,7 +512,9 @@ class NN_degenerate(object):
         self.stats["scan_calls"] += int(res["stats"][0])
         self.stats["candidates"] += int(res["stats"][1])
         self.stats["evals"] += int(res["stats"][2]) * N
-        return self._finish(hist, own, mine, owner, keep, res)
+        out = self._finish(hist, own, mine, owner, keep, res)
+        lap("finish")
+        return out
 
     def _exchange(self, hist, positions, owner):
         """Sequence-sharded run: every per-window quantity is a sum over sequences.  Gap counters are
@@ -670,10 +673,14 @@ class NN_degenerate(object):
         # track IS the final primer); a final scan pass is only needed for the per-sequence non-cover bits
         bits = None
         if self.sidecars or self.keep_bits:
-            _, bits = hist.cscan(self.fmask, self.rmask, _lib.make_cands(wis, allow), bits_slot=np.arange(n, dtype=np.int32))
+            # per-sequence F / R non-cover and gap-row bits of the final primers: to the host for the JSON side files,
+            # left in HBM when only the pairing step (pairing.py) consumes them
+            on_dev = self.keep_bits and not self.sidecars and hasattr(self.ctx, "h")
+            _, bits = hist.cscan(self.fmask, self.rmask, _lib.make_cands(wis, allow), bits_slot=np.arange(n, dtype=np.int32),
+                                 bits_out="device" if on_dev else None)
             self.stats["scan_calls"] += 1
             if self.keep_bits:
-                self.bit_vectors = [(int(p), bits[i]) for i, p in enumerate(pos.tolist())]
+                self.bit_vectors.append((pos.copy(), bits))
         perfect = res["counts"][:, 4]
         lap("fin_scan")
         if self.comm.world == 1:

@@ -79,9 +79,12 @@ extern "C" int mpb_ctx_create(int device, mpb_ctx** out) {
     c->profile = false;
     c->pending_units = 0;
     c->copy_stream = nullptr;
-    if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    c->pinned = nullptr;
+    if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMallocHost(&c->pinned, MPB_CTX_PINNED_INTS * sizeof(int)) != cudaSuccess) {
+        if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
         delete c;
-        return fail(MPB_ECUDA, "copy stream");
+        return fail(MPB_ECUDA, "copy stream / pinned scratch");
     }
     *out = c;
     return 0;
@@ -93,6 +96,7 @@ extern "C" void mpb_ctx_destroy(mpb_ctx* ctx) {
         cudaEventDestroy(r.e1);
     }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
     delete ctx;
 }
 extern "C" int mpb_ctx_set_stream(mpb_ctx* ctx, void* s) {
@@ -106,6 +110,20 @@ extern "C" int mpb_ctx_sync(mpb_ctx* ctx) {
     return 0;
 }
 extern "C" int64_t mpb_ctx_launches(mpb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// stream-ordered device memory for results that stay in HBM between calls (bit vectors of the scan -> pair coverage)
+extern "C" int mpb_dev_alloc(mpb_ctx* ctx, int64_t bytes, void** out) {
+    if (!ctx || !out || bytes < 0) return fail(MPB_EINVAL, "bad argument");
+    CK(cudaSetDevice(ctx->device));
+    void* p = nullptr;
+    cudaError_t e = cudaMallocAsync(&p, bytes > 0 ? (size_t)bytes : 1, ctx->stream);
+    if (e != cudaSuccess) return fail(MPB_ENOMEM, "%lld bytes: %s", (long long)bytes, cudaGetErrorString(e));
+    *out = p;
+    return 0;
+}
+extern "C" void mpb_dev_free(mpb_ctx* ctx, void* p) {
+    if (ctx && p) cudaFreeAsync(p, ctx->stream);
+}
 
 // plain copy between any two of host / device memory on the context's stream, synchronised on return
 extern "C" int mpb_ctx_memcpy(mpb_ctx* ctx, void* dst, const void* src, int64_t bytes) {

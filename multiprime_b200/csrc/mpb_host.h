@@ -27,10 +27,12 @@ struct ProfRec {
     cudaEvent_t e0, e1;
     double units;  // algorithmic work units of this launch (kernel specific; evals for the scan kernels)
 };
+#define MPB_CTX_PINNED_INTS 256
 struct mpb_ctx {
     int device;
     cudaStream_t stream;
     cudaStream_t copy_stream;  // H2D chunks of mpb_msa_upload overlap the plane build on `stream`
+    int* pinned;               // small pinned scratch (MPB_CTX_PINNED_INTS ints): device -> host flags without a sync
     int64_t launches;
     int sm_count;
     bool profile;

@@ -176,11 +176,11 @@ extern "C" int mpb_walk_dev_begin(mpb_hist* h, int dnum, int degeneracy, uint32_
     if (e == cudaSuccess) e = cudaMallocAsync(&w->live_dev, (size_t)(w->max_rounds + 1) * 4, ctx->stream);
     if (e == cudaSuccess) e = cudaMallocAsync(&w->totals, 16, ctx->stream);
     if (e == cudaSuccess) e = cudaMallocAsync(&w->err, 4, ctx->stream);
-    if (e == cudaSuccess) e = cudaMallocHost(&w->live_host, (size_t)(w->max_rounds + 1) * 4);
     if (e != cudaSuccess) {
         mpb_walk_dev_free(w);
         return fail(MPB_ENOMEM, "walk state for %d windows: %s", n_win, cudaGetErrorString(e));
     }
+    w->live_host = ctx->pinned;  // one walk at a time per context
     for (int i = 0; i <= w->max_rounds; ++i) w->live_host[i] = -1;
     CK(cudaMemsetAsync(w->n_cand, 0, 8, ctx->stream));
     CK(cudaMemsetAsync(w->live_dev, 0, (size_t)(w->max_rounds + 1) * 4, ctx->stream));
@@ -197,7 +197,8 @@ extern "C" int mpb_walk_dev_begin(mpb_hist* h, int dnum, int degeneracy, uint32_
     LAUNCH(ctx, k_walk_seed, (unsigned)((n_win + 63) / 64), 64, 0, n_win, k, wi.dev<int32_t>(),
            freq_hd ? fq.dev<unsigned long long>() : h->freq, freq_hd ? nq.dev<unsigned long long>() : h->nn,
            freq_hd ? 0 : 1, mk.dev<uint64_t>(), w->tracks, w->ntracks);
-    CK(cudaStreamSynchronize(ctx->stream));  // host staging buffers (cover, win_idx, mm_key, tensors)
+    // no synchronisation: the inputs are pageable host arrays (staged by the runtime before the copy calls return) or
+    // device memory; the InBuf staging buffers are freed in stream order
     *out = w;
     return 0;
 }
@@ -362,9 +363,5 @@ extern "C" void mpb_walk_dev_free(mpb_walk_dev* w) {
                     w->n_cand, w->live_dev, w->totals, w->err};
     for (void* p : ptrs)
         if (p) cudaFreeAsync(p, st);
-    if (w->live_host) {
-        cudaStreamSynchronize(st);  // pending async copies into the pinned mirror
-        cudaFreeHost(w->live_host);
-    }
     delete w;
 }
