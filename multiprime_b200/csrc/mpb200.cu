@@ -461,195 +461,52 @@ extern "C" int mpb_seq_attr(mpb_msa* m, int32_t* lead_hd, int32_t* rstrip_hd) {
 }
 
 // ------------------------------------------------------------------------------------------------------
-// window haplotype tables
+// window passes: every (window, sequence) k-mer of a window batch, once for the entropy prefilter (all windows) and once
+// for the haplotype tables (the windows that survive it)
 // ------------------------------------------------------------------------------------------------------
+// Both kernels stream without block barriers.  Block (x, y) owns WIN_TILES x 256 sequences and walks the windows
+// y, y + gridDim.y, ...; a warp owns 32 sequences per tile.  In a window below the entropy gate most sequences carry
+// the SAME k-mer, so each warp keeps that majority k-mer and its count in registers for the whole window (one global
+// atomic per warp and window) and sends only the minority rows to global memory one by one; a variable window
+// degenerates to one atomic per row, which is what it costs anyway.  (Round 1 staged every row in a block-private
+// hash table: three block barriers per window, 150 instructions per tile in the probing loops of the variable
+// windows; ncu: 35-41 % of the stall samples at the barriers, 18 active threads per instruction.)
+// Rows that need more than the funnel shift — the window starts / ends inside a gap run (patched with flank bases,
+// core:671-682), holds IUPAC cells, runs past a ragged row end, or (tables only) holds a gap and therefore needs the
+// base-5 key — are recorded in a block-private list and handled densely, one per thread, after the window loop.
 #define HIST_THREADS 256
+#define WIN_TILES 16
+#define WIN_ROWS (HIST_THREADS * WIN_TILES)
+#define DEFER_CAP 12000  // deferred (window slot, row) pairs per block; beyond it rows are handled where they stand
 
-// Block-private staging table: the haplotypes of HIST_TILES x 256 sequences of one window are first counted in
-// shared memory (a hot haplotype then costs ONE global atomic per block instead of one per warp: same-address L2
-// atomics were the bound of the first version), then flushed to the window's global table.
-#define HIST_TILES 4
-#define HIST_SLOTS 512  // power of two
-#define HIST_PROBES 8
-#define HIST_SPECIAL_CAP 256  // deferred rows per (block, window)
-
-__device__ __forceinline__ void hist_stage(unsigned long long* s_key, unsigned int* s_cnt, unsigned long long* s_first,
-                                           uint64_t* K, uint32_t* C, uint64_t* F, int log2cap, uint64_t key,
-                                           uint32_t add, uint64_t ord, int* err, unsigned long long* n_new,
-                                           uint32_t* E) {
-    uint32_t h = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 55) & (HIST_SLOTS - 1);
-    for (int probe = 0; probe < HIST_PROBES; ++probe) {
-        unsigned long long cur = s_key[h];
-        if (cur == MPB_KEY_EMPTY_D) {
-            cur = atomicCAS(&s_key[h], (unsigned long long)MPB_KEY_EMPTY_D, (unsigned long long)key);
-            if (cur == MPB_KEY_EMPTY_D) cur = key;
-        }
-        if (cur == key) {
-            atomicAdd(&s_cnt[h], add);
-            atomicMin(&s_first[h], (unsigned long long)ord);
-            return;
-        }
-        h = (h + 1) & (HIST_SLOTS - 1);
-    }
-    mpb_table_add(K, C, F, log2cap, key, add, ord, err, n_new, E);  // staging table crowded (variable window): go global
+// window words of one row: funnel shift of the two column words
+struct RawWin {
+    uint32_t a, c, g, t, gapv;
+    bool special;  // needs patching / expansion / ragged handling
+};
+__device__ __forceinline__ RawWin win_raw(const uint4* __restrict__ wbase, int64_t nsp, int64_t s, int sh, uint32_t kmask,
+                                          int p, int k, int len) {
+    const uint4 q0 = __ldg(wbase + s), q1 = __ldg(wbase + nsp + s);
+    RawWin r;
+    r.a = __funnelshift_r(q0.x, q1.x, sh) & kmask;
+    r.c = __funnelshift_r(q0.y, q1.y, sh) & kmask;
+    r.g = __funnelshift_r(q0.z, q1.z, sh) & kmask;
+    r.t = __funnelshift_r(q0.w, q1.w, sh) & kmask;
+    r.gapv = ~(r.a | r.c | r.g | r.t) & kmask;
+    r.special = (p + k > len) || ((((r.gapv & 1u) | ((r.gapv >> (k - 1)) & 1u)) != 0u) && r.gapv != kmask) ||
+                mpb_multi(r.a, r.c, r.g, r.t) != 0u;
+    return r;
 }
 
-// block (x, y): sequence tiles [x*HIST_TILES, (x+1)*HIST_TILES) ; blockIdx.y strides over the windows of the batch
-__global__ void __launch_bounds__(HIST_THREADS)
-k_hist(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq, const int32_t* __restrict__ lens, int k, int v,
-       const int32_t* __restrict__ win_pos, int nw, uint64_t* __restrict__ keys, uint32_t* __restrict__ cnt,
-       uint64_t* __restrict__ first, int log2cap, unsigned long long* __restrict__ gap_n,
-       unsigned long long* __restrict__ iupac_gap_n, int32_t* __restrict__ exc, unsigned long long* __restrict__ exc_n,
-       long long exc_max, long long row0, unsigned long long* __restrict__ n_entries, uint32_t* __restrict__ elist,
-       uint32_t* __restrict__ spec_bits, uint32_t* __restrict__ gap_bits, long long nwords, uint4* __restrict__ spec_win,
-       int32_t* __restrict__ spec_row, unsigned long long* __restrict__ spec_n, long long spec_cap,
-       int* __restrict__ err) {
-    __shared__ unsigned long long s_key[HIST_SLOTS];
-    __shared__ unsigned long long s_first[HIST_SLOTS];
-    __shared__ unsigned int s_cnt[HIST_SLOTS];
-    __shared__ unsigned int s_gap;
-    __shared__ unsigned int s_nspecial;
-    __shared__ unsigned int s_special[HIST_SPECIAL_CAP];
-    const int lane = threadIdx.x & 31;
-    const uint32_t kmask = (1u << k) - 1u;
-    const uint64_t cap = 1ull << log2cap;
-    for (int i = threadIdx.x; i < HIST_SLOTS; i += HIST_THREADS) {
-        s_key[i] = MPB_KEY_EMPTY_D;
-        s_first[i] = ~0ull;
-        s_cnt[i] = 0;
-    }
-    if (threadIdx.x == 0) {
-        s_gap = 0;
-        s_nspecial = 0;
-    }
-    __syncthreads();
-    for (int wi = blockIdx.y; wi < nw; wi += gridDim.y) {
-        const int p = win_pos[wi];
-        uint64_t* K = keys + (uint64_t)wi * cap;
-        uint32_t* C = cnt + (uint64_t)wi * cap;
-        uint64_t* F = first + (uint64_t)wi * cap;
-        uint32_t* E = elist + (uint64_t)wi * cap;
-        const uint4* __restrict__ wbase = reinterpret_cast<const uint4*>(pl) + (int64_t)(p >> 5) * nsp;
-        const int sh = p & 31;
-        // pass 1: plain rows (funnel shift only); rows needing gap patching / IUPAC expansion / ragged handling are
-        // recorded and handled densely in pass 2 (they left most of a warp idle when handled inline)
-        for (int t = 0; t < HIST_TILES; ++t) {
-            const int64_t tile = (int64_t)blockIdx.x * HIST_TILES + t;
-            if (tile * HIST_THREADS >= n_seq) break;  // uniform
-            const int64_t s = tile * HIST_THREADS + threadIdx.x;
-            const bool valid = s < n_seq;
-            bool plain = false, isgap = false;
-            uint64_t key = 0;
-            if (valid) {
-                const uint4 q0 = __ldg(wbase + s), q1 = __ldg(wbase + nsp + s);
-                const uint32_t a = __funnelshift_r(q0.x, q1.x, sh) & kmask, c = __funnelshift_r(q0.y, q1.y, sh) & kmask,
-                               g = __funnelshift_r(q0.z, q1.z, sh) & kmask, tt = __funnelshift_r(q0.w, q1.w, sh) & kmask;
-                const uint32_t gapv = ~(a | c | g | tt) & kmask;
-                const bool special = (p + k > lens[s]) || ((((gapv & 1u) | ((gapv >> (k - 1)) & 1u)) != 0u) && gapv != kmask) ||
-                                     mpb_multi(a, c, g, tt) != 0u;
-                if (special) {
-                    const unsigned slot = atomicAdd(&s_nspecial, 1u);
-                    if (slot < HIST_SPECIAL_CAP) s_special[slot] = (unsigned)(t * HIST_THREADS + threadIdx.x);
-                } else {
-                    plain = true;
-                    isgap = __popc(gapv) > v;
-                    key = mpb_key(c, g, tt, gapv, k);
-                }
-            }
-            const unsigned gb = __ballot_sync(0xffffffffu, plain && isgap);
-            if (lane == 0 && gb) atomicAdd(&s_gap, (unsigned)__popc(gb));
-            const unsigned smask = __ballot_sync(0xffffffffu, plain);
-            {   // row classes of this 32-sequence word for the column scan (padding rows count as special)
-                const long long word = tile * (HIST_THREADS / 32) + (threadIdx.x >> 5);
-                if (lane == 0 && word < nwords) {
-                    spec_bits[(long long)wi * nwords + word] = ~smask;
-                    gap_bits[(long long)wi * nwords + word] = gb;
-                }
-            }
-            if (plain) {
-                const unsigned peers = __match_any_sync(smask, key);
-                if (lane == __ffs(peers) - 1)  // lowest lane = lowest sequence index = first seen
-                    hist_stage(s_key, s_cnt, s_first, K, C, F, log2cap, key, (uint32_t)__popc(peers),
-                               (uint64_t)(row0 + s) << 16, err, &n_entries[wi], E);
-            }
-        }
-        __syncthreads();
-        // pass 2: the special rows of this window, one per thread (list overflow: every thread re-checks its rows)
-        {
-            const unsigned nsp_rows = s_nspecial;
-            const bool overflow = nsp_rows > HIST_SPECIAL_CAP;
-            const unsigned n_items = overflow ? (unsigned)(HIST_TILES * HIST_THREADS) : nsp_rows;
-            for (unsigned i = threadIdx.x; i < n_items; i += HIST_THREADS) {
-                const unsigned local = overflow ? i : s_special[i];
-                const int64_t s = (int64_t)blockIdx.x * HIST_TILES * HIST_THREADS + local;
-                if (s >= n_seq) continue;
-                const uint64_t gs = (uint64_t)(row0 + s);
-                Win w;
-                if (overflow) {  // only the rows pass 1 skipped
-                    const uint4 q0 = __ldg(wbase + s), q1 = __ldg(wbase + nsp + s);
-                    const uint32_t a = __funnelshift_r(q0.x, q1.x, sh) & kmask, c = __funnelshift_r(q0.y, q1.y, sh) & kmask,
-                                   g = __funnelshift_r(q0.z, q1.z, sh) & kmask, tt = __funnelshift_r(q0.w, q1.w, sh) & kmask;
-                    const uint32_t gapv = ~(a | c | g | tt) & kmask;
-                    const bool special = (p + k > lens[s]) ||
-                                         ((((gapv & 1u) | ((gapv >> (k - 1)) & 1u)) != 0u) && gapv != kmask) ||
-                                         mpb_multi(a, c, g, tt) != 0u;
-                    if (!special) continue;
-                }
-                if (!mpb_load_window(pl, nsp, s, lens[s], p, k, kmask, w)) atomicOr(err, MPB_ERR_SHORT_ROW);
-                const bool isgap = __popc(w.gapv) > v;
-                if (isgap) {
-                    atomicAdd(&s_gap, 1u);
-                    atomicOr(&gap_bits[(long long)wi * nwords + (s >> 5)], 1u << (s & 31));
-                } else {  // the patched window itself, for the column scan's special pass
-                    const unsigned long long slot = atomicAdd(&spec_n[wi], 1ull);
-                    if ((long long)slot < spec_cap) {
-                        spec_win[(long long)wi * spec_cap + slot] = make_uint4(w.a, w.c, w.g, w.t);
-                        spec_row[(long long)wi * spec_cap + slot] = (int32_t)s;
-                    }
-                }
-                if (!isgap && w.multi == 0) {
-                    hist_stage(s_key, s_cnt, s_first, K, C, F, log2cap, mpb_key(w.c, w.g, w.t, w.gapv, k), 1u, gs << 16, err, &n_entries[wi], E);
-                } else if (!isgap) {
-                    const uint32_t total = mpb_expansions(w);
-                    if (total > MPB_MAX_EXP) {
-                        atomicOr(err, MPB_ERR_EXPAND);
-                    } else {
-                        for (uint32_t e = 0; e < total; ++e) {
-                            uint32_t a, c, g, tt;
-                            mpb_expand(w, e, a, c, g, tt);
-                            hist_stage(s_key, s_cnt, s_first, K, C, F, log2cap, mpb_key(c, g, tt, w.gapv, k), 1u,
-                                       (gs << 16) | e, err, &n_entries[wi], E);
-                        }
-                    }
-                } else if (w.multi == 0) {
-                    hist_stage(s_key, s_cnt, s_first, K, C, F, log2cap, mpb_key(w.c, w.g, w.t, w.gapv, k), 1u, gs << 16, err, &n_entries[wi], E);
-                } else {
-                    atomicAdd(&iupac_gap_n[wi], 1ull);
-                    unsigned long long slot = atomicAdd(exc_n, 1ull);
-                    if ((long long)slot < exc_max) {
-                        exc[2 * slot] = wi;
-                        exc[2 * slot + 1] = (int32_t)s;
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        for (int i = threadIdx.x; i < HIST_SLOTS; i += HIST_THREADS) {  // flush + clear the staging table
-            const unsigned long long key = s_key[i];
-            if (key != MPB_KEY_EMPTY_D) {
-                mpb_table_add(K, C, F, log2cap, key, s_cnt[i], s_first[i], err, &n_entries[wi], E);
-                s_key[i] = MPB_KEY_EMPTY_D;
-                s_first[i] = ~0ull;
-                s_cnt[i] = 0;
-            }
-        }
-        if (threadIdx.x == 0) {
-            if (s_gap) atomicAdd(&gap_n[wi], (unsigned long long)s_gap);
-            s_gap = 0;
-            s_nspecial = 0;
-        }
-        __syncthreads();
-    }
+// the code / key most lanes of the warp share (first-tile vote)
+template <class T>
+__device__ __forceinline__ T warp_majority(unsigned mask, bool mine, T val) {
+    unsigned peers = 0;
+    if (mine) peers = __match_any_sync(mask, val);
+    const unsigned cnt = __popc(peers);
+    const unsigned mx = __reduce_max_sync(0xffffffffu, cnt);
+    const int leader = __ffs(__ballot_sync(0xffffffffu, cnt == mx && mine)) - 1;
+    return __shfl_sync(0xffffffffu, val, leader);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -668,27 +525,8 @@ __device__ __forceinline__ uint32_t pre_code(uint32_t c, uint32_t g, uint32_t t)
     return ((lo ^ (hi << 7) ^ (hi >> 9)) * 0x9E3779B1u) >> 16;
 }
 
-__device__ __forceinline__ void pre_stage(unsigned long long* s_key, unsigned int* s_cnt, unsigned int* bins,
-                                          uint32_t code, uint32_t add) {
-    uint32_t h = (code * 0x9E3779B1u) >> 23;  // 9 bits
-    for (int probe = 0; probe < HIST_PROBES; ++probe) {
-        unsigned long long cur = s_key[h];
-        if (cur == MPB_KEY_EMPTY_D) {
-            cur = atomicCAS(&s_key[h], (unsigned long long)MPB_KEY_EMPTY_D, (unsigned long long)code);
-            if (cur == MPB_KEY_EMPTY_D) cur = code;
-        }
-        if (cur == code) {
-            atomicAdd(&s_cnt[h], add);
-            return;
-        }
-        h = (h + 1) & (HIST_SLOTS - 1);
-    }
-    atomicAdd(&bins[code], add);
-}
-
-// one item of the prefilter: a cover row expansion or a gap row, already loaded
-__device__ __forceinline__ void pre_row(const Win& w, int v, unsigned long long* s_key, unsigned int* s_cnt,
-                                        unsigned int* B, int* err) {
+// one deferred row of the prefilter: a cover row expansion or a gap row, patched window already loaded
+__device__ __forceinline__ void pre_row(const Win& w, int v, unsigned int* B, int* err) {
     const bool isgap = __popc(w.gapv) > v;
     if (w.multi == 0 || isgap) {
         uint32_t c = w.c, g = w.g, tt = w.t;
@@ -698,7 +536,7 @@ __device__ __forceinline__ void pre_row(const Win& w, int v, unsigned long long*
             g &= ~(a | c);
             tt &= ~(a | c | g);
         }
-        pre_stage(s_key, s_cnt, B, pre_code(c, g, tt), 1u);
+        atomicAdd(&B[pre_code(c, g, tt)], 1u);
     } else {
         const uint32_t total = mpb_expansions(w);
         if (total > MPB_MAX_EXP) {
@@ -707,7 +545,7 @@ __device__ __forceinline__ void pre_row(const Win& w, int v, unsigned long long*
             for (uint32_t e = 0; e < total; ++e) {
                 uint32_t a, c, g, tt;
                 mpb_expand(w, e, a, c, g, tt);
-                pre_stage(s_key, s_cnt, B, pre_code(c, g, tt), 1u);
+                atomicAdd(&B[pre_code(c, g, tt)], 1u);
             }
         }
     }
@@ -716,84 +554,215 @@ __device__ __forceinline__ void pre_row(const Win& w, int v, unsigned long long*
 __global__ void __launch_bounds__(HIST_THREADS)
 k_prefilter(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq, const int32_t* __restrict__ lens, int k, int v,
             const int32_t* __restrict__ win_pos, int nw, unsigned int* __restrict__ bins, int* __restrict__ err) {
-    __shared__ unsigned long long s_key[HIST_SLOTS];
-    __shared__ unsigned int s_cnt[HIST_SLOTS];
-    __shared__ unsigned int s_nspecial;
-    __shared__ unsigned int s_special[HIST_SPECIAL_CAP];
+    __shared__ unsigned int s_defer[DEFER_CAP];
+    __shared__ unsigned int s_ndefer;
     const uint32_t kmask = (1u << k) - 1u;
-    for (int i = threadIdx.x; i < HIST_SLOTS; i += HIST_THREADS) {
-        s_key[i] = MPB_KEY_EMPTY_D;
-        s_cnt[i] = 0;
-    }
-    if (threadIdx.x == 0) s_nspecial = 0;
+    const int lane = threadIdx.x & 31;
+    const int64_t row_base = (int64_t)blockIdx.x * WIN_ROWS;
+    if (threadIdx.x == 0) s_ndefer = 0;
     __syncthreads();
-    for (int wi = blockIdx.y; wi < nw; wi += gridDim.y) {
+    int slot = 0;
+    for (int wi = blockIdx.y; wi < nw; wi += gridDim.y, ++slot) {
         const int p = win_pos[wi];
         unsigned int* B = bins + (long long)wi * PRE_BINS;
         const uint4* __restrict__ wbase = reinterpret_cast<const uint4*>(pl) + (int64_t)(p >> 5) * nsp;
         const int sh = p & 31;
-        for (int t = 0; t < HIST_TILES; ++t) {  // pass 1: plain rows; the others are recorded for pass 2
-            const int64_t tile = (int64_t)blockIdx.x * HIST_TILES + t;
-            if (tile * HIST_THREADS >= n_seq) break;  // uniform
-            const int64_t s = tile * HIST_THREADS + threadIdx.x;
+        uint32_t major = 0;
+        unsigned count = 0;
+        bool have = false;
+#pragma unroll 4
+        for (int t = 0; t < WIN_TILES; ++t) {
+            const int64_t tile0 = row_base + t * HIST_THREADS;
+            if (tile0 >= n_seq) break;  // uniform
+            const int64_t s = tile0 + threadIdx.x;
             bool plain = false;
             uint32_t code = 0;
             if (s < n_seq) {
-                const uint4 q0 = __ldg(wbase + s), q1 = __ldg(wbase + nsp + s);
-                const uint32_t a = __funnelshift_r(q0.x, q1.x, sh) & kmask, c = __funnelshift_r(q0.y, q1.y, sh) & kmask,
-                               g = __funnelshift_r(q0.z, q1.z, sh) & kmask, tt = __funnelshift_r(q0.w, q1.w, sh) & kmask;
-                const uint32_t gapv = ~(a | c | g | tt) & kmask;
-                const bool special = (p + k > lens[s]) || ((((gapv & 1u) | ((gapv >> (k - 1)) & 1u)) != 0u) && gapv != kmask) ||
-                                     mpb_multi(a, c, g, tt) != 0u;
-                if (special) {
-                    const unsigned slot = atomicAdd(&s_nspecial, 1u);
-                    if (slot < HIST_SPECIAL_CAP) s_special[slot] = (unsigned)(t * HIST_THREADS + threadIdx.x);
+                const int len = __ldg(lens + s);
+                const RawWin r = win_raw(wbase, nsp, s, sh, kmask, p, k, len);
+                if (r.special) {
+                    const unsigned idx = atomicAdd(&s_ndefer, 1u);
+                    if (idx < DEFER_CAP) {
+                        s_defer[idx] = ((unsigned)slot << 12) | (unsigned)(t * HIST_THREADS + threadIdx.x);
+                    } else {  // list full: handle the row here
+                        Win w;
+                        if (!mpb_load_window(pl, nsp, s, len, p, k, kmask, w)) atomicOr(err, MPB_ERR_SHORT_ROW);
+                        pre_row(w, v, B, err);
+                    }
                 } else {
                     plain = true;
-                    code = pre_code(c, g, tt);
+                    code = pre_code(r.c, r.g, r.t);
                 }
             }
-            const unsigned smask = __ballot_sync(0xffffffffu, plain);
-            if (plain) {
-                const unsigned peers = __match_any_sync(smask, code);
-                if ((threadIdx.x & 31) == __ffs(peers) - 1) pre_stage(s_key, s_cnt, B, code, (uint32_t)__popc(peers));
+            const unsigned pm = __ballot_sync(0xffffffffu, plain);
+            if (!have && pm) {
+                major = warp_majority<uint32_t>(pm, plain, code);
+                have = true;
+            }
+            const unsigned eq = __ballot_sync(0xffffffffu, plain && code == major);
+            count += __popc(eq);
+            if (plain && code != major) atomicAdd(&B[code], 1u);
+        }
+        if (lane == 0 && count) atomicAdd(&B[major], count);
+    }
+    __syncthreads();
+    const unsigned nd = s_ndefer < DEFER_CAP ? s_ndefer : DEFER_CAP;
+    for (unsigned i = threadIdx.x; i < nd; i += HIST_THREADS) {
+        const unsigned e = s_defer[i];
+        const int wi = blockIdx.y + (int)(e >> 12) * gridDim.y;
+        const int64_t s = row_base + (e & 0xFFFu);
+        Win w;
+        if (!mpb_load_window(pl, nsp, s, lens[s], win_pos[wi], k, kmask, w)) atomicOr(err, MPB_ERR_SHORT_ROW);
+        pre_row(w, v, bins + (long long)wi * PRE_BINS, err);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// window haplotype tables (core:651-711) + the row classes and patched windows the column scan needs
+// ------------------------------------------------------------------------------------------------------
+// one deferred row of the table build: patching, gap test, IUPAC expansion in product order, exceptions
+__device__ __forceinline__ void hist_row(const uint32_t* __restrict__ pl, int64_t nsp, int64_t s, int len, int p, int k,
+                                         int v, uint32_t kmask, long long row0, int wi, uint64_t* K, uint32_t* C,
+                                         uint64_t* F, uint32_t* E, int log2cap, unsigned long long* __restrict__ gap_n,
+                                         unsigned long long* __restrict__ iupac_gap_n, int32_t* __restrict__ exc,
+                                         unsigned long long* __restrict__ exc_n, long long exc_max,
+                                         unsigned long long* __restrict__ n_entries, uint32_t* __restrict__ gap_bits,
+                                         long long nwords, uint4* __restrict__ spec_win, int32_t* __restrict__ spec_row,
+                                         unsigned long long* __restrict__ spec_n, long long spec_cap, bool is_special,
+                                         int* __restrict__ err) {
+    const uint64_t gs = (uint64_t)(row0 + s);
+    Win w;
+    if (!mpb_load_window(pl, nsp, s, len, p, k, kmask, w)) atomicOr(err, MPB_ERR_SHORT_ROW);
+    const bool isgap = __popc(w.gapv) > v;
+    if (is_special) {  // plain rows were classified (gap bit, gap count) where they stand
+        if (isgap) {
+            atomicAdd(&gap_n[wi], 1ull);
+            atomicOr(&gap_bits[(long long)wi * nwords + (s >> 5)], 1u << (s & 31));
+        } else {  // the patched window itself, for the column scan's special pass
+            const unsigned long long slot = atomicAdd(&spec_n[wi], 1ull);
+            if ((long long)slot < spec_cap) {
+                spec_win[(long long)wi * spec_cap + slot] = make_uint4(w.a, w.c, w.g, w.t);
+                spec_row[(long long)wi * spec_cap + slot] = (int32_t)s;
             }
         }
-        __syncthreads();
-        {
-            const unsigned nrec = s_nspecial;
-            const bool overflow = nrec > HIST_SPECIAL_CAP;
-            const unsigned n_items = overflow ? (unsigned)(HIST_TILES * HIST_THREADS) : nrec;
-            for (unsigned i = threadIdx.x; i < n_items; i += HIST_THREADS) {
-                const unsigned local = overflow ? i : s_special[i];
-                const int64_t s = (int64_t)blockIdx.x * HIST_TILES * HIST_THREADS + local;
-                if (s >= n_seq) continue;
-                if (overflow) {
-                    const uint4 q0 = __ldg(wbase + s), q1 = __ldg(wbase + nsp + s);
-                    const uint32_t a = __funnelshift_r(q0.x, q1.x, sh) & kmask, c = __funnelshift_r(q0.y, q1.y, sh) & kmask,
-                                   g = __funnelshift_r(q0.z, q1.z, sh) & kmask, tt = __funnelshift_r(q0.w, q1.w, sh) & kmask;
-                    const uint32_t gapv = ~(a | c | g | tt) & kmask;
-                    const bool special = (p + k > lens[s]) ||
-                                         ((((gapv & 1u) | ((gapv >> (k - 1)) & 1u)) != 0u) && gapv != kmask) ||
-                                         mpb_multi(a, c, g, tt) != 0u;
-                    if (!special) continue;
+    }
+    if (w.multi == 0) {
+        mpb_table_add(K, C, F, log2cap, mpb_key(w.c, w.g, w.t, w.gapv, k), 1u, gs << 16, err, &n_entries[wi], E);
+    } else if (!isgap) {
+        const uint32_t total = mpb_expansions(w);
+        if (total > MPB_MAX_EXP) {
+            atomicOr(err, MPB_ERR_EXPAND);
+        } else {
+            for (uint32_t e = 0; e < total; ++e) {
+                uint32_t a, c, g, tt;
+                mpb_expand(w, e, a, c, g, tt);
+                mpb_table_add(K, C, F, log2cap, mpb_key(c, g, tt, w.gapv, k), 1u, (gs << 16) | e, err, &n_entries[wi], E);
+            }
+        }
+    } else {  // gap row holding IUPAC cells: not table material (its raw k-mer needs 4 bits per cell)
+        atomicAdd(&iupac_gap_n[wi], 1ull);
+        const unsigned long long slot = atomicAdd(exc_n, 1ull);
+        if ((long long)slot < exc_max) {
+            exc[2 * slot] = wi;
+            exc[2 * slot + 1] = (int32_t)s;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(HIST_THREADS)
+k_hist(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq, const int32_t* __restrict__ lens, int k, int v,
+       const int32_t* __restrict__ win_pos, int nw, uint64_t* __restrict__ keys, uint32_t* __restrict__ cnt,
+       uint64_t* __restrict__ first, int log2cap, unsigned long long* __restrict__ gap_n,
+       unsigned long long* __restrict__ iupac_gap_n, int32_t* __restrict__ exc, unsigned long long* __restrict__ exc_n,
+       long long exc_max, long long row0, unsigned long long* __restrict__ n_entries, uint32_t* __restrict__ elist,
+       uint32_t* __restrict__ spec_bits, uint32_t* __restrict__ gap_bits, long long nwords, uint4* __restrict__ spec_win,
+       int32_t* __restrict__ spec_row, unsigned long long* __restrict__ spec_n, long long spec_cap,
+       int* __restrict__ err) {
+    __shared__ unsigned int s_defer[DEFER_CAP];
+    __shared__ unsigned int s_ndefer;
+    const uint32_t kmask = (1u << k) - 1u;
+    const uint64_t cap = 1ull << log2cap;
+    const int lane = threadIdx.x & 31;
+    const int64_t row_base = (int64_t)blockIdx.x * WIN_ROWS;
+    if (threadIdx.x == 0) s_ndefer = 0;
+    __syncthreads();
+    int slot = 0;
+    for (int wi = blockIdx.y; wi < nw; wi += gridDim.y, ++slot) {
+        const int p = win_pos[wi];
+        uint64_t* K = keys + (uint64_t)wi * cap;
+        uint32_t* C = cnt + (uint64_t)wi * cap;
+        uint64_t* F = first + (uint64_t)wi * cap;
+        uint32_t* E = elist + (uint64_t)wi * cap;
+        const uint4* __restrict__ wbase = reinterpret_cast<const uint4*>(pl) + (int64_t)(p >> 5) * nsp;
+        const int sh = p & 31;
+        uint64_t major = 0, major_first = 0;
+        unsigned count = 0, gaps = 0;
+        bool have = false;
+#pragma unroll 2
+        for (int t = 0; t < WIN_TILES; ++t) {
+            const int64_t tile0 = row_base + t * HIST_THREADS;
+            if (tile0 >= n_seq) break;  // uniform
+            const int64_t s = tile0 + threadIdx.x;
+            bool plain = false, simple = false, isgap = false, late = false, late_special = false;
+            uint64_t key = 0;
+            int len = 0;
+            if (s < n_seq) {
+                len = __ldg(lens + s);
+                const RawWin r = win_raw(wbase, nsp, s, sh, kmask, p, k, len);
+                plain = !r.special;
+                isgap = plain && __popc(r.gapv) > v;
+                simple = plain && r.gapv == 0u;     // gap-free: the 2-bit key; rows holding gaps need the base-5 key
+                if (simple) {
+                    key = (uint64_t)(r.c | r.t) | ((uint64_t)(r.g | r.t) << k);
+                } else {
+                    const unsigned idx = atomicAdd(&s_ndefer, 1u);
+                    if (idx < DEFER_CAP) {
+                        s_defer[idx] = ((unsigned)slot << 13) | (r.special ? 0x1000u : 0u) | (unsigned)(t * HIST_THREADS + threadIdx.x);
+                    } else {  // list full: handle the row in this iteration, after the class words are stored
+                        late = true;
+                        late_special = r.special;
+                    }
                 }
-                Win w;
-                if (!mpb_load_window(pl, nsp, s, lens[s], p, k, kmask, w)) atomicOr(err, MPB_ERR_SHORT_ROW);
-                pre_row(w, v, s_key, s_cnt, B, err);
+            }
+            const unsigned pm = __ballot_sync(0xffffffffu, plain);
+            const unsigned gb = __ballot_sync(0xffffffffu, plain && isgap);
+            gaps += __popc(gb);
+            {   // row classes of this 32-sequence word for the column scan (padding rows count as special)
+                const long long word = tile0 / 32 + (threadIdx.x >> 5);
+                if (lane == 0 && word < nwords) {
+                    spec_bits[(long long)wi * nwords + word] = ~pm;
+                    gap_bits[(long long)wi * nwords + word] = gb;
+                }
+            }
+            __syncwarp();  // the class words are in place before a late row ORs its gap bit in
+            const unsigned sm = __ballot_sync(0xffffffffu, simple);
+            if (!have && sm) {
+                major = warp_majority<unsigned long long>(sm, simple, key);
+                have = true;
+            }
+            const unsigned eq = __ballot_sync(0xffffffffu, simple && key == major);
+            if (count == 0 && eq) major_first = (uint64_t)(row0 + tile0 + (threadIdx.x & ~31) + (__ffs(eq) - 1)) << 16;
+            count += __popc(eq);
+            if (simple && key != major) mpb_table_add(K, C, F, log2cap, key, 1u, (uint64_t)(row0 + s) << 16, err, &n_entries[wi], E);
+            if (late) {
+                hist_row(pl, nsp, s, len, p, k, v, kmask, row0, wi, K, C, F, E, log2cap, gap_n, iupac_gap_n, exc, exc_n,
+                         exc_max, n_entries, gap_bits, nwords, spec_win, spec_row, spec_n, spec_cap, late_special, err);
             }
         }
-        __syncthreads();
-        for (int i = threadIdx.x; i < HIST_SLOTS; i += HIST_THREADS) {
-            const unsigned long long key = s_key[i];
-            if (key != MPB_KEY_EMPTY_D) {
-                atomicAdd(&B[(uint32_t)key], s_cnt[i]);
-                s_key[i] = MPB_KEY_EMPTY_D;
-                s_cnt[i] = 0;
-            }
+        if (lane == 0) {
+            if (count) mpb_table_add(K, C, F, log2cap, major, count, major_first, err, &n_entries[wi], E);
+            if (gaps) atomicAdd(&gap_n[wi], (unsigned long long)gaps);
         }
-        if (threadIdx.x == 0) s_nspecial = 0;
-        __syncthreads();
+    }
+    __syncthreads();
+    const unsigned nd = s_ndefer < DEFER_CAP ? s_ndefer : DEFER_CAP;
+    for (unsigned i = threadIdx.x; i < nd; i += HIST_THREADS) {
+        const unsigned e = s_defer[i];
+        const int wi = blockIdx.y + (int)(e >> 13) * gridDim.y;
+        const int64_t s = row_base + (e & 0xFFFu);
+        hist_row(pl, nsp, s, lens[s], win_pos[wi], k, v, kmask, row0, wi, keys + (uint64_t)wi * cap, cnt + (uint64_t)wi * cap,
+                 first + (uint64_t)wi * cap, elist + (uint64_t)wi * cap, log2cap, gap_n, iupac_gap_n, exc, exc_n, exc_max,
+                 n_entries, gap_bits, nwords, spec_win, spec_row, spec_n, spec_cap, (e & 0x1000u) != 0u, err);
     }
 }
 
@@ -829,6 +798,29 @@ k_prefilter_sums(const unsigned int* __restrict__ bins, double* __restrict__ s0,
     }
 }
 
+// blocks along y (window stride) for a window pass: fill whole waves of resident blocks, a few waves deep
+template <class Kern>
+static unsigned window_pass_gy(mpb_ctx* ctx, Kern kern, unsigned gx, int nw) {
+    int per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, HIST_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    const long long resident = (long long)per_sm * ctx->sm_count;
+    long long lo = (resident + gx - 1) / gx, hi = (4 * resident + gx - 1) / gx + 1;
+    if (lo < 1) lo = 1;
+    if (hi > nw) hi = nw;
+    if (lo > hi) lo = hi;
+    unsigned best = (unsigned)lo;
+    double best_eff = -1;
+    for (long long gy = lo; gy <= hi; ++gy) {
+        const long long blocks = (long long)gx * gy, waves = (blocks + resident - 1) / resident;
+        const double eff = (double)blocks / (double)(waves * resident);
+        if (eff >= best_eff) {
+            best_eff = eff;
+            best = (unsigned)gy;
+        }
+    }
+    return best;
+}
+
 extern "C" int mpb_window_prefilter(mpb_msa* m, int k, int v, const int32_t* win_pos, int32_t nw, double* s0_hd,
                                     double* s1_hd) {
     if (!m || !win_pos || !s0_hd || !s1_hd) return fail(MPB_EINVAL, "NULL argument");
@@ -844,11 +836,8 @@ extern "C" int mpb_window_prefilter(mpb_msa* m, int k, int v, const int32_t* win
     InBuf wp(ctx, win_pos, (size_t)nw * 4);
     OutBuf o0(ctx, s0_hd, (size_t)nw * 8), o1(ctx, s1_hd, (size_t)nw * 8);
     if (wp.rc || o0.rc || o1.rc) return MPB_ECUDA;
-    const unsigned gx = (unsigned)((m->n_seq + (long long)HIST_THREADS * HIST_TILES - 1) / ((long long)HIST_THREADS * HIST_TILES));
-    unsigned gy = (unsigned)nw;
-    const unsigned want = (unsigned)ctx->sm_count * 8;
-    if (gx >= want) gy = 1;
-    else if (gy > (want + gx - 1) / gx) gy = (want + gx - 1) / gx;
+    const unsigned gx = (unsigned)((m->n_seq + (long long)WIN_ROWS - 1) / (long long)WIN_ROWS);
+    const unsigned gy = window_pass_gy(ctx, k_prefilter, gx, nw);
     ctx->pending_units = (double)nw * (double)m->n_seq;
     LAUNCH(ctx, k_prefilter, dim3(gx, gy), HIST_THREADS, 0, m->planes, m->nsp, m->n_seq, m->lens, k, v, wp.dev<int32_t>(),
            nw, bins, m->err);
@@ -882,11 +871,8 @@ static int hist_launch_build(mpb_hist* h) {
     CK(cudaMemsetAsync(h->n_entries, 0, (size_t)nw * 8, ctx->stream));
     CK(cudaMemsetAsync(h->spec_n, 0, (size_t)nw * 8, ctx->stream));
     CK(cudaMemsetAsync(h->exc_n, 0, 8, ctx->stream));
-    const unsigned gx = (unsigned)((m->n_seq + (long long)HIST_THREADS * HIST_TILES - 1) / ((long long)HIST_THREADS * HIST_TILES));
-    unsigned gy = (unsigned)nw;
-    const unsigned want = (unsigned)ctx->sm_count * 8;
-    if (gx >= want) gy = 1;
-    else if (gy > (want + gx - 1) / gx) gy = (want + gx - 1) / gx;
+    const unsigned gx = (unsigned)((m->n_seq + (long long)WIN_ROWS - 1) / (long long)WIN_ROWS);
+    const unsigned gy = window_pass_gy(ctx, k_hist, gx, nw);
     ctx->pending_units = (double)nw * (double)m->n_seq;  // (window, sequence) k-mers extracted
     LAUNCH(ctx, k_hist, dim3(gx, gy), HIST_THREADS, 0, m->planes, m->nsp, m->n_seq, m->lens, h->k, h->v, h->win_pos, nw,
            h->keys, h->cnt, h->first, h->log2cap, h->gap_n, h->iupac_gap_n, h->exc, h->exc_n, (long long)h->exc_max,
