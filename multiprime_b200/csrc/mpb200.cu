@@ -464,29 +464,31 @@ extern "C" int mpb_seq_attr(mpb_msa* m, int32_t* lead_hd, int32_t* rstrip_hd) {
 // window passes: every (window, sequence) k-mer of a window batch, once for the entropy prefilter (all windows) and once
 // for the haplotype tables (the windows that survive it)
 // ------------------------------------------------------------------------------------------------------
-// Both kernels stream without block barriers.  Block (x, y) owns WIN_TILES x 256 sequences and walks the windows
-// y, y + gridDim.y, ...; a warp owns 32 sequences per tile.  In a window below the entropy gate most sequences carry
-// the SAME k-mer, so each warp keeps that majority k-mer and its count in registers for the whole window (one global
-// atomic per warp and window) and sends only the minority rows to global memory one by one; a variable window
-// degenerates to one atomic per row, which is what it costs anyway.  (Round 1 staged every row in a block-private
-// hash table: three block barriers per window, 150 instructions per tile in the probing loops of the variable
-// windows; ncu: 35-41 % of the stall samples at the barriers, 18 active threads per instruction.)
-// Rows that need more than the funnel shift — the window starts / ends inside a gap run (patched with flank bases,
-// core:671-682), holds IUPAC cells, runs past a ragged row end, or (tables only) holds a gap and therefore needs the
-// base-5 key — are recorded in a block-private list and handled densely, one per thread, after the window loop.
+// Both kernels stream without block barriers and read every alignment word ONCE per group of windows.
+//   * Windows are grouped by column word (mpb_window_groups: consecutive batch entries with the same p >> 5, at most
+//     32): all of them cut their k-mers out of the same two 128-bit plane words of a sequence, so a thread loads the
+//     two words once per tile and funnel-shifts up to 32 windows out of them (round 1 and the first version of this
+//     round re-read them per window: 18.6 GB of L2 traffic per pass, and 73 % of the stall samples waiting for it).
+//   * Block (x, y) owns WIN_TILES x 256 sequences and walks the groups y, y + gridDim.y, ...; a warp owns 32
+//     sequences per tile, and LANE j of the warp keeps the running state of WINDOW j of the group.  In a window below
+//     the entropy gate most sequences carry the SAME k-mer, so the warp keeps that majority k-mer and its count in
+//     lane j's registers for the whole pass (one global atomic per warp and window) and sends only the minority rows
+//     to global memory one by one; a variable window degenerates to one atomic per row, which is what it costs
+//     anyway.  (Round 1 staged every row in a block-private hash table: three block barriers per window, 150
+//     instructions per tile in the probing loops of the variable windows.)
+//   * Rows that need more than the funnel shift — the window starts / ends inside a gap run (patched with flank
+//     bases, core:671-682), holds IUPAC cells, runs past a ragged row end, or (tables only) holds a gap and therefore
+//     needs the base-5 key — are recorded in a block-private list and handled densely, one per thread, at the end.
 #define HIST_THREADS 256
 #define WIN_TILES 16
 #define WIN_ROWS (HIST_THREADS * WIN_TILES)
-#define DEFER_CAP 12000  // deferred (window slot, row) pairs per block; beyond it rows are handled where they stand
+#define DEFER_CAP 8000  // deferred (window, row) pairs per block; beyond it rows are handled where they stand
 
-// window words of one row: funnel shift of the two column words
 struct RawWin {
     uint32_t a, c, g, t, gapv;
     bool special;  // needs patching / expansion / ragged handling
 };
-__device__ __forceinline__ RawWin win_raw(const uint4* __restrict__ wbase, int64_t nsp, int64_t s, int sh, uint32_t kmask,
-                                          int p, int k, int len) {
-    const uint4 q0 = __ldg(wbase + s), q1 = __ldg(wbase + nsp + s);
+__device__ __forceinline__ RawWin win_cut(const uint4& q0, const uint4& q1, int sh, uint32_t kmask, int p, int k, int len) {
     RawWin r;
     r.a = __funnelshift_r(q0.x, q1.x, sh) & kmask;
     r.c = __funnelshift_r(q0.y, q1.y, sh) & kmask;
@@ -498,7 +500,7 @@ __device__ __forceinline__ RawWin win_raw(const uint4* __restrict__ wbase, int64
     return r;
 }
 
-// the code / key most lanes of the warp share (first-tile vote)
+// the code / key most lanes of the warp share (vote on the first tile that has any)
 template <class T>
 __device__ __forceinline__ T warp_majority(unsigned mask, bool mine, T val) {
     unsigned peers = 0;
@@ -507,6 +509,17 @@ __device__ __forceinline__ T warp_majority(unsigned mask, bool mine, T val) {
     const unsigned mx = __reduce_max_sync(0xffffffffu, cnt);
     const int leader = __ffs(__ballot_sync(0xffffffffu, cnt == mx && mine)) - 1;
     return __shfl_sync(0xffffffffu, val, leader);
+}
+
+// host: groups (first batch index, count) of consecutive windows that share their column word
+static void mpb_window_groups(const int32_t* win_pos, int nw, std::vector<int2>& groups) {
+    groups.clear();
+    for (int i = 0; i < nw;) {
+        int j = i + 1;
+        while (j < nw && j - i < 32 && (win_pos[j] >> 5) == (win_pos[i] >> 5)) ++j;
+        groups.push_back(make_int2(i, j - i));
+        i = j;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -553,7 +566,8 @@ __device__ __forceinline__ void pre_row(const Win& w, int v, unsigned int* B, in
 
 __global__ void __launch_bounds__(HIST_THREADS)
 k_prefilter(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq, const int32_t* __restrict__ lens, int k, int v,
-            const int32_t* __restrict__ win_pos, int nw, unsigned int* __restrict__ bins, int* __restrict__ err) {
+            const int32_t* __restrict__ win_pos, const int2* __restrict__ groups, int n_groups,
+            unsigned int* __restrict__ bins, int* __restrict__ err) {
     __shared__ unsigned int s_defer[DEFER_CAP];
     __shared__ unsigned int s_ndefer;
     const uint32_t kmask = (1u << k) - 1u;
@@ -561,55 +575,68 @@ k_prefilter(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq, const i
     const int64_t row_base = (int64_t)blockIdx.x * WIN_ROWS;
     if (threadIdx.x == 0) s_ndefer = 0;
     __syncthreads();
-    int slot = 0;
-    for (int wi = blockIdx.y; wi < nw; wi += gridDim.y, ++slot) {
-        const int p = win_pos[wi];
-        unsigned int* B = bins + (long long)wi * PRE_BINS;
-        const uint4* __restrict__ wbase = reinterpret_cast<const uint4*>(pl) + (int64_t)(p >> 5) * nsp;
-        const int sh = p & 31;
-        uint32_t major = 0;
-        unsigned count = 0;
-        bool have = false;
-#pragma unroll 4
+    int gslot = 0;
+    for (int g = blockIdx.y; g < n_groups; g += gridDim.y, ++gslot) {
+        const int2 gr = groups[g];
+        const int my_p = lane < gr.y ? win_pos[gr.x + lane] : 0;  // lane j <-> window j of the group
+        const uint4* __restrict__ wbase = reinterpret_cast<const uint4*>(pl) + (int64_t)(__shfl_sync(0xffffffffu, my_p, 0) >> 5) * nsp;
+        uint32_t my_major = 0;
+        unsigned my_count = 0, have_mask = 0;
         for (int t = 0; t < WIN_TILES; ++t) {
             const int64_t tile0 = row_base + t * HIST_THREADS;
             if (tile0 >= n_seq) break;  // uniform
             const int64_t s = tile0 + threadIdx.x;
-            bool plain = false;
-            uint32_t code = 0;
-            if (s < n_seq) {
-                const int len = __ldg(lens + s);
-                const RawWin r = win_raw(wbase, nsp, s, sh, kmask, p, k, len);
-                if (r.special) {
-                    const unsigned idx = atomicAdd(&s_ndefer, 1u);
-                    if (idx < DEFER_CAP) {
-                        s_defer[idx] = ((unsigned)slot << 12) | (unsigned)(t * HIST_THREADS + threadIdx.x);
-                    } else {  // list full: handle the row here
-                        Win w;
-                        if (!mpb_load_window(pl, nsp, s, len, p, k, kmask, w)) atomicOr(err, MPB_ERR_SHORT_ROW);
-                        pre_row(w, v, B, err);
+            const bool valid = s < n_seq;
+            uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0;
+            int len = 0;
+            if (valid) {
+                q0 = __ldg(wbase + s);
+                q1 = __ldg(wbase + nsp + s);
+                len = __ldg(lens + s);
+            }
+            for (int j = 0; j < gr.y; ++j) {
+                const int p = __shfl_sync(0xffffffffu, my_p, j);
+                unsigned int* B = bins + (long long)(gr.x + j) * PRE_BINS;
+                bool plain = false;
+                uint32_t code = 0;
+                if (valid) {
+                    const RawWin r = win_cut(q0, q1, p & 31, kmask, p, k, len);
+                    if (r.special) {
+                        const unsigned idx = atomicAdd(&s_ndefer, 1u);
+                        if (idx < DEFER_CAP) {
+                            s_defer[idx] = ((unsigned)(gslot * 32 + j) << 12) | (unsigned)(t * HIST_THREADS + threadIdx.x);
+                        } else {  // list full: handle the row here
+                            Win w;
+                            if (!mpb_load_window(pl, nsp, s, len, p, k, kmask, w)) atomicOr(err, MPB_ERR_SHORT_ROW);
+                            pre_row(w, v, B, err);
+                        }
+                    } else {
+                        plain = true;
+                        code = pre_code(r.c, r.g, r.t);
                     }
-                } else {
-                    plain = true;
-                    code = pre_code(r.c, r.g, r.t);
                 }
+                const unsigned pm = __ballot_sync(0xffffffffu, plain);
+                uint32_t major;
+                if (!((have_mask >> j) & 1u) && pm) {
+                    major = warp_majority<uint32_t>(pm, plain, code);
+                    if (lane == j) my_major = major;
+                    have_mask |= 1u << j;
+                } else {
+                    major = __shfl_sync(0xffffffffu, my_major, j);
+                }
+                const unsigned eq = __ballot_sync(0xffffffffu, plain && code == major);
+                if (lane == j) my_count += __popc(eq);
+                if (plain && code != major) atomicAdd(&B[code], 1u);
             }
-            const unsigned pm = __ballot_sync(0xffffffffu, plain);
-            if (!have && pm) {
-                major = warp_majority<uint32_t>(pm, plain, code);
-                have = true;
-            }
-            const unsigned eq = __ballot_sync(0xffffffffu, plain && code == major);
-            count += __popc(eq);
-            if (plain && code != major) atomicAdd(&B[code], 1u);
         }
-        if (lane == 0 && count) atomicAdd(&B[major], count);
+        if (lane < gr.y && my_count) atomicAdd(&bins[(long long)(gr.x + lane) * PRE_BINS + my_major], my_count);
     }
     __syncthreads();
     const unsigned nd = s_ndefer < DEFER_CAP ? s_ndefer : DEFER_CAP;
     for (unsigned i = threadIdx.x; i < nd; i += HIST_THREADS) {
         const unsigned e = s_defer[i];
-        const int wi = blockIdx.y + (int)(e >> 12) * gridDim.y;
+        const unsigned ws = e >> 12;
+        const int wi = groups[blockIdx.y + (int)(ws >> 5) * gridDim.y].x + (int)(ws & 31u);
         const int64_t s = row_base + (e & 0xFFFu);
         Win w;
         if (!mpb_load_window(pl, nsp, s, lens[s], win_pos[wi], k, kmask, w)) atomicOr(err, MPB_ERR_SHORT_ROW);
@@ -671,8 +698,8 @@ __device__ __forceinline__ void hist_row(const uint32_t* __restrict__ pl, int64_
 
 __global__ void __launch_bounds__(HIST_THREADS)
 k_hist(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq, const int32_t* __restrict__ lens, int k, int v,
-       const int32_t* __restrict__ win_pos, int nw, uint64_t* __restrict__ keys, uint32_t* __restrict__ cnt,
-       uint64_t* __restrict__ first, int log2cap, unsigned long long* __restrict__ gap_n,
+       const int32_t* __restrict__ win_pos, const int2* __restrict__ groups, int n_groups, uint64_t* __restrict__ keys,
+       uint32_t* __restrict__ cnt, uint64_t* __restrict__ first, int log2cap, unsigned long long* __restrict__ gap_n,
        unsigned long long* __restrict__ iupac_gap_n, int32_t* __restrict__ exc, unsigned long long* __restrict__ exc_n,
        long long exc_max, long long row0, unsigned long long* __restrict__ n_entries, uint32_t* __restrict__ elist,
        uint32_t* __restrict__ spec_bits, uint32_t* __restrict__ gap_bits, long long nwords, uint4* __restrict__ spec_win,
@@ -686,79 +713,95 @@ k_hist(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq, const int32_
     const int64_t row_base = (int64_t)blockIdx.x * WIN_ROWS;
     if (threadIdx.x == 0) s_ndefer = 0;
     __syncthreads();
-    int slot = 0;
-    for (int wi = blockIdx.y; wi < nw; wi += gridDim.y, ++slot) {
-        const int p = win_pos[wi];
-        uint64_t* K = keys + (uint64_t)wi * cap;
-        uint32_t* C = cnt + (uint64_t)wi * cap;
-        uint64_t* F = first + (uint64_t)wi * cap;
-        uint32_t* E = elist + (uint64_t)wi * cap;
-        const uint4* __restrict__ wbase = reinterpret_cast<const uint4*>(pl) + (int64_t)(p >> 5) * nsp;
-        const int sh = p & 31;
-        uint64_t major = 0, major_first = 0;
-        unsigned count = 0, gaps = 0;
-        bool have = false;
-#pragma unroll 2
+    int gslot = 0;
+    for (int g = blockIdx.y; g < n_groups; g += gridDim.y, ++gslot) {
+        const int2 gr = groups[g];
+        const int my_p = lane < gr.y ? win_pos[gr.x + lane] : 0;  // lane j <-> window j of the group
+        const uint4* __restrict__ wbase = reinterpret_cast<const uint4*>(pl) + (int64_t)(__shfl_sync(0xffffffffu, my_p, 0) >> 5) * nsp;
+        unsigned long long my_major = 0, my_first = 0;
+        unsigned my_count = 0, my_gaps = 0, have_mask = 0;
         for (int t = 0; t < WIN_TILES; ++t) {
             const int64_t tile0 = row_base + t * HIST_THREADS;
             if (tile0 >= n_seq) break;  // uniform
             const int64_t s = tile0 + threadIdx.x;
-            bool plain = false, simple = false, isgap = false, late = false, late_special = false;
-            uint64_t key = 0;
+            const bool valid = s < n_seq;
+            uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0;
             int len = 0;
-            if (s < n_seq) {
+            if (valid) {
+                q0 = __ldg(wbase + s);
+                q1 = __ldg(wbase + nsp + s);
                 len = __ldg(lens + s);
-                const RawWin r = win_raw(wbase, nsp, s, sh, kmask, p, k, len);
-                plain = !r.special;
-                isgap = plain && __popc(r.gapv) > v;
-                simple = plain && r.gapv == 0u;     // gap-free: the 2-bit key; rows holding gaps need the base-5 key
-                if (simple) {
-                    key = (uint64_t)(r.c | r.t) | ((uint64_t)(r.g | r.t) << k);
-                } else {
-                    const unsigned idx = atomicAdd(&s_ndefer, 1u);
-                    if (idx < DEFER_CAP) {
-                        s_defer[idx] = ((unsigned)slot << 13) | (r.special ? 0x1000u : 0u) | (unsigned)(t * HIST_THREADS + threadIdx.x);
-                    } else {  // list full: handle the row in this iteration, after the class words are stored
-                        late = true;
-                        late_special = r.special;
+            }
+            const long long word = tile0 / 32 + (threadIdx.x >> 5);
+            for (int j = 0; j < gr.y; ++j) {
+                const int p = __shfl_sync(0xffffffffu, my_p, j);
+                const int wi = gr.x + j;
+                uint64_t* K = keys + (uint64_t)wi * cap;
+                uint32_t* C = cnt + (uint64_t)wi * cap;
+                uint64_t* F = first + (uint64_t)wi * cap;
+                uint32_t* E = elist + (uint64_t)wi * cap;
+                bool plain = false, simple = false, isgap = false, late = false, late_special = false;
+                unsigned long long key = 0;
+                if (valid) {
+                    const RawWin r = win_cut(q0, q1, p & 31, kmask, p, k, len);
+                    plain = !r.special;
+                    isgap = plain && __popc(r.gapv) > v;
+                    simple = plain && r.gapv == 0u;  // gap-free: the 2-bit key; rows holding gaps need the base-5 key
+                    if (simple) {
+                        key = (unsigned long long)(r.c | r.t) | ((unsigned long long)(r.g | r.t) << k);
+                    } else {
+                        const unsigned idx = atomicAdd(&s_ndefer, 1u);
+                        if (idx < DEFER_CAP) {
+                            s_defer[idx] = ((unsigned)(gslot * 32 + j) << 13) | (r.special ? 0x1000u : 0u) |
+                                           (unsigned)(t * HIST_THREADS + threadIdx.x);
+                        } else {  // list full: handle the row in this iteration, after the class words are stored
+                            late = true;
+                            late_special = r.special;
+                        }
                     }
                 }
-            }
-            const unsigned pm = __ballot_sync(0xffffffffu, plain);
-            const unsigned gb = __ballot_sync(0xffffffffu, plain && isgap);
-            gaps += __popc(gb);
-            {   // row classes of this 32-sequence word for the column scan (padding rows count as special)
-                const long long word = tile0 / 32 + (threadIdx.x >> 5);
-                if (lane == 0 && word < nwords) {
-                    spec_bits[(long long)wi * nwords + word] = ~pm;
+                const unsigned pm = __ballot_sync(0xffffffffu, plain);
+                const unsigned gb = __ballot_sync(0xffffffffu, plain && isgap);
+                if (lane == j) my_gaps += __popc(gb);
+                if (lane == 0 && word < nwords) {  // row classes of this 32-sequence word for the column scan
+                    spec_bits[(long long)wi * nwords + word] = ~pm;  // (padding rows count as special)
                     gap_bits[(long long)wi * nwords + word] = gb;
                 }
-            }
-            __syncwarp();  // the class words are in place before a late row ORs its gap bit in
-            const unsigned sm = __ballot_sync(0xffffffffu, simple);
-            if (!have && sm) {
-                major = warp_majority<unsigned long long>(sm, simple, key);
-                have = true;
-            }
-            const unsigned eq = __ballot_sync(0xffffffffu, simple && key == major);
-            if (count == 0 && eq) major_first = (uint64_t)(row0 + tile0 + (threadIdx.x & ~31) + (__ffs(eq) - 1)) << 16;
-            count += __popc(eq);
-            if (simple && key != major) mpb_table_add(K, C, F, log2cap, key, 1u, (uint64_t)(row0 + s) << 16, err, &n_entries[wi], E);
-            if (late) {
-                hist_row(pl, nsp, s, len, p, k, v, kmask, row0, wi, K, C, F, E, log2cap, gap_n, iupac_gap_n, exc, exc_n,
-                         exc_max, n_entries, gap_bits, nwords, spec_win, spec_row, spec_n, spec_cap, late_special, err);
+                __syncwarp();  // the class words are in place before a late row ORs its gap bit in
+                const unsigned sm = __ballot_sync(0xffffffffu, simple);
+                unsigned long long major;
+                if (!((have_mask >> j) & 1u) && sm) {
+                    major = warp_majority<unsigned long long>(sm, simple, key);
+                    if (lane == j) my_major = major;
+                    have_mask |= 1u << j;
+                } else {
+                    major = __shfl_sync(0xffffffffu, my_major, j);
+                }
+                const unsigned eq = __ballot_sync(0xffffffffu, simple && key == major);
+                if (lane == j) {
+                    if (my_count == 0 && eq) my_first = (unsigned long long)(row0 + tile0 + (threadIdx.x & ~31) + (__ffs(eq) - 1)) << 16;
+                    my_count += __popc(eq);
+                }
+                if (simple && key != major) mpb_table_add(K, C, F, log2cap, key, 1u, (uint64_t)(row0 + s) << 16, err, &n_entries[wi], E);
+                if (late)
+                    hist_row(pl, nsp, s, len, p, k, v, kmask, row0, wi, K, C, F, E, log2cap, gap_n, iupac_gap_n, exc, exc_n,
+                             exc_max, n_entries, gap_bits, nwords, spec_win, spec_row, spec_n, spec_cap, late_special, err);
             }
         }
-        if (lane == 0) {
-            if (count) mpb_table_add(K, C, F, log2cap, major, count, major_first, err, &n_entries[wi], E);
-            if (gaps) atomicAdd(&gap_n[wi], (unsigned long long)gaps);
+        if (lane < gr.y) {
+            const int wi = gr.x + lane;
+            if (my_count)
+                mpb_table_add(keys + (uint64_t)wi * cap, cnt + (uint64_t)wi * cap, first + (uint64_t)wi * cap, log2cap, my_major,
+                              my_count, my_first, err, &n_entries[wi], elist + (uint64_t)wi * cap);
+            if (my_gaps) atomicAdd(&gap_n[wi], (unsigned long long)my_gaps);
         }
     }
     __syncthreads();
     const unsigned nd = s_ndefer < DEFER_CAP ? s_ndefer : DEFER_CAP;
     for (unsigned i = threadIdx.x; i < nd; i += HIST_THREADS) {
         const unsigned e = s_defer[i];
-        const int wi = blockIdx.y + (int)(e >> 13) * gridDim.y;
+        const unsigned ws = e >> 13;
+        const int wi = groups[blockIdx.y + (int)(ws >> 5) * gridDim.y].x + (int)(ws & 31u);
         const int64_t s = row_base + (e & 0xFFFu);
         hist_row(pl, nsp, s, lens[s], win_pos[wi], k, v, kmask, row0, wi, keys + (uint64_t)wi * cap, cnt + (uint64_t)wi * cap,
                  first + (uint64_t)wi * cap, elist + (uint64_t)wi * cap, log2cap, gap_n, iupac_gap_n, exc, exc_n, exc_max,
@@ -804,6 +847,7 @@ static unsigned window_pass_gy(mpb_ctx* ctx, Kern kern, unsigned gx, int nw) {
     int per_sm = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, HIST_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
     const long long resident = (long long)per_sm * ctx->sm_count;
+    if ((long long)gx * nw <= 16 * resident) return (unsigned)nw;  // one group per block: uniform work, many waves
     long long lo = (resident + gx - 1) / gx, hi = (4 * resident + gx - 1) / gx + 1;
     if (lo < 1) lo = 1;
     if (hi > nw) hi = nw;
@@ -837,10 +881,14 @@ extern "C" int mpb_window_prefilter(mpb_msa* m, int k, int v, const int32_t* win
     OutBuf o0(ctx, s0_hd, (size_t)nw * 8), o1(ctx, s1_hd, (size_t)nw * 8);
     if (wp.rc || o0.rc || o1.rc) return MPB_ECUDA;
     const unsigned gx = (unsigned)((m->n_seq + (long long)WIN_ROWS - 1) / (long long)WIN_ROWS);
-    const unsigned gy = window_pass_gy(ctx, k_prefilter, gx, nw);
+    std::vector<int2> groups;
+    mpb_window_groups(win_pos, nw, groups);
+    InBuf gr(ctx, groups.data(), groups.size() * sizeof(int2));
+    if (gr.rc) return gr.rc;
+    const unsigned gy = window_pass_gy(ctx, k_prefilter, gx, (int)groups.size());
     ctx->pending_units = (double)nw * (double)m->n_seq;
     LAUNCH(ctx, k_prefilter, dim3(gx, gy), HIST_THREADS, 0, m->planes, m->nsp, m->n_seq, m->lens, k, v, wp.dev<int32_t>(),
-           nw, bins, m->err);
+           gr.dev<int2>(), (int)groups.size(), bins, m->err);
     LAUNCH(ctx, k_prefilter_sums, (unsigned)nw, 256, 0, bins, o0.dev<double>(), o1.dev<double>());
     CK(o0.finish());
     CK(o1.finish());
@@ -872,10 +920,14 @@ static int hist_launch_build(mpb_hist* h) {
     CK(cudaMemsetAsync(h->spec_n, 0, (size_t)nw * 8, ctx->stream));
     CK(cudaMemsetAsync(h->exc_n, 0, 8, ctx->stream));
     const unsigned gx = (unsigned)((m->n_seq + (long long)WIN_ROWS - 1) / (long long)WIN_ROWS);
-    const unsigned gy = window_pass_gy(ctx, k_hist, gx, nw);
+    std::vector<int2> groups;
+    mpb_window_groups(h->h_win_pos.data(), nw, groups);
+    InBuf gr(ctx, groups.data(), groups.size() * sizeof(int2));
+    if (gr.rc) return gr.rc;
+    const unsigned gy = window_pass_gy(ctx, k_hist, gx, (int)groups.size());
     ctx->pending_units = (double)nw * (double)m->n_seq;  // (window, sequence) k-mers extracted
-    LAUNCH(ctx, k_hist, dim3(gx, gy), HIST_THREADS, 0, m->planes, m->nsp, m->n_seq, m->lens, h->k, h->v, h->win_pos, nw,
-           h->keys, h->cnt, h->first, h->log2cap, h->gap_n, h->iupac_gap_n, h->exc, h->exc_n, (long long)h->exc_max,
+    LAUNCH(ctx, k_hist, dim3(gx, gy), HIST_THREADS, 0, m->planes, m->nsp, m->n_seq, m->lens, h->k, h->v, h->win_pos,
+           gr.dev<int2>(), (int)groups.size(), h->keys, h->cnt, h->first, h->log2cap, h->gap_n, h->iupac_gap_n, h->exc, h->exc_n, (long long)h->exc_max,
            (long long)m->row0, h->n_entries, h->elist, h->spec_bits, h->gap_bits, (long long)m->nwords, h->spec_win,
            h->spec_row, h->spec_n, (long long)h->spec_cap, m->err);
     return 0;
