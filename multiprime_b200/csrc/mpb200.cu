@@ -570,16 +570,22 @@ k_prefilter(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq, const i
             unsigned int* __restrict__ bins, int* __restrict__ err) {
     __shared__ unsigned int s_defer[DEFER_CAP];
     __shared__ unsigned int s_ndefer;
+    __shared__ int s_p[HIST_THREADS / 32][32];            // window start columns of the group, per warp
+    __shared__ uint32_t s_major[HIST_THREADS / 32][32];   // majority code of every window of the group, per warp
     const uint32_t kmask = (1u << k) - 1u;
-    const int lane = threadIdx.x & 31;
+    int lane;
+    asm("mov.u32 %0, %%laneid;" : "=r"(lane));
+    const int warp = threadIdx.x >> 5;
     const int64_t row_base = (int64_t)blockIdx.x * WIN_ROWS;
     if (threadIdx.x == 0) s_ndefer = 0;
     __syncthreads();
     int gslot = 0;
     for (int g = blockIdx.y; g < n_groups; g += gridDim.y, ++gslot) {
         const int2 gr = groups[g];
-        const int my_p = lane < gr.y ? win_pos[gr.x + lane] : 0;  // lane j <-> window j of the group
-        const uint4* __restrict__ wbase = reinterpret_cast<const uint4*>(pl) + (int64_t)(__shfl_sync(0xffffffffu, my_p, 0) >> 5) * nsp;
+        __syncwarp();
+        s_p[warp][lane] = lane < gr.y ? win_pos[gr.x + lane] : 0;  // lane j <-> window j of the group
+        __syncwarp();
+        const uint4* __restrict__ wbase = reinterpret_cast<const uint4*>(pl) + (int64_t)(s_p[warp][0] >> 5) * nsp;
         uint32_t my_major = 0;
         unsigned my_count = 0, have_mask = 0;
         for (int t = 0; t < WIN_TILES; ++t) {
@@ -594,8 +600,9 @@ k_prefilter(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq, const i
                 q1 = __ldg(wbase + nsp + s);
                 len = __ldg(lens + s);
             }
+#pragma unroll 2
             for (int j = 0; j < gr.y; ++j) {
-                const int p = __shfl_sync(0xffffffffu, my_p, j);
+                const int p = s_p[warp][j];
                 unsigned int* B = bins + (long long)(gr.x + j) * PRE_BINS;
                 bool plain = false;
                 uint32_t code = 0;
@@ -619,10 +626,14 @@ k_prefilter(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq, const i
                 uint32_t major;
                 if (!((have_mask >> j) & 1u) && pm) {
                     major = warp_majority<uint32_t>(pm, plain, code);
-                    if (lane == j) my_major = major;
+                    if (lane == j) {
+                        my_major = major;
+                        s_major[warp][j] = major;
+                    }
                     have_mask |= 1u << j;
+                    __syncwarp();
                 } else {
-                    major = __shfl_sync(0xffffffffu, my_major, j);
+                    major = s_major[warp][j];
                 }
                 const unsigned eq = __ballot_sync(0xffffffffu, plain && code == major);
                 if (lane == j) my_count += __popc(eq);
@@ -707,17 +718,23 @@ k_hist(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq, const int32_
        int* __restrict__ err) {
     __shared__ unsigned int s_defer[DEFER_CAP];
     __shared__ unsigned int s_ndefer;
+    __shared__ int s_p[HIST_THREADS / 32][32];                      // window start columns of the group, per warp
+    __shared__ unsigned long long s_major[HIST_THREADS / 32][32];   // majority key of every window of the group, per warp
     const uint32_t kmask = (1u << k) - 1u;
     const uint64_t cap = 1ull << log2cap;
-    const int lane = threadIdx.x & 31;
+    int lane;
+    asm("mov.u32 %0, %%laneid;" : "=r"(lane));
+    const int warp = threadIdx.x >> 5;
     const int64_t row_base = (int64_t)blockIdx.x * WIN_ROWS;
     if (threadIdx.x == 0) s_ndefer = 0;
     __syncthreads();
     int gslot = 0;
     for (int g = blockIdx.y; g < n_groups; g += gridDim.y, ++gslot) {
         const int2 gr = groups[g];
-        const int my_p = lane < gr.y ? win_pos[gr.x + lane] : 0;  // lane j <-> window j of the group
-        const uint4* __restrict__ wbase = reinterpret_cast<const uint4*>(pl) + (int64_t)(__shfl_sync(0xffffffffu, my_p, 0) >> 5) * nsp;
+        __syncwarp();
+        s_p[warp][lane] = lane < gr.y ? win_pos[gr.x + lane] : 0;  // lane j <-> window j of the group
+        __syncwarp();
+        const uint4* __restrict__ wbase = reinterpret_cast<const uint4*>(pl) + (int64_t)(s_p[warp][0] >> 5) * nsp;
         unsigned long long my_major = 0, my_first = 0;
         unsigned my_count = 0, my_gaps = 0, have_mask = 0;
         for (int t = 0; t < WIN_TILES; ++t) {
@@ -732,9 +749,9 @@ k_hist(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq, const int32_
                 q1 = __ldg(wbase + nsp + s);
                 len = __ldg(lens + s);
             }
-            const long long word = tile0 / 32 + (threadIdx.x >> 5);
+            const long long word = tile0 / 32 + warp;
             for (int j = 0; j < gr.y; ++j) {
-                const int p = __shfl_sync(0xffffffffu, my_p, j);
+                const int p = s_p[warp][j];
                 const int wi = gr.x + j;
                 uint64_t* K = keys + (uint64_t)wi * cap;
                 uint32_t* C = cnt + (uint64_t)wi * cap;
@@ -772,14 +789,18 @@ k_hist(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq, const int32_
                 unsigned long long major;
                 if (!((have_mask >> j) & 1u) && sm) {
                     major = warp_majority<unsigned long long>(sm, simple, key);
-                    if (lane == j) my_major = major;
+                    if (lane == j) {
+                        my_major = major;
+                        s_major[warp][j] = major;
+                    }
                     have_mask |= 1u << j;
+                    __syncwarp();
                 } else {
-                    major = __shfl_sync(0xffffffffu, my_major, j);
+                    major = s_major[warp][j];
                 }
                 const unsigned eq = __ballot_sync(0xffffffffu, simple && key == major);
                 if (lane == j) {
-                    if (my_count == 0 && eq) my_first = (unsigned long long)(row0 + tile0 + (threadIdx.x & ~31) + (__ffs(eq) - 1)) << 16;
+                    if (my_count == 0 && eq) my_first = (unsigned long long)(row0 + tile0 + warp * 32 + (__ffs(eq) - 1)) << 16;
                     my_count += __popc(eq);
                 }
                 if (simple && key != major) mpb_table_add(K, C, F, log2cap, key, 1u, (uint64_t)(row0 + s) << 16, err, &n_entries[wi], E);
