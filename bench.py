@@ -2,14 +2,15 @@
 """bench.py — candidate x sequence mismatch evaluations per second of the degenerate-primer candidate scan.
 
     python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run, one rank/GPU)
-    python bench.py --impl reference ...                     (the CPU arm: the oracle port on the host cores)
+    python bench.py --impl reference ...                     (the CPU arm: the reference's algorithm on the host cores)
 
 Workload (BASELINE.json configs[3], the configuration the metric is quoted on): synthetic 10^6-sequence x 600-column
 alignment (multiprime_b200/synth.py), k=18, degeneracy <= 256 (-n 8), <= 3 mismatches, other flags default.
-One step = one full pass of the hot path over every window of the conserved region: window k-mer extraction +
-haplotype tables, gates, base/dinucleotide tensors, seeds, the NN-array refinement walk with one candidate scan per
-round, Tm, filters -> the rows of the reference's .out TSV.  `value` counts exactly the evaluations the reference
-makes: (calls to mis_primer_check) x (sequences), summed over windows, divided by the step time.
+One step = one full pass of the hot path over every window of the conserved region: entropy prefilter, window k-mer
+extraction + haplotype tables, gates, base/dinucleotide tensors, seeds, the NN-array refinement walk with one
+candidate scan per round, the per-sequence coverage bit vectors of the chosen primers, Tm, filters, self-dimer gate
+-> the rows of the reference's .out TSV.  `value` counts exactly the evaluations the reference makes: (calls to
+mis_primer_check) x (sequences), summed over windows, divided by the step time.
 With N GPUs every rank holds n_seq sequences of the same synthetic family (weak scaling).
 """
 from __future__ import annotations
@@ -17,6 +18,7 @@ from __future__ import annotations
 import argparse
 import json
 import os
+import statistics
 import subprocess
 import sys
 import threading
@@ -28,21 +30,34 @@ sys.path.insert(0, ROOT)
 K, DNUM, DEG, VAR = 18, 8, 256, 3
 PARAMS = dict(primer_length=K, coverage=0.8, number_of_dege_bases=DNUM, score_of_dege_bases=DEG, product_len=100,
               position="1,2,-1", variation=VAR, raw_entropy_threshold=3.6, distance=4, GC="0.2,0.7", nproc=1)
-BYTES_PER_EVAL = K / 2 + 0.25                     # one k-column window in 4-bit cells + 2 result bits
+BYTES_PER_EVAL = K / 2 + 0.25      # one k-column window in 4-bit cells + 2 result bits
+BYTES_PER_KMER = K / 2             # window passes: one k-column window in 4-bit cells per (window, sequence)
+KERNELS = ("k_prefilter", "k_prefilter_sums", "k_hist", "k_hist_summary", "k_hist_match", "k_cscan", "k_cscan_plan",
+           "k_cscan_special", "k_walk_advance", "k_walk_compact", "k_walk_seed", "k_tm", "k_dimer_pairs",
+           "k_dimer_expand", "k_dimer_ends")
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n-seq", type=int, default=1_000_000, help="sequences per GPU")
     ap.add_argument("--n-col", type=int, default=600)
-    ap.add_argument("--cpu-sample-seqs", type=int, default=50000)
+    ap.add_argument("--cpu-sample-seqs", type=int, default=20000)
     ap.add_argument("--cpu-sample-windows", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--parity-seqs", type=int, default=1 << 18, help="rows of the untimed sharded-parity check (N>1)")
     return ap.parse_args()
+
+
+def host_cores() -> int:
+    """the cores this process may run on (cgroup / affinity aware: os.cpu_count() over-reports inside a lease)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -69,7 +84,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append(f)
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.1)
 
     def summary(self):
         if not self.rows:
@@ -81,13 +96,13 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows)}
 
 
-def scan_traffic():
-    """DRAM bytes (read + write) of one k_scan launch from the committed `ncu --set full` capture"""
-    path = os.path.join(ROOT, "profiles", "k_scan_traffic.json")
+def kernel_traffic():
+    """DRAM bytes (read + write) per launch of the profiled kernels, from the committed `ncu --set full` captures"""
+    path = os.path.join(ROOT, "profiles", "r02_traffic.json")
     if os.path.exists(path):
         with open(path) as fh:
-            return json.load(fh)["traffic_bytes_per_launch"]
-    return None
+            return json.load(fh)
+    return {}
 
 
 def peaks():
@@ -99,9 +114,12 @@ def peaks():
 
 
 # ----------------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port (the Python reference cannot travel to the GPU box)
+# CPU arm.  The reference is a set of Python scripts: in the build container (where /root/reference exists) the live
+# NN_degenerate.get_primers is timed (kind "live"); on the GPU box, where the reference cannot travel, its restatement
+# oracle/mp_oracle.py (kind "port", pinned to the live reference by tests/golden/) runs the same windows.
 # ----------------------------------------------------------------------------------------------------------
 _CPU_DATA = {}
+REF_CORE = "/root/reference/scripts/multiPrime-core_V20.py"
 
 
 def _oracle_window(p):
@@ -114,25 +132,68 @@ def _oracle_window(p):
     return len(trace)
 
 
-def cpu_sample(n_seq: int, n_col: int, n_windows: int, procs: int):
-    """oracle over a bounded sample: the first n_seq synthetic sequences, n_windows windows spread over the region.
-    Returns (evals, seconds).  Windows are dealt to `procs` forked workers (the reference itself is single-process:
-    its pool is inert, core:1143; this is the best case for the CPU side)."""
+def _live_window(p):
+    """one window through the live reference class (mis_primer_check calls counted by wrapping the method)"""
+    app = _CPU_DATA["live"]
+    calls = [0]
+    orig = app.mis_primer_check
+
+    def wrapped(*a):
+        calls[0] += 1
+        return orig(*a)
+
+    app.mis_primer_check = wrapped
+    try:
+        app.get_primers(app.seq_dict, p)
+        app.resQ.get()
+    finally:
+        app.mis_primer_check = orig
+    return calls[0]
+
+
+def cpu_prepare(n_seq: int, n_col: int, live: bool):
     from multiprime_b200 import synth
     from oracle import mp_oracle as o
-    if _CPU_DATA.get("key") != (n_seq, n_col):
-        codes = synth.synth_codes(n_seq, n_col)
-        _CPU_DATA.update(key=(n_seq, n_col), ids=synth.seq_ids(n_seq), seqs=synth.codes_to_strings(codes))
-    start, stop = o.region(_CPU_DATA["seqs"], 0.8)
+    key = (n_seq, n_col, live)
+    if _CPU_DATA.get("key") == key:
+        return
+    codes = synth.synth_codes(n_seq, n_col)
+    ids, seqs = synth.seq_ids(n_seq), synth.codes_to_strings(codes)
+    _CPU_DATA.clear()
+    _CPU_DATA.update(key=key, ids=ids, seqs=seqs, region=o.region(seqs, 0.8))
+    if live:
+        import importlib.util
+        import tempfile
+        import warnings
+        warnings.filterwarnings("ignore")
+        spec = importlib.util.spec_from_file_location("mpcore_live", REF_CORE)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        tmp = tempfile.mkdtemp()
+        fa = os.path.join(tmp, "in.fa")
+        synth.write_fasta(fa, codes)
+        _CPU_DATA["live"] = mod.NN_degenerate(seq_file=fa, primer_length=K, coverage=0.8, number_of_dege_bases=DNUM,
+                                              score_of_dege_bases=DEG, product_len=100, position="1,2,-1",
+                                              variation=VAR, raw_entropy_threshold=3.6, distance=4, GC="0.2,0.7",
+                                              nproc=1, outfile=os.path.join(tmp, "x.out"))
+
+
+def cpu_sample(n_seq: int, n_col: int, n_windows: int, procs: int, live: bool = False):
+    """the CPU implementation over a bounded sample: the first n_seq synthetic sequences, n_windows windows spread over
+    the region.  Returns (evals, seconds).  Windows are dealt to `procs` forked workers (the reference itself is
+    single-process: its pool is inert, core:1143; this is the best case for the CPU side)."""
+    cpu_prepare(n_seq, n_col, live)
+    start, stop = _CPU_DATA["region"]
     all_pos = list(range(start, stop - K))
     pos = [all_pos[int(i * (len(all_pos) - 1) / max(1, n_windows - 1))] for i in range(n_windows)]
+    fn = _live_window if live else _oracle_window
     t0 = time.perf_counter()
     if procs <= 1:
-        calls = [_oracle_window(p) for p in pos]
+        calls = [fn(p) for p in pos]
     else:
         import multiprocessing as mp
         with mp.get_context("fork").Pool(procs) as pool:
-            calls = pool.map(_oracle_window, pos, chunksize=1)
+            calls = pool.map(fn, pos, chunksize=1)
     dt = time.perf_counter() - t0
     return sum(calls) * n_seq, dt
 
@@ -141,30 +202,64 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = host_cores()
+    live = os.path.exists(REF_CORE)
     n_windows = max(args.cpu_sample_windows, 2 * cores)            # keep every core busy
     procs = min(cores, n_windows)
     vals = []
     for i in range(args.warmup + args.steps):
-        ev, dt = cpu_sample(args.cpu_sample_seqs, args.n_col, n_windows, procs)
+        ev, dt = cpu_sample(args.cpu_sample_seqs, args.n_col, n_windows, procs, live)
         if i >= args.warmup:
             vals.append((ev, dt))
-    ev = sum(v[0] for v in vals)
-    dt = sum(v[1] for v in vals)
-    value = ev / dt
-    sample = "oracle port (oracle/mp_oracle.py), first %d synthetic sequences x %d windows spread over the region, " \
-             "%d worker processes" % (args.cpu_sample_seqs, n_windows, procs)
+        if i == 0 and dt > 40:                                      # a slow host: one warm-up pass is enough
+            args.warmup = 1
+    per_step = [v[0] / v[1] for v in vals]
+    value = statistics.median(per_step)
+    sample = "%s, first %d synthetic sequences x %d windows spread over the region, %d worker processes on %d usable " \
+             "cores; median of %d steps (min %.3g, max %.3g evals/s)" % (
+                 "live reference multiPrime-core_V20.py NN_degenerate.get_primers" if live else
+                 "oracle port (oracle/mp_oracle.py; the Python reference cannot travel to the GPU box)",
+                 args.cpu_sample_seqs, n_windows, procs, cores, len(vals), min(per_step), max(per_step))
     line = {"impl": "reference", "metric": "candidate_x_sequence_evals_per_sec", "value": value, "unit": "evals/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000 * statistics.median(v[1] for v in vals),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": "synthetic MSA %dx%d k=%d d<=%d v<=%d (bounded sample)" %
                        (args.n_seq, args.n_col, K, DEG, VAR)},
-            "cpu_baseline": {"value": value, "unit": "evals/s", "cores": procs, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "evals/s", "cores": procs, "kind": "reference" if live else "port",
+                             "sample": sample},
             "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
 # ----------------------------------------------------------------------------------------------------------
+def sharded_parity(args, rank, local, world, comm, stream):
+    """untimed strong-scaling check (N > 1): the SAME alignment once on one rank without a communicator and once
+    sharded over all ranks with NCCL — rows and call traces must be identical"""
+    import numpy as np
+    import torch.distributed as dist
+    from multiprime_b200 import core, synth
+    n, L = args.parity_seqs, args.n_col
+    codes = synth.synth_codes(n, L, seed=77)
+    ids = synth.seq_ids(n)
+    lo, hi = rank * n // world, (rank + 1) * n // world
+    kw = dict(PARAMS)
+    app = core.NN_degenerate(seq_file=None, outfile="", alignment=(ids[lo:hi], codes[lo:hi], np.full(hi - lo, L, np.int32)),
+                             device=local, sidecars=False, stream=stream, comm=comm, row0=lo, **kw)
+    pos = list(range(app.start_position, app.stop_position - K))
+    got = sorted((r["row"], r["trace"]) for r in app.design(pos))
+    app.close()
+    out = None
+    if rank == 0:
+        one = core.NN_degenerate(seq_file=None, outfile="", alignment=(ids, codes, np.full(n, L, np.int32)), device=local,
+                                 sidecars=False, stream=stream, **kw)
+        want = sorted((r["row"], r["trace"]) for r in one.design(pos))
+        one.close()
+        out = {"sequences": n, "windows": len(pos), "rows": len(want), "equal": got == want}
+    dist.barrier()
+    return out
+
+
 def run_b200(args):
     from multiprime_b200 import core, synth
 
@@ -173,7 +268,7 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     n_seq, n_col = args.n_seq, args.n_col
     # synthetic input first: the generator forks worker processes, which must happen before CUDA / NCCL threads exist
-    codes = synth.synth_codes_parallel(n_seq, n_col, row0=rank * n_seq, procs=max(1, (os.cpu_count() or 8) // world))
+    codes = synth.synth_codes_parallel(n_seq, n_col, row0=rank * n_seq, procs=max(1, host_cores() // world))
     packed = core.pack4(codes)
     del codes
     import torch
@@ -192,6 +287,9 @@ def run_b200(args):
         comm = TorchComm(torch.device("cuda", local))
 
     def make_app():
+        # sidecars=False: no JSON side files (they list sequence ids per uncovered haplotype and do not scale to 10^6
+        # sequences); keep_bits=True: the per-sequence F / R non-cover and gap-row bit vectors of every chosen primer ARE
+        # produced (in HBM, where the pairing step reads them)
         return core.NN_degenerate(seq_file=None, outfile="", packed=(ids, packed_pinned, n_col, None), device=local,
                                   sidecars=False, want_trace=False, keep_bits=True, stream=stream, comm=comm,
                                   row0=rank * n_seq, **PARAMS)
@@ -200,6 +298,8 @@ def run_b200(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    parity = sharded_parity(args, rank, local, world, comm, stream) if world > 1 else None
 
     app = make_app()
     positions = list(range(app.start_position, app.stop_position - K))
@@ -249,12 +349,7 @@ def run_b200(args):
         if name == "value":
             sampler.stop_flag.set()
             results["launches"] = app.ctx.launches - launches0
-            results["scan"] = app.ctx.profile_read("k_cscan")
-            results["kernel_ms"] = {kn: app.ctx.profile_read(kn)[0] / args.steps for kn in
-                                    ("k_prefilter", "k_prefilter_sums", "k_hist", "k_hist_summary", "k_hist_match",
-                                     "k_cscan", "k_cscan_plan", "k_cscan_special", "k_walk_advance", "k_walk_seed",
-                                     "k_tm", "k_dimer_pairs", "k_dimer_expand", "k_dimer_ends")}
-            results["hist"] = app.ctx.profile_read("k_hist")
+            results["prof"] = {kn: app.ctx.profile_read(kn) for kn in KERNELS}
             results["evals_per_step"] = app.stats["evals"] / args.steps
             results["scan_calls"] = app.stats["scan_calls"] / args.steps
             results["candidates"] = app.stats["candidates"] / args.steps
@@ -269,8 +364,27 @@ def run_b200(args):
     value = evals_all / (ms_step / 1000)
     e2e_ms = results["e2e"]["ms"] / args.steps
     peak, peak_src = peaks()
-    scan_ms, scan_n, scan_units = results["scan"]
-    achieved = scan_units * BYTES_PER_EVAL / (scan_ms / 1000) / 1e9 if scan_ms > 0 else 0.0
+    prof = results["prof"]
+    traffic = kernel_traffic()
+
+    def roofline_of(kn):
+        ms, n, units = prof[kn]
+        per_unit = BYTES_PER_EVAL if kn == "k_cscan" else BYTES_PER_KMER
+        ach = units * per_unit / (ms / 1000) / 1e9 if ms > 0 else 0.0
+        return {"bound": "hbm", "kernel": kn, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": traffic.get(kn), "peak_source": peak_src, "launches": n,
+                "avg_launch_ms": ms / max(1, n), "units_in_launches": units, "bytes_per_unit": per_unit,
+                "ms_per_step": ms / args.steps}
+
+    big = max(("k_prefilter", "k_hist", "k_cscan"), key=lambda kn: prof[kn][0])
+    roof = roofline_of(big)
+    roof["note"] = (
+        "dominant kernel of the step by CUDA-event time. achieved = algorithmic bytes (SURVEY.md 8d: k/2 B per (window, "
+        "sequence) k-mer for the window passes, k/2 + 0.25 B per candidate x sequence evaluation for the scan) / "
+        "event-timed kernel time; traffic = dram read+write bytes of one launch (ncu --set full, profiles/). The "
+        "algorithmic figure assumes no reuse: the window passes cut up to 32 windows out of every loaded word and the "
+        "column scan re-reads plane rows from L2, so real DRAM traffic is far below it and a fraction above 1 is "
+        "reuse, not a faster-than-HBM kernel; these kernels are bound by L2 atomics / integer issue (see profiles/README.md)")
     line = {
         "metric": "candidate_x_sequence_evals_per_sec", "value": value, "unit": "evals/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
@@ -278,35 +392,32 @@ def run_b200(args):
         "config": {"workload": "synthetic MSA %dx%d per GPU (multiprime_b200/synth.py seed 20240923), k=%d, -n %d -d %d "
                                "-v %d, %d windows, %d rows out" % (n_seq, n_col, K, DNUM, DEG, VAR, len(positions),
                                                                   results["value"]["rows"]),
-                   "parallelism": "sequence shards x%d, all-reduce of coverage counts per scan round" % world,
-                   "l2": "inputs (%.0f MB of bit-planes + GB-sized haplotype tables) exceed the 126 MB L2" %
+                   "parallelism": "sequence shards x%d: windows owned round-robin (all-to-all of haplotype entries), "
+                                  "all-reduce of the coverage-count vector per scan round" % world,
+                   "l2": "inputs (2 x %.0f MB of bit-planes + GB-sized haplotype tables) exceed the 126 MB L2" %
                          (n_seq * n_col / 2 / 1e6),
-                   "evals_per_step": evals_all, "scan_launches_per_step": results["scan_calls"],
+                   "evals_per_step": evals_all, "scan_rounds_per_step": results["scan_calls"],
                    "scan_candidates_per_step": results["candidates"]},
         "clocks": sampler.summary(),
         "e2e": {"value": evals_all / (e2e_ms / 1000), "unit": "evals/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": int(results["value"]["rows"] * 120), "ms_per_step": e2e_ms,
                 "setup_ms_per_step": {kk: round(vv / args.steps, 2) for kk, vv in e2e_init.items()}},
         "gpu_launches": int(results["launches"]),
-        "roofline": {"bound": "hbm", "kernel": "k_cscan", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": scan_traffic(), "peak_source": peak_src,
-                     "launches": scan_n, "avg_launch_ms": scan_ms / max(1, scan_n),
-                     "evals_in_launches": scan_units,
-                     "note": "achieved = scanned candidate x sequence pairs x %.2f B / event-timed k_scan time; traffic = "
-                             "dram read+write bytes of one launch (ncu --set full, profiles/): far BELOW the algorithmic "
-                             "bytes because a loaded window serves all candidates of its window and neighbouring windows "
-                             "share words through L1/L2 - the kernel is bound by integer issue (ncu: 77%% issue active, "
-                             "2.7%% of peak DRAM throughput)" % BYTES_PER_EVAL},
-        "kernels": {"k_hist_ms_per_step": results["hist"][0] / args.steps,
-                    "k_scan_ms_per_step": scan_ms / args.steps,
-                    "ms_per_step": {kk: round(vv, 3) for kk, vv in results["kernel_ms"].items()}},
+        "roofline": roof,
+        "roofline_scan": roofline_of("k_cscan"),
+        "kernels": {"k_scan_ms_per_step": prof["k_cscan"][0] / args.steps,
+                    "ms_per_step": {kn: round(prof[kn][0] / args.steps, 3) for kn in KERNELS}},
         "host_phases_ms_per_step": results["phases"],
     }
+    if parity is not None:
+        line["sharded_parity"] = parity
     if not args.no_cpu_baseline and world == 1:       # the CPU baseline is timed on rank 0 at N = 1 only
-        evc, dtc = cpu_sample(args.cpu_sample_seqs, n_col, args.cpu_sample_windows, 1)
-        line["cpu_baseline"] = {"value": evc / dtc, "unit": "evals/s", "cores": 1, "kind": "port",
-                                "sample": "oracle/mp_oracle.py, first %d synthetic sequences x %d windows, %.1f s" %
-                                          (args.cpu_sample_seqs, args.cpu_sample_windows, dtc)}
+        live = os.path.exists(REF_CORE)
+        evc, dtc = cpu_sample(args.cpu_sample_seqs, n_col, args.cpu_sample_windows, 1, live)
+        line["cpu_baseline"] = {"value": evc / dtc, "unit": "evals/s", "cores": 1, "kind": "reference" if live else "port",
+                                "sample": "%s, first %d synthetic sequences x %d windows, %.1f s" %
+                                          ("multiPrime-core_V20.py" if live else "oracle/mp_oracle.py",
+                                           args.cpu_sample_seqs, args.cpu_sample_windows, dtc)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -117,6 +117,12 @@ int mpb_hist_counts(mpb_hist* h, int64_t* gap_n, int64_t* n_iupac_gap, int64_t* 
 int mpb_hist_export(mpb_hist* h, const uint8_t* sel, const int64_t* win_off, uint64_t* keys_hd, uint32_t* cnt_hd,
                     uint64_t* first_hd);
 
+/* The same with explicit placement: the entries of window sel_idx[i] (host array, any order) land in
+ * [start[i], start[i] + room[i]) of the hd arrays (total elements).  A sequence shard lays its windows out by owning
+ * rank so that one all-to-all moves them.  Does not synchronise when the outputs are device memory. */
+int mpb_hist_export_at(mpb_hist* h, int32_t n_sel, const int32_t* sel_idx, const int64_t* start, const int64_t* room,
+                       int64_t total, uint64_t* keys_hd, uint32_t* cnt_hd, uint64_t* first_hd);
+
 /* Insert foreign (key, count, first) triples into the tables (multi-GPU merge of per-rank tables).
  * win_off (host, nw+1) delimits the triples of each window inside the hd arrays. */
 int mpb_hist_merge(mpb_hist* h, const int64_t* win_off, const uint64_t* keys_hd, const uint32_t* cnt_hd,

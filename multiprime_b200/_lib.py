@@ -55,6 +55,7 @@ SIGNATURES = {
     "mpb_tm": (C.c_int, [_P, _P, C.c_int, C.c_int64, _P, _P, _P, _P]),
     "mpb_walk": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int32, _P, _P, _P, _P, _P, _P,
                            _P, _P, _P, _P, _P, C.c_int64, _P, _P, _P]),
+    "mpb_hist_export_at": (C.c_int, [_P, C.c_int32, _P, _P, _P, C.c_int64, _P, _P, _P]),
     "mpb_hist_merge_segments": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P]),
     "mpb_hist_create_empty": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int32, C.c_int, C.POINTER(_P)]),
     "mpb_hist_add_counts": (C.c_int, [_P, _P, _P]),
@@ -241,14 +242,31 @@ class DevBuf:
 class Context:
     """one CUDA device + stream"""
 
+    _shared = {}
+
     def __init__(self, device: int = 0, stream: int | None = None):
         lib = load()
         h = C.c_void_p()
         check(lib.mpb_ctx_create(device, C.byref(h)))
         self.h = h
         self.device = device
+        self.is_shared = False
         if stream is not None:
             self.set_stream(stream)
+
+    @classmethod
+    def shared(cls, device: int = 0, stream: int | None = None) -> "Context":
+        """the process-wide context of (device, stream): creating one costs a pinned allocation and a stream, which a
+        caller that designs many alignments in a row (the Snakemake pipeline calls the CLI once per cluster, a server
+        would not) should not pay per call.  close() leaves it open."""
+        import threading
+        key = (device, stream, threading.get_ident())
+        ctx = cls._shared.get(key)
+        if ctx is None or not ctx.h:
+            ctx = cls(device, stream)
+            ctx.is_shared = True
+            cls._shared[key] = ctx
+        return ctx
 
     def set_stream(self, stream: int):
         check(load().mpb_ctx_set_stream(self.h, C.c_void_p(stream)))
@@ -298,7 +316,7 @@ class Context:
         return out
 
     def close(self):
-        if self.h:
+        if self.h and not self.is_shared:
             load().mpb_ctx_destroy(self.h)
             self.h = None
 
@@ -535,6 +553,23 @@ class Hist:
                 cnt = np.ascontiguousarray(cnt, dtype=np.uint32)
                 first = np.ascontiguousarray(first, dtype=np.uint64)
             check(load().mpb_hist_merge(self.h, ptr(win_off), ptr(keys), ptr(cnt), ptr(first)))
+
+    def export_at(self, order, counts, comm=None):
+        """entries of the windows `order` (batch indices, in this order), counts[i] of window order[i] -> (keys, cnt,
+        first) compact arrays; device tensors allocated through comm when it is on the GPU, numpy otherwise"""
+        order = np.ascontiguousarray(order, dtype=np.int32)
+        room = np.ascontiguousarray(counts, dtype=np.int64)
+        start = np.zeros(len(order), np.int64)
+        start[1:] = np.cumsum(room)[:-1]
+        total = int(room.sum())
+        if comm is not None:
+            keys, cnt, first = comm.empty_dev(total, np.uint64), comm.empty_dev(total, np.uint32), comm.empty_dev(total, np.uint64)
+        else:
+            keys, cnt, first = np.empty(total, np.uint64), np.empty(total, np.uint32), np.empty(total, np.uint64)
+        if total:
+            check(load().mpb_hist_export_at(self.h, len(order), ptr(order), ptr(start), ptr(room), total, ptr(keys),
+                                            ptr(cnt), ptr(first)))
+        return keys, cnt, first
 
     def merge_segments(self, seg_off, keys, cnt, first):
         """merge() for m * nw segments: segment s belongs to window s % nw (keys / cnt / first: numpy or device tensors)"""

@@ -239,7 +239,8 @@ class NN_degenerate(object):
         self.total_sequence_number = int(self.comm.allreduce_sum(np.array([self.n_local], np.int64))[0])
         self.lens = lens if lens is not None else np.full(len(self.ids), self.n_col, np.int32)
         backend = _backend or _lib                # tests inject tests/fake_device.py to exercise the host logic
-        self.ctx = backend.Context(device, stream)
+        self.ctx = backend.Context.shared(device, stream) if hasattr(backend.Context, "shared") else \
+            backend.Context(device, stream)
         self.msa = backend.Msa(self.ctx, packed4, len(self.ids), self.n_col,
                                lens=None if (self.lens == self.n_col).all() else self.lens)
         if row0:
@@ -276,49 +277,57 @@ class NN_degenerate(object):
         return self.raw_entropy_threshold * 0.9
 
     # -- entropy (core:602-614) ----------------------------------------------------------------------------
+    def _exception_records(self, hist) -> np.ndarray:
+        """gap rows that hold IUPAC cells are not in the device table (their raw k-mer needs 4 bits per cell): one record
+        (first order, count, window, 32 raw cells) per such (window, local sequence), cut from the host copy"""
+        k = self.primer_length
+        exc_w, exc_s = self._exceptions(hist)
+        rec = np.zeros((len(exc_w), 3 + 32), np.int64)
+        if len(exc_w):
+            exc_pos = np.asarray(hist.win_pos)[exc_w]
+            cells, got = _lib.window_cells(self._packed4, self.lens, self.n_col, k, exc_s, exc_pos)
+            if (got < k).any():
+                raise ValueError("a sequence is too short to supply a %d-mer at window %d"
+                                 % (k, int(exc_pos[np.argmax(got < k)])))
+            rec[:, 0] = (self.row0 + exc_s.astype(np.int64)) << 16
+            rec[:, 1] = 1
+            rec[:, 2] = exc_w
+            rec[:, 3:] = cells
+        return rec
+
+    def _group_exception_records(self, rec) -> dict:
+        """{window: [(first order, count)]}: the records grouped by (window, raw k-mer)"""
+        k = self.primer_length
+        cache = {}
+        if len(rec):
+            # the k 4-bit cells are folded into two integers, rows sorted, runs reduced
+            cells = rec[:, 3:]
+            lo = np.zeros(len(rec), np.int64)
+            hi = np.zeros(len(rec), np.int64)
+            for j in range(k):
+                if j < 15:
+                    lo |= cells[:, j] << (4 * j)
+                else:
+                    hi |= cells[:, j] << (4 * (j - 15))
+            order = np.lexsort((lo, hi, rec[:, 2]))
+            w_s, lo_s, hi_s = rec[order, 2], lo[order], hi[order]
+            new_run = np.ones(len(rec), bool)
+            new_run[1:] = (w_s[1:] != w_s[:-1]) | (lo_s[1:] != lo_s[:-1]) | (hi_s[1:] != hi_s[:-1])
+            starts = np.nonzero(new_run)[0]
+            first = np.minimum.reduceat(rec[order, 0], starts)
+            count = np.add.reduceat(rec[order, 1], starts)
+            win = w_s[starts]
+            cuts = np.nonzero(np.diff(win))[0] + 1
+            for a, b in zip(np.concatenate([[0], cuts]).tolist(), np.concatenate([cuts, [len(win)]]).tolist()):
+                cache[int(win[a])] = list(zip(first[a:b].tolist(), count[a:b].tolist()))
+        return cache
+
     def _iupac_gap_groups(self, hist, wi):
-        """gap rows that hold IUPAC cells are not in the device table (their raw k-mer needs 4 bits per cell):
-        group the few of them by raw k-mer here -> [(first order, count)] of window wi"""
+        """[(first order, count)] of the gap rows of window wi that hold IUPAC cells (a sharded run fills the cache in
+        _exchange, where the shards' records travel with the window counters)"""
         cache = getattr(hist, "_iupac_groups", None)
         if cache is None:
-            k = self.primer_length
-            exc_w, exc_s = self._exceptions(hist)
-            rec = np.zeros((len(exc_w), 3 + 32), np.int64)          # first, count, window, raw cells
-            if len(exc_w):
-                exc_pos = np.asarray(hist.win_pos)[exc_w]
-                cells, got = _lib.window_cells(self._packed4, self.lens, self.n_col, k, exc_s, exc_pos)
-                if (got < k).any():
-                    raise ValueError("a sequence is too short to supply a %d-mer at window %d"
-                                     % (k, int(exc_pos[np.argmax(got < k)])))
-                rec[:, 0] = (self.row0 + exc_s.astype(np.int64)) << 16
-                rec[:, 1] = 1
-                rec[:, 2] = exc_w
-                rec[:, 3:] = cells
-            if self.comm.world > 1:                                  # shards exchange their records as plain arrays
-                rec = self.comm.allgather_concat(rec.reshape(-1))[0].reshape(-1, 35)
-            cache = {}
-            if len(rec):
-                # group by (window, raw k-mer): the k 4-bit cells are folded into two integers, rows sorted, runs reduced
-                cells = rec[:, 3:]
-                lo = np.zeros(len(rec), np.int64)
-                hi = np.zeros(len(rec), np.int64)
-                for j in range(k):
-                    if j < 15:
-                        lo |= cells[:, j] << (4 * j)
-                    else:
-                        hi |= cells[:, j] << (4 * (j - 15))
-                order = np.lexsort((lo, hi, rec[:, 2]))
-                w_s, lo_s, hi_s = rec[order, 2], lo[order], hi[order]
-                new_run = np.ones(len(rec), bool)
-                new_run[1:] = (w_s[1:] != w_s[:-1]) | (lo_s[1:] != lo_s[:-1]) | (hi_s[1:] != hi_s[:-1])
-                starts = np.nonzero(new_run)[0]
-                first = np.minimum.reduceat(rec[order, 0], starts)
-                count = np.add.reduceat(rec[order, 1], starts)
-                win = w_s[starts]
-                cuts = np.nonzero(np.diff(win))[0] + 1
-                for a, b in zip(np.concatenate([[0], cuts]).tolist(), np.concatenate([cuts, [len(win)]]).tolist()):
-                    cache[int(win[a])] = list(zip(first[a:b].tolist(), count[a:b].tolist()))
-            hist._iupac_groups = cache
+            cache = hist._iupac_groups = self._group_exception_records(self._exception_records(hist))
         return cache.get(wi, [])
 
     def _entropy_exact(self, table, ti, wi, n_unique, hist=None):
@@ -454,14 +463,8 @@ class NN_degenerate(object):
         lap("prefilter")
         if not positions:
             return []
-        if comm.world > 1:
-            # sequence shards: rank r OWNS the windows with (index mod world) == r; the batch is laid out owner-major so
-            # that a shard's table entries leave in one contiguous piece per destination
-            order = sorted(range(len(positions)), key=lambda i: (i % comm.world, i))
-            positions = [positions[i] for i in order]
-            owner = np.array([i % comm.world for i in order], np.int32)
-        else:
-            owner = np.zeros(len(positions), np.int32)
+        # sequence shards: rank r OWNS the windows with (batch index mod world) == r
+        owner = (np.arange(len(positions)) % comm.world).astype(np.int32)
         with self.msa.hist(k, v, positions, self._table_log2cap(k, self.n_local)) as hist:
             lap("hist_build")
             own = None
@@ -518,74 +521,86 @@ class NN_degenerate(object):
 
     def _exchange(self, hist, positions, owner):
         """Sequence-sharded run: every per-window quantity is a sum over sequences.  Gap counters are
-        all-reduced; the haplotype entries of every window travel to the window's OWNER (one all-to-all), which merges
+        summed; the haplotype entries of every window travel to the window's OWNER (one all-to-all), which merges
         them into its own table, takes the window statistics and tensors, and the small per-window results are
         all-gathered: every rank ends up with the same `st` for all windows and takes identical decisions, while the
-        table work is divided by the world size."""
+        table work is divided by the world size.  Two host collectives (counters + exception rows; per-window
+        results) and one device all-to-all per array."""
         comm, N, k, v = self.comm, self.total_sequence_number, self.primer_length, self.variation
         world, rank, nw = comm.world, comm.rank, len(positions)
+        ph = self.stats.setdefault("phase_ms", {})
+        tick = [time.perf_counter()]
+
+        def lap(name):
+            now = time.perf_counter()
+            ph[name] = ph.get(name, 0.0) + 1000 * (now - tick[0])
+            tick[0] = now
+
         gap_local, iupac_local, n_ent = hist.counts()
-        both = comm.allreduce_sum(np.concatenate([gap_local, iupac_local]))
-        gap_n, iupac_gap = both[:nw], both[nw:]
+        # collective 1: per-window counters of every shard + the records of the gap rows holding IUPAC cells
+        head = np.concatenate([gap_local, iupac_local, n_ent]).astype(np.int64)
+        flat, lens_r = comm.allgather_concat(np.concatenate([head, self._exception_records(hist).reshape(-1)]))
+        starts = np.concatenate([[0], np.cumsum(lens_r)])
+        heads = np.stack([flat[starts[r]:starts[r] + 3 * nw] for r in range(world)]).reshape(world, 3, nw)
+        hist._iupac_groups = self._group_exception_records(
+            np.concatenate([flat[starts[r] + 3 * nw:starts[r + 1]] for r in range(world)]).reshape(-1, 35))
+        gap_n, iupac_gap = heads[:, 0].sum(axis=0), heads[:, 1].sum(axis=0)
+        lap("x_counters")
         gap_fail = np.array([round(int(g) / N, 2) >= (1 - self.coverage) for g in gap_n])
         travel = ~gap_fail
-        n_send = np.where(travel, n_ent, 0).astype(np.int64)
-        sizes_all, _ = comm.allgather_concat(n_send)                      # world x nw entry counts
-        sizes_all = sizes_all.reshape(world, nw)
-        mine = np.nonzero(owner == rank)[0]                               # my windows (ascending batch index)
-        send_counts = np.array([int(n_send[owner == r].sum()) for r in range(world)], np.int64)
+        sizes_all = np.where(travel[None, :], heads[:, 2], 0).astype(np.int64)     # world x nw entry counts
+        mine = np.nonzero(owner == rank)[0]                                        # my windows (ascending batch index)
+        order = np.concatenate([np.nonzero(owner == r)[0] for r in range(world)])   # owner-major export order
+        send_counts = np.array([int(sizes_all[rank, owner == r].sum()) for r in range(world)], np.int64)
         recv_counts = sizes_all[:, mine].sum(axis=1).astype(np.int64)
         on_gpu = getattr(comm, "on_gpu", False) and hasattr(hist, "export_dev")
         if on_gpu:                                 # entries stay in HBM: export -> NCCL all-to-all -> merge
-            _, keys, cnt, first = hist.export_dev(travel.astype(np.uint8), n_ent, comm)
+            keys, cnt, first = hist.export_at(order, sizes_all[rank, order], comm)
             rk, rc, rf = (comm.alltoall_dev(t, send_counts, recv_counts) for t in (keys, cnt, first))
         else:
-            _, keys, cnt, first = hist.export(travel.astype(np.uint8), n_ent)
+            keys, cnt, first = hist.export_at(order, sizes_all[rank, order])
             rk, rc, rf = (comm.alltoall(a, send_counts, recv_counts) for a in (keys, cnt, first))
+        lap("x_alltoall")
         # segment offsets of the received entries: source rank major, my windows inside
         seg = np.concatenate([[0], np.cumsum(sizes_all[:, mine].reshape(-1))]).astype(np.int64)
         my_pos = [positions[i] for i in mine]
         log2cap = self._table_log2cap(k, N)
         if log2cap == 0:
             log2cap = max(6, int(math.ceil(math.log2(2 * N + 64))))
+        per = int(np.ceil(nw / world))
+        fields = [("ent", 4, np.float64), ("nuniq", 3, np.int64), ("mm_key", 1, np.uint64), ("mm_cnt", 1, np.int64),
+                  ("mm_first", 1, np.uint64), ("freq", 4 * k, np.int64), ("nn", 16 * (k - 1), np.int64)]
+        width = 1 + sum(f[1] for f in fields)
         own = None
         while True:
-            failed = 0
+            rec = np.zeros((per, width), np.int64)
             if len(mine):
                 own = self.msa.hist(k, v, my_pos, log2cap, empty=True)
                 try:
                     own.merge_segments(seg, rk, rc, rf)
+                    own.add_counts(gap_n[mine], iupac_gap[mine])
+                    st_own = own.summary()
+                    c0 = 1
+                    for name, w, dt in fields:
+                        rec[:len(mine), c0:c0 + w] = np.ascontiguousarray(st_own[name]).reshape(len(mine), w).view(np.int64)
+                        c0 += w
                 except _lib.MpbError as exc:
                     if exc.code != -4:
                         raise
-                    failed = 1
-            # a full table on one rank is a collective event: everybody rebuilds with doubled owner tables
-            if int(comm.allreduce_sum(np.array([failed], np.int64))[0]) == 0:
+                    rec[:, 0] = 1              # a full table on one rank is a collective event (column 0 = failed)
+            lap("x_merge_summary")
+            # collective 2: the per-window results of every owner (fixed-size records, padded to the maximum)
+            rec_all, _ = comm.allgather_concat(rec.reshape(-1))
+            lap("x_results")
+            rec_all = rec_all.reshape(world, per, width)
+            if not rec_all[:, :, 0].any():
                 break
-            if own is not None:
+            if own is not None:                # everybody rebuilds with doubled owner tables
                 own.close()
                 own = None
             log2cap += 1
-        if own is not None:
-            own.add_counts(gap_n[mine], iupac_gap[mine])
-            st_own = own.summary()
-        else:
-            st_own = None
-        # all-gather the per-window results (fixed-size records, windows per rank padded to the maximum)
-        per = int(np.ceil(nw / world))
-        fields = [("ent", 4, np.float64), ("nuniq", 3, np.int64), ("mm_key", 1, np.uint64), ("mm_cnt", 1, np.int64),
-                  ("mm_first", 1, np.uint64), ("freq", 4 * k, np.int64), ("nn", 16 * (k - 1), np.int64)]
-        width = sum(f[1] for f in fields)
-        rec = np.zeros((per, width), np.int64)
-        if st_own is not None:
-            c0 = 0
-            for name, w, dt in fields:
-                rec[:len(mine), c0:c0 + w] = np.ascontiguousarray(st_own[name]).reshape(len(mine), w).view(np.int64)
-                c0 += w
-        rec_all, _ = comm.allgather_concat(rec.reshape(-1))
-        rec_all = rec_all.reshape(world, per, width)
         st = {}
-        c0 = 0
+        c0 = 1
         for name, w, dt in fields:
             full = np.zeros((nw, w), dt)
             for r in range(world):
@@ -611,8 +626,6 @@ class NN_degenerate(object):
         comm = self.comm
         ent = st["ent"].astype(np.float64).copy()
         with_iupac = np.nonzero(alive & (st["n_iupac_gap"] > 0))[0].tolist()
-        if with_iupac or (comm.world > 1 and bool((st["n_iupac_gap"] > 0).any())):
-            self._iupac_gap_groups(hist, 0)                   # collective in a sharded run: every rank, same moment
         for wi in with_iupac:                                  # gap rows holding IUPAC cells
             for _, c in self._iupac_gap_groups(hist, wi):
                 ent[wi, 2] += c

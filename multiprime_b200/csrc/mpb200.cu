@@ -1077,48 +1077,71 @@ extern "C" void mpb_hist_free(mpb_hist* h) {
     delete h;
 }
 
-// copy the entries of the selected windows into one compact array: window w's entries land at win_off[w] + (their
-// position in the entry list); room for win_off[w+1] - win_off[w] of them
+// copy the entries of the selected windows into one compact array: window sel_idx[y]'s entries land at start[y] + (their
+// position in the entry list); room for room[y] of them
 __global__ void k_hist_export(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ cnt,
                               const uint64_t* __restrict__ first, const uint32_t* __restrict__ elist,
                               const unsigned long long* __restrict__ n_entries, int log2cap,
-                              const int32_t* __restrict__ sel_idx, const long long* __restrict__ win_off,
-                              uint64_t* __restrict__ ok, uint32_t* __restrict__ oc, uint64_t* __restrict__ of) {
+                              const int32_t* __restrict__ sel_idx, const long long* __restrict__ start,
+                              const long long* __restrict__ room, uint64_t* __restrict__ ok, uint32_t* __restrict__ oc,
+                              uint64_t* __restrict__ of) {
     const int wi = sel_idx[blockIdx.y];
     const uint64_t cap = 1ull << log2cap;
     const uint64_t base = (uint64_t)wi * cap;
     long long n = (long long)n_entries[wi];
-    const long long room = win_off[wi + 1] - win_off[wi];
-    if (n > room) n = room;
+    if (n > room[blockIdx.y]) n = room[blockIdx.y];
+    const long long o = start[blockIdx.y];
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const uint64_t slot = base + elist[base + i];
-        ok[win_off[wi] + i] = keys[slot];
-        oc[win_off[wi] + i] = cnt[slot];
-        of[win_off[wi] + i] = first[slot];
+        ok[o + i] = keys[slot];
+        oc[o + i] = cnt[slot];
+        of[o + i] = first[slot];
     }
+}
+
+// windows sel_idx[0..n_sel) (host) in THIS order: entries of window sel_idx[i] go to [start[i], start[i] + room[i])
+extern "C" int mpb_hist_export_at(mpb_hist* h, int32_t n_sel, const int32_t* sel_idx, const int64_t* start,
+                                  const int64_t* room, int64_t total, uint64_t* keys_hd, uint32_t* cnt_hd,
+                                  uint64_t* first_hd) {
+    if (!h || !sel_idx || !start || !room || !keys_hd || !cnt_hd || !first_hd) return fail(MPB_EINVAL, "NULL argument");
+    mpb_ctx* ctx = h->msa->ctx;
+    CK(cudaSetDevice(ctx->device));
+    for (int i = 0; i < n_sel; ++i)
+        if (sel_idx[i] < 0 || sel_idx[i] >= h->nw || start[i] < 0 || room[i] < 0 || start[i] + room[i] > total)
+            return fail(MPB_EINVAL, "bad placement of window %d", i);
+    if (n_sel < 1 || total <= 0) return 0;
+    InBuf si(ctx, sel_idx, (size_t)n_sel * 4), st(ctx, start, (size_t)n_sel * 8), rm(ctx, room, (size_t)n_sel * 8);
+    OutBuf ok(ctx, keys_hd, total * 8), oc(ctx, cnt_hd, total * 4), of(ctx, first_hd, total * 8);
+    if (si.rc || st.rc || rm.rc || ok.rc || oc.rc || of.rc) return MPB_ECUDA;
+    LAUNCH(ctx, k_hist_export, dim3(32, (unsigned)n_sel), 256, 0, h->keys, h->cnt, h->first, h->elist, h->n_entries,
+           h->log2cap, si.dev<int32_t>(), st.dev<long long>(), rm.dev<long long>(), ok.dev<uint64_t>(), oc.dev<uint32_t>(),
+           of.dev<uint64_t>());
+    CK(ok.finish());
+    CK(oc.finish());
+    CK(of.finish());
+    if (ok.is_host() || oc.is_host() || of.is_host()) CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
 }
 
 extern "C" int mpb_hist_export(mpb_hist* h, const uint8_t* sel, const int64_t* win_off, uint64_t* keys_hd,
                                uint32_t* cnt_hd, uint64_t* first_hd) {
     if (!h || !sel || !win_off || !keys_hd || !cnt_hd || !first_hd) return fail(MPB_EINVAL, "NULL argument");
-    mpb_ctx* ctx = h->msa->ctx;
-    CK(cudaSetDevice(ctx->device));
     std::vector<int32_t> idx;
+    std::vector<int64_t> start, room;
     for (int i = 0; i < h->nw; ++i) {
-        if (sel[i]) idx.push_back(i);
-        else if (win_off[i + 1] != win_off[i]) return fail(MPB_EINVAL, "win_off reserves room for unselected window %d", i);
+        if (sel[i]) {
+            idx.push_back(i);
+            start.push_back(win_off[i]);
+            room.push_back(win_off[i + 1] - win_off[i]);
+        } else if (win_off[i + 1] != win_off[i]) {
+            return fail(MPB_EINVAL, "win_off reserves room for unselected window %d", i);
+        }
     }
-    const int64_t total = win_off[h->nw];
-    if (idx.empty() || total <= 0) return 0;
-    InBuf si(ctx, idx.data(), idx.size() * 4), wo(ctx, win_off, (size_t)(h->nw + 1) * 8);
-    OutBuf ok(ctx, keys_hd, total * 8), oc(ctx, cnt_hd, total * 4), of(ctx, first_hd, total * 8);
-    if (si.rc || wo.rc || ok.rc || oc.rc || of.rc) return MPB_ECUDA;
-    LAUNCH(ctx, k_hist_export, dim3(32, (unsigned)idx.size()), 256, 0, h->keys, h->cnt, h->first, h->elist, h->n_entries,
-           h->log2cap, si.dev<int32_t>(), wo.dev<long long>(), ok.dev<uint64_t>(), oc.dev<uint32_t>(), of.dev<uint64_t>());
-    CK(ok.finish());
-    CK(oc.finish());
-    CK(of.finish());
-    CK(cudaStreamSynchronize(ctx->stream));
+    if (idx.empty()) return 0;
+    int rc = mpb_hist_export_at(h, (int32_t)idx.size(), idx.data(), start.data(), room.data(), win_off[h->nw], keys_hd,
+                                cnt_hd, first_hd);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(h->msa->ctx->stream));
     return 0;
 }
 

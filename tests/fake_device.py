@@ -34,6 +34,10 @@ class Context:
     def __init__(self, device=0, stream=None):
         self.launches = 0
 
+    @classmethod
+    def shared(cls, device=0, stream=None):
+        return cls(device, stream)
+
     def tm(self, seqs2bit, consts3, want_hs=False):
         tm, dh, ds = [], [], []
         for row in np.asarray(seqs2bit):
@@ -237,6 +241,18 @@ class Hist:
         out = self.stats()
         out["freq"], out["nn"] = self.tensors(np.ones(self.nw, np.uint8))
         return out
+
+    def export_at(self, order, counts, comm=None):
+        keys, cnt, first = [], [], []
+        for wi, n in zip(order, counts):
+            tab = self.tables[int(wi)]
+            assert n in (0, len(tab))
+            if n:
+                for key, (c, f) in tab.items():
+                    keys.append(key)
+                    cnt.append(c)
+                    first.append(f)
+        return np.array(keys, np.uint64), np.array(cnt, np.uint32), np.array(first, np.uint64)
 
     def merge_segments(self, seg_off, keys, cnt, first):
         for s in range(len(seg_off) - 1):

@@ -87,3 +87,18 @@ def test_two_ranks_equal_single(name, limit):
         assert (start, stop) == (case["start"], case["stop"])
         assert not bad, (rank, bad[:3])
         assert n_acc > 0
+
+
+@pytest.mark.parametrize("name,world", [("synth_iupac", 3), ("c3_tmsa", 4)])
+def test_window_owners_threads(name, world):
+    """window ownership with 3 and 4 shards (windows per owner differ by one, some owners idle on short batches): the
+    shards run on threads with the loop-back communicator and the stand-in device"""
+    from tests import fake_device
+    from tests.loopback_comm import run_shards
+    from tests.test_gpu_sharded import _shard_rows
+    res = run_shards(world, lambda rank, comm: _shard_rows(name, rank, world, comm, _backend=fake_device))
+    case = load_case(name)
+    for rank, (start, stop, bad, n_acc) in enumerate(res):
+        assert (start, stop) == (case["start"], case["stop"])
+        assert not bad, (rank, bad[:3])
+        assert n_acc > 0
