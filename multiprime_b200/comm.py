@@ -19,6 +19,9 @@ class NoComm:
     def allgather_object(self, obj):
         return [obj]
 
+    def allgather_fixed(self, arr):
+        return np.asarray(arr)[None]
+
     def alltoall(self, arr, send_counts, recv_counts):
         return arr
 
@@ -71,6 +74,15 @@ class TorchComm:
         out = [None] * self.world
         self.dist.all_gather_object(out, obj, group=self.group)
         return out
+
+    def allgather_fixed(self, arr):
+        """all-gather of equally shaped int64 / float64 arrays -> array of shape (world,) + arr.shape: one collective,
+        one copy to the device and one back (allgather_concat pays a size exchange and a copy per rank)"""
+        arr = np.ascontiguousarray(arr)
+        t = self._to(arr.reshape(-1).view(np.int64))
+        out = self.torch.empty(self.world * t.numel(), dtype=t.dtype, device=t.device)
+        self.dist.all_gather_into_tensor(out, t, group=self.group)
+        return out.cpu().numpy().view(arr.dtype).reshape((self.world,) + arr.shape)
 
     def alltoall(self, arr, send_counts, recv_counts):
         """variable-size all-to-all of a 1-d numpy array: send_counts[r] consecutive elements go to rank r; returns the

@@ -473,7 +473,7 @@ class NN_degenerate(object):
                     st, own, mine = self._exchange(hist, positions, owner)
                     lap("exchange")
                 else:
-                    st, mine = hist.summary(), None
+                    st, mine = hist.stats(), None        # tensors follow for the windows that pass the gates only
                     lap("summary")
                 out = self._gates_walk_finish(hist, own, mine, owner, st, positions, lap)
             finally:
@@ -496,7 +496,15 @@ class NN_degenerate(object):
         for wi, ent in self._entropies(hist, own, mine, owner, st, positions, alive):
             accepted.append((wi, positions[wi], ent[0], ent[1], N - int(gap_n[wi]), bool(st["nuniq"][wi, 2] > 0)))
         lap("gates")
-        freq, nn = st["freq"], st["nn"]
+        if not accepted:
+            return []
+        if "freq" in st:                       # sharded run: the owners' tensors came with the statistics
+            freq, nn = st["freq"], st["nn"]
+        else:
+            sel = np.zeros(len(positions), np.uint8)
+            sel[[a[0] for a in accepted]] = 1
+            freq, nn = hist.tensors(sel)
+            lap("tensors")
         keep = []
         for a in accepted:                                                     # core:736-740
             f = freq[a[0]]
@@ -537,13 +545,19 @@ class NN_degenerate(object):
             tick[0] = now
 
         gap_local, iupac_local, n_ent = hist.counts()
-        # collective 1: per-window counters of every shard + the records of the gap rows holding IUPAC cells
-        head = np.concatenate([gap_local, iupac_local, n_ent]).astype(np.int64)
-        flat, lens_r = comm.allgather_concat(np.concatenate([head, self._exception_records(hist).reshape(-1)]))
-        starts = np.concatenate([[0], np.cumsum(lens_r)])
-        heads = np.stack([flat[starts[r]:starts[r] + 3 * nw] for r in range(world)]).reshape(world, 3, nw)
-        hist._iupac_groups = self._group_exception_records(
-            np.concatenate([flat[starts[r] + 3 * nw:starts[r + 1]] for r in range(world)]).reshape(-1, 35))
+        # collective 1: per-window counters of every shard (+ how many gap rows holding IUPAC cells it has: their
+        # records follow in a second, padded gather when there are any)
+        exc = self._exception_records(hist)
+        head = np.concatenate([gap_local, iupac_local, n_ent, [len(exc)]]).astype(np.int64)
+        heads_flat = comm.allgather_fixed(head)
+        heads = heads_flat[:, :3 * nw].reshape(world, 3, nw)
+        n_exc = heads_flat[:, 3 * nw]
+        if int(n_exc.max()) > 0:
+            pad = np.zeros((int(n_exc.max()), 35), np.int64)
+            pad[:len(exc)] = exc
+            exc_all = comm.allgather_fixed(pad)
+            exc = np.concatenate([exc_all[r, :int(n_exc[r])] for r in range(world)])
+        hist._iupac_groups = self._group_exception_records(exc)
         gap_n, iupac_gap = heads[:, 0].sum(axis=0), heads[:, 1].sum(axis=0)
         lap("x_counters")
         gap_fail = np.array([round(int(g) / N, 2) >= (1 - self.coverage) for g in gap_n])
@@ -564,9 +578,10 @@ class NN_degenerate(object):
         # segment offsets of the received entries: source rank major, my windows inside
         seg = np.concatenate([[0], np.cumsum(sizes_all[:, mine].reshape(-1))]).astype(np.int64)
         my_pos = [positions[i] for i in mine]
-        log2cap = self._table_log2cap(k, N)
-        if log2cap == 0:
-            log2cap = max(6, int(math.ceil(math.log2(2 * N + 64))))
+        # owner tables: the entries arriving for a window bound its distinct haplotypes, so twice the largest arrival
+        # (load <= 0.5) is room enough, and far less to clear than a table sized by the sequence count
+        most = int(sizes_all[:, mine].sum(axis=0).max()) if len(mine) else 0
+        log2cap = max(8, int(math.ceil(math.log2(2 * most + 64))))
         per = int(np.ceil(nw / world))
         fields = [("ent", 4, np.float64), ("nuniq", 3, np.int64), ("mm_key", 1, np.uint64), ("mm_cnt", 1, np.int64),
                   ("mm_first", 1, np.uint64), ("freq", 4 * k, np.int64), ("nn", 16 * (k - 1), np.int64)]
@@ -590,9 +605,8 @@ class NN_degenerate(object):
                     rec[:, 0] = 1              # a full table on one rank is a collective event (column 0 = failed)
             lap("x_merge_summary")
             # collective 2: the per-window results of every owner (fixed-size records, padded to the maximum)
-            rec_all, _ = comm.allgather_concat(rec.reshape(-1))
+            rec_all = comm.allgather_fixed(rec)
             lap("x_results")
-            rec_all = rec_all.reshape(world, per, width)
             if not rec_all[:, :, 0].any():
                 break
             if own is not None:                # everybody rebuilds with doubled owner tables

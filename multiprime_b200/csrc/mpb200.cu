@@ -1224,14 +1224,15 @@ struct StatsPart {
     Best best;
 };
 
+template <bool STATS, bool TENS>
 __global__ void __launch_bounds__(SUM_THREADS)
 k_hist_summary(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ cnt, const uint64_t* __restrict__ first,
                const uint32_t* __restrict__ elist, const unsigned long long* __restrict__ n_entries, int log2cap, int k,
-               int v, StatsPart* __restrict__ part, unsigned long long* __restrict__ freq,
-               unsigned long long* __restrict__ nn) {
+               int v, const int32_t* __restrict__ sel_idx, StatsPart* __restrict__ part,
+               unsigned long long* __restrict__ freq, unsigned long long* __restrict__ nn) {
     __shared__ unsigned long long s_freq[4 * MPB_MAX_K];
     __shared__ unsigned long long s_nn[(MPB_MAX_K - 1) * 16];
-    const int wi = blockIdx.y;
+    const int wi = sel_idx ? sel_idx[blockIdx.y] : blockIdx.y;
     const uint64_t cap = 1ull << log2cap;
     const uint64_t base = (uint64_t)wi * cap;
     const uint32_t kmask = (1u << k) - 1u;
@@ -1250,17 +1251,18 @@ k_hist_summary(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ c
         uint32_t pa, pc, pg, pt, gapv;
         mpb_key_planes(key, k, kmask, pa, pc, pg, pt, gapv);
         const bool is_cover = __popc(gapv) <= v;
-        if (key < MPB_KEY_BASE5_D) {
+        if (STATS && key < MPB_KEY_BASE5_D) {
             ++ngf;
             Best b = {(unsigned long long)ci, first[slot], key};
             if (better(b, best)) best = b;
         }
-        const double clog = ci == 1u ? 0.0 : c * log2(c);  // singletons (most of a variable window) cost no log
+        const double clog = (!STATS || ci == 1u) ? 0.0 : c * log2(c);  // singletons (most of a variable window) cost no log
         if (is_cover) {
             s0c += c;
             s1c += clog;
             ++nc;
             int prev = -1;
+            if (TENS)
             for (int j = 0; j < k; ++j) {
                 const int d = ((gapv >> j) & 1u) ? -1 : (int)(((pc >> j) & 1u) + 2u * ((pg >> j) & 1u) + 3u * ((pt >> j) & 1u));
                 if (d >= 0) atomicAdd(&s_freq[d * k + j], (unsigned long long)ci);
@@ -1277,6 +1279,7 @@ k_hist_summary(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ c
     __shared__ long long sl[3][SUM_THREADS / 32];
     __shared__ Best sbest[SUM_THREADS / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (STATS)
     for (int o = 16; o > 0; o >>= 1) {
         s0c += __shfl_xor_sync(0xffffffffu, s0c, o);
         s1c += __shfl_xor_sync(0xffffffffu, s1c, o);
@@ -1291,7 +1294,7 @@ k_hist_summary(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ c
         ob.key = __shfl_xor_sync(0xffffffffu, best.key, o);
         if (better(ob, best)) best = ob;
     }
-    if (lane == 0) {
+    if (STATS && lane == 0) {
         sd[0][warp] = s0c;
         sd[1][warp] = s1c;
         sd[2][warp] = s0g;
@@ -1302,7 +1305,7 @@ k_hist_summary(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ c
         sbest[warp] = best;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (STATS && threadIdx.x == 0) {
         StatsPart r = {sd[0][0], sd[1][0], sd[2][0], sd[3][0], sl[0][0], sl[1][0], sl[2][0], sbest[0]};
         for (int w = 1; w < SUM_THREADS / 32; ++w) {
             r.s0c += sd[0][w];
@@ -1316,10 +1319,12 @@ k_hist_summary(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ c
         }
         part[(long long)wi * SUM_SB + blockIdx.x] = r;
     }
-    for (int i = threadIdx.x; i < 4 * k; i += SUM_THREADS)
-        if (s_freq[i]) atomicAdd(&freq[(long long)wi * 4 * k + i], s_freq[i]);
-    for (int i = threadIdx.x; i < (k - 1) * 16; i += SUM_THREADS)
-        if (s_nn[i]) atomicAdd(&nn[(long long)wi * (k - 1) * 16 + i], s_nn[i]);
+    if (TENS) {
+        for (int i = threadIdx.x; i < 4 * k; i += SUM_THREADS)
+            if (s_freq[i]) atomicAdd(&freq[(long long)wi * 4 * k + i], s_freq[i]);
+        for (int i = threadIdx.x; i < (k - 1) * 16; i += SUM_THREADS)
+            if (s_nn[i]) atomicAdd(&nn[(long long)wi * (k - 1) * 16 + i], s_nn[i]);
+    }
 }
 
 // all outputs host arrays (any may be NULL); freq / nn also stay on the device for the walk (mpb_walk_dev.cu)
@@ -1333,10 +1338,18 @@ extern "C" int mpb_hist_summary(mpb_hist* h, int64_t* gap_n, double* ent, int64_
     const size_t fb = nw * 4 * k * 8, nb = nw * (k - 1) * 16 * 8;
     StatsPart* dpart = nullptr;
     CK(cudaMallocAsync(&dpart, nw * SUM_SB * sizeof(StatsPart), ctx->stream));
-    CK(cudaMemsetAsync(h->freq, 0, fb, ctx->stream));
-    CK(cudaMemsetAsync(h->nn, 0, nb, ctx->stream));
-    LAUNCH(ctx, k_hist_summary, dim3(SUM_SB, (unsigned)nw), SUM_THREADS, 0, h->keys, h->cnt, h->first, h->elist,
-           h->n_entries, h->log2cap, k, h->v, dpart, h->freq, h->nn);
+    const bool tens = freq != nullptr || nn != nullptr;
+    if (tens) {
+        CK(cudaMemsetAsync(h->freq, 0, fb, ctx->stream));
+        CK(cudaMemsetAsync(h->nn, 0, nb, ctx->stream));
+        MPB_LAUNCH_NAMED(ctx, "k_hist_summary", (k_hist_summary<true, true>), dim3(SUM_SB, (unsigned)nw), SUM_THREADS, 0, h->keys,
+                         h->cnt, h->first, h->elist, h->n_entries, h->log2cap, k, h->v, (const int32_t*)nullptr, dpart, h->freq,
+                         h->nn);
+    } else {
+        MPB_LAUNCH_NAMED(ctx, "k_hist_summary", (k_hist_summary<true, false>), dim3(SUM_SB, (unsigned)nw), SUM_THREADS, 0, h->keys,
+                         h->cnt, h->first, h->elist, h->n_entries, h->log2cap, k, h->v, (const int32_t*)nullptr, dpart, h->freq,
+                         h->nn);
+    }
     std::vector<StatsPart> part(nw * SUM_SB);
     CK(cudaMemcpyAsync(part.data(), dpart, nw * SUM_SB * sizeof(StatsPart), cudaMemcpyDeviceToHost, ctx->stream));
     std::vector<long long> hg(nw), hi(nw);
@@ -1346,7 +1359,7 @@ extern "C" int mpb_hist_summary(mpb_hist* h, int64_t* gap_n, double* ent, int64_
     if (nn) CK(cudaMemcpyAsync(nn, h->nn, nb, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaFreeAsync(dpart, ctx->stream));
-    h->have_summary = true;
+    h->have_summary = tens;
     for (size_t w = 0; w < nw; ++w) {
         StatsPart r = part[w * SUM_SB];
         for (int b = 1; b < SUM_SB; ++b) {
@@ -1386,16 +1399,29 @@ extern "C" int mpb_hist_stats(mpb_hist* h, int64_t* gap_n, double* ent, int64_t*
     return mpb_hist_summary(h, gap_n, ent, nuniq, mm_key, mm_cnt, mm_first, n_iupac_gap, nullptr, nullptr);
 }
 
+// tensors of the windows with sel[i] != 0 only (zeros elsewhere); they also stay on the device for the walk
 extern "C" int mpb_hist_tensors(mpb_hist* h, const uint8_t* sel, int64_t* freq_hd, int64_t* nn_hd) {
     if (!h || !sel || !freq_hd || !nn_hd) return fail(MPB_EINVAL, "NULL argument");
-    int rc = mpb_hist_summary(h, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, freq_hd, nn_hd);
-    if (rc) return rc;
-    const size_t f1 = 4 * (size_t)h->k, n1 = (size_t)(h->k - 1) * 16;
-    for (int w = 0; w < h->nw; ++w)
-        if (!sel[w]) {
-            memset(freq_hd + w * f1, 0, f1 * 8);
-            memset(nn_hd + w * n1, 0, n1 * 8);
-        }
+    mpb_ctx* ctx = h->msa->ctx;
+    CK(cudaSetDevice(ctx->device));
+    const int k = h->k;
+    const size_t fb = (size_t)h->nw * 4 * k * 8, nb = (size_t)h->nw * (k - 1) * 16 * 8;
+    std::vector<int32_t> idx;
+    for (int i = 0; i < h->nw; ++i)
+        if (sel[i]) idx.push_back(i);
+    CK(cudaMemsetAsync(h->freq, 0, fb, ctx->stream));
+    CK(cudaMemsetAsync(h->nn, 0, nb, ctx->stream));
+    if (!idx.empty()) {
+        InBuf si(ctx, idx.data(), idx.size() * 4);
+        if (si.rc) return si.rc;
+        MPB_LAUNCH_NAMED(ctx, "k_hist_summary", (k_hist_summary<false, true>), dim3(SUM_SB, (unsigned)idx.size()), SUM_THREADS, 0,
+                         h->keys, h->cnt, h->first, h->elist, h->n_entries, h->log2cap, k, h->v, si.dev<int32_t>(),
+                         (StatsPart*)nullptr, h->freq, h->nn);
+    }
+    CK(cudaMemcpyAsync(freq_hd, h->freq, fb, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(nn_hd, h->nn, nb, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    h->have_summary = true;
     return 0;
 }
 

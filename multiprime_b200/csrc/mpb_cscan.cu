@@ -202,70 +202,94 @@ k_cscan(const uint32_t* __restrict__ colp, long long nwords, int v, const uint32
         const uint32_t* psf = sp + sp[7];
         const uint32_t* psr = psf + nsf;
         unsigned n0 = 0, nf = 0, nr = 0, nt = 0;
+        // two words per pass: their plane loads are independent, so twice as many are in flight per thread (the first
+        // version, one word at a time, spent 60 % of its stall samples waiting for them)
 #pragma unroll 1
-        for (int j = 0; j < CSCAN_WPT; ++j) {
-            const long long w = w0 + (long long)j * CSCAN_THREADS;
-            if (w >= nwords) break;
-            const char* base = reinterpret_cast<const char*>(colp + w);
-            Counter<NB> cnt;
-            cnt.clear();
+        for (int j = 0; j < CSCAN_WPT; j += 2) {
+            const long long wa = w0 + (long long)j * CSCAN_THREADS;
+            if (wa >= nwords) break;
+            long long wb = wa + CSCAN_THREADS;
+            const bool two = wb < nwords;
+            if (!two) wb = wa;  // (re-reads word a; its results are dropped)
+            const char* base_a = reinterpret_cast<const char*>(colp + wa);
+            const char* base_b = reinterpret_cast<const char*>(colp + wb);
+#define LD_A(row) __ldg(reinterpret_cast<const uint32_t*>(base_a + (row) * row_stride))
+#define LD_B(row) __ldg(reinterpret_cast<const uint32_t*>(base_b + (row) * row_stride))
+            Counter<NB> ca, cb;
+            ca.clear();
+            cb.clear();
             for (int t = 0; t < ntri; ++t) {
                 const uint4 r = *reinterpret_cast<const uint4*>(sp + 8 + 4 * t);
-                const uint32_t x0 = __ldg(reinterpret_cast<const uint32_t*>(base + r.x * row_stride));
-                const uint32_t x1 = __ldg(reinterpret_cast<const uint32_t*>(base + r.y * row_stride));
-                const uint32_t x2 = __ldg(reinterpret_cast<const uint32_t*>(base + r.z * row_stride));
-                cnt.add3(x0, x1, x2);
+                const uint32_t a0 = LD_A(r.x), a1 = LD_A(r.y), a2 = LD_A(r.z);
+                const uint32_t b0 = LD_B(r.x), b1 = LD_B(r.y), b2 = LD_B(r.z);
+                ca.add3(a0, a1, a2);
+                cb.add3(b0, b1, b2);
             }
             {
-                uint32_t x = 0;
+                uint32_t xa = 0, xb = 0;
                 for (int e = 0; e < nd; ++e) {
                     const uint32_t r = pdeg[e];
-                    x |= __ldg(reinterpret_cast<const uint32_t*>(base + (r & 0x7FFFFFFFu) * row_stride));
+                    xa |= LD_A(r & 0x7FFFFFFFu);
+                    xb |= LD_B(r & 0x7FFFFFFFu);
                     if (r >> 31) {
-                        cnt.add(~x, 0);
-                        x = 0;
+                        ca.add(~xa, 0);
+                        cb.add(~xb, 0);
+                        xa = xb = 0;
                     }
                 }
             }
-            uint32_t mf = 0, mr = 0;
+            uint32_t mfa = 0, mra = 0, mfb = 0, mrb = 0;
             {
-                uint32_t x = 0;
+                uint32_t xa = 0, xb = 0;
                 for (int e = 0; e < nsf; ++e) {
                     const uint32_t r = psf[e];
-                    x |= __ldg(reinterpret_cast<const uint32_t*>(base + (r & 0x7FFFFFFFu) * row_stride));
+                    xa |= LD_A(r & 0x7FFFFFFFu);
+                    xb |= LD_B(r & 0x7FFFFFFFu);
                     if (r >> 31) {
-                        mf |= ~x;
-                        x = 0;
+                        mfa |= ~xa;
+                        mfb |= ~xb;
+                        xa = xb = 0;
                     }
                 }
                 for (int e = 0; e < nsr; ++e) {
                     const uint32_t r = psr[e];
-                    x |= __ldg(reinterpret_cast<const uint32_t*>(base + (r & 0x7FFFFFFFu) * row_stride));
+                    xa |= LD_A(r & 0x7FFFFFFFu);
+                    xb |= LD_B(r & 0x7FFFFFFFu);
                     if (r >> 31) {
-                        mr |= ~x;
-                        x = 0;
+                        mra |= ~xa;
+                        mrb |= ~xb;
+                        xa = xb = 0;
                     }
                 }
             }
-            const uint32_t spec = __ldg(spec_bits + (long long)win * nwords + w);
-            const uint32_t over = cnt.over(v);
-            const uint32_t perfect = ~cnt.any() & ~spec;
-            const uint32_t okf = ~(over | mf | spec), okr = ~(over | mr | spec);
-            n0 += __popc(perfect);
-            nf += __popc(okf);
-            nr += __popc(okr);
-            if (trial != CSCAN_NONE)
-                nt += __popc(perfect & __ldg(reinterpret_cast<const uint32_t*>(base + trial * row_stride)));
+            const uint32_t spec_a = __ldg(spec_bits + (long long)win * nwords + wa);
+            const uint32_t spec_b = two ? __ldg(spec_bits + (long long)win * nwords + wb) : 0xFFFFFFFFu;
+            const uint32_t over_a = ca.over(v), over_b = cb.over(v);
+            const uint32_t perf_a = ~ca.any() & ~spec_a, perf_b = ~cb.any() & ~spec_b;
+            n0 += __popc(perf_a) + __popc(perf_b);
+            nf += __popc(~(over_a | mfa | spec_a)) + __popc(~(over_b | mfb | spec_b));
+            nr += __popc(~(over_a | mra | spec_a)) + __popc(~(over_b | mrb | spec_b));
+            if (trial != CSCAN_NONE) nt += __popc(perf_a & LD_A(trial)) + __popc(perf_b & LD_B(trial));
             if (BITS) {
                 const int slot = bits_slot[c];
-                if (slot >= 0 && w < out_words) {
-                    const uint32_t gapw = __ldg(gap_bits + (long long)win * nwords + w);
+                if (slot >= 0) {
                     uint32_t* o = bits + (long long)slot * 3 * out_words;
-                    o[w] = (over | mf) & ~spec & ~gapw;   // gap rows carry no non-cover bit (core:689-698)
-                    o[out_words + w] = (over | mr) & ~spec & ~gapw;
-                    o[2 * out_words + w] = gapw;
+                    if (wa < out_words) {
+                        const uint32_t gapw = __ldg(gap_bits + (long long)win * nwords + wa);
+                        o[wa] = (over_a | mfa) & ~spec_a & ~gapw;   // gap rows carry no non-cover bit (core:689-698)
+                        o[out_words + wa] = (over_a | mra) & ~spec_a & ~gapw;
+                        o[2 * out_words + wa] = gapw;
+                    }
+                    if (two && wb < out_words) {
+                        const uint32_t gapw = __ldg(gap_bits + (long long)win * nwords + wb);
+                        o[wb] = (over_b | mfb) & ~spec_b & ~gapw;
+                        o[out_words + wb] = (over_b | mrb) & ~spec_b & ~gapw;
+                        o[2 * out_words + wb] = gapw;
+                    }
                 }
             }
+#undef LD_A
+#undef LD_B
         }
         n0 = __reduce_add_sync(0xffffffffu, n0);
         nf = __reduce_add_sync(0xffffffffu, nf);
@@ -294,12 +318,13 @@ k_cscan_special(const mpb_cand* __restrict__ cands, const int* __restrict__ n_ca
         if (cd.win < 0 || cd.win >= nw) continue;
         long long n = (long long)spec_n[cd.win];
         if (n > spec_cap) n = spec_cap;
+        if ((long long)blockIdx.y * 256 >= n) continue;  // uniform: this slice of the list is empty
         if (threadIdx.x < 4) s_acc[threadIdx.x] = 0;
         __syncthreads();
         const uint32_t nA = ~cd.allow[0] & kmask, nC = ~cd.allow[1] & kmask, nG = ~cd.allow[2] & kmask, nT = ~cd.allow[3] & kmask;
         const int tpos = cd.trial >= 0 ? (cd.trial & 255) : 0, tbase = cd.trial >= 0 ? ((cd.trial >> 8) & 3) : -1;
         unsigned n0 = 0, nf = 0, nr = 0, nt = 0;
-        for (long long i = threadIdx.x; i < n; i += 256) {
+        for (long long i = (long long)blockIdx.y * 256 + threadIdx.x; i < n; i += 256ll * gridDim.y) {
             const uint4 q = __ldg(spec_win + (long long)cd.win * spec_cap + i);
             Win w;
             w.a = q.x;
@@ -377,6 +402,11 @@ int mpb_cscan_launch(mpb_hist* h, uint32_t fmask, uint32_t rmask, const mpb_cand
     if (gy > (unsigned)max_cands) gy = (unsigned)max_cands;
     if (gy < 1) gy = 1;
     const long long out_words = (m->n_seq + 31) / 32;
+    // special rows: blocks (candidate, slice of the window's list); enough slices that a list of spec_cap rows is walked
+    // in a few iterations
+    unsigned spec_gy = (unsigned)((h->spec_cap + 256 * 4 - 1) / (256 * 4));
+    if (spec_gy < 1) spec_gy = 1;
+    if (spec_gy > 16) spec_gy = 16;
     if (bits_slot_d) {
         if (h->v <= 3)
             MPB_LAUNCH_NAMED(ctx, "k_cscan", (k_cscan<3, true>), dim3(gx, gy), CSCAN_THREADS, 0, m->colp, (long long)m->nwords, h->v, plans_d,
@@ -384,7 +414,7 @@ int mpb_cscan_launch(mpb_hist* h, uint32_t fmask, uint32_t rmask, const mpb_cand
         else
             MPB_LAUNCH_NAMED(ctx, "k_cscan", (k_cscan<5, true>), dim3(gx, gy), CSCAN_THREADS, 0, m->colp, (long long)m->nwords, h->v, plans_d,
                    n_cand_d, h->spec_bits, h->gap_bits, counts_d, bits_slot_d, bits_d, out_words);
-        MPB_LAUNCH_NAMED(ctx, "k_cscan_special", k_cscan_special<true>, (unsigned)(max_cands < 4096 ? max_cands : 4096), 256, 0, cands_d, n_cand_d, h->nw,
+        MPB_LAUNCH_NAMED(ctx, "k_cscan_special", k_cscan_special<true>, dim3((unsigned)(max_cands < 4096 ? max_cands : 4096), spec_gy), 256, 0, cands_d, n_cand_d, h->nw,
                h->k, h->v, fmask, rmask, h->spec_win, h->spec_row, h->spec_n, (long long)h->spec_cap, counts_d, bits_slot_d,
                bits_d, out_words, m->err);
     } else {
@@ -394,7 +424,7 @@ int mpb_cscan_launch(mpb_hist* h, uint32_t fmask, uint32_t rmask, const mpb_cand
         else
             MPB_LAUNCH_NAMED(ctx, "k_cscan", (k_cscan<5, false>), dim3(gx, gy), CSCAN_THREADS, 0, m->colp, (long long)m->nwords, h->v, plans_d,
                    n_cand_d, h->spec_bits, h->gap_bits, counts_d, (const int32_t*)nullptr, (uint32_t*)nullptr, out_words);
-        MPB_LAUNCH_NAMED(ctx, "k_cscan_special", k_cscan_special<false>, (unsigned)(max_cands < 4096 ? max_cands : 4096), 256, 0, cands_d, n_cand_d, h->nw,
+        MPB_LAUNCH_NAMED(ctx, "k_cscan_special", k_cscan_special<false>, dim3((unsigned)(max_cands < 4096 ? max_cands : 4096), spec_gy), 256, 0, cands_d, n_cand_d, h->nw,
                h->k, h->v, fmask, rmask, h->spec_win, h->spec_row, h->spec_n, (long long)h->spec_cap, counts_d,
                (const int32_t*)nullptr, (uint32_t*)nullptr, out_words, m->err);
     }

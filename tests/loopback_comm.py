@@ -52,6 +52,9 @@ class ThreadComm:
     def allgather_object(self, obj):
         return self._exchange(obj)
 
+    def allgather_fixed(self, arr):
+        return np.stack(self._exchange(np.ascontiguousarray(arr).copy()))
+
     def alltoall(self, arr, send_counts, recv_counts):
         parts = self._exchange((np.ascontiguousarray(arr).copy(), np.asarray(send_counts)))
         out = []
