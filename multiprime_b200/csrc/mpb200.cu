@@ -1230,8 +1230,10 @@ k_hist_summary(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ c
                const uint32_t* __restrict__ elist, const unsigned long long* __restrict__ n_entries, int log2cap, int k,
                int v, const int32_t* __restrict__ sel_idx, StatsPart* __restrict__ part,
                unsigned long long* __restrict__ freq, unsigned long long* __restrict__ nn) {
-    __shared__ unsigned long long s_freq[4 * MPB_MAX_K];
-    __shared__ unsigned long long s_nn[(MPB_MAX_K - 1) * 16];
+    // block-private 32-bit counters (native shared-memory atomics; 64-bit ones are CAS loops): a block sees an eighth of
+    // a window's entries, whose counts sum to far less than 2^32
+    __shared__ unsigned int s_freq[4 * MPB_MAX_K];
+    __shared__ unsigned int s_nn[(MPB_MAX_K - 1) * 16];
     const int wi = sel_idx ? sel_idx[blockIdx.y] : blockIdx.y;
     const uint64_t cap = 1ull << log2cap;
     const uint64_t base = (uint64_t)wi * cap;
@@ -1265,8 +1267,8 @@ k_hist_summary(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ c
             if (TENS)
             for (int j = 0; j < k; ++j) {
                 const int d = ((gapv >> j) & 1u) ? -1 : (int)(((pc >> j) & 1u) + 2u * ((pg >> j) & 1u) + 3u * ((pt >> j) & 1u));
-                if (d >= 0) atomicAdd(&s_freq[d * k + j], (unsigned long long)ci);
-                if (j > 0 && d >= 0 && prev >= 0) atomicAdd(&s_nn[(j - 1) * 16 + prev * 4 + d], (unsigned long long)ci);
+                if (d >= 0) atomicAdd(&s_freq[d * k + j], ci);
+                if (j > 0 && d >= 0 && prev >= 0) atomicAdd(&s_nn[(j - 1) * 16 + prev * 4 + d], ci);
                 prev = d;
             }
         } else {
@@ -1321,9 +1323,9 @@ k_hist_summary(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ c
     }
     if (TENS) {
         for (int i = threadIdx.x; i < 4 * k; i += SUM_THREADS)
-            if (s_freq[i]) atomicAdd(&freq[(long long)wi * 4 * k + i], s_freq[i]);
+            if (s_freq[i]) atomicAdd(&freq[(long long)wi * 4 * k + i], (unsigned long long)s_freq[i]);
         for (int i = threadIdx.x; i < (k - 1) * 16; i += SUM_THREADS)
-            if (s_nn[i]) atomicAdd(&nn[(long long)wi * (k - 1) * 16 + i], s_nn[i]);
+            if (s_nn[i]) atomicAdd(&nn[(long long)wi * (k - 1) * 16 + i], (unsigned long long)s_nn[i]);
     }
 }
 
