@@ -62,7 +62,9 @@ def host_cores() -> int:
 
 # ----------------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)"""
+    """SM clock and throttle reasons during the timed region (B200_PROFILING.md), read through NVML in-process: spawning
+    nvidia-smi five times a second initialises every GPU of the box each time and perturbs the ranks it shares them
+    with; nvidia-smi is only the fallback when the NVML binding is missing"""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -71,29 +73,54 @@ class ClockSampler(threading.Thread):
     def __init__(self, index: int):
         super().__init__(daemon=True)
         self.index = index
-        self.rows = []
+        self.rows = []            # (sm MHz, max MHz, [reason flags hw_slowdown, hw_thermal, sw_thermal, sw_power_cap])
         self.stop_flag = threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+        r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        flags = [bool(r & 0x8), bool(r & 0x40), bool(r & 0x20), bool(r & 0x4)]
+        self.rows.append((float(sm), float(mx), flags))
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+        f = [x.strip() for x in out.strip().split(",")]
+        if len(f) >= 7:
+            self.rows.append((float(f[0]), float(f[1]), [x.lower().startswith("active") for x in f[3:7]]))
 
     def run(self):
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(",")]
-                if len(f) >= 7:
-                    self.rows.append(f)
+                if self.nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self.stop_flag.wait(0.1)
+            self.stop_flag.wait(0.05 if self.nvml is not None else 0.5)
 
     def summary(self):
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        sm = sorted(float(r[0]) for r in self.rows)
+        sm = sorted(r[0] for r in self.rows)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "samples": len(self.rows)}
+        reasons = [n for i, n in enumerate(names) if any(r[2][i] for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.rows[0][1], "reasons": reasons,
+                "samples": len(self.rows), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def kernel_traffic():
@@ -292,7 +319,7 @@ def run_b200(args):
         # produced (in HBM, where the pairing step reads them)
         return core.NN_degenerate(seq_file=None, outfile="", packed=(ids, packed_pinned, n_col, None), device=local,
                                   sidecars=False, want_trace=False, keep_bits=True, stream=stream, comm=comm,
-                                  row0=rank * n_seq, **PARAMS)
+                                  row0=rank * n_seq, rows_on_rank0_only=True, **PARAMS)
 
     def barrier():
         if world > 1:
@@ -356,6 +383,8 @@ def run_b200(args):
             results["phases"] = {k: round(v / args.steps, 2) for k, v in app.stats["phase_ms"].items()}
             app.ctx.profile(False)
     evals_all = float(results["evals_per_step"])      # already global: calls x (sequences of ALL shards)
+    if world > 1:
+        sys.stderr.write("rank %d phases ms/step: %s\n" % (rank, json.dumps(results["phases"])))
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

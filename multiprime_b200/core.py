@@ -195,7 +195,8 @@ class NN_degenerate(object):
     def __init__(self, seq_file, primer_length=18, coverage=0.8, number_of_dege_bases=18, score_of_dege_bases=1000,
                  product_len=250, position="2,-1", variation=2, raw_entropy_threshold=3.6, distance=4, GC="0.4,0.6",
                  nproc=10, outfile="", device=0, windows_per_batch=0, sidecars=True, alignment=None, packed=None,
-                 stream=None, comm=None, row0=0, want_trace=True, keep_bits=False, _backend=None):
+                 stream=None, comm=None, row0=0, want_trace=True, keep_bits=False, rows_on_rank0_only=False,
+                 _backend=None):
         self.primer_length = primer_length
         self.coverage = coverage
         self.number_of_dege_bases = number_of_dege_bases
@@ -212,6 +213,7 @@ class NN_degenerate(object):
         self.want_trace = want_trace            # record the primers handed to mis_primer_check (the tests compare them)
         self.keep_bits = keep_bits              # keep the per-sequence F / R / gap bit vectors of every row (pairing)
         self.bit_vectors = []
+        self.rows_on_rank0_only = rows_on_rank0_only   # sharded runs: the replicated row assembly on rank 0 only
         self.windows_per_batch = windows_per_batch
         if not 3 <= primer_length <= _lib.MAX_K:
             raise ValueError("primer length must be within 3..%d" % _lib.MAX_K)
@@ -505,11 +507,10 @@ class NN_degenerate(object):
             sel[[a[0] for a in accepted]] = 1
             freq, nn = hist.tensors(sel)
             lap("tensors")
-        keep = []
-        for a in accepted:                                                     # core:736-740
-            f = freq[a[0]]
-            if not ((f.sum(axis=1) == 0).any() or (f.sum(axis=0) == 0).any()):
-                keep.append(a)
+        acc_w = np.array([a[0] for a in accepted], np.int64)                   # core:736-740, all windows at once
+        fa = freq[acc_w]
+        ok = ~((fa.sum(axis=2) == 0).any(axis=1) | (fa.sum(axis=1) == 0).any(axis=1))
+        keep = [a for a, o in zip(accepted, ok.tolist()) if o]
         if not keep:
             return []
         wis = np.array([a[0] for a in keep], np.int32)
@@ -719,6 +720,8 @@ class NN_degenerate(object):
                 distinct[sel] = own.match(np.searchsorted(mine, wis[sel]).astype(np.int32), allow[sel])
             distinct = self.comm.allreduce_sum(distinct)
         lap("fin_match")
+        if self.rows_on_rank0_only and self.comm.rank != 0 and not self.sidecars:
+            return []                  # rows are identical on every rank: only rank 0 assembles (and writes) them
         tm_avg, gc, flags, deg, ndeg = self._primer_props(sets_arr, k, gc_lo, gc_hi)
         lap("fin_props")
         seqkeys = self.msa.seqkeys(k, pos) if self.sidecars else None
