@@ -213,6 +213,11 @@ int mpb_seqkeys(mpb_msa* msa, int k, const int32_t* win_pos, int32_t nw, uint64_
 int mpb_tm(mpb_ctx* ctx, const uint8_t* seqs2bit_hd, int k, int64_t n, const double* consts3, double* tm_hd,
            double* dh_hd, double* ds_hd);
 
+/* The same for degenerate primers given as base sets (sets[n*32], one byte per position, hd): sums[n] = sum over the
+ * expansions of round(Tm, 2) in hundredths of a degree (exact integers), ties[n] = expansions left out because their Tm
+ * sits within 1e-6 of a rounding tie (the caller replays such a primer with Python's round()).  Host outputs. */
+int mpb_tm_sets(mpb_ctx* ctx, const uint8_t* sets_hd, int k, int32_t n, const double* consts3, int64_t* sums, int32_t* ties);
+
 /* ---- per-window control logic: seeds core:579-600, NN-array refinement walk core:860-1089, NM-vs-MM core:816 ----------
  * The logic lives once in csrc/mpb_walk_core.h and compiles for host and device.
  *

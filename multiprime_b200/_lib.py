@@ -53,6 +53,7 @@ SIGNATURES = {
     "mpb_scan": (C.c_int, [_P, C.c_int, C.c_int, C.c_uint32, C.c_uint32, _P, _P, C.c_int64, _P, _P, _P]),
     "mpb_seqkeys": (C.c_int, [_P, C.c_int, _P, C.c_int32, _P]),
     "mpb_tm": (C.c_int, [_P, _P, C.c_int, C.c_int64, _P, _P, _P, _P]),
+    "mpb_tm_sets": (C.c_int, [_P, _P, C.c_int, C.c_int32, _P, _P, _P]),
     "mpb_walk": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int32, _P, _P, _P, _P, _P, _P,
                            _P, _P, _P, _P, _P, C.c_int64, _P, _P, _P]),
     "mpb_hist_export_at": (C.c_int, [_P, C.c_int32, _P, _P, _P, C.c_int64, _P, _P, _P]),

@@ -558,6 +558,8 @@ class NN_degenerate(object):
             pad[:len(exc)] = exc
             exc_all = comm.allgather_fixed(pad)
             exc = np.concatenate([exc_all[r, :int(n_exc[r])] for r in range(world)])
+        # only a window's owner needs them (entropy of its window, exact replay): the others drop them unsorted
+        exc = exc[owner[exc[:, 2]] == rank] if len(exc) else exc
         hist._iupac_groups = self._group_exception_records(exc)
         gap_n, iupac_gap = heads[:, 0].sum(axis=0), heads[:, 1].sum(axis=0)
         lap("x_counters")
@@ -596,6 +598,10 @@ class NN_degenerate(object):
                     own.merge_segments(seg, rk, rc, rf)
                     own.add_counts(gap_n[mine], iupac_gap[mine])
                     st_own = own.summary()
+                    for j, wi in enumerate(mine.tolist()):      # gap rows holding IUPAC cells are not table entries
+                        for _, c in hist._iupac_groups.get(wi, ()):
+                            st_own["ent"][j, 2] += c
+                            st_own["ent"][j, 3] += c * math.log2(c)
                     c0 = 1
                     for name, w, dt in fields:
                         rec[:len(mine), c0:c0 + w] = np.ascontiguousarray(st_own[name]).reshape(len(mine), w).view(np.int64)
@@ -627,6 +633,7 @@ class NN_degenerate(object):
         st["nn"] = st["nn"].reshape(nw, k - 1, 4, 4)
         st["gap_n"] = gap_n
         st["n_iupac_gap"] = iupac_gap
+        st["ent_complete"] = True              # the owners added the IUPAC gap rows to their windows' sums
         # windows that failed the gap gate did not travel: their (empty) statistics must not pass a later gate
         st["nuniq"][gap_fail] = 0
         return st, own, mine
@@ -640,7 +647,7 @@ class NN_degenerate(object):
         thr = self.entropy_threshold
         comm = self.comm
         ent = st["ent"].astype(np.float64).copy()
-        with_iupac = np.nonzero(alive & (st["n_iupac_gap"] > 0))[0].tolist()
+        with_iupac = [] if st.get("ent_complete") else np.nonzero(alive & (st["n_iupac_gap"] > 0))[0].tolist()
         for wi in with_iupac:                                  # gap rows holding IUPAC cells
             for _, c in self._iupac_gap_groups(hist, wi):
                 ent[wi, 2] += c

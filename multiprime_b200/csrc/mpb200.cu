@@ -1977,6 +1977,88 @@ extern "C" int mpb_tm(mpb_ctx* ctx, const uint8_t* seqs_hd, int k, int64_t n, co
     return 0;
 }
 
+// Tm of a degenerate primer = mean over its expansions of the per-expansion Tm rounded to 2 decimals (core:849-852).
+// One block per primer; a thread decodes its expansions straight from the base sets (no host enumeration, no H2D of
+// expansion strings), evaluates Tm in the reference's operation order (as k_tm) and rounds it to integer hundredths;
+// the block adds the integers — exact and order-independent.  An expansion whose Tm sits within 1e-6 of a rounding tie
+// is counted in `ties`: the caller then replays that primer on the host with Python's round().
+__global__ void __launch_bounds__(128)
+k_tm_sets(const uint8_t* __restrict__ sets, int k, int n, double c_nonsym, double c_sym, double corr,
+          long long* __restrict__ sums, int* __restrict__ ties) {
+    __shared__ __align__(16) double tab[40];
+    __shared__ long long s_sum;
+    __shared__ int s_tie;
+    for (int i = threadIdx.x; i < 40; i += blockDim.x) tab[i] = g_nn_tables[i];
+    if (threadIdx.x == 0) {
+        s_sum = 0;
+        s_tie = 0;
+    }
+    __syncthreads();
+    const int pi = blockIdx.x;
+    if (pi >= n) return;
+    const uint8_t* S = sets + (long long)pi * 32;
+    long long deg = 1;
+    for (int i = 0; i < k; ++i) deg *= c_fold[S[i] & 15];
+    long long acc = 0;
+    int tie = 0;
+    for (long long e0 = threadIdx.x; e0 < deg; e0 += blockDim.x) {
+        uint8_t q[MPB_MAX_K + 5];
+        long long e = e0;
+        for (int i = k - 1; i >= 0; --i) {
+            const int code = S[i] & 15;
+            const int f = c_fold[code];
+            q[i] = (uint8_t)((c_order[code] >> (2 * (int)(e % f))) & 3);
+            e /= f;
+        }
+        double dh = 0.0, ds = 0.0;
+        for (int j = 0; j + 1 < k; ++j) {
+            const int nx = q[j + 1], cu = q[j];
+            dh = __dadd_rn(dh, tab[nx * 4 + cu]);
+            ds = __dadd_rn(ds, tab[16 + nx * 4 + cu]);
+        }
+        dh = __dadd_rn(dh, __dadd_rn(tab[32 + q[0]], tab[32 + q[k - 1]]));
+        ds = __dadd_rn(ds, __dadd_rn(tab[36 + q[0]], tab[36 + q[k - 1]]));
+        bool sym = (k % 2) == 0;
+        for (int j = 0; sym && j < k / 2; ++j) sym = (q[j] + q[k / 2 + j]) == 3;
+        if (sym) ds = __dadd_rn(ds, -1.4);
+        dh = __dmul_rn(dh, 1000.0);
+        const double denom = __dadd_rn(ds, sym ? c_sym : c_nonsym);
+        const double t = __dadd_rn(__ddiv_rn(1.0, __dadd_rn(__ddiv_rn(1.0, __ddiv_rn(dh, denom)), corr)), -273.15);
+        const double y = __dmul_rn(t, 100.0);
+        const double fl = floor(y);
+        const double fr = y - fl;
+        if (fr < 0.5 - 1e-6) acc += (long long)fl;
+        else if (fr > 0.5 + 1e-6) acc += (long long)fl + 1;
+        else ++tie;
+    }
+    atomicAdd((unsigned long long*)&s_sum, (unsigned long long)acc);
+    if (tie) atomicAdd(&s_tie, tie);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        sums[pi] = s_sum;
+        ties[pi] = s_tie;
+    }
+}
+
+// sums[n]: sum over the expansions of round(Tm, 2) in hundredths; ties[n]: expansions left out because they sit on a
+// rounding tie (host outputs)
+extern "C" int mpb_tm_sets(mpb_ctx* ctx, const uint8_t* sets_hd, int k, int32_t n, const double* consts3, int64_t* sums,
+                           int32_t* ties) {
+    if (!ctx || !sets_hd || !consts3 || !sums || !ties) return fail(MPB_EINVAL, "NULL argument");
+    if (k < 2 || k > MPB_MAX_K || n < 0) return fail(MPB_EINVAL, "bad k=%d n=%d", k, n);
+    if (n == 0) return 0;
+    CK(cudaSetDevice(ctx->device));
+    InBuf in(ctx, sets_hd, (size_t)n * 32);
+    OutBuf os(ctx, sums, (size_t)n * 8), ot(ctx, ties, (size_t)n * 4);
+    if (in.rc || os.rc || ot.rc) return MPB_ECUDA;
+    LAUNCH(ctx, k_tm_sets, (unsigned)n, 128, 0, in.dev<uint8_t>(), k, (int)n, consts3[0], consts3[1], consts3[2],
+           os.dev<long long>(), ot.dev<int>());
+    CK(os.finish());
+    CK(ot.finish());
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------------
 // pair coverage (get_multiPrime.py:560-569): the sequences NOT covered by a primer pair are the union of the forward
 // primer's and the reverse primer's uncovered sets; with per-sequence bit vectors that is popcount(F | R).

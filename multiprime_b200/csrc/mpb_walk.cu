@@ -268,57 +268,30 @@ extern "C" int mpb_primer_props(mpb_ctx* ctx, const uint8_t* sets, int k, int32_
     if (!ctx || !sets || !tm_consts3 || !tm_avg || !gc || !flags) return mpb_fail(MPB_EINVAL, "NULL argument");
     if (k < 3 || k > 32 || n < 0) return mpb_fail(MPB_EINVAL, "bad k or n");
     if (n == 0) return 0;
-    // all expansions of all primers, product order (leftmost position slowest), as bases 0..3
-    std::vector<int64_t> off(n + 1, 0);
+    std::vector<int64_t> degs(n);
     for (int i = 0; i < n; ++i) {
         int nd = 0;
         const int d = degeneracy_of(sets + (int64_t)i * 32, k, &nd);
         if (d > (1 << 20)) return mpb_fail(MPB_EEXPAND, "primer %d expands to more than 2^20 sequences", i);
         if (deg_out) deg_out[i] = d;
         if (ndeg_out) ndeg_out[i] = nd;
-        off[i + 1] = off[i] + d;
+        degs[i] = d;
     }
-    std::vector<uint8_t> seqs((size_t)off[n] * k);
-    for (int i = 0; i < n; ++i) {
-        // odometer over the positions, rightmost fastest: each expansion is its predecessor with a changed suffix
-        const uint8_t* S = sets + (int64_t)i * 32;
-        const int64_t d = off[i + 1] - off[i];
-        int digit[32];
-        uint8_t* q = &seqs[(size_t)off[i] * k];
-        for (int p = 0; p < k; ++p) {
-            digit[p] = 0;
-            q[p] = (uint8_t)ORD[S[p] & 15][0];
-        }
-        for (int64_t e = 1; e < d; ++e) {
-            uint8_t* nx = q + k;
-            memcpy(nx, q, (size_t)k);
-            for (int p = k - 1; p >= 0; --p) {
-                const int code = S[p] & 15;
-                if (++digit[p] < FOLD[code]) {
-                    nx[p] = (uint8_t)ORD[code][digit[p]];
-                    break;
-                }
-                digit[p] = 0;
-                nx[p] = (uint8_t)ORD[code][0];
-            }
-            q = nx;
-        }
-    }
-    std::vector<double> tm(off[n]);
-    int rc = mpb_tm(ctx, seqs.data(), k, off[n], tm_consts3, tm.data(), nullptr, nullptr);
+    // per-expansion Tm, rounded and summed on the device (k_tm_sets)
+    std::vector<int64_t> tm_sum(n);
+    std::vector<int32_t> tm_ties(n);
+    int rc = mpb_tm_sets(ctx, sets, k, n, tm_consts3, tm_sum.data(), tm_ties.data());
     if (rc) return rc;
     double gc_frac[33];  // round(g / k, 3) of core:405 for every possible G/C count
     for (int g = 0; g <= k; ++g) gc_frac[g] = round3((double)g / (double)k);
     for (int i = 0; i < n; ++i) {
         const uint8_t* S = sets + (int64_t)i * 32;
         int fl = 0;
-        // Tm: mean over expansions of round(tm, 2), rounded to 2 (core:849-852)
+        // Tm: mean over expansions of round(tm, 2), rounded to 2 (core:849-852); the device summed the rounded values
+        // as integer hundredths
         {
-            long double acc = 0.0L;
-            const int64_t d = off[i + 1] - off[i];
-            for (int64_t e = off[i]; e < off[i + 1]; ++e) acc += (long double)round2(tm[e]);
-            const double m = (double)(acc / (long double)d);
-            if (near_tie2(m)) fl |= 64;
+            const double m = (double)((long double)tm_sum[i] / 100.0L / (long double)degs[i]);
+            if (tm_ties[i] > 0 || near_tie2(m)) fl |= 64;
             tm_avg[i] = round2(m);
         }
         // GC: mean over expansions of round(gc/len, 3), rounded to 2 (core:401-407), via the GC-count distribution

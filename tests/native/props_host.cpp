@@ -1,30 +1,23 @@
-// Host build of multiprime_b200/csrc/mpb_walk.cu (pure host code) with the device call mpb_tm replaced by a stub
-// that records the expansion buffer it is handed: lets the CPU suite check the expansion order of mpb_primer_props.
+// Host build of multiprime_b200/csrc/mpb_walk.cu (pure host code) with the device call mpb_tm_sets replaced by a stub:
+// lets the CPU suite check what mpb_primer_props computes on the host (degeneracy, GC content, di-nucleotide / hairpin
+// flags, the rounding of the Tm mean).
 #include "../../multiprime_b200/csrc/mpb_walk.cu"
-
-static std::vector<uint8_t> g_seqs;
-static int64_t g_n = 0;
 
 int mpb_fail(int code, const char*, ...) { return code; }
 
-extern "C" int mpb_tm(mpb_ctx*, const uint8_t* seqs, int k, int64_t n, const double*, double* tm, double*, double*) {
-    g_seqs.assign(seqs, seqs + n * k);
-    g_n = n;
-    for (int64_t i = 0; i < n; ++i) tm[i] = 50.0 + (double)(i % 7);
+// every expansion "has" Tm 50.00 + 0.01 * (its primer index % 7): sums are then known in closed form
+extern "C" int mpb_tm_sets(mpb_ctx*, const uint8_t* sets, int k, int32_t n, const double*, int64_t* sums, int32_t* ties) {
+    for (int i = 0; i < n; ++i) {
+        int nd = 0;
+        sums[i] = (int64_t)degeneracy_of(sets + (int64_t)i * 32, k, &nd) * (5000 + i % 7);
+        ties[i] = 0;
+    }
     return 0;
 }
 
-// runs mpb_primer_props and returns the number of expansion rows handed to mpb_tm (copied to out, up to cap rows)
-// (gc, flags: the GC content and filter flags it computed; the Tm mean is meaningless here)
-extern "C" int64_t props_expansions(const uint8_t* sets, int k, int32_t n, uint8_t* out, int64_t cap, int32_t* deg,
-                                    double* gc, int32_t* flags) {
-    std::vector<double> tm(n);
-    std::vector<int32_t> ndeg(n);
+extern "C" int props_host(const uint8_t* sets, int k, int32_t n, int32_t* deg, int32_t* ndeg, double* tm, double* gc,
+                          int32_t* flags) {
     const double consts[3] = {0, 0, 0};
-    int rc = mpb_primer_props(reinterpret_cast<mpb_ctx*>(&g_n), sets, k, n, 0.4, 0.6, 4, consts, tm.data(), gc, flags, deg,
-                              ndeg.data());
-    if (rc) return rc;
-    const int64_t take = g_n < cap ? g_n : cap;
-    memcpy(out, g_seqs.data(), (size_t)take * k);
-    return g_n;
+    int dummy = 0;
+    return mpb_primer_props(reinterpret_cast<mpb_ctx*>(&dummy), sets, k, n, 0.4, 0.6, 4, consts, tm, gc, flags, deg, ndeg);
 }
