@@ -362,8 +362,11 @@ def run_b200(args):
         e0.record()
         t0 = time.perf_counter()
         nrows = 0
+        per_step = []
         for _ in range(args.steps):
+            ts = time.perf_counter()
             nrows = len(fn())
+            per_step.append(1000 * (time.perf_counter() - ts))
         e1.record()
         barrier()
         wall = time.perf_counter() - t0
@@ -372,7 +375,8 @@ def run_b200(args):
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        results[name] = {"ms": float(t.item()), "rows": nrows}
+        results[name] = {"ms": float(t.item()), "rows": nrows,
+                         "per_step": [round(min(per_step), 2), round(statistics.median(per_step), 2), round(max(per_step), 2)]}
         if name == "value":
             sampler.stop_flag.set()
             results["launches"] = app.ctx.launches - launches0
@@ -430,7 +434,9 @@ def run_b200(args):
         "clocks": sampler.summary(),
         "e2e": {"value": evals_all / (e2e_ms / 1000), "unit": "evals/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": int(results["value"]["rows"] * 120), "ms_per_step": e2e_ms,
+                "host_ms_min_median_max": results["e2e"]["per_step"],
                 "setup_ms_per_step": {kk: round(vv / args.steps, 2) for kk, vv in e2e_init.items()}},
+        "host_ms_min_median_max": results["value"]["per_step"],
         "gpu_launches": int(results["launches"]),
         "roofline": roof,
         "roofline_scan": roofline_of("k_cscan"),
