@@ -49,6 +49,9 @@ def parse_args():
     ap.add_argument("--cpu-sample-windows", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--parity-seqs", type=int, default=1 << 18, help="rows of the untimed sharded-parity check (N>1)")
+    ap.add_argument("--workload", default="scan", choices=["scan", "dimer"],
+                    help="scan: the headline metric (default); dimer: BASELINE.json configs[4], all-pairs dimer grid")
+    ap.add_argument("--primers", type=int, default=100_000, help="primers of the dimer workload")
     return ap.parse_args()
 
 
@@ -458,9 +461,82 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def run_dimer(args):
+    """secondary metric (BASELINE.json configs[4]): primer pairs per second of the all-pairs dimer grid (finDimer
+    semantics, threshold 3.96) on P synthetic 18-mers with ~6 % two-fold positions.  The grid is a set of independent
+    units: with N ranks the row bands are dealt round-robin and the sparse hit lists gathered (strong scaling)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from multiprime_b200 import _lib
+    from multiprime_b200.dimer import dg_consts, loss_table
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    comm = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        from multiprime_b200.comm import TorchComm
+        comm = TorchComm(torch.device("cuda", local))
+    P = args.primers
+    rng = np.random.default_rng(5)
+    sets = (1 << rng.integers(0, 4, (P, 18))).astype(np.uint8)
+    amb = rng.random((P, 18)) < 0.06
+    sets[amb] |= (1 << rng.integers(0, 4, int(amb.sum()))).astype(np.uint8)
+    sets_list = [row.tolist() for row in sets]
+    ctx = _lib.Context.shared(local, torch.cuda.current_stream().cuda_stream)
+    eng = _lib.Dimer(ctx, sets_list, 5, 18, True, loss_table(3.96), dg_consts())
+    band = max(1, min(P, (1 << 25) // P * 8))
+    bands = list(range(0, P, band))
+
+    def step():
+        hits = tested = 0
+        for b, r0 in enumerate(bands):
+            if b % world != rank:
+                continue
+            hi, hj, ho, hd, nt = eng.grid(r0, min(P, r0 + band), max_hits=1 << 24)
+            hits += len(hi)
+            tested += nt
+        tot = np.array([hits, tested], np.int64)
+        return comm.allreduce_sum(tot) if comm else tot
+
+    for _ in range(min(args.warmup, 1)):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = ctx.launches
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        tot = step()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    pairs = P * (P + 1) // 2
+    if rank == 0:
+        print(json.dumps({"metric": "dimer_pairs_per_sec", "value": pairs * args.steps / dt, "unit": "pairs/s",
+                          "n_gpus": world, "steps": args.steps, "warmup": min(args.warmup, 1),
+                          "ms_per_step": 1000 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
+                          "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+                          "config": {"workload": "all-pairs dimer grid, %d synthetic 18-mers (~6%% two-fold positions), "
+                                                 "threshold 3.96" % P, "pairs": pairs,
+                                     "pairs_after_5mer_prefilter": int(tot[1]), "dimer_pairs": int(tot[0]),
+                                     "parallelism": "row bands round-robin over %d ranks, hit counts all-reduced" % world},
+                          "gpu_launches": int(ctx.launches - launches0)}))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 if __name__ == "__main__":
     a = parse_args()
-    if a.impl == "reference":
+    if a.workload == "dimer":
+        run_dimer(a)
+    elif a.impl == "reference":
         run_reference(a)
     else:
         run_b200(a)

@@ -289,6 +289,12 @@ int mpb_window_cells(const uint8_t* packed, int64_t row_stride, const int32_t* l
 int mpb_pair_cover(mpb_ctx* ctx, const uint32_t* uf_hd, const uint32_t* ur_hd, int32_t n_rows, int32_t words,
                    const int32_t* pf_hd, const int32_t* pr_hd, int64_t n_pairs, int32_t* uncovered_hd);
 
+/* The same straight from the scan's bit vectors bits[n_rows*3*words] (hd; mpb_cscan layout: F non-cover, R non-cover,
+ * gap rows per candidate): uncovered[q] = popcount(F[pf] | gap[pf] | R[pr] | gap[pr]).  SURVEY.md 8f-1: the pairing
+ * step reads the scan's output where it lies, no JSON side files in between. */
+int mpb_pair_cover3(mpb_ctx* ctx, const uint32_t* bits_hd, int32_t n_rows, int64_t words, const int32_t* pf_hd,
+                    const int32_t* pr_hd, int64_t n_pairs, int32_t* uncovered_hd);
+
 /* ---- primer-dimer predicates: core:457-503 dimer_check, finDimer_V4.py:191-224 ---------------------------------
  * sets[n*32] 4-bit base sets of n primers (one byte per position, row stride 32), lens[n] (host arrays).
  * Ends = suffixes of length min(max_end, len) .. min_end (max_end <= 0: len + max_end .. min_end, the

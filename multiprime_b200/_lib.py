@@ -78,6 +78,7 @@ SIGNATURES = {
                                    _P]),
     "mpb_window_cells": (C.c_int, [_P, C.c_int64, _P, C.c_int32, C.c_int, C.c_int64, _P, _P, _P, _P]),
     "mpb_pair_cover": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P, _P, C.c_int64, _P]),
+    "mpb_pair_cover3": (C.c_int, [_P, _P, C.c_int32, C.c_int64, _P, _P, C.c_int64, _P]),
     "mpb_dimer_prepare": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int, C.c_int, C.c_int, _P, _P, C.POINTER(_P)]),
     "mpb_dimer_free": (None, [_P]),
     "mpb_dimer_counts": (C.c_int, [_P, _P, _P]),
@@ -314,6 +315,19 @@ class Context:
         if len(pf):
             check(load().mpb_pair_cover(self.h, ptr(uf), ptr(ur), uf.shape[0], uf.shape[1], ptr(pf), ptr(pr), len(pf),
                                         ptr(out)))
+        return out
+
+    def pair_cover3(self, bits, pf, pr) -> np.ndarray:
+        """popcount(F[pf] | gap[pf] | R[pr] | gap[pr]) per pair on the scan's bit vectors bits[n, 3, words] (numpy or a
+        DevBuf left in HBM by Hist.cscan)"""
+        pf = np.ascontiguousarray(pf, dtype=np.int32)
+        pr = np.ascontiguousarray(pr, dtype=np.int32)
+        out = np.zeros(len(pf), np.int32)
+        shape = bits.shape
+        if isinstance(bits, np.ndarray):
+            bits = np.ascontiguousarray(bits, dtype=np.uint32)
+        if len(pf):
+            check(load().mpb_pair_cover3(self.h, ptr(bits), shape[0], shape[2], ptr(pf), ptr(pr), len(pf), ptr(out)))
         return out
 
     def close(self):

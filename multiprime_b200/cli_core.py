@@ -37,6 +37,7 @@ def parseArg(argv=None):
                         metavar="<int>")
     parser.add_argument("-o", "--out", type=str, required=True, help="output file", metavar="<file>")
     parser.add_argument("--device", type=int, default=0, help=argparse.SUPPRESS)
+    parser.add_argument("--sidecars", default="auto", choices=["auto", "json", "bits"], help=argparse.SUPPRESS)
     return parser.parse_args(argv)
 
 
@@ -80,7 +81,7 @@ def main(argv=None):
                         number_of_dege_bases=args.dnum, score_of_dege_bases=args.degeneracy,
                         raw_entropy_threshold=args.entropy, product_len=args.size, position=args.coordinate,
                         variation=args.variation, distance=args.away, GC=args.gc, nproc=args.proc, outfile=args.out,
-                        **extra)
+                        sidecar_format=args.sidecars, want_trace=False, **extra)
     app.run()
     app.close()
     if "comm" in extra:

@@ -196,7 +196,7 @@ class NN_degenerate(object):
                  product_len=250, position="2,-1", variation=2, raw_entropy_threshold=3.6, distance=4, GC="0.4,0.6",
                  nproc=10, outfile="", device=0, windows_per_batch=0, sidecars=True, alignment=None, packed=None,
                  stream=None, comm=None, row0=0, want_trace=True, keep_bits=False, rows_on_rank0_only=False,
-                 _backend=None):
+                 sidecar_format="auto", _backend=None):
         self.primer_length = primer_length
         self.coverage = coverage
         self.number_of_dege_bases = number_of_dege_bases
@@ -214,6 +214,7 @@ class NN_degenerate(object):
         self.keep_bits = keep_bits              # keep the per-sequence F / R / gap bit vectors of every row (pairing)
         self.bit_vectors = []
         self.rows_on_rank0_only = rows_on_rank0_only   # sharded runs: the replicated row assembly on rank 0 only
+        self.sidecar_format = sidecar_format    # run(): "json" (the reference's two files), "bits", "auto" by size
         self.windows_per_batch = windows_per_batch
         if not 3 <= primer_length <= _lib.MAX_K:
             raise ValueError("primer length must be within 3..%d" % _lib.MAX_K)
@@ -833,16 +834,35 @@ class NN_degenerate(object):
 
     # -- core:1133-1180 -------------------------------------------------------------------------------------
     def run(self):
+        """core:1133-1180: the .out TSV and the side files.  The reference's JSON side files list sequence ids per
+        uncovered haplotype and window — megabytes at 500 sequences, unusable at 10^6 — so above SIDE_JSON_MAX sequences
+        (or with sidecar_format="bits") the same information is written as per-sequence bit vectors instead
+        (<out>.coverage_bits.npz: F non-cover / R non-cover / gap row per chosen primer), which is what the pairing
+        step (pairing.py) actually consumes.  Below the threshold the files are the reference's."""
         k = self.primer_length
-        recs = self.design(range(self.start_position, self.stop_position - k))
+        fmt = self.sidecar_format
+        if fmt == "auto":
+            fmt = "json" if self.total_sequence_number <= SIDE_JSON_MAX else "bits"
+        want_json = self.sidecars and fmt == "json"
+        want_bits = self.sidecars and fmt == "bits"
+        saved = (self.sidecars, self.keep_bits)
+        self.sidecars, self.keep_bits = want_json, want_bits or self.keep_bits
+        try:
+            recs = self.design(range(self.start_position, self.stop_position - k))
+        finally:
+            self.sidecars, self.keep_bits = saved[0], saved[1]
         recs.sort(key=lambda r: r["row"][0])
         if self.comm.rank == 0:
             with open(self.outfile, "w") as fo:
                 fo.write("\t".join(TSV_HEADER) + "\n")
                 for r in recs:
                     fo.write("\t".join(map(str, r["row"])) + "\n")
-        non_cov = {r["row"][0]: r["non_cov"] for r in recs} if self.sidecars else {}
-        gap_ids = {r["row"][0]: r["gap_ids"] for r in recs} if self.sidecars else {}
+        if want_bits:
+            self.write_bits(self.outfile)
+        if not want_json:
+            return recs
+        non_cov = {r["row"][0]: r["non_cov"] for r in recs}
+        gap_ids = {r["row"][0]: r["gap_ids"] for r in recs}
         if self.comm.world > 1:                 # shards hold disjoint id lists: concatenate them in rank order
             non_cov, gap_ids = _merge_sidecars(self.comm.allgather_object((non_cov, gap_ids)))
             if self.comm.rank != 0:
@@ -852,6 +872,24 @@ class NN_degenerate(object):
         with open(self.outfile + ".gap_seq_id_json", "w") as fg:
             json.dump(gap_ids, fg, indent=4)
         return recs
+
+    def coverage_bits(self):
+        """(positions int32[n], bits uint32[n, 3, words]) of the last design(): F non-cover, R non-cover and gap-row
+        bit vectors of every chosen primer over this process's sequences (host copy)"""
+        pos, bits = [], []
+        for p, b in self.bit_vectors:
+            pos.append(np.asarray(p, np.int32))
+            bits.append(b.to_host() if hasattr(b, "to_host") else np.asarray(b))
+        words = (self.n_local + 31) // 32
+        if not pos:
+            return np.zeros(0, np.int32), np.zeros((0, 3, words), np.uint32)
+        return np.concatenate(pos), np.concatenate(bits)[:, :, :words]
+
+    def write_bits(self, out: str):
+        """<out>.coverage_bits.npz (one per rank in a sequence-sharded run: shards hold disjoint sequences)"""
+        pos, bits = self.coverage_bits()
+        np.savez(bits_file(out, self.comm.rank, self.comm.world), positions=pos, bits=bits, n_local=self.n_local,
+                 row0=self.row0, n_total=self.total_sequence_number, world=self.comm.world)
 
     def close(self):
         self.msa.close()
@@ -872,6 +910,13 @@ def _merge_sidecars(parts):
             for hap, ids in d.items():
                 tgt.setdefault(hap, []).extend(ids)
     return non_cov, gap_ids
+
+
+SIDE_JSON_MAX = 20000      # sequences up to which run() writes the reference's JSON side files
+
+
+def bits_file(out: str, rank: int = 0, world: int = 1) -> str:
+    return out + (".coverage_bits.npz" if world == 1 else ".coverage_bits.%dof%d.npz" % (rank, world))
 
 
 class _AllMerged:

@@ -2092,3 +2092,37 @@ extern "C" int mpb_pair_cover(mpb_ctx* ctx, const uint32_t* uf_hd, const uint32_
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
+
+// The same straight from the scan's bit vectors (mpb_cscan / mpb_scan layout bits[row][3][words]: F non-cover, R
+// non-cover, gap rows): the forward use of candidate pf leaves F | gap uncovered, the reverse use of pr leaves R | gap
+// (get_multiPrime.py:556-569 on the ids of the two JSON side files).  No JSON round trip: SURVEY.md 8f-1.
+__global__ void k_pair_cover3(const uint32_t* __restrict__ bits, const int32_t* __restrict__ pf,
+                              const int32_t* __restrict__ pr, long long n_pairs, long long words,
+                              int32_t* __restrict__ out) {
+    const long long q = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // warp per pair
+    const int lane = threadIdx.x & 31;
+    if (q >= n_pairs) return;
+    const uint32_t* a = bits + (long long)pf[q] * 3 * words;
+    const uint32_t* b = bits + (long long)pr[q] * 3 * words;
+    int n = 0;
+    for (long long w = lane; w < words; w += 32) n += __popc(a[w] | a[2 * words + w] | b[words + w] | b[2 * words + w]);
+    n = __reduce_add_sync(0xffffffffu, n);
+    if (lane == 0) out[q] = n;
+}
+
+extern "C" int mpb_pair_cover3(mpb_ctx* ctx, const uint32_t* bits_hd, int32_t n_rows, int64_t words, const int32_t* pf_hd,
+                               const int32_t* pr_hd, int64_t n_pairs, int32_t* uncovered_hd) {
+    if (!ctx || !bits_hd || !pf_hd || !pr_hd || !uncovered_hd) return fail(MPB_EINVAL, "NULL argument");
+    if (n_pairs < 1) return 0;
+    CK(cudaSetDevice(ctx->device));
+    InBuf bt(ctx, bits_hd, (size_t)n_rows * 3 * words * 4), pf(ctx, pf_hd, (size_t)n_pairs * 4), pr(ctx, pr_hd, (size_t)n_pairs * 4);
+    OutBuf o(ctx, uncovered_hd, (size_t)n_pairs * 4);
+    if (bt.rc || pf.rc || pr.rc || o.rc) return MPB_ECUDA;
+    ctx->pending_units = (double)n_pairs;
+    LAUNCH(ctx, k_pair_cover3, (unsigned)((n_pairs * 32 + 255) / 256), 256, 0, bt.dev<uint32_t>(), pf.dev<int32_t>(),
+           pr.dev<int32_t>(), (long long)n_pairs, (long long)words, o.dev<int32_t>());
+    CK(o.finish());
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+

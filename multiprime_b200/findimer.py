@@ -118,9 +118,10 @@ class Dimer(object):
             n_p = np.diff(eng.off_p)
         finally:
             eng.close()
-        if self.comm and world > 1:
-            parts = self.comm.allgather_object(hits)
-            hits = sorted(h for part in parts for h in part)
+        if self.comm and world > 1:              # hit lists of the ranks: one variable-length gather of int64 quadruples
+            flat, _ = self.comm.allgather_concat(np.array(hits, np.int64).reshape(-1))
+            hits = sorted(tuple(int(x) for x in h) for h in flat.reshape(-1, 4))
+            tested = int(self.comm.allreduce_sum(np.array([tested], np.int64))[0])
         self.pairs_tested = tested
         rows = []
         for i, j, order, d2 in hits:
@@ -151,15 +152,39 @@ class Dimer(object):
         return rows
 
 
+def shard_setup(device: int):
+    """under torchrun: one rank per GPU (NCCL; MPB_DIST_BACKEND=gloo for ranks that share a GPU).  The pair grid is a set
+    of independent units: row bands are dealt round-robin, the sparse hit lists gathered."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1:
+        return {"device": device}, 0
+    import torch
+    import torch.distributed as dist
+    from .comm import TorchComm
+    rank, local = int(os.environ["RANK"]), int(os.environ.get("LOCAL_RANK", "0"))
+    backend = os.environ.get("MPB_DIST_BACKEND", "nccl")
+    dev = local if backend == "nccl" else device
+    if backend == "nccl":
+        torch.cuda.set_device(dev)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
+    else:
+        dist.init_process_group(backend)
+    return {"device": dev, "comm": TorchComm()}, rank
+
+
 def main(argv=None):
     e1 = time.time()
     args = parseArg(argv)
-    app = Dimer(primer_file=args.input, threshold=args.threshold, outfile=args.output, nproc=args.num,
-                device=args.device)
+    extra, rank = shard_setup(args.device)
+    app = Dimer(primer_file=args.input, threshold=args.threshold, outfile=args.output, nproc=args.num, **extra)
     app.run()
+    if "comm" in extra:
+        import torch.distributed as dist
+        dist.destroy_process_group()
     e2 = time.time()
-    print("INFO {} Total times: {}".format(time.strftime("%Y-%m-%d %H:%M:%S", time.localtime(time.time())),
-                                           round(float(e2 - e1), 2)))
+    if rank == 0:
+        print("INFO {} Total times: {}".format(time.strftime("%Y-%m-%d %H:%M:%S", time.localtime(time.time())),
+                                               round(float(e2 - e1), 2)))
 
 
 if __name__ == "__main__":

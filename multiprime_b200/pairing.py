@@ -100,7 +100,8 @@ class Primers_filter(object):
     """get_multiPrime.py:303-321 constructor arguments"""
 
     def __init__(self, ref_file, primer_file, adaptor, rep_seq_number=500, distance=4, outfile="", diff_Tm=5,
-                 size="300,700", position=9, GC="0.4,0.6", nproc=10, fraction=0.6, device=0, _backend=None):
+                 size="300,700", position=9, GC="0.4,0.6", nproc=10, fraction=0.6, device=0, comm=None, coverage=None,
+                 rows=None, number=None, _backend=None):
         self.nproc = nproc
         self.primer_file = primer_file
         self.adaptor = adaptor
@@ -112,15 +113,35 @@ class Primers_filter(object):
         self.GC = GC
         self.diff_Tm = diff_Tm
         self.rep_seq_number = rep_seq_number
-        self.number = self.get_number()
+        self.rows = rows                          # the core step's rows handed over in-process (else read from primer_file)
+        self.number = number if number is not None else self.get_number()
         self.position = position
+        from .comm import NoComm
+        self.comm = comm or NoComm()              # sequence shards: every rank holds the bit vectors of its sequences
+        self.coverage = coverage                  # (positions, bits[n, 3, words]) handed over in-process, or None
         self.primers, self.gap_id, self.non_cover_id = self.parse_primers()
         self._backend = _backend or _lib          # tests inject tests/fake_device.py
-        self.ctx = self._backend.Context(device)
+        self.ctx = self._backend.Context.shared(device) if hasattr(self._backend.Context, "shared") else \
+            self._backend.Context(device)
         self.pre_filter_primers = self.pre_filter()
+
+    @classmethod
+    def from_core(cls, app, recs, outfile, **kw):
+        """pair the rows of a core run (multiprime_b200.core.NN_degenerate, keep_bits=True) in the same process: the
+        scan's bit vectors are read where design() left them (in HBM), no files in between"""
+        pos = np.concatenate([np.asarray(p, np.int32) for p, _ in app.bit_vectors]) if app.bit_vectors else np.zeros(0, np.int32)
+        bits = app.bit_vectors[0][1] if len(app.bit_vectors) == 1 else app.coverage_bits()[1]
+        return cls(ref_file=None, primer_file=None, outfile=outfile, rows=[r["row"] for r in recs], coverage=(pos, bits),
+                   number=app.total_sequence_number, comm=app.comm if app.comm.world > 1 else None,
+                   device=getattr(app.ctx, "device", 0), **kw)
 
     def parse_primers(self):
         primer_dict = {}
+        if self.rows is not None:
+            for r in self.rows:
+                primer_dict[int(r[0])] = [r[3], round(int(r[6]) / self.number, 2), int(r[7]), int(r[8]),
+                                          round(float(r[9]), 2)]
+            return primer_dict, None, None
         with open(self.primer_file) as f:
             for line in f:
                 if line.startswith("Pos"):
@@ -128,6 +149,20 @@ class Primers_filter(object):
                 i = line.strip().split("\t")
                 primer_dict[int(i[0])] = [i[3], round(int(i[6]) / self.number, 2), int(i[7]), int(i[8]),
                                           round(float(i[9]), 2)]
+        # coverage information of the core step: its per-sequence bit vectors when they exist (handed over in-process,
+        # or <input>.coverage_bits*.npz written above core.SIDE_JSON_MAX sequences), else the reference's JSON side files
+        from .core import bits_file
+        if self.coverage is None:
+            path = bits_file(self.primer_file, self.comm.rank, self.comm.world)
+            if os.path.exists(path):
+                z = np.load(path)
+                if int(z["world"]) != self.comm.world:
+                    raise SystemExit("Error: %s was written by %d ranks" % (path, int(z["world"])))
+                self.coverage = (z["positions"], z["bits"])
+        if self.coverage is not None:
+            return primer_dict, None, None
+        if self.comm.world > 1:
+            raise SystemExit("Error: a sharded pairing run needs the core step's coverage_bits files")
         with open(self.primer_file + ".gap_seq_id_json") as g:
             gap_dict = json.load(g)
         with open(self.primer_file + ".non_coverage_seq_id_json") as n:
@@ -191,15 +226,33 @@ class Primers_filter(object):
                             arr[r, j >> 5] |= np.uint32(1 << (j & 31))
         return uf, ur
 
+    def _pair_uncovered(self, cand, pairs):
+        """sequences a (forward, reverse) pair leaves uncovered (get_multiPrime.py:556-569), for all pairs at once"""
+        if not pairs:
+            return []
+        pf, pr = [p[0] for p in pairs], [p[1] for p in pairs]
+        if self.coverage is None:                 # from the id lists of the JSON side files
+            uf, ur = self._uncovered_bits(cand)
+            return self.ctx.pair_cover(uf, ur, pf, pr)
+        # from the scan's own bit vectors: popcount(F | gap | R' | gap') on the device; sequence shards add up
+        positions, bits = self.coverage
+        row_of = {int(p): i for i, p in enumerate(np.asarray(positions).tolist())}
+        rows = np.array([row_of[int(p)] for p in cand], np.int32)
+        unc = self.ctx.pair_cover3(bits, rows[pf], rows[pr]).astype(np.int64)
+        return self.comm.allreduce_sum(unc) if self.comm.world > 1 else unc
+
     def run(self):
         min_len, max_len = (int(x) for x in self.size.split(","))
         cand = self.pre_filter_primers
         adaptor = self.adaptor.split(",")
-        print("Candidata degenerate primer number is: {}".format(len(cand)))
+        chief = self.comm.rank == 0
+        say = print if chief else (lambda *a, **k: None)
+        say("Candidata degenerate primer number is: {}".format(len(cand)))
         if int(cand[-1]) - int(cand[0]) < min_len:
-            print("Max PCR product legnth < min len!")
-            with open(self.outfile, "w") as fo:
-                fo.write(str(self.outfile) + "\n")
+            say("Max PCR product legnth < min len!")
+            if chief:
+                with open(self.outfile, "w") as fo:
+                    fo.write(str(self.outfile) + "\n")
             return []
         n = len(cand)
         fwd = [self.primers[p][0] for p in cand]
@@ -239,24 +292,29 @@ class Primers_filter(object):
                 self_hit = eng.pairs(idx, idx)[0] >= 0
                 ps = np.array([p[0] for p in pairs], np.int32)
                 pt = np.array([p[1] for p in pairs], np.int32) + n
-                cross = (eng.pairs(ps, pt)[0] >= 0) | (eng.pairs(pt, ps)[0] >= 0)
+                if self.comm.world > 1:        # the pair list is dealt round-robin to the ranks, the hit flags added up
+                    mine = np.arange(self.comm.rank, len(pairs), self.comm.world)
+                    part = np.zeros(len(pairs), np.int64)
+                    part[mine] = (eng.pairs(ps[mine], pt[mine])[0] >= 0) | (eng.pairs(pt[mine], ps[mine])[0] >= 0)
+                    cross = self.comm.allreduce_sum(part) > 0
+                else:
+                    cross = (eng.pairs(ps, pt)[0] >= 0) | (eng.pairs(pt, ps)[0] >= 0)
                 dimer = cross | self_hit[ps] | self_hit[pt]
             finally:
                 eng.close()
-        uf, ur = self._uncovered_bits(cand)
-        uncovered = self.ctx.pair_cover(uf, ur, [p[0] for p in pairs], [p[1] for p in pairs]) if pairs else []
+        uncovered = self._pair_uncovered(cand, pairs)
         out = []
 
         def one_pass(threshold, echo):
             for s in range(n):
                 if echo:                       # get_multiPrime.py:620 prints the index in the first pass only
-                    print(s)
+                    say(s)
                 for t, q in per_start[s]:
                     if q == "break":
-                        print("Error! PCR product greater than max length !")
+                        say("Error! PCR product greater than max length !")
                         break
                     if dimer[q]:
-                        print("Dimer detection between Primer-F and Primer-R!")
+                        say("Dimer detection between Primer-F and Primer-R!")
                         continue
                     tm_f, tm_r = self.primers[cand[s]][4], self.primers[cand[t]][4]
                     if abs(tm_f - tm_r) > self.diff_Tm:
@@ -275,6 +333,8 @@ class Primers_filter(object):
         if len(out) < 10:
             coverage_threshold += 0.1
             one_pass(coverage_threshold, False)
+        if not chief:
+            return out
         ID = str(self.outfile)
         primer_ID = str(self.outfile).split("/")[-1].rstrip(".txt")
         with open(self.outfile, "w") as fo, open(self.outfile.strip(".txt") + ".xls", "w") as fo_xls, \
@@ -291,16 +351,42 @@ class Primers_filter(object):
         return out
 
 
+def _shard_setup(args):
+    """under torchrun: one rank per GPU (NCCL; MPB_DIST_BACKEND=gloo for ranks that share a GPU), every rank reads the
+    coverage_bits shard the core step wrote for it (get_multiPrime.py:509-582 / SURVEY.md 8e: pair coverage is a
+    popcount over sequences, so sequence shards add up; the F-R dimer tests are dealt to the ranks)"""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1:
+        return {"device": args.device}, 0
+    import torch
+    import torch.distributed as dist
+    from .comm import TorchComm
+    rank, local = int(os.environ["RANK"]), int(os.environ.get("LOCAL_RANK", "0"))
+    backend = os.environ.get("MPB_DIST_BACKEND", "nccl")
+    device = local if backend == "nccl" else args.device
+    if backend == "nccl":
+        torch.cuda.set_device(device)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", device))
+    else:
+        dist.init_process_group(backend)
+    return {"device": device, "comm": TorchComm()}, rank
+
+
 def main(argv=None, _backend=None):
     e1 = time.time()
     args = parseArg(argv)
+    extra, rank = _shard_setup(args)
     app = Primers_filter(ref_file=args.ref, primer_file=args.input, adaptor=args.adaptor, rep_seq_number=args.maxseq,
                          distance=args.dist, outfile=args.out, size=args.size, position=args.end, fraction=args.fraction,
-                         diff_Tm=args.Tm, nproc=args.proc, device=args.device, _backend=_backend)
+                         diff_Tm=args.Tm, nproc=args.proc, _backend=_backend, **extra)
     app.run()
+    if "comm" in extra:
+        import torch.distributed as dist
+        dist.destroy_process_group()
     e2 = time.time()
-    print("INFO {} Total times: {}".format(time.strftime("%Y-%m-%d %H:%M:%S", time.localtime(time.time())),
-                                           round(float(e2 - e1), 2)))
+    if rank == 0:
+        print("INFO {} Total times: {}".format(time.strftime("%Y-%m-%d %H:%M:%S", time.localtime(time.time())),
+                                               round(float(e2 - e1), 2)))
 
 
 if __name__ == "__main__":

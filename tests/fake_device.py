@@ -67,6 +67,11 @@ class Context:
     def pair_cover(self, uf, ur, pf, pr):
         return np.array([int(np.unpackbits((uf[a] | ur[b]).view(np.uint8)).sum()) for a, b in zip(pf, pr)], np.int32)
 
+    def pair_cover3(self, bits, pf, pr):
+        bits = np.asarray(bits)
+        return np.array([int(np.unpackbits((bits[a, 0] | bits[a, 2] | bits[b, 1] | bits[b, 2]).view(np.uint8)).sum())
+                         for a, b in zip(pf, pr)], np.int32)
+
     def dimer_flags(self, sets_list):
         return np.array([o.self_dimer("".join(CODE_CHARS[c] for c in s)) for s in sets_list], bool)
 

@@ -200,6 +200,52 @@ def test_get_multiprime_golden(tmp_path, tag):
     assert strip(res.stdout) == strip(want["stdout"])
 
 
+@pytest.mark.parametrize("tag,world", [("a", 1), ("b", 1), ("a", 2)])
+def test_core_to_pairing_through_bit_vectors(tmp_path, tag, world):
+    """the core CLI writes per-sequence bit vectors (--sidecars bits) instead of the JSON side files
+    and the get_multiPrime drop-in takes its pair coverage from them on the device; with two ranks (torchrun, gloo, one
+    GPU) both steps run sequence-sharded.  The reference's three output files come out byte for byte."""
+    import json
+    import os
+    import subprocess
+    import sys
+    from multiprime_b200 import synth
+    from tests.helpers import GOLDEN
+    g = json.load(open(os.path.join(GOLDEN, "pairs_get_multiprime.json")))
+    n, L, seed, gr, ir = g["synth"]
+    fa = tmp_path / "in.fa"
+    synth.write_fasta(str(fa), synth.synth_codes(n, L, seed=seed, gap_rate=gr, iupac_rate=ir))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    core_out = tmp_path / "c.out"
+    env = dict(os.environ, MPB_DIST_BACKEND="gloo")
+    launch = [sys.executable]
+    if world > 1:
+        import socket
+        sk = socket.socket()
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+        sk.close()
+        launch = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+                  "--master-addr", "127.0.0.1", "--master-port", str(port)]
+    res = subprocess.run(launch + [os.path.join(root, "scripts", "multiPrime-core.py"), "-i", str(fa), "-o", str(core_out),
+                                   "-l", "18", "-n", "4", "-d", "10", "-v", "1", "-p", "1", "--sidecars", "bits"],
+                         capture_output=True, text=True, env=env, timeout=600)
+    assert res.returncode == 0, res.stderr[-3000:]
+    assert core_out.read_text() == g["core_tsv"]
+    assert not os.path.exists(str(core_out) + ".gap_seq_id_json")
+    out = tmp_path / ("Cluster_%s.candidate.primers.txt" % tag)
+    want = g[tag]
+    res = subprocess.run(launch + [os.path.join(root, "scripts", "get_multiPrime.py"), "-i", str(core_out), "-r", str(fa),
+                                   "-o", str(out)] + want["args"], capture_output=True, text=True, env=env, timeout=600)
+    assert res.returncode == want["rc"], res.stderr[-3000:]
+    stem = str(out).strip(".txt")
+    assert out.read_text().replace(str(tmp_path), "<TMP>") == want["txt"]
+    assert open(stem + ".xls").read() == want["xls"]
+    assert open(stem + ".fa").read() == want["fa"]
+    strip = lambda text: [ln for ln in text.replace(str(tmp_path), "<TMP>").splitlines() if not ln.startswith("INFO")]
+    assert strip(res.stdout) == strip(want["stdout"])
+
+
 def test_prefilter_matches_definition():
     """mpb_window_prefilter: item counts and sum(c log2 c) of the coarse bins equal the plain-Python definition, and
     the bound never exceeds the reference's total entropy"""

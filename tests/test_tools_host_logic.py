@@ -59,3 +59,50 @@ def test_get_multiprime(tmp_path, tag, capsys):
     assert out.read_text().replace(str(tmp_path), "<TMP>") == want["txt"]
     assert open(stem + ".xls").read() == want["xls"]
     assert open(stem + ".fa").read() == want["fa"]
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_get_multiprime_from_bit_vectors(tmp_path, tag, capsys):
+    """the core step writes per-sequence bit vectors instead of the JSON side files and the pairing step
+    takes its pair coverage from them — the reference's three output files must come out byte for byte"""
+    from multiprime_b200 import cli_core, core, pairing, synth
+    g = _load("pairs_get_multiprime.json")
+    n, L, seed, gr, ir = g["synth"]
+    fa = tmp_path / "in.fa"
+    synth.write_fasta(str(fa), synth.synth_codes(n, L, seed=seed, gap_rate=gr, iupac_rate=ir))
+    core_out = tmp_path / "c.out"
+    ids, codes, lens = core.parse_msa(str(fa))
+    app = core.NN_degenerate(seq_file=None, primer_length=18, coverage=0.8, number_of_dege_bases=4, score_of_dege_bases=10,
+                             raw_entropy_threshold=3.6, product_len=100, position="1,2,-1", variation=1, distance=4,
+                             GC="0.2,0.7", nproc=1, outfile=str(core_out), alignment=(ids, codes, lens),
+                             sidecar_format="bits", want_trace=False, _backend=fake_device)
+    app.run()
+    assert core_out.read_text() == g["core_tsv"]
+    assert os.path.exists(str(core_out) + ".coverage_bits.npz")
+    assert not os.path.exists(str(core_out) + ".gap_seq_id_json")
+    out = tmp_path / ("Cluster_%s.candidate.primers.txt" % tag)
+    want = g[tag]
+    pairing.main(["-i", str(core_out), "-r", str(fa), "-o", str(out)] + want["args"], _backend=fake_device)
+    stem = str(out).strip(".txt")
+    assert out.read_text().replace(str(tmp_path), "<TMP>") == want["txt"]
+    assert open(stem + ".xls").read() == want["xls"]
+    assert open(stem + ".fa").read() == want["fa"]
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_findimer_row_bands_over_ranks(tmp_path, world):
+    """the dimer grid's row bands dealt over ranks (threads + loop-back communicator + the stand-in
+    engine) and the hit lists gathered give the reference's rows"""
+    from multiprime_b200 import findimer
+    from tests.loopback_comm import run_shards
+    g = _load("dimer_findimer.json")
+    fa = tmp_path / "p.fa"
+    fa.write_text("".join(">P%03d\n%s\n" % (i, p) for i, p in enumerate(g["primers"])))
+
+    def shard(rank, comm):
+        app = findimer.Dimer(primer_file=str(fa), outfile=str(tmp_path / ("o%d.txt" % rank)), threshold=g["threshold"],
+                             nproc=1, comm=comm, _backend=fake_device)
+        return app.find(rows_per_band=20)
+
+    for rows in run_shards(world, shard):
+        assert [list(r) for r in rows] == g["rows"]
