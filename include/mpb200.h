@@ -199,6 +199,15 @@ typedef struct mpb_cand {
 int mpb_cscan(mpb_hist* h, uint32_t fmask, uint32_t rmask, const mpb_cand* cands_hd, int64_t nc, int64_t* counts_hd,
               const int32_t* bits_slot, uint32_t* bits_hd);
 
+/* Exhaustive exact search (extract_PCR_product_V1.py:189-216 get_PCR_PRODUCT): every position of every
+ * sequence of the alignment handle (an unaligned FASTA uploaded as ragged rows) against n_pat degenerate patterns
+ * (allow[n_pat*4] allowed-base masks, lens[n_pat] <= 32; host arrays).  Host outputs of capacity max_hits receive
+ * (pattern, sequence, position) of every occurrence of an expansion, unordered; *n_hits may exceed max_hits (then call
+ * again with more room).  A cell that is not exactly one base (IUPAC code, N, gap) never matches, as in the reference's
+ * plain-text search. */
+int mpb_pattern_hits(mpb_msa* msa, int32_t n_pat, const uint32_t* allow, const int32_t* lens, int64_t max_hits,
+                     int32_t* hit_pat, int32_t* hit_row, int32_t* hit_pos, int64_t* n_hits);
+
 /* Per (window, sequence) haplotype key, for the JSON side files (core:1172-1176): the table key of the
  * sequence's k-mer, MPB_KEY_IUPAC for rows whose window holds IUPAC cells. out[nw*n_seq]. */
 #define MPB_KEY_IUPAC 0xFFFFFFFFFFFFFFFEull

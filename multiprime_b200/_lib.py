@@ -51,6 +51,7 @@ SIGNATURES = {
     "mpb_hist_match": (C.c_int, [_P, _P, _P, C.c_int32, _P]),
     "mpb_hist_exceptions": (C.c_int, [_P, C.c_int64, _P, _P, C.POINTER(C.c_int64)]),
     "mpb_scan": (C.c_int, [_P, C.c_int, C.c_int, C.c_uint32, C.c_uint32, _P, _P, C.c_int64, _P, _P, _P]),
+    "mpb_pattern_hits": (C.c_int, [_P, C.c_int32, _P, _P, C.c_int64, _P, _P, _P, C.POINTER(C.c_int64)]),
     "mpb_seqkeys": (C.c_int, [_P, C.c_int, _P, C.c_int32, _P]),
     "mpb_tm": (C.c_int, [_P, _P, C.c_int, C.c_int64, _P, _P, _P, _P]),
     "mpb_tm_sets": (C.c_int, [_P, _P, C.c_int, C.c_int32, _P, _P, _P]),
@@ -410,6 +411,23 @@ class Msa:
             check(load().mpb_scan(self.h, k, v, fmask, rmask, ptr(cand_pos), ptr(cand_allow), nc, ptr(counts),
                                   ptr(bits_slot), ptr(bits)))
         return counts, bits
+
+    def pattern_hits(self, allow, lens, max_hits: int = 1 << 20):
+        """mpb_pattern_hits: every exact occurrence of the degenerate patterns -> (pattern, sequence, position) arrays
+        sorted by (pattern, sequence, position)"""
+        allow = np.ascontiguousarray(allow, dtype=np.uint32).reshape(-1, 4)
+        lens = np.ascontiguousarray(lens, dtype=np.int32)
+        while True:
+            hp, hr, hx = (np.empty(max_hits, np.int32) for _ in range(3))
+            n = C.c_int64()
+            check(load().mpb_pattern_hits(self.h, len(lens), ptr(allow), ptr(lens), max_hits, ptr(hp), ptr(hr), ptr(hx),
+                                          C.byref(n)))
+            if n.value <= max_hits:
+                break
+            max_hits = int(n.value) + 16
+        n = n.value
+        order = np.lexsort((hx[:n], hr[:n], hp[:n]))
+        return hp[:n][order], hr[:n][order], hx[:n][order]
 
     def seqkeys(self, k: int, win_pos) -> np.ndarray:
         win_pos = np.ascontiguousarray(win_pos, dtype=np.int32)

@@ -465,3 +465,79 @@ extern "C" int mpb_cscan(mpb_hist* h, uint32_t fmask, uint32_t rmask, const mpb_
     CK(ob.finish());
     return mpb_check_flags(ctx, m->err);  // synchronises: host staging buffers and n32 stay alive until here
 }
+
+// ---- exhaustive pattern search -----------------------------------------------------------------------
+// Every position of every sequence against a set of degenerate patterns, exact match: the in-silico PCR of
+// extract_PCR_product_V1.py:189-216 (and the coverage validation the pipeline otherwise delegates to bowtie2) asks "where
+// does an expansion of this primer occur in this sequence".  On the column view that is the scan kernel with the window
+// start as a free variable: thread = (position, 32-sequence word); the running AND of the per-column match words dies
+// after two or three columns almost everywhere.  Hits are rare and leave as (pattern, sequence, position) triples.
+struct mpb_pattern {
+    uint32_t allow[4];
+    int32_t len;
+};
+
+__global__ void __launch_bounds__(256)
+k_pattern_hits(const uint32_t* __restrict__ colp, long long nwords, int n_col, const mpb_pattern* __restrict__ pats, int n_pat,
+               long long max_hits, int32_t* __restrict__ hit_pat, int32_t* __restrict__ hit_row, int32_t* __restrict__ hit_pos,
+               unsigned long long* __restrict__ n_hits) {
+    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int x = blockIdx.y;
+    if (w >= nwords) return;
+    for (int p = 0; p < n_pat; ++p) {
+        const mpb_pattern pt = pats[p];
+        if (x + pt.len > n_col) continue;
+        uint32_t acc = 0xFFFFFFFFu;
+        for (int i = 0; i < pt.len && acc; ++i) {
+            uint32_t m = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+                if ((pt.allow[b] >> i) & 1u) m |= __ldg(colp + ((long long)(x + i) * 4 + b) * nwords + w);
+            acc &= m;
+        }
+        while (acc) {
+            const int bit = __ffs(acc) - 1;
+            acc &= acc - 1;
+            const unsigned long long slot = atomicAdd(n_hits, 1ull);
+            if ((long long)slot < max_hits) {
+                hit_pat[slot] = p;
+                hit_row[slot] = (int32_t)(w * 32 + bit);
+                hit_pos[slot] = x;
+            }
+        }
+    }
+}
+
+extern "C" int mpb_pattern_hits(mpb_msa* m, int32_t n_pat, const uint32_t* allow, const int32_t* lens, int64_t max_hits,
+                                int32_t* hit_pat, int32_t* hit_row, int32_t* hit_pos, int64_t* n_hits) {
+    if (!m || !allow || !lens || !hit_pat || !hit_row || !hit_pos || !n_hits) return fail(MPB_EINVAL, "NULL argument");
+    if (n_pat < 1 || max_hits < 0) return fail(MPB_EINVAL, "bad n_pat or max_hits");
+    mpb_ctx* ctx = m->ctx;
+    CK(cudaSetDevice(ctx->device));
+    std::vector<mpb_pattern> pats(n_pat);
+    for (int i = 0; i < n_pat; ++i) {
+        if (lens[i] < 1 || lens[i] > 32) return fail(MPB_EINVAL, "pattern %d: length %d outside 1..32", i, lens[i]);
+        for (int b = 0; b < 4; ++b) pats[i].allow[b] = allow[i * 4 + b];
+        pats[i].len = lens[i];
+    }
+    InBuf pd(ctx, pats.data(), pats.size() * sizeof(mpb_pattern));
+    OutBuf op(ctx, hit_pat, (size_t)max_hits * 4), orow(ctx, hit_row, (size_t)max_hits * 4), opos(ctx, hit_pos, (size_t)max_hits * 4);
+    if (pd.rc || op.rc || orow.rc || opos.rc) return MPB_ECUDA;
+    unsigned long long* dn = nullptr;
+    CK(cudaMallocAsync(&dn, 8, ctx->stream));
+    CK(cudaMemsetAsync(dn, 0, 8, ctx->stream));
+    ctx->pending_units = (double)n_pat * (double)m->n_seq * (double)m->n_col;
+    LAUNCH(ctx, k_pattern_hits, dim3((unsigned)((m->nwords + 255) / 256), (unsigned)m->n_col), 256, 0, m->colp,
+           (long long)m->nwords, (int)m->n_col, pd.dev<mpb_pattern>(), (int)n_pat, (long long)max_hits, op.dev<int32_t>(),
+           orow.dev<int32_t>(), opos.dev<int32_t>(), dn);
+    unsigned long long n = 0;
+    CK(cudaMemcpyAsync(&n, dn, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(op.finish());
+    CK(orow.finish());
+    CK(opos.finish());
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaFreeAsync(dn, ctx->stream));
+    *n_hits = (int64_t)n;
+    return 0;
+}
+

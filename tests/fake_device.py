@@ -171,6 +171,20 @@ class Msa:
                             bits[sl, j, si >> 5] |= np.uint32(1 << (si & 31))
         return counts, bits
 
+    def pattern_hits(self, allow, lens, max_hits=1 << 20):
+        """mpb_pattern_hits: exact occurrences of degenerate patterns; only single-base cells can match"""
+        single = {"A": 0, "C": 1, "G": 2, "T": 3}
+        allow = np.asarray(allow).reshape(-1, 4)
+        out = []
+        for p, (al, ln) in enumerate(zip(allow, lens)):
+            for r, row in enumerate(self.rows):
+                for x in range(0, len(row) - int(ln) + 1):
+                    if all(row[x + i] in single and (int(al[single[row[x + i]]]) >> i) & 1 for i in range(int(ln))):
+                        out.append((p, r, x))
+        out.sort()
+        a = np.array(out, np.int32).reshape(-1, 3)
+        return a[:, 0], a[:, 1], a[:, 2]
+
     def seqkeys(self, k, win_pos):
         out = np.empty((len(win_pos), self.n_seq), np.uint64)
         for wi, p in enumerate(win_pos):

@@ -324,6 +324,106 @@ def make_pairs():
         json.dump(blob, fh)
 
 
+def pcr_primer_sets():
+    """primer pairs cut from test_data/test.fa itself (so that they amplify), some made degenerate, one pair whose forward
+    primer occurs twice in a genome, one with N, one that matches nothing"""
+    seqs = []
+    with open(os.path.join(REF, "test_data", "test.fa")) as fh:
+        for line in fh:
+            if not line.startswith(">"):
+                seqs.append(line.strip())
+    comp = str.maketrans("ATGC", "TACG")
+    rc = lambda x: x.translate(comp)[::-1]
+    s0, s4 = seqs[0], seqs[4]
+    pairs = {}
+    with_base = {"A": "RMWNHVD", "C": "YMSHBVN", "G": "RKSBVDN", "T": "YKWHBDN"}
+
+    def dege(seq, spots):
+        """seq with the bases at `spots` replaced by the (spot-th, cyclically) IUPAC code that contains them"""
+        out = list(seq)
+        for n, i in enumerate(spots):
+            out[i] = with_base[seq[i]][(n + i) % 7]
+        return "".join(out)
+
+    f, r = s0[100:118], rc(s0[400:420])
+    pairs["plain_0_100"] = (f, r)
+    pairs["dege_0_100"] = (dege(f, [5, 11]), dege(r, [3, 9]))
+    f4, r4 = s4[2000:2020], rc(s4[2300:2318])
+    pairs["dege_4_2000"] = (dege(f4, [2, 10, 15]), dege(r4, [8]))
+    # the most frequent 12-mer of genome 0 as forward primer: it occurs more than once
+    from collections import Counter
+    cnt = Counter(s0[i:i + 12] for i in range(len(s0) - 300))
+    kmer, n = [(km, c) for km, c in cnt.most_common() if len(set(km)) > 2][0]
+    assert n >= 2
+    first = s0.index(kmer)
+    pairs["repeat_0"] = (kmer, rc(s0[first + 40:first + 58]))
+    pairs["nomatch"] = ("ACGTACGTACGTACGTAC", "TTTTTTTTGGGGGGGGCC")
+    pairs["hbvdn_0_3000"] = (dege(s0[3000:3019], [0, 6, 12, 17]), dege(rc(s0[3200:3220]), [1, 7, 13]))
+    return pairs
+
+
+def make_pcr():
+    """extract_PCR_product_V1.py on test_data/test.fa: formats seq and fa, outputs recorded file by file"""
+    import subprocess
+    pairs = pcr_primer_sets()
+    blob = {"pairs": pairs, "runs": {}}
+    ref = os.path.join(REF, "test_data", "test.fa")
+    script = os.path.join(REF, "scripts", "extract_PCR_product_V1.py")
+
+    def collect(tmp, outdir, cov):
+        files = {}
+        for fn in sorted(os.listdir(outdir)):
+            files[fn] = open(os.path.join(outdir, fn)).read()
+        return {"files": files, "coverage": open(cov).read()}
+
+    for name, (f, r) in pairs.items():
+        with tempfile.TemporaryDirectory() as tmp:
+            outdir, cov = os.path.join(tmp, "PCR"), os.path.join(tmp, "Coverage.xls")
+            res = subprocess.run([sys.executable, script, "-r", ref, "-i", f + "," + r, "-f", "seq", "-o", outdir, "-s", cov,
+                                  "-p", "1"], capture_output=True, text=True)
+            blob["runs"]["seq:" + name] = dict(collect(tmp, outdir, cov), rc=res.returncode)
+            print("pcr", name, res.returncode, blob["runs"]["seq:" + name]["coverage"].splitlines()[0][:120], res.stderr[-200:])
+    with tempfile.TemporaryDirectory() as tmp:
+        fa = os.path.join(tmp, "primers.fa")
+        with open(fa, "w") as fh:
+            for name, (f, r) in pairs.items():
+                fh.write(">%s_F\n%s\n>%s_R\n%s\n" % (name, f, name, r))
+        outdir, cov = os.path.join(tmp, "PCR"), os.path.join(tmp, "Coverage.xls")
+        res = subprocess.run([sys.executable, script, "-r", ref, "-i", fa, "-f", "fa", "-o", outdir, "-s", cov, "-p", "1"],
+                             capture_output=True, text=True)
+        blob["runs"]["fa"] = dict(collect(tmp, outdir, cov), rc=res.returncode, primers_fa=open(fa).read())
+        print("pcr fa", res.returncode, res.stderr[-300:])
+    with open(os.path.join(HERE, "pcr_product.json"), "w") as fh:
+        json.dump(blob, fh)
+
+
+def make_degeprimer():
+    """get_degePrimer_V6.py on a DegePrime-format table built from the full C2 golden rows (k = 18) and
+    test_data/1000.fasta as the reference FASTA; two parameter sets"""
+    import subprocess
+    case = json.load(open(os.path.join(HERE, "core_c2f_k18.json")))
+    lines = ["Pos\tTotalSeq\tUniqueMers\tEntropy\tPrimerDeg\tPrimerSeq\tPrimerMatching"]
+    for rec in case["records"]:
+        if rec["row"]:
+            r = rec["row"]
+            lines.append("\t".join(map(str, [r[0], case["n_seq"], r[5] + 1, r[2], r[4], r[3], max(r[7], r[8])])))
+    table = "\n".join(lines) + "\n"
+    blob = {"table": table, "runs": {}}
+    ref = os.path.join(REF, "test_data", "1000.fasta")
+    for tag, extra in (("a", ["-s", "100,300", "-f", "0.3", "-e", "2", "-m", "0"]),
+                       ("b", ["-s", "150,400", "-f", "0.6", "-a", ",", "-d", "3"])):
+        with tempfile.TemporaryDirectory() as tmp:
+            inp, out = os.path.join(tmp, "degeprime.out"), os.path.join(tmp, "Cluster.candidate.primers.txt")
+            open(inp, "w").write(table)
+            res = subprocess.run([sys.executable, os.path.join(REF, "scripts", "get_degePrimer_V6.py"), "-i", inp, "-r", ref,
+                                  "-o", out] + extra, capture_output=True, text=True)
+            blob["runs"][tag] = {"args": extra, "rc": res.returncode, "txt": open(out).read().replace(tmp, "<TMP>"),
+                                 "stdout": [ln for ln in res.stdout.splitlines() if not ln.startswith("INFO")]}
+            print("degeprimer", tag, res.returncode, blob["runs"][tag]["txt"].count(":") , res.stderr[-200:])
+    with open(os.path.join(HERE, "pairs_get_degeprimer.json"), "w") as fh:
+        json.dump(blob, fh)
+
+
 def make_cli():
     """the reference CLI end to end on a small synthetic alignment: TSV text + the two JSON side files"""
     import subprocess
@@ -357,6 +457,10 @@ def main():
             make_cover()
         elif name == "pairs":
             make_pairs()
+        elif name == "pcr":
+            make_pcr()
+        elif name == "degeprimer":
+            make_degeprimer()
         elif name in CASES:
             run_case(core, name)
 

@@ -106,3 +106,21 @@ def test_findimer_row_bands_over_ranks(tmp_path, world):
 
     for rows in run_shards(world, shard):
         assert [list(r) for r in rows] == g["rows"]
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_get_degeprimer(tmp_path, tag, capsys):
+    """get_degePrimer drop-in against get_degePrimer_V6.py on a DegePrime table built from the C2 rows
+    (tests/golden/make_golden.py degeprimer); the reference FASTA only supplies the sequence count (1000)"""
+    from multiprime_b200 import degeprimer
+    g = _load("pairs_get_degeprimer.json")
+    inp = tmp_path / "degeprime.out"
+    inp.write_text(g["table"])
+    ref = tmp_path / "ref.fa"
+    ref.write_text("".join(">s%d\nACGT\n" % i for i in range(1000)))
+    out = tmp_path / "Cluster.candidate.primers.txt"
+    want = g["runs"][tag]
+    degeprimer.main(["-i", str(inp), "-r", str(ref), "-o", str(out)] + want["args"])
+    assert out.read_text().replace(str(tmp_path), "<TMP>") == want["txt"]
+    got = [ln for ln in capsys.readouterr().out.splitlines() if not ln.startswith("INFO")]
+    assert got == want["stdout"]

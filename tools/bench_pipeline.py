@@ -28,7 +28,7 @@ for it in range(steps + 1):
     so, sys.stdout = sys.stdout, devnull                     # the reference prints one line per start candidate
     try:
         pf = pairing.Primers_filter.from_core(app, recs, out, adaptor=",", size="150,400", fraction=0.6, diff_Tm=4,
-                                              position=4, distance=4)
+                                              position=0, distance=4, GC="0.1,0.9")
         app.ctx.profile_read(None)
         app.ctx.profile(True)
         rows = pf.run()
