@@ -431,7 +431,7 @@ class NN_degenerate(object):
         self.bit_vectors = []
         if not positions:
             return []
-        per_batch = self.windows_per_batch or _default_batch(self.n_local)
+        per_batch = min(65535, self.windows_per_batch or _default_batch(self.n_local))
         out = []
         for b0 in range(0, len(positions), per_batch):
             out.extend(self._design_batch(positions[b0:b0 + per_batch]))

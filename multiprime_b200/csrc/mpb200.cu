@@ -564,7 +564,7 @@ __device__ __forceinline__ void pre_row(const Win& w, int v, unsigned int* B, in
     }
 }
 
-__global__ void __launch_bounds__(HIST_THREADS)
+__global__ void __launch_bounds__(HIST_THREADS, 6)
 k_prefilter(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq, const int32_t* __restrict__ lens, int k, int v,
             const int32_t* __restrict__ win_pos, const int2* __restrict__ groups, int n_groups,
             unsigned int* __restrict__ bins, int* __restrict__ err) {
@@ -707,6 +707,27 @@ __device__ __forceinline__ void hist_row(const uint32_t* __restrict__ pl, int64_
     }
 }
 
+#define HIST_DEFER_CAP 4000  // deferred special / gapped rows per block
+#define HIST_QCAP 256        // queued minority rows per warp
+
+// insert a warp's queued minority rows, one per lane at a time
+__device__ __forceinline__ void hist_flush(const unsigned long long* __restrict__ qkey, const unsigned int* __restrict__ qmeta,
+                                           unsigned qn, int lane, uint64_t* __restrict__ keys, uint32_t* __restrict__ cnt,
+                                           uint64_t* __restrict__ first, uint32_t* __restrict__ elist,
+                                           unsigned long long* __restrict__ n_entries, int log2cap, long long row0,
+                                           int64_t row_base, int* __restrict__ err) {
+    __syncwarp();
+    const uint64_t cap = 1ull << log2cap;
+    for (unsigned i = lane; i < qn; i += 32) {
+        const unsigned m = qmeta[i];
+        const unsigned wi = m & 0xFFFFu;
+        const uint64_t s = (uint64_t)(row_base + (m >> 16));
+        mpb_table_add(keys + (uint64_t)wi * cap, cnt + (uint64_t)wi * cap, first + (uint64_t)wi * cap, log2cap, qkey[i], 1u,
+                      (uint64_t)(row0 + s) << 16, err, &n_entries[wi], elist + (uint64_t)wi * cap);
+    }
+    __syncwarp();
+}
+
 __global__ void __launch_bounds__(HIST_THREADS)
 k_hist(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq, const int32_t* __restrict__ lens, int k, int v,
        const int32_t* __restrict__ win_pos, const int2* __restrict__ groups, int n_groups, uint64_t* __restrict__ keys,
@@ -716,10 +737,15 @@ k_hist(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq, const int32_
        uint32_t* __restrict__ spec_bits, uint32_t* __restrict__ gap_bits, long long nwords, uint4* __restrict__ spec_win,
        int32_t* __restrict__ spec_row, unsigned long long* __restrict__ spec_n, long long spec_cap,
        int* __restrict__ err) {
-    __shared__ unsigned int s_defer[DEFER_CAP];
+    __shared__ unsigned int s_defer[HIST_DEFER_CAP];
     __shared__ unsigned int s_ndefer;
     __shared__ int s_p[HIST_THREADS / 32][32];                      // window start columns of the group, per warp
     __shared__ unsigned long long s_major[HIST_THREADS / 32][32];   // majority key of every window of the group, per warp
+    // minority rows wait in a per-warp queue and are inserted 32 at a time: a table insert is three dependent trips to
+    // L2, and done where the row stands it ran with ~5 of 32 lanes (ncu: 35 % of the stall samples at the first of them)
+    __shared__ unsigned long long s_qkey[HIST_THREADS / 32][HIST_QCAP];
+    __shared__ unsigned int s_qmeta[HIST_THREADS / 32][HIST_QCAP];  // window index | row within the block << 16
+    unsigned qn = 0;
     const uint32_t kmask = (1u << k) - 1u;
     const uint64_t cap = 1ull << log2cap;
     int lane;
@@ -768,7 +794,7 @@ k_hist(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq, const int32_
                         key = (unsigned long long)(r.c | r.t) | ((unsigned long long)(r.g | r.t) << k);
                     } else {
                         const unsigned idx = atomicAdd(&s_ndefer, 1u);
-                        if (idx < DEFER_CAP) {
+                        if (idx < HIST_DEFER_CAP) {
                             s_defer[idx] = ((unsigned)(gslot * 32 + j) << 13) | (r.special ? 0x1000u : 0u) |
                                            (unsigned)(t * HIST_THREADS + threadIdx.x);
                         } else {  // list full: handle the row in this iteration, after the class words are stored
@@ -803,7 +829,23 @@ k_hist(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq, const int32_
                     if (my_count == 0 && eq) my_first = (unsigned long long)(row0 + tile0 + warp * 32 + (__ffs(eq) - 1)) << 16;
                     my_count += __popc(eq);
                 }
-                if (simple && key != major) mpb_table_add(K, C, F, log2cap, key, 1u, (uint64_t)(row0 + s) << 16, err, &n_entries[wi], E);
+                {
+                    const unsigned mm = __ballot_sync(0xffffffffu, simple && key != major);
+                    if (mm) {
+                        if (qn + 32 > HIST_QCAP) {  // warp-uniform: make room first
+                            hist_flush(s_qkey[warp], s_qmeta[warp], qn, lane, keys, cnt, first, elist, n_entries, log2cap, row0,
+                                       row_base, err);
+                            qn = 0;
+                        }
+                        if (simple && key != major) {
+                            const unsigned slot = qn + __popc(mm & ((1u << lane) - 1u));
+                            s_qkey[warp][slot] = key;
+                            s_qmeta[warp][slot] = (unsigned)wi | ((unsigned)(t * HIST_THREADS + threadIdx.x) << 16);
+                        }
+                        qn += __popc(mm);
+                        __syncwarp();
+                    }
+                }
                 if (late)
                     hist_row(pl, nsp, s, len, p, k, v, kmask, row0, wi, K, C, F, E, log2cap, gap_n, iupac_gap_n, exc, exc_n,
                              exc_max, n_entries, gap_bits, nwords, spec_win, spec_row, spec_n, spec_cap, late_special, err);
@@ -817,8 +859,9 @@ k_hist(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq, const int32_
             if (my_gaps) atomicAdd(&gap_n[wi], (unsigned long long)my_gaps);
         }
     }
+    hist_flush(s_qkey[warp], s_qmeta[warp], qn, lane, keys, cnt, first, elist, n_entries, log2cap, row0, row_base, err);
     __syncthreads();
-    const unsigned nd = s_ndefer < DEFER_CAP ? s_ndefer : DEFER_CAP;
+    const unsigned nd = s_ndefer < HIST_DEFER_CAP ? s_ndefer : HIST_DEFER_CAP;
     for (unsigned i = threadIdx.x; i < nd; i += HIST_THREADS) {
         const unsigned e = s_defer[i];
         const unsigned ws = e >> 13;
@@ -959,7 +1002,7 @@ static int hist_launch_build(mpb_hist* h) {
 static int hist_create(mpb_msa* m, int k, int v, const int32_t* win_pos, int32_t nw, int log2_cap, int fill, mpb_hist** out) {
     if (!m || !win_pos || !out) return fail(MPB_EINVAL, "NULL argument");
     if (k < 3 || k > MPB_MAX_K) return fail(MPB_EINVAL, "primer length %d outside 3..%d", k, MPB_MAX_K);
-    if (v < 0 || nw < 1) return fail(MPB_EINVAL, "bad v=%d or nw=%d", v, nw);
+    if (v < 0 || nw < 1 || nw > 65535) return fail(MPB_EINVAL, "bad v=%d or nw=%d (at most 65535 windows per batch)", v, nw);
     for (int i = 0; i < nw; ++i)
         if (win_pos[i] < 0 || win_pos[i] >= m->n_col)
             return fail(MPB_EINVAL, "win_pos[%d]=%d outside the alignment", i, win_pos[i]);
