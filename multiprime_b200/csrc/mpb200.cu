@@ -564,7 +564,7 @@ __device__ __forceinline__ void pre_row(const Win& w, int v, unsigned int* B, in
     }
 }
 
-__global__ void __launch_bounds__(HIST_THREADS, 6)
+__global__ void __launch_bounds__(HIST_THREADS)
 k_prefilter(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq, const int32_t* __restrict__ lens, int k, int v,
             const int32_t* __restrict__ win_pos, const int2* __restrict__ groups, int n_groups,
             unsigned int* __restrict__ bins, int* __restrict__ err) {

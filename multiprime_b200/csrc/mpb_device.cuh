@@ -366,7 +366,8 @@ __device__ __forceinline__ void mpb_table_add(uint64_t* __restrict__ keys, uint3
         }
         if (cur == key) {
             atomicAdd(&cnt[h], add);
-            atomicMin((unsigned long long*)&first[h], (unsigned long long)ord);
+            // `first` only ever decreases: a row that is not earlier than the value already there needs no atomic
+            if (*((volatile uint64_t*)&first[h]) > ord) atomicMin((unsigned long long*)&first[h], (unsigned long long)ord);
             return;
         }
         h = (h + 1) & mask;
