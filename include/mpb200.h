@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MPB_ABI_VERSION 2
+#define MPB_ABI_VERSION 3
 #define MPB_MAX_K 27
 #define MPB_MAX_EXPANSIONS 65536 /* expansions of one k-mer window of one sequence */
 
@@ -259,6 +259,27 @@ int mpb_walk_dev_run(mpb_walk_dev* w, int lag, int64_t* rounds);
 int mpb_walk_dev_finish(mpb_walk_dev* w, uint8_t* out_sets, int64_t* out_counts, uint8_t* out_seeds, int64_t* out_seed_cover,
                         int32_t* out_ntracks, int64_t trace_cap, uint8_t* trace_sets, int64_t* trace_off, int64_t* stats);
 void mpb_walk_dev_free(mpb_walk_dev* w);
+
+/* ---- peer-memory all-reduce for sequence-sharded walks (no counterpart in the reference) --------------
+ * One process (or thread) per GPU.  Every rank creates a group member, publishes its 128-byte handle, collects the
+ * handles of all ranks in rank order (through whatever channel the host has: torch.distributed, MPI, a file) and
+ * connects.  The receive buffers are opened through CUDA IPC over NVLink (same-process members are used by address).
+ * mpb_walk_dev_set_peer makes mpb_walk_dev_run sum the count vector over the ranks after every scan with ONE
+ * single-block kernel on the walk's stream (push to every peer, signal, wait, sum) instead of a collective-library call
+ * from the host per round.  cap_elems = capacity of the vector in int64 elements (4 per candidate of a round). */
+#define MPB_PEER_MAX_WORLD 8
+#define MPB_PEER_HANDLE_BYTES 128
+typedef struct mpb_peer mpb_peer;
+int mpb_peer_create(mpb_ctx* ctx, int rank, int world, int64_t cap_elems, mpb_peer** out);
+int mpb_peer_handle(mpb_peer* p, void* handle_out /* MPB_PEER_HANDLE_BYTES */);
+int mpb_peer_connect(mpb_peer* p, const void* handles /* world x MPB_PEER_HANDLE_BYTES, rank order */);
+int64_t mpb_peer_cap(mpb_peer* p);
+/* in-place sum over the ranks of data_dev[0..n) (device memory); collective: same calls in the same order on all ranks */
+int mpb_peer_allreduce(mpb_peer* p, int64_t* data_dev, int64_t n);
+void mpb_peer_free(mpb_peer* p);
+/* the walk's rounds all-reduce their counts through `peer` (NULL: back to the caller's own all-reduce between
+ * mpb_walk_dev_scan and mpb_walk_dev_advance); fails when a round's vector could exceed the group's capacity */
+int mpb_walk_dev_set_peer(mpb_walk_dev* w, mpb_peer* peer);
 
 /* mpb_walk: the same walk driven from the host with the scan as a callback (no device code, no CUDA calls): the CPU
  * tests run it against a stand-in scan.  Candidates name windows 0..n_win-1.

@@ -75,6 +75,13 @@ SIGNATURES = {
     "mpb_walk_dev_run": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int64)]),
     "mpb_walk_dev_finish": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int64, _P, _P, _P]),
     "mpb_walk_dev_free": (None, [_P]),
+    "mpb_walk_dev_set_peer": (C.c_int, [_P, _P]),
+    "mpb_peer_create": (C.c_int, [_P, C.c_int, C.c_int, C.c_int64, C.POINTER(_P)]),
+    "mpb_peer_handle": (C.c_int, [_P, _P]),
+    "mpb_peer_connect": (C.c_int, [_P, _P]),
+    "mpb_peer_cap": (C.c_int64, [_P]),
+    "mpb_peer_allreduce": (C.c_int, [_P, _P, C.c_int64]),
+    "mpb_peer_free": (None, [_P]),
     "mpb_primer_props": (C.c_int, [_P, _P, C.c_int, C.c_int32, C.c_double, C.c_double, C.c_int, _P, _P, _P, _P, _P,
                                    _P]),
     "mpb_window_cells": (C.c_int, [_P, C.c_int64, _P, C.c_int32, C.c_int, C.c_int64, _P, _P, _P, _P]),
@@ -111,7 +118,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.mpb_abi_version() != 2:
+    if lib.mpb_abi_version() != 3:
         raise ImportError("libmpb200.so ABI version mismatch")
     _lib = lib
     return lib
@@ -511,11 +518,12 @@ class Hist:
         return counts, bits
 
     def walk(self, dnum, degeneracy, fmask, rmask, win_idx, cover_number, mm_key, freq=None, nn=None, comm=None,
-             want_trace=True, lag=2):
+             want_trace=True, lag=2, peer=None):
         """the device-resident refinement walk of the windows win_idx (indices into this batch) -> walk() outputs.
-        comm (sequence shards): the count vector is all-reduced between scan and advance."""
+        comm (sequence shards): the count vector is summed over the ranks between scan and advance — inside the round's
+        kernel chain through `peer` (NVLink peer memory), else by the communicator's all-reduce, one host call per round."""
         with WalkDev(self, dnum, degeneracy, fmask, rmask, win_idx, cover_number, mm_key, freq, nn) as w:
-            if comm is None or comm.world == 1:
+            if comm is None or comm.world == 1 or (peer is not None and w.set_peer(peer)):
                 w.run(lag)
             else:
                 on_gpu = getattr(comm, "on_gpu", False)
@@ -645,6 +653,45 @@ class Hist:
         return w, s
 
 
+PEER_HANDLE_BYTES = 128
+PEER_MAX_WORLD = 8
+
+
+class Peer:
+    """mpb_peer_*: this rank's member of a peer-memory group (one rank per GPU, NVLink): the walk's count vector is
+    summed over the ranks by one small kernel per round.  `comm` only carries the 128-byte handles once."""
+
+    def __init__(self, ctx: Context, comm, cap_elems: int = 1 << 18):
+        self.ctx, self.rank, self.world, self.cap = ctx, comm.rank, comm.world, int(cap_elems)
+        h = C.c_void_p()
+        check(load().mpb_peer_create(ctx.h, comm.rank, comm.world, self.cap, C.byref(h)))
+        self.h = h
+        mine = np.zeros(PEER_HANDLE_BYTES // 8, np.int64)
+        check(load().mpb_peer_handle(self.h, ptr(mine)))
+        handles = np.ascontiguousarray(comm.allgather_fixed(mine))
+        check(load().mpb_peer_connect(self.h, ptr(handles)))
+        comm.barrier()                       # nobody pushes before every rank has opened every buffer
+
+    @classmethod
+    def of(cls, ctx: Context, comm, cap_elems: int = 1 << 18):
+        """the group member cached on a (shared) context: opening IPC handles costs milliseconds, once per process"""
+        cache = ctx.__dict__.setdefault("_peers", {})
+        key = (getattr(comm, "peer_key", None), comm.rank, comm.world)     # one group per process group
+        peer = cache.get(key)
+        if peer is None or not peer.h:
+            peer = cls(ctx, comm, cap_elems)
+            cache[key] = peer
+        return peer
+
+    def allreduce(self, dev_ptr: int, n: int):
+        check(load().mpb_peer_allreduce(self.h, C.c_void_p(dev_ptr), n))
+
+    def close(self):
+        if self.h:
+            load().mpb_peer_free(self.h)
+            self.h = None
+
+
 class WalkDev:
     """mpb_walk_dev_*: tracks resident in HBM, rounds chained on the context's stream"""
 
@@ -673,6 +720,13 @@ class WalkDev:
         if self.h:
             load().mpb_walk_dev_free(self.h)
             self.h = None
+
+    def set_peer(self, peer) -> bool:
+        """all-reduce the counts through the peer group; False when a round could exceed the group's capacity"""
+        if 2 * self.n * (self.hist.k - 1) * 4 > peer.cap:
+            return False
+        check(load().mpb_walk_dev_set_peer(self.h, peer.h))
+        return True
 
     def advance(self):
         check(load().mpb_walk_dev_advance(self.h))

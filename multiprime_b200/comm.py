@@ -40,6 +40,7 @@ class TorchComm:
             device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" \
                 else torch.device("cpu")
         self.device = device
+        self.peer_key = ("torch", id(group) if group is not None else 0)
 
     def _to(self, arr):
         t = self.torch.from_numpy(np.ascontiguousarray(arr))
@@ -121,6 +122,12 @@ class TorchComm:
     @property
     def on_gpu(self) -> bool:
         return self.device.type == "cuda"
+
+    @property
+    def peer_ok(self) -> bool:
+        """one GPU per rank on one box (at most 8): the walk may use peer memory (mpb_peer_*) instead of a collective
+        call per round.  Ranks that share a GPU (gloo) would spin on each other across time slices."""
+        return self.device.type == "cuda" and self.world <= 8
 
     def empty_dev(self, n: int, dtype):
         """uninitialised device tensor of a numpy dtype (haplotype entries stay on the GPU between export and merge)"""

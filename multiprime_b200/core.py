@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import json
 import math
+import os
 import sys
 import time
 from statistics import mean
@@ -248,6 +249,11 @@ class NN_degenerate(object):
                                lens=None if (self.lens == self.n_col).all() else self.lens)
         if row0:
             self.msa.set_row0(row0)
+        # sequence shards, one GPU per rank: the walk sums its count vectors over NVLink peer memory (mpb_peer_*)
+        self.peer = None
+        if self.comm.world > 1 and getattr(self.comm, "peer_ok", False) and hasattr(backend, "Peer") \
+                and os.environ.get("MPB_PEER", "1") != "0":
+            self.peer = backend.Peer.of(self.ctx, self.comm)
         lap("upload")
         self.position_list = self.seq_attribute()
         lap("region")
@@ -520,7 +526,8 @@ class NN_degenerate(object):
         res = hist.walk(self.number_of_dege_bases, self.score_of_dege_bases, self.fmask, self.rmask, wis,
                         np.array([a[4] for a in keep], np.int64), mm_key,
                         freq=freq[wis] if sharded else None, nn=nn[wis].reshape(len(keep), k - 1, 16) if sharded else None,
-                        comm=comm if sharded else None, want_trace=self.want_trace)
+                        comm=comm if sharded else None, want_trace=self.want_trace,
+                        **({"peer": self.peer} if self.peer is not None else {}))
         lap("walk")
         self.stats["scan_calls"] += int(res["stats"][0])
         self.stats["candidates"] += int(res["stats"][1])

@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <string>
+#include <algorithm>
 #include <vector>
 
 #include "mpb200.h"
@@ -266,6 +267,35 @@ __global__ void k_fill_i32(int32_t* __restrict__ dst, int64_t n, int64_t n_set, 
     if (i < n) dst[i] = i < n_set ? value : 0;
 }
 
+// a frequent base of every column, counted on up to CONS_SAMPLE 32-sequence words spread evenly over the rows
+#define CONS_SAMPLE 1024
+__global__ void __launch_bounds__(128)
+k_col_consensus(const uint32_t* __restrict__ colp, int64_t nwords, uint8_t* __restrict__ cons) {
+    __shared__ unsigned int s_n[4];
+    if (threadIdx.x < 4) s_n[threadIdx.x] = 0;
+    __syncthreads();
+    const int col = blockIdx.x;
+    const int64_t n_s = nwords < CONS_SAMPLE ? nwords : CONS_SAMPLE;
+    unsigned n[4] = {0, 0, 0, 0};
+    for (int64_t i = threadIdx.x; i < n_s; i += 128) {
+        const int64_t w = i * nwords / n_s;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) n[b] += __popc(__ldg(colp + ((int64_t)col * 4 + b) * nwords + w));
+    }
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        const unsigned t = __reduce_add_sync(0xffffffffu, n[b]);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&s_n[b], t);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int best = 0;
+        for (int b = 1; b < 4; ++b)
+            if (s_n[b] > s_n[best]) best = b;
+        cons[col] = (uint8_t)best;
+    }
+}
+
 #define UPLOAD_CHUNK_ROWS 65536  // multiple of 1024 (k_build_colp tiles) and of PACK_ROWS
 
 extern "C" int mpb_msa_upload(mpb_ctx* ctx, const uint8_t* packed4, int64_t n_seq, int64_t n_col, int64_t row_bytes,
@@ -290,6 +320,7 @@ extern "C" int mpb_msa_upload(mpb_ctx* ctx, const uint8_t* packed4, int64_t n_se
     if (e == cudaSuccess) e = cudaMallocAsync(&m->colp, crows * m->nwords * 4, ctx->stream);
     if (e == cudaSuccess) e = cudaMallocAsync(&m->lens, m->nsp * sizeof(int32_t), ctx->stream);
     if (e == cudaSuccess) e = cudaMallocAsync(&m->err, sizeof(int), ctx->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&m->cons, (size_t)(m->ncw - 1) * 32, ctx->stream);
     if (e != cudaSuccess) {
         mpb_msa_free(m);
         return fail(MPB_ENOMEM, "alignment planes (2 x %zu bytes): %s", pbytes, cudaGetErrorString(e));
@@ -355,6 +386,11 @@ extern "C" int mpb_msa_upload(mpb_ctx* ctx, const uint8_t* packed4, int64_t n_se
         if (cudaGetLastError() != cudaSuccess) rc = fail(MPB_ECUDA, "upload kernels");
         if (!on_dev && rc == 0 && cudaEventRecord(consumed[slot], ctx->stream) != cudaSuccess) rc = fail(MPB_ECUDA, "event record");
     }
+    if (rc == 0) {
+        k_col_consensus<<<(unsigned)((m->ncw - 1) * 32), 128, 0, ctx->stream>>>(m->colp, m->nwords, m->cons);
+        ctx->launches++;
+        if (cudaGetLastError() != cudaSuccess) rc = fail(MPB_ECUDA, "upload kernels");
+    }
     cudaError_t se = cudaStreamSynchronize(ctx->stream);  // hl / staging lifetime
     for (int i = 0; i < 2; ++i) {
         if (stage[i]) cudaFreeAsync(stage[i], ctx->stream);
@@ -376,6 +412,7 @@ extern "C" void mpb_msa_free(mpb_msa* m) {
     if (m->colp) cudaFreeAsync(m->colp, m->ctx->stream);
     if (m->lens) cudaFreeAsync(m->lens, m->ctx->stream);
     if (m->err) cudaFreeAsync(m->err, m->ctx->stream);
+    if (m->cons) cudaFreeAsync(m->cons, m->ctx->stream);
     delete m;
 }
 extern "C" int64_t mpb_msa_nseq(const mpb_msa* m) { return m ? m->n_seq : 0; }
@@ -666,17 +703,19 @@ __device__ __forceinline__ void hist_row(const uint32_t* __restrict__ pl, int64_
                                          unsigned long long* __restrict__ exc_n, long long exc_max,
                                          unsigned long long* __restrict__ n_entries, uint32_t* __restrict__ gap_bits,
                                          long long nwords, uint4* __restrict__ spec_win, int32_t* __restrict__ spec_row,
-                                         unsigned long long* __restrict__ spec_n, long long spec_cap, bool is_special,
+                                         unsigned long long* __restrict__ spec_n, long long spec_cap, int mode,
                                          int* __restrict__ err) {
+    // mode 0: plain row already classified where it stood (gap bit, gap count); 1: special row; 2: plain row holding
+    // gaps whose gap test is still to do (column-domain pass)
     const uint64_t gs = (uint64_t)(row0 + s);
     Win w;
     if (!mpb_load_window(pl, nsp, s, len, p, k, kmask, w)) atomicOr(err, MPB_ERR_SHORT_ROW);
     const bool isgap = __popc(w.gapv) > v;
-    if (is_special) {  // plain rows were classified (gap bit, gap count) where they stand
+    if (mode != 0) {
         if (isgap) {
             atomicAdd(&gap_n[wi], 1ull);
             atomicOr(&gap_bits[(long long)wi * nwords + (s >> 5)], 1u << (s & 31));
-        } else {  // the patched window itself, for the column scan's special pass
+        } else if (mode == 1) {  // the patched window itself, for the column scan's special pass
             const unsigned long long slot = atomicAdd(&spec_n[wi], 1ull);
             if ((long long)slot < spec_cap) {
                 spec_win[(long long)wi * spec_cap + slot] = make_uint4(w.a, w.c, w.g, w.t);
@@ -848,7 +887,7 @@ k_hist(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq, const int32_
                 }
                 if (late)
                     hist_row(pl, nsp, s, len, p, k, v, kmask, row0, wi, K, C, F, E, log2cap, gap_n, iupac_gap_n, exc, exc_n,
-                             exc_max, n_entries, gap_bits, nwords, spec_win, spec_row, spec_n, spec_cap, late_special, err);
+                             exc_max, n_entries, gap_bits, nwords, spec_win, spec_row, spec_n, spec_cap, late_special ? 1 : 0, err);
             }
         }
         if (lane < gr.y) {
@@ -869,7 +908,7 @@ k_hist(const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq, const int32_
         const int64_t s = row_base + (e & 0xFFFu);
         hist_row(pl, nsp, s, lens[s], win_pos[wi], k, v, kmask, row0, wi, keys + (uint64_t)wi * cap, cnt + (uint64_t)wi * cap,
                  first + (uint64_t)wi * cap, elist + (uint64_t)wi * cap, log2cap, gap_n, iupac_gap_n, exc, exc_n, exc_max,
-                 n_entries, gap_bits, nwords, spec_win, spec_row, spec_n, spec_cap, (e & 0x1000u) != 0u, err);
+                 n_entries, gap_bits, nwords, spec_win, spec_row, spec_n, spec_cap, (e & 0x1000u) != 0u ? 1 : 0, err);
     }
 }
 
@@ -903,6 +942,364 @@ k_prefilter_sums(const unsigned int* __restrict__ bins, double* __restrict__ s0,
         s0[blockIdx.x] = a0;
         s1[blockIdx.x] = a1;
     }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// column-domain window passes
+// ------------------------------------------------------------------------------------------------------
+// The row-domain passes above spend ~80 (prefilter) / ~210 (tables) warp instructions per (window, 32 rows) to find out,
+// row by row, that most rows of a conserved window carry the same k-mer (ncu: both issue-bound at ~44 %).  On the column
+// view (colp: one bit per sequence, 32 sequences per word) that question is an AND: with lane = column and a word of 32
+// rows per warp, "row equals the reference k-mer R_w of window w" is the AND over the window's columns of
+// plane[column][base R_w has there] — a sliding AND over k lanes, done for all windows that start in the lanes' columns
+// by log2(k) shuffles.  The same shuffles give "any gap", "any IUPAC cell", "all gaps" and the two edge cells, i.e. the
+// reference's row classes (core:666-687): special rows (edge gap, IUPAC, ragged), gap rows, plain rows.  Per (window,
+// 32 rows) that is ~5 instructions; rows equal to R_w and all-gap rows are counted in bulk, and only the others — the
+// minority haplotypes, rows holding inner gaps, special rows — are queued (block-shared queue, warp-aggregated) and
+// handled on the row view with all lanes busy.  R_w is the per-column frequent base of a row sample (mpb_msa::cons):
+// any reference k-mer gives the same tables, a frequent one leaves few rows for the queue.
+#define CW_THREADS 256
+#define CW_WARPS (CW_THREADS / 32)
+#define CW_WPW 16                         // words per warp and block
+#define CW_WORDS (CW_WARPS * CW_WPW)
+#define CW_ROWS (CW_WORDS * 32)           // 4096 rows per block (12 bits in a queue entry)
+#define CW_QCAP 10240
+#define CW_QROOM 7680                     // most entries one pass of the block adds: 8 warps x 30 windows x 32 rows
+
+struct ColClass {
+    uint32_t plain, agp, match;  // plain rows; plain all-gap rows; gap-free plain rows equal to the reference k-mer
+};
+
+// lane = column cs + lane; A..T = that column's plane words of one 32-sequence word; cb = the column's reference base.
+// Valid for the windows starting in lanes 0 .. 32 - k.
+__device__ __forceinline__ ColClass col_classify(uint32_t A, uint32_t C, uint32_t G, uint32_t T, int cb, int k, int L,
+                                                 uint32_t vm, uint32_t ragged) {
+    const uint32_t gapc = ~(A | C | G | T);
+    uint32_t anygap = gapc, allgap = gapc;
+    uint32_t anymul = mpb_multi(A, C, G, T);
+    uint32_t alleq = cb == 0 ? A : cb == 1 ? C : cb == 2 ? G : T;
+    for (int o = 1; o < L; o <<= 1) {  // windows of L = 2^j <= k columns by doubling
+        anygap |= __shfl_down_sync(0xffffffffu, anygap, o);
+        anymul |= __shfl_down_sync(0xffffffffu, anymul, o);
+        allgap &= __shfl_down_sync(0xffffffffu, allgap, o);
+        alleq &= __shfl_down_sync(0xffffffffu, alleq, o);
+    }
+    const int d = k - L;  // two overlapping windows of L columns cover k
+    anygap |= __shfl_down_sync(0xffffffffu, anygap, d);
+    anymul |= __shfl_down_sync(0xffffffffu, anymul, d);
+    allgap &= __shfl_down_sync(0xffffffffu, allgap, d);
+    alleq &= __shfl_down_sync(0xffffffffu, alleq, d);
+    const uint32_t last = __shfl_down_sync(0xffffffffu, gapc, k - 1);
+    const uint32_t special = (((gapc | last) & ~allgap) | anymul | ragged);
+    ColClass r;
+    r.plain = ~special & vm;
+    r.agp = r.plain & allgap;
+    r.match = r.plain & ~anygap & alleq;
+    return r;
+}
+
+// rows of this word whose sequence ends before the lane's window does (lane's window ends at column `need`)
+__device__ __forceinline__ uint32_t col_ragged(const int32_t* __restrict__ lens, int64_t s_lane, int64_t n_seq, int need,
+                                               int pend) {
+    int len_l = 0x7FFFFFFF;
+    if (s_lane < n_seq) len_l = __ldg(lens + s_lane);
+    const int minlen = __reduce_min_sync(0xffffffffu, len_l);
+    uint32_t ragged = 0;
+    if (minlen < pend) {  // uniform; rare
+        for (int r = 0; r < 32; ++r) {
+            const int lr = __shfl_sync(0xffffffffu, len_l, r);
+            ragged |= (lr < need ? 1u : 0u) << r;
+        }
+    }
+    return ragged;
+}
+
+// queue the set bits of every lane's word (row = row_in_block0 + bit) as entries wi | row << 16: one shared-memory
+// atomic per warp, the lanes write their own runs
+__device__ __forceinline__ void cw_push(uint32_t bits, unsigned wi, unsigned row_in_block0, unsigned int* s_q,
+                                        unsigned int* s_qn, int lane) {
+    const unsigned n = __popc(bits);
+    unsigned incl = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += u;
+    }
+    const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) return;  // uniform
+    unsigned base = 0;
+    if (lane == 31) base = atomicAdd(s_qn, total);
+    base = __shfl_sync(0xffffffffu, base, 31) + incl - n;
+    while (bits) {
+        const unsigned b = __ffs(bits) - 1;
+        bits &= bits - 1;
+        s_q[base++] = wi | ((row_in_block0 + b) << 16);
+    }
+}
+
+struct HistOut {
+    uint64_t* keys;
+    uint32_t* cnt;
+    uint64_t* first;
+    uint32_t* elist;
+    int log2cap;
+    unsigned long long *gap_n, *iupac_gap_n, *exc_n, *n_entries, *spec_n;
+    int32_t* exc;
+    long long exc_max, row0, nwords, spec_cap;
+    uint32_t *spec_bits, *gap_bits;
+    uint4* spec_win;
+    int32_t* spec_row;
+};
+
+// the queued rows of the table build, on the row view
+__device__ __forceinline__ void hist_col_flush(const uint32_t* __restrict__ pl, int64_t nsp, const int32_t* __restrict__ lens,
+                                               int k, int v, uint32_t kmask, const int32_t* __restrict__ win_pos,
+                                               const HistOut& o, int64_t row_base, const unsigned int* s_q,
+                                               unsigned int* s_qn, int* __restrict__ err) {
+    __syncthreads();
+    const unsigned n = *s_qn;
+    const uint64_t cap = 1ull << o.log2cap;
+    for (unsigned i = threadIdx.x; i < n; i += CW_THREADS) {
+        const unsigned e = s_q[i];
+        const int wi = (int)(e & 0xFFFFu);
+        const int64_t s = row_base + (e >> 16);
+        const int p = __ldg(win_pos + wi);
+        const int len = __ldg(lens + s);
+        const uint4* wb = reinterpret_cast<const uint4*>(pl) + (int64_t)(p >> 5) * nsp + s;
+        const uint4 q0 = __ldg(wb), q1 = __ldg(wb + nsp);
+        const RawWin r = win_cut(q0, q1, p & 31, kmask, p, k, len);
+        uint64_t* K = o.keys + (uint64_t)wi * cap;
+        uint32_t* C = o.cnt + (uint64_t)wi * cap;
+        uint64_t* F = o.first + (uint64_t)wi * cap;
+        uint32_t* E = o.elist + (uint64_t)wi * cap;
+        if (!r.special && r.gapv == 0u) {
+            mpb_table_add(K, C, F, o.log2cap, (uint64_t)(r.c | r.t) | ((uint64_t)(r.g | r.t) << k), 1u,
+                          (uint64_t)(o.row0 + s) << 16, err, &o.n_entries[wi], E);
+        } else {
+            hist_row(pl, nsp, s, len, p, k, v, kmask, o.row0, wi, K, C, F, E, o.log2cap, o.gap_n, o.iupac_gap_n, o.exc, o.exc_n,
+                     o.exc_max, o.n_entries, o.gap_bits, o.nwords, o.spec_win, o.spec_row, o.spec_n, o.spec_cap,
+                     r.special ? 1 : 2, err);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *s_qn = 0;
+    __syncthreads();
+}
+
+// chunks: (first column, largest window end) of a group of windows that start within 33 - k consecutive columns;
+// chunk_win[chunk * 32 + lane] = batch index of the window starting at column first + lane, or -1
+__global__ void __launch_bounds__(CW_THREADS)
+k_hist_col(const uint32_t* __restrict__ colp, int ncols, const uint8_t* __restrict__ cons, const uint32_t* __restrict__ pl,
+           int64_t nsp, int64_t n_seq, const int32_t* __restrict__ lens, int k, int v, const int32_t* __restrict__ win_pos,
+           const int2* __restrict__ chunks, const int32_t* __restrict__ chunk_win, int n_chunks, HistOut o,
+           int* __restrict__ err) {
+    __shared__ unsigned int s_q[CW_QCAP];
+    __shared__ unsigned int s_qn;
+    const uint32_t kmask = (1u << k) - 1u;
+    int lane;
+    asm("mov.u32 %0, %%laneid;" : "=r"(lane));
+    const int warp = threadIdx.x >> 5;
+    const int64_t row_base = (int64_t)blockIdx.x * CW_ROWS;
+    const long long word_base = (long long)blockIdx.x * CW_WORDS;
+    const uint64_t cap = 1ull << o.log2cap;
+    int L = 1;
+    while (2 * L <= k) L *= 2;
+    const bool ag_gap = k > v;  // an all-gap row is a gap row (core:688) unless the variation allows k gaps
+    if (threadIdx.x == 0) s_qn = 0;
+    __syncthreads();
+    for (int ch = blockIdx.y; ch < n_chunks; ch += gridDim.y) {
+        const int2 cc = chunks[ch];
+        const int wi = chunk_win[ch * 32 + lane];
+        const bool lane_ok = wi >= 0 && lane + k <= 32;
+        const int col = cc.x + lane;
+        const bool colok = col < ncols;
+        const int cb = colok ? (int)cons[col] : 0;
+        const uint32_t lo_w = __ballot_sync(0xffffffffu, cb & 1), hi_w = __ballot_sync(0xffffffffu, cb & 2);
+        const uint64_t major = (uint64_t)((lo_w >> lane) & kmask) | ((uint64_t)((hi_w >> lane) & kmask) << k);
+        unsigned my_count = 0, ag_count = 0;
+        unsigned long long my_first = 0, ag_first = 0;
+        for (int it = 0; it < CW_WPW; ++it) {
+            __syncthreads();
+            if (s_qn > CW_QCAP - CW_QROOM)  // uniform: the counter is read between two barriers
+                hist_col_flush(pl, nsp, lens, k, v, kmask, win_pos, o, row_base, s_q, &s_qn, err);
+            else
+                __syncthreads();
+            const long long W = word_base + it * CW_WARPS + warp;
+            if (W >= o.nwords) continue;  // (the barriers above are passed by every warp)
+            const long long left = (long long)n_seq - W * 32;
+            const uint32_t vm = left >= 32 ? 0xFFFFFFFFu : left <= 0 ? 0u : ((1u << left) - 1u);
+            uint32_t A = 0, C = 0, G = 0, T = 0;
+            if (colok && vm) {
+                const uint32_t* base = colp + ((long long)col * 4) * o.nwords + W;
+                A = __ldg(base);
+                C = __ldg(base + o.nwords);
+                G = __ldg(base + 2 * o.nwords);
+                T = __ldg(base + 3 * o.nwords);
+            }
+            const uint32_t ragged = vm ? col_ragged(lens, W * 32 + lane, n_seq, col + k, cc.y) : 0u;
+            const ColClass r = col_classify(A, C, G, T, cb, k, L, vm, ragged);
+            uint32_t defer = 0;
+            if (lane_ok) {
+                o.spec_bits[(long long)wi * o.nwords + W] = ~r.plain;
+                o.gap_bits[(long long)wi * o.nwords + W] = ag_gap ? r.agp : 0u;
+                if (r.match) {
+                    if (my_count == 0) my_first = (unsigned long long)(o.row0 + W * 32 + (__ffs(r.match) - 1)) << 16;
+                    my_count += __popc(r.match);
+                }
+                if (r.agp) {
+                    if (ag_count == 0) ag_first = (unsigned long long)(o.row0 + W * 32 + (__ffs(r.agp) - 1)) << 16;
+                    ag_count += __popc(r.agp);
+                }
+                defer = vm & ~(r.match | r.agp);
+            }
+            cw_push(defer, (unsigned)wi, (unsigned)((it * CW_WARPS + warp) * 32), s_q, &s_qn, lane);
+        }
+        if (lane_ok) {
+            uint64_t* K = o.keys + (uint64_t)wi * cap;
+            uint32_t* C = o.cnt + (uint64_t)wi * cap;
+            uint64_t* F = o.first + (uint64_t)wi * cap;
+            uint32_t* E = o.elist + (uint64_t)wi * cap;
+            if (my_count) mpb_table_add(K, C, F, o.log2cap, major, my_count, my_first, err, &o.n_entries[wi], E);
+            if (ag_count) {
+                mpb_table_add(K, C, F, o.log2cap, mpb_key(0u, 0u, 0u, kmask, k), ag_count, ag_first, err, &o.n_entries[wi], E);
+                if (ag_gap) atomicAdd(&o.gap_n[wi], (unsigned long long)ag_count);
+            }
+        }
+    }
+    hist_col_flush(pl, nsp, lens, k, v, kmask, win_pos, o, row_base, s_q, &s_qn, err);
+}
+
+// the queued rows of the prefilter, on the row view
+__device__ __forceinline__ void pre_col_flush(const uint32_t* __restrict__ pl, int64_t nsp, const int32_t* __restrict__ lens,
+                                              int k, int v, uint32_t kmask, const int32_t* __restrict__ win_pos,
+                                              unsigned int* __restrict__ bins, int64_t row_base, const unsigned int* s_q,
+                                              unsigned int* s_qn, int* __restrict__ err) {
+    __syncthreads();
+    const unsigned n = *s_qn;
+    for (unsigned i = threadIdx.x; i < n; i += CW_THREADS) {
+        const unsigned e = s_q[i];
+        const int wi = (int)(e & 0xFFFFu);
+        const int64_t s = row_base + (e >> 16);
+        const int p = __ldg(win_pos + wi);
+        const int len = __ldg(lens + s);
+        const uint4* wb = reinterpret_cast<const uint4*>(pl) + (int64_t)(p >> 5) * nsp + s;
+        const uint4 q0 = __ldg(wb), q1 = __ldg(wb + nsp);
+        const RawWin r = win_cut(q0, q1, p & 31, kmask, p, k, len);
+        unsigned int* B = bins + (long long)wi * PRE_BINS;
+        if (!r.special) {
+            atomicAdd(&B[pre_code(r.c, r.g, r.t)], 1u);
+        } else {
+            Win w;
+            if (!mpb_load_window(pl, nsp, s, len, p, k, kmask, w)) atomicOr(err, MPB_ERR_SHORT_ROW);
+            pre_row(w, v, B, err);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *s_qn = 0;
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(CW_THREADS)
+k_prefilter_col(const uint32_t* __restrict__ colp, long long nwords, int ncols, const uint8_t* __restrict__ cons,
+                const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq, const int32_t* __restrict__ lens, int k, int v,
+                const int32_t* __restrict__ win_pos, const int2* __restrict__ chunks, const int32_t* __restrict__ chunk_win,
+                int n_chunks, unsigned int* __restrict__ bins, int* __restrict__ err) {
+    __shared__ unsigned int s_q[CW_QCAP];
+    __shared__ unsigned int s_qn;
+    const uint32_t kmask = (1u << k) - 1u;
+    int lane;
+    asm("mov.u32 %0, %%laneid;" : "=r"(lane));
+    const int warp = threadIdx.x >> 5;
+    const int64_t row_base = (int64_t)blockIdx.x * CW_ROWS;
+    const long long word_base = (long long)blockIdx.x * CW_WORDS;
+    int L = 1;
+    while (2 * L <= k) L *= 2;
+    if (threadIdx.x == 0) s_qn = 0;
+    __syncthreads();
+    for (int ch = blockIdx.y; ch < n_chunks; ch += gridDim.y) {
+        const int2 cc = chunks[ch];
+        const int wi = chunk_win[ch * 32 + lane];
+        const bool lane_ok = wi >= 0 && lane + k <= 32;
+        const int col = cc.x + lane;
+        const bool colok = col < ncols;
+        const int cb = colok ? (int)cons[col] : 0;
+        const uint32_t lo_w = __ballot_sync(0xffffffffu, cb & 1), hi_w = __ballot_sync(0xffffffffu, cb & 2);
+        // pre_code(c, g, t) only looks at c | t and g | t: the low and high bits of the reference bases
+        const uint32_t lo = (lo_w >> lane) & kmask, hi = (hi_w >> lane) & kmask;
+        const uint32_t major_code = pre_code(lo & ~hi, hi & ~lo, lo & hi);
+        unsigned my_count = 0, ag_count = 0;
+        for (int it = 0; it < CW_WPW; ++it) {
+            __syncthreads();
+            if (s_qn > CW_QCAP - CW_QROOM)
+                pre_col_flush(pl, nsp, lens, k, v, kmask, win_pos, bins, row_base, s_q, &s_qn, err);
+            else
+                __syncthreads();
+            const long long W = word_base + it * CW_WARPS + warp;
+            if (W >= nwords) continue;
+            const long long left = (long long)n_seq - W * 32;
+            const uint32_t vm = left >= 32 ? 0xFFFFFFFFu : left <= 0 ? 0u : ((1u << left) - 1u);
+            uint32_t A = 0, C = 0, G = 0, T = 0;
+            if (colok && vm) {
+                const uint32_t* base = colp + ((long long)col * 4) * nwords + W;
+                A = __ldg(base);
+                C = __ldg(base + nwords);
+                G = __ldg(base + 2 * nwords);
+                T = __ldg(base + 3 * nwords);
+            }
+            const uint32_t ragged = vm ? col_ragged(lens, W * 32 + lane, n_seq, col + k, cc.y) : 0u;
+            const ColClass r = col_classify(A, C, G, T, cb, k, L, vm, ragged);
+            uint32_t defer = 0;
+            if (lane_ok) {
+                my_count += __popc(r.match);
+                ag_count += __popc(r.agp);
+                defer = vm & ~(r.match | r.agp);
+            }
+            cw_push(defer, (unsigned)wi, (unsigned)((it * CW_WARPS + warp) * 32), s_q, &s_qn, lane);
+        }
+        if (lane_ok) {
+            unsigned int* B = bins + (long long)wi * PRE_BINS;
+            if (my_count) atomicAdd(&B[major_code], my_count);
+            if (ag_count) atomicAdd(&B[pre_code(0u, 0u, 0u)], ag_count);
+        }
+    }
+    pre_col_flush(pl, nsp, lens, k, v, kmask, win_pos, bins, row_base, s_q, &s_qn, err);
+}
+
+// host: chunks of windows for the column-domain passes (windows sorted by start column; a chunk holds the windows that
+// start within 33 - k columns of its first one, at most one per column)
+static void mpb_window_chunks(const int32_t* win_pos, int nw, int k, std::vector<int2>& chunks, std::vector<int32_t>& chunk_win) {
+    std::vector<int32_t> order(nw);
+    for (int i = 0; i < nw; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return win_pos[a] < win_pos[b]; });
+    chunks.clear();
+    chunk_win.clear();
+    const int span = 32 - k;  // a window may start in lanes 0 .. span
+    std::vector<char> done(nw, 0);
+    int n_done = 0;
+    size_t from = 0;
+    while (n_done < nw) {
+        while (done[order[from]]) ++from;
+        const int cs = win_pos[order[from]];
+        int2 c = make_int2(cs, cs + k);
+        const size_t base = chunk_win.size();
+        chunk_win.resize(base + 32, -1);
+        for (size_t j = from; j < (size_t)nw; ++j) {
+            const int32_t w = order[j];
+            const int lane = win_pos[w] - cs;
+            if (lane > span) break;
+            if (done[w] || chunk_win[base + lane] >= 0) continue;  // (a second window at the same column waits)
+            chunk_win[base + lane] = w;
+            done[w] = 1;
+            ++n_done;
+            if (win_pos[w] + k > c.y) c.y = win_pos[w] + k;
+        }
+        chunks.push_back(c);
+    }
+}
+
+static bool mpb_use_col_passes() {
+    const char* e = getenv("MPB_WINPASS");
+    return !(e && strcmp(e, "row") == 0);
 }
 
 // blocks along y (window stride) for a window pass: fill whole waves of resident blocks, a few waves deep
@@ -944,15 +1341,28 @@ extern "C" int mpb_window_prefilter(mpb_msa* m, int k, int v, const int32_t* win
     InBuf wp(ctx, win_pos, (size_t)nw * 4);
     OutBuf o0(ctx, s0_hd, (size_t)nw * 8), o1(ctx, s1_hd, (size_t)nw * 8);
     if (wp.rc || o0.rc || o1.rc) return MPB_ECUDA;
-    const unsigned gx = (unsigned)((m->n_seq + (long long)WIN_ROWS - 1) / (long long)WIN_ROWS);
-    std::vector<int2> groups;
-    mpb_window_groups(win_pos, nw, groups);
-    InBuf gr(ctx, groups.data(), groups.size() * sizeof(int2));
-    if (gr.rc) return gr.rc;
-    const unsigned gy = window_pass_gy(ctx, k_prefilter, gx, (int)groups.size());
-    ctx->pending_units = (double)nw * (double)m->n_seq;
-    LAUNCH(ctx, k_prefilter, dim3(gx, gy), HIST_THREADS, 0, m->planes, m->nsp, m->n_seq, m->lens, k, v, wp.dev<int32_t>(),
-           gr.dev<int2>(), (int)groups.size(), bins, m->err);
+    if (mpb_use_col_passes() && nw <= 65535) {
+        std::vector<int2> chunks;
+        std::vector<int32_t> chunk_win;
+        mpb_window_chunks(win_pos, nw, k, chunks, chunk_win);
+        InBuf cd(ctx, chunks.data(), chunks.size() * sizeof(int2)), cw(ctx, chunk_win.data(), chunk_win.size() * 4);
+        if (cd.rc || cw.rc) return MPB_ECUDA;
+        const unsigned gx = (unsigned)((m->nwords + CW_WORDS - 1) / CW_WORDS);
+        ctx->pending_units = (double)nw * (double)m->n_seq;
+        MPB_LAUNCH_NAMED(ctx, "k_prefilter", k_prefilter_col, dim3(gx, (unsigned)chunks.size()), CW_THREADS, 0, m->colp,
+                         (long long)m->nwords, (m->ncw - 1) * 32, m->cons, m->planes, m->nsp, m->n_seq, m->lens, k, v,
+                         wp.dev<int32_t>(), cd.dev<int2>(), cw.dev<int32_t>(), (int)chunks.size(), bins, m->err);
+    } else {
+        const unsigned gx = (unsigned)((m->n_seq + (long long)WIN_ROWS - 1) / (long long)WIN_ROWS);
+        std::vector<int2> groups;
+        mpb_window_groups(win_pos, nw, groups);
+        InBuf gr(ctx, groups.data(), groups.size() * sizeof(int2));
+        if (gr.rc) return gr.rc;
+        const unsigned gy = window_pass_gy(ctx, k_prefilter, gx, (int)groups.size());
+        ctx->pending_units = (double)nw * (double)m->n_seq;
+        LAUNCH(ctx, k_prefilter, dim3(gx, gy), HIST_THREADS, 0, m->planes, m->nsp, m->n_seq, m->lens, k, v, wp.dev<int32_t>(),
+               gr.dev<int2>(), (int)groups.size(), bins, m->err);
+    }
     LAUNCH(ctx, k_prefilter_sums, (unsigned)nw, 256, 0, bins, o0.dev<double>(), o1.dev<double>());
     CK(o0.finish());
     CK(o1.finish());
@@ -983,6 +1393,39 @@ static int hist_launch_build(mpb_hist* h) {
     CK(cudaMemsetAsync(h->n_entries, 0, (size_t)nw * 8, ctx->stream));
     CK(cudaMemsetAsync(h->spec_n, 0, (size_t)nw * 8, ctx->stream));
     CK(cudaMemsetAsync(h->exc_n, 0, 8, ctx->stream));
+    if (mpb_use_col_passes()) {
+        std::vector<int2> chunks;
+        std::vector<int32_t> chunk_win;
+        mpb_window_chunks(h->h_win_pos.data(), nw, h->k, chunks, chunk_win);
+        InBuf cd(ctx, chunks.data(), chunks.size() * sizeof(int2)), cw(ctx, chunk_win.data(), chunk_win.size() * 4);
+        if (cd.rc || cw.rc) return MPB_ECUDA;
+        HistOut o;
+        o.keys = h->keys;
+        o.cnt = h->cnt;
+        o.first = h->first;
+        o.elist = h->elist;
+        o.log2cap = h->log2cap;
+        o.gap_n = h->gap_n;
+        o.iupac_gap_n = h->iupac_gap_n;
+        o.exc_n = h->exc_n;
+        o.n_entries = h->n_entries;
+        o.spec_n = h->spec_n;
+        o.exc = h->exc;
+        o.exc_max = (long long)h->exc_max;
+        o.row0 = (long long)m->row0;
+        o.nwords = (long long)m->nwords;
+        o.spec_cap = (long long)h->spec_cap;
+        o.spec_bits = h->spec_bits;
+        o.gap_bits = h->gap_bits;
+        o.spec_win = h->spec_win;
+        o.spec_row = h->spec_row;
+        const unsigned gx = (unsigned)((m->nwords + CW_WORDS - 1) / CW_WORDS);
+        ctx->pending_units = (double)nw * (double)m->n_seq;
+        MPB_LAUNCH_NAMED(ctx, "k_hist", k_hist_col, dim3(gx, (unsigned)chunks.size()), CW_THREADS, 0, m->colp, (m->ncw - 1) * 32,
+                         m->cons, m->planes, m->nsp, m->n_seq, m->lens, h->k, h->v, h->win_pos, cd.dev<int2>(),
+                         cw.dev<int32_t>(), (int)chunks.size(), o, m->err);
+        return 0;
+    }
     const unsigned gx = (unsigned)((m->n_seq + (long long)WIN_ROWS - 1) / (long long)WIN_ROWS);
     std::vector<int2> groups;
     mpb_window_groups(h->h_win_pos.data(), nw, groups);

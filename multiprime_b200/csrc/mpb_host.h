@@ -73,6 +73,8 @@ struct mpb_msa {
     uint32_t* colp;     // column view [(ncw-1)*32*4 + 2][nwords]: row (col*4 + base) holds, per 32-sequence word, the
                         // bit "sequence s has base b at column col"; the last two rows are all-ones / all-zeros
     int64_t nwords;     // nsp / 32
+    uint8_t* cons;      // [(ncw-1)*32] a frequent base (0..3) of every column, from a sample of the rows: the reference
+                        // k-mer of the column-domain window passes (any choice is valid, a good one saves work)
     int32_t* lens;      // [nsp]
     int* err;           // device error flags
     int64_t row0;       // global index of local sequence 0 (sequence-sharded runs)

@@ -11,7 +11,8 @@
 //     k_cscan_plan / k_cscan / k_cscan_special    (mpb_cscan.cu) read the candidate count from device memory
 // The host only enqueues; it learns the number of live tracks from a pinned word written by an asynchronous copy and
 // stops enqueueing when it reads zero (rounds enqueued past the end are no-ops: zero candidates).
-// Sequence-sharded runs all-reduce the count vector between scan and advance (the caller does, on the same stream).
+// Sequence-sharded runs sum the count vector over the shards between scan and advance: one single-block kernel over
+// NVLink peer memory on the same stream (mpb_peer.cu, mpb_walk_dev_set_peer), or the caller's own all-reduce.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string.h>
@@ -21,6 +22,7 @@
 #include "mpb200.h"
 #include "mpb_host.h"
 #include "mpb_cscan.h"
+#include "mpb_peer.h"
 #include "mpb_walk_core.h"
 
 #define fail mpb_fail
@@ -45,6 +47,7 @@ struct mpb_walk_dev {
     unsigned long long* totals;  // [2] rounds with candidates, candidates scanned
     int* live_host;         // pinned mirror of live_dev
     int* err;               // track error flags (OR)
+    mpb_peer* peer;         // sharded run: the scan is followed by the peer-memory all-reduce of counts
 };
 
 __global__ void k_walk_seed(int n_win, int k, const int32_t* __restrict__ win_idx, const unsigned long long* __restrict__ freq,
@@ -222,8 +225,19 @@ extern "C" int mpb_walk_dev_scan(mpb_walk_dev* w) {
     if (!w) return fail(MPB_EINVAL, "NULL argument");
     mpb_ctx* ctx = w->h->msa->ctx;
     CK(cudaSetDevice(ctx->device));
-    return mpb_cscan_launch(w->h, w->fmask, w->rmask, w->cands, w->n_cand, w->max_cands, w->plans, w->counts, 1, nullptr,
-                            nullptr);
+    int rc = mpb_cscan_launch(w->h, w->fmask, w->rmask, w->cands, w->n_cand, w->max_cands, w->plans, w->counts, 1, nullptr,
+                              nullptr);
+    if (rc || !w->peer) return rc;
+    return mpb_peer_allreduce_launch(w->peer, w->counts, w->n_cand, 4, w->err);
+}
+
+extern "C" int mpb_walk_dev_set_peer(mpb_walk_dev* w, mpb_peer* peer) {
+    if (!w) return fail(MPB_EINVAL, "NULL argument");
+    if (peer && (int64_t)w->max_cands * 4 > mpb_peer_cap(peer))
+        return fail(MPB_EINVAL, "a round of this walk may hold %lld counters, the peer group carries %lld",
+                    (long long)w->max_cands * 4, (long long)mpb_peer_cap(peer));
+    w->peer = peer;
+    return 0;
 }
 
 extern "C" int mpb_walk_dev_round(mpb_walk_dev* w) {
@@ -317,6 +331,8 @@ extern "C" int mpb_walk_dev_finish(mpb_walk_dev* w, uint8_t* out_sets, int64_t* 
     if (err & 1) return fail(MPB_EINVAL, "refinement would re-add a base (the reference raises KeyError)");
     if (err & 2) return fail(MPB_EOVERFLOW, "more than %d refinement rounds in one window", MPB_WALK_MAX_ROUNDS);
     if (err & 4) return fail(MPB_EOVERFLOW, "candidate buffer overflow");
+    if (err & MPB_ERR_PEER_TIMEOUT) return fail(MPB_ECUDA, "sharded walk: a peer's counts did not arrive (peer all-reduce timed out)");
+    if (err & MPB_ERR_PEER_CAP) return fail(MPB_EOVERFLOW, "sharded walk: count vector longer than the peer group's capacity");
     // the last scanned round's candidates are not in totals yet when live tracks remain (caller stopped early)
     for (int s = 0; s < 2 * n_win; ++s)
         if ((s & 1) < ntr[s >> 1] && tracks[s].state != 2) return fail(MPB_EINVAL, "walk not finished: track %d still live", s);

@@ -3,8 +3,10 @@
 TEST INFRASTRUCTURE ONLY.  It implements the interface of multiprime_b200.comm.TorchComm with `on_gpu = True`, so a
 single-GPU box exercises the DEVICE branches of the sharded path — Hist.export_dev -> all-to-all of device tensors ->
 mpb_hist_merge_segments from device pointers, and the in-place all-reduce of the walk's device count vector — that
-otherwise only run under NCCL with two or more GPUs.  All shards use the legacy default stream, so device work is ordered
-by issue order; the host side is ordered by barriers."""
+otherwise only run under NCCL with two or more GPUs.  By default all shards use the legacy default stream, so device
+work is ordered by issue order and the host side by barriers.  With `streams=True` every shard works on a stream of its
+own (the device collectives synchronise it around every exchange) and `peer_ok` is set: the walk then sums its counts
+through the peer-memory kernel (mpb_peer_*), the shards' single-block kernels waiting for each other on ONE GPU."""
 from __future__ import annotations
 
 import threading
@@ -13,7 +15,11 @@ import numpy as np
 
 
 class _Shared:
+    _serial = [0]
+
     def __init__(self, world):
+        _Shared._serial[0] += 1
+        self.serial = _Shared._serial[0]     # names the group in caches that outlive it (ids are reused)
         self.world = world
         self.barrier = threading.Barrier(world)
         self.slots = [None] * world
@@ -22,10 +28,17 @@ class _Shared:
 class ThreadComm:
     on_gpu = True
 
-    def __init__(self, shared: _Shared, rank: int, device):
+    def __init__(self, shared: _Shared, rank: int, device, own_stream: bool = False):
         import torch
         self.torch = torch
         self.sh, self.rank, self.world, self.device = shared, rank, shared.world, device
+        self.own_stream = own_stream
+        self.peer_ok = own_stream            # peer kernels of two shards on ONE stream would wait for each other forever
+        self.peer_key = ("thread", shared.serial)
+
+    def _sync(self):
+        if self.own_stream:
+            self.torch.cuda.current_stream().synchronize()
 
     # -- plumbing -----------------------------------------------------------------------------------------
     def _exchange(self, obj):
@@ -72,12 +85,14 @@ class ThreadComm:
         return self.torch.empty(max(1, n), dtype=tdt, device=self.device)
 
     def alltoall_dev(self, t, send_counts, recv_counts):
+        self._sync()
         parts = self._exchange_keep((t, np.asarray(send_counts)))
         out = []
         for a, sc in parts:
             off = np.concatenate([[0], np.cumsum(sc)])
             out.append(a[int(off[self.rank]):int(off[self.rank + 1])])
         res = self.torch.cat(out) if out else t[:0]
+        self._sync()
         self.sh.barrier.wait()                    # nobody frees a tensor another shard is still reading
         assert [len(o) for o in out] == [int(c) for c in recv_counts]
         if res.numel() == 0:
@@ -90,12 +105,15 @@ class ThreadComm:
         return list(self.sh.slots)
 
     def allreduce_dev_inplace(self, t):
+        self._sync()
         parts = self._exchange_keep(t)
         total = parts[0].clone()
         for p in parts[1:]:
             total += p
+        self._sync()
         self.sh.barrier.wait()                    # every shard has its sum before anybody overwrites an input
         t.copy_(total)
+        self._sync()
         self.sh.barrier.wait()
 
     def wrap_dev(self, ptr: int, n: int):
@@ -104,15 +122,21 @@ class ThreadComm:
         return self.torch.as_tensor(_Raw(), device=self.device)
 
 
-def run_shards(world: int, fn):
-    """run fn(rank, comm) on `world` threads; returns the results in rank order (re-raises the first failure)"""
+def run_shards(world: int, fn, streams: bool = False):
+    """run fn(rank, comm) on `world` threads; returns the results in rank order (re-raises the first failure).
+    streams: every shard inside its own torch stream (fn reads it with torch.cuda.current_stream())"""
     import torch
     shared = _Shared(world)
     out, errs = [None] * world, []
 
     def body(rank):
         try:
-            out[rank] = fn(rank, ThreadComm(shared, rank, torch.device("cuda", 0)))
+            if streams:
+                with torch.cuda.stream(torch.cuda.Stream(device=0)):
+                    out[rank] = fn(rank, ThreadComm(shared, rank, torch.device("cuda", 0), own_stream=True))
+                    torch.cuda.current_stream().synchronize()
+            else:
+                out[rank] = fn(rank, ThreadComm(shared, rank, torch.device("cuda", 0)))
         except BaseException as exc:              # a dead shard would leave the others at a barrier
             errs.append(exc)
             shared.barrier.abort()

@@ -19,7 +19,7 @@ def test_build_and_symbols():
     for name in declared:
         assert hasattr(lib, name), name
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
-    assert _lib.load().mpb_abi_version() == 2
+    assert _lib.load().mpb_abi_version() == 3
 
 
 def test_no_cpu_fallback():

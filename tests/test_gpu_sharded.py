@@ -81,7 +81,7 @@ def test_two_shards_one_gpu(name):
         assert not bad, (rank, bad[:3])
 
 
-def _shard_rows(name, rank, world, comm, **extra):
+def _shard_rows(name, rank, world, comm, _expect_peer=None, **extra):
     """design() of one shard of a golden case -> (start, stop, mismatching records)"""
     import numpy as np
     from multiprime_b200 import core
@@ -97,6 +97,8 @@ def _shard_rows(name, rank, world, comm, **extra):
         codes = np.pad(codes, ((0, 0), (0, full_cols - codes.shape[1])))
     app = core.NN_degenerate(seq_file=None, nproc=1, outfile="", alignment=(ids[lo:hi], codes, lens), row0=lo,
                              comm=comm, **extra, **case["params"])
+    if _expect_peer is not None:
+        assert (app.peer is not None) == _expect_peer
     recs = case["records"]
     got = {r["row"][0]: r for r in app.design([r["pos"] for r in recs])}
     bad = []
@@ -122,6 +124,56 @@ def test_device_collectives_loopback(name, world):
         assert n_acc > 0
 
 
+def test_peer_allreduce_kernel():
+    """mpb_peer_allreduce on its own: three shards on threads (one stream each), a few rounds of different lengths, the
+    sums compared with numpy; the sequence numbers and slot parities carry over from round to round"""
+    import numpy as np
+    import torch
+    from multiprime_b200 import _lib
+    from tests.loopback_comm import run_shards
+    world, rounds = 3, [1, 5, 1000, 4096, 7, 4096, 33]
+    rng = np.random.default_rng(5)
+    data = [[rng.integers(0, 1 << 40, n) for n in rounds] for _ in range(world)]
+
+    def body(rank, comm):
+        ctx = _lib.Context(0, torch.cuda.current_stream().cuda_stream)
+        peer = _lib.Peer(ctx, comm, cap_elems=4096)
+        got = []
+        for i, n in enumerate(rounds):
+            t = torch.from_numpy(data[rank][i].astype(np.int64)).cuda()
+            torch.cuda.current_stream().synchronize()
+            peer.allreduce(t.data_ptr(), n)
+            got.append(t.cpu().numpy())
+        comm.barrier()
+        peer.close()
+        return got
+
+    res = run_shards(world, body, streams=True)
+    for i, n in enumerate(rounds):
+        want = sum(data[r][i] for r in range(world))
+        for r in range(world):
+            assert (res[r][i] == want).all(), (r, i)
+
+
+@pytest.mark.parametrize("name,world", [("synth_iupac", 2), ("c2_k18", 3)])
+def test_walk_over_peer_memory_loopback(name, world):
+    """the sharded walk with the peer-memory all-reduce in its kernel chain (what NCCL runs use), shards on threads"""
+    import torch
+    from tests.loopback_comm import run_shards
+
+    def body(rank, comm):
+        assert comm.peer_ok
+        return _shard_rows(name, rank, world, comm, device=0, stream=torch.cuda.current_stream().cuda_stream,
+                           _expect_peer=True)
+
+    res = run_shards(world, body, streams=True)
+    case = load_case(name)
+    for rank, (start, stop, bad, n_acc) in enumerate(res):
+        assert (start, stop) == (case["start"], case["stop"])
+        assert not bad, (rank, bad[:3])
+        assert n_acc > 0
+
+
 def _nccl_worker(rank, world, port, name, q):
     import torch
     import torch.distributed as dist
@@ -131,17 +183,19 @@ def _nccl_worker(rank, world, port, name, q):
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     res = _shard_rows(name, rank, world, TorchComm(torch.device("cuda", rank)), device=rank,
-                      stream=torch.cuda.current_stream().cuda_stream)
+                      stream=torch.cuda.current_stream().cuda_stream, _expect_peer=os.environ.get("MPB_PEER", "1") != "0")
     q.put((rank,) + res)
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("name", ["synth_iupac", "c2_k18"])
-def test_two_ranks_nccl(name):
-    """the NCCL path bench.py --gpus N runs: two ranks on two GPUs, rows and traces of the golden case"""
+@pytest.mark.parametrize("name,peer", [("synth_iupac", "1"), ("c2_k18", "1"), ("c2_k18", "0")])
+def test_two_ranks_nccl(name, peer, monkeypatch):
+    """the NCCL path bench.py --gpus N runs: two ranks on two GPUs, rows and traces of the golden case; the walk's counts
+    summed through peer memory opened over CUDA IPC (MPB_PEER=1, the default) or by NCCL all-reduces (MPB_PEER=0)"""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
+    monkeypatch.setenv("MPB_PEER", peer)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
