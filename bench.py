@@ -348,6 +348,11 @@ def run_b200(args):
         a.close()
         return recs
 
+    # a long-lived process (server, pipeline driver) does not want the cyclic GC to walk the 10^6 sequence ids and the
+    # imported modules in the middle of a step (a full collection costs 100+ ms here): park everything allocated so far
+    import gc
+    gc.collect()
+    gc.freeze()
     results = {}
     sampler = ClockSampler(local)
     for name, fn in (("value", step_resident), ("e2e", step_e2e)):

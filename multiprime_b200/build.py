@@ -10,7 +10,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libmpb200.so")
-SOURCES = ["mpb200.cu", "mpb_cscan.cu", "mpb_walk_dev.cu", "mpb_peer.cu", "mpb_dimer.cu", "mpb_walk.cu"]
+SOURCES = ["mpb200.cu", "mpb_cscan.cu", "mpb_prefilter.cu", "mpb_walk_dev.cu", "mpb_peer.cu", "mpb_dimer.cu", "mpb_walk.cu"]
 HEADERS = [os.path.join(CSRC, h) for h in ("mpb_device.cuh", "mpb_host.h", "mpb_cscan.h", "mpb_walk_core.h")] + \
     [os.path.join(ROOT, "include", "mpb200.h")]
 

@@ -13,6 +13,7 @@
 #include "mpb200.h"
 #include "mpb_host.h"
 #include "mpb_device.cuh"
+#include "mpb_prefilter.h"
 
 // ------------------------------------------------------------------------------------------------------
 // host-side plumbing (shared pieces live in mpb_host.h)
@@ -335,6 +336,7 @@ extern "C" int mpb_msa_upload(mpb_ctx* ctx, const uint8_t* packed4, int64_t n_se
                 return fail(MPB_EINVAL, "lens[%lld]=%d outside 0..n_col", (long long)i, lens[i]);
             }
             hl[i] = lens[i];
+            if (lens[i] < n_col) m->short_rows = true;
         }
         CK(cudaMemcpyAsync(m->lens, hl.data(), m->nsp * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     } else {
@@ -1169,102 +1171,6 @@ k_hist_col(const uint32_t* __restrict__ colp, int ncols, const uint8_t* __restri
     hist_col_flush(pl, nsp, lens, k, v, kmask, win_pos, o, row_base, s_q, &s_qn, err);
 }
 
-// the queued rows of the prefilter, on the row view
-__device__ __forceinline__ void pre_col_flush(const uint32_t* __restrict__ pl, int64_t nsp, const int32_t* __restrict__ lens,
-                                              int k, int v, uint32_t kmask, const int32_t* __restrict__ win_pos,
-                                              unsigned int* __restrict__ bins, int64_t row_base, const unsigned int* s_q,
-                                              unsigned int* s_qn, int* __restrict__ err) {
-    __syncthreads();
-    const unsigned n = *s_qn;
-    for (unsigned i = threadIdx.x; i < n; i += CW_THREADS) {
-        const unsigned e = s_q[i];
-        const int wi = (int)(e & 0xFFFFu);
-        const int64_t s = row_base + (e >> 16);
-        const int p = __ldg(win_pos + wi);
-        const int len = __ldg(lens + s);
-        const uint4* wb = reinterpret_cast<const uint4*>(pl) + (int64_t)(p >> 5) * nsp + s;
-        const uint4 q0 = __ldg(wb), q1 = __ldg(wb + nsp);
-        const RawWin r = win_cut(q0, q1, p & 31, kmask, p, k, len);
-        unsigned int* B = bins + (long long)wi * PRE_BINS;
-        if (!r.special) {
-            atomicAdd(&B[pre_code(r.c, r.g, r.t)], 1u);
-        } else {
-            Win w;
-            if (!mpb_load_window(pl, nsp, s, len, p, k, kmask, w)) atomicOr(err, MPB_ERR_SHORT_ROW);
-            pre_row(w, v, B, err);
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) *s_qn = 0;
-    __syncthreads();
-}
-
-__global__ void __launch_bounds__(CW_THREADS)
-k_prefilter_col(const uint32_t* __restrict__ colp, long long nwords, int ncols, const uint8_t* __restrict__ cons,
-                const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq, const int32_t* __restrict__ lens, int k, int v,
-                const int32_t* __restrict__ win_pos, const int2* __restrict__ chunks, const int32_t* __restrict__ chunk_win,
-                int n_chunks, unsigned int* __restrict__ bins, int* __restrict__ err) {
-    __shared__ unsigned int s_q[CW_QCAP];
-    __shared__ unsigned int s_qn;
-    const uint32_t kmask = (1u << k) - 1u;
-    int lane;
-    asm("mov.u32 %0, %%laneid;" : "=r"(lane));
-    const int warp = threadIdx.x >> 5;
-    const int64_t row_base = (int64_t)blockIdx.x * CW_ROWS;
-    const long long word_base = (long long)blockIdx.x * CW_WORDS;
-    int L = 1;
-    while (2 * L <= k) L *= 2;
-    if (threadIdx.x == 0) s_qn = 0;
-    __syncthreads();
-    for (int ch = blockIdx.y; ch < n_chunks; ch += gridDim.y) {
-        const int2 cc = chunks[ch];
-        const int wi = chunk_win[ch * 32 + lane];
-        const bool lane_ok = wi >= 0 && lane + k <= 32;
-        const int col = cc.x + lane;
-        const bool colok = col < ncols;
-        const int cb = colok ? (int)cons[col] : 0;
-        const uint32_t lo_w = __ballot_sync(0xffffffffu, cb & 1), hi_w = __ballot_sync(0xffffffffu, cb & 2);
-        // pre_code(c, g, t) only looks at c | t and g | t: the low and high bits of the reference bases
-        const uint32_t lo = (lo_w >> lane) & kmask, hi = (hi_w >> lane) & kmask;
-        const uint32_t major_code = pre_code(lo & ~hi, hi & ~lo, lo & hi);
-        unsigned my_count = 0, ag_count = 0;
-        for (int it = 0; it < CW_WPW; ++it) {
-            __syncthreads();
-            if (s_qn > CW_QCAP - CW_QROOM)
-                pre_col_flush(pl, nsp, lens, k, v, kmask, win_pos, bins, row_base, s_q, &s_qn, err);
-            else
-                __syncthreads();
-            const long long W = word_base + it * CW_WARPS + warp;
-            if (W >= nwords) continue;
-            const long long left = (long long)n_seq - W * 32;
-            const uint32_t vm = left >= 32 ? 0xFFFFFFFFu : left <= 0 ? 0u : ((1u << left) - 1u);
-            uint32_t A = 0, C = 0, G = 0, T = 0;
-            if (colok && vm) {
-                const uint32_t* base = colp + ((long long)col * 4) * nwords + W;
-                A = __ldg(base);
-                C = __ldg(base + nwords);
-                G = __ldg(base + 2 * nwords);
-                T = __ldg(base + 3 * nwords);
-            }
-            const uint32_t ragged = vm ? col_ragged(lens, W * 32 + lane, n_seq, col + k, cc.y) : 0u;
-            const ColClass r = col_classify(A, C, G, T, cb, k, L, vm, ragged);
-            uint32_t defer = 0;
-            if (lane_ok) {
-                my_count += __popc(r.match);
-                ag_count += __popc(r.agp);
-                defer = vm & ~(r.match | r.agp);
-            }
-            cw_push(defer, (unsigned)wi, (unsigned)((it * CW_WARPS + warp) * 32), s_q, &s_qn, lane);
-        }
-        if (lane_ok) {
-            unsigned int* B = bins + (long long)wi * PRE_BINS;
-            if (my_count) atomicAdd(&B[major_code], my_count);
-            if (ag_count) atomicAdd(&B[pre_code(0u, 0u, 0u)], ag_count);
-        }
-    }
-    pre_col_flush(pl, nsp, lens, k, v, kmask, win_pos, bins, row_base, s_q, &s_qn, err);
-}
-
 // host: chunks of windows for the column-domain passes (windows sorted by start column; a chunk holds the windows that
 // start within 33 - k columns of its first one, at most one per column)
 static void mpb_window_chunks(const int32_t* win_pos, int nw, int k, std::vector<int2>& chunks, std::vector<int32_t>& chunk_win) {
@@ -1335,24 +1241,16 @@ extern "C" int mpb_window_prefilter(mpb_msa* m, int k, int v, const int32_t* win
             return fail(MPB_EINVAL, "win_pos[%d]=%d outside the alignment", i, win_pos[i]);
     mpb_ctx* ctx = m->ctx;
     CK(cudaSetDevice(ctx->device));
+    bool inside = true;  // the bit-sliced kernel walks columns win_pos .. win_pos + k - 1 of the column view
+    for (int i = 0; i < nw; ++i) inside = inside && win_pos[i] + k <= m->n_col;
+    if (mpb_use_col_passes() && inside && !m->short_rows) return mpb_prefilter_bs(m, k, v, win_pos, nw, s0_hd, s1_hd);
     unsigned int* bins = nullptr;
     CK(cudaMallocAsync(&bins, (size_t)nw * PRE_BINS * 4, ctx->stream));
     CK(cudaMemsetAsync(bins, 0, (size_t)nw * PRE_BINS * 4, ctx->stream));
     InBuf wp(ctx, win_pos, (size_t)nw * 4);
     OutBuf o0(ctx, s0_hd, (size_t)nw * 8), o1(ctx, s1_hd, (size_t)nw * 8);
     if (wp.rc || o0.rc || o1.rc) return MPB_ECUDA;
-    if (mpb_use_col_passes() && nw <= 65535) {
-        std::vector<int2> chunks;
-        std::vector<int32_t> chunk_win;
-        mpb_window_chunks(win_pos, nw, k, chunks, chunk_win);
-        InBuf cd(ctx, chunks.data(), chunks.size() * sizeof(int2)), cw(ctx, chunk_win.data(), chunk_win.size() * 4);
-        if (cd.rc || cw.rc) return MPB_ECUDA;
-        const unsigned gx = (unsigned)((m->nwords + CW_WORDS - 1) / CW_WORDS);
-        ctx->pending_units = (double)nw * (double)m->n_seq;
-        MPB_LAUNCH_NAMED(ctx, "k_prefilter", k_prefilter_col, dim3(gx, (unsigned)chunks.size()), CW_THREADS, 0, m->colp,
-                         (long long)m->nwords, (m->ncw - 1) * 32, m->cons, m->planes, m->nsp, m->n_seq, m->lens, k, v,
-                         wp.dev<int32_t>(), cd.dev<int2>(), cw.dev<int32_t>(), (int)chunks.size(), bins, m->err);
-    } else {
+    {
         const unsigned gx = (unsigned)((m->n_seq + (long long)WIN_ROWS - 1) / (long long)WIN_ROWS);
         std::vector<int2> groups;
         mpb_window_groups(win_pos, nw, groups);

@@ -76,6 +76,7 @@ struct mpb_msa {
     uint8_t* cons;      // [(ncw-1)*32] a frequent base (0..3) of every column, from a sample of the rows: the reference
                         // k-mer of the column-domain window passes (any choice is valid, a good one saves work)
     int32_t* lens;      // [nsp]
+    bool short_rows;    // some row ends before the alignment does (unaligned input)
     int* err;           // device error flags
     int64_t row0;       // global index of local sequence 0 (sequence-sharded runs)
 };

@@ -1,6 +1,7 @@
-"""GPU suite: the column-domain window passes (k_prefilter_col, k_hist_col: the default) against the row-domain kernels
-(MPB_WINPASS=row) on identical inputs — prefilter sums, table contents, per-window counters, statistics, and, through
-the column scan on random candidates, the row classes and patched special windows both builds leave behind."""
+"""GPU suite: the column-domain window passes (k_prefilter_bs, k_hist_col: the default) against the row-domain kernels
+(MPB_WINPASS=row) on identical inputs — table contents, per-window counters, statistics, and, through the column scan on
+random candidates, the row classes and patched special windows both builds leave behind.  The two prefilters use
+different code functions: their item counts must agree exactly, and both must stay below the exact entropy."""
 import numpy as np
 import pytest
 
@@ -61,7 +62,15 @@ def test_column_passes_equal_row_passes(n, L, k, v, kw, monkeypatch):
         snaps[mode] = _snapshot(msa, k, v, pos, codes, 11, with_prefilter=k >= 8)
     a, b = snaps["row"], snaps["col"]
     if k >= 8:
-        assert (a["pre"][0] == b["pre"][0]).all() and (a["pre"][1] == b["pre"][1]).all()
+        assert (a["pre"][0] == b["pre"][0]).all()                               # items counted: every expansion, every gap row
+        ent, n_ig = a["ent"], a["stats"]["n_iupac_gap"]
+        exact = -((ent[:, 1] - ent[:, 0] * np.log2(n)) + (ent[:, 3] - ent[:, 2] * np.log2(n))) / n
+        ok = n_ig == 0                                                           # (those rows are not table entries)
+        assert ok.sum() > 10
+        for snap in (a, b):
+            bound = (snap["pre"][0] * np.log2(n) - snap["pre"][1]) / n
+            assert (bound[ok] <= exact[ok] + 1e-9).all()
+            assert (bound[ok] >= 0.5 * exact[ok] - 1e-9).all()                   # and it is not a trivial bound
     for x, y in zip(a["counts"], b["counts"]):
         assert (x == y).all()
     for name in a["stats"]:
@@ -74,6 +83,34 @@ def test_column_passes_equal_row_passes(n, L, k, v, kw, monkeypatch):
     assert (a["scan"][0] == b["scan"][0]).all()
     assert (a["scan"][1] == b["scan"][1]).all()
     assert a["counts"][2].sum() > 0
+    msa.close()
+    ctx.close()
+
+
+def test_bitsliced_prefilter_is_tight_on_plain_rows():
+    """gap-free, IUPAC-free alignment: every row is one item, the exact window entropy comes from numpy; the 8192-bin
+    code histogram must bound it from below and, where the window has few distinct k-mers, reach it"""
+    from multiprime_b200 import _lib, core, synth
+    n, L, k = 40000, 150, 18
+    codes = synth.synth_codes(n, L, seed=12, gap_rate=0.0, iupac_rate=0.0, term_gap=0.0)
+    ctx = _lib.Context(0)
+    msa = _lib.Msa(ctx, core.pack4(codes), n, L)
+    pos = list(range(0, L - k, 3))
+    s0, s1 = msa.prefilter(k, 2, pos)
+    assert (s0 == n).all()
+    bound = (s0 * np.log2(n) - s1) / n
+    base = np.log2(codes).astype(np.uint64)                                      # one-hot 1,2,4,8 -> 0..3
+    for wi, p in enumerate(pos):
+        key = np.zeros(n, np.uint64)
+        for j in range(k):
+            key = key * np.uint64(4) + base[:, p + j]
+        _, cnt = np.unique(key, return_counts=True)
+        exact = float(-(cnt / n * np.log2(cnt / n)).sum())
+        assert bound[wi] <= exact + 1e-9, (p, bound[wi], exact)
+        if len(cnt) < 300:
+            assert bound[wi] >= exact - 0.05, (p, bound[wi], exact, len(cnt))
+        else:
+            assert bound[wi] >= min(exact, 12.0) - 1.5, (p, bound[wi], exact, len(cnt))
     msa.close()
     ctx.close()
 
