@@ -1053,38 +1053,100 @@ struct HistOut {
     int32_t* spec_row;
 };
 
-// the queued rows of the table build, on the row view
+// make sure first[slot of key] <= ord for a key that is already in the table (a warp-mate has just inserted it)
+__device__ __forceinline__ void mpb_table_min_first(const uint64_t* __restrict__ keys, uint64_t* __restrict__ first,
+                                                    int log2cap, uint64_t key, uint64_t ord) {
+    const uint32_t mask = (1u << log2cap) - 1u;
+    const uint32_t last_probe = mask < 8191u ? mask : 8191u;
+    uint32_t h = mpb_hash(key, log2cap);
+    for (uint32_t probe = 0; probe <= last_probe; ++probe) {
+        const uint64_t cur = *((volatile const uint64_t*)&keys[h]);
+        if (cur == key) {
+            if (*((volatile uint64_t*)&first[h]) > ord) atomicMin((unsigned long long*)&first[h], (unsigned long long)ord);
+            return;
+        }
+        if (cur == MPB_KEY_EMPTY_D) return;  // (cannot happen: the leader's insert is ordered before this probe)
+        h = (h + 1) & mask;
+    }
+}
+
+#define CW_Q2CAP 1024  // rows of one flush that need the general path (gaps, patching, IUPAC expansion)
+
+// the queued rows of the table build, on the row view.  Pass 1, every queued row: cut the window; a gap-free plain row
+// is a table insert — rows of one warp that carry the same k-mer of the same window (clade variants, frequent single
+// mutants) are inserted once, with their number — the others are set aside.  Pass 2, the rows set aside, with all lanes
+// busy again: patching, gap test, expansion, base-5 keys (hist_row).
 __device__ __forceinline__ void hist_col_flush(const uint32_t* __restrict__ pl, int64_t nsp, const int32_t* __restrict__ lens,
                                                int k, int v, uint32_t kmask, const int32_t* __restrict__ win_pos,
                                                const HistOut& o, int64_t row_base, const unsigned int* s_q,
-                                               unsigned int* s_qn, int* __restrict__ err) {
+                                               unsigned int* s_qn, unsigned int* s_q2, unsigned int* s_q2n,
+                                               int short_rows, int* __restrict__ err) {
     __syncthreads();
     const unsigned n = *s_qn;
     const uint64_t cap = 1ull << o.log2cap;
-    for (unsigned i = threadIdx.x; i < n; i += CW_THREADS) {
-        const unsigned e = s_q[i];
-        const int wi = (int)(e & 0xFFFFu);
-        const int64_t s = row_base + (e >> 16);
-        const int p = __ldg(win_pos + wi);
-        const int len = __ldg(lens + s);
-        const uint4* wb = reinterpret_cast<const uint4*>(pl) + (int64_t)(p >> 5) * nsp + s;
-        const uint4 q0 = __ldg(wb), q1 = __ldg(wb + nsp);
-        const RawWin r = win_cut(q0, q1, p & 31, kmask, p, k, len);
-        uint64_t* K = o.keys + (uint64_t)wi * cap;
-        uint32_t* C = o.cnt + (uint64_t)wi * cap;
-        uint64_t* F = o.first + (uint64_t)wi * cap;
-        uint32_t* E = o.elist + (uint64_t)wi * cap;
-        if (!r.special && r.gapv == 0u) {
-            mpb_table_add(K, C, F, o.log2cap, (uint64_t)(r.c | r.t) | ((uint64_t)(r.g | r.t) << k), 1u,
-                          (uint64_t)(o.row0 + s) << 16, err, &o.n_entries[wi], E);
-        } else {
-            hist_row(pl, nsp, s, len, p, k, v, kmask, o.row0, wi, K, C, F, E, o.log2cap, o.gap_n, o.iupac_gap_n, o.exc, o.exc_n,
-                     o.exc_max, o.n_entries, o.gap_bits, o.nwords, o.spec_win, o.spec_row, o.spec_n, o.spec_cap,
-                     r.special ? 1 : 2, err);
+    const int lane = threadIdx.x & 31;
+    for (unsigned i0 = 0; i0 < n; i0 += CW_THREADS) {  // whole warps stay together for the votes
+        const unsigned i = i0 + threadIdx.x;
+        const bool have = i < n;
+        int wi = -1;
+        int64_t s = 0;
+        bool simple = false, special = false;
+        unsigned long long key = 0;
+        unsigned e = 0;
+        if (have) {
+            e = s_q[i];
+            wi = (int)(e & 0xFFFFu);
+            s = row_base + (e >> 16);
+            const int p = __ldg(win_pos + wi);
+            const uint4* wb = reinterpret_cast<const uint4*>(pl) + (int64_t)(p >> 5) * nsp + s;
+            const uint4 q0 = __ldg(wb), q1 = __ldg(wb + nsp);
+            const RawWin r = win_cut(q0, q1, p & 31, kmask, p, k, short_rows ? __ldg(lens + s) : 0x7FFFFFFF);
+            special = r.special;
+            simple = !r.special && r.gapv == 0u;
+            key = (unsigned long long)(r.c | r.t) | ((unsigned long long)(r.g | r.t) << k);
+        }
+        const unsigned sm = __ballot_sync(0xffffffffu, simple);
+        if (simple) {
+            const unsigned peers = __match_any_sync(sm, key) & __match_any_sync(sm, wi);
+            const int leader = __ffs(peers) - 1;
+            const uint64_t ord = (uint64_t)(o.row0 + s) << 16;
+            if (lane == leader)
+                mpb_table_add(o.keys + (uint64_t)wi * cap, o.cnt + (uint64_t)wi * cap, o.first + (uint64_t)wi * cap, o.log2cap,
+                              key, (uint32_t)__popc(peers), ord, err, &o.n_entries[wi], o.elist + (uint64_t)wi * cap);
+            const uint64_t ord_leader = __shfl_sync(peers, ord, leader);
+            __syncwarp(peers);  // the leader's insert is visible to its peers
+            if (lane != leader && ord < ord_leader)  // rows are queued nearly in order: rare
+                mpb_table_min_first(o.keys + (uint64_t)wi * cap, o.first + (uint64_t)wi * cap, o.log2cap, key, ord);
+        } else if (have) {
+            const unsigned idx = atomicAdd(s_q2n, 1u);
+            if (idx < CW_Q2CAP) {
+                s_q2[idx] = e | (special ? 0x10000000u : 0u);
+            } else {  // list full: where the row stands
+                const int p = __ldg(win_pos + wi);
+                hist_row(pl, nsp, s, __ldg(lens + s), p, k, v, kmask, o.row0, wi, o.keys + (uint64_t)wi * cap,
+                         o.cnt + (uint64_t)wi * cap, o.first + (uint64_t)wi * cap, o.elist + (uint64_t)wi * cap, o.log2cap,
+                         o.gap_n, o.iupac_gap_n, o.exc, o.exc_n, o.exc_max, o.n_entries, o.gap_bits, o.nwords, o.spec_win,
+                         o.spec_row, o.spec_n, o.spec_cap, special ? 1 : 2, err);
+            }
         }
     }
     __syncthreads();
-    if (threadIdx.x == 0) *s_qn = 0;
+    const unsigned n2 = *s_q2n < CW_Q2CAP ? *s_q2n : CW_Q2CAP;
+    for (unsigned i = threadIdx.x; i < n2; i += CW_THREADS) {
+        const unsigned e = s_q2[i];
+        const int wi = (int)(e & 0xFFFFu);
+        const int64_t s = row_base + ((e >> 16) & 0xFFFu);
+        const int p = __ldg(win_pos + wi);
+        hist_row(pl, nsp, s, __ldg(lens + s), p, k, v, kmask, o.row0, wi, o.keys + (uint64_t)wi * cap, o.cnt + (uint64_t)wi * cap,
+                 o.first + (uint64_t)wi * cap, o.elist + (uint64_t)wi * cap, o.log2cap, o.gap_n, o.iupac_gap_n, o.exc, o.exc_n,
+                 o.exc_max, o.n_entries, o.gap_bits, o.nwords, o.spec_win, o.spec_row, o.spec_n, o.spec_cap,
+                 (e & 0x10000000u) ? 1 : 2, err);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        *s_qn = 0;
+        *s_q2n = 0;
+    }
     __syncthreads();
 }
 
@@ -1094,9 +1156,10 @@ __global__ void __launch_bounds__(CW_THREADS)
 k_hist_col(const uint32_t* __restrict__ colp, int ncols, const uint8_t* __restrict__ cons, const uint32_t* __restrict__ pl,
            int64_t nsp, int64_t n_seq, const int32_t* __restrict__ lens, int k, int v, const int32_t* __restrict__ win_pos,
            const int2* __restrict__ chunks, const int32_t* __restrict__ chunk_win, int n_chunks, HistOut o,
-           int* __restrict__ err) {
+           int short_rows, int* __restrict__ err) {
     __shared__ unsigned int s_q[CW_QCAP];
-    __shared__ unsigned int s_qn;
+    __shared__ unsigned int s_q2[CW_Q2CAP];
+    __shared__ unsigned int s_qn, s_q2n;
     const uint32_t kmask = (1u << k) - 1u;
     int lane;
     asm("mov.u32 %0, %%laneid;" : "=r"(lane));
@@ -1107,7 +1170,10 @@ k_hist_col(const uint32_t* __restrict__ colp, int ncols, const uint8_t* __restri
     int L = 1;
     while (2 * L <= k) L *= 2;
     const bool ag_gap = k > v;  // an all-gap row is a gap row (core:688) unless the variation allows k gaps
-    if (threadIdx.x == 0) s_qn = 0;
+    if (threadIdx.x == 0) {
+        s_qn = 0;
+        s_q2n = 0;
+    }
     __syncthreads();
     for (int ch = blockIdx.y; ch < n_chunks; ch += gridDim.y) {
         const int2 cc = chunks[ch];
@@ -1123,7 +1189,7 @@ k_hist_col(const uint32_t* __restrict__ colp, int ncols, const uint8_t* __restri
         for (int it = 0; it < CW_WPW; ++it) {
             __syncthreads();
             if (s_qn > CW_QCAP - CW_QROOM)  // uniform: the counter is read between two barriers
-                hist_col_flush(pl, nsp, lens, k, v, kmask, win_pos, o, row_base, s_q, &s_qn, err);
+                hist_col_flush(pl, nsp, lens, k, v, kmask, win_pos, o, row_base, s_q, &s_qn, s_q2, &s_q2n, short_rows, err);
             else
                 __syncthreads();
             const long long W = word_base + it * CW_WARPS + warp;
@@ -1138,7 +1204,7 @@ k_hist_col(const uint32_t* __restrict__ colp, int ncols, const uint8_t* __restri
                 G = __ldg(base + 2 * o.nwords);
                 T = __ldg(base + 3 * o.nwords);
             }
-            const uint32_t ragged = vm ? col_ragged(lens, W * 32 + lane, n_seq, col + k, cc.y) : 0u;
+            const uint32_t ragged = (short_rows && vm) ? col_ragged(lens, W * 32 + lane, n_seq, col + k, cc.y) : 0u;
             const ColClass r = col_classify(A, C, G, T, cb, k, L, vm, ragged);
             uint32_t defer = 0;
             if (lane_ok) {
@@ -1168,7 +1234,7 @@ k_hist_col(const uint32_t* __restrict__ colp, int ncols, const uint8_t* __restri
             }
         }
     }
-    hist_col_flush(pl, nsp, lens, k, v, kmask, win_pos, o, row_base, s_q, &s_qn, err);
+    hist_col_flush(pl, nsp, lens, k, v, kmask, win_pos, o, row_base, s_q, &s_qn, s_q2, &s_q2n, short_rows, err);
 }
 
 // host: chunks of windows for the column-domain passes (windows sorted by start column; a chunk holds the windows that
@@ -1321,7 +1387,7 @@ static int hist_launch_build(mpb_hist* h) {
         ctx->pending_units = (double)nw * (double)m->n_seq;
         MPB_LAUNCH_NAMED(ctx, "k_hist", k_hist_col, dim3(gx, (unsigned)chunks.size()), CW_THREADS, 0, m->colp, (m->ncw - 1) * 32,
                          m->cons, m->planes, m->nsp, m->n_seq, m->lens, h->k, h->v, h->win_pos, cd.dev<int2>(),
-                         cw.dev<int32_t>(), (int)chunks.size(), o, m->err);
+                         cw.dev<int32_t>(), (int)chunks.size(), o, m->short_rows ? 1 : 0, m->err);
         return 0;
     }
     const unsigned gx = (unsigned)((m->n_seq + (long long)WIN_ROWS - 1) / (long long)WIN_ROWS);

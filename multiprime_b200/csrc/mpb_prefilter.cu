@@ -8,7 +8,7 @@
 // How: the row-domain kernel (k_prefilter in mpb200.cu) pays ~80 warp instructions per (window, 32 rows) and one global
 // reduction per minority row — 3.8e8 L2 reductions per pass on the 10^6 x 600 workload, which bound it (3.5 ms).  Here
 //   * one CLUSTER of BS_CLUSTER thread blocks owns one window; each block keeps the window's whole histogram in shared
-//     memory (8192 bins) for its quarter of the rows — no global atomics at all;
+//     memory (8192 bins) for its share of the rows — no global atomics at all;
 //   * a thread takes 32 sequences at a time (one word of the column view) and walks the window's k columns once: the row
 //     classes of core:666-687 (edge gap, IUPAC cell -> special; the rest plain) are ORs / ANDs of plane words, and the
 //     code is a GF(2)-linear hash — code bit i is the XOR of the low / high base bits of a fixed subset of the columns —
@@ -17,8 +17,8 @@
 //     the others are transposed (13 x 32 bits -> 32 indices, SWAR) and counted with shared-memory atomics;
 //   * special rows (0.6 % on the workload) are listed and handled at the end on the row view, expansion by expansion,
 //     with the same code function evaluated by popcounts;
-//   * the cluster's blocks then each sum a quarter of the bins over all four histograms through distributed shared
-//     memory and write (sum c, sum c log2 c) partials; the host adds the four partials in rank order (deterministic).
+//   * the cluster's blocks then each sum their slice of the bins over all the cluster's histograms through distributed
+//     shared memory and write (sum c, sum c log2 c) partials; the host adds the partials in rank order (deterministic).
 // Algorithmic bytes: k/2 per (window, sequence) k-mer; real traffic: 4 k plane words per (window, 32 rows)
 // from L2, the column view itself (300 MB) from DRAM about once.
 //
@@ -43,7 +43,7 @@ namespace cg = cooperative_groups;
 #define BS_BITS 13
 #define BS_BINS (1 << BS_BITS)
 #define BS_THREADS 256
-#define BS_CLUSTER 4
+#define BS_CLUSTER 8
 #define BS_DEFER 2048
 
 // per-column code patterns (weight 3, all 27 x {low, high, low ^ high} distinct): a difference in one cell always
@@ -79,11 +79,12 @@ struct BsAcc {
     uint32_t anygap, allgap, anymul, gfirst, glast;
 };
 
-// columns J, J+1, ... k-1 of the window for one word of 32 sequences (q: plane A of column J)
+// columns J, J+1, ... k-1 of the window for word W of 32 sequences (q: plane A of column J, the same for all threads)
 template <int J>
-__device__ __forceinline__ void bs_cols(const uint32_t* __restrict__ q, long long nwords, int k, uint32_t (&H)[16], BsAcc& a) {
+__device__ __forceinline__ void bs_cols(const uint32_t* __restrict__ q, long long nwords, unsigned W, int k, uint32_t (&H)[16],
+                                        BsAcc& a) {
     if (J < k) {  // uniform
-        const uint32_t A = __ldg(q), C = __ldg(q + nwords), G = __ldg(q + 2 * nwords), T = __ldg(q + 3 * nwords);
+        const uint32_t A = __ldg(q + W), C = __ldg(q + nwords + W), G = __ldg(q + 2 * nwords + W), T = __ldg(q + 3 * nwords + W);
         const uint32_t gap = ~(A | C | G | T);
         a.anygap |= gap;
         a.allgap &= gap;
@@ -91,7 +92,7 @@ __device__ __forceinline__ void bs_cols(const uint32_t* __restrict__ q, long lon
         if (J == 0) a.gfirst = gap;
         a.glast = gap;  // the last column walked is column k - 1
         bs_mix<J, 0>(H, C | T, G | T);
-        if constexpr (J + 1 < MPB_MAX_K) bs_cols<J + 1>(q + 4 * nwords, nwords, k, H, a);
+        if constexpr (J + 1 < MPB_MAX_K) bs_cols<J + 1>(q + 4 * nwords, nwords, W, k, H, a);
     }
 }
 
@@ -131,7 +132,7 @@ __device__ __forceinline__ void bs_slow_row(const uint32_t* __restrict__ pl, int
     }
 }
 
-__global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(BS_THREADS)
+__global__ void __cluster_dims__(BS_CLUSTER, 1, 1) __launch_bounds__(BS_THREADS, 4)
 k_prefilter_bs(const uint32_t* __restrict__ colp, long long nwords, const uint8_t* __restrict__ cons,
                const uint32_t* __restrict__ pl, int64_t nsp, int64_t n_seq, const int32_t* __restrict__ lens, int k, int v,
                const int32_t* __restrict__ win_pos, double* __restrict__ part, int* __restrict__ err) {
@@ -170,7 +171,7 @@ k_prefilter_bs(const uint32_t* __restrict__ colp, long long nwords, const uint8_
 #pragma unroll
         for (int i = 0; i < 16; ++i) H[i] = 0;
         BsAcc a = {0u, 0xFFFFFFFFu, 0u, 0u, 0u};
-        bs_cols<0>(col0 + W, nwords, k, H, a);
+        bs_cols<0>(col0, nwords, (unsigned)W, k, H, a);
         const uint32_t special = ((a.gfirst | a.glast) & ~a.allgap) | a.anymul;
         const uint32_t plain = ~special & vm;
         uint32_t match = plain;

@@ -104,8 +104,15 @@ class Msa:
         rstrip = np.array([len(s.rstrip("-")) for s in self.rows], np.int32)
         return lead, rstrip
 
-    def prefilter(self, k, v, win_pos):
-        """coarse 16-bit view (a hash of the whole item) of every counted item (mpb_window_prefilter)"""
+    # per-column code patterns of the bit-sliced prefilter (mpb_prefilter.cu BS_LO / BS_HI)
+    BS_LO = [0x414, 0x1900, 0x32, 0x13, 0xc40, 0xc4, 0x602, 0x1088, 0x4a0, 0xd, 0x1401, 0x409, 0x1a0, 0x248, 0x1204, 0x184,
+             0x100c, 0x1028, 0x1104, 0x1018, 0x58, 0x1006, 0x118, 0x881, 0xc8, 0x482, 0x504]
+    BS_HI = [0x608, 0x62, 0x1110, 0x811, 0x1802, 0xa04, 0x43, 0x320, 0x640, 0x86, 0x1a00, 0x40a, 0x809, 0x222, 0xa40, 0xe0,
+             0x806, 0x29, 0x1300, 0x501, 0x221, 0x841, 0x211, 0x1044, 0x460, 0x484, 0x920]
+
+    def prefilter(self, k, v, win_pos, code="bs"):
+        """coarse view of every counted item (mpb_window_prefilter): code="bs" the 13-bit GF(2)-linear code of the
+        bit-sliced kernel (mpb_prefilter.cu), code="row" the 16-bit multiplicative hash of the row-domain kernel"""
         s0, s1 = np.zeros(len(win_pos)), np.zeros(len(win_pos))
         low = {c: ("A" if i & 1 else "C" if i & 2 else "G" if i & 4 else "T") for i, c in enumerate(CODE_CHARS) if i}
         low["-"] = "A"
@@ -115,11 +122,19 @@ class Msa:
                 w = o.window_kmer(s, int(p), k)
                 items = ["".join(low[ch] for ch in w)] if w.count("-") > v else [e.replace("-", "A") for e in o.expand(w)]
                 for it in items:
-                    lo = sum(1 << j for j, ch in enumerate(it) if ch in "CT")       # pre_code() of mpb200.cu
-                    hi = sum(1 << j for j, ch in enumerate(it) if ch in "GT")
-                    x = (lo ^ ((hi << 7) & 0xFFFFFFFF) ^ (hi >> 9)) & 0xFFFFFFFF
-                    code = ((x * 0x9E3779B1) & 0xFFFFFFFF) >> 16
-                    bins[code] = bins.get(code, 0) + 1
+                    if code == "bs":
+                        c = 0
+                        for j, ch in enumerate(it):
+                            if ch in "CT":
+                                c ^= self.BS_LO[j]
+                            if ch in "GT":
+                                c ^= self.BS_HI[j]
+                    else:
+                        lo = sum(1 << j for j, ch in enumerate(it) if ch in "CT")       # pre_code() of mpb200.cu
+                        hi = sum(1 << j for j, ch in enumerate(it) if ch in "GT")
+                        x = (lo ^ ((hi << 7) & 0xFFFFFFFF) ^ (hi >> 9)) & 0xFFFFFFFF
+                        c = ((x * 0x9E3779B1) & 0xFFFFFFFF) >> 16
+                    bins[c] = bins.get(c, 0) + 1
             cs = np.array(list(bins.values()), float)
             s0[wi], s1[wi] = cs.sum(), (cs * np.log2(cs)).sum()
         return s0, s1

@@ -246,9 +246,11 @@ def test_core_to_pairing_through_bit_vectors(tmp_path, tag, world):
     assert strip(res.stdout) == strip(want["stdout"])
 
 
-def test_prefilter_matches_definition():
-    """mpb_window_prefilter: item counts and sum(c log2 c) of the coarse bins equal the plain-Python definition, and
-    the bound never exceeds the reference's total entropy"""
+@pytest.mark.parametrize("mode", ["bs", "row"])
+def test_prefilter_matches_definition(mode, monkeypatch):
+    """mpb_window_prefilter (bit-sliced cluster kernel / row-domain kernel): item counts and sum(c log2 c) of the coarse
+    bins equal the plain-Python definition, and the bound never exceeds the reference's total entropy"""
+    monkeypatch.setenv("MPB_WINPASS", "row" if mode == "row" else "col")
     from multiprime_b200 import _lib, core
     from tests import fake_device
     from tests.helpers import case_alignment, load_case
@@ -262,7 +264,7 @@ def test_prefilter_matches_definition():
     msa = _lib.Msa(ctx, core.pack4(codes), len(ids), codes.shape[1])
     s0, s1 = msa.prefilter(k, v, pos)
     fmsa = fake_device.Msa(None, core.pack4(codes), len(ids), codes.shape[1])
-    f0, f1 = fmsa.prefilter(k, v, pos)
+    f0, f1 = fmsa.prefilter(k, v, pos, code=mode)
     assert (s0 == f0).all()
     assert np.allclose(s1, f1, rtol=1e-12, atol=1e-9)
     n = len(ids)
