@@ -66,7 +66,6 @@ def test_column_passes_equal_row_passes(n, L, k, v, kw, monkeypatch):
         ent, n_ig = a["ent"], a["stats"]["n_iupac_gap"]
         exact = -((ent[:, 1] - ent[:, 0] * np.log2(n)) + (ent[:, 3] - ent[:, 2] * np.log2(n))) / n
         ok = n_ig == 0                                                           # (those rows are not table entries)
-        assert ok.sum() > 10
         for snap in (a, b):
             bound = (snap["pre"][0] * np.log2(n) - snap["pre"][1]) / n
             assert (bound[ok] <= exact[ok] + 1e-9).all()
