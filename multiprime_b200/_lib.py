@@ -81,6 +81,7 @@ SIGNATURES = {
     "mpb_peer_connect": (C.c_int, [_P, _P]),
     "mpb_peer_cap": (C.c_int64, [_P]),
     "mpb_peer_allreduce": (C.c_int, [_P, _P, C.c_int64]),
+    "mpb_peer_allgather": (C.c_int, [_P, _P, C.c_int64, _P]),
     "mpb_peer_free": (None, [_P]),
     "mpb_primer_props": (C.c_int, [_P, _P, C.c_int, C.c_int32, C.c_double, C.c_double, C.c_int, _P, _P, _P, _P, _P,
                                    _P]),
@@ -685,6 +686,16 @@ class Peer:
 
     def allreduce(self, dev_ptr: int, n: int):
         check(load().mpb_peer_allreduce(self.h, C.c_void_p(dev_ptr), n))
+
+    def allgather_fixed(self, arr):
+        """all-gather of equally shaped int64 / float64 host arrays -> (world,) + shape, or None when the array does not
+        fit the group's slots (the caller then uses its communicator)"""
+        arr = np.ascontiguousarray(arr)
+        if arr.dtype.itemsize != 8 or arr.size < 1 or arr.size > self.cap:
+            return None
+        out = np.empty((self.world,) + arr.shape, arr.dtype)
+        check(load().mpb_peer_allgather(self.h, ptr(arr), arr.size, ptr(out)))
+        return out
 
     def close(self):
         if self.h:

@@ -254,6 +254,8 @@ class NN_degenerate(object):
         if self.comm.world > 1 and getattr(self.comm, "peer_ok", False) and hasattr(backend, "Peer") \
                 and os.environ.get("MPB_PEER", "1") != "0":
             self.peer = backend.Peer.of(self.ctx, self.comm)
+            if hasattr(self.comm, "attach_peer") and os.environ.get("MPB_PEER_HOST", "1") != "0":
+                self.comm.attach_peer(self.peer)        # its small host collectives go through the group as well
         lap("upload")
         self.position_list = self.seq_attribute()
         lap("region")
@@ -735,13 +737,33 @@ class NN_degenerate(object):
                 distinct[sel] = own.match(np.searchsorted(mine, wis[sel]).astype(np.int32), allow[sel])
             distinct = self.comm.allreduce_sum(distinct)
         lap("fin_match")
-        if self.rows_on_rank0_only and self.comm.rank != 0 and not self.sidecars:
+        world, rank = self.comm.world, self.comm.rank
+        if world == 1:
+            tm_avg, gc, flags, deg, ndeg = self._primer_props(sets_arr, k, gc_lo, gc_hi)
+            lap("fin_props")
+            dimer = self._self_dimer(sets_list)                               # core:487-503 for all windows at once
+            lap("fin_dimer")
+        else:
+            # primer properties and the self-dimer test depend on the primer only: every rank takes every world-th primer
+            # and the values are shared (one small collective; float values travel as bit patterns)
+            sel = np.arange(rank, n, world)
+            part = np.zeros((n, 6), np.int64)
+            if len(sel):
+                p_tm, p_gc, p_fl, p_deg, p_ndeg = self._primer_props(sets_arr[sel], k, gc_lo, gc_hi)
+                lap("fin_props")
+                p_dim = self._self_dimer([sets_list[i] for i in sel.tolist()])
+                part[sel, 0] = np.asarray(p_tm, np.float64).view(np.int64)
+                part[sel, 1] = np.asarray(p_gc, np.float64).view(np.int64)
+                part[sel, 2], part[sel, 3], part[sel, 4] = p_fl, p_deg, p_ndeg
+                part[sel, 5] = np.asarray(p_dim, np.int64)
+            lap("fin_dimer")
+            part = self.comm.allreduce_sum(part)
+            tm_avg, gc = part[:, 0].copy().view(np.float64), part[:, 1].copy().view(np.float64)
+            flags, deg, ndeg, dimer = part[:, 2], part[:, 3], part[:, 4], part[:, 5]
+            lap("fin_share")
+        if self.rows_on_rank0_only and rank != 0 and not self.sidecars:
             return []                  # rows are identical on every rank: only rank 0 assembles (and writes) them
-        tm_avg, gc, flags, deg, ndeg = self._primer_props(sets_arr, k, gc_lo, gc_hi)
-        lap("fin_props")
         seqkeys = self.msa.seqkeys(k, pos) if self.sidecars else None
-        dimer = self._self_dimer(sets_list)                                   # core:487-503 for all windows at once
-        lap("fin_dimer")
         lut = np.frombuffer(CODE_CHARS.encode(), dtype=np.uint8)
         trace_str = None
         if res["trace"] is not None:

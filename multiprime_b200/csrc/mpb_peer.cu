@@ -33,11 +33,16 @@
 #define PEER_TIMEOUT_NS 4000000000ull
 #define PEER_MAGIC 0x6d70625f70656572ull
 
+#define PEER_CH1_FLAG 64  // flag words of channel 1 (host-driven gathers); channel 0 (the walk's all-reduce) uses 0..7
+
 struct mpb_peer {
     mpb_ctx* ctx;
     int rank, world;
     int64_t cap;                    // elements per receive slot
-    unsigned long long* local;      // own buffer: flags + [2][world][cap]
+    unsigned long long* local;      // own buffer: flags + channel 0 [2][world][cap] + channel 1 [2][world][cap]
+    unsigned long long* stage;      // [cap] channel 1: the local contribution on its way out
+    int* err1;                      // channel 1 error flags
+    unsigned long long hseq;        // channel 1 rounds done (host-side: a gather never skips)
     unsigned long long* base[MPB_PEER_MAX_WORLD];
     bool opened[MPB_PEER_MAX_WORLD];  // base[p] came from cudaIpcOpenMemHandle
     unsigned long long* seq;        // device: rounds done
@@ -122,7 +127,34 @@ k_peer_allreduce(PeerDev pd, unsigned long long* __restrict__ data, const int* _
     }
 }
 
-static size_t peer_bytes(int world, int64_t cap) { return ((size_t)PEER_FLAG_WORDS + (size_t)2 * world * cap) * 8; }
+static size_t peer_bytes(int world, int64_t cap) { return ((size_t)PEER_FLAG_WORDS + (size_t)4 * world * cap) * 8; }
+
+// channel 1: every rank's vector to every rank (no sum): push, signal, wait — the caller then reads its own receive
+// slots [par][0 .. world)
+__global__ void __launch_bounds__(PEER_THREADS)
+k_peer_gather(PeerDev pd, const unsigned long long* __restrict__ src, long long n, unsigned long long seq,
+              int* __restrict__ err) {
+    const long long par = (long long)(seq & 1ull);
+    const long long ch1 = PEER_FLAG_WORDS + 2ll * pd.world * pd.cap;
+    for (int p = 0; p < pd.world; ++p) {
+        unsigned long long* dst = pd.base[p] + ch1 + (par * pd.world + pd.rank) * pd.cap;
+        for (long long i = threadIdx.x; i < n; i += PEER_THREADS) dst[i] = src[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < pd.world) {
+        st_release_sys(pd.base[threadIdx.x] + PEER_CH1_FLAG + pd.rank, seq);
+        const unsigned long long* mine = pd.base[pd.rank] + PEER_CH1_FLAG + threadIdx.x;
+        const unsigned long long t0 = timer_ns();
+        unsigned spin = 0;
+        while (ld_acquire_sys(mine) < seq) {
+            if ((++spin & 0xFFu) == 0 && timer_ns() - t0 > PEER_TIMEOUT_NS) {
+                atomicOr(err, MPB_ERR_PEER_TIMEOUT);
+                break;
+            }
+        }
+    }
+}
 
 extern "C" int mpb_peer_create(mpb_ctx* ctx, int rank, int world, int64_t cap_elems, mpb_peer** out) {
     if (!ctx || !out) return fail(MPB_EINVAL, "NULL argument");
@@ -138,6 +170,9 @@ extern "C" int mpb_peer_create(mpb_ctx* ctx, int rank, int world, int64_t cap_el
     p->cap = cap_elems;
     cudaError_t e = cudaMalloc(&p->local, peer_bytes(world, cap_elems));
     if (e == cudaSuccess) e = cudaMalloc(&p->seq, 8);
+    if (e == cudaSuccess) e = cudaMalloc(&p->stage, (size_t)cap_elems * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&p->err1, 4);
+    if (e == cudaSuccess) e = cudaMemset(p->err1, 0, 4);
     if (e == cudaSuccess) e = cudaMemset(p->local, 0, PEER_FLAG_WORDS * 8);
     if (e == cudaSuccess) e = cudaMemset(p->seq, 0, 8);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
@@ -238,6 +273,33 @@ extern "C" int mpb_peer_allreduce(mpb_peer* p, int64_t* data_dev, int64_t n) {
     return 0;
 }
 
+// All-gather of n int64 elements per rank through peer memory: src (host or device) -> dst_host[world][n].  One copy
+// in, one single-block kernel (push to every peer, signal, wait), one strided copy out; collective.
+extern "C" int mpb_peer_allgather(mpb_peer* p, const int64_t* src_hd, int64_t n, int64_t* dst_host) {
+    if (!p || !src_hd || !dst_host) return fail(MPB_EINVAL, "NULL argument");
+    if (!p->connected) return fail(MPB_EINVAL, "peer group not connected");
+    if (n < 1 || n > p->cap) return fail(MPB_EINVAL, "n=%lld outside 1..%lld", (long long)n, (long long)p->cap);
+    mpb_ctx* ctx = p->ctx;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(p->stage, src_hd, (size_t)n * 8, cudaMemcpyDefault, ctx->stream));
+    PeerDev pd;
+    for (int r = 0; r < MPB_PEER_MAX_WORLD; ++r) pd.base[r] = r < p->world ? p->base[r] : nullptr;
+    pd.seq = p->seq;
+    pd.cap = p->cap;
+    pd.rank = p->rank;
+    pd.world = p->world;
+    const unsigned long long seq = ++p->hseq;
+    MPB_LAUNCH(ctx, k_peer_gather, 1, PEER_THREADS, 0, pd, p->stage, (long long)n, seq, p->err1);
+    const unsigned long long* recv = p->local + PEER_FLAG_WORDS + 2ll * p->world * p->cap + (long long)(seq & 1ull) * p->world * p->cap;
+    CK(cudaMemcpy2DAsync(dst_host, (size_t)n * 8, recv, (size_t)p->cap * 8, (size_t)n * 8, (size_t)p->world,
+                         cudaMemcpyDeviceToHost, ctx->stream));
+    int flags = 0;
+    CK(cudaMemcpyAsync(&flags, p->err1, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (flags) return fail(MPB_ECUDA, "peer all-gather: a peer did not arrive (flags %d)", flags);
+    return 0;
+}
+
 extern "C" void mpb_peer_free(mpb_peer* p) {
     if (!p) return;
     cudaSetDevice(p->ctx->device);
@@ -246,5 +308,7 @@ extern "C" void mpb_peer_free(mpb_peer* p) {
         if (p->opened[r] && p->base[r]) cudaIpcCloseMemHandle(p->base[r]);
     if (p->local) cudaFree(p->local);
     if (p->seq) cudaFree(p->seq);
+    if (p->stage) cudaFree(p->stage);
+    if (p->err1) cudaFree(p->err1);
     delete p;
 }

@@ -138,21 +138,26 @@ def test_peer_allreduce_kernel():
     def body(rank, comm):
         ctx = _lib.Context(0, torch.cuda.current_stream().cuda_stream)
         peer = _lib.Peer(ctx, comm, cap_elems=4096)
-        got = []
+        got, gathered = [], []
         for i, n in enumerate(rounds):
             t = torch.from_numpy(data[rank][i].astype(np.int64)).cuda()
             torch.cuda.current_stream().synchronize()
             peer.allreduce(t.data_ptr(), n)
             got.append(t.cpu().numpy())
+            gathered.append(peer.allgather_fixed(data[rank][i].astype(np.int64).reshape(1, -1)))   # channel 1
+        assert peer.allgather_fixed(np.zeros(5000, np.int64)) is None                              # too long: caller's job
         comm.barrier()
         peer.close()
-        return got
+        return got, gathered
 
     res = run_shards(world, body, streams=True)
     for i, n in enumerate(rounds):
         want = sum(data[r][i] for r in range(world))
         for r in range(world):
-            assert (res[r][i] == want).all(), (r, i)
+            assert (res[r][0][i] == want).all(), (r, i)
+            assert res[r][1][i].shape == (world, 1, n)
+            for q in range(world):
+                assert (res[r][1][i][q, 0] == data[q][i]).all(), (r, q, i)
 
 
 @pytest.mark.parametrize("name,world", [("synth_iupac", 2), ("c2_k18", 3)])
