@@ -276,8 +276,9 @@ int mpb_peer_connect(mpb_peer* p, const void* handles /* world x MPB_PEER_HANDLE
 int64_t mpb_peer_cap(mpb_peer* p);
 /* in-place sum over the ranks of data_dev[0..n) (device memory); collective: same calls in the same order on all ranks */
 int mpb_peer_allreduce(mpb_peer* p, int64_t* data_dev, int64_t n);
-/* all-gather of n int64 elements per rank: src (host or device) -> dst_host[world][n]; collective, synchronises */
-int mpb_peer_allgather(mpb_peer* p, const int64_t* src_hd, int64_t n, int64_t* dst_host);
+/* the two halves of a round as separate calls — phases 1: push + signal, 2: wait + sum, 3: both — so that one stream can
+ * play every rank of a group in turn (all ranks' phase 1, then all ranks' phase 2) */
+int mpb_peer_allreduce_phases(mpb_peer* p, int64_t* data_dev, int64_t n, int phases);
 void mpb_peer_free(mpb_peer* p);
 /* the walk's rounds all-reduce their counts through `peer` (NULL: back to the caller's own all-reduce between
  * mpb_walk_dev_scan and mpb_walk_dev_advance); fails when a round's vector could exceed the group's capacity */

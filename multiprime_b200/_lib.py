@@ -81,7 +81,7 @@ SIGNATURES = {
     "mpb_peer_connect": (C.c_int, [_P, _P]),
     "mpb_peer_cap": (C.c_int64, [_P]),
     "mpb_peer_allreduce": (C.c_int, [_P, _P, C.c_int64]),
-    "mpb_peer_allgather": (C.c_int, [_P, _P, C.c_int64, _P]),
+    "mpb_peer_allreduce_phases": (C.c_int, [_P, _P, C.c_int64, C.c_int]),
     "mpb_peer_free": (None, [_P]),
     "mpb_primer_props": (C.c_int, [_P, _P, C.c_int, C.c_int32, C.c_double, C.c_double, C.c_int, _P, _P, _P, _P, _P,
                                    _P]),
@@ -659,43 +659,71 @@ PEER_MAX_WORLD = 8
 
 
 class Peer:
-    """mpb_peer_*: this rank's member of a peer-memory group (one rank per GPU, NVLink): the walk's count vector is
-    summed over the ranks by one small kernel per round.  `comm` only carries the 128-byte handles once."""
+    """mpb_peer_*: one rank's member of a peer-memory group (one rank per GPU, NVLink): the walk's count vector is summed
+    over the ranks by one small kernel per round instead of a collective-library call."""
 
-    def __init__(self, ctx: Context, comm, cap_elems: int = 1 << 18):
-        self.ctx, self.rank, self.world, self.cap = ctx, comm.rank, comm.world, int(cap_elems)
+    def __init__(self, ctx: Context, rank: int, world: int, cap_elems: int = 1 << 18):
+        self.ctx, self.rank, self.world, self.cap = ctx, rank, world, int(cap_elems)
         h = C.c_void_p()
-        check(load().mpb_peer_create(ctx.h, comm.rank, comm.world, self.cap, C.byref(h)))
+        check(load().mpb_peer_create(ctx.h, rank, world, self.cap, C.byref(h)))
         self.h = h
-        mine = np.zeros(PEER_HANDLE_BYTES // 8, np.int64)
-        check(load().mpb_peer_handle(self.h, ptr(mine)))
-        handles = np.ascontiguousarray(comm.allgather_fixed(mine))
+
+    def handle(self) -> np.ndarray:
+        out = np.zeros(PEER_HANDLE_BYTES // 8, np.int64)
+        check(load().mpb_peer_handle(self.h, ptr(out)))
+        return out
+
+    def connect(self, handles):
+        handles = np.ascontiguousarray(handles, dtype=np.int64)
+        assert handles.shape == (self.world, PEER_HANDLE_BYTES // 8)
         check(load().mpb_peer_connect(self.h, ptr(handles)))
-        comm.barrier()                       # nobody pushes before every rank has opened every buffer
 
     @classmethod
     def of(cls, ctx: Context, comm, cap_elems: int = 1 << 18):
-        """the group member cached on a (shared) context: opening IPC handles costs milliseconds, once per process"""
+        """The member of this process in the group of `comm` (cached on the context: opening IPC handles costs
+        milliseconds), or None when the group cannot be used — a rank failed to create or open a buffer, or the trial
+        all-reduce did not give the expected sum.  Every step is agreed on by all ranks through `comm`, so either all of
+        them use peer memory or none does (the walk then all-reduces through the communicator)."""
         cache = ctx.__dict__.setdefault("_peers", {})
-        key = (getattr(comm, "peer_key", None), comm.rank, comm.world)     # one group per process group
-        peer = cache.get(key)
-        if peer is None or not peer.h:
-            peer = cls(ctx, comm, cap_elems)
-            cache[key] = peer
+        key = (getattr(comm, "peer_key", None), comm.rank, comm.world)
+        if key in cache:
+            return cache[key]
+        peer, words = None, PEER_HANDLE_BYTES // 8
+        mine = np.zeros(words + 1, np.int64)
+        try:
+            peer = cls(ctx, comm.rank, comm.world, cap_elems)
+            mine[:words] = peer.handle()
+            mine[words] = 1
+        except MpbError:
+            peer = None
+        everyone = comm.allgather_fixed(mine)
+        ok = bool(everyone[:, words].all())
+        if ok:
+            try:
+                peer.connect(everyone[:, :words])
+            except MpbError:
+                ok = False
+        ok = int(comm.allreduce_sum(np.array([1 if ok else 0], np.int64))[0]) == comm.world
+        if ok:                               # (the barrier inside the all-reduce: every rank has opened every buffer)
+            trial = DevBuf(ctx, (8,), np.int64)
+            try:
+                want = np.arange(8, dtype=np.int64) * comm.world + comm.world * (comm.world + 1) // 2
+                check(load().mpb_ctx_memcpy(ctx.h, C.c_void_p(trial.p), ptr(np.arange(8, dtype=np.int64) + comm.rank + 1), 64))
+                peer.allreduce(trial.p, 8)
+                ok = bool((trial.to_host() == want).all())
+            except MpbError:
+                ok = False
+            finally:
+                trial.close()
+            ok = int(comm.allreduce_sum(np.array([1 if ok else 0], np.int64))[0]) == comm.world
+        if not ok and peer is not None:
+            peer.close()
+            peer = None
+        cache[key] = peer
         return peer
 
-    def allreduce(self, dev_ptr: int, n: int):
-        check(load().mpb_peer_allreduce(self.h, C.c_void_p(dev_ptr), n))
-
-    def allgather_fixed(self, arr):
-        """all-gather of equally shaped int64 / float64 host arrays -> (world,) + shape, or None when the array does not
-        fit the group's slots (the caller then uses its communicator)"""
-        arr = np.ascontiguousarray(arr)
-        if arr.dtype.itemsize != 8 or arr.size < 1 or arr.size > self.cap:
-            return None
-        out = np.empty((self.world,) + arr.shape, arr.dtype)
-        check(load().mpb_peer_allgather(self.h, ptr(arr), arr.size, ptr(out)))
-        return out
+    def allreduce(self, dev_ptr: int, n: int, phases: int = 3):
+        check(load().mpb_peer_allreduce_phases(self.h, C.c_void_p(dev_ptr), n, phases))
 
     def close(self):
         if self.h:

@@ -41,24 +41,15 @@ class TorchComm:
                 else torch.device("cpu")
         self.device = device
         self.peer_key = ("torch", id(group) if group is not None else 0)
-        self.peer = None                # _lib.Peer of this group: small host collectives go through NVLink peer memory
-
-    def attach_peer(self, peer):
-        self.peer = peer
 
     def _to(self, arr):
         t = self.torch.from_numpy(np.ascontiguousarray(arr))
         return t.to(self.device) if self.device.type != "cpu" else t.clone()
 
     def allreduce_sum(self, arr):
-        """element-wise sum over ranks of an int64 / float64 array (through the peer group: gathered, then added in rank
-        order — the same result on every rank)"""
+        """element-wise sum over ranks of an int64 / float64 array"""
         arr = np.asarray(arr)
         kind = np.float64 if arr.dtype.kind == "f" else np.int64
-        if self.peer is not None:
-            got = self.peer.allgather_fixed(arr.astype(kind))
-            if got is not None:
-                return got.sum(axis=0).astype(arr.dtype).reshape(arr.shape)
         t = self._to(arr.astype(kind))
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
         return t.cpu().numpy().astype(arr.dtype).reshape(arr.shape)
@@ -89,10 +80,6 @@ class TorchComm:
         """all-gather of equally shaped int64 / float64 arrays -> array of shape (world,) + arr.shape: one collective,
         one copy to the device and one back (allgather_concat pays a size exchange and a copy per rank)"""
         arr = np.ascontiguousarray(arr)
-        if self.peer is not None:
-            got = self.peer.allgather_fixed(arr)
-            if got is not None:
-                return got
         t = self._to(arr.reshape(-1).view(np.int64))
         out = self.torch.empty(self.world * t.numel(), dtype=t.dtype, device=t.device)
         self.dist.all_gather_into_tensor(out, t, group=self.group)

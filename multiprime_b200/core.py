@@ -254,8 +254,6 @@ class NN_degenerate(object):
         if self.comm.world > 1 and getattr(self.comm, "peer_ok", False) and hasattr(backend, "Peer") \
                 and os.environ.get("MPB_PEER", "1") != "0":
             self.peer = backend.Peer.of(self.ctx, self.comm)
-            if hasattr(self.comm, "attach_peer") and os.environ.get("MPB_PEER_HOST", "1") != "0":
-                self.comm.attach_peer(self.peer)        # its small host collectives go through the group as well
         lap("upload")
         self.position_list = self.seq_attribute()
         lap("region")

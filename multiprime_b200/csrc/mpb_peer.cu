@@ -33,16 +33,11 @@
 #define PEER_TIMEOUT_NS 4000000000ull
 #define PEER_MAGIC 0x6d70625f70656572ull
 
-#define PEER_CH1_FLAG 64  // flag words of channel 1 (host-driven gathers); channel 0 (the walk's all-reduce) uses 0..7
-
 struct mpb_peer {
     mpb_ctx* ctx;
     int rank, world;
     int64_t cap;                    // elements per receive slot
-    unsigned long long* local;      // own buffer: flags + channel 0 [2][world][cap] + channel 1 [2][world][cap]
-    unsigned long long* stage;      // [cap] channel 1: the local contribution on its way out
-    int* err1;                      // channel 1 error flags
-    unsigned long long hseq;        // channel 1 rounds done (host-side: a gather never skips)
+    unsigned long long* local;      // own buffer: flags + [2][world][cap]
     unsigned long long* base[MPB_PEER_MAX_WORLD];
     bool opened[MPB_PEER_MAX_WORLD];  // base[p] came from cudaIpcOpenMemHandle
     unsigned long long* seq;        // device: rounds done
@@ -84,7 +79,7 @@ __device__ __forceinline__ unsigned long long timer_ns() {
 #define PEER_THREADS 1024
 __global__ void __launch_bounds__(PEER_THREADS)
 k_peer_allreduce(PeerDev pd, unsigned long long* __restrict__ data, const int* __restrict__ n_items, int mult,
-                 int* __restrict__ err) {
+                 int phases, int* __restrict__ err) {
     __shared__ unsigned long long s_seq;
     const long long n = (long long)n_items[0] * mult;
     if (n <= 0) return;  // the same on every rank
@@ -93,21 +88,26 @@ k_peer_allreduce(PeerDev pd, unsigned long long* __restrict__ data, const int* _
         if (threadIdx.x == 0) atomicOr(err, MPB_ERR_PEER_CAP);
         return;
     }
+    // phases: 1 = push + signal, 2 = wait + sum, 3 = both (a round).  The split form lets ONE stream play all the ranks
+    // of a group in turn (every rank's phase 1, then every rank's phase 2): the single-GPU test of this kernel.
     if (threadIdx.x == 0) {
-        s_seq = pd.seq[0] + 1ull;
+        s_seq = pd.seq[0] + ((phases & 1) ? 1ull : 0ull);
         pd.seq[0] = s_seq;
     }
     __syncthreads();
     const unsigned long long seq = s_seq;
     const long long par = (long long)(seq & 1ull);
-    for (int p = 0; p < pd.world; ++p) {
-        unsigned long long* dst = pd.base[p] + PEER_FLAG_WORDS + (par * pd.world + pd.rank) * pd.cap;
-        for (long long i = threadIdx.x; i < n; i += PEER_THREADS) dst[i] = data[i];
+    if (phases & 1) {
+        for (int p = 0; p < pd.world; ++p) {
+            unsigned long long* dst = pd.base[p] + PEER_FLAG_WORDS + (par * pd.world + pd.rank) * pd.cap;
+            for (long long i = threadIdx.x; i < n; i += PEER_THREADS) dst[i] = data[i];
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x < pd.world) st_release_sys(pd.base[threadIdx.x] + pd.rank, seq);
     }
-    __threadfence_system();
-    __syncthreads();
+    if (!(phases & 2)) return;
     if (threadIdx.x < pd.world) {
-        st_release_sys(pd.base[threadIdx.x] + pd.rank, seq);
         const unsigned long long* mine = pd.base[pd.rank] + threadIdx.x;
         const unsigned long long t0 = timer_ns();
         unsigned spin = 0;
@@ -127,34 +127,7 @@ k_peer_allreduce(PeerDev pd, unsigned long long* __restrict__ data, const int* _
     }
 }
 
-static size_t peer_bytes(int world, int64_t cap) { return ((size_t)PEER_FLAG_WORDS + (size_t)4 * world * cap) * 8; }
-
-// channel 1: every rank's vector to every rank (no sum): push, signal, wait — the caller then reads its own receive
-// slots [par][0 .. world)
-__global__ void __launch_bounds__(PEER_THREADS)
-k_peer_gather(PeerDev pd, const unsigned long long* __restrict__ src, long long n, unsigned long long seq,
-              int* __restrict__ err) {
-    const long long par = (long long)(seq & 1ull);
-    const long long ch1 = PEER_FLAG_WORDS + 2ll * pd.world * pd.cap;
-    for (int p = 0; p < pd.world; ++p) {
-        unsigned long long* dst = pd.base[p] + ch1 + (par * pd.world + pd.rank) * pd.cap;
-        for (long long i = threadIdx.x; i < n; i += PEER_THREADS) dst[i] = src[i];
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x < pd.world) {
-        st_release_sys(pd.base[threadIdx.x] + PEER_CH1_FLAG + pd.rank, seq);
-        const unsigned long long* mine = pd.base[pd.rank] + PEER_CH1_FLAG + threadIdx.x;
-        const unsigned long long t0 = timer_ns();
-        unsigned spin = 0;
-        while (ld_acquire_sys(mine) < seq) {
-            if ((++spin & 0xFFu) == 0 && timer_ns() - t0 > PEER_TIMEOUT_NS) {
-                atomicOr(err, MPB_ERR_PEER_TIMEOUT);
-                break;
-            }
-        }
-    }
-}
+static size_t peer_bytes(int world, int64_t cap) { return ((size_t)PEER_FLAG_WORDS + (size_t)2 * world * cap) * 8; }
 
 extern "C" int mpb_peer_create(mpb_ctx* ctx, int rank, int world, int64_t cap_elems, mpb_peer** out) {
     if (!ctx || !out) return fail(MPB_EINVAL, "NULL argument");
@@ -170,9 +143,6 @@ extern "C" int mpb_peer_create(mpb_ctx* ctx, int rank, int world, int64_t cap_el
     p->cap = cap_elems;
     cudaError_t e = cudaMalloc(&p->local, peer_bytes(world, cap_elems));
     if (e == cudaSuccess) e = cudaMalloc(&p->seq, 8);
-    if (e == cudaSuccess) e = cudaMalloc(&p->stage, (size_t)cap_elems * 8);
-    if (e == cudaSuccess) e = cudaMalloc(&p->err1, 4);
-    if (e == cudaSuccess) e = cudaMemset(p->err1, 0, 4);
     if (e == cudaSuccess) e = cudaMemset(p->local, 0, PEER_FLAG_WORDS * 8);
     if (e == cudaSuccess) e = cudaMemset(p->seq, 0, 8);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
@@ -236,7 +206,7 @@ extern "C" int mpb_peer_connect(mpb_peer* p, const void* handles) {
 
 extern "C" int64_t mpb_peer_cap(mpb_peer* p) { return p ? p->cap : 0; }
 
-int mpb_peer_allreduce_launch(mpb_peer* p, unsigned long long* data_d, const int* n_items_d, int mult, int* err_d) {
+static int peer_launch(mpb_peer* p, unsigned long long* data_d, const int* n_items_d, int mult, int phases, int* err_d) {
     if (!p->connected) return fail(MPB_EINVAL, "peer group not connected");
     mpb_ctx* ctx = p->ctx;
     PeerDev pd;
@@ -245,14 +215,22 @@ int mpb_peer_allreduce_launch(mpb_peer* p, unsigned long long* data_d, const int
     pd.cap = p->cap;
     pd.rank = p->rank;
     pd.world = p->world;
-    MPB_LAUNCH(ctx, k_peer_allreduce, 1, PEER_THREADS, 0, pd, data_d, n_items_d, mult, err_d);
+    MPB_LAUNCH(ctx, k_peer_allreduce, 1, PEER_THREADS, 0, pd, data_d, n_items_d, mult, phases, err_d);
     return 0;
+}
+
+int mpb_peer_allreduce_launch(mpb_peer* p, unsigned long long* data_d, const int* n_items_d, int mult, int* err_d) {
+    return peer_launch(p, data_d, n_items_d, mult, 3, err_d);
 }
 
 // Stand-alone form: sum over the ranks of data[0 .. n) (int64, device memory, n <= capacity), in place, on the
 // context's stream.  Every rank of the group must make the same calls in the same order.
-extern "C" int mpb_peer_allreduce(mpb_peer* p, int64_t* data_dev, int64_t n) {
+extern "C" int mpb_peer_allreduce(mpb_peer* p, int64_t* data_dev, int64_t n) { return mpb_peer_allreduce_phases(p, data_dev, n, 3); }
+
+// phases 1 (push + signal) and 2 (wait + sum) of a round as separate calls: see k_peer_allreduce
+extern "C" int mpb_peer_allreduce_phases(mpb_peer* p, int64_t* data_dev, int64_t n, int phases) {
     if (!p || !data_dev) return fail(MPB_EINVAL, "NULL argument");
+    if (phases < 1 || phases > 3) return fail(MPB_EINVAL, "phases");
     if (n < 1 || n > p->cap) return fail(MPB_EINVAL, "n=%lld outside 1..%lld", (long long)n, (long long)p->cap);
     mpb_ctx* ctx = p->ctx;
     CK(cudaSetDevice(ctx->device));
@@ -260,7 +238,7 @@ extern "C" int mpb_peer_allreduce(mpb_peer* p, int64_t* data_dev, int64_t n) {
     CK(cudaMallocAsync(&scratch, 8, ctx->stream));
     const int init[2] = {(int)n, 0};
     CK(cudaMemcpyAsync(scratch, init, 8, cudaMemcpyHostToDevice, ctx->stream));
-    int rc = mpb_peer_allreduce_launch(p, (unsigned long long*)data_dev, scratch, 1, scratch + 1);
+    int rc = peer_launch(p, (unsigned long long*)data_dev, scratch, 1, phases, scratch + 1);
     int got[2] = {0, 0};
     if (!rc) {
         CK(cudaMemcpyAsync(got, scratch, 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -273,33 +251,6 @@ extern "C" int mpb_peer_allreduce(mpb_peer* p, int64_t* data_dev, int64_t n) {
     return 0;
 }
 
-// All-gather of n int64 elements per rank through peer memory: src (host or device) -> dst_host[world][n].  One copy
-// in, one single-block kernel (push to every peer, signal, wait), one strided copy out; collective.
-extern "C" int mpb_peer_allgather(mpb_peer* p, const int64_t* src_hd, int64_t n, int64_t* dst_host) {
-    if (!p || !src_hd || !dst_host) return fail(MPB_EINVAL, "NULL argument");
-    if (!p->connected) return fail(MPB_EINVAL, "peer group not connected");
-    if (n < 1 || n > p->cap) return fail(MPB_EINVAL, "n=%lld outside 1..%lld", (long long)n, (long long)p->cap);
-    mpb_ctx* ctx = p->ctx;
-    CK(cudaSetDevice(ctx->device));
-    CK(cudaMemcpyAsync(p->stage, src_hd, (size_t)n * 8, cudaMemcpyDefault, ctx->stream));
-    PeerDev pd;
-    for (int r = 0; r < MPB_PEER_MAX_WORLD; ++r) pd.base[r] = r < p->world ? p->base[r] : nullptr;
-    pd.seq = p->seq;
-    pd.cap = p->cap;
-    pd.rank = p->rank;
-    pd.world = p->world;
-    const unsigned long long seq = ++p->hseq;
-    MPB_LAUNCH(ctx, k_peer_gather, 1, PEER_THREADS, 0, pd, p->stage, (long long)n, seq, p->err1);
-    const unsigned long long* recv = p->local + PEER_FLAG_WORDS + 2ll * p->world * p->cap + (long long)(seq & 1ull) * p->world * p->cap;
-    CK(cudaMemcpy2DAsync(dst_host, (size_t)n * 8, recv, (size_t)p->cap * 8, (size_t)n * 8, (size_t)p->world,
-                         cudaMemcpyDeviceToHost, ctx->stream));
-    int flags = 0;
-    CK(cudaMemcpyAsync(&flags, p->err1, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    if (flags) return fail(MPB_ECUDA, "peer all-gather: a peer did not arrive (flags %d)", flags);
-    return 0;
-}
-
 extern "C" void mpb_peer_free(mpb_peer* p) {
     if (!p) return;
     cudaSetDevice(p->ctx->device);
@@ -308,7 +259,5 @@ extern "C" void mpb_peer_free(mpb_peer* p) {
         if (p->opened[r] && p->base[r]) cudaIpcCloseMemHandle(p->base[r]);
     if (p->local) cudaFree(p->local);
     if (p->seq) cudaFree(p->seq);
-    if (p->stage) cudaFree(p->stage);
-    if (p->err1) cudaFree(p->err1);
     delete p;
 }

@@ -3,10 +3,10 @@
 TEST INFRASTRUCTURE ONLY.  It implements the interface of multiprime_b200.comm.TorchComm with `on_gpu = True`, so a
 single-GPU box exercises the DEVICE branches of the sharded path — Hist.export_dev -> all-to-all of device tensors ->
 mpb_hist_merge_segments from device pointers, and the in-place all-reduce of the walk's device count vector — that
-otherwise only run under NCCL with two or more GPUs.  By default all shards use the legacy default stream, so device
-work is ordered by issue order and the host side by barriers.  With `streams=True` every shard works on a stream of its
-own (the device collectives synchronise it around every exchange) and `peer_ok` is set: the walk then sums its counts
-through the peer-memory kernel (mpb_peer_*), the shards' single-block kernels waiting for each other on ONE GPU."""
+otherwise only run under NCCL with two or more GPUs.  All shards use the legacy default stream, so device work is ordered
+by issue order and the host side by barriers.  (The peer-memory all-reduce is NOT exercised here: kernels of several
+shards that wait for each other on one GPU can be serialised by the hardware queues and never finish; its kernel is
+tested with the two phases of a round played in turn on one stream, and end to end by the two-GPU NCCL tests.)"""
 from __future__ import annotations
 
 import threading
@@ -28,21 +28,12 @@ class _Shared:
 class ThreadComm:
     on_gpu = True
 
-    def __init__(self, shared: _Shared, rank: int, device, own_stream: bool = False):
+    peer_ok = False
+
+    def __init__(self, shared: _Shared, rank: int, device):
         import torch
         self.torch = torch
         self.sh, self.rank, self.world, self.device = shared, rank, shared.world, device
-        self.own_stream = own_stream
-        self.peer_ok = own_stream            # peer kernels of two shards on ONE stream would wait for each other forever
-        self.peer_key = ("thread", shared.serial)
-        self.peer = None
-
-    def attach_peer(self, peer):
-        self.peer = peer
-
-    def _sync(self):
-        if self.own_stream:
-            self.torch.cuda.current_stream().synchronize()
 
     # -- plumbing -----------------------------------------------------------------------------------------
     def _exchange(self, obj):
@@ -59,11 +50,6 @@ class ThreadComm:
     # -- host collectives -----------------------------------------------------------------------------------
     def allreduce_sum(self, arr):
         arr = np.asarray(arr)
-        if self.peer is not None:
-            kind = np.float64 if arr.dtype.kind == "f" else np.int64
-            got = self.peer.allgather_fixed(arr.astype(kind))
-            if got is not None:
-                return got.sum(axis=0).astype(arr.dtype).reshape(arr.shape)
         parts = self._exchange(arr.copy())
         return np.sum(np.stack(parts), axis=0).astype(arr.dtype).reshape(arr.shape)
 
@@ -75,10 +61,6 @@ class ThreadComm:
         return self._exchange(obj)
 
     def allgather_fixed(self, arr):
-        if self.peer is not None:
-            got = self.peer.allgather_fixed(arr)
-            if got is not None:
-                return got
         return np.stack(self._exchange(np.ascontiguousarray(arr).copy()))
 
     def alltoall(self, arr, send_counts, recv_counts):
@@ -98,14 +80,12 @@ class ThreadComm:
         return self.torch.empty(max(1, n), dtype=tdt, device=self.device)
 
     def alltoall_dev(self, t, send_counts, recv_counts):
-        self._sync()
         parts = self._exchange_keep((t, np.asarray(send_counts)))
         out = []
         for a, sc in parts:
             off = np.concatenate([[0], np.cumsum(sc)])
             out.append(a[int(off[self.rank]):int(off[self.rank + 1])])
         res = self.torch.cat(out) if out else t[:0]
-        self._sync()
         self.sh.barrier.wait()                    # nobody frees a tensor another shard is still reading
         assert [len(o) for o in out] == [int(c) for c in recv_counts]
         if res.numel() == 0:
@@ -118,15 +98,12 @@ class ThreadComm:
         return list(self.sh.slots)
 
     def allreduce_dev_inplace(self, t):
-        self._sync()
         parts = self._exchange_keep(t)
         total = parts[0].clone()
         for p in parts[1:]:
             total += p
-        self._sync()
         self.sh.barrier.wait()                    # every shard has its sum before anybody overwrites an input
         t.copy_(total)
-        self._sync()
         self.sh.barrier.wait()
 
     def wrap_dev(self, ptr: int, n: int):
@@ -135,21 +112,15 @@ class ThreadComm:
         return self.torch.as_tensor(_Raw(), device=self.device)
 
 
-def run_shards(world: int, fn, streams: bool = False):
-    """run fn(rank, comm) on `world` threads; returns the results in rank order (re-raises the first failure).
-    streams: every shard inside its own torch stream (fn reads it with torch.cuda.current_stream())"""
+def run_shards(world: int, fn):
+    """run fn(rank, comm) on `world` threads; returns the results in rank order (re-raises the first failure)"""
     import torch
     shared = _Shared(world)
     out, errs = [None] * world, []
 
     def body(rank):
         try:
-            if streams:
-                with torch.cuda.stream(torch.cuda.Stream(device=0)):
-                    out[rank] = fn(rank, ThreadComm(shared, rank, torch.device("cuda", 0), own_stream=True))
-                    torch.cuda.current_stream().synchronize()
-            else:
-                out[rank] = fn(rank, ThreadComm(shared, rank, torch.device("cuda", 0)))
+            out[rank] = fn(rank, ThreadComm(shared, rank, torch.device("cuda", 0)))
         except BaseException as exc:              # a dead shard would leave the others at a barrier
             errs.append(exc)
             shared.barrier.abort()

@@ -125,58 +125,38 @@ def test_device_collectives_loopback(name, world):
 
 
 def test_peer_allreduce_kernel():
-    """mpb_peer_allreduce on its own: three shards on threads (one stream each), a few rounds of different lengths, the
-    sums compared with numpy; the sequence numbers and slot parities carry over from round to round"""
+    """k_peer_allreduce on one GPU: four group members on ONE stream, the two phases of every round played in turn (all
+    ranks push and signal, then all ranks wait and sum) — rounds of different lengths, the sequence numbers and slot
+    parities carrying over from round to round, the sums compared with numpy.  (Across processes the same kernel runs
+    both phases at once: test_two_ranks_nccl.)"""
     import numpy as np
-    import torch
     from multiprime_b200 import _lib
-    from tests.loopback_comm import run_shards
-    world, rounds = 3, [1, 5, 1000, 4096, 7, 4096, 33]
+    world, cap, rounds = 4, 4096, [1, 5, 1000, 4096, 7, 4096, 33]
     rng = np.random.default_rng(5)
-    data = [[rng.integers(0, 1 << 40, n) for n in rounds] for _ in range(world)]
-
-    def body(rank, comm):
-        ctx = _lib.Context(0, torch.cuda.current_stream().cuda_stream)
-        peer = _lib.Peer(ctx, comm, cap_elems=4096)
-        got, gathered = [], []
-        for i, n in enumerate(rounds):
-            t = torch.from_numpy(data[rank][i].astype(np.int64)).cuda()
-            torch.cuda.current_stream().synchronize()
-            peer.allreduce(t.data_ptr(), n)
-            got.append(t.cpu().numpy())
-            gathered.append(peer.allgather_fixed(data[rank][i].astype(np.int64).reshape(1, -1)))   # channel 1
-        assert peer.allgather_fixed(np.zeros(5000, np.int64)) is None                              # too long: caller's job
-        comm.barrier()
-        peer.close()
-        return got, gathered
-
-    res = run_shards(world, body, streams=True)
-    for i, n in enumerate(rounds):
-        want = sum(data[r][i] for r in range(world))
+    ctx = _lib.Context(0)
+    peers = [_lib.Peer(ctx, r, world, cap) for r in range(world)]
+    handles = np.stack([p.handle() for p in peers])
+    for p in peers:
+        p.connect(handles)
+    bufs = [_lib.DevBuf(ctx, (cap,), np.int64) for _ in range(world)]
+    for n in rounds:
+        data = [rng.integers(0, 1 << 40, n).astype(np.int64) for _ in range(world)]
         for r in range(world):
-            assert (res[r][0][i] == want).all(), (r, i)
-            assert res[r][1][i].shape == (world, 1, n)
-            for q in range(world):
-                assert (res[r][1][i][q, 0] == data[q][i]).all(), (r, q, i)
-
-
-@pytest.mark.parametrize("name,world", [("synth_iupac", 2), ("c2_k18", 3)])
-def test_walk_over_peer_memory_loopback(name, world):
-    """the sharded walk with the peer-memory all-reduce in its kernel chain (what NCCL runs use), shards on threads"""
-    import torch
-    from tests.loopback_comm import run_shards
-
-    def body(rank, comm):
-        assert comm.peer_ok
-        return _shard_rows(name, rank, world, comm, device=0, stream=torch.cuda.current_stream().cuda_stream,
-                           _expect_peer=True)
-
-    res = run_shards(world, body, streams=True)
-    case = load_case(name)
-    for rank, (start, stop, bad, n_acc) in enumerate(res):
-        assert (start, stop) == (case["start"], case["stop"])
-        assert not bad, (rank, bad[:3])
-        assert n_acc > 0
+            _lib.check(_lib.load().mpb_ctx_memcpy(ctx.h, _lib.C.c_void_p(bufs[r].p), _lib.ptr(data[r]), n * 8))
+        for r in range(world):
+            peers[r].allreduce(bufs[r].p, n, phases=1)
+        for r in range(world):
+            peers[r].allreduce(bufs[r].p, n, phases=2)
+        want = sum(data)
+        for r in range(world):
+            assert (bufs[r].to_host()[:n] == want).all(), (r, n)
+    with pytest.raises(_lib.MpbError):
+        peers[0].allreduce(bufs[0].p, cap + 1)
+    for b in bufs:
+        b.close()
+    for p in peers:
+        p.close()
+    ctx.close()
 
 
 def _nccl_worker(rank, world, port, name, q):
