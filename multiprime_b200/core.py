@@ -337,6 +337,9 @@ class NN_degenerate(object):
         cache = getattr(hist, "_iupac_groups", None)
         if cache is None:
             cache = hist._iupac_groups = self._group_exception_records(self._exception_records(hist))
+            ws = [w for w, groups in cache.items() for _ in groups]
+            cs = [c for groups in cache.values() for _, c in groups]
+            hist._iupac_sums = (np.array(ws, np.int64), np.array(cs, np.int64))
         return cache.get(wi, [])
 
     def _entropy_exact(self, table, ti, wi, n_unique, hist=None):
@@ -655,11 +658,13 @@ class NN_degenerate(object):
         thr = self.entropy_threshold
         comm = self.comm
         ent = st["ent"].astype(np.float64).copy()
-        with_iupac = [] if st.get("ent_complete") else np.nonzero(alive & (st["n_iupac_gap"] > 0))[0].tolist()
-        for wi in with_iupac:                                  # gap rows holding IUPAC cells
-            for _, c in self._iupac_gap_groups(hist, wi):
-                ent[wi, 2] += c
-                ent[wi, 3] += c * math.log2(c)
+        if not st.get("ent_complete") and (alive & (st["n_iupac_gap"] > 0)).any():
+            self._iupac_gap_groups(hist, -1)                   # gap rows holding IUPAC cells: fills the cache
+            gw, gc_ = hist._iupac_sums                         # (window, count) of every group of equal raw k-mers
+            if len(gw):
+                gc_f = gc_.astype(np.float64)
+                ent[:, 2] += np.bincount(gw, weights=gc_f, minlength=len(ent))
+                ent[:, 3] += np.bincount(gw, weights=gc_f * np.log2(gc_f), minlength=len(ent))
         cover_number = (N - st["gap_n"]).astype(np.float64)
         with np.errstate(divide="ignore", invalid="ignore"):
             c_raw = -(ent[:, 1] - ent[:, 0] * np.log2(cover_number)) / cover_number

@@ -22,6 +22,7 @@
 #include "mpb_host.h"
 #include "mpb_device.cuh"
 #include "mpb_cscan.h"
+#include "mpb_cscan_plan.cuh"
 
 #define fail mpb_fail
 #define CK MPB_CK
@@ -40,81 +41,7 @@ __global__ void k_cscan_plan(const mpb_cand* __restrict__ cands, const int* __re
                              int zero_counts, int* __restrict__ err) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= *n_cand_ptr) return;
-    const mpb_cand cd = cands[c];
-    uint32_t* P = plans + (size_t)c * CSCAN_PLAN_WORDS;
-    if (zero_counts)
-        for (int i = 0; i < 4; ++i) counts[(size_t)c * 4 + i] = 0;
-    if (cd.win < 0 || cd.win >= nw) {
-        atomicOr(err, MPB_ERR_BAD_CAND);
-        P[0] = P[1] = P[2] = P[3] = 0;
-        P[4] = CSCAN_NONE;
-        P[5] = 0;
-        return;
-    }
-    const uint32_t p = (uint32_t)win_pos[cd.win];
-    int n1 = 0;
-    uint32_t simple[MPB_MAX_K + 2];
-    uint32_t* deg = P + 8 + 4 * ((MPB_MAX_K + 2) / 3);
-    int nd = 0;
-    for (int i = 0; i < k; ++i) {
-        const uint32_t set = ((cd.allow[0] >> i) & 1u) | (((cd.allow[1] >> i) & 1u) << 1) | (((cd.allow[2] >> i) & 1u) << 2) |
-                             (((cd.allow[3] >> i) & 1u) << 3);
-        const int nb = __popc(set);
-        if (nb == 1) {
-            simple[n1++] = (p + i) * 4 + (__ffs(set) - 1);
-        } else if (nb == 0) {
-            // no base allowed: every row mismatches here — the all-zeros row never matches
-            simple[n1++] = ones_row + 1;
-        } else {
-            uint32_t s = set;
-            while (s) {
-                const int b = __ffs(s) - 1;
-                s &= s - 1;
-                deg[nd++] = ((p + i) * 4 + b) | (s ? 0u : 0x80000000u);
-            }
-        }
-    }
-    const int ntri = (n1 + 2) / 3;
-    for (int i = n1; i < ntri * 3; ++i) simple[i] = ones_row;
-    for (int t = 0; t < ntri; ++t) {
-        P[8 + t * 4 + 0] = simple[t * 3 + 0];
-        P[8 + t * 4 + 1] = simple[t * 3 + 1];
-        P[8 + t * 4 + 2] = simple[t * 3 + 2];
-        P[8 + t * 4 + 3] = 0;
-    }
-    // the degenerate list was written behind the widest possible tri region; move it right behind the actual one
-    uint32_t* dst = P + 8 + 4 * ntri;
-    for (int i = 0; i < nd; ++i) dst[i] = deg[i];
-    int off = 8 + 4 * ntri + nd;
-    int ns[2];
-    for (int side = 0; side < 2; ++side) {
-        const uint32_t sm = side == 0 ? fmask : rmask;
-        int n = 0;
-        for (int i = 0; i < k; ++i) {
-            if (!((sm >> i) & 1u)) continue;
-            uint32_t set = ((cd.allow[0] >> i) & 1u) | (((cd.allow[1] >> i) & 1u) << 1) | (((cd.allow[2] >> i) & 1u) << 2) |
-                           (((cd.allow[3] >> i) & 1u) << 3);
-            if (set == 0) {
-                P[off + n++] = (ones_row + 1) | 0x80000000u;
-                continue;
-            }
-            while (set) {
-                const int b = __ffs(set) - 1;
-                set &= set - 1;
-                P[off + n++] = ((p + i) * 4 + b) | (set ? 0u : 0x80000000u);
-            }
-        }
-        ns[side] = n;
-        off += n;
-    }
-    P[0] = (uint32_t)ntri;
-    P[1] = (uint32_t)nd;
-    P[2] = (uint32_t)ns[0];
-    P[3] = (uint32_t)ns[1];
-    P[4] = cd.trial >= 0 ? (p + (uint32_t)(cd.trial & 255)) * 4 + (uint32_t)((cd.trial >> 8) & 3) : CSCAN_NONE;
-    P[5] = (uint32_t)cd.win;
-    P[6] = (uint32_t)(8 + 4 * ntri);
-    P[7] = (uint32_t)(8 + 4 * ntri + nd);
+    cscan_plan_one(c, cands, win_pos, nw, k, fmask, rmask, ones_row, plans, counts, zero_counts, err);
 }
 
 // ---- the column kernel ----------------------------------------------------------------------------------------------
@@ -388,14 +315,15 @@ k_cscan_special(const mpb_cand* __restrict__ cands, const int* __restrict__ n_ca
 // ---- launch helper shared with the device walk ------------------------------------------------------------------------
 int mpb_cscan_launch(mpb_hist* h, uint32_t fmask, uint32_t rmask, const mpb_cand* cands_d, const int* n_cand_d,
                      int max_cands, uint32_t* plans_d, unsigned long long* counts_d, int zero_counts,
-                     const int32_t* bits_slot_d, uint32_t* bits_d) {
+                     const int32_t* bits_slot_d, uint32_t* bits_d, int plans_ready) {
     mpb_msa* m = h->msa;
     mpb_ctx* ctx = m->ctx;
     if (h->v > 15) return fail(MPB_EINVAL, "the column scan supports variation <= 15 (got %d)", h->v);
     if (!h->spec_bits || !h->spec_win) return fail(MPB_EINVAL, "this mpb_hist was not built from the alignment (no row classes)");
     if (max_cands < 1) return 0;
-    LAUNCH(ctx, k_cscan_plan, (unsigned)((max_cands + 127) / 128), 128, 0, cands_d, n_cand_d, h->win_pos, h->nw, h->k, fmask,
-           rmask, MPB_COLP_ONES(m), plans_d, counts_d, zero_counts, m->err);
+    if (!plans_ready)
+        LAUNCH(ctx, k_cscan_plan, (unsigned)((max_cands + 127) / 128), 128, 0, cands_d, n_cand_d, h->win_pos, h->nw, h->k, fmask,
+               rmask, MPB_COLP_ONES(m), plans_d, counts_d, zero_counts, m->err);
     const long long per_block = (long long)CSCAN_THREADS * CSCAN_WPT;
     const unsigned gx = (unsigned)((m->nwords + per_block - 1) / per_block);
     unsigned gy = (unsigned)(((long long)ctx->sm_count * 8 + gx - 1) / gx);
@@ -457,7 +385,7 @@ extern "C" int mpb_cscan(mpb_hist* h, uint32_t fmask, uint32_t rmask, const mpb_
     ctx->pending_units = 0;
     ctx->extra_units["k_cscan"] += (double)nc * (double)m->n_seq;
     int rc = mpb_cscan_launch(h, fmask, rmask, ca.dev<mpb_cand>(), n_d, n32, plans, oc.dev<unsigned long long>(), 1,
-                              bits_slot ? bs.dev<int32_t>() : nullptr, ob.dev<uint32_t>());
+                              bits_slot ? bs.dev<int32_t>() : nullptr, ob.dev<uint32_t>(), 0);
     CK(cudaFreeAsync(plans, ctx->stream));
     CK(cudaFreeAsync(n_d, ctx->stream));
     if (rc) return rc;

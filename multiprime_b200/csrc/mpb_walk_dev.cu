@@ -22,6 +22,7 @@
 #include "mpb200.h"
 #include "mpb_host.h"
 #include "mpb_cscan.h"
+#include "mpb_cscan_plan.cuh"
 #include "mpb_peer.h"
 #include "mpb_walk_core.h"
 
@@ -47,6 +48,7 @@ struct mpb_walk_dev {
     unsigned long long* totals;  // [2] rounds with candidates, candidates scanned
     int* live_host;         // pinned mirror of live_dev
     int* err;               // track error flags (OR)
+    bool fused;             // rounds go through k_walk_round (advance + compact + plans in one block)
     mpb_peer* peer;         // sharded run: the scan is followed by the peer-memory all-reduce of counts
 };
 
@@ -64,12 +66,11 @@ __global__ void k_walk_seed(int n_win, int k, const int32_t* __restrict__ win_id
 
 // one thread per track slot: take the counts of the track's candidates of the previous round, advance, and stage the
 // next candidates in the track's own region stage[s * (k - 1) ..] (n_emit[s] of them).
-__global__ void k_walk_advance(int n_win, int k, int dnum, int degeneracy, int round, mpb_track* __restrict__ tracks,
-                               const int32_t* __restrict__ ntracks, const int64_t* __restrict__ cover,
-                               const unsigned long long* __restrict__ counts, mpb_cand* __restrict__ stage,
-                               int32_t* __restrict__ n_emit, uint8_t* __restrict__ trace, int* __restrict__ err) {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= 2 * n_win) return;
+__device__ __forceinline__ void walk_advance_slot(int s, int n_win, int k, int dnum, int degeneracy, int round,
+                                                  mpb_track* __restrict__ tracks, const int32_t* __restrict__ ntracks,
+                                                  const int64_t* __restrict__ cover, const unsigned long long* __restrict__ counts,
+                                                  mpb_cand* __restrict__ stage, int32_t* __restrict__ n_emit,
+                                                  uint8_t* __restrict__ trace, int* __restrict__ err) {
     int n = 0;
     if ((s & 1) < ntracks[s >> 1]) {
         mpb_track& t = tracks[s];
@@ -84,16 +85,23 @@ __global__ void k_walk_advance(int n_win, int k, int dnum, int degeneracy, int r
     n_emit[s] = n;
 }
 
+__global__ void k_walk_advance(int n_win, int k, int dnum, int degeneracy, int round, mpb_track* __restrict__ tracks,
+                               const int32_t* __restrict__ ntracks, const int64_t* __restrict__ cover,
+                               const unsigned long long* __restrict__ counts, mpb_cand* __restrict__ stage,
+                               int32_t* __restrict__ n_emit, uint8_t* __restrict__ trace, int* __restrict__ err) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= 2 * n_win) return;
+    walk_advance_slot(s, n_win, k, dnum, degeneracy, round, tracks, ntracks, cover, counts, stage, n_emit, trace, err);
+}
+
 // ONE block: exclusive prefix sum of n_emit over the track slots -> every track's first candidate, candidates copied to
 // their compact positions.  The slot order is the track order, so the candidate list is identical on every rank of a
 // sequence-sharded run (the count vectors are summed element by element) and from run to run.
 #define COMPACT_THREADS 1024
-__global__ void __launch_bounds__(COMPACT_THREADS)
-k_walk_compact(int n_slots, int k, int round, mpb_track* __restrict__ tracks, const mpb_cand* __restrict__ stage,
-               const int32_t* __restrict__ n_emit, mpb_cand* __restrict__ cands, int* __restrict__ n_cand,
-               int* __restrict__ live, unsigned long long* __restrict__ totals) {
-    __shared__ int s_warp[COMPACT_THREADS / 32];
-    __shared__ int s_live[COMPACT_THREADS / 32];
+__device__ __forceinline__ int walk_compact_block(int n_slots, int k, int round, mpb_track* __restrict__ tracks,
+                                                  const mpb_cand* __restrict__ stage, const int32_t* __restrict__ n_emit,
+                                                  mpb_cand* __restrict__ cands, int* __restrict__ n_cand, int* __restrict__ live,
+                                                  unsigned long long* __restrict__ totals, int* s_warp, int* s_live) {
     const int per = (n_slots + COMPACT_THREADS - 1) / COMPACT_THREADS;
     const int lo = threadIdx.x * per, hi = min(n_slots, lo + per);
     int sum = 0, alive = 0;
@@ -132,8 +140,8 @@ k_walk_compact(int n_slots, int k, int round, mpb_track* __restrict__ tracks, co
             base += n;
         }
     }
+    const int total = s_warp[COMPACT_THREADS / 32 - 1];
     if (threadIdx.x == 0) {
-        const int total = s_warp[COMPACT_THREADS / 32 - 1];
         n_cand[0] = total;
         live[round] = s_live[0];
         if (total > 0) {
@@ -141,6 +149,38 @@ k_walk_compact(int n_slots, int k, int round, mpb_track* __restrict__ tracks, co
             totals[1] += (unsigned long long)total;
         }
     }
+    return total;
+}
+
+__global__ void __launch_bounds__(COMPACT_THREADS)
+k_walk_compact(int n_slots, int k, int round, mpb_track* __restrict__ tracks, const mpb_cand* __restrict__ stage,
+               const int32_t* __restrict__ n_emit, mpb_cand* __restrict__ cands, int* __restrict__ n_cand,
+               int* __restrict__ live, unsigned long long* __restrict__ totals) {
+    __shared__ int s_warp[COMPACT_THREADS / 32];
+    __shared__ int s_live[COMPACT_THREADS / 32];
+    walk_compact_block(n_slots, k, round, tracks, stage, n_emit, cands, n_cand, live, totals, s_warp, s_live);
+}
+
+// A whole round's bookkeeping in ONE block (batches of up to WALK_FUSED_MAX windows): advance every track, compact the
+// staged candidates in track order, build the scan plans of the new candidates and clear their counters — three dependent
+// launches of a few hundred threads each otherwise, a dozen times per window batch.
+#define WALK_FUSED_MAX 2048
+__global__ void __launch_bounds__(COMPACT_THREADS)
+k_walk_round(int n_win, int k, int dnum, int degeneracy, int round, mpb_track* __restrict__ tracks,
+             const int32_t* __restrict__ ntracks, const int64_t* __restrict__ cover, unsigned long long* __restrict__ counts,
+             mpb_cand* __restrict__ stage, int32_t* __restrict__ n_emit, uint8_t* __restrict__ trace, mpb_cand* __restrict__ cands,
+             int* __restrict__ n_cand, int* __restrict__ live, unsigned long long* __restrict__ totals,
+             const int32_t* __restrict__ win_pos, int nw, uint32_t fmask, uint32_t rmask, uint32_t ones_row,
+             uint32_t* __restrict__ plans, int* __restrict__ err, int* __restrict__ scan_err) {
+    __shared__ int s_warp[COMPACT_THREADS / 32];
+    __shared__ int s_live[COMPACT_THREADS / 32];
+    for (int s = threadIdx.x; s < 2 * n_win; s += COMPACT_THREADS)
+        walk_advance_slot(s, n_win, k, dnum, degeneracy, round, tracks, ntracks, cover, counts, stage, n_emit, trace, err);
+    __syncthreads();  // (orders the block's global writes: n_emit, stage, tracks)
+    const int total = walk_compact_block(2 * n_win, k, round, tracks, stage, n_emit, cands, n_cand, live, totals, s_warp, s_live);
+    __syncthreads();
+    for (int c = threadIdx.x; c < total; c += COMPACT_THREADS)
+        cscan_plan_one(c, cands, win_pos, nw, k, fmask, rmask, ones_row, plans, counts, 1, scan_err);
 }
 
 extern "C" int mpb_walk_dev_begin(mpb_hist* h, int dnum, int degeneracy, uint32_t fmask, uint32_t rmask, int32_t n_win,
@@ -166,6 +206,7 @@ extern "C" int mpb_walk_dev_begin(mpb_hist* h, int dnum, int degeneracy, uint32_
     w->rmask = rmask;
     w->max_cands = 2 * n_win * (k - 1);
     w->max_rounds = MPB_WALK_MAX_ROUNDS;
+    w->fused = n_win <= WALK_FUSED_MAX;
     cudaError_t e = cudaMallocAsync(&w->tracks, (size_t)2 * n_win * sizeof(mpb_track), ctx->stream);
     if (e == cudaSuccess) e = cudaMallocAsync(&w->ntracks, (size_t)n_win * 4, ctx->stream);
     if (e == cudaSuccess) e = cudaMallocAsync(&w->cover, (size_t)n_win * 8, ctx->stream);
@@ -212,10 +253,17 @@ extern "C" int mpb_walk_dev_advance(mpb_walk_dev* w) {
     mpb_ctx* ctx = w->h->msa->ctx;
     CK(cudaSetDevice(ctx->device));
     const int r = w->rounds_enqueued;
-    LAUNCH(ctx, k_walk_advance, (unsigned)((2 * w->n_win + 63) / 64), 64, 0, w->n_win, w->k, w->dnum, w->degeneracy, r,
-           w->tracks, w->ntracks, w->cover, w->counts, w->stage, w->n_emit, w->trace, w->err);
-    LAUNCH(ctx, k_walk_compact, 1, COMPACT_THREADS, 0, 2 * w->n_win, w->k, r, w->tracks, w->stage, w->n_emit, w->cands,
-           w->n_cand, w->live_dev, w->totals);
+    if (w->fused) {
+        mpb_msa* m = w->h->msa;
+        LAUNCH(ctx, k_walk_round, 1, COMPACT_THREADS, 0, w->n_win, w->k, w->dnum, w->degeneracy, r, w->tracks, w->ntracks,
+               w->cover, w->counts, w->stage, w->n_emit, w->trace, w->cands, w->n_cand, w->live_dev, w->totals,
+               w->h->win_pos, w->h->nw, w->fmask, w->rmask, MPB_COLP_ONES(m), w->plans, w->err, m->err);
+    } else {
+        LAUNCH(ctx, k_walk_advance, (unsigned)((2 * w->n_win + 63) / 64), 64, 0, w->n_win, w->k, w->dnum, w->degeneracy, r,
+               w->tracks, w->ntracks, w->cover, w->counts, w->stage, w->n_emit, w->trace, w->err);
+        LAUNCH(ctx, k_walk_compact, 1, COMPACT_THREADS, 0, 2 * w->n_win, w->k, r, w->tracks, w->stage, w->n_emit, w->cands,
+               w->n_cand, w->live_dev, w->totals);
+    }
     CK(cudaMemcpyAsync(&w->live_host[r], &w->live_dev[r], 4, cudaMemcpyDeviceToHost, ctx->stream));
     w->rounds_enqueued = r + 1;
     return 0;
@@ -226,7 +274,7 @@ extern "C" int mpb_walk_dev_scan(mpb_walk_dev* w) {
     mpb_ctx* ctx = w->h->msa->ctx;
     CK(cudaSetDevice(ctx->device));
     int rc = mpb_cscan_launch(w->h, w->fmask, w->rmask, w->cands, w->n_cand, w->max_cands, w->plans, w->counts, 1, nullptr,
-                              nullptr);
+                              nullptr, w->fused ? 1 : 0);
     if (rc || !w->peer) return rc;
     return mpb_peer_allreduce_launch(w->peer, w->counts, w->n_cand, 4, w->err);
 }
