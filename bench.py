@@ -33,8 +33,8 @@ PARAMS = dict(primer_length=K, coverage=0.8, number_of_dege_bases=DNUM, score_of
 BYTES_PER_EVAL = K / 2 + 0.25      # one k-column window in 4-bit cells + 2 result bits
 BYTES_PER_KMER = K / 2             # window passes: one k-column window in 4-bit cells per (window, sequence)
 KERNELS = ("k_prefilter", "k_prefilter_sums", "k_hist", "k_hist_summary", "k_hist_match", "k_cscan", "k_cscan_plan",
-           "k_cscan_special", "k_walk_advance", "k_walk_compact", "k_walk_seed", "k_tm", "k_dimer_pairs",
-           "k_dimer_expand", "k_dimer_ends")
+           "k_cscan_special", "k_walk_round", "k_walk_advance", "k_walk_compact", "k_walk_seed", "k_peer_allreduce", "k_tm",
+           "k_tm_sets", "k_dimer_pairs", "k_dimer_expand", "k_dimer_ends")
 
 
 def parse_args():
