@@ -288,36 +288,30 @@ class NN_degenerate(object):
     # -- entropy (core:602-614) ----------------------------------------------------------------------------
     def _exception_records(self, hist) -> np.ndarray:
         """gap rows that hold IUPAC cells are not in the device table (their raw k-mer needs 4 bits per cell): one record
-        (first order, count, window, 32 raw cells) per such (window, local sequence), cut from the host copy"""
+        (first order, count, window, raw cells 0..14, raw cells 15..) per such (window, local sequence), cut from the
+        host copy; the k 4-bit cells travel folded into two integers"""
         k = self.primer_length
         exc_w, exc_s = self._exceptions(hist)
-        rec = np.zeros((len(exc_w), 3 + 32), np.int64)
+        rec = np.zeros((len(exc_w), 5), np.int64)
         if len(exc_w):
             exc_pos = np.asarray(hist.win_pos)[exc_w]
             cells, got = _lib.window_cells(self._packed4, self.lens, self.n_col, k, exc_s, exc_pos)
             if (got < k).any():
                 raise ValueError("a sequence is too short to supply a %d-mer at window %d"
                                  % (k, int(exc_pos[np.argmax(got < k)])))
+            cells = cells.astype(np.int64)
             rec[:, 0] = (self.row0 + exc_s.astype(np.int64)) << 16
             rec[:, 1] = 1
             rec[:, 2] = exc_w
-            rec[:, 3:] = cells
+            for j in range(k):
+                rec[:, 3 if j < 15 else 4] |= cells[:, j] << (4 * (j if j < 15 else j - 15))
         return rec
 
     def _group_exception_records(self, rec) -> dict:
         """{window: [(first order, count)]}: the records grouped by (window, raw k-mer)"""
-        k = self.primer_length
         cache = {}
         if len(rec):
-            # the k 4-bit cells are folded into two integers, rows sorted, runs reduced
-            cells = rec[:, 3:]
-            lo = np.zeros(len(rec), np.int64)
-            hi = np.zeros(len(rec), np.int64)
-            for j in range(k):
-                if j < 15:
-                    lo |= cells[:, j] << (4 * j)
-                else:
-                    hi |= cells[:, j] << (4 * (j - 15))
+            lo, hi = rec[:, 3], rec[:, 4]                  # rows sorted by (window, raw k-mer), runs reduced
             order = np.lexsort((lo, hi, rec[:, 2]))
             w_s, lo_s, hi_s = rec[order, 2], lo[order], hi[order]
             new_run = np.ones(len(rec), bool)
@@ -539,6 +533,8 @@ class NN_degenerate(object):
         lap("finish")
         return out
 
+    EXC_INLINE = 2048          # exception records carried by the counter gather of a sharded batch (80 KB per rank)
+
     def _exchange(self, hist, positions, owner):
         """Sequence-sharded run: every per-window quantity is a sum over sequences.  Gap counters are
         summed; the haplotype entries of every window travel to the window's OWNER (one all-to-all), which merges
@@ -557,18 +553,23 @@ class NN_degenerate(object):
             tick[0] = now
 
         gap_local, iupac_local, n_ent = hist.counts()
-        # collective 1: per-window counters of every shard (+ how many gap rows holding IUPAC cells it has: their
-        # records follow in a second, padded gather when there are any)
+        # collective 1: per-window counters of every shard and its gap rows holding IUPAC cells (5 integers per record,
+        # EXC_INLINE of them ride along; only a shard with more triggers a second, padded gather)
         exc = self._exception_records(hist)
-        head = np.concatenate([gap_local, iupac_local, n_ent, [len(exc)]]).astype(np.int64)
+        inline = np.zeros((self.EXC_INLINE, 5), np.int64)
+        inline[:min(len(exc), self.EXC_INLINE)] = exc[:self.EXC_INLINE]
+        head = np.concatenate([gap_local, iupac_local, n_ent, [len(exc)], inline.reshape(-1)]).astype(np.int64)
         heads_flat = comm.allgather_fixed(head)
         heads = heads_flat[:, :3 * nw].reshape(world, 3, nw)
         n_exc = heads_flat[:, 3 * nw]
-        if int(n_exc.max()) > 0:
-            pad = np.zeros((int(n_exc.max()), 35), np.int64)
-            pad[:len(exc)] = exc
+        exc_in = heads_flat[:, 3 * nw + 1:].reshape(world, self.EXC_INLINE, 5)
+        parts = [exc_in[r, :min(int(n_exc[r]), self.EXC_INLINE)] for r in range(world)]
+        if int(n_exc.max()) > self.EXC_INLINE:
+            pad = np.zeros((int(n_exc.max()) - self.EXC_INLINE, 5), np.int64)
+            pad[:max(0, len(exc) - self.EXC_INLINE)] = exc[self.EXC_INLINE:]
             exc_all = comm.allgather_fixed(pad)
-            exc = np.concatenate([exc_all[r, :int(n_exc[r])] for r in range(world)])
+            parts += [exc_all[r, :max(0, int(n_exc[r]) - self.EXC_INLINE)] for r in range(world)]
+        exc = np.concatenate(parts) if parts else exc
         # only a window's owner needs them (entropy of its window, exact replay): the others drop them unsorted
         exc = exc[owner[exc[:, 2]] == rank] if len(exc) else exc
         hist._iupac_groups = self._group_exception_records(exc)
@@ -609,10 +610,12 @@ class NN_degenerate(object):
                     own.merge_segments(seg, rk, rc, rf)
                     own.add_counts(gap_n[mine], iupac_gap[mine])
                     st_own = own.summary()
-                    for j, wi in enumerate(mine.tolist()):      # gap rows holding IUPAC cells are not table entries
-                        for _, c in hist._iupac_groups.get(wi, ()):
-                            st_own["ent"][j, 2] += c
-                            st_own["ent"][j, 3] += c * math.log2(c)
+                    if hist._iupac_groups:                      # gap rows holding IUPAC cells are not table entries
+                        slot = {int(wi): j for j, wi in enumerate(mine.tolist())}
+                        gj = np.array([slot[w] for w, groups in hist._iupac_groups.items() for _ in groups], np.int64)
+                        gc_f = np.array([c for groups in hist._iupac_groups.values() for _, c in groups], np.float64)
+                        st_own["ent"][:, 2] += np.bincount(gj, weights=gc_f, minlength=len(mine))
+                        st_own["ent"][:, 3] += np.bincount(gj, weights=gc_f * np.log2(gc_f), minlength=len(mine))
                     c0 = 1
                     for name, w, dt in fields:
                         rec[:len(mine), c0:c0 + w] = np.ascontiguousarray(st_own[name]).reshape(len(mine), w).view(np.int64)

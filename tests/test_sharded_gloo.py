@@ -102,3 +102,19 @@ def test_window_owners_threads(name, world):
         assert (start, stop) == (case["start"], case["stop"])
         assert not bad, (rank, bad[:3])
         assert n_acc > 0
+
+
+def test_exception_records_beyond_the_inline_room(monkeypatch):
+    """gap rows holding IUPAC cells travel with the counter gather; a shard with more of them than the inline room
+    triggers the second, padded gather — same rows either way"""
+    from multiprime_b200 import core
+    from tests import fake_device
+    from tests.loopback_comm import run_shards
+    from tests.test_gpu_sharded import _shard_rows
+    monkeypatch.setattr(core.NN_degenerate, "EXC_INLINE", 1)
+    world, name = 3, "synth_iupac"
+    res = run_shards(world, lambda rank, comm: _shard_rows(name, rank, world, comm, _backend=fake_device))
+    case = load_case(name)
+    for rank, (start, stop, bad, n_acc) in enumerate(res):
+        assert (start, stop) == (case["start"], case["stop"])
+        assert not bad, (rank, bad[:3])
