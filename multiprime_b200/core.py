@@ -20,7 +20,7 @@ import numpy as np
 
 from . import _lib
 from .comm import NoComm
-from .iupac import BASES, CODE_CHARS, CHAR_CODE, allow_masks, expand_keys, expand_strings, primer_string, rc_sets
+from .iupac import BASES, CODE_CHARS, CHAR_CODE, allow_masks, expand_array, expand_keys, expand_strings, primer_string, rc_sets
 
 TSV_HEADER = ["Position", "Entropy of cover (bit)", "Entropy of total (bit)", "Optimal_primer",
               "primer_degenerate_number", "nonsense_primer_number", "Optimal_coverage", "Mis-F-coverage",
@@ -690,11 +690,8 @@ class NN_degenerate(object):
                 vals = comm.allreduce_sum(vals.view(np.int64)).view(np.float64)
             replay = {wi: (float(vals[j, 0]), float(vals[j, 1])) for j, wi in enumerate(need)}
         out = []
-        for wi in cand:
-            if exact[wi]:
-                c_bit, t_bit = replay[wi]
-            else:
-                c_bit, t_bit = round(float(c_raw[wi]), 2), round(float(t_raw[wi]), 2)
+        for wi, c_x, t_x, ex in zip(cand, c_raw[cand].tolist(), t_raw[cand].tolist(), exact[cand].tolist()):
+            c_bit, t_bit = replay[wi] if ex else (round(c_x, 2), round(t_x, 2))
             if not t_bit > thr:                                               # core:723
                 out.append((wi, (c_bit, t_bit)))
         return out
@@ -774,16 +771,19 @@ class NN_degenerate(object):
         trace_str = None
         if res["trace"] is not None:
             trace_str = lut[res["trace"][:int(res["trace_off"][n]), :k]].view("S%d" % k).ravel().astype(str).tolist()
+        # core:846: expansions that are not keys of `cover`; the defaultdict look-ups of the seeds (core:787-835) added
+        # their strings as keys, observed or not: a seed nobody carries that the final primer matches is one key more
+        seeds = np.asarray(res["seeds"])[:, :, :k]
+        matched = ((sets_arr[:, None, :k] >> seeds) & 1).all(axis=2)                     # [window, track]
+        live = np.arange(2)[None, :] < np.asarray(res["ntracks"])[:, None]
+        ghost = (matched & live & (np.asarray(res["seed_cover"]) == 0)).sum(axis=1)
+        nonsense_all = (np.asarray(deg, np.int64) - np.asarray(distinct, np.int64) - ghost).tolist()
+        strings = lut[sets_arr[:, :k]].view("S%d" % k).ravel().astype(str).tolist()     # primer_string() of every row
         out = []
         for i in range(n):
             wi, p, c_bit, t_bit, cover_number, _ = keep[i]
             sets = sets_list[i]
-            # core:846: expansions that are not keys of `cover`; the defaultdict look-ups of the seeds (core:787-835)
-            # added their strings as keys, observed or not
-            nonsense = int(deg[i]) - int(distinct[i])
-            for ti in range(int(res["ntracks"][i])):
-                if res["seed_cover"][i, ti] == 0 and all((sets[j] >> int(res["seeds"][i, ti, j])) & 1 for j in range(k)):
-                    nonsense -= 1
+            nonsense = nonsense_all[i]
             if dimer[i]:
                 continue                                                  # core:749-751
             fl = int(flags[i])
@@ -795,7 +795,7 @@ class NN_degenerate(object):
             if fl & 4:
                 notes.append("hairpin")
             init, fm, rm = (int(x) for x in res["counts"][i, :3])
-            row = [p, c_bit, t_bit, primer_string(sets), int(ndeg[i]), nonsense, int(perfect[i]), init + fm,
+            row = [p, c_bit, t_bit, strings[i], int(ndeg[i]), nonsense, int(perfect[i]), init + fm,
                    init + rm, float(tm_avg[i]), float(gc[i]) if not notes else "|".join(notes)]
             rec = {"row": row}
             if trace_str is not None:
@@ -816,7 +816,7 @@ class NN_degenerate(object):
         for i in np.nonzero(flags & (64 | 128))[0].tolist():      # a mean on a rounding tie: exact rational replay
             sets = sets_arr[i, :k].tolist()
             if flags[i] & 64:
-                raw = self.ctx.tm(np.asarray(expand_keys(sets), np.uint8).reshape(-1, k), TM_CONSTS)
+                raw = self.ctx.tm(expand_array(sets), TM_CONSTS)
                 tm_avg[i] = round(exact_mean([round(float(x), 2) for x in raw]), 2)
             if flags[i] & 128:
                 gc[i] = gc_content(sets)
@@ -965,6 +965,11 @@ ALL_MERGED = _AllMerged()
 def exact_mean(vals) -> float:
     """statistics.mean of floats (exact rational mean, correctly rounded once) without Fractions: every value is
     scaled by 2^60 exactly (holds for 2^-8 <= |x| < 2^11, i.e. any Tm / GC fraction; else fall back)"""
+    arr = np.asarray(vals, np.float64)
+    mag = np.abs(arr)
+    if len(arr) and bool(((mag >= 1.0) & (mag < 1024.0)).all()):
+        # 1 <= |x| < 2^10: a multiple of 2^-52 below 2^10, so x * 2^52 is an integer below 2^62 (exact in int64)
+        return sum((arr * 4503599627370496.0).astype(np.int64).tolist()) / (len(arr) << 52)
     if all((x == 0.0) or (0.00390625 <= abs(x) < 2048.0) for x in vals):
         total = 0
         for x in vals:

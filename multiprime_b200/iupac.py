@@ -61,6 +61,21 @@ def expand_keys(sets) -> list[tuple]:
     return list(product(*[ORDER[s] for s in sets]))
 
 
+def expand_array(sets):
+    """expand_keys as a (number of expansions, len(sets)) uint8 array, same order (leftmost position slowest)"""
+    import numpy as np
+    opts = [np.array(ORDER[s], np.uint8) for s in sets]
+    n = 1
+    for o in opts:
+        n *= len(o)
+    out = np.empty((n, len(sets)), np.uint8)
+    rep = n
+    for j, o in enumerate(opts):          # column j: every option repeated `rep` times, the pattern tiled
+        rep //= len(o)
+        out[:, j] = np.tile(np.repeat(o, rep), n // (rep * len(o)))
+    return out
+
+
 def expand_strings(sets) -> list[str]:
     """like expand_keys, as strings; a gap cell (0) stays '-'"""
     return ["".join(t) for t in product(*[[BASES[b] for b in ORDER[s]] if s else ["-"] for s in sets])]
