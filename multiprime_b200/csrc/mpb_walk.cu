@@ -108,10 +108,6 @@ extern "C" int mpb_walk(int k, int v, int dnum, int degeneracy, int32_t n_win, c
 
 namespace {
 const int FOLD[16] = {0, 1, 1, 2, 1, 2, 2, 3, 1, 2, 2, 3, 2, 3, 3, 4};
-// expansion order of each base set (core:105-107): ORD[set] lists base indices A,C,G,T = 0..3
-const int8_t ORD[16][4] = {{-1, -1, -1, -1}, {0, -1, -1, -1}, {1, -1, -1, -1}, {0, 1, -1, -1},  {2, -1, -1, -1}, {0, 2, -1, -1},
-                           {2, 1, -1, -1},   {2, 0, 1, -1},   {3, -1, -1, -1}, {0, 3, -1, -1},  {1, 3, -1, -1},  {0, 3, 1, -1},
-                           {2, 3, -1, -1},   {2, 0, 3, -1},   {2, 3, 1, -1},   {0, 3, 2, 1}};
 int degeneracy_of(const uint8_t* sets, int k, int* ndeg) {
     long long d = 1;
     int n = 0;

@@ -15,11 +15,7 @@ import numpy as np
 
 
 class _Shared:
-    _serial = [0]
-
     def __init__(self, world):
-        _Shared._serial[0] += 1
-        self.serial = _Shared._serial[0]     # names the group in caches that outlive it (ids are reused)
         self.world = world
         self.barrier = threading.Barrier(world)
         self.slots = [None] * world
