@@ -82,17 +82,11 @@ extern "C" int mpb_ctx_create(int device, mpb_ctx** out) {
     c->pending_units = 0;
     c->copy_stream = nullptr;
     c->pinned = nullptr;
-    c->ev_fork = c->ev_join = nullptr;
     if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaMallocHost(&c->pinned, MPB_CTX_PINNED_INTS * sizeof(int)) != cudaSuccess ||
-        cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        cudaMallocHost(&c->pinned, MPB_CTX_PINNED_INTS * sizeof(int)) != cudaSuccess) {
         if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
-        if (c->pinned) cudaFreeHost(c->pinned);
-        if (c->ev_fork) cudaEventDestroy(c->ev_fork);
-        if (c->ev_join) cudaEventDestroy(c->ev_join);
         delete c;
-        return fail(MPB_ECUDA, "copy stream / pinned scratch / events");
+        return fail(MPB_ECUDA, "copy stream / pinned scratch");
     }
     *out = c;
     return 0;
@@ -105,8 +99,6 @@ extern "C" void mpb_ctx_destroy(mpb_ctx* ctx) {
     }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
-    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
-    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     delete ctx;
 }
 extern "C" int mpb_ctx_set_stream(mpb_ctx* ctx, void* s) {

@@ -335,35 +335,26 @@ int mpb_cscan_launch(mpb_hist* h, uint32_t fmask, uint32_t rmask, const mpb_cand
     unsigned spec_gy = (unsigned)((h->spec_cap + 256 * 4 - 1) / (256 * 4));
     if (spec_gy < 1) spec_gy = 1;
     if (spec_gy > 16) spec_gy = 16;
-    const dim3 sgrid((unsigned)(max_cands < 4096 ? max_cands : 4096), spec_gy);
-    if (bits_slot_d) {  // the column kernel stores whole words of the bit vectors, the special pass ORs its rows in: in order
+    if (bits_slot_d) {
         if (h->v <= 3)
             MPB_LAUNCH_NAMED(ctx, "k_cscan", (k_cscan<3, true>), dim3(gx, gy), CSCAN_THREADS, 0, m->colp, (long long)m->nwords, h->v, plans_d,
                    n_cand_d, h->spec_bits, h->gap_bits, counts_d, bits_slot_d, bits_d, out_words);
         else
             MPB_LAUNCH_NAMED(ctx, "k_cscan", (k_cscan<5, true>), dim3(gx, gy), CSCAN_THREADS, 0, m->colp, (long long)m->nwords, h->v, plans_d,
                    n_cand_d, h->spec_bits, h->gap_bits, counts_d, bits_slot_d, bits_d, out_words);
-        MPB_LAUNCH_NAMED(ctx, "k_cscan_special", k_cscan_special<true>, sgrid, 256, 0, cands_d, n_cand_d, h->nw, h->k, h->v, fmask,
-                         rmask, h->spec_win, h->spec_row, h->spec_n, (long long)h->spec_cap, counts_d, bits_slot_d, bits_d, out_words,
-                         m->err);
+        MPB_LAUNCH_NAMED(ctx, "k_cscan_special", k_cscan_special<true>, dim3((unsigned)(max_cands < 4096 ? max_cands : 4096), spec_gy), 256, 0, cands_d, n_cand_d, h->nw,
+               h->k, h->v, fmask, rmask, h->spec_win, h->spec_row, h->spec_n, (long long)h->spec_cap, counts_d, bits_slot_d,
+               bits_d, out_words, m->err);
     } else {
-        // Counts only (the walk's rounds): the special rows (a fraction of a percent) are a latency-bound pass of their own
-        // that shares nothing with the column kernel but the counters (atomics) — it runs beside it on the context's side
-        // stream, forked here and joined below.
-        cudaStream_t side = ctx->copy_stream;
-        CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
-        CK(cudaStreamWaitEvent(side, ctx->ev_fork, 0));
-        MPB_LAUNCH_ON(ctx, side, "k_cscan_special", k_cscan_special<false>, sgrid, 256, 0, cands_d, n_cand_d, h->nw, h->k, h->v, fmask,
-                      rmask, h->spec_win, h->spec_row, h->spec_n, (long long)h->spec_cap, counts_d, (const int32_t*)nullptr,
-                      (uint32_t*)nullptr, out_words, m->err);
         if (h->v <= 3)
             MPB_LAUNCH_NAMED(ctx, "k_cscan", (k_cscan<3, false>), dim3(gx, gy), CSCAN_THREADS, 0, m->colp, (long long)m->nwords, h->v, plans_d,
                    n_cand_d, h->spec_bits, h->gap_bits, counts_d, (const int32_t*)nullptr, (uint32_t*)nullptr, out_words);
         else
             MPB_LAUNCH_NAMED(ctx, "k_cscan", (k_cscan<5, false>), dim3(gx, gy), CSCAN_THREADS, 0, m->colp, (long long)m->nwords, h->v, plans_d,
                    n_cand_d, h->spec_bits, h->gap_bits, counts_d, (const int32_t*)nullptr, (uint32_t*)nullptr, out_words);
-        CK(cudaEventRecord(ctx->ev_join, side));
-        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+        MPB_LAUNCH_NAMED(ctx, "k_cscan_special", k_cscan_special<false>, dim3((unsigned)(max_cands < 4096 ? max_cands : 4096), spec_gy), 256, 0, cands_d, n_cand_d, h->nw,
+               h->k, h->v, fmask, rmask, h->spec_win, h->spec_row, h->spec_n, (long long)h->spec_cap, counts_d,
+               (const int32_t*)nullptr, (uint32_t*)nullptr, out_words, m->err);
     }
     return 0;
 }

@@ -31,9 +31,7 @@ struct ProfRec {
 struct mpb_ctx {
     int device;
     cudaStream_t stream;
-    cudaStream_t copy_stream;  // H2D chunks of mpb_msa_upload overlap the plane build on `stream`; also the side stream of
-                               // the scan's special-row pass (forked from / joined into `stream` with the two events)
-    cudaEvent_t ev_fork, ev_join;
+    cudaStream_t copy_stream;  // H2D chunks of mpb_msa_upload overlap the plane build on `stream`
     int* pinned;               // small pinned scratch (MPB_CTX_PINNED_INTS ints): device -> host flags without a sync
     int64_t launches;
     int sm_count;
@@ -65,24 +63,6 @@ static inline int mpb_ctx_sms(mpb_ctx* c) { return c->sm_count; }
         (ctx)->pending_units = 0;                                                 \
     } while (0)
 #define MPB_LAUNCH(ctx, kern, grid, block, smem, ...) MPB_LAUNCH_NAMED(ctx, #kern, kern, grid, block, smem, __VA_ARGS__)
-// the same on another stream of the context (the caller orders it against `stream` with events)
-#define MPB_LAUNCH_ON(ctx, st, name, kern, grid, block, smem, ...)                \
-    do {                                                                          \
-        ProfRec pr__ = {name, nullptr, nullptr, (ctx)->pending_units};            \
-        if ((ctx)->profile) {                                                     \
-            MPB_CK(cudaEventCreate(&pr__.e0));                                    \
-            MPB_CK(cudaEventCreate(&pr__.e1));                                    \
-            MPB_CK(cudaEventRecord(pr__.e0, (st)));                               \
-        }                                                                         \
-        kern<<<grid, block, smem, (st)>>>(__VA_ARGS__);                           \
-        (ctx)->launches++;                                                        \
-        MPB_CK(cudaGetLastError());                                               \
-        if ((ctx)->profile) {                                                     \
-            MPB_CK(cudaEventRecord(pr__.e1, (st)));                               \
-            (ctx)->recs.push_back(pr__);                                          \
-        }                                                                         \
-        (ctx)->pending_units = 0;                                                 \
-    } while (0)
 
 // ---- handles ---------------------------------------------------------------------------------------------------
 struct mpb_msa {
