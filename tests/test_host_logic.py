@@ -81,3 +81,75 @@ def test_primer_props_host_part(tmp_path):
                 assert bool(flags[i] & 1) == (not 0.4 <= gc[i] <= 0.6)
             assert bool(flags[i] & 2) == core.has_repeat(row)
             assert bool(flags[i] & 4) == core.has_hairpin(row, 4)
+
+
+def test_expand_array_and_exact_mean_match_their_definitions():
+    """the numpy forms used on the hot path against the plain ones: itertools.product order, statistics.mean exactness"""
+    import random
+    from statistics import mean
+    import numpy as np
+    from multiprime_b200.core import exact_mean
+    from multiprime_b200.iupac import expand_array, expand_keys
+    rnd = random.Random(11)
+    for _ in range(100):
+        sets = [rnd.choice([1, 2, 4, 8, 1, 2, 4, 8, 5, 10, 3, 12, 6, 9, 11, 14, 7, 13, 15]) for _ in range(rnd.randint(3, 10))]
+        want = np.asarray(expand_keys(sets), np.uint8).reshape(-1, len(sets))
+        got = expand_array(sets)
+        assert got.shape == want.shape and (got == want).all(), sets
+    for _ in range(200):
+        vals = [round(rnd.uniform(1.5, 99.0), 2) for _ in range(rnd.randint(1, 300))]
+        assert exact_mean(vals) == mean(vals)
+        vals = [round(rnd.uniform(0.01, 0.99), 2) for _ in range(rnd.randint(1, 60))]       # below 1: the 2^60 path
+        assert exact_mean(vals) == mean(vals)
+        vals = [round(rnd.uniform(-50.0, 2000.0), 2) for _ in range(rnd.randint(1, 60))]    # mixed: falls back as needed
+        assert exact_mean(vals) == mean(vals)
+
+
+def test_peer_group_is_all_or_nothing(monkeypatch):
+    """_lib.Peer.of: when one rank cannot create its buffer, every rank ends up without a peer group (the walk then
+    all-reduces through the communicator) — decided with the communicator's own collectives, no device involved"""
+    import threading
+    import numpy as np
+    from multiprime_b200 import _lib
+    from tests.loopback_comm import _Shared, ThreadComm
+
+    class FakePeer(_lib.Peer):
+        closed = []
+
+        def __init__(self, ctx, rank, world, cap_elems=1 << 18):
+            if rank == 1:
+                raise _lib.MpbError(-3, "no memory for the peer buffer")
+            self.ctx, self.rank, self.world, self.cap, self.h = ctx, rank, world, cap_elems, object()
+
+        def handle(self):
+            return np.full(_lib.PEER_HANDLE_BYTES // 8, self.rank + 1, np.int64)
+
+        def connect(self, handles):
+            raise AssertionError("nobody connects when a rank has no buffer")
+
+        def close(self):
+            FakePeer.closed.append(self.rank)
+            self.h = None
+
+    world, shared, out = 3, _Shared(3), [None] * 3
+
+    class Ctx:
+        pass
+
+    def body(rank):
+        try:
+            comm = ThreadComm.__new__(ThreadComm)
+            comm.sh, comm.rank, comm.world, comm.device = shared, rank, world, None
+            comm.peer_key = ("test", 1)
+            out[rank] = FakePeer.of(Ctx(), comm)
+        except BaseException as exc:          # a dead shard would leave the others at a barrier
+            out[rank] = exc
+            shared.barrier.abort()
+
+    threads = [threading.Thread(target=body, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert out == [None, None, None]
+    assert sorted(FakePeer.closed) == [0, 2]
