@@ -46,7 +46,10 @@ def parse_args():
     ap.add_argument("--n-seq", type=int, default=1_000_000, help="sequences per GPU")
     ap.add_argument("--n-col", type=int, default=600)
     ap.add_argument("--cpu-sample-seqs", type=int, default=20000)
-    ap.add_argument("--cpu-sample-windows", type=int, default=32)
+    ap.add_argument("--cpu-sample-windows", type=int, default=256,
+                    help="windows of the single-core cpu_baseline leg (about 13 s of CPU work for the port)")
+    ap.add_argument("--ref-sample-windows", type=int, default=32,
+                    help="windows per step of --impl reference (raised to two per usable core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--parity-seqs", type=int, default=1 << 18, help="rows of the untimed sharded-parity check (N>1)")
     ap.add_argument("--workload", default="scan", choices=["scan", "dimer"],
@@ -234,7 +237,7 @@ def run_reference(args):
         return
     cores = host_cores()
     live = os.path.exists(REF_CORE)
-    n_windows = max(args.cpu_sample_windows, 2 * cores)            # keep every core busy
+    n_windows = max(args.ref_sample_windows, 2 * cores)            # keep every core busy
     procs = min(cores, n_windows)
     vals = []
     for i in range(args.warmup + args.steps):
